@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- encode throughput of the fractal encoder hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--size S] [--block B] [--pattern structured|noise]
+
+One "step" = one full encode (pool build + range x domain search + code solve) of one
+synthetic greyscale image with the whole domain pool as the search window
+(widthKernel = domain blocks per width), BASELINE.json configs[2]/[3]:
+    N = 1 : 4096 x 4096, B = 8 (the reference's default block size), 1 B200
+    N > 1 : 8192 x 8192, B = 8, range-block rows sharded over N B200s, NCCL image broadcast
+`value` is range x candidate evaluations per second of the whole job (inputs resident in
+HBM); `mpixel_per_s` is the same time expressed as image pixels.  `e2e` is the same metric
+through the C ABI with pinned HOST buffers (H2D of the image and D2H of the codes inside
+the timed region).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=0, help="image edge; default 4096 (N=1) / 8192 (N>1)")
+    ap.add_argument("--block", type=int, default=8)
+    ap.add_argument("--pattern", default="structured", choices=["structured", "noise"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "direct", "umma"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def workload(args):
+    size = args.size or (4096 if args.gpus == 1 else 8192)
+    B = args.block
+    wk = 2 * size // B - 3
+    NR = (size // B) ** 2
+    ND = wk * wk
+    return size, B, wk, NR, ND
+
+
+def make_image(args, size):
+    import fractal_image_compression_b200 as fic
+
+    gen = fic.synth.structured if args.pattern == "structured" else fic.synth.noise
+    return gen(size, size, 1)
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference (the Java encoder cannot run: no JVM here)
+# ----------------------------------------------------------------------------------------
+
+def cpu_sample(plane, B, wk, nthreads, target_s):
+    """Times the oracle's range loop on the first R ranges of the workload.  The codebook
+    build is timed separately (a call with zero ranges) and subtracted, so the figure is
+    the search rate the reference would sustain over the full image."""
+    from oracle import oracle as O
+    import fractal_image_compression_b200 as fic
+
+    argb = fic.synth.grey_to_argb(plane)
+    t0 = time.perf_counter()
+    O.encode(argb, B, wk, range_begin=0, range_end=0, nthreads=1)
+    t_pool = time.perf_counter() - t0
+    R = nthreads
+    t0 = time.perf_counter()
+    O.encode(argb, B, wk, range_begin=0, range_end=R, nthreads=nthreads)
+    t_probe = max(time.perf_counter() - t0 - t_pool, 1e-3)
+    R = max(nthreads, int(R * target_s / t_probe) // nthreads * nthreads)
+    t0 = time.perf_counter()
+    O.encode(argb, B, wk, range_begin=0, range_end=R, nthreads=nthreads)
+    t = max(time.perf_counter() - t0 - t_pool, 1e-6)
+    return R, t, t_pool
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    size, B, wk, NR, ND = workload(args)
+    plane = make_image(args, size)
+    threads = os.cpu_count() or 1
+    per_step = max(1.0, min(10.0, 100.0 / max(1, args.steps + args.warmup)))
+    rates, times = [], []
+    R = 0
+    for i in range(args.warmup + args.steps):
+        R, t, t_pool = cpu_sample(plane, B, wk, threads, per_step)
+        if i >= args.warmup:
+            rates.append(R * ND / t)
+            times.append(t)
+    v = statistics.mean(rates)
+    full_s = NR * ND / v
+    line = {
+        "impl": "reference", "metric": "encode_evals_per_s", "value": v / 1e9, "unit": "Gevals/s",
+        "mpixel_per_s": size * size / full_s / 1e6,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": statistics.mean(times) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"synthetic {args.pattern} {size}x{size} grey, B={B}, widthKernel={wk} (full pool)",
+                   "ranges": NR, "domains": ND},
+        "cpu_baseline": {"value": v / 1e9, "unit": "Gevals/s", "cores": threads, "kind": "port",
+                         "sample": f"first {R} of {NR} range blocks against the full pool per step "
+                                   f"(C restatement of the reference; JVM unavailable; codebook build excluded)"},
+        "e2e": {"value": v / 1e9, "unit": "Gevals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import fractal_image_compression_b200 as fic
+    from fractal_image_compression_b200.dist import ShardedEncoder
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    size, B, wk, NR, ND = workload(args)
+    plane = make_image(args, size)
+    evals = float(NR) * float(ND)
+
+    handle = fic.Handle(local)
+    handle.set_engine({"auto": fic.FIC_ENGINE_AUTO, "direct": fic.FIC_ENGINE_DIRECT, "umma": fic.FIC_ENGINE_UMMA}[args.engine])
+    stream = torch.cuda.current_stream(dev)
+    handle.set_stream(stream.cuda_stream)
+    enc = ShardedEncoder(handle=handle) if world > 1 else None
+
+    d_planes = torch.from_numpy(plane).to(dev).reshape(1, size, size).contiguous() if rank == 0 else None
+    d_info = torch.empty((NR, 3), dtype=torch.float32, device=dev)
+    d_q = torch.empty((NR, 3), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # pinned host buffers for the e2e leg
+    h_argb = torch.from_numpy(fic.synth.grey_to_argb(plane)).pin_memory() if rank == 0 else None
+    h_plane = torch.from_numpy(plane).pin_memory() if rank == 0 else None
+    h_info = torch.empty((NR, 3), dtype=torch.float32).pin_memory()
+    h_q = torch.empty((NR, 3), dtype=torch.int32).pin_memory()
+
+    def step_device():
+        if world == 1:
+            handle.encode_planes_dev(d_planes.data_ptr(), False, size, size, B, wk, 0, NR, d_info.data_ptr(), d_q.data_ptr())
+            return None
+        return enc.encode(d_planes, False, size, size, B, wk, device=dev)
+
+    def step_e2e():
+        if world == 1:
+            # the call a user of the library makes: host ARGB in, host codes out
+            handle.set_stream(None)
+            handle.encode(h_argb.numpy(), B, wk, rgb=False, info=h_info.numpy(), q=h_q.numpy())
+            handle.set_stream(stream.cuda_stream)
+            return
+        pl = h_plane.to(dev, non_blocking=True).reshape(1, size, size) if rank == 0 else None
+        out = enc.encode(pl, False, size, size, B, wk, device=dev)
+        if rank == 0:
+            h_info.copy_(out[0], non_blocking=True)
+            h_q.copy_(out[1], non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, device_events):
+        total_ms = 0.0
+        kernel_ms, launches, search_ms, pool_ms = [], 0, [], []
+        for _ in range(steps):
+            flush.fill_(1)  # evict L2 between timed iterations (not timed)
+            barrier()
+            if device_events:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                total_ms += e0.elapsed_time(e1)
+            else:
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize(dev)
+                total_ms += (time.perf_counter() - t0) * 1e3
+            t = handle.timings()
+            kernel_ms.append(t.kernel_ms)
+            search_ms.append(t.search_ms)
+            pool_ms.append(t.pool_ms)
+            launches += t.launches
+            barrier()
+        return total_ms, kernel_ms, search_ms, pool_ms, launches
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    total_ms, kernel_ms, search_ms, pool_ms, launches = timed(step_device, args.steps, True)
+    clocks = sampler.stop()
+    t = handle.timings()
+    engine = t.engine
+    step_evals = t.search_evals  # this rank's evaluations per step
+
+    for _ in range(2):
+        step_e2e()
+    e2e_ms, _, _, _, e2e_launches = timed(step_e2e, args.steps, False)
+
+    if world > 1:
+        agg = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = agg.tolist()
+        nl = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(nl)
+        launches = int(nl.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = total_ms / args.steps
+    value = evals / (ms_per_step * 1e-3)
+    pk, pk_kind = peaks()
+    k_ms = statistics.mean(kernel_ms)
+    int8_peak = 2.0 * pk["bf16_tflops"]  # TOP/s: the i8 pipe issues 2x the bf16 rate
+    ops = 2.0 * B * B * step_evals       # algorithmic int8 ops of one launch (2*B^2 per eval)
+    achieved = ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": "k_umma_search" if engine == fic.FIC_ENGINE_UMMA else "k_search_direct_grey",
+        "achieved": achieved, "peak": int8_peak, "unit": "TOP/s", "frac": achieved / int8_peak,
+        "peak_source": f"2 x bf16_tflops ({pk['bf16_tflops']}) of {pk_kind} (MEASURED_PEAKS.json has no int8 entry; "
+                       f"nominal dense int8 is 4500)",
+        "frac_of_nominal_4500": achieved / 4500.0, "kernel_ms": k_ms, "search_ms": statistics.mean(search_ms),
+        "pool_ms": statistics.mean(pool_ms), "traffic": None,
+    }
+    line = {
+        "metric": "encode_evals_per_s", "value": value / 1e9, "unit": "Gevals/s",
+        "mpixel_per_s": size * size / (ms_per_step * 1e-3) / 1e6,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": f"synthetic {args.pattern} {size}x{size} grey, B={B}, widthKernel={wk} (full pool)",
+                   "ranges": NR, "domains": ND, "engine": "tcgen05" if engine == fic.FIC_ENGINE_UMMA else "direct",
+                   "parallelism": f"range-rows x{world}", "l2": "flushed between timed iterations (256 MiB write)"},
+        "clocks": clocks,
+        "e2e": {"value": evals / (e2e_ms / args.steps * 1e-3) / 1e9, "unit": "Gevals/s",
+                "mpixel_per_s": size * size / (e2e_ms / args.steps * 1e-3) / 1e6,
+                "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": size * size * (4 if world == 1 else 1), "d2h_bytes_per_step": NR * 24},
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        R, tcpu, t_pool = cpu_sample(plane, B, wk, 1, args.cpu_seconds)
+        v = R * ND / tcpu
+        line["cpu_baseline"] = {
+            "value": v / 1e9, "unit": "Gevals/s", "cores": 1, "kind": "port",
+            "host_cores": os.cpu_count(),
+            "sample": f"first {R} of {NR} range blocks against the full pool, single thread like the reference "
+                      f"(C restatement; JVM unavailable; codebook build {t_pool:.2f}s excluded)",
+            "full_image_seconds_extrapolated": NR * ND / v,
+        }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

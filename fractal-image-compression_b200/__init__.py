@@ -1,0 +1,13 @@
+"""fractal-image-compression_b200: B200-native (sm_100a) drop-in for the encode/decode hot
+path of LariWa/Fractal-Image-Compression.  The product is the C-ABI library
+lib/libfic_b200.so (include/fic_b200.h); this package is its host-side mirror of the
+reference's codec interface plus the torch.distributed plumbing for multi-GPU encodes.
+"""
+from . import _lib, synth
+from ._lib import (FIC_ENGINE_AUTO, FIC_ENGINE_DIRECT, FIC_ENGINE_UMMA, ABI_SYMBOLS, LIB_PATH, FicError, Timings)
+from .codec import ByteSink, FractalCompression, Handle, RasterImage, stream_read, stream_write
+
+__all__ = [
+    "ABI_SYMBOLS", "ByteSink", "FIC_ENGINE_AUTO", "FIC_ENGINE_DIRECT", "FIC_ENGINE_UMMA", "FicError",
+    "FractalCompression", "Handle", "LIB_PATH", "RasterImage", "Timings", "stream_read", "stream_write", "synth",
+]

@@ -1,0 +1,278 @@
+"""Host-side mirror of the reference's codec interface on top of the C ABI.
+
+The reference is Java (src/bvk_ss19/FractalCompression.java = FC, RasterImage.java = RI)
+and no JVM exists in the build environment, so the host side that stays in Java
+(image container, grey/RGB dispatch, stream writer, decoder entry) is mirrored here
+with the reference's own names and argument meaning; the hot path is the native
+library.  Nothing in this module computes codes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import io
+import struct
+
+import numpy as np
+
+from . import _lib
+from ._lib import FicError, Timings
+
+
+class RasterImage:
+    """RI:18-72: `argb` int32 0xAARRGGBB pixels in scanline order, `width`, `height`."""
+
+    GRAY = np.int32(np.uint32(0xFFA0A0A0).view(np.int32))  # RI:19
+
+    def __init__(self, width: int, height: int):
+        self.width, self.height = int(width), int(height)
+        self.argb = np.full((self.height, self.width), self.GRAY, np.int32)  # RI:31
+
+    @classmethod
+    def from_argb(cls, argb) -> "RasterImage":
+        a = np.ascontiguousarray(argb, dtype=np.int32)
+        im = cls.__new__(cls)
+        im.height, im.width = a.shape
+        im.argb = a
+        return im
+
+    @classmethod
+    def from_grey(cls, plane) -> "RasterImage":
+        v = np.ascontiguousarray(plane, dtype=np.uint8).astype(np.uint32)
+        return cls.from_argb((0xFF000000 | (v << 16) | (v << 8) | v).view(np.int32))
+
+    @classmethod
+    def from_rgb(cls, rgb) -> "RasterImage":
+        a = np.ascontiguousarray(rgb, dtype=np.uint8).astype(np.uint32)
+        return cls.from_argb((0xFF000000 | (a[..., 0] << 16) | (a[..., 1] << 8) | a[..., 2]).view(np.int32))
+
+    @classmethod
+    def from_file(cls, path: str) -> "RasterImage":
+        """RI:34-52 (JavaFX Image + getIntArgbInstance); PIL decodes the bundled images identically."""
+        from PIL import Image
+
+        return cls.from_rgb(np.asarray(Image.open(path).convert("RGB")))
+
+    def red(self) -> np.ndarray:
+        return ((self.argb.view(np.uint32) >> 16) & 0xFF).astype(np.uint8)
+
+    def rgb(self) -> np.ndarray:
+        u = self.argb.view(np.uint32)
+        return np.stack([(u >> 16) & 0xFF, (u >> 8) & 0xFF, u & 0xFF], -1).astype(np.uint8)
+
+
+class ByteSink(io.BytesIO):
+    """A DataOutputStream stand-in whose contents survive close() (FC:259 closes `out`)."""
+
+    def close(self):  # noqa: D401
+        self.closed_by_codec = True
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Handle:
+    """One libfic_b200 context (device memory, stream) on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        rc = self._L.fic_create(int(device), C.byref(h))
+        if rc:
+            raise FicError(rc, self._L.fic_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.fic_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc: int):
+        if rc:
+            raise FicError(rc, self._L.fic_last_error(self._h).decode())
+
+    def set_engine(self, engine: int):
+        self._check(self._L.fic_set_option(self._h, _lib.FIC_OPT_ENGINE, int(engine)))
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._L.fic_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        self._check(self._L.fic_sync(self._h))
+
+    def timings(self) -> Timings:
+        t = Timings()
+        self._check(self._L.fic_get_timings(self._h, C.byref(t)))
+        return t
+
+    def geometry(self, W, H, B, wk):
+        nr, nd = C.c_int64(), C.c_int64()
+        self._check(self._L.fic_geometry(W, H, B, wk, C.byref(nr), C.byref(nd)))
+        return nr.value, nd.value
+
+    def encode(self, argb: np.ndarray, B: int, wk: int, rgb: bool, range_begin: int = 0,
+               range_end: int | None = None, info: np.ndarray | None = None, q: np.ndarray | None = None):
+        """Runs fic_encode_grey / fic_encode_rgb; returns (imageInfo float32[NR][S], qcodes int32[NR][S])."""
+        a = np.ascontiguousarray(argb, dtype=np.int32)
+        H, W = a.shape
+        S = 5 if rgb else 3
+        nr = (W // B) * (H // B) if B > 0 else 0
+        if range_end is None:
+            range_end = nr
+        if info is None:
+            info = np.zeros((max(nr, 0), S), np.float32)
+        if q is None:
+            q = np.zeros((max(nr, 0), S), np.int32)
+        fn = self._L.fic_encode_rgb if rgb else self._L.fic_encode_grey
+        self._check(fn(self._h, _ptr(a), W, H, B, wk, range_begin, range_end, _ptr(info), _ptr(q)))
+        return info, q
+
+    def encode_planes_dev(self, d_planes: int, rgb: bool, W: int, H: int, B: int, wk: int, range_begin: int,
+                          range_end: int, d_info: int | None, d_q: int | None):
+        """Asynchronous device-pointer entry (fic_encode_planes_dev)."""
+        self._check(self._L.fic_encode_planes_dev(self._h, C.c_void_p(d_planes), int(rgb), W, H, B, wk,
+                                                  range_begin, range_end, C.c_void_p(d_info or 0),
+                                                  C.c_void_p(d_q or 0)))
+
+    def decode(self, q: np.ndarray, W: int, H: int, B: int, wk: int, rgb: bool, avg_error: float = 0.0,
+               max_iters: int = 50):
+        qq = np.ascontiguousarray(q, dtype=np.int32)
+        out = np.empty((H, W), np.int32)
+        avg = C.c_float(avg_error)
+        it = C.c_int(0)
+        self._check(self._L.fic_decode(self._h, int(rgb), W, H, B, wk, _ptr(qq), max_iters, _ptr(out),
+                                       C.byref(avg), C.byref(it)))
+        return out, np.float32(avg.value), it.value
+
+    def collage(self, argb: np.ndarray, info: np.ndarray, B: int, wk: int, rgb: bool):
+        """fic_collage; `info` is rewritten in place (window-local -> codebook index, FC:273)."""
+        a = np.ascontiguousarray(argb, dtype=np.int32)
+        H, W = a.shape
+        assert info.dtype == np.float32 and info.flags["C_CONTIGUOUS"]
+        out = np.empty((H, W), np.int32)
+        self._check(self._L.fic_collage(self._h, int(rgb), _ptr(a), W, H, B, wk, _ptr(info), _ptr(out)))
+        return out
+
+    def build_pool(self, argb: np.ndarray, B: int, rgb: bool):
+        a = np.ascontiguousarray(argb, dtype=np.int32)
+        H, W = a.shape
+        Cn = 3 if rgb else 1
+        nd = (2 * W // B - 3) * (2 * H // B - 3)
+        dec = np.empty((Cn, H // 2, W // 2), np.uint8)
+        s1 = np.empty((Cn, nd), np.int32)
+        s2 = np.empty((Cn, nd), np.int32)
+        self._check(self._L.fic_build_pool(self._h, _ptr(a), int(rgb), W, H, B, _ptr(dec), _ptr(s1), _ptr(s2)))
+        return dec, s1, s2
+
+
+# ---- .run stream helpers (native) ---------------------------------------------------
+
+def stream_write(q: np.ndarray, W: int, H: int, B: int, wk: int, rgb: bool) -> bytes:
+    L = _lib.load()
+    n = L.fic_stream_size(int(rgb), W, H, B)
+    buf = np.empty(n, np.uint8)
+    qq = np.ascontiguousarray(q, dtype=np.int32)
+    rc = L.fic_stream_write(int(rgb), W, H, B, wk, _ptr(qq), _ptr(buf), n)
+    if rc:
+        raise FicError(rc, "fic_stream_write rejected its arguments")
+    return buf.tobytes()
+
+
+def stream_read(stream: bytes):
+    """Returns (is_rgb, W, H, B, wk, qcodes int32[NR][S])."""
+    L = _lib.load()
+    buf = np.frombuffer(stream, np.uint8)
+    v = [C.c_int() for _ in range(5)]
+    off = C.c_size_t()
+    rc = L.fic_stream_read_header(_ptr(buf), len(buf), *[C.byref(x) for x in v], C.byref(off))
+    if rc:
+        raise FicError(rc, "malformed .run stream")
+    rgb, W, H, B, wk = [x.value for x in v]
+    S = 5 if rgb else 3
+    q = np.empty(((W // B) * (H // B), S), np.int32)
+    rc = L.fic_stream_read_codes(_ptr(buf), len(buf), _ptr(q))
+    if rc:
+        raise FicError(rc, "malformed .run stream")
+    return bool(rgb), W, H, B, wk, q
+
+
+class FractalCompression:
+    """Mirror of the reference's static codec facade (FC:12-59, FC:230-261, FC:547-553).
+
+    The mutable statics `blockgroesse`, `widthKernel` (FC:14-15) and `avgError` (FC:20) are
+    class attributes, as in the reference; the native handle is created on first use.
+    """
+
+    blockgroesse = 8
+    widthKernel = 2
+    avgError = np.float32(0.0)
+    imageInfo: np.ndarray | None = None      # FC:17
+    imageInfoRGB: np.ndarray | None = None   # FC:18
+    _handle: Handle | None = None
+    device = 0
+
+    @classmethod
+    def handle(cls) -> Handle:
+        if cls._handle is None:
+            cls._handle = Handle(cls.device)
+        return cls._handle
+
+    @classmethod
+    def getAvgError(cls):  # FC:22-24
+        return cls.avgError
+
+    @staticmethod
+    def isGreyScale(input: RasterImage) -> bool:  # FC:32-45
+        u = input.argb.view(np.uint32)
+        r, g, b = (u >> 16) & 0xFF, (u >> 8) & 0xFF, u & 0xFF
+        return bool(np.all(r == g) and np.all(g == b))
+
+    @classmethod
+    def encode(cls, input: RasterImage, out) -> RasterImage:  # FC:54-59
+        if cls.isGreyScale(input):
+            return cls.encodeGrayScale(input, out)
+        return cls.encodeRGB(input, out)
+
+    @classmethod
+    def encodeGrayScale(cls, input: RasterImage, out) -> RasterImage:  # FC:109-162
+        info, q = cls.handle().encode(input.argb, cls.blockgroesse, cls.widthKernel, rgb=False)
+        cls.imageInfo, cls._q = info, q
+        cls.writeData(out, 0, input.width, input.height)
+        return cls.getBestGeneratedCollage(input)
+
+    @classmethod
+    def encodeRGB(cls, input: RasterImage, out) -> RasterImage:  # FC:171-219
+        info, q = cls.handle().encode(input.argb, cls.blockgroesse, cls.widthKernel, rgb=True)
+        cls.imageInfoRGB, cls._q = info, q
+        cls.writeData(out, 1, input.width, input.height)
+        return cls.getBestGeneratedCollageRGB(input)
+
+    @classmethod
+    def writeData(cls, out, isRGB: int, width: int, height: int):  # FC:230-261
+        out.write(stream_write(cls._q, width, height, cls.blockgroesse, cls.widthKernel, bool(isRGB)))
+        out.close()  # FC:259
+
+    @classmethod
+    def getBestGeneratedCollage(cls, originalImage: RasterImage) -> RasterImage:  # FC:269-300
+        out = cls.handle().collage(originalImage.argb, cls.imageInfo, cls.blockgroesse, cls.widthKernel, rgb=False)
+        return RasterImage.from_argb(out)
+
+    @classmethod
+    def getBestGeneratedCollageRGB(cls, originalImage: RasterImage) -> RasterImage:  # FC:308-347
+        out = cls.handle().collage(originalImage.argb, cls.imageInfoRGB, cls.blockgroesse, cls.widthKernel, rgb=True)
+        return RasterImage.from_argb(out)
+
+    @classmethod
+    def decode(cls, inputStream) -> RasterImage:  # FC:547-553 -> FC:356-421 / FC:430-508
+        data = inputStream.read() if hasattr(inputStream, "read") else bytes(inputStream)
+        rgb, W, H, B, wk, q = stream_read(data)
+        img, avg, _ = cls.handle().decode(q, W, H, B, wk, rgb, avg_error=float(cls.avgError))
+        cls.avgError = avg
+        return RasterImage.from_argb(img)
+
+
+def parse_header(stream: bytes):
+    return struct.unpack(">5i", stream[:20])

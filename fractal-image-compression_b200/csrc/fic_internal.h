@@ -1,0 +1,80 @@
+// fic_internal.h -- shared host/device declarations of libfic_b200 (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fic_b200.h"
+
+namespace fic {
+
+// Block / pool geometry of one encode or decode call (FC:111-116, FC:1019-1022).
+struct Geom {
+    int W, H, B, n;       // image size, block size, n = B*B
+    int wk;               // widthKernel: search window edge in domain-grid cells
+    int rpw, rph;         // range blocks per width / height
+    int dpw, dph;         // domain blocks per width / height (= 2*rp - 3)
+    int sw, sh;           // decimated image size (W/2, H/2)
+    int step;             // domain grid stride in decimated pixels (B/4, FC:1019)
+    int C;                // channels: 1 grey, 3 RGB
+    int64_t NR, ND;
+};
+
+// Returns FIC_OK or FIC_E_ARG (same rejections as the reference's exceptions).
+int make_geom(int W, int H, int B, int wk, int is_rgb, Geom *g, const char **why);
+
+// Device workspace owned by a handle (grow-only).
+struct Work {
+    int32_t *argb = nullptr;    // W*H staging of the caller's ARGB ints
+    uint8_t *src = nullptr;     // C planes W*H (grey: red channel)
+    uint8_t *dec = nullptr;     // C planes sw*sh, 2x decimated
+    int32_t *dsum = nullptr;    // [C][ND] sum of domain pixels
+    int32_t *dsq = nullptr;     // [C][ND] sum of squares of domain pixels
+    int32_t *rsum = nullptr;    // [C][NR] sum of range pixels
+    int32_t *best = nullptr;    // [NR] winning window-local candidate index
+    float *info = nullptr;      // [NR][3|5] unquantised codes
+    int32_t *q = nullptr;       // [NR][3|5] quantised codes
+    // tcgen05 search operands (see fic_search_umma.cu)
+    uint8_t *opA = nullptr;     // range operand blobs
+    uint8_t *opB = nullptr;     // domain operand blobs
+    // decoder
+    uint8_t *img = nullptr;     // C planes W*H: the image being reconstructed (updated in place)
+    uint8_t *dec2 = nullptr;    // second decimated buffer (Jacobi ping-pong with `dec`)
+    float *avgf = nullptr;      // 1 float: running avgError for the exact replay kernel
+    float *dcode = nullptr;     // [NR][3|5] dequantised codes with codebook indices
+    int32_t *perr = nullptr;    // per-pixel squared change in reference loop order (exact avgError path)
+    unsigned long long *acc = nullptr;  // [64] integer accumulators / flags
+    size_t cap[16] = {0};
+};
+
+// ---- kernel launchers (each returns the number of kernels it launched) -----------
+int launch_unpack(const int32_t *d_argb, uint8_t *d_planes, int W, int H, int C, cudaStream_t s);
+int launch_pack_argb(const uint8_t *d_planes, int32_t *d_argb, int W, int H, int C, cudaStream_t s);
+int launch_decimate(const uint8_t *d_src, uint8_t *d_dec, const Geom &g, cudaStream_t s);
+int launch_domain_stats(const uint8_t *d_dec, int32_t *d_dsum, int32_t *d_dsq, const Geom &g,
+                        cudaStream_t s);
+int launch_range_stats(const uint8_t *d_src, int32_t *d_rsum, const Geom &g, cudaStream_t s);
+int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, cudaStream_t s);
+int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_info, int32_t *d_q,
+                 cudaStream_t s);
+
+// tcgen05 fused full-pool search (grey, window == whole pool).
+bool umma_applicable(const Geom &g);
+size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1);
+size_t umma_opB_bytes(const Geom &g);
+int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms,
+                       cudaStream_t s, const char **err, cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr);
+int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms,
+                             cudaStream_t s, const char **err, int32_t *dump, int64_t dump_ld,
+                             int *status_dev, int variant);
+
+// decoder
+int launch_dequant(const int32_t *d_q, float *d_code, const Geom &g, int unquantised,
+                   const float *d_info, unsigned long long *d_acc, cudaStream_t s);
+int launch_fill(uint8_t *d_planes, size_t bytes, int value, cudaStream_t s);
+int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out,
+                        const float *d_code, const Geom &g, unsigned long long *d_acc,
+                        int32_t *d_perr, cudaStream_t s);
+int launch_serial_avg(const int32_t *d_perr, int64_t count, float *d_avg_inout, cudaStream_t s);
+
+}  // namespace fic

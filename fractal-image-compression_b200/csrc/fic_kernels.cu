@@ -1,0 +1,646 @@
+// fic_kernels.cu -- HBM-bound kernels of libfic_b200 (sm_100a):
+//   K1  pool builder: ARGB unpack, 2x decimation, per-domain / per-range integer sums
+//   K2w direct windowed search (grey + RGB), the reference's default widthKernel path
+//   K3s code solve + quantisation (shared by the direct and the tcgen05 search)
+//   K4  iterative decoder sweep (+ one-shot collage), exact avgError bookkeeping
+//
+// file:line citations refer to the reference, src/bvk_ss19/FractalCompression.java (FC)
+// and src/bvk_ss19/Domainblock.java (DB).
+#include "fic_device.cuh"
+
+namespace fic {
+
+// ------------------------------------------------------------------------------------
+// K1a: ARGB int32 -> 8-bit planes.  Grey keeps the red channel only (FC:596, FC:977).
+// 16-byte loads, 4-byte stores per plane.
+// ------------------------------------------------------------------------------------
+template <int C>
+__global__ void k_unpack(const int4 *__restrict__ argb, uchar4 *__restrict__ planes, int64_t quads,
+                         int64_t plane_quads)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < quads; i += stride) {
+        int4 p = __ldg(argb + i);
+        planes[i] = make_uchar4((p.x >> 16) & 0xff, (p.y >> 16) & 0xff, (p.z >> 16) & 0xff, (p.w >> 16) & 0xff);
+        if (C == 3) {
+            planes[plane_quads + i] =
+                make_uchar4((p.x >> 8) & 0xff, (p.y >> 8) & 0xff, (p.z >> 8) & 0xff, (p.w >> 8) & 0xff);
+            planes[2 * plane_quads + i] = make_uchar4(p.x & 0xff, p.y & 0xff, p.z & 0xff, p.w & 0xff);
+        }
+    }
+}
+
+int launch_unpack(const int32_t *d_argb, uint8_t *d_planes, int W, int H, int C, cudaStream_t s)
+{
+    int64_t quads = (int64_t)W * H / 4;  // W % 4 == 0 is guaranteed by make_geom
+    int blocks = (int)((quads + 255) / 256 < 148 * 16 ? (quads + 255) / 256 : 148 * 16);
+    if (blocks < 1) blocks = 1;
+    if (C == 1)
+        k_unpack<1><<<blocks, 256, 0, s>>>((const int4 *)d_argb, (uchar4 *)d_planes, quads, quads);
+    else
+        k_unpack<3><<<blocks, 256, 0, s>>>((const int4 *)d_argb, (uchar4 *)d_planes, quads, quads);
+    return 1;
+}
+
+// planes -> ARGB (0xff alpha), grey replicates the plane (FC:404, FC:490).
+template <int C>
+__global__ void k_pack_argb(const uchar4 *__restrict__ planes, int4 *__restrict__ argb, int64_t quads)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < quads; i += stride) {
+        uchar4 r = planes[i], g = r, b = r;
+        if (C == 3) {
+            g = planes[quads + i];
+            b = planes[2 * quads + i];
+        }
+        int4 o;
+        o.x = (int)(0xff000000u | (r.x << 16) | (g.x << 8) | b.x);
+        o.y = (int)(0xff000000u | (r.y << 16) | (g.y << 8) | b.y);
+        o.z = (int)(0xff000000u | (r.z << 16) | (g.z << 8) | b.z);
+        o.w = (int)(0xff000000u | (r.w << 16) | (g.w << 8) | b.w);
+        argb[i] = o;
+    }
+}
+
+int launch_pack_argb(const uint8_t *d_planes, int32_t *d_argb, int W, int H, int C, cudaStream_t s)
+{
+    int64_t quads = (int64_t)W * H / 4;
+    int blocks = (int)((quads + 255) / 256 < 148 * 16 ? (quads + 255) / 256 : 148 * 16);
+    if (blocks < 1) blocks = 1;
+    if (C == 1)
+        k_pack_argb<1><<<blocks, 256, 0, s>>>((const uchar4 *)d_planes, (int4 *)d_argb, quads);
+    else
+        k_pack_argb<3><<<blocks, 256, 0, s>>>((const uchar4 *)d_planes, (int4 *)d_argb, quads);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------
+// K1b: 2x decimation (FC:970-1007 grey, FC:901-962 RGB).
+//   grey: (p00 + p10 + p01 + p11) / 4;  RGB: (p00 + p10 + 2*p01) / 4 (FC:945 re-reads
+//   (x, y+1)).  With W, H even the only live border branch is the reference's
+//   `x + 1 >= image.height` test (FC:993, FC:940), which substitutes 128 for the fourth
+//   tap on landscape images; it is reproduced here.
+// One thread makes 2 output pixels from two 4-byte loads; stores are 2 bytes.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ int dec_tap4(int p00, int p10, int p01, int p11, int x, int H, bool rgb)
+{
+    int fourth = (x + 1 >= H) ? 128 : (rgb ? p01 : p11);
+    return (p00 + p10 + p01 + fourth) / 4;
+}
+
+__global__ void k_decimate(const uint8_t *__restrict__ src, uint8_t *__restrict__ dec, int W, int H, int C)
+{
+    int sw = W / 2, sh = H / 2;
+    int64_t pairs_per_plane = (int64_t)(sw / 2) * sh;
+    int64_t total = pairs_per_plane * C;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool rgb = C == 3;
+    for (; i < total; i += stride) {
+        int c = (int)(i / pairs_per_plane);
+        int64_t k = i - c * pairs_per_plane;
+        int qy = (int)(k / (sw / 2)), qx2 = (int)(k % (sw / 2));
+        const uint8_t *p = src + (int64_t)c * W * H + (int64_t)(2 * qy) * W + 4 * qx2;
+        uchar4 a = *(const uchar4 *)p;
+        uchar4 b = *(const uchar4 *)(p + W);
+        int x0 = 4 * qx2;
+        uchar2 o;
+        o.x = (unsigned char)dec_tap4(a.x, a.y, b.x, b.y, x0, H, rgb);
+        o.y = (unsigned char)dec_tap4(a.z, a.w, b.z, b.w, x0 + 2, H, rgb);
+        *(uchar2 *)(dec + (int64_t)c * sw * sh + (int64_t)qy * sw + 2 * qx2) = o;
+    }
+}
+
+int launch_decimate(const uint8_t *d_src, uint8_t *d_dec, const Geom &g, cudaStream_t s)
+{
+    int64_t total = (int64_t)(g.sw / 2) * g.sh * g.C;
+    int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    if (blocks < 1) blocks = 1;
+    k_decimate<<<blocks, 256, 0, s>>>(d_src, d_dec, g.W, g.H, g.C);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------
+// K1c: per-domain integer sums (DB:92-115).  Domain j = (gy, gx) covers the BxB block
+// of the decimated plane at (gx*step, gy*step) (FC:1027-1047).  sum d and sum d^2 are
+// exact in s32; mean and variance follow from them (dom_var()).
+// ------------------------------------------------------------------------------------
+__global__ void k_domain_stats(const uint8_t *__restrict__ dec, int32_t *__restrict__ dsum,
+                               int32_t *__restrict__ dsq, Geom g)
+{
+    int64_t total = g.ND * g.C;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i / g.ND);
+    int64_t j = i - c * g.ND;
+    int gx = (int)(j % g.dpw), gy = (int)(j / g.dpw);
+    const uint8_t *p = dec + (int64_t)c * g.sw * g.sh + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+    int s1 = 0, s2 = 0;
+    for (int ry = 0; ry < g.B; ry++) {
+        const uint8_t *row = p + (int64_t)ry * g.sw;
+        for (int rx = 0; rx < g.B; rx++) {
+            int v = __ldg(row + rx);
+            s1 += v;
+            s2 += v * v;
+        }
+    }
+    dsum[i] = s1;
+    dsq[i] = s2;
+}
+
+int launch_domain_stats(const uint8_t *d_dec, int32_t *d_dsum, int32_t *d_dsq, const Geom &g, cudaStream_t s)
+{
+    int64_t total = g.ND * g.C;
+    k_domain_stats<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_dec, d_dsum, d_dsq, g);
+    return 1;
+}
+
+// K1d: per-range pixel sums (FC:67-73 getMittelwert of FC:588-602 getRangeblock).
+__global__ void k_range_stats(const uint8_t *__restrict__ src, int32_t *__restrict__ rsum, Geom g)
+{
+    int64_t total = g.NR * g.C;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i / g.NR);
+    int64_t j = i - c * g.NR;
+    int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    const uint8_t *p = src + (int64_t)c * g.W * g.H + (int64_t)(yr * g.B) * g.W + xr * g.B;
+    int s1 = 0;
+    for (int ry = 0; ry < g.B; ry++) {
+        const uchar4 *row = (const uchar4 *)(p + (int64_t)ry * g.W);
+        for (int rx = 0; rx < g.B / 4; rx++) {
+            uchar4 v = __ldg(row + rx);
+            s1 += v.x + v.y + v.z + v.w;
+        }
+    }
+    rsum[i] = s1;
+}
+
+int launch_range_stats(const uint8_t *d_src, int32_t *d_rsum, const Geom &g, cudaStream_t s)
+{
+    int64_t total = g.NR * g.C;
+    k_range_stats<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(d_src, d_rsum, g);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------
+// K2w: direct windowed search.  One CTA per range block; threads stride over the wk*wk
+// window candidates in ascending order, score each exactly as the reference does and
+// keep the strict-< running minimum (FC:619-632); a lexicographic (error, index) block
+// reduction then picks the lowest index among equal errors, which is what the
+// reference's ascending loop with strict < yields.
+// ------------------------------------------------------------------------------------
+constexpr int kDirectThreads = 128;
+
+__device__ __forceinline__ void block_argmin(float &err, int &c, float *s_err, int *s_c)
+{
+    // warp level
+    for (int o = 16; o > 0; o >>= 1) {
+        float e2 = __shfl_down_sync(0xffffffffu, err, o);
+        int c2 = __shfl_down_sync(0xffffffffu, c, o);
+        if (e2 < err || (e2 == err && c2 < c)) { err = e2; c = c2; }
+    }
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_err[warp] = err; s_c[warp] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kDirectThreads / 32; w++) {
+            float e2 = s_err[w];
+            int c2 = s_c[w];
+            if (e2 < err || (e2 == err && c2 < c)) { err = e2; c = c2; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kDirectThreads)
+k_search_direct_grey(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec,
+                     const int32_t *__restrict__ dsum, const int32_t *__restrict__ dsq,
+                     const int32_t *__restrict__ rsum, int32_t *__restrict__ best, Geom g, int64_t j0)
+{
+    __shared__ int s_rt[256];  // r - rmean, B <= 16
+    __shared__ float s_err[kDirectThreads / 32];
+    __shared__ int s_c[kDirectThreads / 32];
+    int64_t j = j0 + blockIdx.x;
+    int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    int rs = rsum[j];
+    int rmean = rs / g.n;       // FC:72
+    int vR = rs - g.n * rmean;  // sum (r - rmean), FC:671
+    for (int t = threadIdx.x; t < g.n; t += kDirectThreads) {
+        int ry = t / g.B, rx = t % g.B;
+        s_rt[t] = (int)src[(int64_t)(yr * g.B + ry) * g.W + xr * g.B + rx] - rmean;
+    }
+    __syncthreads();
+    int dy, dx;
+    range_window(g, j, &dy, &dx);
+    float best_err = 10000000.0f;  // FC:615
+    int best_c = 0;
+    int ncand = g.wk * g.wk;
+    for (int c = threadIdx.x; c < ncand; c += kDirectThreads) {
+        int ky = c / g.wk, kx = c - ky * g.wk;
+        int gx = dx + kx, gy = dy + ky;
+        int64_t idx = gx + (int64_t)gy * g.dpw;  // FC:145
+        const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+        int dot = 0;
+        for (int ry = 0; ry < g.B; ry++) {
+            const uint8_t *row = p + (int64_t)ry * g.sw;
+            for (int rx = 0; rx < g.B; rx++) dot += s_rt[ry * g.B + rx] * (int)__ldg(row + rx);
+        }
+        int dmean;
+        int varD = dom_var(dsum[idx], dsq[idx], g.n, &dmean);
+        int kov = dot - dmean * vR;  // sum (r-rmean)(d-dmean)
+        float err = grey_error(kov, vR, __dsqrt_rn((double)varD));
+        if (err < best_err) { best_err = err; best_c = c; }  // FC:627
+    }
+    block_argmin(best_err, best_c, s_err, s_c);
+    if (threadIdx.x == 0) best[j] = best_c;
+}
+
+// RGB: one shared domain and contrast for the three channels (FC:760-808).  The
+// covariance is accumulated sequentially in binary32 in pixel order exactly as the
+// reference does (it is only guaranteed to be an exact integer for B <= 4).
+struct RgbScore {
+    float err, kov;
+};
+
+__device__ __forceinline__ RgbScore rgb_score(const float *s_gR, float vR, const uint8_t *dec, const Geom &g,
+                                              int gx, int gy, int mR, int mG, int mB)
+{
+    int64_t plane = (int64_t)g.sw * g.sh;
+    const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+    float dR = (float)mR, dG = (float)mG, dB = (float)mB;
+    float kov = 0.0f, vD = 0.0f;  // FC:775, FC:778 (sqrt(variance) == 0 on the RGB path)
+    for (int ry = 0; ry < g.B; ry++) {
+        const uint8_t *row = p + (int64_t)ry * g.sw;
+        for (int rx = 0; rx < g.B; rx++) {
+            float gD = __fadd_rn(__fadd_rn(__fsub_rn((float)__ldg(row + rx), dR),
+                                           __fsub_rn((float)__ldg(row + plane + rx), dG)),
+                                 __fsub_rn((float)__ldg(row + 2 * plane + rx), dB));  // FC:783-784
+            kov = __fadd_rn(kov, __fmul_rn(s_gR[ry * g.B + rx], gD));                // FC:789
+            vD = __fadd_rn(vD, gD);                                                  // FC:791
+        }
+    }
+    float r = 0.0f;
+    if (!(vR == 0.0f || vD == 0.0f)) r = __fdiv_rn(kov, __fmul_rn(vR, vD));  // FC:797-800
+    r = __fmul_rn(r, r);
+    RgbScore o;
+    o.err = __fmul_rn(__fmul_rn(vR, vR), __fsub_rn(1.0f, r));  // FC:803
+    o.kov = kov;
+    return o;
+}
+
+// Loads (r - rmean) summed over the channels for the range block into smem (FC:785-786)
+// and returns vR = sum of it (FC:790).  rm[] receives the per-channel integer means.
+__device__ __forceinline__ float rgb_range_prep(const uint8_t *src, const int32_t *rsum, const Geom &g, int64_t j,
+                                                float *s_gR, int rm[3])
+{
+    int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    int64_t plane = (int64_t)g.W * g.H;
+    int v = 0;
+    for (int c = 0; c < 3; c++) {
+        int rs = rsum[(int64_t)c * g.NR + j];
+        rm[c] = rs / g.n;
+        v += rs - g.n * rm[c];
+    }
+    for (int t = threadIdx.x; t < g.n; t += blockDim.x) {
+        int ry = t / g.B, rx = t % g.B;
+        int64_t o = (int64_t)(yr * g.B + ry) * g.W + xr * g.B + rx;
+        s_gR[t] = (float)(((int)src[o] - rm[0]) + ((int)src[plane + o] - rm[1]) + ((int)src[2 * plane + o] - rm[2]));
+    }
+    return (float)v;
+}
+
+__global__ void __launch_bounds__(kDirectThreads)
+k_search_direct_rgb(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec,
+                    const int32_t *__restrict__ dsum, const int32_t *__restrict__ rsum,
+                    int32_t *__restrict__ best, Geom g, int64_t j0)
+{
+    __shared__ float s_gR[256];
+    __shared__ float s_err[kDirectThreads / 32];
+    __shared__ int s_c[kDirectThreads / 32];
+    int64_t j = j0 + blockIdx.x;
+    int rm[3];
+    float vR = rgb_range_prep(src, rsum, g, j, s_gR, rm);
+    __syncthreads();
+    int dy, dx;
+    range_window(g, j, &dy, &dx);
+    float best_err = 10000000.0f;  // FC:698
+    int best_c = 0;
+    int ncand = g.wk * g.wk;
+    for (int c = threadIdx.x; c < ncand; c += kDirectThreads) {
+        int ky = c / g.wk, kx = c - ky * g.wk;
+        int gx = dx + kx, gy = dy + ky;
+        int64_t idx = gx + (int64_t)gy * g.dpw;
+        RgbScore sc = rgb_score(s_gR, vR, dec, g, gx, gy, dsum[idx] / g.n, dsum[g.ND + idx] / g.n,
+                                dsum[2 * g.ND + idx] / g.n);
+        if (sc.err < best_err) { best_err = sc.err; best_c = c; }  // FC:710
+    }
+    block_argmin(best_err, best_c, s_err, s_c);
+    if (threadIdx.x == 0) best[j] = best_c;
+}
+
+int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, cudaStream_t s)
+{
+    if (j1 <= j0) return 0;
+    int64_t left = j1 - j0, at = j0;
+    int launches = 0;
+    while (left > 0) {  // grid.x limit is 2^31-1; chunk anyway to keep launches bounded
+        unsigned chunk = (unsigned)(left < (1 << 30) ? left : (1 << 30));
+        if (g.C == 1)
+            k_search_direct_grey<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, g, at);
+        else
+            k_search_direct_rgb<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.rsum, w.best, g, at);
+        left -= chunk;
+        at += chunk;
+        launches++;
+    }
+    return launches;
+}
+
+// ------------------------------------------------------------------------------------
+// K3s: code solve + quantisation for the winning candidate (FC:634-643 grey,
+// FC:718-733 RGB; quantisation FC:242-244 / FC:250-254).  One thread per range block.
+// ------------------------------------------------------------------------------------
+__global__ void k_solve_grey(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec,
+                             const int32_t *__restrict__ dsum, const int32_t *__restrict__ dsq,
+                             const int32_t *__restrict__ rsum, const int32_t *__restrict__ best,
+                             float *__restrict__ info, int32_t *__restrict__ q, Geom g, int64_t j0, int64_t j1)
+{
+    int64_t j = j0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= j1) return;
+    int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    int c = best[j];
+    int dy, dx;
+    range_window(g, j, &dy, &dx);
+    int ky = c / g.wk, kx = c - ky * g.wk;
+    int gx = dx + kx, gy = dy + ky;
+    int64_t idx = gx + (int64_t)gy * g.dpw;
+    int rs = rsum[j];
+    int rmean = rs / g.n, vR = rs - g.n * rmean;
+    const uint8_t *pr = src + (int64_t)(yr * g.B) * g.W + xr * g.B;
+    const uint8_t *pd = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+    int dot = 0;
+    for (int ry = 0; ry < g.B; ry++)
+        for (int rx = 0; rx < g.B; rx++)
+            dot += ((int)pr[(int64_t)ry * g.W + rx] - rmean) * (int)pd[(int64_t)ry * g.sw + rx];
+    int dmean;
+    int varD = dom_var(dsum[idx], dsq[idx], g.n, &dmean);
+    int kov = dot - dmean * vR;
+    float a = __fdiv_rn((float)kov, (float)varD);  // FC:634 (0/0 -> NaN on flat winners)
+    if (a < -1.0f) a = -1.0f;                      // FC:636-639 (NaN passes through)
+    else if (a > 1.0f) a = 1.0f;
+    float b = __fsub_rn((float)rmean, __fmul_rn(a, (float)dmean));  // FC:641
+    float fc = (float)c;
+    if (info) {
+        info[3 * j + 0] = fc;
+        info[3 * j + 1] = a;
+        info[3 * j + 2] = b;
+    }
+    if (q) {
+        q[3 * j + 0] = j_f2i(fc);                     // FC:242
+        q[3 * j + 1] = j_f2i(__fmul_rn(a, 100.0f));   // FC:243
+        q[3 * j + 2] = j_f2i(b);                      // FC:244
+    }
+}
+
+__global__ void k_solve_rgb(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec,
+                            const int32_t *__restrict__ dsum, const int32_t *__restrict__ dsq,
+                            const int32_t *__restrict__ rsum, const int32_t *__restrict__ best,
+                            float *__restrict__ info, int32_t *__restrict__ q, Geom g, int64_t j0, int64_t j1)
+{
+    int64_t j = j0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= j1) return;
+    int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    int c = best[j];
+    int dy, dx;
+    range_window(g, j, &dy, &dx);
+    int ky = c / g.wk, kx = c - ky * g.wk;
+    int gx = dx + kx, gy = dy + ky;
+    int64_t idx = gx + (int64_t)gy * g.dpw;
+    int rm[3], dm[3], dv[3];
+    for (int ch = 0; ch < 3; ch++) {
+        rm[ch] = rsum[(int64_t)ch * g.NR + j] / g.n;
+        dv[ch] = dom_var(dsum[(int64_t)ch * g.ND + idx], dsq[(int64_t)ch * g.ND + idx], g.n, &dm[ch]);
+    }
+    int64_t planeS = (int64_t)g.W * g.H, planeD = (int64_t)g.sw * g.sh;
+    const uint8_t *pr = src + (int64_t)(yr * g.B) * g.W + xr * g.B;
+    const uint8_t *pd = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+    float dR = (float)dm[0], dG = (float)dm[1], dB = (float)dm[2];
+    float kov = 0.0f;
+    for (int ry = 0; ry < g.B; ry++)
+        for (int rx = 0; rx < g.B; rx++) {
+            int64_t os = (int64_t)ry * g.W + rx, od = (int64_t)ry * g.sw + rx;
+            float gD = __fadd_rn(__fadd_rn(__fsub_rn((float)pd[od], dR), __fsub_rn((float)pd[planeD + od], dG)),
+                                 __fsub_rn((float)pd[2 * planeD + od], dB));
+            float gR = (float)(((int)pr[os] - rm[0]) + ((int)pr[planeS + os] - rm[1]) +
+                               ((int)pr[2 * planeS + os] - rm[2]));
+            kov = __fadd_rn(kov, __fmul_rn(gR, gD));
+        }
+    // FC:776: varianzSquare = varianceR + varianceG + mittelWertB (sic)
+    float varSq = __fadd_rn(__fadd_rn((float)dv[0], (float)dv[1]), (float)dm[2]);
+    float a = __fdiv_rn(kov, varSq);  // FC:718
+    if (a > 1.0f) a = 1.0f;           // FC:721-724
+    if (a < -1.0f) a = -1.0f;
+    float bR = __fsub_rn((float)rm[0], __fmul_rn(a, dR));  // FC:727-731
+    float bG = __fsub_rn((float)rm[1], __fmul_rn(a, dG));
+    float bB = __fsub_rn((float)rm[2], __fmul_rn(a, dB));
+    float fc = (float)c;
+    if (info) {
+        info[5 * j + 0] = fc;
+        info[5 * j + 1] = a;
+        info[5 * j + 2] = bR;
+        info[5 * j + 3] = bG;
+        info[5 * j + 4] = bB;
+    }
+    if (q) {
+        q[5 * j + 0] = j_f2i(fc);                          // FC:250
+        q[5 * j + 1] = j_f2i(__fmul_rn(a, 1000000.0f));    // FC:251
+        q[5 * j + 2] = j_f2i(__fmul_rn(bR, 100000.0f));    // FC:252
+        q[5 * j + 3] = j_f2i(__fmul_rn(bG, 100000.0f));    // FC:253
+        q[5 * j + 4] = j_f2i(bB);                          // FC:254
+    }
+}
+
+int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_info, int32_t *d_q, cudaStream_t s)
+{
+    if (j1 <= j0) return 0;
+    unsigned blocks = (unsigned)((j1 - j0 + 127) / 128);
+    if (g.C == 1)
+        k_solve_grey<<<blocks, 128, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, d_info, d_q, g, j0, j1);
+    else
+        k_solve_rgb<<<blocks, 128, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, d_info, d_q, g, j0, j1);
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------
+// K4: decoder.
+// ------------------------------------------------------------------------------------
+
+// Stream ints -> float codes (FC:372-374 / FC:446-450) and window-local -> codebook
+// index (FC:853-893 calculateIndices, float division / float remainder as in Java).
+// With `unquantised` the float codes of an encode are used instead (collage, FC:271).
+// acc[1] is set when an index falls outside the pool (the reference would throw).
+__global__ void k_dequant(const int32_t *__restrict__ q, const float *__restrict__ info_in,
+                          float *__restrict__ code, Geom g, int unquantised, unsigned long long *acc)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.NR) return;
+    int S = g.C == 1 ? 3 : 5;
+    float v[5];
+    if (unquantised) {
+        for (int k = 0; k < S; k++) v[k] = info_in[S * j + k];
+    } else if (g.C == 1) {
+        v[0] = (float)q[3 * j];
+        v[1] = __fdiv_rn((float)q[3 * j + 1], 100.0f);
+        v[2] = (float)q[3 * j + 2];
+    } else {
+        v[0] = (float)q[5 * j];
+        v[1] = __fdiv_rn((float)q[5 * j + 1], 1000000.0f);
+        v[2] = __fdiv_rn((float)q[5 * j + 2], 100000.0f);
+        v[3] = __fdiv_rn((float)q[5 * j + 3], 100000.0f);
+        v[4] = (float)q[5 * j + 4];
+    }
+    int dy, dx;
+    range_window(g, j, &dy, &dx);
+    float fwk = (float)g.wk;
+    int yd = j_f2i(__fdiv_rn(v[0], fwk));  // FC:882
+    int xd = j_f2i(fmodf(v[0], fwk));      // FC:883
+    int64_t result = (int64_t)xd + dx + (int64_t)(yd + dy) * g.dpw;  // FC:886
+    if (result < 0 || result >= g.ND) {
+        atomicOr(acc + 1, 1ull);
+        result = 0;
+    }
+    v[0] = (float)(int)result;  // FC:888 stores the index back into the float table
+    for (int k = 0; k < S; k++) code[S * j + k] = v[k];
+}
+
+int launch_dequant(const int32_t *d_q, float *d_code, const Geom &g, int unquantised, const float *d_info,
+                   unsigned long long *d_acc, cudaStream_t s)
+{
+    k_dequant<<<(unsigned)((g.NR + 127) / 128), 128, 0, s>>>(d_q, d_info, d_code, g, unquantised, d_acc);
+    return 1;
+}
+
+__global__ void k_fill(uint4 *p, int64_t n16, uint32_t v)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n16; i += stride) p[i] = make_uint4(v, v, v, v);
+}
+
+int launch_fill(uint8_t *d_planes, size_t bytes, int value, cudaStream_t s)
+{
+    uint32_t v = (uint32_t)(value & 0xff) * 0x01010101u;
+    int64_t n16 = (int64_t)(bytes / 16);  // plane sizes are multiples of 16 (W % 4 == 0, H % 4 == 0)
+    int blocks = (int)((n16 + 255) / 256 < 148 * 8 ? (n16 + 255) / 256 : 148 * 8);
+    if (blocks < 1) blocks = 1;
+    k_fill<<<blocks, 256, 0, s>>>((uint4 *)d_planes, n16, v);
+    return 1;
+}
+
+// One Jacobi sweep of FC:386-412 / FC:463-499.  The reference snapshots the codebook
+// of the current image (FC:382), then rewrites every pixel from it; here the snapshot
+// is the 2x-decimated plane `dec_in` of the current image, and the sweep emits the
+// decimated plane of the image it writes (`dec_out`), so the next sweep needs no
+// separate decimation pass.  One thread owns a 2x2 pixel quad (same range block, same
+// code): 4 gathered domain bytes in, 4 image bytes + 1 decimated byte out per channel.
+//   acc[0] += sum of squared pixel changes (exact integer; see fic_api.cu for how this
+//   reproduces the reference's float avgError), perr (optional) gets the per-pixel
+//   squared change in the reference's accumulation order (range-major, ry, rx).
+template <int C>
+__global__ void __launch_bounds__(256)
+k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, uint8_t *__restrict__ dec_out,
+               const float *__restrict__ code, Geom g, unsigned long long *acc, int32_t *__restrict__ perr)
+{
+    int qw = g.W / 2;
+    int64_t quads = (int64_t)qw * (g.H / 2);
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long local = 0;
+    if (t < quads) {
+        int qy = (int)(t / qw), qx = (int)(t - (int64_t)qy * qw);
+        int x = 2 * qx, y = 2 * qy;
+        int xr = x / g.B, yr = y / g.B;
+        int rx = x - xr * g.B, ry = y - yr * g.B;
+        int64_t j = (int64_t)yr * g.rpw + xr;
+        constexpr int S = C == 1 ? 3 : 5;
+        const float *cd = code + S * j;
+        int idx = j_f2i(cd[0]);  // FC:394 (int) imgData[i][0]
+        float a = cd[1];
+        int gx = idx % g.dpw, gy = idx / g.dpw;
+        int64_t planeI = (int64_t)g.W * g.H, planeD = (int64_t)g.sw * g.sh;
+        int e[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            float b = cd[2 + c];
+            const uint8_t *pd = dec_in + c * planeD + (int64_t)(gy * g.step + ry) * g.sw + gx * g.step + rx;
+            int d00 = pd[0], d10 = pd[1], d01 = pd[g.sw], d11 = pd[g.sw + 1];
+            // FC:396 / FC:482: (int)(a * domain + b), float multiply then float add
+            int v00 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d00), b)));
+            int v10 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d10), b)));
+            int v01 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d01), b)));
+            int v11 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d11), b)));
+            uint8_t *pi = img + c * planeI + (int64_t)y * g.W + x;
+            uchar2 o0 = *(uchar2 *)pi, o1 = *(uchar2 *)(pi + g.W);
+            e[0] += (o0.x - v00) * (o0.x - v00);  // FC:407 / FC:493
+            e[1] += (o0.y - v10) * (o0.y - v10);
+            e[2] += (o1.x - v01) * (o1.x - v01);
+            e[3] += (o1.y - v11) * (o1.y - v11);
+            *(uchar2 *)pi = make_uchar2(v00, v10);
+            *(uchar2 *)(pi + g.W) = make_uchar2(v01, v11);
+            if (dec_out) dec_out[c * planeD + (int64_t)qy * g.sw + qx] = (uint8_t)dec_tap4(v00, v10, v01, v11, x, g.H, C == 3);
+        }
+        local = (unsigned long long)(e[0] + e[1] + e[2] + e[3]);
+        if (perr) {
+            int32_t *pe = perr + j * g.n + ry * g.B + rx;
+            pe[0] = e[0];
+            pe[1] = e[1];
+            pe[g.B] = e[2];
+            pe[g.B + 1] = e[3];
+        }
+    }
+    if (acc) {
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(acc, local);
+    }
+}
+
+int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out, const float *d_code,
+                        const Geom &g, unsigned long long *d_acc, int32_t *d_perr, cudaStream_t s)
+{
+    int64_t quads = (int64_t)(g.W / 2) * (g.H / 2);
+    unsigned blocks = (unsigned)((quads + 255) / 256);
+    if (g.C == 1)
+        k_decode_sweep<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, g, d_acc, d_perr);
+    else
+        k_decode_sweep<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, g, d_acc, d_perr);
+    return 1;
+}
+
+// Exact replay of the reference's float accumulation `avgError += e` (FC:407) over the
+// per-pixel squared changes in loop order.  Single thread: the binary32 running sum is
+// order dependent once it passes 2^24.  Only launched when the integer sum cannot
+// decide (see fic_api.cu); never on the common path.
+__global__ void k_serial_avg(const int32_t *__restrict__ perr, int64_t count, float *avg)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    float a = *avg;
+    int64_t i = 0;
+    for (; i + 4 <= count; i += 4) {
+        int4 v = *(const int4 *)(perr + i);
+        a = __fadd_rn(a, (float)v.x);
+        a = __fadd_rn(a, (float)v.y);
+        a = __fadd_rn(a, (float)v.z);
+        a = __fadd_rn(a, (float)v.w);
+    }
+    for (; i < count; i++) a = __fadd_rn(a, (float)perr[i]);
+    *avg = a;
+}
+
+int launch_serial_avg(const int32_t *d_perr, int64_t count, float *d_avg_inout, cudaStream_t s)
+{
+    k_serial_avg<<<1, 32, 0, s>>>(d_perr, count, d_avg_inout);
+    return 1;
+}
+
+}  // namespace fic

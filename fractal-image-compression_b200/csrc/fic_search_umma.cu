@@ -1,0 +1,629 @@
+// fic_search_umma.cu -- K2+K3: the full-pool range x domain search as an exact integer
+// contraction on the 5th-generation tensor cores (tcgen05, kind::i8, accumulators in
+// TMEM), with the scoring / argmin epilogue fused so that no score matrix is ever
+// written to HBM.  sm_100a only.
+//
+// What is computed.  For range block i and domain block j the reference scores
+//     error = vR^2 * (1 - (kov / (vR * sqrt(varD)))^2)          (FC:677-683)
+// with the exact integers kov = sum (r - rmean)(d - dmean), vR = sum (r - rmean) and
+// varD = sum (d - dmean)^2, and keeps the first index with the smallest float error
+// (strict <, ascending loop, FC:619-632).  error is a non-increasing function of
+// x = |kov| / sqrt(varD) through every rounding step, so the reference's winner is the
+// lowest index at which the running maximum of x is (re)attained up to rounding.  The
+// epilogue therefore
+//   1. gets kov[i][j] exactly from the tensor cores,
+//   2. filters with the cheap binary32 score f = |kov| * rsqrt(varD_j) against the
+//      running maximum of the row (relative slack 2^-20, far above f's rounding error),
+//   3. evaluates the reference's own float/double error formula only for candidates
+//      that pass, and applies the reference's strict-< update in ascending index order.
+// Result: the same winner index as the reference for every row, bit for bit.
+//
+// How kov becomes one u8 x s8 GEMM.  With dt = d - dmean_j (|dt| <= 254 for B <= 8),
+// split dt = h + l, h = dt >> 1, l = dt - h (both fit s8).  Then
+//     kov = sum_k r_k * h_k + sum_k r_k * l_k + rmean_i * (-alpha_j),   alpha_j = sum d - n*dmean_j
+// i.e. A row = [ r | r | rmean 0.. ] (u8) and B row = [ h | l | -alpha 0.. ] (s8), K
+// padded to a multiple of 32 (one kind::i8 MMA consumes K = 32).  The duplicated `r`
+// half of A is not stored twice: the MMA issuer simply points the A descriptor of
+// K-slices 2,3 back at slices 0,1 (B = 8).
+//
+// Data movement.  Operands are packed once per encode by two HBM-bound kernels into
+// "blobs" that are already in the canonical no-swizzle K-major UMMA shared-memory
+// layout (8x16-byte core matrices, LBO = 128 B between K-adjacent core matrices,
+// SBO = KS*256 B between 8-row groups).  A blob is moved with ONE 1-D TMA bulk copy
+// (cp.async.bulk, SASS UBLKCP) that completes on an mbarrier; a domain tile blob also
+// carries the 128 per-column scales rsqrt(varD) (f32) and sqrt(varD) (f64).
+//
+// CTA organisation (1 CTA / SM, 640 threads, persistent over work units):
+//   warp 0      TMA producer: A super-block (512 range rows, resident for the whole
+//               unit) + a ring of domain tiles (128 domains each)
+//   warp 1      MMA issuer: per domain tile 4 accumulators (128 rows x 128 domains s32,
+//               4 x 128 = all 512 TMEM columns) x NS K-slices of tcgen05.mma
+//   warp 2      TMEM allocator
+//   warps 4-19  epilogue: warp e owns accumulator q = e / 4, TMEM lanes 32*(e % 4)..+31;
+//               one thread owns one range row for the whole unit
+// A work unit is (super-block of 512 rows) x (1/n_chunks of the domain tiles); per-unit
+// row winners go to part_err / part_idx and are merged in ascending chunk order.
+#include "fic_device.cuh"
+
+namespace fic {
+
+namespace {
+
+constexpr int kTileN = 128;        // domains per B tile == MMA N
+constexpr int kBlockM = 128;       // rows per accumulator == MMA M
+constexpr int kAccs = 4;           // accumulators per tile (TMEM: 4 x 128 columns)
+constexpr int kRowsPerSB = kBlockM * kAccs;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = (4 + kEpiWarps) * 32;
+constexpr int kScaleBytes = kTileN * 4 + kTileN * 8;  // rsd f32 + sqd f64
+
+template <int B>
+struct Cfg;
+template <>
+struct Cfg<8> {
+    static constexpr int n = 64;
+    static constexpr int KS_A = 3;   // physical A K-slices (32 B each): r[0:32] r[32:64] [rmean 0..]
+    static constexpr int KS_B = 5;   // h[0:32] h[32:64] l[0:32] l[32:64] [-alpha 0..]
+    static constexpr int NS = 5;     // MMA K-slices
+    static constexpr int NSTAGE = 6;
+    __host__ __device__ static constexpr int amap(int s) { return s < 4 ? (s & 1) : 2; }
+};
+template <>
+struct Cfg<4> {
+    static constexpr int n = 16;
+    static constexpr int KS_A = 2;   // [r r] [rmean 0..]
+    static constexpr int KS_B = 2;   // [h l] [-alpha 0..]
+    static constexpr int NS = 2;
+    static constexpr int NSTAGE = 8;
+    __host__ __device__ static constexpr int amap(int s) { return s; }
+};
+
+template <int B>
+struct Lay {
+    using C = Cfg<B>;
+    static constexpr int SBO_A = C::KS_A * 256;
+    static constexpr int SBO_B = C::KS_B * 256;
+    static constexpr int A_BLOCK_BYTES = (kBlockM / 8) * SBO_A;
+    static constexpr int A_SB_BYTES = kAccs * A_BLOCK_BYTES;
+    static constexpr int B_OP_BYTES = (kTileN / 8) * SBO_B;
+    static constexpr int B_TILE_BYTES = B_OP_BYTES + kScaleBytes;
+    static constexpr int SMEM_BYTES = A_SB_BYTES + C::NSTAGE * B_TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------- operand packing ----
+
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
+{
+    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+}
+
+// One thread per (padded) domain: centre by the integer mean, split into two s8 digits,
+// write the tile blob row and the two per-column scales.
+template <int B>
+__global__ void __launch_bounds__(128)
+k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
+                    const int32_t *__restrict__ dsq, uint8_t *__restrict__ opB, Geom g, int64_t ntiles)
+{
+    using L = Lay<B>;
+    constexpr int n = Cfg<B>::n;
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ntiles * kTileN) return;
+    int64_t tile = j / kTileN;
+    int row = (int)(j % kTileN);
+    uint8_t *blob = opB + tile * L::B_TILE_BYTES;
+    uint8_t *rowp = blob + (row >> 3) * L::SBO_B + (row & 7) * 16;
+    float *rsd = (float *)(blob + L::B_OP_BYTES);
+    double *sqd = (double *)(blob + L::B_OP_BYTES + kTileN * 4);
+    constexpr int NCH = Cfg<B>::KS_B * 2;  // 16-byte chunks per row
+    if (j >= g.ND) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
+        rsd[row] = 0.0f;
+        sqd[row] = 0.0;
+        return;
+    }
+    int gx = (int)(j % g.dpw), gy = (int)(j / g.dpw);
+    const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+    int dmean;
+    int varD = dom_var(dsum[j], dsq[j], n, &dmean);
+    int alpha = dsum[j] - n * dmean;
+    constexpr int PCH = n / 16;  // pixel chunks per digit
+#pragma unroll
+    for (int c = 0; c < PCH; c++) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            int hv[4], lv[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int k = c * 16 + w * 4 + e;
+                int dt = (int)__ldg(p + (int64_t)(k / B) * g.sw + (k % B)) - dmean;
+                hv[e] = dt >> 1;
+                lv[e] = dt - hv[e];
+            }
+            hw[w] = pack4(hv[0], hv[1], hv[2], hv[3]);
+            lw[w] = pack4(lv[0], lv[1], lv[2], lv[3]);
+        }
+        *(uint4 *)(rowp + c * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *(uint4 *)(rowp + (PCH + c) * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+    *(uint4 *)(rowp + (2 * PCH) * 128) = make_uint4((uint32_t)((-alpha) & 0xff), 0, 0, 0);
+    *(uint4 *)(rowp + (2 * PCH + 1) * 128) = make_uint4(0, 0, 0, 0);
+    double sq = __dsqrt_rn((double)varD);
+    sqd[row] = sq;
+    rsd[row] = varD > 0 ? __double2float_rn(__ddiv_rn(1.0, sq)) : 0.0f;
+}
+
+// One thread per (padded) range row of the slice [j0, j1): raw pixels + integer mean.
+template <int B>
+__global__ void __launch_bounds__(128)
+k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, uint8_t *__restrict__ opA,
+                   int32_t *__restrict__ vRout, Geom g, int64_t j0, int64_t j1, int64_t rows_padded)
+{
+    using L = Lay<B>;
+    constexpr int n = Cfg<B>::n;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows_padded) return;
+    int64_t sb = i / kRowsPerSB;
+    int rr = (int)(i % kRowsPerSB);
+    int blk = rr / kBlockM, row = rr % kBlockM;
+    uint8_t *rowp = opA + sb * L::A_SB_BYTES + blk * L::A_BLOCK_BYTES + (row >> 3) * L::SBO_A + (row & 7) * 16;
+    constexpr int NCH = Cfg<B>::KS_A * 2;
+    int64_t j = j0 + i;
+    if (j >= j1) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
+        vRout[i] = 0;
+        return;
+    }
+    int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    const uint8_t *p = src + (int64_t)(yr * B) * g.W + xr * B;
+    int rs = rsum[j];
+    int rmean = rs / n;
+    vRout[i] = rs - n * rmean;
+    constexpr int PCH = n / 16;
+#pragma unroll
+    for (int c = 0; c < PCH; c++) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            int k = c * 16 + w * 4;
+            // 4 consecutive k share a pixel row for B >= 4; 4-byte aligned since xr*B, k%B are multiples of 4
+            w4[w] = *(const uint32_t *)(p + (int64_t)(k / B) * g.W + (k % B));
+        }
+        uint4 v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        *(uint4 *)(rowp + c * 128) = v;
+        if (B == 4) *(uint4 *)(rowp + (PCH + c) * 128) = v;  // [r r] shares one 32-byte slice
+    }
+    constexpr int XCH = (B == 4) ? 2 * PCH : PCH;
+    *(uint4 *)(rowp + XCH * 128) = make_uint4((uint32_t)rmean, 0, 0, 0);
+    *(uint4 *)(rowp + (XCH + 1) * 128) = make_uint4(0, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------- PTX wrappers -------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a pipeline bug must end in an error, never in a hung GPU.  status is
+// pinned host memory (mapped), so the code survives the trap.
+__device__ __noinline__ void mbar_timeout(volatile int *status, int code)
+{
+    if (status) {
+        *status = code;
+        __threadfence_system();
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int *status, int code)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000ll) mbar_timeout(status, code);
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (PTX "matrix descriptor";
+// cute::UMMA::SmemDescriptor): start address, leading (K) and stride (M/N) byte offsets
+// in 16-byte units, descriptor version 1 (Blackwell) in bits 46-47, layout type 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
+}
+
+// kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor): D = s32 (c_format 2 at
+// bit 4), A = u8 (0 at bit 7), B = s8 (1 at bit 10), both K-major, N>>3 at bit 17, M>>4
+// at bit 24.
+constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+                            ((uint32_t)(kBlockM >> 4) << 24);
+
+// ---------------------------------------------------------------- epilogue state -----
+
+struct RowState {
+    float thresh;    // candidates with f <= thresh cannot win (see file header)
+    float fmax;      // running maximum of the filter score
+    float best_err;  // reference float error of the current winner (FC:615 start value)
+    int best_idx;
+};
+
+// Exact evaluation of one candidate, reference arithmetic (FC:677-683) and the
+// reference's strict-< update (FC:627).  Rarely executed: kept out of line.
+__device__ __noinline__ RowState eval_candidate(RowState st, float f, int kov, int vR, double sqd, int idx)
+{
+    float err = grey_error(kov, vR, sqd);
+    if (err < st.best_err) {
+        st.best_err = err;
+        st.best_idx = idx;
+    }
+    st.fmax = fmaxf(st.fmax, f);
+    st.thresh = st.fmax * (1.0f - 9.5367431640625e-07f);  // 1 - 2^-20
+    return st;
+}
+
+// Slow path for one 32-column chunk: re-read the chunk from TMEM (warp-collective) and
+// walk it in ascending column order.
+__device__ __noinline__ RowState slow_chunk(RowState st, uint32_t taddr, const float *rsd, const double *sqd,
+                                            int vR, int idx0)
+{
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        float f = fabsf(__int2float_rn((int)v[k]) * rsd[k]);
+        if (f > st.thresh) st = eval_candidate(st, f, (int)v[k], vR, sqd[k], idx0 + k);
+    }
+    return st;
+}
+
+// ---------------------------------------------------------------- the search kernel --
+
+template <int B>
+__global__ void __launch_bounds__(kThreads, 1)
+k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
+              float *__restrict__ part_err, int32_t *__restrict__ part_idx, int n_sb, int n_chunks, int ntiles,
+              int64_t rows_padded, int32_t *__restrict__ dump, int64_t dump_ld, volatile int *status,
+              uint32_t lbo_bytes_a, uint32_t sbo_bytes_a, uint32_t lbo_bytes_b, uint32_t sbo_bytes_b)
+{
+    using C = Cfg<B>;
+    using L = Lay<B>;
+    constexpr int NSTAGE = C::NSTAGE;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [A super-block][NSTAGE domain tiles][barriers]
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + L::A_SB_BYTES;
+    uint64_t *bars = (uint64_t *)(sB + NSTAGE * L::B_TILE_BYTES);
+    // barrier map
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR_B_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto BAR_B_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+    auto BAR_T_FULL = [&](int q) { return bar0 + 8u * (2 * NSTAGE + q); };
+    auto BAR_T_EMPTY = [&](int q) { return bar0 + 8u * (2 * NSTAGE + kAccs + q); };
+    const uint32_t BAR_A_FULL = bar0 + 8u * (2 * NSTAGE + 2 * kAccs);
+    const uint32_t BAR_A_EMPTY = BAR_A_FULL + 8u;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * NSTAGE + 2 * kAccs + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NSTAGE; s++) {
+            mbar_init(BAR_B_FULL(s), 1);
+            mbar_init(BAR_B_EMPTY(s), kEpiWarps);
+        }
+        for (int q = 0; q < kAccs; q++) {
+            mbar_init(BAR_T_FULL(q), 1);
+            mbar_init(BAR_T_EMPTY(q), kEpiWarps / kAccs);
+        }
+        mbar_init(BAR_A_FULL, 1);
+        mbar_init(BAR_A_EMPTY, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_units = n_sb * n_chunks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                int sb = u / n_chunks, ch = u % n_chunks;
+                int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
+                mbar_wait(BAR_A_EMPTY, a_phase ^ 1, status, 1);
+                mbar_expect_tx(BAR_A_FULL, L::A_SB_BYTES);
+                bulk_g2s(smem_u32(sA), opA + (int64_t)sb * L::A_SB_BYTES, L::A_SB_BYTES, BAR_A_FULL);
+                for (int t = t0; t < t1; t++) {
+                    mbar_wait(BAR_B_EMPTY(stage), phase ^ 1, status, 2);
+                    mbar_expect_tx(BAR_B_FULL(stage), L::B_TILE_BYTES);
+                    bulk_g2s(smem_u32(sB + stage * L::B_TILE_BYTES), opB + (int64_t)t * L::B_TILE_BYTES,
+                             L::B_TILE_BYTES, BAR_B_FULL(stage));
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                a_phase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0, t_phase = 0;  // t_phase: bit q
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                int ch = u % n_chunks;
+                int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
+                mbar_wait(BAR_A_FULL, a_phase, status, 3);
+                for (int t = t0; t < t1; t++) {
+                    mbar_wait(BAR_B_FULL(stage), phase, status, 4);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(sB + stage * L::B_TILE_BYTES);
+#pragma unroll
+                    for (int q = 0; q < kAccs; q++) {
+                        mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ 1, status, 5);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(sA) + q * L::A_BLOCK_BYTES;
+#pragma unroll
+                        for (int s = 0; s < C::NS; s++) {
+                            uint64_t ad = make_desc(a_addr + C::amap(s) * 256, lbo_bytes_a, sbo_bytes_a);
+                            uint64_t bd = make_desc(b_addr + s * 256, lbo_bytes_b, sbo_bytes_b);
+                            tc_mma_i8(tmem_base + q * kTileN, ad, bd, kIdesc, s > 0 ? 1u : 0u);
+                        }
+                        tc_commit(BAR_T_FULL(q));
+                        t_phase ^= 1u << q;
+                    }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(BAR_A_EMPTY);  // every MMA that reads this A super-block has completed
+                a_phase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int e = warp - 4;
+        const int q = e >> 2, lq = e & 3;  // lq == warp % 4: the TMEM lane quarter this warp may read
+        const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16) + q * kTileN;
+        uint32_t stage = 0, phase = 0, tf_phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            int sb = u / n_chunks, ch = u % n_chunks;
+            int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
+            const int64_t row = (int64_t)sb * kRowsPerSB + q * kBlockM + lq * 32 + lane;
+            const int vR = vRarr[row];
+            RowState st;
+            st.best_err = 10000000.0f;  // FC:615
+            st.best_idx = 0;
+            st.fmax = -1.0f;
+            // vR == 0: every candidate scores error 0, the first one wins (FC:677-678, FC:627)
+            st.thresh = (vR == 0) ? __int_as_float(0x7f800000) : -1.0f;
+            for (int t = t0; t < t1; t++) {
+                mbar_wait(BAR_B_FULL(stage), phase, status, 6);
+                mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
+                tc_fence_after();
+                const uint8_t *tile = sB + stage * L::B_TILE_BYTES;
+                const float *rsd = (const float *)(tile + L::B_OP_BYTES);
+                const double *sqd = (const double *)(tile + L::B_OP_BYTES + kTileN * 4);
+#pragma unroll 1
+                for (int c = 0; c < kTileN / 32; c++) {
+                    uint32_t v[32];
+                    tmem_ld32(t_lane + c * 32, v);
+                    tmem_ld_wait();
+                    float m = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) {
+                        float4 s4 = *(const float4 *)(rsd + c * 32 + k);
+                        float f0 = __int2float_rn((int)v[k + 0]) * s4.x;
+                        float f1 = __int2float_rn((int)v[k + 1]) * s4.y;
+                        float f2 = __int2float_rn((int)v[k + 2]) * s4.z;
+                        float f3 = __int2float_rn((int)v[k + 3]) * s4.w;
+                        m = fmaxf(fmaxf(m, fabsf(f0)), fabsf(f1));
+                        m = fmaxf(fmaxf(m, fabsf(f2)), fabsf(f3));
+                    }
+                    if (dump) {
+#pragma unroll
+                        for (int k = 0; k < 32; k++) dump[row * dump_ld + (int64_t)t * kTileN + c * 32 + k] = (int)v[k];
+                    }
+                    if (__any_sync(0xffffffffu, m > st.thresh))
+                        st = slow_chunk(st, t_lane + c * 32, rsd + c * 32, sqd + c * 32, vR, t * kTileN + c * 32);
+                }
+                // accumulator q and the tile's scales are consumed
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(BAR_T_EMPTY(q));
+                    mbar_arrive(BAR_B_EMPTY(stage));
+                }
+                tf_phase ^= 1;
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            part_err[(int64_t)ch * rows_padded + row] = st.best_err;
+            part_idx[(int64_t)ch * rows_padded + row] = st.best_idx;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// Merge per-chunk winners in ascending chunk (= ascending domain index) order with the
+// reference's strict < (FC:627), and store the window-local index (== codebook index,
+// the window is the whole pool).
+__global__ void k_umma_merge(const float *__restrict__ part_err, const int32_t *__restrict__ part_idx, int n_chunks,
+                             int64_t rows_padded, int64_t rows, int32_t *__restrict__ best, int64_t j0)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    float be = part_err[i];
+    int bi = part_idx[i];
+    for (int c = 1; c < n_chunks; c++) {
+        float e = part_err[(int64_t)c * rows_padded + i];
+        if (e < be) {
+            be = e;
+            bi = part_idx[(int64_t)c * rows_padded + i];
+        }
+    }
+    best[j0 + i] = bi;
+}
+
+inline int64_t pad_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+template <int B>
+size_t opA_bytes_t(int64_t rows)
+{
+    int64_t rp = pad_up(rows, kRowsPerSB);
+    // [A blobs][vR s32][part_err f32 x 8 chunks][part_idx s32 x 8 chunks]
+    return (size_t)(rp / kRowsPerSB) * Lay<B>::A_SB_BYTES + (size_t)rp * 4 + (size_t)rp * 8 * 8 + 1024;
+}
+
+template <int B>
+int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s, const char **err,
+             int32_t *dump, int64_t dump_ld, int *status_dev, int variant, cudaEvent_t k0 = nullptr,
+             cudaEvent_t k1 = nullptr)
+{
+    using L = Lay<B>;
+    int64_t rows = j1 - j0;
+    if (rows <= 0) return 0;
+    int64_t rp = pad_up(rows, kRowsPerSB);
+    int n_sb = (int)(rp / kRowsPerSB);
+    int ntiles = (int)((g.ND + kTileN - 1) / kTileN);
+    // split the domain sweep so that the unit count fills whole waves of num_sms CTAs
+    int n_chunks = 1;
+    {
+        double best_eff = 0;
+        for (int c = 1; c <= 8 && c <= ntiles; c++) {
+            int64_t units = (int64_t)n_sb * c;
+            int64_t waves = (units + num_sms - 1) / num_sms;
+            double eff = (double)units / (double)(waves * num_sms);
+            if (eff > best_eff + 0.02) { best_eff = eff; n_chunks = c; }
+        }
+    }
+    uint8_t *opA = w.opA;
+    int32_t *vR = (int32_t *)(opA + (size_t)n_sb * L::A_SB_BYTES);
+    float *part_err = (float *)(vR + rp);
+    int32_t *part_idx = (int32_t *)(part_err + rp * 8);
+    int launches = 0;
+    k_umma_pack_domains<B><<<(unsigned)(((int64_t)ntiles * kTileN + 127) / 128), 128, 0, s>>>(w.dec, w.dsum, w.dsq, w.opB, g, ntiles);
+    k_umma_pack_ranges<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
+    launches += 2;
+    cudaError_t ce = cudaFuncSetAttribute(k_umma_search<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
+    if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
+    int n_units = n_sb * n_chunks;
+    int grid = n_units < num_sms ? n_units : num_sms;
+    uint32_t lbo_a = 128, sbo_a = L::SBO_A, lbo_b = 128, sbo_b = L::SBO_B;
+    if (variant == 1) { lbo_a = L::SBO_A; sbo_a = 128; lbo_b = L::SBO_B; sbo_b = 128; }  // probe only
+    if (k0) cudaEventRecord(k0, s);
+    k_umma_search<B><<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, part_err, part_idx, n_sb, n_chunks, ntiles,
+                                                           rp, dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
+    if (k1) cudaEventRecord(k1, s);
+    k_umma_merge<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(part_err, part_idx, n_chunks, rp, rows, w.best, j0);
+    launches += 2;
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
+    return launches;
+}
+
+}  // namespace
+
+bool umma_applicable(const Geom &g)
+{
+    return g.C == 1 && (g.B == 8 || g.B == 4) && g.wk == g.dpw && g.wk == g.dph;
+}
+
+size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1)
+{
+    return g.B == 8 ? opA_bytes_t<8>(j1 - j0) : opA_bytes_t<4>(j1 - j0);
+}
+
+size_t umma_opB_bytes(const Geom &g)
+{
+    int64_t ntiles = (g.ND + kTileN - 1) / kTileN;
+    return (size_t)ntiles * (g.B == 8 ? Lay<8>::B_TILE_BYTES : Lay<4>::B_TILE_BYTES);
+}
+
+int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s,
+                       const char **err, cudaEvent_t k0, cudaEvent_t k1)
+{
+    if (g.B == 8) return launch_t<8>(w, g, j0, j1, num_sms, s, err, nullptr, 0, nullptr, 0, k0, k1);
+    return launch_t<4>(w, g, j0, j1, num_sms, s, err, nullptr, 0, nullptr, 0, k0, k1);
+}
+
+// Debug entry used by tools/umma_probe: also dumps the raw accumulators (kov) of every
+// (row, domain) pair, and lets the probe pick the descriptor variant.
+int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s,
+                             const char **err, int32_t *dump, int64_t dump_ld, int *status_dev, int variant)
+{
+    if (g.B == 8) return launch_t<8>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant);
+    return launch_t<4>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant);
+}
+
+}  // namespace fic

@@ -1,0 +1,151 @@
+/*
+ * fic_b200.h -- C ABI of libfic_b200.so, the B200-native (sm_100a) drop-in for the
+ * encode / decode hot path of LariWa/Fractal-Image-Compression.
+ *
+ * The reference (Java, src/bvk_ss19/FractalCompression.java = "FC") has no FFI seam of
+ * its own; this header is the seam SURVEY.md section 8(b) cuts: the bodies of the two
+ * range-block driver loops and of the decoder sweep move behind these calls, while
+ * image loading (RasterImage.java), grey/RGB dispatch (FC:54-59) and the stream
+ * writer stay on the host side (Java through Panama FFM / JNI, see INTEGRATION.md;
+ * C++ and Python mirrors live in fractal-image-compression_b200/host/).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  The caller owns every host buffer; the library
+ *     owns device memory, streams and events inside the opaque handle.
+ *   - `argb` is the reference's pixel format: int32 0xAARRGGBB, scanline order,
+ *     W*H entries (RasterImage.java:22).
+ *   - Codes are returned in the reference's own layout: `info` is
+ *     FractalCompression.imageInfo (float[NR][3] = {window-local index, a, b}, FC:124,
+ *     FC:642) or imageInfoRGB (float[NR][5] = {index, a, bR, bG, bB}, FC:185, FC:733);
+ *     `qcodes` (optional, may be NULL) holds the ints writeData would emit for the same
+ *     rows (FC:242-244 / FC:250-254), so the Java side needs no float work.
+ *   - Range blocks j are in raster order (FC:123-158); every encode entry takes a
+ *     half-open range-block interval [range_begin, range_end) so that one image can be
+ *     sharded over GPUs / processes by range rows.  Outputs are indexed by absolute j;
+ *     rows outside the interval are left untouched.
+ *   - Every entry returns FIC_OK (0) or a negative FIC_E_* code; fic_last_error()
+ *     gives the message.  The reference signals all failures as `throws Exception`
+ *     (FC:54, FC:109, FC:171, FC:230, FC:356, FC:547); argument sets on which the
+ *     reference would throw (ArithmeticException for B < 4 at FC:1019,
+ *     ArrayIndexOutOfBounds for W % B != 0 at FC:124-126 or widthKernel > pool width at
+ *     FC:93-96) are rejected with FIC_E_ARG, not "fixed".
+ *   - One in-flight call per handle; distinct handles are independent.
+ *   - There is no CPU fallback: without a CUDA device every compute entry fails with
+ *     FIC_E_CUDA.
+ */
+#ifndef FIC_B200_H
+#define FIC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FIC_OK 0
+#define FIC_E_ARG (-1)     /* arguments the reference would throw on              */
+#define FIC_E_CUDA (-2)    /* CUDA runtime / launch failure, or no device         */
+#define FIC_E_NOMEM (-3)   /* device or host allocation failed                    */
+#define FIC_E_STREAM (-4)  /* malformed .run stream                               */
+#define FIC_E_INTERNAL (-5)
+
+/* Search engine selection (fic_set_option(FIC_OPT_ENGINE, ...)). */
+#define FIC_ENGINE_AUTO 0   /* tcgen05 fused search when the window is the whole pool */
+#define FIC_ENGINE_DIRECT 1 /* direct (CUDA-core) windowed search for every window    */
+#define FIC_ENGINE_UMMA 2   /* force the tcgen05 search; FIC_E_ARG if not applicable  */
+
+#define FIC_OPT_ENGINE 1
+
+typedef struct fic_handle fic_handle;
+
+/* Per-call device timings in milliseconds (CUDA events on the handle's stream). */
+typedef struct fic_timings {
+    float h2d_ms;     /* host -> device copies                                   */
+    float pool_ms;    /* unpack + 2x decimation + per-domain / per-range stats   */
+    float search_ms;  /* range x domain search (direct or tcgen05) incl. operand packing */
+    float kernel_ms;  /* the dominant search kernel alone (k_umma_search or k_search_direct_*) */
+    float solve_ms;   /* winner -> (a, b) solve + quantisation                   */
+    float d2h_ms;     /* device -> host copies                                   */
+    float total_ms;
+    int engine;       /* FIC_ENGINE_DIRECT or FIC_ENGINE_UMMA actually used      */
+    int launches;     /* kernels launched by this call                           */
+    double search_evals; /* range x candidate evaluations done by the search     */
+} fic_timings;
+
+/* ---- lifetime ---------------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device` (cudaSetDevice ordinal). */
+int fic_create(int device, fic_handle **out);
+void fic_destroy(fic_handle *h);
+const char *fic_last_error(const fic_handle *h); /* h may be NULL: last create error */
+const char *fic_version(void);
+int fic_set_option(fic_handle *h, int option, int value);
+/* Run subsequent calls on a caller-provided CUDA stream (cudaStream_t), or NULL for
+ * the handle's own stream.  Used by the torch.distributed host so that library work
+ * orders after the NCCL broadcast without a device-wide sync. */
+int fic_set_stream(fic_handle *h, void *cuda_stream);
+int fic_get_timings(const fic_handle *h, fic_timings *out);
+
+/* ---- geometry (pure host helpers, no device needed) -------------------------- */
+
+/* NR = (W/B)*(H/B), pool size ND = (2W/B-3)*(2H/B-3) (FC:111-116, FC:1022); returns
+ * FIC_E_ARG on argument sets the reference would throw on. */
+int fic_geometry(int W, int H, int B, int wk, int64_t *n_ranges, int64_t *n_domains);
+
+/* ---- encode: replaces FC:119 + FC:125-159 (grey) and FC:181 + FC:186-215 (RGB) */
+
+int fic_encode_grey(fic_handle *h, const int32_t *argb, int W, int H, int B, int wk,
+                    int64_t range_begin, int64_t range_end, float *info, int32_t *qcodes);
+int fic_encode_rgb(fic_handle *h, const int32_t *argb, int W, int H, int B, int wk,
+                   int64_t range_begin, int64_t range_end, float *info, int32_t *qcodes);
+
+/* Same, with the image already resident in device memory as 8-bit planes
+ * (grey: red channel, W*H bytes; RGB: R, G, B planes, 3*W*H bytes) and device output
+ * buffers (float[NR][3|5], int32[NR][3|5]; either may be NULL).  Asynchronous on the
+ * handle's stream; fic_sync() waits.  This is the entry the multi-GPU host uses after
+ * the NCCL image broadcast. */
+int fic_encode_planes_dev(fic_handle *h, const uint8_t *d_planes, int is_rgb, int W, int H,
+                          int B, int wk, int64_t range_begin, int64_t range_end,
+                          float *d_info, int32_t *d_qcodes);
+int fic_sync(fic_handle *h);
+
+/* ---- decode: replaces FC:378-418 / FC:455-505 (after header + code parsing) --- */
+
+/* `qcodes` are the ints read from the stream after the 5-int header (FC:370-376 /
+ * FC:444-453), NR*3 (grey) or NR*5 (RGB).  *avg_error is FractalCompression.avgError:
+ * read on entry (the reference never resets it between decodes, FC:20) and written on
+ * exit; *iterations receives the sweep count (<= max_iters; the reference uses 50). */
+int fic_decode(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int32_t *qcodes,
+               int max_iters, int32_t *argb_out, float *avg_error, int *iterations);
+
+/* getBestGeneratedCollage[RGB] (FC:269-347): one decode step from the source image
+ * with the unquantised codes.  Like the reference it rewrites info[.][0] in place from
+ * window-local to codebook index (FC:273). */
+int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, int B, int wk,
+                float *info, int32_t *argb_out);
+
+/* ---- domain pool inspection (tests / debugging; not on the hot path) ---------- */
+
+/* Runs the pool builder only and returns the 2x-decimated plane(s) (W/2*H/2 bytes per
+ * channel), per-domain integer sums (ND per channel) and sums of squares. Any output
+ * may be NULL. */
+int fic_build_pool(fic_handle *h, const int32_t *argb, int is_rgb, int W, int H, int B,
+                   uint8_t *decimated, int32_t *dom_sum, int32_t *dom_sumsq);
+
+/* ---- .run stream (writeData FC:230-261, header parse FC:357-363, FC:548) ------ */
+
+size_t fic_stream_size(int is_rgb, int W, int H, int B);
+/* Serialises header + qcodes big-endian exactly as DataOutputStream.writeInt does. */
+int fic_stream_write(int is_rgb, int W, int H, int B, int wk, const int32_t *qcodes,
+                     uint8_t *out, size_t out_bytes);
+/* Parses the header; *qcodes_off is the byte offset of the first code. */
+int fic_stream_read_header(const uint8_t *stream, size_t nbytes, int *is_rgb, int *W, int *H,
+                           int *B, int *wk, size_t *qcodes_off);
+/* Copies the big-endian codes of a stream into host-endian ints (NR*3 or NR*5). */
+int fic_stream_read_codes(const uint8_t *stream, size_t nbytes, int32_t *qcodes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIC_B200_H */

@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+inputs, bit for bit -- codes are integer / index work, and the float a, b are produced by
+the same IEEE operations as the reference's."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, to_argb_grey, to_argb_rgb
+
+pytestmark = pytest.mark.gpu
+
+
+def q_from_stream(s, S):
+    return np.frombuffer(s[20:], ">i4").astype(np.int32).reshape(-1, S)
+
+
+def assert_codes_equal(info, q, oinfo, ostream, S):
+    # float codes: compare bit patterns (NaN == NaN on flat winners)
+    assert info.view(np.uint32).tobytes() == oinfo.view(np.uint32).tobytes()
+    assert (q == q_from_stream(ostream, S)).all()
+
+
+# ---------------------------------------------------------------- K1 pool builder
+
+@pytest.mark.parametrize("name,B,rgb", [("lena_grey", 8, False), ("lena_grey", 4, False), ("lena_grey", 16, False),
+                                        ("lena64", 8, False), ("lena_colored", 8, True), ("lena_colored", 4, True)])
+def test_pool_builder(handle, oracle, request, name, B, rgb):
+    img = request.getfixturevalue(name)
+    dec, s1, s2 = handle.build_pool(img, B, rgb)
+    sc = oracle.scale_image(img, rgb=rgb).view(np.uint32)
+    planes = [(sc >> 16) & 0xFF, (sc >> 8) & 0xFF, sc & 0xFF] if rgb else [(sc >> 16) & 0xFF]
+    for c, p in enumerate(planes):
+        assert (dec[c] == p).all()
+    pool, mean, var = oracle.create_codebook(img, B, rgb=rgb)
+    n = B * B
+    if not rgb:
+        assert (s1[0] == pool.sum(1)).all() and (s2[0] == (pool.astype(np.int64) ** 2).sum(1)).all()
+        m = s1[0] // n
+        assert (m == mean).all()
+        assert ((s2[0] - 2 * m * s1[0] + n * m * m).astype(np.float32) == var).all()
+    else:
+        u = pool.view(np.uint32)
+        for c, sh in enumerate((16, 8, 0)):
+            ch = ((u >> sh) & 0xFF).astype(np.int64)
+            assert (s1[c] == ch.sum(1)).all() and (s2[c] == (ch ** 2).sum(1)).all()
+            m = s1[c] // n
+            assert (m == mean[:, c + 1]).all()
+            assert ((s2[c] - 2 * m * s1[c] + n * m * m).astype(np.float32) == var[:, c]).all()
+
+
+# ---------------------------------------------------------------- encode, reference window sizes
+
+@pytest.mark.parametrize("name,B,wk", [("lena_grey", 8, 2), ("lena_grey", 8, 4), ("lena_grey", 8, 16),
+                                       ("lena_grey", 16, 16), ("lena_grey", 4, 16), ("lena_grey", 4, 2),
+                                       ("lena64", 8, 2), ("lena64", 4, 8), ("lena64", 16, 2), ("lena64", 16, 5)])
+def test_encode_grey_windowed(handle, oracle, request, name, B, wk):
+    img = request.getfixturevalue(name)
+    H, W = img.shape
+    info, q = handle.encode(img, B, wk, rgb=False)
+    oinfo = oracle.encode(img, B, wk, nthreads=4)
+    assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, W, H, B, wk), 3)
+
+
+@pytest.mark.parametrize("B,wk", [(8, 2), (4, 4), (16, 2), (8, 7)])
+def test_encode_rgb(handle, oracle, lena_colored, B, wk):
+    info, q = handle.encode(lena_colored, B, wk, rgb=True)
+    oinfo = oracle.encode(lena_colored, B, wk, rgb=True, nthreads=4)
+    assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, 256, 256, B, wk, rgb=True), 5)
+
+
+def test_rgb_stream_equals_the_references_own_file(fic, handle, lena_colored):
+    # unknown.run is the reference's own output for LenaColored.jpg at B=8, wk=2
+    ref = open(os.path.join(GOLD, "unknown_run.bin"), "rb").read()
+    _, q = handle.encode(lena_colored, 8, 2, rgb=True)
+    assert fic.stream_write(q, 256, 256, 8, 2, rgb=True) == ref
+
+
+def test_golden_streams(fic, handle, golden, lena_grey, lena64, lena_colored):
+    imgs = {"lena_grey": lena_grey, "lena64": lena64, "lena_colored": lena_colored}
+    for name, g in golden["oracle_streams"].items():
+        img = imgs[name.rsplit("_b", 1)[0]]
+        _, q = handle.encode(img, g["B"], g["wk"], rgb=g["rgb"])
+        s = fic.stream_write(q, g["W"], g["H"], g["B"], g["wk"], rgb=g["rgb"])
+        assert hashlib.sha256(s).hexdigest() == g["stream_sha256"], name
+
+
+# ---------------------------------------------------------------- full pool: direct and tcgen05 engines
+
+FULL = [("lena64", 8, 13), ("lena64", 4, 29), ("lena_grey", 8, 61), ("lena_grey", 4, 125), ("lena_grey", 16, 29)]
+
+
+@pytest.mark.parametrize("name,B,wk", FULL)
+def test_full_pool_direct(fic, handle, oracle, request, name, B, wk):
+    img = request.getfixturevalue(name)
+    H, W = img.shape
+    handle.set_engine(fic.FIC_ENGINE_DIRECT)
+    try:
+        info, q = handle.encode(img, B, wk, rgb=False)
+    finally:
+        handle.set_engine(fic.FIC_ENGINE_AUTO)
+    oinfo = oracle.encode(img, B, wk, nthreads=8)
+    assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, W, H, B, wk), 3)
+
+
+@pytest.mark.parametrize("name,B,wk", [f for f in FULL if f[1] in (4, 8)])
+def test_full_pool_tcgen05(fic, handle, oracle, request, name, B, wk):
+    img = request.getfixturevalue(name)
+    H, W = img.shape
+    handle.set_engine(fic.FIC_ENGINE_UMMA)
+    try:
+        info, q = handle.encode(img, B, wk, rgb=False)
+        assert handle.timings().engine == fic.FIC_ENGINE_UMMA
+    finally:
+        handle.set_engine(fic.FIC_ENGINE_AUTO)
+    oinfo = oracle.encode(img, B, wk, nthreads=8)
+    assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, W, H, B, wk), 3)
+
+
+@pytest.mark.parametrize("kind,B", [("noise", 8), ("structured", 8), ("structured", 4), ("sparse", 8), ("flat", 8)])
+def test_full_pool_tcgen05_synthetic(fic, handle, oracle, kind, B):
+    W = H = 128
+    if kind == "noise":
+        p = fic.synth.noise(W, H, 3)
+    elif kind == "structured":
+        p = fic.synth.structured(W, H, 3)
+    elif kind == "flat":
+        p = np.full((H, W), 77, np.uint8)
+    else:  # flat background + sparse dots: ties and vR == 0 rows everywhere
+        p = np.full((H, W), 100, np.uint8)
+        p[fic.synth.noise(W, H, 9) < 3] = 103
+    img = to_argb_grey(p)
+    wk = 2 * W // B - 3
+    handle.set_engine(fic.FIC_ENGINE_UMMA)
+    try:
+        info, q = handle.encode(img, B, wk, rgb=False)
+    finally:
+        handle.set_engine(fic.FIC_ENGINE_AUTO)
+    oinfo = oracle.encode(img, B, wk, nthreads=8)
+    assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, W, H, B, wk), 3)
+
+
+# ---------------------------------------------------------------- edge cases
+
+def test_flat_image(handle, oracle):
+    img = to_argb_grey(np.full((64, 64), 128, np.uint8))
+    info, q = handle.encode(img, 8, 13, rgb=False)
+    assert (q == 0).all()
+    oinfo = oracle.encode(img, 8, 13)
+    assert info.view(np.uint32).tobytes() == oinfo.view(np.uint32).tobytes()
+
+
+def test_non_square(fic, handle, oracle):
+    # landscape exercises FC:993 (`x + 1 >= image.height`), portrait does not
+    for W, H in [(96, 64), (64, 96), (128, 32)]:
+        p = fic.synth.structured(W, H, 11)
+        img = to_argb_grey(p)
+        for B, wk in [(8, 2), (8, 5), (4, 3)]:
+            info, q = handle.encode(img, B, wk, rgb=False)
+            oinfo = oracle.encode(img, B, wk)
+            assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, W, H, B, wk), 3)
+    rgbp = np.stack([fic.synth.noise(96, 64, s) for s in (1, 2, 3)], -1)
+    img = to_argb_rgb(rgbp)
+    info, q = handle.encode(img, 8, 3, rgb=True)
+    oinfo = oracle.encode(img, 8, 3, rgb=True)
+    assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, 96, 64, 8, 3, rgb=True), 5)
+
+
+def test_range_slices_compose(fic, handle, lena_grey):
+    full_info, full_q = handle.encode(lena_grey, 8, 61, rgb=False)
+    info = np.zeros_like(full_info)
+    q = np.zeros_like(full_q)
+    for j0, j1 in [(0, 512), (512, 544), (544, 1024)]:   # row slices, as the multi-GPU host shards
+        handle.encode(lena_grey, 8, 61, rgb=False, range_begin=j0, range_end=j1, info=info, q=q)
+    assert info.view(np.uint32).tobytes() == full_info.view(np.uint32).tobytes() and (q == full_q).all()
+
+
+def test_rejected_arguments(fic, handle):
+    for W, H, B, wk in [(64, 64, 2, 1), (60, 64, 8, 2), (64, 64, 8, 14), (64, 64, 8, 0), (8, 8, 8, 1), (64, 64, 32, 1)]:
+        with pytest.raises(fic.FicError) as e:
+            handle.encode(np.zeros((H, W), np.int32), B, wk, rgb=False)
+        assert e.value.code == fic._lib.FIC_E_ARG
+
+
+# ---------------------------------------------------------------- decoder / collage
+
+@pytest.mark.parametrize("fname", ["lena_grey_b8_wk2.run", "lena64_b8_full.run", "lena64_b4_full.run", "unknown_run.bin"])
+def test_decode_golden_streams(fic, handle, oracle, fname):
+    s = open(os.path.join(GOLD, fname), "rb").read()
+    rgb, W, H, B, wk, q = fic.stream_read(s)
+    img, avg, it = handle.decode(q, W, H, B, wk, rgb)
+    oimg, oavg, oit = oracle.decode(s)
+    assert it == oit and np.float32(avg) == np.float32(oavg)
+    assert (img == oimg).all()
+
+
+def test_decode_avg_error_labels(fic, handle, golden, lena_grey):
+    # the reference's own published numbers: Animation.gif "MSE" labels
+    for B, wk, label in golden["gif_avg_error"]:
+        _, q = handle.encode(lena_grey, B, wk, rgb=False)
+        _, avg, _ = handle.decode(q, 256, 256, B, wk, False)
+        assert np.float32(label) == np.float32(avg)
+
+
+def test_decode_carry_and_iteration_cap(fic, handle, oracle):
+    s = open(os.path.join(GOLD, "lena_grey_b8_wk2.run"), "rb").read()
+    rgb, W, H, B, wk, q = fic.stream_read(s)
+    # FractalCompression.avgError is static and never reset (FC:20): carry-in from a previous decode
+    img, avg, it = handle.decode(q, W, H, B, wk, rgb, avg_error=0.5863342)
+    oimg, oavg, oit = oracle.decode(s, avg_error_in=0.5863342)
+    assert it == oit and np.float32(avg) == np.float32(oavg) and (img == oimg).all()
+    # iteration cap: stop after 3 sweeps without convergence -> avgError is the unconverged float sum / (W*H)
+    img3, avg3, it3 = handle.decode(q, W, H, B, wk, rgb, max_iters=3)
+    assert it3 == 3 and avg3 >= 1
+
+
+def test_collage(fic, handle, oracle, lena_grey, lena_colored):
+    for img, B, wk, rgb in [(lena_grey, 8, 2, False), (lena_grey, 8, 61, False), (lena_colored, 8, 2, True)]:
+        info, _ = handle.encode(img, B, wk, rgb=rgb)
+        oinfo = info.copy()
+        got = handle.collage(img, info, B, wk, rgb)
+        want = oracle.collage(img, oinfo, B, wk, rgb=rgb)
+        assert (got == want).all()
+
+
+def test_facade_roundtrip(fic, oracle, lena_grey):
+    FC = fic.FractalCompression
+    FC.blockgroesse, FC.widthKernel, FC.avgError = 8, 4, np.float32(0)
+    sink = fic.ByteSink()
+    collage = FC.encode(fic.RasterImage.from_argb(lena_grey), sink)
+    stream = sink.getvalue()
+    oinfo = oracle.encode(lena_grey, 8, 4)
+    assert stream == oracle.write_data(oinfo, 256, 256, 8, 4)
+    import io
+
+    dec = FC.decode(io.BytesIO(stream))
+    oimg, oavg, _ = oracle.decode(stream)
+    assert (dec.argb == oimg).all() and FC.getAvgError() == oavg
+    assert (collage.argb == oracle.collage(lena_grey, oinfo.copy(), 8, 4)).all()

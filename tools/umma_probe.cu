@@ -1,0 +1,205 @@
+// umma_probe -- development probe for the tcgen05 fused search (not part of the product).
+//
+//   umma_probe <mode> <B> <W> [variant] [pattern]
+//     mode   check : dump every accumulator (kov) and compare with a CPU integer dot
+//                    product, then compare winners with the direct CUDA-core search
+//            time  : no dump; time the fused search and the direct search, compare winners
+//     B      4 | 8       W = H, multiple of B
+//     variant 0 = descriptor strides as designed (LBO 128, SBO KS*256), 1 = swapped
+//     pattern 0 = noise, 1 = structured, 2 = flat + sparse dots (tie-heavy)
+//
+// Runs each experiment in its own process so that a faulting variant cannot poison the
+// next one; every mbarrier wait in the kernel is bounded (trap + status code).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../fractal-image-compression_b200/csrc/fic_device.cuh"
+
+using namespace fic;
+
+#define CK(x)                                                                                  \
+    do {                                                                                       \
+        cudaError_t e_ = (x);                                                                  \
+        if (e_ != cudaSuccess) {                                                               \
+            printf("CUDA error %s at %s:%d (%s)\n", cudaGetErrorString(e_), __FILE__, __LINE__, #x); \
+            if (g_status) printf("kernel status code: %d\n", *g_status);                      \
+            exit(3);                                                                           \
+        }                                                                                      \
+    } while (0)
+
+static volatile int *g_status = nullptr;
+
+static uint32_t lowbias32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+static int tri(int v, int period)
+{
+    int p = ((v % period) + period) % period;
+    int half = period / 2;
+    int t = p < half ? p : period - p;
+    return t * 255 / half;
+}
+
+static void make_image(std::vector<uint8_t> &img, int W, int H, int pattern, uint32_t seed)
+{
+    img.resize((size_t)W * H);
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            uint32_t h = lowbias32((uint32_t)(y * W + x) + seed * 0x9E3779B9u);
+            int v;
+            if (pattern == 0) v = h >> 24;
+            else if (pattern == 1) {
+                v = (tri(x + (int)seed, 97) + tri(3 * y + x, 211) + tri((x * y) / 64, 151)) / 3 + (int)((h >> 28)) - 8;
+                v = v < 0 ? 0 : (v > 255 ? 255 : v);
+            } else {
+                v = 100 + ((h & 0xff) == 0 ? (int)((h >> 8) & 3) + 1 : 0);
+            }
+            img[(size_t)y * W + x] = (uint8_t)v;
+        }
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 4) {
+        printf("usage: umma_probe check|time B W [variant] [pattern]\n");
+        return 2;
+    }
+    bool check = !strcmp(argv[1], "check");
+    int B = atoi(argv[2]), W = atoi(argv[3]);
+    int variant = argc > 4 ? atoi(argv[4]) : 0;
+    int pattern = argc > 5 ? atoi(argv[5]) : 0;
+    int H = W;
+    Geom g;
+    const char *why = "";
+    int wk = 2 * (W / B) - 3;
+    if (make_geom(W, H, B, wk, 0, &g, &why)) { printf("bad geometry: %s\n", why); return 2; }
+    if (!umma_applicable(g)) { printf("umma not applicable\n"); return 2; }
+    printf("probe mode=%s B=%d W=%d variant=%d pattern=%d NR=%lld ND=%lld\n", argv[1], B, W, variant, pattern,
+           (long long)g.NR, (long long)g.ND);
+
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    printf("device: %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+    int *status_h = nullptr, *status_d = nullptr;
+    CK(cudaHostAlloc((void **)&status_h, 64, cudaHostAllocMapped));
+    *status_h = 0;
+    CK(cudaHostGetDevicePointer((void **)&status_d, status_h, 0));
+    g_status = status_h;
+
+    std::vector<uint8_t> img;
+    make_image(img, W, H, pattern, 1);
+    Work w;
+    CK(cudaMalloc(&w.src, (size_t)W * H));
+    CK(cudaMalloc(&w.dec, (size_t)g.sw * g.sh));
+    CK(cudaMalloc(&w.dsum, 4 * g.ND));
+    CK(cudaMalloc(&w.dsq, 4 * g.ND));
+    CK(cudaMalloc(&w.rsum, 4 * g.NR));
+    CK(cudaMalloc(&w.best, 4 * g.NR));
+    CK(cudaMalloc(&w.opA, umma_opA_bytes(g, 0, g.NR)));
+    CK(cudaMalloc(&w.opB, umma_opB_bytes(g)));
+    CK(cudaMemcpy(w.src, img.data(), (size_t)W * H, cudaMemcpyHostToDevice));
+    cudaStream_t s;
+    CK(cudaStreamCreate(&s));
+    launch_decimate(w.src, w.dec, g, s);
+    launch_domain_stats(w.dec, w.dsum, w.dsq, g, s);
+    launch_range_stats(w.src, w.rsum, g, s);
+    CK(cudaStreamSynchronize(s));
+
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float ms_direct = 0, ms_umma = 0;
+
+    // reference winners: direct CUDA-core search
+    std::vector<int32_t> best_direct(g.NR), best_umma(g.NR);
+    CK(cudaEventRecord(e0, s));
+    launch_search_direct(w, g, 0, g.NR, s);
+    CK(cudaEventRecord(e1, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&ms_direct, e0, e1));
+    CK(cudaMemcpy(best_direct.data(), w.best, 4 * g.NR, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(w.best, 0xff, 4 * g.NR));
+
+    int ntiles = (int)((g.ND + 127) / 128);
+    int64_t dump_ld = (int64_t)ntiles * 128;
+    int64_t rp = (g.NR + 511) / 512 * 512;
+    int32_t *dump = nullptr;
+    if (check) {
+        CK(cudaMalloc(&dump, (size_t)rp * dump_ld * 4));
+        CK(cudaMemset(dump, 0x7f, (size_t)rp * dump_ld * 4));
+    }
+    const char *err = "";
+    int reps = check ? 1 : 3;
+    for (int r = 0; r < reps; r++) {
+        CK(cudaEventRecord(e0, s));
+        int n = launch_search_umma_debug(w, g, 0, g.NR, prop.multiProcessorCount, s, &err, dump, dump_ld, status_d, variant);
+        if (n < 0) { printf("launch failed: %s\n", err); return 3; }
+        CK(cudaEventRecord(e1, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaEventElapsedTime(&ms_umma, e0, e1));
+        printf("umma search (pack + search + merge) run %d: %.3f ms   status=%d\n", r, ms_umma, *status_h);
+    }
+    CK(cudaMemcpy(best_umma.data(), w.best, 4 * g.NR, cudaMemcpyDeviceToHost));
+    double evals = (double)g.NR * (double)g.ND;
+    printf("direct search: %.3f ms (%.3e evals/s)   umma: %.3f ms (%.3e evals/s, %.1f%% of 4.5 POPS int8 at 2*B*B ops/eval)\n",
+           ms_direct, evals / (ms_direct * 1e-3), ms_umma, evals / (ms_umma * 1e-3),
+           100.0 * evals * 2 * g.n / (ms_umma * 1e-3) / 4.5e15);
+
+    int rc = 0;
+    if (check) {
+        std::vector<int32_t> hd((size_t)rp * dump_ld);
+        CK(cudaMemcpy(hd.data(), dump, hd.size() * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint8_t> dec((size_t)g.sw * g.sh);
+        CK(cudaMemcpy(dec.data(), w.dec, dec.size(), cudaMemcpyDeviceToHost));
+        long long bad = 0, shown = 0;
+        for (int64_t i = 0; i < g.NR; i++) {
+            int xr = (int)(i % g.rpw), yr = (int)(i / g.rpw);
+            int rs = 0;
+            int r[256];
+            for (int k = 0; k < g.n; k++) {
+                r[k] = img[(size_t)(yr * B + k / B) * W + xr * B + k % B];
+                rs += r[k];
+            }
+            int rmean = rs / g.n;
+            for (int64_t j = 0; j < g.ND; j++) {
+                int gx = (int)(j % g.dpw), gy = (int)(j / g.dpw);
+                int ds = 0, d[256];
+                for (int k = 0; k < g.n; k++) {
+                    d[k] = dec[(size_t)(gy * g.step + k / B) * g.sw + gx * g.step + k % B];
+                    ds += d[k];
+                }
+                int dmean = ds / g.n;
+                int kov = 0;
+                for (int k = 0; k < g.n; k++) kov += (r[k] - rmean) * (d[k] - dmean);
+                int got = hd[(size_t)i * dump_ld + j];
+                if (got != kov) {
+                    bad++;
+                    if (shown < 12) {
+                        printf("  kov mismatch row %lld dom %lld: got %d want %d\n", (long long)i, (long long)j, got, kov);
+                        shown++;
+                    }
+                }
+            }
+        }
+        printf("accumulator check: %lld mismatches of %lld\n", bad, (long long)(g.NR * g.ND));
+        if (bad) rc = 1;
+    }
+    long long diff = 0, shown = 0;
+    for (int64_t i = 0; i < g.NR; i++)
+        if (best_direct[i] != best_umma[i]) {
+            diff++;
+            if (shown++ < 12) printf("  winner mismatch row %lld: direct %d umma %d\n", (long long)i, best_direct[i], best_umma[i]);
+        }
+    printf("winner check: %lld of %lld rows differ\n", diff, (long long)g.NR);
+    if (diff) rc = 1;
+    printf(rc ? "PROBE FAIL\n" : "PROBE PASS\n");
+    return rc;
+}
