@@ -206,7 +206,8 @@ def run_ours(args):
 
     handle = fic.Handle(local)
     handle.set_engine({"auto": fic.FIC_ENGINE_AUTO, "direct": fic.FIC_ENGINE_DIRECT, "umma": fic.FIC_ENGINE_UMMA}[args.engine])
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)   # library work, NCCL ordering and the timing events all use this stream
+    torch.cuda.set_stream(stream)
     handle.set_stream(stream.cuda_stream)
     enc = ShardedEncoder(handle=handle) if world > 1 else None
 

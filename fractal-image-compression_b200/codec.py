@@ -98,7 +98,13 @@ class Handle:
         self._check(self._L.fic_set_option(self._h, _lib.FIC_OPT_ENGINE, int(engine)))
 
     def set_stream(self, cuda_stream: int | None):
-        self._check(self._L.fic_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """None -> the handle's own stream; an integer cudaStream_t otherwise.  torch reports its default
+        stream as 0, which the C ABI reads as "own stream": pass the legacy-default handle instead."""
+        if cuda_stream is None:
+            v = 0
+        else:
+            v = int(cuda_stream) or 1  # cudaStreamLegacy == (cudaStream_t)0x1
+        self._check(self._L.fic_set_stream(self._h, C.c_void_p(v)))
 
     def sync(self):
         self._check(self._L.fic_sync(self._h))

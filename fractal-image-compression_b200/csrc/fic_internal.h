@@ -66,7 +66,8 @@ int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int
                        cudaStream_t s, const char **err, cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr);
 int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms,
                              cudaStream_t s, const char **err, int32_t *dump, int64_t dump_ld,
-                             int *status_dev, int variant);
+                             int *status_dev, int variant, uint32_t dbg = 0, cudaEvent_t k0 = nullptr,
+                             cudaEvent_t k1 = nullptr);
 
 // decoder
 int launch_dequant(const int32_t *d_q, float *d_code, const Geom &g, int unquantised,

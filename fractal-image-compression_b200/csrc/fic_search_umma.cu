@@ -279,6 +279,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle shared-memory matrix descriptor (PTX "matrix descriptor";
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
               float *__restrict__ part_err, int32_t *__restrict__ part_idx, int n_sb, int n_chunks, int ntiles,
               int64_t rows_padded, int32_t *__restrict__ dump, int64_t dump_ld, volatile int *status,
-              uint32_t lbo_bytes_a, uint32_t sbo_bytes_a, uint32_t lbo_bytes_b, uint32_t sbo_bytes_b)
+              uint32_t lbo_bytes_a, uint32_t sbo_bytes_a, uint32_t lbo_bytes_b, uint32_t sbo_bytes_b, uint32_t dbg)
 {
     using C = Cfg<B>;
     using L = Lay<B>;
@@ -469,15 +475,19 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 const uint8_t *tile = sB + stage * L::B_TILE_BYTES;
                 const float *rsd = (const float *)(tile + L::B_OP_BYTES);
                 const double *sqd = (const double *)(tile + L::B_OP_BYTES + kTileN * 4);
+                const uint32_t rsd_s = smem_u32(rsd);
 #pragma unroll 1
                 for (int c = 0; c < kTileN / 32; c++) {
                     uint32_t v[32];
-                    tmem_ld32(t_lane + c * 32, v);
-                    tmem_ld_wait();
+                    if (!(dbg & 2u)) {
+                        tmem_ld32(t_lane + c * 32, v);
+                        tmem_ld_wait();
+                    }
+                    if (dbg & 1u) continue;  // probe only: measure the pipeline without the scoring math
                     float m = 0.0f;
 #pragma unroll
                     for (int k = 0; k < 32; k += 4) {
-                        float4 s4 = *(const float4 *)(rsd + c * 32 + k);
+                        float4 s4 = lds_f4(rsd_s + (c * 32 + k) * 4);
                         float f0 = __int2float_rn((int)v[k + 0]) * s4.x;
                         float f1 = __int2float_rn((int)v[k + 1]) * s4.y;
                         float f2 = __int2float_rn((int)v[k + 2]) * s4.z;
@@ -489,7 +499,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
 #pragma unroll
                         for (int k = 0; k < 32; k++) dump[row * dump_ld + (int64_t)t * kTileN + c * 32 + k] = (int)v[k];
                     }
-                    if (__any_sync(0xffffffffu, m > st.thresh))
+                    if (!(dbg & 4u) && __any_sync(0xffffffffu, m > st.thresh))
                         st = slow_chunk(st, t_lane + c * 32, rsd + c * 32, sqd + c * 32, vR, t * kTileN + c * 32);
                 }
                 // accumulator q and the tile's scales are consumed
@@ -548,7 +558,7 @@ size_t opA_bytes_t(int64_t rows)
 template <int B>
 int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s, const char **err,
              int32_t *dump, int64_t dump_ld, int *status_dev, int variant, cudaEvent_t k0 = nullptr,
-             cudaEvent_t k1 = nullptr)
+             cudaEvent_t k1 = nullptr, uint32_t dbg = 0)
 {
     using L = Lay<B>;
     int64_t rows = j1 - j0;
@@ -583,7 +593,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     if (variant == 1) { lbo_a = L::SBO_A; sbo_a = 128; lbo_b = L::SBO_B; sbo_b = 128; }  // probe only
     if (k0) cudaEventRecord(k0, s);
     k_umma_search<B><<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, part_err, part_idx, n_sb, n_chunks, ntiles,
-                                                           rp, dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
+                                                           rp, dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b, dbg);
     if (k1) cudaEventRecord(k1, s);
     k_umma_merge<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(part_err, part_idx, n_chunks, rp, rows, w.best, j0);
     launches += 2;
@@ -620,10 +630,11 @@ int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int
 // Debug entry used by tools/umma_probe: also dumps the raw accumulators (kov) of every
 // (row, domain) pair, and lets the probe pick the descriptor variant.
 int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s,
-                             const char **err, int32_t *dump, int64_t dump_ld, int *status_dev, int variant)
+                             const char **err, int32_t *dump, int64_t dump_ld, int *status_dev, int variant,
+                             uint32_t dbg, cudaEvent_t k0, cudaEvent_t k1)
 {
-    if (g.B == 8) return launch_t<8>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant);
-    return launch_t<4>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant);
+    if (g.B == 8) return launch_t<8>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg);
+    return launch_t<4>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg);
 }
 
 }  // namespace fic

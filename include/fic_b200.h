@@ -82,7 +82,7 @@ const char *fic_last_error(const fic_handle *h); /* h may be NULL: last create e
 const char *fic_version(void);
 int fic_set_option(fic_handle *h, int option, int value);
 /* Run subsequent calls on a caller-provided CUDA stream (cudaStream_t), or NULL for
- * the handle's own stream.  Used by the torch.distributed host so that library work
+ * the handle's own stream (pass cudaStreamLegacy, 0x1, to mean the legacy default stream).  Used by the torch.distributed host so that library work
  * orders after the NCCL broadcast without a device-wide sync. */
 int fic_set_stream(fic_handle *h, void *cuda_stream);
 int fic_get_timings(const fic_handle *h, fic_timings *out);

@@ -23,7 +23,9 @@ def test_engines_agree_full_pool(fic, handle, W, B, kind):
     handle.set_engine(fic.FIC_ENGINE_UMMA)
     i2, q2 = handle.encode(img, B, wk, rgb=False)
     handle.set_engine(fic.FIC_ENGINE_AUTO)
-    assert (q1 == q2).all() and i1.view(np.uint32).tobytes() == i2.view(np.uint32).tobytes()
+    from test_gpu_parity import float_bits_equal
+
+    assert (q1 == q2).all() and float_bits_equal(i1, i2)
 
 
 def test_roundtrip_2048(fic, handle):
