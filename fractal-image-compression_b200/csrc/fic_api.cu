@@ -244,7 +244,7 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     ENSURE(w.rsum, S_RSUM, sizeof(int32_t) * g.C * g.NR);
     ENSURE(w.best, S_BEST, sizeof(int32_t) * g.NR);
     if (engine == FIC_ENGINE_UMMA) {
-        ENSURE(w.opA, S_OPA, umma_opA_bytes(g, j0, j1));
+        ENSURE(w.opA, S_OPA, umma_opA_bytes(g, j0, j1, h->num_sms));
         ENSURE(w.opB, S_OPB, umma_opB_bytes(g));
     }
     Work call = w;  // per-call view: the source planes may belong to the caller

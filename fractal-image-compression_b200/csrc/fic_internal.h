@@ -60,7 +60,7 @@ int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_
 
 // tcgen05 fused full-pool search (grey, window == whole pool).
 bool umma_applicable(const Geom &g);
-size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1);
+size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms);
 size_t umma_opB_bytes(const Geom &g);
 int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms,
                        cudaStream_t s, const char **err, cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr);

@@ -55,7 +55,7 @@ constexpr int kAccs = 4;           // accumulators per tile (TMEM: 4 x 128 colum
 constexpr int kRowsPerSB = kBlockM * kAccs;
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = (4 + kEpiWarps) * 32;
-constexpr int kScaleBytes = kTileN * 4 + kTileN * 8;  // rsd f32 + sqd f64
+constexpr int kScaleBytes = kTileN * 4;  // per-column filter scale 1/sqrt(varD), f32
 
 template <int B>
 struct Cfg;
@@ -65,7 +65,7 @@ struct Cfg<8> {
     static constexpr int KS_A = 3;   // physical A K-slices (32 B each): r[0:32] r[32:64] [rmean 0..]
     static constexpr int KS_B = 5;   // h[0:32] h[32:64] l[0:32] l[32:64] [-alpha 0..]
     static constexpr int NS = 5;     // MMA K-slices
-    static constexpr int NSTAGE = 6;
+    static constexpr int NSTAGE = 7;
     __host__ __device__ static constexpr int amap(int s) { return s < 4 ? (s & 1) : 2; }
 };
 template <>
@@ -113,13 +113,11 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
     uint8_t *blob = opB + tile * L::B_TILE_BYTES;
     uint8_t *rowp = blob + (row >> 3) * L::SBO_B + (row & 7) * 16;
     float *rsd = (float *)(blob + L::B_OP_BYTES);
-    double *sqd = (double *)(blob + L::B_OP_BYTES + kTileN * 4);
     constexpr int NCH = Cfg<B>::KS_B * 2;  // 16-byte chunks per row
     if (j >= g.ND) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
         rsd[row] = 0.0f;
-        sqd[row] = 0.0;
         return;
     }
     int gx = (int)(j % g.dpw), gy = (int)(j / g.dpw);
@@ -149,9 +147,7 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
     }
     *(uint4 *)(rowp + (2 * PCH) * 128) = make_uint4((uint32_t)((-alpha) & 0xff), 0, 0, 0);
     *(uint4 *)(rowp + (2 * PCH + 1) * 128) = make_uint4(0, 0, 0, 0);
-    double sq = __dsqrt_rn((double)varD);
-    sqd[row] = sq;
-    rsd[row] = varD > 0 ? __double2float_rn(__ddiv_rn(1.0, sq)) : 0.0f;
+    rsd[row] = varD > 0 ? __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn((double)varD))) : 0.0f;
 }
 
 // One thread per (padded) range row of the slice [j0, j1): raw pixels + integer mean.
@@ -302,51 +298,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
                             ((uint32_t)(kBlockM >> 4) << 24);
 
-// ---------------------------------------------------------------- epilogue state -----
+// ---------------------------------------------------------------- epilogue / refine --
 
-struct RowState {
-    float thresh;    // candidates with f <= thresh cannot win (see file header)
-    float fmax;      // running maximum of the filter score
-    float best_err;  // reference float error of the current winner (FC:615 start value)
-    int best_idx;
-};
-
-// Exact evaluation of one candidate, reference arithmetic (FC:677-683) and the
-// reference's strict-< update (FC:627).  Rarely executed: kept out of line.
-__device__ __noinline__ RowState eval_candidate(RowState st, float f, int kov, int vR, double sqd, int idx)
-{
-    float err = grey_error(kov, vR, sqd);
-    if (err < st.best_err) {
-        st.best_err = err;
-        st.best_idx = idx;
-    }
-    st.fmax = fmaxf(st.fmax, f);
-    st.thresh = st.fmax * (1.0f - 9.5367431640625e-07f);  // 1 - 2^-20
-    return st;
-}
-
-// Slow path for one 32-column chunk: re-read the chunk from TMEM (warp-collective) and
-// walk it in ascending column order.
-__device__ __noinline__ RowState slow_chunk(RowState st, uint32_t taddr, const float *rsd, const double *sqd,
-                                            int vR, int idx0)
-{
-    uint32_t v[32];
-    tmem_ld32(taddr, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int k = 0; k < 32; k++) {
-        float f = fabsf(__int2float_rn((int)v[k]) * rsd[k]);
-        if (f > st.thresh) st = eval_candidate(st, f, (int)v[k], vR, sqd[k], idx0 + k);
-    }
-    return st;
-}
+constexpr int kFlagCap = 32;                            // flagged 32-column chunks kept per (row, unit)
+constexpr float kOneMinusEps = 1.0f - 9.5367431640625e-07f;  // 1 - 2^-20
 
 // ---------------------------------------------------------------- the search kernel --
 
 template <int B>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
-              float *__restrict__ part_err, int32_t *__restrict__ part_idx, int n_sb, int n_chunks, int ntiles,
+              int32_t *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, int n_sb, int n_chunks, int ntiles,
               int64_t rows_padded, int32_t *__restrict__ dump, int64_t dump_ld, volatile int *status,
               uint32_t lbo_bytes_a, uint32_t sbo_bytes_a, uint32_t lbo_bytes_b, uint32_t sbo_bytes_b, uint32_t dbg)
 {
@@ -462,26 +424,29 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
             const int64_t row = (int64_t)sb * kRowsPerSB + q * kBlockM + lq * 32 + lane;
             const int vR = vRarr[row];
-            RowState st;
-            st.best_err = 10000000.0f;  // FC:615
-            st.best_idx = 0;
-            st.fmax = -1.0f;
-            // vR == 0: every candidate scores error 0, the first one wins (FC:677-678, FC:627)
-            st.thresh = (vR == 0) ? __int_as_float(0x7f800000) : -1.0f;
+            // Running filter state of this row.  thresh: chunks whose best filter score is <= thresh
+            // cannot hold the reference's winner.  vR == 0: every candidate scores error 0 and the
+            // first one wins (FC:677-678, FC:627) -> never flag, the refine step returns index 0.
+            float thresh = (vR == 0) ? __int_as_float(0x7f800000) : -1.0f;
+            int cnt = 0;
+            int32_t *my_list = flag_list + ((int64_t)ch * rows_padded + row) * kFlagCap;
             for (int t = t0; t < t1; t++) {
                 mbar_wait(BAR_B_FULL(stage), phase, status, 6);
                 mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
                 tc_fence_after();
-                const uint8_t *tile = sB + stage * L::B_TILE_BYTES;
-                const float *rsd = (const float *)(tile + L::B_OP_BYTES);
-                const double *sqd = (const double *)(tile + L::B_OP_BYTES + kTileN * 4);
-                const uint32_t rsd_s = smem_u32(rsd);
+                const uint32_t rsd_s = smem_u32(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES);
 #pragma unroll 1
                 for (int c = 0; c < kTileN / 32; c++) {
                     uint32_t v[32];
                     if (!(dbg & 2u)) {
                         tmem_ld32(t_lane + c * 32, v);
                         tmem_ld_wait();
+                    }
+                    if (c == kTileN / 32 - 1) {
+                        // last read of accumulator q for this tile: hand it back to the MMA issuer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
                     }
                     if (dbg & 1u) continue;  // probe only: measure the pipeline without the scoring math
                     float m = 0.0f;
@@ -499,21 +464,19 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
 #pragma unroll
                         for (int k = 0; k < 32; k++) dump[row * dump_ld + (int64_t)t * kTileN + c * 32 + k] = (int)v[k];
                     }
-                    if (!(dbg & 4u) && __any_sync(0xffffffffu, m > st.thresh))
-                        st = slow_chunk(st, t_lane + c * 32, rsd + c * 32, sqd + c * 32, vR, t * kTileN + c * 32);
+                    if (m > thresh) {  // a (near-)record for this row: remember the chunk, exact work is deferred
+                        if (cnt < kFlagCap) my_list[cnt] = t * (kTileN / 32) + c;
+                        cnt++;
+                        thresh = m * kOneMinusEps;
+                    }
                 }
-                // accumulator q and the tile's scales are consumed
-                tc_fence_before();
+                // the tile's scales are consumed
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(BAR_T_EMPTY(q));
-                    mbar_arrive(BAR_B_EMPTY(stage));
-                }
+                if (lane == 0) mbar_arrive(BAR_B_EMPTY(stage));
                 tf_phase ^= 1;
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
-            part_err[(int64_t)ch * rows_padded + row] = st.best_err;
-            part_idx[(int64_t)ch * rows_padded + row] = st.best_idx;
+            flag_cnt[(int64_t)ch * rows_padded + row] = cnt;
         }
     }
 
@@ -525,34 +488,124 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     }
 }
 
-// Merge per-chunk winners in ascending chunk (= ascending domain index) order with the
-// reference's strict < (FC:627), and store the window-local index (== codebook index,
-// the window is the whole pool).
-__global__ void k_umma_merge(const float *__restrict__ part_err, const int32_t *__restrict__ part_idx, int n_chunks,
-                             int64_t rows_padded, int64_t rows, int32_t *__restrict__ best, int64_t j0)
+// Refine: exact evaluation of every candidate of every flagged chunk with the reference's own
+// arithmetic (FC:655-687), one warp per range row, lane = candidate within the chunk; the winner is
+// the lexicographic (error, index) minimum = the reference's first index with the smallest error.
+// A row whose flag list overflowed (adversarial score order) is rescanned in full -- slow, exact.
+template <int B>
+__device__ __forceinline__ float refine_eval(const int *s_rt, const uint8_t *__restrict__ dec,
+                                             const int32_t *__restrict__ dsum, const int32_t *__restrict__ dsq,
+                                             const Geom &g, int vR, int64_t idx)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
-    float be = part_err[i];
-    int bi = part_idx[i];
-    for (int c = 1; c < n_chunks; c++) {
-        float e = part_err[(int64_t)c * rows_padded + i];
-        if (e < be) {
-            be = e;
-            bi = part_idx[(int64_t)c * rows_padded + i];
+    constexpr int n = B * B;
+    int gx = (int)(idx % g.dpw), gy = (int)(idx / g.dpw);
+    const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+    int dot = 0;
+#pragma unroll
+    for (int ry = 0; ry < B; ry++) {
+        const uint8_t *row = p + (int64_t)ry * g.sw;
+        if (B == 8) {  // gx*step and sw are even: 2-byte aligned
+#pragma unroll
+            for (int rx = 0; rx < B; rx += 2) {
+                unsigned v = __ldg((const unsigned short *)(row + rx));
+                dot += s_rt[ry * B + rx] * (int)(v & 0xff) + s_rt[ry * B + rx + 1] * (int)(v >> 8);
+            }
+        } else {
+#pragma unroll
+            for (int rx = 0; rx < B; rx++) dot += s_rt[ry * B + rx] * (int)__ldg(row + rx);
         }
     }
-    best[j0 + i] = bi;
+    int dmean;
+    int varD = dom_var(dsum[idx], dsq[idx], n, &dmean);
+    return grey_error(dot - dmean * vR, vR, __dsqrt_rn((double)varD));
+}
+
+template <int B>
+__global__ void __launch_bounds__(128)
+k_umma_refine(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
+              const int32_t *__restrict__ dsq, const int32_t *__restrict__ rsum,
+              const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
+              int64_t rows_padded, int64_t rows, int32_t *__restrict__ best, Geom g, int64_t j0)
+{
+    constexpr int n = B * B;
+    __shared__ int s_rt_all[4][n];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 4 + warp;
+    if (i >= rows) return;
+    const int64_t j = j0 + i;
+    int *s_rt = s_rt_all[warp];
+    const int rs = rsum[j];
+    const int rmean = rs / n, vR = rs - n * rmean;
+    if (vR == 0) {  // FC:677-678 + FC:627: all errors are 0, the first candidate wins
+        if (lane == 0) best[j] = 0;
+        return;
+    }
+    const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    for (int k = lane; k < n; k += 32)
+        s_rt[k] = (int)src[(int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)] - rmean;
+    __syncwarp();
+    float be = 10000000.0f;  // FC:615
+    int bi = 0x7fffffff;
+    bool overflow = false;
+    for (int ch = 0; ch < n_chunks && !overflow; ch++) {
+        const int cnt = flag_cnt[(int64_t)ch * rows_padded + i];
+        if (cnt > kFlagCap) { overflow = true; break; }
+        const int32_t *lst = flag_list + ((int64_t)ch * rows_padded + i) * kFlagCap;
+        for (int e = 0; e < cnt; e++) {
+            const int64_t idx = (int64_t)lst[e] * 32 + lane;
+            if (idx < g.ND) {
+                float err = refine_eval<B>(s_rt, dec, dsum, dsq, g, vR, idx);
+                if (err < be) { be = err; bi = (int)idx; }  // ascending idx per lane: strict < keeps the first
+            }
+        }
+    }
+    if (overflow) {
+        be = 10000000.0f;
+        bi = 0x7fffffff;
+        for (int64_t idx = lane; idx < g.ND; idx += 32) {
+            float err = refine_eval<B>(s_rt, dec, dsum, dsq, g, vR, idx);
+            if (err < be) { be = err; bi = (int)idx; }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        float e2 = __shfl_down_sync(0xffffffffu, be, o);
+        int i2 = __shfl_down_sync(0xffffffffu, bi, o);
+        if (e2 < be || (e2 == be && i2 < bi)) { be = e2; bi = i2; }
+    }
+    if (lane == 0) best[j] = bi == 0x7fffffff ? 0 : bi;
 }
 
 inline int64_t pad_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
-template <int B>
-size_t opA_bytes_t(int64_t rows)
+struct Plan {
+    int64_t rp;     // rows padded to whole super-blocks
+    int n_sb, ntiles, n_chunks;
+};
+
+// Split the domain sweep so that the unit count fills whole waves of num_sms CTAs.
+inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
 {
-    int64_t rp = pad_up(rows, kRowsPerSB);
-    // [A blobs][vR s32][part_err f32 x 8 chunks][part_idx s32 x 8 chunks]
-    return (size_t)(rp / kRowsPerSB) * Lay<B>::A_SB_BYTES + (size_t)rp * 4 + (size_t)rp * 8 * 8 + 1024;
+    Plan p;
+    p.rp = pad_up(rows, kRowsPerSB);
+    p.n_sb = (int)(p.rp / kRowsPerSB);
+    p.ntiles = (int)((g.ND + kTileN - 1) / kTileN);
+    p.n_chunks = 1;
+    double best_eff = 0;
+    for (int c = 1; c <= 8 && c <= p.ntiles; c++) {
+        int64_t units = (int64_t)p.n_sb * c;
+        int64_t waves = (units + num_sms - 1) / num_sms;
+        double eff = (double)units / (double)(waves * num_sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; p.n_chunks = c; }
+    }
+    return p;
+}
+
+template <int B>
+size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
+{
+    Plan p = make_plan(g, rows, num_sms);
+    // [A blobs][vR s32][flag_cnt s32 x n_chunks][flag_list s32 x n_chunks x kFlagCap]
+    return (size_t)p.n_sb * Lay<B>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 4 * (1 + kFlagCap) + 1024;
 }
 
 template <int B>
@@ -563,39 +616,29 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     using L = Lay<B>;
     int64_t rows = j1 - j0;
     if (rows <= 0) return 0;
-    int64_t rp = pad_up(rows, kRowsPerSB);
-    int n_sb = (int)(rp / kRowsPerSB);
-    int ntiles = (int)((g.ND + kTileN - 1) / kTileN);
-    // split the domain sweep so that the unit count fills whole waves of num_sms CTAs
-    int n_chunks = 1;
-    {
-        double best_eff = 0;
-        for (int c = 1; c <= 8 && c <= ntiles; c++) {
-            int64_t units = (int64_t)n_sb * c;
-            int64_t waves = (units + num_sms - 1) / num_sms;
-            double eff = (double)units / (double)(waves * num_sms);
-            if (eff > best_eff + 0.02) { best_eff = eff; n_chunks = c; }
-        }
-    }
+    Plan p = make_plan(g, rows, num_sms);
+    const int64_t rp = p.rp;
     uint8_t *opA = w.opA;
-    int32_t *vR = (int32_t *)(opA + (size_t)n_sb * L::A_SB_BYTES);
-    float *part_err = (float *)(vR + rp);
-    int32_t *part_idx = (int32_t *)(part_err + rp * 8);
+    int32_t *vR = (int32_t *)(opA + (size_t)p.n_sb * L::A_SB_BYTES);
+    int32_t *flag_cnt = vR + rp;
+    int32_t *flag_list = flag_cnt + rp * p.n_chunks;
     int launches = 0;
-    k_umma_pack_domains<B><<<(unsigned)(((int64_t)ntiles * kTileN + 127) / 128), 128, 0, s>>>(w.dec, w.dsum, w.dsq, w.opB, g, ntiles);
+    k_umma_pack_domains<B><<<(unsigned)(((int64_t)p.ntiles * kTileN + 127) / 128), 128, 0, s>>>(w.dec, w.dsum, w.dsq, w.opB, g, p.ntiles);
     k_umma_pack_ranges<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
     launches += 2;
     cudaError_t ce = cudaFuncSetAttribute(k_umma_search<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
-    int n_units = n_sb * n_chunks;
+    int n_units = p.n_sb * p.n_chunks;
     int grid = n_units < num_sms ? n_units : num_sms;
     uint32_t lbo_a = 128, sbo_a = L::SBO_A, lbo_b = 128, sbo_b = L::SBO_B;
     if (variant == 1) { lbo_a = L::SBO_A; sbo_a = 128; lbo_b = L::SBO_B; sbo_b = 128; }  // probe only
     if (k0) cudaEventRecord(k0, s);
-    k_umma_search<B><<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, part_err, part_idx, n_sb, n_chunks, ntiles,
-                                                           rp, dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b, dbg);
+    k_umma_search<B><<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, flag_list, flag_cnt, p.n_sb, p.n_chunks,
+                                                           p.ntiles, rp, dump, dump_ld, status_dev, lbo_a, sbo_a,
+                                                           lbo_b, sbo_b, dbg);
     if (k1) cudaEventRecord(k1, s);
-    k_umma_merge<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(part_err, part_idx, n_chunks, rp, rows, w.best, j0);
+    k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, flag_list, flag_cnt,
+                                                                p.n_chunks, rp, rows, w.best, g, j0);
     launches += 2;
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
@@ -609,9 +652,9 @@ bool umma_applicable(const Geom &g)
     return g.C == 1 && (g.B == 8 || g.B == 4) && g.wk == g.dpw && g.wk == g.dph;
 }
 
-size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1)
+size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms)
 {
-    return g.B == 8 ? opA_bytes_t<8>(j1 - j0) : opA_bytes_t<4>(j1 - j0);
+    return g.B == 8 ? opA_bytes_t<8>(g, j1 - j0, num_sms) : opA_bytes_t<4>(g, j1 - j0, num_sms);
 }
 
 size_t umma_opB_bytes(const Geom &g)

@@ -104,7 +104,7 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&w.dsq, 4 * g.ND));
     CK(cudaMalloc(&w.rsum, 4 * g.NR));
     CK(cudaMalloc(&w.best, 4 * g.NR));
-    CK(cudaMalloc(&w.opA, umma_opA_bytes(g, 0, g.NR)));
+    CK(cudaMalloc(&w.opA, umma_opA_bytes(g, 0, g.NR, prop.multiProcessorCount)));
     CK(cudaMalloc(&w.opB, umma_opB_bytes(g)));
     CK(cudaMemcpy(w.src, img.data(), (size_t)W * H, cudaMemcpyHostToDevice));
     cudaStream_t s;
