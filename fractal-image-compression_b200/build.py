@@ -20,6 +20,7 @@ OBJ = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfic_b200.so")
 PROBE = os.path.join(LIBDIR, "umma_probe")
+CLI = os.path.join(LIBDIR, "fic_cli")
 
 SOURCES = ["fic_kernels.cu", "fic_search_umma.cu", "fic_api.cu"]
 NVCC_FLAGS = [
@@ -73,6 +74,12 @@ def build(force: bool = False, probe: bool = False) -> str:
     arch = ["-gencode", "arch=compute_100a,code=sm_100a"]
     if force or _stale(LIB, objs):
         subprocess.check_call([_nvcc(), "-shared", "-o", LIB] + objs + arch)
+    cli_src = os.path.join(HERE, "host", "fic_cli.cpp")
+    cli_deps = [cli_src, os.path.join(HERE, "host", "fractal_compression.hpp"), LIB]
+    if force or _stale(CLI, cli_deps):  # C++ host mirror + headless CLI over the C ABI
+        gxx = shutil.which("g++") or "g++"
+        subprocess.check_call([gxx, "-std=c++17", "-O2", "-o", CLI, cli_src, "-L" + LIBDIR, "-lfic_b200",
+                               "-Wl,-rpath,$ORIGIN"])
     if probe:
         psrc = os.path.join(ROOT, "tools", "umma_probe.cu")
         if os.path.exists(psrc) and (force or _stale(PROBE, [psrc] + objs)):

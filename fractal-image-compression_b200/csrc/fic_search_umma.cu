@@ -92,6 +92,16 @@ struct Lay {
 
 // ---------------------------------------------------------------- operand packing ----
 
+// The domain sweep order is a fixed pseudo-random permutation of the pool: position p of the
+// sweep holds domain (p * mult) mod NDpad (mult coprime to NDpad; results >= ND are padding).
+// Spatially neighbouring domains have similar scores; sweeping them in raster order would make
+// the running maximum of a row climb in long monotone runs (hundreds of "records" per row),
+// while a scattered order gives the O(log N) records of an i.i.d. sequence.
+__host__ __device__ __forceinline__ int64_t pos_to_domain(int64_t pos, uint32_t mult, int64_t ndpad)
+{
+    return (int64_t)(((uint64_t)pos * (uint64_t)mult) % (uint64_t)ndpad);
+}
+
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
 {
     return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
@@ -102,14 +112,16 @@ __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
 template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
-                    const int32_t *__restrict__ dsq, uint8_t *__restrict__ opB, Geom g, int64_t ntiles)
+                    const int32_t *__restrict__ dsq, uint8_t *__restrict__ opB, Geom g, int64_t ntiles,
+                    uint32_t mult)
 {
     using L = Lay<B>;
     constexpr int n = Cfg<B>::n;
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ntiles * kTileN) return;
-    int64_t tile = j / kTileN;
-    int row = (int)(j % kTileN);
+    int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // position in the (permuted) sweep order
+    if (pos >= ntiles * kTileN) return;
+    int64_t tile = pos / kTileN;
+    int row = (int)(pos % kTileN);
+    const int64_t j = pos_to_domain(pos, mult, ntiles * kTileN);
     uint8_t *blob = opB + tile * L::B_TILE_BYTES;
     uint8_t *rowp = blob + (row >> 3) * L::SBO_B + (row & 7) * 16;
     float *rsd = (float *)(blob + L::B_OP_BYTES);
@@ -301,16 +313,18 @@ constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(kTi
 // ---------------------------------------------------------------- epilogue / refine --
 
 constexpr int kFlagCap = 32;                            // flagged 32-column chunks kept per (row, unit)
-constexpr float kOneMinusEps = 1.0f - 9.5367431640625e-07f;  // 1 - 2^-20
+constexpr float kOneMinusEps = 1.0f - 1.9073486328125e-06f;  // 1 - 2^-19 (applied to the squared score)
 
 // ---------------------------------------------------------------- the search kernel --
 
-template <int B>
+// DBG (probe builds only): 1 = skip the scoring math, 3 = skip the TMEM loads too.  DUMP: write every
+// accumulator to `dump` (probe's exactness check).  The product runs <B, 0, false>.
+template <int B, int DBG, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
               int32_t *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, int n_sb, int n_chunks, int ntiles,
               int64_t rows_padded, int32_t *__restrict__ dump, int64_t dump_ld, volatile int *status,
-              uint32_t lbo_bytes_a, uint32_t sbo_bytes_a, uint32_t lbo_bytes_b, uint32_t sbo_bytes_b, uint32_t dbg)
+              uint32_t lbo_bytes_a, uint32_t sbo_bytes_a, uint32_t lbo_bytes_b, uint32_t sbo_bytes_b)
 {
     using C = Cfg<B>;
     using L = Lay<B>;
@@ -428,6 +442,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             // cannot hold the reference's winner.  vR == 0: every candidate scores error 0 and the
             // first one wins (FC:677-678, FC:627) -> never flag, the refine step returns index 0.
             float thresh = (vR == 0) ? __int_as_float(0x7f800000) : -1.0f;
+            float fmax = 0.0f;
+            const float tie_abs = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
             int cnt = 0;
             int32_t *my_list = flag_list + ((int64_t)ch * rows_padded + row) * kFlagCap;
             for (int t = t0; t < t1; t++) {
@@ -435,10 +451,10 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
                 tc_fence_after();
                 const uint32_t rsd_s = smem_u32(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES);
-#pragma unroll 1
+#pragma unroll
                 for (int c = 0; c < kTileN / 32; c++) {
                     uint32_t v[32];
-                    if (!(dbg & 2u)) {
+                    if (!(DBG & 2)) {
                         tmem_ld32(t_lane + c * 32, v);
                         tmem_ld_wait();
                     }
@@ -448,7 +464,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                         __syncwarp();
                         if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
                     }
-                    if (dbg & 1u) continue;  // probe only: measure the pipeline without the scoring math
+                    if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring math
                     float m = 0.0f;
 #pragma unroll
                     for (int k = 0; k < 32; k += 4) {
@@ -460,14 +476,15 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                         m = fmaxf(fmaxf(m, fabsf(f0)), fabsf(f1));
                         m = fmaxf(fmaxf(m, fabsf(f2)), fabsf(f3));
                     }
-                    if (dump) {
+                    if (DUMP) {
 #pragma unroll
                         for (int k = 0; k < 32; k++) dump[row * dump_ld + (int64_t)t * kTileN + c * 32 + k] = (int)v[k];
                     }
-                    if (m > thresh) {  // a (near-)record for this row: remember the chunk, exact work is deferred
+                    if (m > thresh) {  // may hold the winner or one of its float ties: exact work is deferred
                         if (cnt < kFlagCap) my_list[cnt] = t * (kTileN / 32) + c;
                         cnt++;
-                        thresh = m * kOneMinusEps;
+                        fmax = fmaxf(fmax, m);
+                        thresh = sqrtf(fmaxf(fmax * fmax * kOneMinusEps - tie_abs, 0.0f));
                     }
                 }
                 // the tile's scales are consumed
@@ -525,7 +542,8 @@ __global__ void __launch_bounds__(128)
 k_umma_refine(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
               const int32_t *__restrict__ dsq, const int32_t *__restrict__ rsum,
               const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
-              int64_t rows_padded, int64_t rows, int32_t *__restrict__ best, Geom g, int64_t j0)
+              int64_t rows_padded, int64_t rows, int32_t *__restrict__ best, Geom g, int64_t j0, uint32_t mult,
+              int64_t ndpad)
 {
     constexpr int n = B * B;
     __shared__ int s_rt_all[4][n];
@@ -552,10 +570,10 @@ k_umma_refine(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec, 
         if (cnt > kFlagCap) { overflow = true; break; }
         const int32_t *lst = flag_list + ((int64_t)ch * rows_padded + i) * kFlagCap;
         for (int e = 0; e < cnt; e++) {
-            const int64_t idx = (int64_t)lst[e] * 32 + lane;
+            const int64_t idx = pos_to_domain((int64_t)lst[e] * 32 + lane, mult, ndpad);
             if (idx < g.ND) {
                 float err = refine_eval<B>(s_rt, dec, dsum, dsq, g, vR, idx);
-                if (err < be) { be = err; bi = (int)idx; }  // ascending idx per lane: strict < keeps the first
+                if (err < be || (err == be && (int)idx < bi)) { be = err; bi = (int)idx; }
             }
         }
     }
@@ -580,7 +598,10 @@ inline int64_t pad_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 struct Plan {
     int64_t rp;     // rows padded to whole super-blocks
     int n_sb, ntiles, n_chunks;
+    uint32_t mult;  // sweep-order multiplier (see pos_to_domain)
 };
+
+inline uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
 
 // Split the domain sweep so that the unit count fills whole waves of num_sms CTAs.
 inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
@@ -597,6 +618,10 @@ inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
         double eff = (double)units / (double)(waves * num_sms);
         if (eff > best_eff + 0.02) { best_eff = eff; p.n_chunks = c; }
     }
+    const uint64_t ndpad = (uint64_t)p.ntiles * kTileN;
+    uint64_t m = (uint64_t)((double)ndpad * 0.6180339887498949) | 1u;  // golden-ratio stride, odd
+    while (gcd_u64(m, ndpad) != 1) m += 2;
+    p.mult = ndpad <= 128 ? 1u : (uint32_t)(m % ndpad);
     return p;
 }
 
@@ -623,22 +648,28 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     int32_t *flag_cnt = vR + rp;
     int32_t *flag_list = flag_cnt + rp * p.n_chunks;
     int launches = 0;
-    k_umma_pack_domains<B><<<(unsigned)(((int64_t)p.ntiles * kTileN + 127) / 128), 128, 0, s>>>(w.dec, w.dsum, w.dsq, w.opB, g, p.ntiles);
+    k_umma_pack_domains<B><<<(unsigned)(((int64_t)p.ntiles * kTileN + 127) / 128), 128, 0, s>>>(w.dec, w.dsum, w.dsq, w.opB, g, p.ntiles, p.mult);
     k_umma_pack_ranges<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
     launches += 2;
-    cudaError_t ce = cudaFuncSetAttribute(k_umma_search<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
+    using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int32_t *, int32_t *, int, int, int,
+                             int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
+    KernelT kern = k_umma_search<B, 0, false>;
+    if (dump) kern = k_umma_search<B, 0, true>;
+    else if (dbg == 1) kern = k_umma_search<B, 1, false>;
+    else if (dbg == 3) kern = k_umma_search<B, 3, false>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
     int n_units = p.n_sb * p.n_chunks;
     int grid = n_units < num_sms ? n_units : num_sms;
     uint32_t lbo_a = 128, sbo_a = L::SBO_A, lbo_b = 128, sbo_b = L::SBO_B;
     if (variant == 1) { lbo_a = L::SBO_A; sbo_a = 128; lbo_b = L::SBO_B; sbo_b = 128; }  // probe only
     if (k0) cudaEventRecord(k0, s);
-    k_umma_search<B><<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, flag_list, flag_cnt, p.n_sb, p.n_chunks,
-                                                           p.ntiles, rp, dump, dump_ld, status_dev, lbo_a, sbo_a,
-                                                           lbo_b, sbo_b, dbg);
+    kern<<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, flag_list, flag_cnt, p.n_sb, p.n_chunks, p.ntiles, rp,
+                                               dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
     if (k1) cudaEventRecord(k1, s);
     k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, flag_list, flag_cnt,
-                                                                p.n_chunks, rp, rows, w.best, g, j0);
+                                                                p.n_chunks, rp, rows, w.best, g, j0, p.mult,
+                                                                (int64_t)p.ntiles * kTileN);
     launches += 2;
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
@@ -646,6 +677,13 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
 }
 
 }  // namespace
+
+void umma_sweep_order(const Geom &g, int64_t rows, int num_sms, uint32_t *mult, int64_t *ndpad)
+{
+    Plan p = make_plan(g, rows, num_sms);
+    *mult = p.mult;
+    *ndpad = (int64_t)p.ntiles * kTileN;
+}
 
 bool umma_applicable(const Geom &g)
 {

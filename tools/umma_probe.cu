@@ -166,6 +166,16 @@ int main(int argc, char **argv)
         std::vector<uint8_t> dec((size_t)g.sw * g.sh);
         CK(cudaMemcpy(dec.data(), w.dec, dec.size(), cudaMemcpyDeviceToHost));
         long long bad = 0, shown = 0;
+        uint32_t mult;
+        int64_t ndpad;
+        umma_sweep_order(g, g.NR, prop.multiProcessorCount, &mult, &ndpad);
+        std::vector<int64_t> pos_of(g.ND, -1);
+        for (int64_t p = 0; p < ndpad; p++) {
+            int64_t j = (int64_t)(((uint64_t)p * mult) % (uint64_t)ndpad);
+            if (j < g.ND) pos_of[j] = p;
+        }
+        for (int64_t j = 0; j < g.ND; j++)
+            if (pos_of[j] < 0) { printf("sweep order is not a permutation (domain %lld missing)\n", (long long)j); return 1; }
         for (int64_t i = 0; i < g.NR; i++) {
             int xr = (int)(i % g.rpw), yr = (int)(i / g.rpw);
             int rs = 0;
@@ -185,7 +195,7 @@ int main(int argc, char **argv)
                 int dmean = ds / g.n;
                 int kov = 0;
                 for (int k = 0; k < g.n; k++) kov += (r[k] - rmean) * (d[k] - dmean);
-                int got = hd[(size_t)i * dump_ld + j];
+                int got = hd[(size_t)i * dump_ld + pos_of[j]];
                 if (got != kov) {
                     bad++;
                     if (shown < 12) {
