@@ -92,14 +92,18 @@ struct Lay {
 
 // ---------------------------------------------------------------- operand packing ----
 
-// The domain sweep order is a fixed pseudo-random permutation of the pool: position p of the
-// sweep holds domain (p * mult) mod NDpad (mult coprime to NDpad; results >= ND are padding).
+// The domain sweep order is a fixed pseudo-random permutation of the pool: chunk P (32 positions)
+// of the sweep holds domain chunk (P * mult) mod NCHpad (mult coprime to NCHpad; domains >= ND are
+// padding).
 // Spatially neighbouring domains have similar scores; sweeping them in raster order would make
 // the running maximum of a row climb in long monotone runs (hundreds of "records" per row),
 // while a scattered order gives the O(log N) records of an i.i.d. sequence.
-__host__ __device__ __forceinline__ int64_t pos_to_domain(int64_t pos, uint32_t mult, int64_t ndpad)
+// The permutation acts on whole 32-domain chunks (the unit the epilogue flags), so the 32 lanes
+// of a refine warp still read 32 adjacent, overlapping domain blocks.
+__host__ __device__ __forceinline__ int64_t pos_to_domain(int64_t pos, uint32_t mult, int64_t nchpad)
 {
-    return (int64_t)(((uint64_t)pos * (uint64_t)mult) % (uint64_t)ndpad);
+    const uint64_t chunk = (uint64_t)pos >> 5;
+    return (int64_t)(((chunk * (uint64_t)mult) % (uint64_t)nchpad) * 32 + ((uint64_t)pos & 31));
 }
 
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
@@ -121,7 +125,7 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
     if (pos >= ntiles * kTileN) return;
     int64_t tile = pos / kTileN;
     int row = (int)(pos % kTileN);
-    const int64_t j = pos_to_domain(pos, mult, ntiles * kTileN);
+    const int64_t j = pos_to_domain(pos, mult, ntiles * (kTileN / 32));
     uint8_t *blob = opB + tile * L::B_TILE_BYTES;
     uint8_t *rowp = blob + (row >> 3) * L::SBO_B + (row & 7) * 16;
     float *rsd = (float *)(blob + L::B_OP_BYTES);
@@ -260,6 +264,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ uint32_t elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 r;\n\t"
+        "elect.sync r|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar)
@@ -395,38 +409,44 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, a_phase = 0, t_phase = 0;  // t_phase: bit q
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                int ch = u % n_chunks;
-                int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
-                mbar_wait(BAR_A_FULL, a_phase, status, 3);
-                for (int t = t0; t < t1; t++) {
-                    mbar_wait(BAR_B_FULL(stage), phase, status, 4);
-                    tc_fence_after();
-                    const uint32_t b_addr = smem_u32(sB + stage * L::B_TILE_BYTES);
+        // ===================== MMA issuer =====================
+        // The whole warp walks the (warp-uniform) loop so that addresses and descriptors live in
+        // uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.
+        uint32_t stage = 0, phase = 0, a_phase = 0, t_phase = 0;  // t_phase: bit q
+        const uint32_t elected = elect_one();
+        // descriptors differ only in the 14-bit start-address field (16-byte units)
+        const uint64_t a_desc0 = make_desc(smem_u32(sA), lbo_bytes_a, sbo_bytes_a);
+        const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo_bytes_b, sbo_bytes_b);
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            int ch = u % n_chunks;
+            int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
+            mbar_wait(BAR_A_FULL, a_phase, status, 3);
+            for (int t = t0; t < t1; t++) {
+                mbar_wait(BAR_B_FULL(stage), phase, status, 4);
+                tc_fence_after();
+                const uint64_t b_desc = b_desc0 + (uint64_t)((stage * L::B_TILE_BYTES) >> 4);
 #pragma unroll
-                    for (int q = 0; q < kAccs; q++) {
-                        mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ 1, status, 5);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(sA) + q * L::A_BLOCK_BYTES;
+                for (int q = 0; q < kAccs; q++) {
+                    mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ 1, status, 5);
+                    tc_fence_after();
+                    if (elected) {
 #pragma unroll
                         for (int s = 0; s < C::NS; s++) {
-                            uint64_t ad = make_desc(a_addr + C::amap(s) * 256, lbo_bytes_a, sbo_bytes_a);
-                            uint64_t bd = make_desc(b_addr + s * 256, lbo_bytes_b, sbo_bytes_b);
+                            const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + C::amap(s) * 256) >> 4);
+                            const uint64_t bd = b_desc + (uint64_t)((s * 256) >> 4);
                             tc_mma_i8(tmem_base + q * kTileN, ad, bd, kIdesc, s > 0 ? 1u : 0u);
                         }
                         tc_commit(BAR_T_FULL(q));
-                        t_phase ^= 1u << q;
                     }
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    __syncwarp();
+                    t_phase ^= 1u << q;
                 }
-                tc_commit(BAR_A_EMPTY);  // every MMA that reads this A super-block has completed
-                a_phase ^= 1;
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
+            if (elected) tc_commit(BAR_A_EMPTY);  // every MMA that reads this A super-block has completed
+            __syncwarp();
+            a_phase ^= 1;
         }
-        __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int e = warp - 4;
@@ -543,7 +563,7 @@ k_umma_refine(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec, 
               const int32_t *__restrict__ dsq, const int32_t *__restrict__ rsum,
               const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
               int64_t rows_padded, int64_t rows, int32_t *__restrict__ best, Geom g, int64_t j0, uint32_t mult,
-              int64_t ndpad)
+              int64_t nchpad)
 {
     constexpr int n = B * B;
     __shared__ int s_rt_all[4][n];
@@ -570,7 +590,7 @@ k_umma_refine(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec, 
         if (cnt > kFlagCap) { overflow = true; break; }
         const int32_t *lst = flag_list + ((int64_t)ch * rows_padded + i) * kFlagCap;
         for (int e = 0; e < cnt; e++) {
-            const int64_t idx = pos_to_domain((int64_t)lst[e] * 32 + lane, mult, ndpad);
+            const int64_t idx = pos_to_domain((int64_t)lst[e] * 32 + lane, mult, nchpad);
             if (idx < g.ND) {
                 float err = refine_eval<B>(s_rt, dec, dsum, dsq, g, vR, idx);
                 if (err < be || (err == be && (int)idx < bi)) { be = err; bi = (int)idx; }
@@ -618,10 +638,10 @@ inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
         double eff = (double)units / (double)(waves * num_sms);
         if (eff > best_eff + 0.02) { best_eff = eff; p.n_chunks = c; }
     }
-    const uint64_t ndpad = (uint64_t)p.ntiles * kTileN;
-    uint64_t m = (uint64_t)((double)ndpad * 0.6180339887498949) | 1u;  // golden-ratio stride, odd
-    while (gcd_u64(m, ndpad) != 1) m += 2;
-    p.mult = ndpad <= 128 ? 1u : (uint32_t)(m % ndpad);
+    const uint64_t nchpad = (uint64_t)p.ntiles * (kTileN / 32);
+    uint64_t m = (uint64_t)((double)nchpad * 0.6180339887498949) | 1u;  // golden-ratio stride, odd
+    while (gcd_u64(m, nchpad) != 1) m += 2;
+    p.mult = nchpad <= 8 ? 1u : (uint32_t)(m % nchpad);
     return p;
 }
 
@@ -669,7 +689,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     if (k1) cudaEventRecord(k1, s);
     k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, flag_list, flag_cnt,
                                                                 p.n_chunks, rp, rows, w.best, g, j0, p.mult,
-                                                                (int64_t)p.ntiles * kTileN);
+                                                                (int64_t)p.ntiles * (kTileN / 32));
     launches += 2;
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
@@ -678,11 +698,11 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
 
 }  // namespace
 
-void umma_sweep_order(const Geom &g, int64_t rows, int num_sms, uint32_t *mult, int64_t *ndpad)
+void umma_sweep_order(const Geom &g, int64_t rows, int num_sms, uint32_t *mult, int64_t *nchpad)
 {
     Plan p = make_plan(g, rows, num_sms);
     *mult = p.mult;
-    *ndpad = (int64_t)p.ntiles * kTileN;
+    *nchpad = (int64_t)p.ntiles * (kTileN / 32);
 }
 
 bool umma_applicable(const Geom &g)

@@ -167,11 +167,11 @@ int main(int argc, char **argv)
         CK(cudaMemcpy(dec.data(), w.dec, dec.size(), cudaMemcpyDeviceToHost));
         long long bad = 0, shown = 0;
         uint32_t mult;
-        int64_t ndpad;
-        umma_sweep_order(g, g.NR, prop.multiProcessorCount, &mult, &ndpad);
+        int64_t nchpad;
+        umma_sweep_order(g, g.NR, prop.multiProcessorCount, &mult, &nchpad);
         std::vector<int64_t> pos_of(g.ND, -1);
-        for (int64_t p = 0; p < ndpad; p++) {
-            int64_t j = (int64_t)(((uint64_t)p * mult) % (uint64_t)ndpad);
+        for (int64_t p = 0; p < nchpad * 32; p++) {
+            int64_t j = (int64_t)((((uint64_t)(p >> 5) * mult) % (uint64_t)nchpad) * 32 + (p & 31));
             if (j < g.ND) pos_of[j] = p;
         }
         for (int64_t j = 0; j < g.ND; j++)
