@@ -301,6 +301,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr)
         : "memory");
 }
+// Accumulators are pre-loaded with the bit pattern of 1.5 * 2^23 ("magic" bias): after the integer
+// MMA, lane bits = 0x4B400000 + kov, which read as binary32 is exactly 12582912 + kov for
+// |kov| < 2^22 (B <= 8: |kov| <= 64*255*254).  One FADD then yields float(kov) on the FMA pipe
+// instead of an I2FP on the half-rate ALU pipe.
+constexpr uint32_t kMagicBits = 0x4B400000u;
+constexpr float kMagic = 12582912.0f;
+
+__device__ __forceinline__ void tmem_st8_const(uint32_t taddr, uint32_t c)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(c)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// (a0, a1) = ((a0, a1) - magic) * (s0, s1) with the packed binary32 pipe (FADD2 / FMUL2).
+__device__ __forceinline__ void unbias_scale2(uint32_t a0, uint32_t a1, float s0, float s1, float &f0, float &f1)
+{
+    unsigned long long v, sc, mg, x, f;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(a0), "r"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(sc) : "f"(s0), "f"(s1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(mg) : "f"(-kMagic));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(v), "l"(mg));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(x), "l"(sc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(f0), "=f"(f1) : "l"(f));
+}
+
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr)
 {
     float4 v;
@@ -427,14 +453,14 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 const uint64_t b_desc = b_desc0 + (uint64_t)((stage * L::B_TILE_BYTES) >> 4);
 #pragma unroll
                 for (int q = 0; q < kAccs; q++) {
-                    mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ 1, status, 5);
+                    mbar_wait(BAR_T_EMPTY(q), (t_phase >> q) & 1, status, 5);  // epilogue re-biased accumulator q
                     tc_fence_after();
                     if (elected) {
 #pragma unroll
                         for (int s = 0; s < C::NS; s++) {
                             const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + C::amap(s) * 256) >> 4);
                             const uint64_t bd = b_desc + (uint64_t)((s * 256) >> 4);
-                            tc_mma_i8(tmem_base + q * kTileN, ad, bd, kIdesc, s > 0 ? 1u : 0u);
+                            tc_mma_i8(tmem_base + q * kTileN, ad, bd, kIdesc, 1u);  // D += A*B on top of the bias
                         }
                         tc_commit(BAR_T_FULL(q));
                     }
@@ -453,6 +479,13 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         const int q = e >> 2, lq = e & 3;  // lq == warp % 4: the TMEM lane quarter this warp may read
         const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16) + q * kTileN;
         uint32_t stage = 0, phase = 0, tf_phase = 0;
+        // bias this warp's quarter of accumulator q, then open it for the first MMA
+#pragma unroll
+        for (int c8 = 0; c8 < kTileN / 8; c8++) tmem_st8_const(t_lane + c8 * 8, kMagicBits);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             int sb = u / n_chunks, ch = u % n_chunks;
             int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
@@ -478,8 +511,12 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                         tmem_ld32(t_lane + c * 32, v);
                         tmem_ld_wait();
                     }
+                    // re-bias the columns just read
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; c8++) tmem_st8_const(t_lane + c * 32 + c8 * 8, kMagicBits);
                     if (c == kTileN / 32 - 1) {
-                        // last read of accumulator q for this tile: hand it back to the MMA issuer
+                        // last access to accumulator q for this tile: hand it back to the MMA issuer
+                        tmem_st_wait();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
@@ -489,16 +526,15 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
 #pragma unroll
                     for (int k = 0; k < 32; k += 4) {
                         float4 s4 = lds_f4(rsd_s + (c * 32 + k) * 4);
-                        float f0 = __int2float_rn((int)v[k + 0]) * s4.x;
-                        float f1 = __int2float_rn((int)v[k + 1]) * s4.y;
-                        float f2 = __int2float_rn((int)v[k + 2]) * s4.z;
-                        float f3 = __int2float_rn((int)v[k + 3]) * s4.w;
+                        float f0, f1, f2, f3;
+                        unbias_scale2(v[k + 0], v[k + 1], s4.x, s4.y, f0, f1);
+                        unbias_scale2(v[k + 2], v[k + 3], s4.z, s4.w, f2, f3);
                         m = fmaxf(fmaxf(m, fabsf(f0)), fabsf(f1));
                         m = fmaxf(fmaxf(m, fabsf(f2)), fabsf(f3));
                     }
                     if (DUMP) {
 #pragma unroll
-                        for (int k = 0; k < 32; k++) dump[row * dump_ld + (int64_t)t * kTileN + c * 32 + k] = (int)v[k];
+                        for (int k = 0; k < 32; k++) dump[row * dump_ld + (int64_t)t * kTileN + c * 32 + k] = (int)(v[k] - kMagicBits);
                     }
                     if (m > thresh) {  // may hold the winner or one of its float ties: exact work is deferred
                         if (cnt < kFlagCap) my_list[cnt] = t * (kTileN / 32) + c;
