@@ -327,6 +327,16 @@ __device__ __forceinline__ void unbias_scale2(uint32_t a0, uint32_t a1, float s0
     asm("mov.b64 {%0, %1}, %2;" : "=f"(f0), "=f"(f1) : "l"(f));
 }
 
+// (f0, f1) = (x0, x1) * (s0, s1), packed binary32 multiply (FMUL2).
+__device__ __forceinline__ void scale2(float x0, float x1, float s0, float s1, float &f0, float &f1)
+{
+    unsigned long long x, sc, f;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(sc) : "f"(s0), "f"(s1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(x), "l"(sc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(f0), "=f"(f1) : "l"(f));
+}
+
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr)
 {
     float4 v;
@@ -352,6 +362,7 @@ constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(kTi
 
 // ---------------------------------------------------------------- epilogue / refine --
 
+constexpr int kDefaultEpi = 0;
 constexpr int kFlagCap = 32;                            // flagged 32-column chunks kept per (row, unit)
 constexpr float kOneMinusEps = 1.0f - 1.9073486328125e-06f;  // 1 - 2^-19 (applied to the squared score)
 
@@ -359,7 +370,9 @@ constexpr float kOneMinusEps = 1.0f - 1.9073486328125e-06f;  // 1 - 2^-19 (appli
 
 // DBG (probe builds only): 1 = skip the scoring math, 3 = skip the TMEM loads too.  DUMP: write every
 // accumulator to `dump` (probe's exactness check).  The product runs <B, 0, false>.
-template <int B, int DBG, bool DUMP>
+// EPI: 0 = I2FP + FMUL2 scoring on plain s32 accumulators; 1 = magic-biased accumulators (FADD2 + FMUL2,
+// tcgen05.st re-bias).
+template <int B, int DBG, bool DUMP, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
               int32_t *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, int n_sb, int n_chunks, int ntiles,
@@ -394,7 +407,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         }
         for (int q = 0; q < kAccs; q++) {
             mbar_init(BAR_T_FULL(q), 1);
-            mbar_init(BAR_T_EMPTY(q), kEpiWarps / kAccs);
+            mbar_init(BAR_T_EMPTY(q), 2 * kEpiWarps / kAccs);  // 4 lane quarters x 2 column halves
         }
         mbar_init(BAR_A_FULL, 1);
         mbar_init(BAR_A_EMPTY, 1);
@@ -453,14 +466,16 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 const uint64_t b_desc = b_desc0 + (uint64_t)((stage * L::B_TILE_BYTES) >> 4);
 #pragma unroll
                 for (int q = 0; q < kAccs; q++) {
-                    mbar_wait(BAR_T_EMPTY(q), (t_phase >> q) & 1, status, 5);  // epilogue re-biased accumulator q
+                    // EPI 1: the epilogue (re-)biased accumulator q and arrived, also once before the first
+                    // tile; EPI 0: a fresh barrier passes the inverted-parity wait.
+                    mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ (EPI == 1 ? 0u : 1u), status, 5);
                     tc_fence_after();
                     if (elected) {
 #pragma unroll
                         for (int s = 0; s < C::NS; s++) {
                             const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + C::amap(s) * 256) >> 4);
                             const uint64_t bd = b_desc + (uint64_t)((s * 256) >> 4);
-                            tc_mma_i8(tmem_base + q * kTileN, ad, bd, kIdesc, 1u);  // D += A*B on top of the bias
+                            tc_mma_i8(tmem_base + q * kTileN, ad, bd, kIdesc, (EPI == 1 || s > 0) ? 1u : 0u);
                         }
                         tc_commit(BAR_T_FULL(q));
                     }
@@ -475,72 +490,106 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
+        // Warp e: TMEM lane quarter lq = e % 4 (== warp % 4, the quarter this warp may access), column half
+        // `half` (64 of the 128 domains of a tile) of the two accumulators qa and qa + 2.  Two warps share
+        // each (accumulator, lane quarter), so an accumulator is drained in two chunk-times, and every warp
+        // alternates between two accumulators so that it always has one ready while the other is refilled.
         const int e = warp - 4;
-        const int q = e >> 2, lq = e & 3;  // lq == warp % 4: the TMEM lane quarter this warp may read
-        const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16) + q * kTileN;
+        const int lq = e & 3, kk = e >> 2;
+        const int half = kk & 1, qa = kk >> 1;
+        const uint32_t t_lane0 = tmem_base + ((uint32_t)(lq * 32) << 16) + half * 64;
         uint32_t stage = 0, phase = 0, tf_phase = 0;
-        // bias this warp's quarter of accumulator q, then open it for the first MMA
+        if (EPI == 1) {
 #pragma unroll
-        for (int c8 = 0; c8 < kTileN / 8; c8++) tmem_st8_const(t_lane + c8 * 8, kMagicBits);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
+            for (int sl = 0; sl < 2; sl++) {
+                const uint32_t ta = t_lane0 + (qa + 2 * sl) * kTileN;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; c8++) tmem_st8_const(ta + c8 * 8, kMagicBits);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(BAR_T_EMPTY(qa));
+                mbar_arrive(BAR_T_EMPTY(qa + 2));
+            }
+        }
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             int sb = u / n_chunks, ch = u % n_chunks;
             int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
-            const int64_t row = (int64_t)sb * kRowsPerSB + q * kBlockM + lq * 32 + lane;
-            const int vR = vRarr[row];
-            // Running filter state of this row.  thresh: chunks whose best filter score is <= thresh
-            // cannot hold the reference's winner.  vR == 0: every candidate scores error 0 and the
-            // first one wins (FC:677-678, FC:627) -> never flag, the refine step returns index 0.
-            float thresh = (vR == 0) ? __int_as_float(0x7f800000) : -1.0f;
-            float fmax = 0.0f;
-            const float tie_abs = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
-            int cnt = 0;
-            int32_t *my_list = flag_list + ((int64_t)ch * rows_padded + row) * kFlagCap;
+            // Running filter state of this thread's two rows.  thresh: chunks whose best filter score is
+            // <= thresh cannot hold the reference's winner or one of its float ties.  vR == 0: every
+            // candidate scores error 0 and the first one wins (FC:677-678, FC:627) -> never flag.
+            int64_t row[2];
+            float thresh[2], fmax[2], tie_abs[2];
+            int cnt[2];
+            int32_t *my_list[2];
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+                row[sl] = (int64_t)sb * kRowsPerSB + (qa + 2 * sl) * kBlockM + lq * 32 + lane;
+                const int vR = vRarr[row[sl]];
+                thresh[sl] = (vR == 0) ? __int_as_float(0x7f800000) : -1.0f;
+                fmax[sl] = 0.0f;
+                tie_abs[sl] = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
+                cnt[sl] = 0;
+                my_list[sl] = flag_list + (((int64_t)ch * rows_padded + row[sl]) * 2 + half) * kFlagCap;
+            }
             for (int t = t0; t < t1; t++) {
                 mbar_wait(BAR_B_FULL(stage), phase, status, 6);
-                mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
-                tc_fence_after();
-                const uint32_t rsd_s = smem_u32(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES);
+                const uint32_t rsd_s = smem_u32(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES) + half * 64 * 4;
 #pragma unroll
-                for (int c = 0; c < kTileN / 32; c++) {
-                    uint32_t v[32];
-                    if (!(DBG & 2)) {
-                        tmem_ld32(t_lane + c * 32, v);
-                        tmem_ld_wait();
-                    }
-                    // re-bias the columns just read
+                for (int sl = 0; sl < 2; sl++) {
+                    const int q = qa + 2 * sl;
+                    const uint32_t ta = t_lane0 + q * kTileN;
+                    mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
+                    tc_fence_after();
 #pragma unroll
-                    for (int c8 = 0; c8 < 4; c8++) tmem_st8_const(t_lane + c * 32 + c8 * 8, kMagicBits);
-                    if (c == kTileN / 32 - 1) {
-                        // last access to accumulator q for this tile: hand it back to the MMA issuer
-                        tmem_st_wait();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
-                    }
-                    if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring math
-                    float m = 0.0f;
+                    for (int cc = 0; cc < 2; cc++) {
+                        uint32_t v[32];
+                        if (!(DBG & 2)) {
+                            tmem_ld32(ta + cc * 32, v);
+                            tmem_ld_wait();
+                        }
+                        if (EPI == 1) {  // re-bias the columns just read
 #pragma unroll
-                    for (int k = 0; k < 32; k += 4) {
-                        float4 s4 = lds_f4(rsd_s + (c * 32 + k) * 4);
-                        float f0, f1, f2, f3;
-                        unbias_scale2(v[k + 0], v[k + 1], s4.x, s4.y, f0, f1);
-                        unbias_scale2(v[k + 2], v[k + 3], s4.z, s4.w, f2, f3);
-                        m = fmaxf(fmaxf(m, fabsf(f0)), fabsf(f1));
-                        m = fmaxf(fmaxf(m, fabsf(f2)), fabsf(f3));
-                    }
-                    if (DUMP) {
+                            for (int c8 = 0; c8 < 4; c8++) tmem_st8_const(ta + cc * 32 + c8 * 8, kMagicBits);
+                        }
+                        if (cc == 1) {
+                            // last access to this half of accumulator q for this tile: hand it back
+                            if (EPI == 1) tmem_st_wait();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
+                        }
+                        if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring math
+                        float m = 0.0f;
 #pragma unroll
-                        for (int k = 0; k < 32; k++) dump[row * dump_ld + (int64_t)t * kTileN + c * 32 + k] = (int)(v[k] - kMagicBits);
-                    }
-                    if (m > thresh) {  // may hold the winner or one of its float ties: exact work is deferred
-                        if (cnt < kFlagCap) my_list[cnt] = t * (kTileN / 32) + c;
-                        cnt++;
-                        fmax = fmaxf(fmax, m);
-                        thresh = sqrtf(fmaxf(fmax * fmax * kOneMinusEps - tie_abs, 0.0f));
+                        for (int k = 0; k < 32; k += 4) {
+                            float4 s4 = lds_f4(rsd_s + (cc * 32 + k) * 4);
+                            float f0, f1, f2, f3;
+                            if (EPI == 1) {
+                                unbias_scale2(v[k + 0], v[k + 1], s4.x, s4.y, f0, f1);
+                                unbias_scale2(v[k + 2], v[k + 3], s4.z, s4.w, f2, f3);
+                            } else {
+                                scale2(__int2float_rn((int)v[k + 0]), __int2float_rn((int)v[k + 1]), s4.x, s4.y, f0, f1);
+                                scale2(__int2float_rn((int)v[k + 2]), __int2float_rn((int)v[k + 3]), s4.z, s4.w, f2, f3);
+                            }
+                            m = fmaxf(fmaxf(m, fabsf(f0)), fabsf(f1));
+                            m = fmaxf(fmaxf(m, fabsf(f2)), fabsf(f3));
+                        }
+                        const int c = half * 2 + cc;  // chunk of the tile
+                        if (DUMP) {
+#pragma unroll
+                            for (int k = 0; k < 32; k++)
+                                dump[row[sl] * dump_ld + (int64_t)t * kTileN + c * 32 + k] =
+                                    (int)(v[k] - (EPI == 1 ? kMagicBits : 0u));
+                        }
+                        if (m > thresh[sl]) {  // may hold the winner or one of its float ties: exact work is deferred
+                            if (cnt[sl] < kFlagCap) my_list[sl][cnt[sl]] = t * (kTileN / 32) + c;
+                            cnt[sl]++;
+                            fmax[sl] = fmaxf(fmax[sl], m);
+                            thresh[sl] = sqrtf(fmaxf(fmax[sl] * fmax[sl] * kOneMinusEps - tie_abs[sl], 0.0f));
+                        }
                     }
                 }
                 // the tile's scales are consumed
@@ -549,7 +598,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 tf_phase ^= 1;
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
-            flag_cnt[(int64_t)ch * rows_padded + row] = cnt;
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) flag_cnt[((int64_t)ch * rows_padded + row[sl]) * 2 + half] = cnt[sl];
         }
     }
 
@@ -621,10 +671,11 @@ k_umma_refine(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec, 
     float be = 10000000.0f;  // FC:615
     int bi = 0x7fffffff;
     bool overflow = false;
-    for (int ch = 0; ch < n_chunks && !overflow; ch++) {
-        const int cnt = flag_cnt[(int64_t)ch * rows_padded + i];
+    for (int lh = 0; lh < 2 * n_chunks && !overflow; lh++) {  // (domain chunk of the unit, column half) lists
+        const int64_t li = ((int64_t)(lh >> 1) * rows_padded + i) * 2 + (lh & 1);
+        const int cnt = flag_cnt[li];
         if (cnt > kFlagCap) { overflow = true; break; }
-        const int32_t *lst = flag_list + ((int64_t)ch * rows_padded + i) * kFlagCap;
+        const int32_t *lst = flag_list + li * kFlagCap;
         for (int e = 0; e < cnt; e++) {
             const int64_t idx = pos_to_domain((int64_t)lst[e] * 32 + lane, mult, nchpad);
             if (idx < g.ND) {
@@ -685,8 +736,8 @@ template <int B>
 size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p = make_plan(g, rows, num_sms);
-    // [A blobs][vR s32][flag_cnt s32 x n_chunks][flag_list s32 x n_chunks x kFlagCap]
-    return (size_t)p.n_sb * Lay<B>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 4 * (1 + kFlagCap) + 1024;
+    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap]
+    return (size_t)p.n_sb * Lay<B>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 2 * 4 * (1 + kFlagCap) + 1024;
 }
 
 template <int B>
@@ -702,17 +753,21 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     uint8_t *opA = w.opA;
     int32_t *vR = (int32_t *)(opA + (size_t)p.n_sb * L::A_SB_BYTES);
     int32_t *flag_cnt = vR + rp;
-    int32_t *flag_list = flag_cnt + rp * p.n_chunks;
+    int32_t *flag_list = flag_cnt + rp * p.n_chunks * 2;
     int launches = 0;
     k_umma_pack_domains<B><<<(unsigned)(((int64_t)p.ntiles * kTileN + 127) / 128), 128, 0, s>>>(w.dec, w.dsum, w.dsq, w.opB, g, p.ntiles, p.mult);
     k_umma_pack_ranges<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
     launches += 2;
     using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int32_t *, int32_t *, int, int, int,
                              int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
-    KernelT kern = k_umma_search<B, 0, false>;
-    if (dump) kern = k_umma_search<B, 0, true>;
-    else if (dbg == 1) kern = k_umma_search<B, 1, false>;
-    else if (dbg == 3) kern = k_umma_search<B, 3, false>;
+    // dbg (probe only): bit 3 selects the magic-bias epilogue; low bits 1 / 3 strip the scoring math / TMEM loads
+    KernelT kern = k_umma_search<B, 0, false, kDefaultEpi>;
+    const int epi = (dbg & 8u) ? 1 : ((dbg & 16u) ? 0 : kDefaultEpi);
+    const int strip = (int)(dbg & 3u);
+    if (dump) kern = epi ? k_umma_search<B, 0, true, 1> : k_umma_search<B, 0, true, 0>;
+    else if (strip == 1) kern = epi ? k_umma_search<B, 1, false, 1> : k_umma_search<B, 1, false, 0>;
+    else if (strip == 3) kern = epi ? k_umma_search<B, 3, false, 1> : k_umma_search<B, 3, false, 0>;
+    else kern = epi ? k_umma_search<B, 0, false, 1> : k_umma_search<B, 0, false, 0>;
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
     int n_units = p.n_sb * p.n_chunks;
