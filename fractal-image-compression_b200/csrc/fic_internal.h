@@ -62,8 +62,9 @@ int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_
 bool umma_applicable(const Geom &g);
 size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms);
 size_t umma_opB_bytes(const Geom &g);
-// sweep chunk P (32 positions) holds domain chunk (P * mult) % nchpad (domains >= ND: padding); probe only
-void umma_sweep_order(const Geom &g, int64_t rows, int num_sms, uint32_t *mult, int64_t *nchpad);
+// device table: sweep position -> domain index (-1: padding), valid after a launch; probe only
+void umma_debug_positions(const Work &w, const Geom &g, int64_t rows, int num_sms, const int32_t **d_pos_dom,
+                          int64_t *npos);
 int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms,
                        cudaStream_t s, const char **err, cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr);
 int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms,

@@ -7,42 +7,59 @@
 //     error = vR^2 * (1 - (kov / (vR * sqrt(varD)))^2)          (FC:677-683)
 // with the exact integers kov = sum (r - rmean)(d - dmean), vR = sum (r - rmean) and
 // varD = sum (d - dmean)^2, and keeps the first index with the smallest float error
-// (strict <, ascending loop, FC:619-632).  error is a non-increasing function of
-// x = |kov| / sqrt(varD) through every rounding step, so the reference's winner is the
-// lowest index at which the running maximum of x is (re)attained up to rounding.  The
-// epilogue therefore
-//   1. gets kov[i][j] exactly from the tensor cores,
-//   2. filters with the cheap binary32 score f = |kov| * rsqrt(varD_j) against the
-//      running maximum of the row (relative slack 2^-20, far above f's rounding error),
-//   3. evaluates the reference's own float/double error formula only for candidates
-//      that pass, and applies the reference's strict-< update in ascending index order.
-// Result: the same winner index as the reference for every row, bit for bit.
+// (strict <, ascending loop, FC:619-632).  Every rounding step of that expression is
+// monotone, so error is a non-increasing function of x = |kov| / sqrt(varD), and the set T
+// of candidates that reach the minimal float error is { j : x_j >= x_lo } for some x_lo
+// within a relative 2^-20 (and an absolute 2^-21 in (x/vR)^2, the resolution of 1 - r^2)
+// of the row maximum.  The reference's answer is the lowest index in T.
+//
+//   1. The tensor cores produce kov[i][j] exactly (u8 x s8 -> s32).
+//   2. The fused epilogue needs no per-candidate floating point: domains are swept in
+//      order of increasing varD, so every 32-column chunk of an accumulator shares the
+//      scale 1/sqrt(varD) up to a tiny spread [rlo, rhi].  A thread takes the integer
+//      max |kov| of its row over the chunk (VIMNMX3), and with M = max |kov|:
+//      M*rhi bounds every x of the chunk from above, M*rlo bounds the row maximum from
+//      below.  A chunk is flagged when M*rhi exceeds the row's threshold
+//      thresh^2 = lb_max^2 * (1 - 2^-19) - vR^2 * 2^-21  (lb_max = running max of M*rlo),
+//      i.e. whenever it could contain a member of T.  Flags are rare (O(log N) per row).
+//   3. A refine kernel evaluates every candidate of every flagged chunk with the
+//      reference's own float/double expression and takes the lexicographic (error, index)
+//      minimum -- over a superset of T that is exactly the reference's winner.
+// Result: the same winner index as the reference for every row, bit for bit, in any sweep
+// order.
 //
 // How kov becomes one u8 x s8 GEMM.  With dt = d - dmean_j (|dt| <= 254 for B <= 8),
 // split dt = h + l, h = dt >> 1, l = dt - h (both fit s8).  Then
 //     kov = sum_k r_k * h_k + sum_k r_k * l_k + rmean_i * (-alpha_j),   alpha_j = sum d - n*dmean_j
 // i.e. A row = [ r | r | rmean 0.. ] (u8) and B row = [ h | l | -alpha 0.. ] (s8), K
 // padded to a multiple of 32 (one kind::i8 MMA consumes K = 32).  The duplicated `r`
-// half of A is not stored twice: the MMA issuer simply points the A descriptor of
-// K-slices 2,3 back at slices 0,1 (B = 8).
+// half of A is not stored twice: the MMA issuer points the A descriptor of K-slices 2,3
+// back at slices 0,1 (B = 8).  The accumulator IS kov; no per-output correction exists.
 //
 // Data movement.  Operands are packed once per encode by two HBM-bound kernels into
 // "blobs" that are already in the canonical no-swizzle K-major UMMA shared-memory
 // layout (8x16-byte core matrices, LBO = 128 B between K-adjacent core matrices,
 // SBO = KS*256 B between 8-row groups).  A blob is moved with ONE 1-D TMA bulk copy
 // (cp.async.bulk, SASS UBLKCP) that completes on an mbarrier; a domain tile blob also
-// carries the 128 per-column scales rsqrt(varD) (f32) and sqrt(varD) (f64).
+// carries the (rhi, rlo) pair of each of its four 32-column chunks.
+//
+// Sweep order.  Sorted position sp holds domain perm[sp] (perm = domains by increasing
+// varD, k_umma_sortkeys + cub radix sort).  Sorted chunks (32 positions) are visited in
+// a fixed pseudo-random order (sweep chunk P holds sorted chunk (P * mult) mod NCH), so
+// the chunk maxima a row sees behave like an i.i.d. sequence: O(log N) records.
 //
 // CTA organisation (1 CTA / SM, 640 threads, persistent over work units):
 //   warp 0      TMA producer: A super-block (512 range rows, resident for the whole
 //               unit) + a ring of domain tiles (128 domains each)
-//   warp 1      MMA issuer: per domain tile 4 accumulators (128 rows x 128 domains s32,
-//               4 x 128 = all 512 TMEM columns) x NS K-slices of tcgen05.mma
+//   warp 1      MMA issuer (warp-uniform loop, one elected lane issues): per domain tile
+//               4 accumulators (128 rows x 128 domains s32 = all 512 TMEM columns) x NS
+//               K-slices of tcgen05.mma, tcgen05.commit -> t_full[q]
 //   warp 2      TMEM allocator
-//   warps 4-19  epilogue: warp e owns accumulator q = e / 4, TMEM lanes 32*(e % 4)..+31;
-//               one thread owns one range row for the whole unit
-// A work unit is (super-block of 512 rows) x (1/n_chunks of the domain tiles); per-unit
-// row winners go to part_err / part_idx and are merged in ascending chunk order.
+//   warps 4-19  epilogue: warp e owns TMEM lane quarter e % 4 and column half (e / 4) & 1
+//               of accumulators (e / 8) and (e / 8) + 2; one thread = two range rows
+// A work unit is (super-block of 512 rows) x (1/n_chunks of the domain tiles).
+#include <cub/device/device_radix_sort.cuh>
+
 #include "fic_device.cuh"
 
 namespace fic {
@@ -55,7 +72,10 @@ constexpr int kAccs = 4;           // accumulators per tile (TMEM: 4 x 128 colum
 constexpr int kRowsPerSB = kBlockM * kAccs;
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = (4 + kEpiWarps) * 32;
-constexpr int kScaleBytes = kTileN * 4;  // per-column filter scale 1/sqrt(varD), f32
+constexpr int kChunksPerTile = kTileN / 32;
+constexpr int kBoundBytes = kChunksPerTile * 2 * 4;  // (rhi, rlo) f32 per 32-column chunk
+constexpr int kFlagCap = 32;                         // flagged chunks kept per (row, unit, column half)
+constexpr float kOneMinusEps = 1.0f - 1.9073486328125e-06f;  // 1 - 2^-19 (applied to the squared score)
 
 template <int B>
 struct Cfg;
@@ -86,84 +106,109 @@ struct Lay {
     static constexpr int A_BLOCK_BYTES = (kBlockM / 8) * SBO_A;
     static constexpr int A_SB_BYTES = kAccs * A_BLOCK_BYTES;
     static constexpr int B_OP_BYTES = (kTileN / 8) * SBO_B;
-    static constexpr int B_TILE_BYTES = B_OP_BYTES + kScaleBytes;
+    static constexpr int B_TILE_BYTES = B_OP_BYTES + kBoundBytes;
     static constexpr int SMEM_BYTES = A_SB_BYTES + C::NSTAGE * B_TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-// ---------------------------------------------------------------- operand packing ----
+// ---------------------------------------------------------------- sweep order --------
 
-// The domain sweep order is a fixed pseudo-random permutation of the pool: chunk P (32 positions)
-// of the sweep holds domain chunk (P * mult) mod NCHpad (mult coprime to NCHpad; domains >= ND are
-// padding).
-// Spatially neighbouring domains have similar scores; sweeping them in raster order would make
-// the running maximum of a row climb in long monotone runs (hundreds of "records" per row),
-// while a scattered order gives the O(log N) records of an i.i.d. sequence.
-// The permutation acts on whole 32-domain chunks (the unit the epilogue flags), so the 32 lanes
-// of a refine warp still read 32 adjacent, overlapping domain blocks.
-__host__ __device__ __forceinline__ int64_t pos_to_domain(int64_t pos, uint32_t mult, int64_t nchpad)
+// Sweep chunk P (32 positions) holds sorted chunk (P * mult) mod nch (mult coprime to nch).
+__host__ __device__ __forceinline__ int64_t sweep_to_sorted(int64_t pos, uint32_t mult, int64_t nch)
 {
     const uint64_t chunk = (uint64_t)pos >> 5;
-    return (int64_t)(((chunk * (uint64_t)mult) % (uint64_t)nchpad) * 32 + ((uint64_t)pos & 31));
+    return (int64_t)(((chunk * (uint64_t)mult) % (uint64_t)nch) * 32 + ((uint64_t)pos & 31));
 }
+
+// Sort keys: varD of every domain (DB:106-115), payload: the domain index.
+__global__ void k_umma_sortkeys(const int32_t *__restrict__ dsum, const int32_t *__restrict__ dsq, int n,
+                                int64_t ND, uint32_t *__restrict__ keys, int32_t *__restrict__ vals)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ND) return;
+    int dmean;
+    keys[j] = (uint32_t)dom_var(dsum[j], dsq[j], n, &dmean);
+    vals[j] = (int32_t)j;
+}
+
+// ---------------------------------------------------------------- operand packing ----
 
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
 {
     return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
 }
 
-// One thread per (padded) domain: centre by the integer mean, split into two s8 digits,
-// write the tile blob row and the two per-column scales.
+// One thread per sweep position (a warp = one 32-position chunk): centre the domain by its
+// integer mean, split into two s8 digits, write the tile-blob row, the position tables used
+// by the refine step, and the chunk's scale bounds.
 template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
-                    const int32_t *__restrict__ dsq, uint8_t *__restrict__ opB, Geom g, int64_t ntiles,
-                    uint32_t mult)
+                    const int32_t *__restrict__ dsq, const int32_t *__restrict__ perm, uint8_t *__restrict__ opB,
+                    int32_t *__restrict__ pos_dom, int32_t *__restrict__ pos_var, int64_t *__restrict__ dom0_pos,
+                    Geom g, int64_t ntiles, uint32_t mult)
 {
     using L = Lay<B>;
     constexpr int n = Cfg<B>::n;
-    int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // position in the (permuted) sweep order
-    if (pos >= ntiles * kTileN) return;
-    int64_t tile = pos / kTileN;
-    int row = (int)(pos % kTileN);
-    const int64_t j = pos_to_domain(pos, mult, ntiles * (kTileN / 32));
+    const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= ntiles * kTileN) return;  // whole warps only: ntiles * 128 is a multiple of 32
+    const int64_t tile = pos / kTileN;
+    const int row = (int)(pos % kTileN);
+    const int64_t sp = sweep_to_sorted(pos, mult, ntiles * kChunksPerTile);
     uint8_t *blob = opB + tile * L::B_TILE_BYTES;
     uint8_t *rowp = blob + (row >> 3) * L::SBO_B + (row & 7) * 16;
-    float *rsd = (float *)(blob + L::B_OP_BYTES);
     constexpr int NCH = Cfg<B>::KS_B * 2;  // 16-byte chunks per row
-    if (j >= g.ND) {
+    float rsd_hi = 0.0f, rsd_lo = __int_as_float(0x7f800000);
+    if (sp >= g.ND) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
-        rsd[row] = 0.0f;
-        return;
-    }
-    int gx = (int)(j % g.dpw), gy = (int)(j / g.dpw);
-    const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
-    int dmean;
-    int varD = dom_var(dsum[j], dsq[j], n, &dmean);
-    int alpha = dsum[j] - n * dmean;
-    constexpr int PCH = n / 16;  // pixel chunks per digit
+        pos_dom[pos] = -1;
+        pos_var[pos] = 0;
+    } else {
+        const int64_t j = perm[sp];
+        const int gx = (int)(j % g.dpw), gy = (int)(j / g.dpw);
+        const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+        int dmean;
+        const int varD = dom_var(dsum[j], dsq[j], n, &dmean);
+        const int alpha = dsum[j] - n * dmean;
+        constexpr int PCH = n / 16;  // pixel chunks per digit
 #pragma unroll
-    for (int c = 0; c < PCH; c++) {
-        uint32_t hw[4], lw[4];
+        for (int c = 0; c < PCH; c++) {
+            uint32_t hw[4], lw[4];
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            int hv[4], lv[4];
+            for (int w = 0; w < 4; w++) {
+                int hv[4], lv[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                int k = c * 16 + w * 4 + e;
-                int dt = (int)__ldg(p + (int64_t)(k / B) * g.sw + (k % B)) - dmean;
-                hv[e] = dt >> 1;
-                lv[e] = dt - hv[e];
+                for (int e = 0; e < 4; e++) {
+                    int k = c * 16 + w * 4 + e;
+                    int dt = (int)__ldg(p + (int64_t)(k / B) * g.sw + (k % B)) - dmean;
+                    hv[e] = dt >> 1;
+                    lv[e] = dt - hv[e];
+                }
+                hw[w] = pack4(hv[0], hv[1], hv[2], hv[3]);
+                lw[w] = pack4(lv[0], lv[1], lv[2], lv[3]);
             }
-            hw[w] = pack4(hv[0], hv[1], hv[2], hv[3]);
-            lw[w] = pack4(lv[0], lv[1], lv[2], lv[3]);
+            *(uint4 *)(rowp + c * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *(uint4 *)(rowp + (PCH + c) * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
-        *(uint4 *)(rowp + c * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *(uint4 *)(rowp + (PCH + c) * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        *(uint4 *)(rowp + (2 * PCH) * 128) = make_uint4((uint32_t)((-alpha) & 0xff), 0, 0, 0);
+        *(uint4 *)(rowp + (2 * PCH + 1) * 128) = make_uint4(0, 0, 0, 0);
+        pos_dom[pos] = (int32_t)j;
+        pos_var[pos] = varD;
+        if (j == 0) *dom0_pos = pos;  // the refine step always evaluates domain 0
+        if (varD > 0) {  // flat domains have kov == 0: they never set a chunk's max |kov|
+            float r = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn((double)varD)));
+            rsd_hi = r * (1.0f + 2.384185791015625e-07f);  // >= 1/sqrt(varD) * (1 + 2^-23)
+            rsd_lo = r * (1.0f - 2.384185791015625e-07f);  // <= 1/sqrt(varD) * (1 - 2^-23)
+        }
     }
-    *(uint4 *)(rowp + (2 * PCH) * 128) = make_uint4((uint32_t)((-alpha) & 0xff), 0, 0, 0);
-    *(uint4 *)(rowp + (2 * PCH + 1) * 128) = make_uint4(0, 0, 0, 0);
-    rsd[row] = varD > 0 ? __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn((double)varD))) : 0.0f;
+    for (int o = 16; o > 0; o >>= 1) {
+        rsd_hi = fmaxf(rsd_hi, __shfl_xor_sync(0xffffffffu, rsd_hi, o));
+        rsd_lo = fminf(rsd_lo, __shfl_xor_sync(0xffffffffu, rsd_lo, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (rsd_hi == 0.0f) rsd_lo = 0.0f;  // chunk of flat / padding columns only
+        *(float2 *)(blob + L::B_OP_BYTES + (row >> 5) * 8) = make_float2(rsd_hi, rsd_lo);
+    }
 }
 
 // One thread per (padded) range row of the slice [j0, j1): raw pixels + integer mean.
@@ -301,49 +346,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr)
         : "memory");
 }
-// Accumulators are pre-loaded with the bit pattern of 1.5 * 2^23 ("magic" bias): after the integer
-// MMA, lane bits = 0x4B400000 + kov, which read as binary32 is exactly 12582912 + kov for
-// |kov| < 2^22 (B <= 8: |kov| <= 64*255*254).  One FADD then yields float(kov) on the FMA pipe
-// instead of an I2FP on the half-rate ALU pipe.
-constexpr uint32_t kMagicBits = 0x4B400000u;
-constexpr float kMagic = 12582912.0f;
-
-__device__ __forceinline__ void tmem_st8_const(uint32_t taddr, uint32_t c)
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(c)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// (a0, a1) = ((a0, a1) - magic) * (s0, s1) with the packed binary32 pipe (FADD2 / FMUL2).
-__device__ __forceinline__ void unbias_scale2(uint32_t a0, uint32_t a1, float s0, float s1, float &f0, float &f1)
-{
-    unsigned long long v, sc, mg, x, f;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(a0), "r"(a1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(sc) : "f"(s0), "f"(s1));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(mg) : "f"(-kMagic));
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(v), "l"(mg));
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(x), "l"(sc));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(f0), "=f"(f1) : "l"(f));
-}
-
-// (f0, f1) = (x0, x1) * (s0, s1), packed binary32 multiply (FMUL2).
-__device__ __forceinline__ void scale2(float x0, float x1, float s0, float s1, float &f0, float &f1)
-{
-    unsigned long long x, sc, f;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(sc) : "f"(s0), "f"(s1));
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(x), "l"(sc));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(f0), "=f"(f1) : "l"(f));
-}
-
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr)
 {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
     return v;
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
 
 // K-major, no-swizzle shared-memory matrix descriptor (PTX "matrix descriptor";
 // cute::UMMA::SmemDescriptor): start address, leading (K) and stride (M/N) byte offsets
@@ -360,19 +375,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
                             ((uint32_t)(kBlockM >> 4) << 24);
 
-// ---------------------------------------------------------------- epilogue / refine --
-
-constexpr int kDefaultEpi = 0;
-constexpr int kFlagCap = 32;                            // flagged 32-column chunks kept per (row, unit)
-constexpr float kOneMinusEps = 1.0f - 1.9073486328125e-06f;  // 1 - 2^-19 (applied to the squared score)
-
 // ---------------------------------------------------------------- the search kernel --
 
-// DBG (probe builds only): 1 = skip the scoring math, 3 = skip the TMEM loads too.  DUMP: write every
-// accumulator to `dump` (probe's exactness check).  The product runs <B, 0, false>.
-// EPI: 0 = I2FP + FMUL2 scoring on plain s32 accumulators; 1 = magic-biased accumulators (FADD2 + FMUL2,
-// tcgen05.st re-bias).
-template <int B, int DBG, bool DUMP, int EPI>
+// DBG (probe builds only): 1 = skip the scoring, 3 = skip the TMEM loads too.  DUMP: write every
+// accumulator to `dump` (the probe's exactness check).  The product runs <B, 0, false>.
+template <int B, int DBG, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
               int32_t *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, int n_sb, int n_chunks, int ntiles,
@@ -388,7 +395,6 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     uint8_t *sA = smem;
     uint8_t *sB = smem + L::A_SB_BYTES;
     uint64_t *bars = (uint64_t *)(sB + NSTAGE * L::B_TILE_BYTES);
-    // barrier map
     const uint32_t bar0 = smem_u32(bars);
     auto BAR_B_FULL = [&](int s) { return bar0 + 8u * s; };
     auto BAR_B_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
@@ -466,16 +472,14 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 const uint64_t b_desc = b_desc0 + (uint64_t)((stage * L::B_TILE_BYTES) >> 4);
 #pragma unroll
                 for (int q = 0; q < kAccs; q++) {
-                    // EPI 1: the epilogue (re-)biased accumulator q and arrived, also once before the first
-                    // tile; EPI 0: a fresh barrier passes the inverted-parity wait.
-                    mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ (EPI == 1 ? 0u : 1u), status, 5);
+                    mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ 1, status, 5);
                     tc_fence_after();
                     if (elected) {
 #pragma unroll
                         for (int s = 0; s < C::NS; s++) {
                             const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + C::amap(s) * 256) >> 4);
                             const uint64_t bd = b_desc + (uint64_t)((s * 256) >> 4);
-                            tc_mma_i8(tmem_base + q * kTileN, ad, bd, kIdesc, (EPI == 1 || s > 0) ? 1u : 0u);
+                            tc_mma_i8(tmem_base + q * kTileN, ad, bd, kIdesc, s > 0 ? 1u : 0u);
                         }
                         tc_commit(BAR_T_FULL(q));
                     }
@@ -493,35 +497,19 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         // Warp e: TMEM lane quarter lq = e % 4 (== warp % 4, the quarter this warp may access), column half
         // `half` (64 of the 128 domains of a tile) of the two accumulators qa and qa + 2.  Two warps share
         // each (accumulator, lane quarter), so an accumulator is drained in two chunk-times, and every warp
-        // alternates between two accumulators so that it always has one ready while the other is refilled.
+        // alternates between two accumulators so that one is ready while the other is being refilled.
         const int e = warp - 4;
         const int lq = e & 3, kk = e >> 2;
         const int half = kk & 1, qa = kk >> 1;
         const uint32_t t_lane0 = tmem_base + ((uint32_t)(lq * 32) << 16) + half * 64;
         uint32_t stage = 0, phase = 0, tf_phase = 0;
-        if (EPI == 1) {
-#pragma unroll
-            for (int sl = 0; sl < 2; sl++) {
-                const uint32_t ta = t_lane0 + (qa + 2 * sl) * kTileN;
-#pragma unroll
-                for (int c8 = 0; c8 < 8; c8++) tmem_st8_const(ta + c8 * 8, kMagicBits);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(BAR_T_EMPTY(qa));
-                mbar_arrive(BAR_T_EMPTY(qa + 2));
-            }
-        }
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             int sb = u / n_chunks, ch = u % n_chunks;
             int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
-            // Running filter state of this thread's two rows.  thresh: chunks whose best filter score is
-            // <= thresh cannot hold the reference's winner or one of its float ties.  vR == 0: every
+            // Running filter state of this thread's two rows (see the file header).  vR == 0: every
             // candidate scores error 0 and the first one wins (FC:677-678, FC:627) -> never flag.
             int64_t row[2];
-            float thresh[2], fmax[2], tie_abs[2];
+            float thresh[2], lbmax[2], tie_abs[2];
             int cnt[2];
             int32_t *my_list[2];
 #pragma unroll
@@ -529,14 +517,15 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 row[sl] = (int64_t)sb * kRowsPerSB + (qa + 2 * sl) * kBlockM + lq * 32 + lane;
                 const int vR = vRarr[row[sl]];
                 thresh[sl] = (vR == 0) ? __int_as_float(0x7f800000) : -1.0f;
-                fmax[sl] = 0.0f;
+                lbmax[sl] = 0.0f;
                 tie_abs[sl] = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
                 cnt[sl] = 0;
                 my_list[sl] = flag_list + (((int64_t)ch * rows_padded + row[sl]) * 2 + half) * kFlagCap;
             }
             for (int t = t0; t < t1; t++) {
                 mbar_wait(BAR_B_FULL(stage), phase, status, 6);
-                const uint32_t rsd_s = smem_u32(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES) + half * 64 * 4;
+                // (rhi, rlo) of this warp's two chunks of the tile
+                const float4 bnd = lds_f4(smem_u32(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES) + half * 16);
 #pragma unroll
                 for (int sl = 0; sl < 2; sl++) {
                     const int q = qa + 2 * sl;
@@ -550,49 +539,35 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                             tmem_ld32(ta + cc * 32, v);
                             tmem_ld_wait();
                         }
-                        if (EPI == 1) {  // re-bias the columns just read
-#pragma unroll
-                            for (int c8 = 0; c8 < 4; c8++) tmem_st8_const(ta + cc * 32 + c8 * 8, kMagicBits);
-                        }
                         if (cc == 1) {
-                            // last access to this half of accumulator q for this tile: hand it back
-                            if (EPI == 1) tmem_st_wait();
+                            // last read of this half of accumulator q for this tile: hand it back
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
                         }
-                        if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring math
-                        float m = 0.0f;
+                        if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring
+                        int mx = 0, mn = 0;
 #pragma unroll
-                        for (int k = 0; k < 32; k += 4) {
-                            float4 s4 = lds_f4(rsd_s + (cc * 32 + k) * 4);
-                            float f0, f1, f2, f3;
-                            if (EPI == 1) {
-                                unbias_scale2(v[k + 0], v[k + 1], s4.x, s4.y, f0, f1);
-                                unbias_scale2(v[k + 2], v[k + 3], s4.z, s4.w, f2, f3);
-                            } else {
-                                scale2(__int2float_rn((int)v[k + 0]), __int2float_rn((int)v[k + 1]), s4.x, s4.y, f0, f1);
-                                scale2(__int2float_rn((int)v[k + 2]), __int2float_rn((int)v[k + 3]), s4.z, s4.w, f2, f3);
-                            }
-                            m = fmaxf(fmaxf(m, fabsf(f0)), fabsf(f1));
-                            m = fmaxf(fmaxf(m, fabsf(f2)), fabsf(f3));
+                        for (int k = 0; k < 32; k += 2) {
+                            mx = max(mx, max((int)v[k], (int)v[k + 1]));
+                            mn = min(mn, min((int)v[k], (int)v[k + 1]));
                         }
-                        const int c = half * 2 + cc;  // chunk of the tile
+                        const float M = __int2float_rn(max(mx, -mn));  // max |kov| over the chunk, exact
+                        const int c = half * 2 + cc;                   // chunk of the tile
                         if (DUMP) {
 #pragma unroll
                             for (int k = 0; k < 32; k++)
-                                dump[row[sl] * dump_ld + (int64_t)t * kTileN + c * 32 + k] =
-                                    (int)(v[k] - (EPI == 1 ? kMagicBits : 0u));
+                                dump[row[sl] * dump_ld + (int64_t)t * kTileN + c * 32 + k] = (int)v[k];
                         }
-                        if (m > thresh[sl]) {  // may hold the winner or one of its float ties: exact work is deferred
-                            if (cnt[sl] < kFlagCap) my_list[sl][cnt[sl]] = t * (kTileN / 32) + c;
+                        if (M * (cc ? bnd.z : bnd.x) > thresh[sl]) {  // may hold the winner or one of its float ties
+                            if (cnt[sl] < kFlagCap) my_list[sl][cnt[sl]] = t * kChunksPerTile + c;
                             cnt[sl]++;
-                            fmax[sl] = fmaxf(fmax[sl], m);
-                            thresh[sl] = sqrtf(fmaxf(fmax[sl] * fmax[sl] * kOneMinusEps - tie_abs[sl], 0.0f));
+                            lbmax[sl] = fmaxf(lbmax[sl], M * (cc ? bnd.w : bnd.y));
+                            thresh[sl] = sqrtf(fmaxf(lbmax[sl] * lbmax[sl] * kOneMinusEps - tie_abs[sl], 0.0f));
                         }
                     }
                 }
-                // the tile's scales are consumed
+                // the tile's bounds are consumed
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR_B_EMPTY(stage));
                 tf_phase ^= 1;
@@ -611,53 +586,57 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     }
 }
 
-// Refine: exact evaluation of every candidate of every flagged chunk with the reference's own
-// arithmetic (FC:655-687), one warp per range row, lane = candidate within the chunk; the winner is
-// the lexicographic (error, index) minimum = the reference's first index with the smallest error.
-// A row whose flag list overflowed (adversarial score order) is rescanned in full -- slow, exact.
+// ---------------------------------------------------------------- refine --------------
+
+// Exact score of the candidate at sweep position `pos` for one range row, from the packed
+// operand row (coalesced 16-byte loads): kov = sum r*h + sum r*l + rmean*(-alpha), then the
+// reference's own expression (FC:677-683).  rw[] = the range block as packed u8 words.
 template <int B>
-__device__ __forceinline__ float refine_eval(const int *s_rt, const uint8_t *__restrict__ dec,
-                                             const int32_t *__restrict__ dsum, const int32_t *__restrict__ dsq,
-                                             const Geom &g, int vR, int64_t idx)
+__device__ __forceinline__ float refine_eval_packed(const uint32_t *rw, int rmean, int vR, const uint8_t *__restrict__ opB,
+                                                    int64_t pos, int varD)
 {
-    constexpr int n = B * B;
-    int gx = (int)(idx % g.dpw), gy = (int)(idx / g.dpw);
-    const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
-    int dot = 0;
+    using L = Lay<B>;
+    constexpr int PCH = Cfg<B>::n / 16;
+    const int64_t tile = pos / kTileN;
+    const int row = (int)(pos % kTileN);
+    const uint8_t *rowp = opB + tile * L::B_TILE_BYTES + (row >> 3) * L::SBO_B + (row & 7) * 16;
+    int kov = 0;
 #pragma unroll
-    for (int ry = 0; ry < B; ry++) {
-        const uint8_t *row = p + (int64_t)ry * g.sw;
-        if (B == 8) {  // gx*step and sw are even: 2-byte aligned
-#pragma unroll
-            for (int rx = 0; rx < B; rx += 2) {
-                unsigned v = __ldg((const unsigned short *)(row + rx));
-                dot += s_rt[ry * B + rx] * (int)(v & 0xff) + s_rt[ry * B + rx + 1] * (int)(v >> 8);
-            }
-        } else {
-#pragma unroll
-            for (int rx = 0; rx < B; rx++) dot += s_rt[ry * B + rx] * (int)__ldg(row + rx);
-        }
+    for (int c = 0; c < PCH; c++) {
+        const uint4 h = __ldg((const uint4 *)(rowp + c * 128));
+        const uint4 l = __ldg((const uint4 *)(rowp + (PCH + c) * 128));
+        kov = dp4a_us(rw[4 * c + 0], h.x, kov);
+        kov = dp4a_us(rw[4 * c + 1], h.y, kov);
+        kov = dp4a_us(rw[4 * c + 2], h.z, kov);
+        kov = dp4a_us(rw[4 * c + 3], h.w, kov);
+        kov = dp4a_us(rw[4 * c + 0], l.x, kov);
+        kov = dp4a_us(rw[4 * c + 1], l.y, kov);
+        kov = dp4a_us(rw[4 * c + 2], l.z, kov);
+        kov = dp4a_us(rw[4 * c + 3], l.w, kov);
     }
-    int dmean;
-    int varD = dom_var(dsum[idx], dsq[idx], n, &dmean);
-    return grey_error(dot - dmean * vR, vR, __dsqrt_rn((double)varD));
+    const int neg_alpha = (int)(int8_t)(__ldg((const uint32_t *)(rowp + (2 * PCH) * 128)) & 0xff);
+    kov += rmean * neg_alpha;
+    return grey_error(kov, vR, __dsqrt_rn((double)varD));
 }
 
+// One warp per range row, lane = candidate within a flagged chunk.  The winner is the
+// lexicographic (error, index) minimum over every candidate of every flagged chunk plus domain
+// 0 (which wins when the whole row ties, e.g. all scores 0) = the reference's first index with
+// the smallest error.  A row whose flag list overflowed is rescanned in full -- slow, exact.
 template <int B>
 __global__ void __launch_bounds__(128)
-k_umma_refine(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
-              const int32_t *__restrict__ dsq, const int32_t *__restrict__ rsum,
+k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ opB,
+              const int32_t *__restrict__ pos_dom, const int32_t *__restrict__ pos_var,
               const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
-              int64_t rows_padded, int64_t rows, int32_t *__restrict__ best, Geom g, int64_t j0, uint32_t mult,
-              int64_t nchpad)
+              int64_t rows_padded, int64_t rows, int64_t npos, const int64_t *__restrict__ dom0_pos,
+              int32_t *__restrict__ best, Geom g, int64_t j0)
 {
     constexpr int n = B * B;
-    __shared__ int s_rt_all[4][n];
+    constexpr int NW = n / 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * 4 + warp;
     if (i >= rows) return;
     const int64_t j = j0 + i;
-    int *s_rt = s_rt_all[warp];
     const int rs = rsum[j];
     const int rmean = rs / n, vR = rs - n * rmean;
     if (vR == 0) {  // FC:677-678 + FC:627: all errors are 0, the first candidate wins
@@ -665,33 +644,32 @@ k_umma_refine(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec, 
         return;
     }
     const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
-    for (int k = lane; k < n; k += 32)
-        s_rt[k] = (int)src[(int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)] - rmean;
-    __syncwarp();
+    uint32_t rw[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        const int k = 4 * w;
+        rw[w] = __ldg((const uint32_t *)(src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)));
+    }
     float be = 10000000.0f;  // FC:615
     int bi = 0x7fffffff;
+    auto consider = [&](int64_t pos) {
+        const int idx = pos_dom[pos];
+        if (idx >= 0) {
+            const float err = refine_eval_packed<B>(rw, rmean, vR, opB, pos, pos_var[pos]);
+            if (err < be || (err == be && idx < bi)) { be = err; bi = idx; }
+        }
+    };
+    if (lane == 0) consider(*dom0_pos);
     bool overflow = false;
     for (int lh = 0; lh < 2 * n_chunks && !overflow; lh++) {  // (domain chunk of the unit, column half) lists
         const int64_t li = ((int64_t)(lh >> 1) * rows_padded + i) * 2 + (lh & 1);
         const int cnt = flag_cnt[li];
         if (cnt > kFlagCap) { overflow = true; break; }
         const int32_t *lst = flag_list + li * kFlagCap;
-        for (int e = 0; e < cnt; e++) {
-            const int64_t idx = pos_to_domain((int64_t)lst[e] * 32 + lane, mult, nchpad);
-            if (idx < g.ND) {
-                float err = refine_eval<B>(s_rt, dec, dsum, dsq, g, vR, idx);
-                if (err < be || (err == be && (int)idx < bi)) { be = err; bi = (int)idx; }
-            }
-        }
+        for (int e = 0; e < cnt; e++) consider((int64_t)lst[e] * 32 + lane);
     }
-    if (overflow) {
-        be = 10000000.0f;
-        bi = 0x7fffffff;
-        for (int64_t idx = lane; idx < g.ND; idx += 32) {
-            float err = refine_eval<B>(s_rt, dec, dsum, dsq, g, vR, idx);
-            if (err < be) { be = err; bi = (int)idx; }
-        }
-    }
+    if (overflow)
+        for (int64_t pos = lane; pos < npos; pos += 32) consider(pos);
     for (int o = 16; o > 0; o >>= 1) {
         float e2 = __shfl_down_sync(0xffffffffu, be, o);
         int i2 = __shfl_down_sync(0xffffffffu, bi, o);
@@ -700,15 +678,17 @@ k_umma_refine(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec, 
     if (lane == 0) best[j] = bi == 0x7fffffff ? 0 : bi;
 }
 
+// ---------------------------------------------------------------- host side ------------
+
 inline int64_t pad_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+inline uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
 
 struct Plan {
     int64_t rp;     // rows padded to whole super-blocks
     int n_sb, ntiles, n_chunks;
-    uint32_t mult;  // sweep-order multiplier (see pos_to_domain)
+    uint32_t mult;  // sweep-order multiplier (see sweep_to_sorted)
+    int64_t npos;   // ntiles * 128 sweep positions
 };
-
-inline uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
 
 // Split the domain sweep so that the unit count fills whole waves of num_sms CTAs.
 inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
@@ -717,6 +697,7 @@ inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
     p.rp = pad_up(rows, kRowsPerSB);
     p.n_sb = (int)(p.rp / kRowsPerSB);
     p.ntiles = (int)((g.ND + kTileN - 1) / kTileN);
+    p.npos = (int64_t)p.ntiles * kTileN;
     p.n_chunks = 1;
     double best_eff = 0;
     for (int c = 1; c <= 8 && c <= p.ntiles; c++) {
@@ -725,12 +706,36 @@ inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
         double eff = (double)units / (double)(waves * num_sms);
         if (eff > best_eff + 0.02) { best_eff = eff; p.n_chunks = c; }
     }
-    const uint64_t nchpad = (uint64_t)p.ntiles * (kTileN / 32);
-    uint64_t m = (uint64_t)((double)nchpad * 0.6180339887498949) | 1u;  // golden-ratio stride, odd
-    while (gcd_u64(m, nchpad) != 1) m += 2;
-    p.mult = nchpad <= 8 ? 1u : (uint32_t)(m % nchpad);
+    const uint64_t nch = (uint64_t)p.ntiles * kChunksPerTile;
+    uint64_t m = (uint64_t)((double)nch * 0.6180339887498949) | 1u;  // golden-ratio stride, odd
+    while (gcd_u64(m, nch) != 1) m += 2;
+    p.mult = nch <= 8 ? 1u : (uint32_t)(m % nch);
     return p;
 }
+
+// opB workspace: [tile blobs][pos_dom s32][pos_var s32][dom0 pos s64][sort: keys x2, vals x2, cub temp]
+template <int B>
+struct OpBLayout {
+    size_t off_posdom, off_posvar, off_dom0, off_keys0, off_keys1, off_vals0, off_vals1, off_temp, temp_bytes, total;
+    OpBLayout(const Geom &g, const Plan &p)
+    {
+        size_t o = (size_t)p.ntiles * Lay<B>::B_TILE_BYTES;
+        auto take = [&](size_t bytes) { size_t at = (o + 255) & ~(size_t)255; o = at + bytes; return at; };
+        off_posdom = take((size_t)p.npos * 4);
+        off_posvar = take((size_t)p.npos * 4);
+        off_dom0 = take(8);
+        off_keys0 = take((size_t)g.ND * 4);
+        off_keys1 = take((size_t)g.ND * 4);
+        off_vals0 = take((size_t)g.ND * 4);
+        off_vals1 = take((size_t)g.ND * 4);
+        temp_bytes = 0;
+        cub::DoubleBuffer<uint32_t> dk((uint32_t *)nullptr, (uint32_t *)nullptr);
+        cub::DoubleBuffer<int32_t> dv((int32_t *)nullptr, (int32_t *)nullptr);
+        cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, dk, dv, (int)g.ND, 0, 24);
+        off_temp = take(temp_bytes + 256);
+        total = o + 256;
+    }
+};
 
 template <int B>
 size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
@@ -754,21 +759,33 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     int32_t *vR = (int32_t *)(opA + (size_t)p.n_sb * L::A_SB_BYTES);
     int32_t *flag_cnt = vR + rp;
     int32_t *flag_list = flag_cnt + rp * p.n_chunks * 2;
+    OpBLayout<B> lay(g, p);
+    int32_t *pos_dom = (int32_t *)(w.opB + lay.off_posdom);
+    int32_t *pos_var = (int32_t *)(w.opB + lay.off_posvar);
+    int64_t *dom0 = (int64_t *)(w.opB + lay.off_dom0);
     int launches = 0;
-    k_umma_pack_domains<B><<<(unsigned)(((int64_t)p.ntiles * kTileN + 127) / 128), 128, 0, s>>>(w.dec, w.dsum, w.dsq, w.opB, g, p.ntiles, p.mult);
+    cudaError_t ce;
+    // 1. domains by increasing varD
+    cub::DoubleBuffer<uint32_t> dk((uint32_t *)(w.opB + lay.off_keys0), (uint32_t *)(w.opB + lay.off_keys1));
+    cub::DoubleBuffer<int32_t> dv((int32_t *)(w.opB + lay.off_vals0), (int32_t *)(w.opB + lay.off_vals1));
+    k_umma_sortkeys<<<(unsigned)((g.ND + 255) / 256), 256, 0, s>>>(w.dsum, w.dsq, g.n, g.ND, dk.Current(), dv.Current());
+    size_t temp_bytes = lay.temp_bytes;
+    ce = cub::DeviceRadixSort::SortPairs(w.opB + lay.off_temp, temp_bytes, dk, dv, (int)g.ND, 0, 24, s);
+    if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
+    launches += 4;  // key kernel + radix passes (approximate; they are not the timed kernel)
+    // 2. operand blobs
+    k_umma_pack_domains<B><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(w.dec, w.dsum, w.dsq, dv.Current(), w.opB, pos_dom,
+                                                                           pos_var, dom0, g, p.ntiles, p.mult);
     k_umma_pack_ranges<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
     launches += 2;
+    // 3. the fused search
     using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int32_t *, int32_t *, int, int, int,
                              int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
-    // dbg (probe only): bit 3 selects the magic-bias epilogue; low bits 1 / 3 strip the scoring math / TMEM loads
-    KernelT kern = k_umma_search<B, 0, false, kDefaultEpi>;
-    const int epi = (dbg & 8u) ? 1 : ((dbg & 16u) ? 0 : kDefaultEpi);
-    const int strip = (int)(dbg & 3u);
-    if (dump) kern = epi ? k_umma_search<B, 0, true, 1> : k_umma_search<B, 0, true, 0>;
-    else if (strip == 1) kern = epi ? k_umma_search<B, 1, false, 1> : k_umma_search<B, 1, false, 0>;
-    else if (strip == 3) kern = epi ? k_umma_search<B, 3, false, 1> : k_umma_search<B, 3, false, 0>;
-    else kern = epi ? k_umma_search<B, 0, false, 1> : k_umma_search<B, 0, false, 0>;
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
+    KernelT kern = k_umma_search<B, 0, false>;  // dbg (probe only): 1 / 3 strip the scoring / the TMEM loads too
+    if (dump) kern = k_umma_search<B, 0, true>;
+    else if ((dbg & 3u) == 1) kern = k_umma_search<B, 1, false>;
+    else if ((dbg & 3u) == 3) kern = k_umma_search<B, 3, false>;
+    ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
     int n_units = p.n_sb * p.n_chunks;
     int grid = n_units < num_sms ? n_units : num_sms;
@@ -778,9 +795,9 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     kern<<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, flag_list, flag_cnt, p.n_sb, p.n_chunks, p.ntiles, rp,
                                                dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
     if (k1) cudaEventRecord(k1, s);
-    k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, flag_list, flag_cnt,
-                                                                p.n_chunks, rp, rows, w.best, g, j0, p.mult,
-                                                                (int64_t)p.ntiles * (kTileN / 32));
+    // 4. exact refine of the flagged chunks
+    k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, w.opB, pos_dom, pos_var, flag_list, flag_cnt,
+                                                                p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
     launches += 2;
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
@@ -789,11 +806,13 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
 
 }  // namespace
 
-void umma_sweep_order(const Geom &g, int64_t rows, int num_sms, uint32_t *mult, int64_t *nchpad)
+void umma_debug_positions(const Work &w, const Geom &g, int64_t rows, int num_sms, const int32_t **d_pos_dom,
+                          int64_t *npos)
 {
     Plan p = make_plan(g, rows, num_sms);
-    *mult = p.mult;
-    *nchpad = (int64_t)p.ntiles * (kTileN / 32);
+    *npos = p.npos;
+    if (g.B == 8) *d_pos_dom = (const int32_t *)(w.opB + OpBLayout<8>(g, p).off_posdom);
+    else *d_pos_dom = (const int32_t *)(w.opB + OpBLayout<4>(g, p).off_posdom);
 }
 
 bool umma_applicable(const Geom &g)
@@ -808,8 +827,8 @@ size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms)
 
 size_t umma_opB_bytes(const Geom &g)
 {
-    int64_t ntiles = (g.ND + kTileN - 1) / kTileN;
-    return (size_t)ntiles * (g.B == 8 ? Lay<8>::B_TILE_BYTES : Lay<4>::B_TILE_BYTES);
+    Plan p = make_plan(g, kRowsPerSB, 148);  // the opB layout depends on the pool only
+    return g.B == 8 ? OpBLayout<8>(g, p).total : OpBLayout<4>(g, p).total;
 }
 
 int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s,
@@ -820,7 +839,7 @@ int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int
 }
 
 // Debug entry used by tools/umma_probe: also dumps the raw accumulators (kov) of every
-// (row, domain) pair, and lets the probe pick the descriptor variant.
+// (row, sweep position) pair, and lets the probe pick the descriptor variant.
 int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s,
                              const char **err, int32_t *dump, int64_t dump_ld, int *status_dev, int variant,
                              uint32_t dbg, cudaEvent_t k0, cudaEvent_t k1)

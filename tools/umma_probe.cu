@@ -166,14 +166,14 @@ int main(int argc, char **argv)
         std::vector<uint8_t> dec((size_t)g.sw * g.sh);
         CK(cudaMemcpy(dec.data(), w.dec, dec.size(), cudaMemcpyDeviceToHost));
         long long bad = 0, shown = 0;
-        uint32_t mult;
-        int64_t nchpad;
-        umma_sweep_order(g, g.NR, prop.multiProcessorCount, &mult, &nchpad);
+        const int32_t *d_pos_dom;
+        int64_t npos;
+        umma_debug_positions(w, g, g.NR, prop.multiProcessorCount, &d_pos_dom, &npos);
+        std::vector<int32_t> pos_dom(npos);
+        CK(cudaMemcpy(pos_dom.data(), d_pos_dom, npos * 4, cudaMemcpyDeviceToHost));
         std::vector<int64_t> pos_of(g.ND, -1);
-        for (int64_t p = 0; p < nchpad * 32; p++) {
-            int64_t j = (int64_t)((((uint64_t)(p >> 5) * mult) % (uint64_t)nchpad) * 32 + (p & 31));
-            if (j < g.ND) pos_of[j] = p;
-        }
+        for (int64_t p = 0; p < npos; p++)
+            if (pos_dom[p] >= 0) pos_of[pos_dom[p]] = p;
         for (int64_t j = 0; j < g.ND; j++)
             if (pos_of[j] < 0) { printf("sweep order is not a permutation (domain %lld missing)\n", (long long)j); return 1; }
         for (int64_t i = 0; i < g.NR; i++) {
