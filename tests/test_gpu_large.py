@@ -46,3 +46,24 @@ def test_roundtrip_2048(fic, handle):
     for j0, j1 in [(0, 256 * 100), (256 * 100, 256 * 256)]:
         handle.encode(img, 8, wk, rgb=False, range_begin=j0, range_end=j1, info=info2, q=q2)
     assert (q2 == q).all()
+
+
+@pytest.mark.parametrize("W,B,period", [(1024, 8, 16), (512, 4, 8)])
+def test_periodic_image_ties_and_flag_overflow(fic, handle, W, B, period):
+    """A tiled texture makes thousands of domains identical: every copy of the best domain ties, the
+    reference keeps the lowest index, and the tcgen05 path's per-row flag lists overflow (the refine
+    step then rescans those rows in full).  Both engines must still agree on every code."""
+    tile = fic.synth.noise(period, period, 5)
+    p = np.tile(tile, (W // period, W // period))
+    p = p.copy()
+    p[::64, ::64] ^= 1  # a few irregularities so that not every range block is the same
+    img = fic.synth.grey_to_argb(p)
+    wk = 2 * W // B - 3
+    handle.set_engine(fic.FIC_ENGINE_DIRECT)
+    i1, q1 = handle.encode(img, B, wk, rgb=False)
+    handle.set_engine(fic.FIC_ENGINE_UMMA)
+    i2, q2 = handle.encode(img, B, wk, rgb=False)
+    handle.set_engine(fic.FIC_ENGINE_AUTO)
+    from test_gpu_parity import float_bits_equal
+
+    assert (q1 == q2).all() and float_bits_equal(i1, i2)
