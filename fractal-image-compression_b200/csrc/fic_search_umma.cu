@@ -107,7 +107,8 @@ struct Lay {
     static constexpr int A_SB_BYTES = kAccs * A_BLOCK_BYTES;
     static constexpr int B_OP_BYTES = (kTileN / 8) * SBO_B;
     static constexpr int B_TILE_BYTES = B_OP_BYTES + kBoundBytes;
-    static constexpr int SMEM_BYTES = A_SB_BYTES + C::NSTAGE * B_TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = A_SB_BYTES + C::NSTAGE * B_TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+                                      kRowsPerSB * 4 /*per-row lower bound shared by the two column halves*/;
 };
 
 // ---------------------------------------------------------------- sweep order --------
@@ -403,6 +404,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     const uint32_t BAR_A_FULL = bar0 + 8u * (2 * NSTAGE + 2 * kAccs);
     const uint32_t BAR_A_EMPTY = BAR_A_FULL + 8u;
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * NSTAGE + 2 * kAccs + 2);
+    uint32_t *s_lb = (uint32_t *)((uint8_t *)bars + 256);  // [kRowsPerSB] binary32 bits of the row's lower bound
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -512,6 +514,15 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             float thresh[2], lbmax[2], tie_abs[2];
             int cnt[2];
             int32_t *my_list[2];
+            uint32_t *sh_lb[2];
+            // the previous unit's bounds are dead once all 16 epilogue warps are here; reset them
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+                sh_lb[sl] = s_lb + (qa + 2 * sl) * kBlockM + lq * 32 + lane;
+                if (half == 0) *sh_lb[sl] = 0u;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 #pragma unroll
             for (int sl = 0; sl < 2; sl++) {
                 row[sl] = (int64_t)sb * kRowsPerSB + (qa + 2 * sl) * kBlockM + lq * 32 + lane;
@@ -532,6 +543,13 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     const uint32_t ta = t_lane0 + q * kTileN;
                     mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
                     tc_fence_after();
+                    {   // adopt a better lower bound found by the warp that scans the other column half
+                        const float other = __uint_as_float(*(volatile uint32_t *)sh_lb[sl]);
+                        if (other > lbmax[sl]) {
+                            lbmax[sl] = other;
+                            thresh[sl] = sqrtf(fmaxf(other * other * kOneMinusEps - tie_abs[sl], 0.0f));
+                        }
+                    }
 #pragma unroll
                     for (int cc = 0; cc < 2; cc++) {
                         uint32_t v[32];
@@ -562,8 +580,12 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                         if (M * (cc ? bnd.z : bnd.x) > thresh[sl]) {  // may hold the winner or one of its float ties
                             if (cnt[sl] < kFlagCap) my_list[sl][cnt[sl]] = t * kChunksPerTile + c;
                             cnt[sl]++;
-                            lbmax[sl] = fmaxf(lbmax[sl], M * (cc ? bnd.w : bnd.y));
-                            thresh[sl] = sqrtf(fmaxf(lbmax[sl] * lbmax[sl] * kOneMinusEps - tie_abs[sl], 0.0f));
+                            const float lb = M * (cc ? bnd.w : bnd.y);
+                            if (lb > lbmax[sl]) {
+                                lbmax[sl] = lb;
+                                atomicMax(sh_lb[sl], __float_as_uint(lb));  // positive floats order like their bits
+                                thresh[sl] = sqrtf(fmaxf(lb * lb * kOneMinusEps - tie_abs[sl], 0.0f));
+                            }
                         }
                     }
                 }
