@@ -313,7 +313,10 @@ def run_ours(args):
         "peak_source": f"2 x bf16_tflops ({pk['bf16_tflops']}) of {pk_kind} (MEASURED_PEAKS.json has no int8 entry; "
                        f"nominal dense int8 is 4500)",
         "frac_of_nominal_4500": achieved / 4500.0, "kernel_ms": k_ms, "search_ms": statistics.mean(search_ms),
-        "pool_ms": statistics.mean(pool_ms), "traffic": None,
+        "pool_ms": statistics.mean(pool_ms),
+        # dram__bytes_read.sum + dram__bytes_write.sum of one k_umma_search launch from `ncu --set full`
+        # (profiles/r1_k_umma_search_4096x4096_B8_raw.txt); only known for the profiled workload
+        "traffic": 1428918000 if (engine == fic.FIC_ENGINE_UMMA and size == 4096 and B == 8 and world == 1) else None,
     }
     line = {
         "metric": "encode_evals_per_s", "value": value / 1e9, "unit": "Gevals/s",
