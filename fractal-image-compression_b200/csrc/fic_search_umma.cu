@@ -29,7 +29,9 @@
 // order.
 //
 // How kov becomes one u8 x s8 GEMM.  With dt = d - dmean_j (|dt| <= 254 for B <= 8),
-// split dt = h + l, h = dt >> 1, l = dt - h (both fit s8).  Then
+// split dt = h + l, h = clamp(dt, -128, 127), l = dt - h (both fit s8; l is zero unless a
+// pixel is more than 127 grey levels from its block mean, so the MMA issuer skips the l
+// K-slices of every domain tile whose `l` digits are all zero -- most tiles).  Then
 //     kov = sum_k r_k * h_k + sum_k r_k * l_k + rmean_i * (-alpha_j),   alpha_j = sum d - n*dmean_j
 // i.e. A row = [ r | r | rmean 0.. ] (u8) and B row = [ h | l | -alpha 0.. ] (s8), K
 // padded to a multiple of 32 (one kind::i8 MMA consumes K = 32).  The duplicated `r`
@@ -73,7 +75,7 @@ constexpr int kRowsPerSB = kBlockM * kAccs;
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kChunksPerTile = kTileN / 32;
-constexpr int kBoundBytes = kChunksPerTile * 2 * 4;  // (rhi, rlo) f32 per 32-column chunk
+constexpr int kBoundBytes = kChunksPerTile * 2 * 4 + 16;  // (rhi, rlo) f32 per 32-column chunk + tile flags (u32 + pad)
 constexpr int kFlagCap = 32;                         // flagged chunks kept per (row, unit, column half)
 constexpr float kOneMinusEps = 1.0f - 1.9073486328125e-06f;  // 1 - 2^-19 (applied to the squared score)
 
@@ -87,6 +89,7 @@ struct Cfg<8> {
     static constexpr int NS = 5;     // MMA K-slices
     static constexpr int NSTAGE = 7;
     __host__ __device__ static constexpr int amap(int s) { return s < 4 ? (s & 1) : 2; }
+    __host__ __device__ static constexpr bool is_l_slice(int s) { return s == 2 || s == 3; }
 };
 template <>
 struct Cfg<4> {
@@ -96,6 +99,7 @@ struct Cfg<4> {
     static constexpr int NS = 2;
     static constexpr int NSTAGE = 8;
     __host__ __device__ static constexpr int amap(int s) { return s; }
+    __host__ __device__ static constexpr bool is_l_slice(int) { return false; }  // h and l share slice 0
 };
 
 template <int B>
@@ -151,7 +155,6 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
     using L = Lay<B>;
     constexpr int n = Cfg<B>::n;
     const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= ntiles * kTileN) return;  // whole warps only: ntiles * 128 is a multiple of 32
     const int64_t tile = pos / kTileN;
     const int row = (int)(pos % kTileN);
     const int64_t sp = sweep_to_sorted(pos, mult, ntiles * kChunksPerTile);
@@ -159,6 +162,7 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
     uint8_t *rowp = blob + (row >> 3) * L::SBO_B + (row & 7) * 16;
     constexpr int NCH = Cfg<B>::KS_B * 2;  // 16-byte chunks per row
     float rsd_hi = 0.0f, rsd_lo = __int_as_float(0x7f800000);
+    int any_l = 0;
     if (sp >= g.ND) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
@@ -182,8 +186,9 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
                 for (int e = 0; e < 4; e++) {
                     int k = c * 16 + w * 4 + e;
                     int dt = (int)__ldg(p + (int64_t)(k / B) * g.sw + (k % B)) - dmean;
-                    hv[e] = dt >> 1;
+                    hv[e] = max(-128, min(127, dt));  // the low digit is zero unless |dt| > 127
                     lv[e] = dt - hv[e];
+                    any_l |= lv[e];
                 }
                 hw[w] = pack4(hv[0], hv[1], hv[2], hv[3]);
                 lw[w] = pack4(lv[0], lv[1], lv[2], lv[3]);
@@ -210,6 +215,9 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
         if (rsd_hi == 0.0f) rsd_lo = 0.0f;  // chunk of flat / padding columns only
         *(float2 *)(blob + L::B_OP_BYTES + (row >> 5) * 8) = make_float2(rsd_hi, rsd_lo);
     }
+    // One block == one tile (blockDim == kTileN): does any column of the tile need its low digit?
+    const int tile_has_l = __syncthreads_or(any_l != 0);
+    if (threadIdx.x == 0) *(uint4 *)(blob + L::B_OP_BYTES + kChunksPerTile * 8) = make_uint4((uint32_t)tile_has_l, 0, 0, 0);
 }
 
 // One thread per (padded) range row of the slice [j0, j1): raw pixels + integer mean.
@@ -472,6 +480,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 mbar_wait(BAR_B_FULL(stage), phase, status, 4);
                 tc_fence_after();
                 const uint64_t b_desc = b_desc0 + (uint64_t)((stage * L::B_TILE_BYTES) >> 4);
+                // tile flag written by k_umma_pack_domains: 0 -> every low digit of the tile is zero
+                const uint32_t has_l = *(volatile const uint32_t *)(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES + kChunksPerTile * 8);
 #pragma unroll
                 for (int q = 0; q < kAccs; q++) {
                     mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ 1, status, 5);
@@ -479,6 +489,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     if (elected) {
 #pragma unroll
                         for (int s = 0; s < C::NS; s++) {
+                            if (C::is_l_slice(s) && !has_l) continue;  // sum r*l == 0 for the whole tile
                             const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + C::amap(s) * 256) >> 4);
                             const uint64_t bd = b_desc + (uint64_t)((s * 256) >> 4);
                             tc_mma_i8(tmem_base + q * kTileN, ad, bd, kIdesc, s > 0 ? 1u : 0u);
@@ -564,13 +575,15 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                             if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
                         }
                         if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring
-                        int mx = 0, mn = 0;
+                        int mx0 = 0, mn0 = 0, mx1 = 0, mn1 = 0;  // two independent chains each: ALU latency
 #pragma unroll
-                        for (int k = 0; k < 32; k += 2) {
-                            mx = max(mx, max((int)v[k], (int)v[k + 1]));
-                            mn = min(mn, min((int)v[k], (int)v[k + 1]));
+                        for (int k = 0; k < 32; k += 4) {
+                            mx0 = max(mx0, max((int)v[k], (int)v[k + 1]));
+                            mn0 = min(mn0, min((int)v[k], (int)v[k + 1]));
+                            mx1 = max(mx1, max((int)v[k + 2], (int)v[k + 3]));
+                            mn1 = min(mn1, min((int)v[k + 2], (int)v[k + 3]));
                         }
-                        const float M = __int2float_rn(max(mx, -mn));  // max |kov| over the chunk, exact
+                        const float M = __int2float_rn(max(max(mx0, mx1), -min(mn0, mn1)));  // max |kov|, exact
                         const int c = half * 2 + cc;                   // chunk of the tile
                         if (DUMP) {
 #pragma unroll
