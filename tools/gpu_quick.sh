@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+P=fractal-image-compression_b200/lib/umma_probe
+for args in "check 8 256 0 1 0" "check 4 128 0 1 0" "check 8 128 0 2 0"; do
+  echo "== probe $args =="; timeout 120 $P $args > gpurun_out/probe_check.log 2>&1; echo "rc=$?"; grep -E "accumulator|winner check|PROBE|rror|mismatch" gpurun_out/probe_check.log | head -8
+done
+for d in 0 1 3; do
+  echo "== probe time 2048 dbg=$d =="; timeout 300 $P time 8 2048 0 1 $d > gpurun_out/probe_2048_dbg$d.log 2>&1; echo "rc=$?"; grep -E "run 2|winner|rror" gpurun_out/probe_2048_dbg$d.log
+done
+echo "== probe time 4096 =="; timeout 600 $P time 8 4096 0 1 0 > gpurun_out/probe_4096.log 2>&1; echo "rc=$?"; grep -E "run 2|umma:|winner|rror" gpurun_out/probe_4096.log
+echo "== probe time 2048 B=4 =="; timeout 600 $P time 4 2048 0 1 0 > gpurun_out/probe_b4_2048.log 2>&1; echo "rc=$?"; grep -E "run 2|umma:|winner|rror" gpurun_out/probe_b4_2048.log
+echo "== pytest gpu (all) =="; timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/pytest_gpu.log
+echo "== bench =="; timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
