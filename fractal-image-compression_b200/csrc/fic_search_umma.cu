@@ -73,8 +73,7 @@ constexpr int kBlockM = 128;       // rows per accumulator == MMA M
 constexpr int kAccs = 4;           // accumulators per tile (TMEM: 4 x 128 columns)
 constexpr int kRowsPerSB = kBlockM * kAccs;
 constexpr int kEpiWarps = 16;
-constexpr int kFirstEpiWarp = 3;  // warps 0..2: TMA producer, MMA issuer, TMEM allocator
-constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;  // 608: leaves 104 registers per thread
+constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kChunksPerTile = kTileN / 32;
 constexpr int kBoundBytes = kChunksPerTile * 2 * 4 + 16;  // (rhi, rlo) f32 per 32-column chunk + tile flags (u32 + pad)
 constexpr int kFlagCap = 32;                         // flagged chunks kept per (row, unit, column half)
@@ -506,13 +505,14 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             __syncwarp();
             a_phase ^= 1;
         }
-    } else if (warp >= kFirstEpiWarp) {
+    } else if (warp >= 4) {
         // ===================== epilogue =====================
-        // Epilogue warp: TMEM lane quarter lq = warp % 4 (the quarter the hardware lets it access), column half
+        // Warp e: TMEM lane quarter lq = e % 4 (== warp % 4, the quarter this warp may access), column half
         // `half` (64 of the 128 domains of a tile) of the two accumulators qa and qa + 2.  Two warps share
         // each (accumulator, lane quarter), so an accumulator is drained in two chunk-times, and every warp
         // alternates between two accumulators so that one is ready while the other is being refilled.
-        const int lq = warp & 3, kk = (warp - kFirstEpiWarp) >> 2;
+        const int e = warp - 4;
+        const int lq = e & 3, kk = e >> 2;
         const int half = kk & 1, qa = kk >> 1;
         const uint32_t t_lane0 = tmem_base + ((uint32_t)(lq * 32) << 16) + half * 64;
         uint32_t stage = 0, phase = 0, tf_phase = 0;
@@ -561,33 +561,34 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                             thresh[sl] = sqrtf(fmaxf(other * other * kOneMinusEps - tie_abs[sl], 0.0f));
                         }
                     }
-                    uint32_t v[2][32];
-                    if (!(DBG & 2)) {
-                        tmem_ld32(ta, v[0]);
-                        tmem_ld32(ta + 32, v[1]);
-                        tmem_ld_wait();
-                    }
-                    // both chunks of this half of accumulator q are in registers: hand it back to the MMA issuer
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
-                    if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring
 #pragma unroll
                     for (int cc = 0; cc < 2; cc++) {
+                        uint32_t v[32];
+                        if (!(DBG & 2)) {
+                            tmem_ld32(ta + cc * 32, v);
+                            tmem_ld_wait();
+                        }
+                        if (cc == 1) {
+                            // last read of this half of accumulator q for this tile: hand it back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
+                        }
+                        if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring
                         int mx0 = 0, mn0 = 0, mx1 = 0, mn1 = 0;  // two independent chains each: ALU latency
 #pragma unroll
                         for (int k = 0; k < 32; k += 4) {
-                            mx0 = max(mx0, max((int)v[cc][k], (int)v[cc][k + 1]));
-                            mn0 = min(mn0, min((int)v[cc][k], (int)v[cc][k + 1]));
-                            mx1 = max(mx1, max((int)v[cc][k + 2], (int)v[cc][k + 3]));
-                            mn1 = min(mn1, min((int)v[cc][k + 2], (int)v[cc][k + 3]));
+                            mx0 = max(mx0, max((int)v[k], (int)v[k + 1]));
+                            mn0 = min(mn0, min((int)v[k], (int)v[k + 1]));
+                            mx1 = max(mx1, max((int)v[k + 2], (int)v[k + 3]));
+                            mn1 = min(mn1, min((int)v[k + 2], (int)v[k + 3]));
                         }
                         const float M = __int2float_rn(max(max(mx0, mx1), -min(mn0, mn1)));  // max |kov|, exact
-                        const int c = half * 2 + cc;  // chunk of the tile
+                        const int c = half * 2 + cc;                   // chunk of the tile
                         if (DUMP) {
 #pragma unroll
                             for (int k = 0; k < 32; k++)
-                                dump[row[sl] * dump_ld + (int64_t)t * kTileN + c * 32 + k] = (int)v[cc][k];
+                                dump[row[sl] * dump_ld + (int64_t)t * kTileN + c * 32 + k] = (int)v[k];
                         }
                         if (M * (cc ? bnd.z : bnd.x) > thresh[sl]) {  // may hold the winner or one of its float ties
                             if (cnt[sl] < kFlagCap) my_list[sl][cnt[sl]] = t * kChunksPerTile + c;
