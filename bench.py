@@ -335,6 +335,19 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": roofline,
     }
+    if world == 1:
+        # verification leg (untimed part of the contract): the GPU decoder reconstructs the image from the
+        # quantised codes just produced; PSNR against the source is what fractal coding reaches on this content
+        q_host = d_q.cpu().numpy()
+        handle.set_stream(None)
+        t0 = time.perf_counter()
+        dec, avg_err, iters = handle.decode(q_host, size, size, B, wk, False)
+        t_dec = time.perf_counter() - t0
+        rec = ((dec.view(np.uint32) >> 16) & 0xFF).astype(np.float64)
+        mse = float(np.mean((rec - plane.astype(np.float64)) ** 2))
+        line["decode"] = {"iterations": int(iters), "avg_error": float(avg_err), "psnr_db": 10 * np.log10(255.0 ** 2 / max(mse, 1e-12)),
+                          "ms_total_host_clock": t_dec * 1e3, "device_ms": handle.timings().total_ms,
+                          "mpixel_per_s_per_sweep": size * size * iters / max(handle.timings().total_ms, 1e-9) / 1e3}
     if world == 1 and not args.no_cpu_baseline:
         R, tcpu, t_pool = cpu_sample(plane, B, wk, 1, args.cpu_seconds)
         v = R * ND / tcpu

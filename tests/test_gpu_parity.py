@@ -245,3 +245,31 @@ def test_facade_roundtrip(fic, oracle, lena_grey):
     oimg, oavg, _ = oracle.decode(stream)
     assert (dec.argb == oimg).all() and FC.getAvgError() == oavg
     assert (collage.argb == oracle.collage(lena_grey, oinfo.copy(), 8, 4)).all()
+
+
+def test_cpp_host_cli_roundtrip(tmp_path, oracle, lena_grey):
+    """The C++ mirror of the reference facade (host/fractal_compression.hpp) through its headless CLI:
+    encode + decode of LenaGrey at the reference defaults must print the oracle's avgError."""
+    import subprocess
+
+    from conftest import ROOT
+
+    cli = os.path.join(ROOT, "fractal-image-compression_b200", "lib", "fic_cli")
+    if not os.path.exists(cli):
+        pytest.skip("fic_cli not built")
+    pgm = tmp_path / "lena.pgm"
+    plane = ((lena_grey.view(np.uint32) >> 16) & 0xFF).astype(np.uint8)
+    with open(pgm, "wb") as f:
+        f.write(b"P5\n256 256\n255\n" + plane.tobytes())
+    run = tmp_path / "lena.run"
+    subprocess.run([cli, "encode", str(pgm), str(run), "8", "2"], check=True, capture_output=True, text=True)
+    want = oracle.write_data(oracle.encode(lena_grey, 8, 2), 256, 256, 8, 2)
+    assert open(run, "rb").read() == want
+    out = tmp_path / "dec.pgm"
+    r = subprocess.run([cli, "decode", str(run), str(out)], check=True, capture_output=True, text=True)
+    _, oavg, oit = oracle.decode(want)
+    assert f"({oit} iterations)" in r.stdout
+    assert abs(float(r.stdout.split()[1]) - float(oavg)) < 1e-9
+    dec = np.frombuffer(open(out, "rb").read().split(b"255\n", 1)[1], np.uint8).reshape(256, 256)
+    oimg, _, _ = oracle.decode(want)
+    assert (dec == ((oimg.view(np.uint32) >> 16) & 0xFF)).all()
