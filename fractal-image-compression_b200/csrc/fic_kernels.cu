@@ -113,8 +113,43 @@ __global__ void k_decimate(const uint8_t *__restrict__ src, uint8_t *__restrict_
     }
 }
 
+// Vector path (W % 16 == 0): one thread makes 8 output pixels from two 16-byte loads, one 8-byte store.
+__global__ void k_decimate_v8(const uint8_t *__restrict__ src, uint8_t *__restrict__ dec, int W, int H, int C)
+{
+    const int sw = W / 2, sh = H / 2;
+    const int64_t oct_per_plane = (int64_t)(sw / 8) * sh;
+    const int64_t total = oct_per_plane * C;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool rgb = C == 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i / oct_per_plane);
+        const int64_t k = i - c * oct_per_plane;
+        const int qy = (int)(k / (sw / 8)), o8 = (int)(k % (sw / 8));
+        const uint8_t *p = src + (int64_t)c * W * H + (int64_t)(2 * qy) * W + 16 * o8;
+        const uint4 a = __ldg((const uint4 *)p);
+        const uint4 b = __ldg((const uint4 *)(p + W));
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        uint32_t out[2] = {0, 0};
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const int x0 = 16 * o8 + 4 * w;
+            const int v0 = dec_tap4(aw[w] & 0xff, (aw[w] >> 8) & 0xff, bw[w] & 0xff, (bw[w] >> 8) & 0xff, x0, H, rgb);
+            const int v1 = dec_tap4((aw[w] >> 16) & 0xff, aw[w] >> 24, (bw[w] >> 16) & 0xff, bw[w] >> 24, x0 + 2, H, rgb);
+            out[w >> 1] |= ((uint32_t)v0 | ((uint32_t)v1 << 8)) << (16 * (w & 1));
+        }
+        *(uint2 *)(dec + (int64_t)c * sw * sh + (int64_t)qy * sw + 8 * o8) = make_uint2(out[0], out[1]);
+    }
+}
+
 int launch_decimate(const uint8_t *d_src, uint8_t *d_dec, const Geom &g, cudaStream_t s)
 {
+    if (g.W % 16 == 0) {
+        int64_t total = (int64_t)(g.sw / 8) * g.sh * g.C;
+        int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        if (blocks < 1) blocks = 1;
+        k_decimate_v8<<<blocks, 256, 0, s>>>(d_src, d_dec, g.W, g.H, g.C);
+        return 1;
+    }
     int64_t total = (int64_t)(g.sw / 2) * g.sh * g.C;
     int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     if (blocks < 1) blocks = 1;
@@ -605,9 +640,97 @@ k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, ui
     }
 }
 
+// Vector path (W % 8 == 0): one thread owns an 8 x 2 pixel strip (four quads): 8-byte loads of the old
+// pixels, 8-byte stores of the new ones, one 4-byte store of the new decimated pixels; the 16 domain
+// bytes are gathered from the (L2-resident) decimated plane.
+template <int C>
+__global__ void __launch_bounds__(256)
+k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, uint8_t *__restrict__ dec_out,
+                  const float *__restrict__ code, Geom g, unsigned long long *acc, int32_t *__restrict__ perr)
+{
+    const int sw8 = g.W / 8;
+    const int64_t strips = (int64_t)sw8 * (g.H / 2);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long local = 0;
+    if (t < strips) {
+        const int qy = (int)(t / sw8), s8 = (int)(t - (int64_t)qy * sw8);
+        const int y = 2 * qy, x0 = 8 * s8;
+        constexpr int S = C == 1 ? 3 : 5;
+        const int64_t planeI = (int64_t)g.W * g.H, planeD = (int64_t)g.sw * g.sh;
+        const int yr = y / g.B, ry = y - yr * g.B;
+        int e[4][4];
+#pragma unroll
+        for (int qd = 0; qd < 4; qd++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) e[qd][k] = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            uint8_t *pi = img + c * planeI + (int64_t)y * g.W + x0;
+            const uint2 o0 = *(const uint2 *)pi, o1 = *(const uint2 *)(pi + g.W);
+            const uint32_t old0[2] = {o0.x, o0.y}, old1[2] = {o1.x, o1.y};
+            uint32_t n0[2] = {0, 0}, n1[2] = {0, 0}, nd = 0;
+#pragma unroll
+            for (int qd = 0; qd < 4; qd++) {
+                const int x = x0 + 2 * qd;
+                const int xr = x / g.B, rx = x - xr * g.B;
+                const float *cd = code + S * ((int64_t)yr * g.rpw + xr);
+                const int idx = j_f2i(cd[0]);  // FC:394 (int) imgData[i][0]
+                const float a = cd[1], b = cd[2 + c];
+                const int gx = idx % g.dpw, gy = idx / g.dpw;
+                const uint8_t *pd = dec_in + c * planeD + (int64_t)(gy * g.step + ry) * g.sw + gx * g.step + rx;
+                const int d00 = pd[0], d10 = pd[1], d01 = pd[g.sw], d11 = pd[g.sw + 1];
+                // FC:396 / FC:482: (int)(a * domain + b), float multiply then float add
+                const int v00 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d00), b)));
+                const int v10 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d10), b)));
+                const int v01 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d01), b)));
+                const int v11 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d11), b)));
+                const int sh = 16 * (qd & 1);
+                const int p00 = (old0[qd >> 1] >> sh) & 0xff, p10 = (old0[qd >> 1] >> (sh + 8)) & 0xff;
+                const int p01 = (old1[qd >> 1] >> sh) & 0xff, p11 = (old1[qd >> 1] >> (sh + 8)) & 0xff;
+                e[qd][0] += (p00 - v00) * (p00 - v00);  // FC:407 / FC:493
+                e[qd][1] += (p10 - v10) * (p10 - v10);
+                e[qd][2] += (p01 - v01) * (p01 - v01);
+                e[qd][3] += (p11 - v11) * (p11 - v11);
+                n0[qd >> 1] |= ((uint32_t)v00 | ((uint32_t)v10 << 8)) << sh;
+                n1[qd >> 1] |= ((uint32_t)v01 | ((uint32_t)v11 << 8)) << sh;
+                nd |= (uint32_t)dec_tap4(v00, v10, v01, v11, x, g.H, C == 3) << (8 * qd);
+            }
+            *(uint2 *)pi = make_uint2(n0[0], n0[1]);
+            *(uint2 *)(pi + g.W) = make_uint2(n1[0], n1[1]);
+            if (dec_out) *(uint32_t *)(dec_out + c * planeD + (int64_t)qy * g.sw + 4 * s8) = nd;
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; qd++) {
+            local += (unsigned long long)(e[qd][0] + e[qd][1] + e[qd][2] + e[qd][3]);
+            if (perr) {
+                const int x = x0 + 2 * qd;
+                const int xr = x / g.B, rx = x - xr * g.B;
+                int32_t *pe = perr + ((int64_t)yr * g.rpw + xr) * g.n + ry * g.B + rx;
+                pe[0] = e[qd][0];
+                pe[1] = e[qd][1];
+                pe[g.B] = e[qd][2];
+                pe[g.B + 1] = e[qd][3];
+            }
+        }
+    }
+    if (acc) {
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(acc, local);
+    }
+}
+
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out, const float *d_code,
                         const Geom &g, unsigned long long *d_acc, int32_t *d_perr, cudaStream_t s)
 {
+    if (g.W % 8 == 0) {
+        int64_t strips = (int64_t)(g.W / 8) * (g.H / 2);
+        unsigned blocks = (unsigned)((strips + 255) / 256);
+        if (g.C == 1)
+            k_decode_sweep_v8<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, g, d_acc, d_perr);
+        else
+            k_decode_sweep_v8<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, g, d_acc, d_perr);
+        return 1;
+    }
     int64_t quads = (int64_t)(g.W / 2) * (g.H / 2);
     unsigned blocks = (unsigned)((quads + 255) / 256);
     if (g.C == 1)

@@ -1,0 +1,21 @@
+"""Runs the HBM-bound kernels (K1 pool builder, K4 decoder) once at 4096^2 so that ncu can capture them."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fractal_image_compression_b200 as fic  # noqa: E402
+
+W = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+img = fic.synth.grey_to_argb(fic.synth.structured(W, W, 1))
+h = fic.Handle(0)
+info, q = h.encode(img, 8, 2, rgb=False)         # reference default window: K1 + direct search + solve
+t = h.timings()
+print(f"encode wk=2: total {t.total_ms:.3f} ms (h2d {t.h2d_ms:.3f}, pool {t.pool_ms:.3f}, search {t.search_ms:.3f}, d2h {t.d2h_ms:.3f})")
+info, q = h.encode(img, 8, 16, rgb=False)
+t = h.timings()
+print(f"encode wk=16: total {t.total_ms:.3f} ms (pool {t.pool_ms:.3f}, search {t.search_ms:.3f})")
+dec, avg, it = h.decode(q, W, W, 8, 16, False)
+t = h.timings()
+print(f"decode: {it} sweeps, avgError {avg}, device {t.total_ms:.3f} ms -> {W * W * it / t.total_ms / 1e3:.1f} Mpixel/s per sweep")
