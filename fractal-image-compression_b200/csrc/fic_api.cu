@@ -403,7 +403,7 @@ int fic_decode(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int
     int S = is_rgb ? 5 : 3;
     size_t plane = (size_t)W * H;
     ENSURE(w.q, S_Q, sizeof(int32_t) * g.NR * S);
-    ENSURE(w.dcode, S_DCODE, sizeof(float) * g.NR * S);
+    ENSURE(w.dcode, S_DCODE, sizeof(float) * g.NR * (S + 1));
     ENSURE(w.img, S_IMG, g.C * plane);
     ENSURE(w.dec, S_DEC, (size_t)g.C * g.sw * g.sh);
     ENSURE(w.dec2, S_DEC2, (size_t)g.C * g.sw * g.sh);
@@ -414,7 +414,8 @@ int fic_decode(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int
     CU(cudaMemcpyAsync(w.q, qcodes, sizeof(int32_t) * g.NR * S, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(w.acc, 0, 64 * sizeof(unsigned long long), s));
     int launches = 0;
-    launches += launch_dequant(w.q, w.dcode, g, 0, nullptr, w.acc, s);
+    int32_t *doff = (int32_t *)(w.dcode + g.NR * S);
+    launches += launch_dequant(w.q, w.dcode, doff, g, 0, nullptr, w.acc, s);
     launches += launch_fill(w.img, g.C * plane, 128, s);  // FC:360, FC:1142-1148
     launches += launch_decimate(w.img, w.dec, g, s);
     CU(cudaMemcpyAsync(h->h_acc, w.acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -439,7 +440,7 @@ int fic_decode(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int
         bool serial = big || last || (it == 0 && avg != 0.0f);
         if (serial) ENSURE(w.perr, S_PERR, sizeof(int32_t) * plane);
         CU(cudaMemsetAsync(w.acc, 0, sizeof(unsigned long long), s));
-        launches += launch_decode_sweep(dcur, w.img, dnext, w.dcode, g, w.acc, serial ? w.perr : nullptr, s);
+        launches += launch_decode_sweep(dcur, w.img, dnext, w.dcode, doff, g, w.acc, serial ? w.perr : nullptr, s);
         float sum;
         if (serial) {
             CU(cudaMemcpyAsync(w.avgf, &avg, sizeof(float), cudaMemcpyHostToDevice, s));
@@ -490,7 +491,7 @@ int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, in
     ENSURE(w.src, S_SRC, g.C * plane);
     ENSURE(w.dec, S_DEC, (size_t)g.C * g.sw * g.sh);
     ENSURE(w.info, S_INFO, sizeof(float) * g.NR * S);
-    ENSURE(w.dcode, S_DCODE, sizeof(float) * g.NR * S);
+    ENSURE(w.dcode, S_DCODE, sizeof(float) * g.NR * (S + 1));
     ENSURE(w.img, S_IMG, g.C * plane);
     ENSURE(w.acc, S_ACC, 64 * sizeof(unsigned long long));
     CU(cudaMemcpyAsync(w.argb, argb, sizeof(int32_t) * plane, cudaMemcpyHostToDevice, s));
@@ -498,9 +499,10 @@ int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, in
     CU(cudaMemsetAsync(w.acc, 0, 64 * sizeof(unsigned long long), s));
     launch_unpack(w.argb, w.src, W, H, g.C, s);
     launch_decimate(w.src, w.dec, g, s);                       // FC:275 codebook of the source
-    launch_dequant(nullptr, w.dcode, g, 1, w.info, w.acc, s);  // FC:273 calculateIndices
+    int32_t *doff = (int32_t *)(w.dcode + g.NR * S);
+    launch_dequant(nullptr, w.dcode, doff, g, 1, w.info, w.acc, s);  // FC:273 calculateIndices
     launch_fill(w.img, g.C * plane, 0xa0, s);                  // RasterImage.java:19,31
-    launch_decode_sweep(w.dec, w.img, nullptr, w.dcode, g, nullptr, nullptr, s);
+    launch_decode_sweep(w.dec, w.img, nullptr, w.dcode, doff, g, nullptr, nullptr, s);
     launch_pack_argb(w.img, w.argb, W, H, g.C, s);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h->h_acc, w.acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));

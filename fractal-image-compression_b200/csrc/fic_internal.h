@@ -41,7 +41,7 @@ struct Work {
     uint8_t *img = nullptr;     // C planes W*H: the image being reconstructed (updated in place)
     uint8_t *dec2 = nullptr;    // second decimated buffer (Jacobi ping-pong with `dec`)
     float *avgf = nullptr;      // 1 float: running avgError for the exact replay kernel
-    float *dcode = nullptr;     // [NR][3|5] dequantised codes with codebook indices
+    float *dcode = nullptr;     // [NR][3|5] dequantised codes with codebook indices, then s32 doff[NR] (domain byte offsets)
     int32_t *perr = nullptr;    // per-pixel squared change in reference loop order (exact avgError path)
     unsigned long long *acc = nullptr;  // [64] integer accumulators / flags
     size_t cap[16] = {0};
@@ -73,12 +73,12 @@ int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j
                              cudaEvent_t k1 = nullptr);
 
 // decoder
-int launch_dequant(const int32_t *d_q, float *d_code, const Geom &g, int unquantised,
+int launch_dequant(const int32_t *d_q, float *d_code, int32_t *d_off, const Geom &g, int unquantised,
                    const float *d_info, unsigned long long *d_acc, cudaStream_t s);
 int launch_fill(uint8_t *d_planes, size_t bytes, int value, cudaStream_t s);
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out,
-                        const float *d_code, const Geom &g, unsigned long long *d_acc,
-                        int32_t *d_perr, cudaStream_t s);
+                        const float *d_code, const int32_t *d_off, const Geom &g,
+                        unsigned long long *d_acc, int32_t *d_perr, cudaStream_t s);
 int launch_serial_avg(const int32_t *d_perr, int64_t count, float *d_avg_inout, cudaStream_t s);
 
 }  // namespace fic

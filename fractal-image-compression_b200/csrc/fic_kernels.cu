@@ -517,7 +517,8 @@ int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_
 // With `unquantised` the float codes of an encode are used instead (collage, FC:271).
 // acc[1] is set when an index falls outside the pool (the reference would throw).
 __global__ void k_dequant(const int32_t *__restrict__ q, const float *__restrict__ info_in,
-                          float *__restrict__ code, Geom g, int unquantised, unsigned long long *acc)
+                          float *__restrict__ code, int32_t *__restrict__ doff, Geom g, int unquantised,
+                          unsigned long long *acc)
 {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= g.NR) return;
@@ -548,12 +549,15 @@ __global__ void k_dequant(const int32_t *__restrict__ q, const float *__restrict
     }
     v[0] = (float)(int)result;  // FC:888 stores the index back into the float table
     for (int k = 0; k < S; k++) code[S * j + k] = v[k];
+    // byte offset of the domain block (FC:394 codebuch[(int) imgData[i][0]]) inside a decimated plane
+    const int idx = j_f2i(v[0]);
+    doff[j] = ((idx / g.dpw) * g.step) * g.sw + (idx % g.dpw) * g.step;
 }
 
-int launch_dequant(const int32_t *d_q, float *d_code, const Geom &g, int unquantised, const float *d_info,
-                   unsigned long long *d_acc, cudaStream_t s)
+int launch_dequant(const int32_t *d_q, float *d_code, int32_t *d_off, const Geom &g, int unquantised,
+                   const float *d_info, unsigned long long *d_acc, cudaStream_t s)
 {
-    k_dequant<<<(unsigned)((g.NR + 127) / 128), 128, 0, s>>>(d_q, d_info, d_code, g, unquantised, d_acc);
+    k_dequant<<<(unsigned)((g.NR + 127) / 128), 128, 0, s>>>(d_q, d_info, d_code, d_off, g, unquantised, d_acc);
     return 1;
 }
 
@@ -586,7 +590,8 @@ int launch_fill(uint8_t *d_planes, size_t bytes, int value, cudaStream_t s)
 template <int C>
 __global__ void __launch_bounds__(256)
 k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, uint8_t *__restrict__ dec_out,
-               const float *__restrict__ code, Geom g, unsigned long long *acc, int32_t *__restrict__ perr)
+               const float *__restrict__ code, const int32_t *__restrict__ doff, Geom g, unsigned long long *acc,
+               int32_t *__restrict__ perr)
 {
     int qw = g.W / 2;
     int64_t quads = (int64_t)qw * (g.H / 2);
@@ -600,15 +605,14 @@ k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, ui
         int64_t j = (int64_t)yr * g.rpw + xr;
         constexpr int S = C == 1 ? 3 : 5;
         const float *cd = code + S * j;
-        int idx = j_f2i(cd[0]);  // FC:394 (int) imgData[i][0]
         float a = cd[1];
-        int gx = idx % g.dpw, gy = idx / g.dpw;
+        const int off = doff[j];
         int64_t planeI = (int64_t)g.W * g.H, planeD = (int64_t)g.sw * g.sh;
         int e[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int c = 0; c < C; c++) {
             float b = cd[2 + c];
-            const uint8_t *pd = dec_in + c * planeD + (int64_t)(gy * g.step + ry) * g.sw + gx * g.step + rx;
+            const uint8_t *pd = dec_in + c * planeD + off + ry * g.sw + rx;
             int d00 = pd[0], d10 = pd[1], d01 = pd[g.sw], d11 = pd[g.sw + 1];
             // FC:396 / FC:482: (int)(a * domain + b), float multiply then float add
             int v00 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d00), b)));
@@ -646,7 +650,8 @@ k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, ui
 template <int C>
 __global__ void __launch_bounds__(256)
 k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, uint8_t *__restrict__ dec_out,
-                  const float *__restrict__ code, Geom g, unsigned long long *acc, int32_t *__restrict__ perr)
+                  const float *__restrict__ code, const int32_t *__restrict__ doff, Geom g, unsigned long long *acc,
+                  int32_t *__restrict__ perr)
 {
     const int sw8 = g.W / 8;
     const int64_t strips = (int64_t)sw8 * (g.H / 2);
@@ -657,7 +662,8 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
         const int y = 2 * qy, x0 = 8 * s8;
         constexpr int S = C == 1 ? 3 : 5;
         const int64_t planeI = (int64_t)g.W * g.H, planeD = (int64_t)g.sw * g.sh;
-        const int yr = y / g.B, ry = y - yr * g.B;
+        const int lb = __ffs(g.B) - 1, bm = g.B - 1;  // B is a power of two
+        const int yr = y >> lb, ry = y & bm;
         int e[4][4];
 #pragma unroll
         for (int qd = 0; qd < 4; qd++)
@@ -672,12 +678,11 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
 #pragma unroll
             for (int qd = 0; qd < 4; qd++) {
                 const int x = x0 + 2 * qd;
-                const int xr = x / g.B, rx = x - xr * g.B;
-                const float *cd = code + S * ((int64_t)yr * g.rpw + xr);
-                const int idx = j_f2i(cd[0]);  // FC:394 (int) imgData[i][0]
+                const int xr = x >> lb, rx = x & bm;
+                const int64_t jr = (int64_t)yr * g.rpw + xr;
+                const float *cd = code + S * jr;
                 const float a = cd[1], b = cd[2 + c];
-                const int gx = idx % g.dpw, gy = idx / g.dpw;
-                const uint8_t *pd = dec_in + c * planeD + (int64_t)(gy * g.step + ry) * g.sw + gx * g.step + rx;
+                const uint8_t *pd = dec_in + c * planeD + doff[jr] + ry * g.sw + rx;
                 const int d00 = pd[0], d10 = pd[1], d01 = pd[g.sw], d11 = pd[g.sw + 1];
                 // FC:396 / FC:482: (int)(a * domain + b), float multiply then float add
                 const int v00 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d00), b)));
@@ -704,7 +709,7 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
             local += (unsigned long long)(e[qd][0] + e[qd][1] + e[qd][2] + e[qd][3]);
             if (perr) {
                 const int x = x0 + 2 * qd;
-                const int xr = x / g.B, rx = x - xr * g.B;
+                const int xr = x >> lb, rx = x & bm;
                 int32_t *pe = perr + ((int64_t)yr * g.rpw + xr) * g.n + ry * g.B + rx;
                 pe[0] = e[qd][0];
                 pe[1] = e[qd][1];
@@ -720,23 +725,23 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
 }
 
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out, const float *d_code,
-                        const Geom &g, unsigned long long *d_acc, int32_t *d_perr, cudaStream_t s)
+                        const int32_t *d_off, const Geom &g, unsigned long long *d_acc, int32_t *d_perr, cudaStream_t s)
 {
     if (g.W % 8 == 0) {
         int64_t strips = (int64_t)(g.W / 8) * (g.H / 2);
         unsigned blocks = (unsigned)((strips + 255) / 256);
         if (g.C == 1)
-            k_decode_sweep_v8<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, g, d_acc, d_perr);
+            k_decode_sweep_v8<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, d_acc, d_perr);
         else
-            k_decode_sweep_v8<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, g, d_acc, d_perr);
+            k_decode_sweep_v8<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, d_acc, d_perr);
         return 1;
     }
     int64_t quads = (int64_t)(g.W / 2) * (g.H / 2);
     unsigned blocks = (unsigned)((quads + 255) / 256);
     if (g.C == 1)
-        k_decode_sweep<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, g, d_acc, d_perr);
+        k_decode_sweep<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, d_acc, d_perr);
     else
-        k_decode_sweep<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, g, d_acc, d_perr);
+        k_decode_sweep<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, d_acc, d_perr);
     return 1;
 }
 
