@@ -305,6 +305,12 @@ def run_ours(args):
     pk, pk_kind = peaks()
     k_ms = statistics.mean(kernel_ms)
     int8_peak = 2.0 * pk["bf16_tflops"]  # TOP/s: the i8 pipe issues 2x the bf16 rate
+    try:
+        handle.set_stream(None)
+        int8_measured = handle.measure_int8_peak()  # bare tcgen05.mma.kind::i8 loop on this GPU, this run
+    except Exception as exc:  # diagnostics only
+        int8_measured = None
+        sys.stderr.write(f"int8 peak measurement failed: {exc}\n")
     ops = 2.0 * B * B * step_evals       # algorithmic int8 ops of one launch (2*B^2 per eval)
     achieved = ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
     roofline = {
@@ -312,7 +318,10 @@ def run_ours(args):
         "achieved": achieved, "peak": int8_peak, "unit": "TOP/s", "frac": achieved / int8_peak,
         "peak_source": f"2 x bf16_tflops ({pk['bf16_tflops']}) of {pk_kind} (MEASURED_PEAKS.json has no int8 entry; "
                        f"nominal dense int8 is 4500)",
-        "frac_of_nominal_4500": achieved / 4500.0, "kernel_ms": k_ms, "search_ms": statistics.mean(search_ms),
+        "frac_of_nominal_4500": achieved / 4500.0,
+        "int8_peak_measured_tops": int8_measured,
+        "frac_of_measured_int8": (achieved / int8_measured) if int8_measured else None,
+        "kernel_ms": k_ms, "search_ms": statistics.mean(search_ms),
         "pool_ms": statistics.mean(pool_ms),
         # dram__bytes_read.sum + dram__bytes_write.sum of one k_umma_search launch from `ncu --set full`
         # (profiles/r1_k_umma_search_4096x4096_B8_raw.txt); only known for the profiled workload

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "fic_create", "fic_destroy", "fic_last_error", "fic_version", "fic_set_option", "fic_set_stream",
     "fic_get_timings", "fic_geometry", "fic_encode_grey", "fic_encode_rgb", "fic_encode_planes_dev",
     "fic_sync", "fic_decode", "fic_collage", "fic_build_pool", "fic_stream_size", "fic_stream_write",
-    "fic_stream_read_header", "fic_stream_read_codes",
+    "fic_stream_read_header", "fic_stream_read_codes", "fic_measure_int8_peak",
 ]
 
 
@@ -73,6 +73,7 @@ def load() -> C.CDLL:
                              C.POINTER(C.c_int)]
     L.fic_collage.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.fic_build_pool.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.fic_measure_int8_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.fic_stream_size.argtypes = [C.c_int] * 4
     L.fic_stream_size.restype = C.c_size_t
     L.fic_stream_write.argtypes = [C.c_int] * 5 + [vp, vp, C.c_size_t]

@@ -162,6 +162,12 @@ class Handle:
         self._check(self._L.fic_collage(self._h, int(rgb), _ptr(a), W, H, B, wk, _ptr(info), _ptr(out)))
         return out
 
+    def measure_int8_peak(self) -> float:
+        """Dense int8 tensor-pipe rate of this GPU in TOP/s, from a bare tcgen05.mma.kind::i8 loop."""
+        v = C.c_double(0.0)
+        self._check(self._L.fic_measure_int8_peak(self._h, C.byref(v)))
+        return v.value
+
     def build_pool(self, argb: np.ndarray, B: int, rgb: bool):
         a = np.ascontiguousarray(argb, dtype=np.int32)
         H, W = a.shape

@@ -354,6 +354,17 @@ int fic_encode_planes_dev(fic_handle *h, const uint8_t *d_planes, int is_rgb, in
     return rc;
 }
 
+int fic_measure_int8_peak(fic_handle *h, double *tops)
+{
+    if (!h || !tops) return FIC_E_ARG;
+    CU(cudaSetDevice(h->device));
+    const char *why = nullptr;
+    double v = measure_int8_peak(h->num_sms, h->stream, 3, &why);
+    if (v < 0) return set_err(h, FIC_E_CUDA, "int8 peak measurement failed: %s", why ? why : "?");
+    *tops = v;
+    return FIC_OK;
+}
+
 int fic_build_pool(fic_handle *h, const int32_t *argb, int is_rgb, int W, int H, int B, uint8_t *decimated,
                    int32_t *dom_sum, int32_t *dom_sumsq)
 {

@@ -59,6 +59,8 @@ int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_
                  cudaStream_t s);
 
 // tcgen05 fused full-pool search (grey, window == whole pool).
+// bare tcgen05 kind::i8 loop: measured dense int8 rate of this GPU in TOP/s (< 0 on error)
+double measure_int8_peak(int num_sms, cudaStream_t s, int reps, const char **err);
 bool umma_applicable(const Geom &g);
 size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms);
 size_t umma_opB_bytes(const Geom &g);

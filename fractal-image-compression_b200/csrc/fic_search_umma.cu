@@ -621,6 +621,63 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     }
 }
 
+// ---------------------------------------------------------------- int8 pipe peak -------
+
+// Bare tcgen05.mma.kind::i8 loop (M=128, N=256, K=32 per instruction, operands resident in shared
+// memory, two alternating TMEM accumulators, no epilogue): measures what the int8 tensor pipe of
+// this GPU sustains, the denominator of the search kernel's roofline (MEASURED_PEAKS.json only
+// carries a bf16 figure).
+__global__ void __launch_bounds__(128, 1) k_int8_peak(int iters, uint32_t seed)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                 // 128 rows x 32 B, core-matrix order (16 groups x 256 B)
+    uint8_t *sB = smem + 4096;          // 256 rows x 32 B
+    uint64_t *bar = (uint64_t *)(smem + 4096 + 8192);
+    uint32_t *tmem_slot = (uint32_t *)(bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (4096 + 8192) / 4; i += blockDim.x) {
+        uint32_t x = (uint32_t)i * 2654435761u + seed + blockIdx.x * 40503u;
+        x ^= x >> 15; x *= 0x2c1b3c6du; x ^= x >> 12;
+        ((uint32_t *)smem)[i] = x;
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> async proxy (MMA)
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 1) {
+        const uint32_t elected = elect_one();
+        const uint64_t ad = make_desc(smem_u32(sA), 128, 256);
+        const uint64_t bd = make_desc(smem_u32(sB), 128, 256);
+        constexpr uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+        if (elected) {
+            for (int i = 0; i < iters; i++) tc_mma_i8(tmem_base + (i & 1) * 256, ad, bd, idesc, i > 1 ? 1u : 0u);
+            tc_commit(smem_u32(bar));
+        }
+        __syncwarp();
+        mbar_wait(smem_u32(bar), 0, nullptr, 9);
+    }
+    (void)lane;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- refine --------------
 
 // Exact score of the candidate at sweep position `pos` for one range row, from the packed
@@ -848,6 +905,33 @@ void umma_debug_positions(const Work &w, const Geom &g, int64_t rows, int num_sm
     *npos = p.npos;
     if (g.B == 8) *d_pos_dom = (const int32_t *)(w.opB + OpBLayout<8>(g, p).off_posdom);
     else *d_pos_dom = (const int32_t *)(w.opB + OpBLayout<4>(g, p).off_posdom);
+}
+
+// Returns the measured dense int8 rate in TOP/s (2 ops per MAC), best of `reps` launches of ~`ms_target` ms.
+double measure_int8_peak(int num_sms, cudaStream_t s, int reps, const char **err)
+{
+    const int smem = 200 * 1024;  // far more than needed: guarantees one CTA (one 512-column TMEM allocation) per SM
+    cudaError_t ce = cudaFuncSetAttribute(k_int8_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1.0; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 200000;  // 128 clk each at full rate: ~13 ms at 1.9 GHz
+    double best = 0.0;
+    for (int r = 0; r < reps + 1; r++) {
+        cudaEventRecord(e0, s);
+        k_int8_peak<<<num_sms, 128, smem, s>>>(iters, 0x9e3779b9u + r);
+        cudaEventRecord(e1, s);
+        ce = cudaStreamSynchronize(s);
+        if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); best = -1.0; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tops = 2.0 * 128.0 * 256.0 * 32.0 * (double)iters * num_sms / (ms * 1e-3) / 1e12;
+        if (r > 0 && tops > best) best = tops;  // launch 0 is the warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return best;
 }
 
 bool umma_applicable(const Geom &g)

@@ -125,6 +125,13 @@ int fic_decode(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int
 int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, int B, int wk,
                 float *info, int32_t *argb_out);
 
+/* ---- diagnostics -------------------------------------------------------------- */
+
+/* Measures the dense int8 tensor-pipe rate of the handle's GPU with a bare tcgen05.mma.kind::i8
+ * loop (no epilogue, operands resident in shared memory): *tops receives TOP/s (2 ops per MAC).
+ * bench.py uses it as the measured roofline denominator of the search kernel. */
+int fic_measure_int8_peak(fic_handle *h, double *tops);
+
 /* ---- domain pool inspection (tests / debugging; not on the hot path) ---------- */
 
 /* Runs the pool builder only and returns the 2x-decimated plane(s) (W/2*H/2 bytes per

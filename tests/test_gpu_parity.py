@@ -273,3 +273,9 @@ def test_cpp_host_cli_roundtrip(tmp_path, oracle, lena_grey):
     dec = np.frombuffer(open(out, "rb").read().split(b"255\n", 1)[1], np.uint8).reshape(256, 256)
     oimg, _, _ = oracle.decode(want)
     assert (dec == ((oimg.view(np.uint32) >> 16) & 0xFF)).all()
+
+
+def test_int8_peak_measurement(handle):
+    tops = handle.measure_int8_peak()
+    # nominal dense int8 on B200 is 4500 TOP/s; anything far outside means the loop is not measuring the pipe
+    assert 1000.0 < tops < 5500.0, tops
