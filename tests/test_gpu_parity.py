@@ -279,3 +279,56 @@ def test_int8_peak_measurement(handle):
     tops = handle.measure_int8_peak()
     # nominal dense int8 on B200 is 4500 TOP/s; anything far outside means the loop is not measuring the pipe
     assert 1000.0 < tops < 5500.0, tops
+
+
+def _random_plane(rng, W, H, kind):
+    if kind == 0:
+        return rng.integers(0, 256, (H, W), dtype=np.uint8)
+    if kind == 1:   # low contrast: many vR == 0 rows, flat domains, float ties
+        return (120 + rng.integers(0, 3, (H, W))).astype(np.uint8)
+    if kind == 2:   # binary: extreme contrast, |d - dmean| > 127 (the second s8 digit is live)
+        return (rng.integers(0, 2, (H, W)) * 255).astype(np.uint8)
+    y, x = np.mgrid[0:H, 0:W]
+    return ((x * 5 + y * 3 + rng.integers(0, 8, (H, W))) % 256).astype(np.uint8)
+
+
+def test_randomised_parity_sweep(fic, handle, oracle):
+    """Seeded sweep over image sizes, block sizes, windows, content kinds, grey and RGB: every code and
+    quantised int must equal the oracle's; square full-pool cases run on both search engines."""
+    rng = np.random.default_rng(20261018)
+    cases = 0
+    for _ in range(70):
+        B = int(rng.choice([4, 8, 16]))
+        rw, rh = int(rng.integers(2, 9)), int(rng.integers(2, 9))
+        if rng.random() < 0.4:
+            rh = rw
+        W, H = rw * B, rh * B
+        dpw, dph = 2 * rw - 3, 2 * rh - 3
+        wk_max = min(dpw, dph)
+        wk = wk_max if rng.random() < 0.4 else int(rng.integers(1, wk_max + 1))
+        rgb = rng.random() < 0.3
+        kind = int(rng.integers(0, 4))
+        if rgb:
+            img = to_argb_rgb(np.stack([_random_plane(rng, W, H, kind) for _ in range(3)], -1))
+        else:
+            img = to_argb_grey(_random_plane(rng, W, H, kind))
+        oinfo = oracle.encode(img, B, wk, rgb=rgb)
+        ostream = oracle.write_data(oinfo, W, H, B, wk, rgb=rgb)
+        engines = [fic.FIC_ENGINE_DIRECT]
+        if not rgb and B in (4, 8) and wk == dpw == dph:
+            engines.append(fic.FIC_ENGINE_UMMA)
+        for eng in engines:
+            handle.set_engine(eng)
+            try:
+                info, q = handle.encode(img, B, wk, rgb=rgb)
+            finally:
+                handle.set_engine(fic.FIC_ENGINE_AUTO)
+            assert float_bits_equal(info, oinfo), (W, H, B, wk, rgb, kind, eng)
+            assert (q == q_from_stream(ostream, 5 if rgb else 3)).all(), (W, H, B, wk, rgb, kind, eng)
+        # decoder on the same stream
+        _, Wd, Hd, Bd, wkd, qd = fic.stream_read(ostream)
+        dimg, davg, dit = handle.decode(qd, Wd, Hd, Bd, wkd, rgb)
+        oimg, oavg, oit = oracle.decode(ostream)
+        assert (dimg == oimg).all() and dit == oit and np.float32(davg) == np.float32(oavg), (W, H, B, wk, rgb, kind)
+        cases += 1
+    assert cases == 70
