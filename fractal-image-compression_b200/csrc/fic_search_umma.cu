@@ -29,7 +29,8 @@
 // order.
 //
 // How kov becomes one u8 x s8 GEMM.  With dt = d - dmean_j (|dt| <= 254 for B <= 8),
-// split dt = h + l, h = clamp(dt, -128, 127), l = dt - h (both fit s8; l is zero unless a
+// (B = 16: |dt| <= 255; the single case dt = +255 does not fit and sends the image to the direct
+// search), split dt = h + l, h = clamp(dt, -128, 127), l = dt - h (both fit s8; l is zero unless a
 // pixel is more than 127 grey levels from its block mean, so the MMA issuer skips the l
 // K-slices of every domain tile whose `l` digits are all zero -- most tiles).  Then
 //     kov = sum_k r_k * h_k + sum_k r_k * l_k + rmean_i * (-alpha_j),   alpha_j = sum d - n*dmean_j
@@ -102,6 +103,17 @@ struct Cfg<4> {
     __host__ __device__ static constexpr bool is_l_slice(int) { return false; }  // h and l share slice 0
 };
 
+template <>
+struct Cfg<16> {
+    static constexpr int n = 256;
+    static constexpr int KS_A = 9;   // r[0:256] (8 slices) [rmean 0..]
+    static constexpr int KS_B = 17;  // h (8 slices) l (8 slices) [-alpha 0..]
+    static constexpr int NS = 17;
+    static constexpr int NSTAGE = 1; // A super-block 144 KB + one 68 KB domain tile fill shared memory
+    __host__ __device__ static constexpr int amap(int s) { return s < 16 ? (s & 7) : 8; }
+    __host__ __device__ static constexpr bool is_l_slice(int s) { return s >= 8 && s < 16; }
+};
+
 template <int B>
 struct Lay {
     using C = Cfg<B>;
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(128)
 k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
                     const int32_t *__restrict__ dsq, const int32_t *__restrict__ perm, uint8_t *__restrict__ opB,
                     int32_t *__restrict__ pos_dom, int32_t *__restrict__ pos_var, int64_t *__restrict__ dom0_pos,
-                    Geom g, int64_t ntiles, uint32_t mult)
+                    int *__restrict__ unsupported, Geom g, int64_t ntiles, uint32_t mult)
 {
     using L = Lay<B>;
     constexpr int n = Cfg<B>::n;
@@ -189,6 +201,9 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
                     hv[e] = max(-128, min(127, dt));  // the low digit is zero unless |dt| > 127
                     lv[e] = dt - hv[e];
                     any_l |= lv[e];
+                    // B = 16 only: d = 255 in a block of mean 0 gives dt = 255 = 127 + 128, one more than two
+                    // s8 digits hold; the caller then falls back to the direct search for this image
+                    if (B == 16 && lv[e] > 127) *unsupported = 1;
                 }
                 hw[w] = pack4(hv[0], hv[1], hv[2], hv[3]);
                 lw[w] = pack4(lv[0], lv[1], lv[2], lv[3]);
@@ -815,7 +830,7 @@ struct OpBLayout {
         auto take = [&](size_t bytes) { size_t at = (o + 255) & ~(size_t)255; o = at + bytes; return at; };
         off_posdom = take((size_t)p.npos * 4);
         off_posvar = take((size_t)p.npos * 4);
-        off_dom0 = take(8);
+        off_dom0 = take(16);  // s64 sweep position of domain 0, then the s32 `unsupported` flag
         off_keys0 = take((size_t)g.ND * 4);
         off_keys1 = take((size_t)g.ND * 4);
         off_vals0 = take((size_t)g.ND * 4);
@@ -855,6 +870,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     int32_t *pos_dom = (int32_t *)(w.opB + lay.off_posdom);
     int32_t *pos_var = (int32_t *)(w.opB + lay.off_posvar);
     int64_t *dom0 = (int64_t *)(w.opB + lay.off_dom0);
+    int *unsupported = (int *)(dom0 + 1);
     int launches = 0;
     cudaError_t ce;
     // 1. domains by increasing varD
@@ -866,8 +882,16 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
     launches += 4;  // key kernel + radix passes (approximate; they are not the timed kernel)
     // 2. operand blobs
+    cudaMemsetAsync(unsupported, 0, sizeof(int), s);
     k_umma_pack_domains<B><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(w.dec, w.dsum, w.dsq, dv.Current(), w.opB, pos_dom,
-                                                                           pos_var, dom0, g, p.ntiles, p.mult);
+                                                                           pos_var, dom0, unsupported, g, p.ntiles, p.mult);
+    if (B == 16) {  // rare digit overflow (see k_umma_pack_domains): decided on the host before the search starts
+        int flag = 0;
+        ce = cudaMemcpyAsync(&flag, unsupported, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
+        if (flag) return -2;
+    }
     k_umma_pack_ranges<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
     launches += 2;
     // 3. the fused search
@@ -904,6 +928,7 @@ void umma_debug_positions(const Work &w, const Geom &g, int64_t rows, int num_sm
     Plan p = make_plan(g, rows, num_sms);
     *npos = p.npos;
     if (g.B == 8) *d_pos_dom = (const int32_t *)(w.opB + OpBLayout<8>(g, p).off_posdom);
+    else if (g.B == 16) *d_pos_dom = (const int32_t *)(w.opB + OpBLayout<16>(g, p).off_posdom);
     else *d_pos_dom = (const int32_t *)(w.opB + OpBLayout<4>(g, p).off_posdom);
 }
 
@@ -936,24 +961,26 @@ double measure_int8_peak(int num_sms, cudaStream_t s, int reps, const char **err
 
 bool umma_applicable(const Geom &g)
 {
-    return g.C == 1 && (g.B == 8 || g.B == 4) && g.wk == g.dpw && g.wk == g.dph;
+    return g.C == 1 && (g.B == 4 || g.B == 8 || g.B == 16) && g.wk == g.dpw && g.wk == g.dph;
 }
 
 size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms)
 {
-    return g.B == 8 ? opA_bytes_t<8>(g, j1 - j0, num_sms) : opA_bytes_t<4>(g, j1 - j0, num_sms);
+    return g.B == 8 ? opA_bytes_t<8>(g, j1 - j0, num_sms)
+                    : (g.B == 16 ? opA_bytes_t<16>(g, j1 - j0, num_sms) : opA_bytes_t<4>(g, j1 - j0, num_sms));
 }
 
 size_t umma_opB_bytes(const Geom &g)
 {
     Plan p = make_plan(g, kRowsPerSB, 148);  // the opB layout depends on the pool only
-    return g.B == 8 ? OpBLayout<8>(g, p).total : OpBLayout<4>(g, p).total;
+    return g.B == 8 ? OpBLayout<8>(g, p).total : (g.B == 16 ? OpBLayout<16>(g, p).total : OpBLayout<4>(g, p).total);
 }
 
 int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s,
                        const char **err, cudaEvent_t k0, cudaEvent_t k1)
 {
     if (g.B == 8) return launch_t<8>(w, g, j0, j1, num_sms, s, err, nullptr, 0, nullptr, 0, k0, k1);
+    if (g.B == 16) return launch_t<16>(w, g, j0, j1, num_sms, s, err, nullptr, 0, nullptr, 0, k0, k1);
     return launch_t<4>(w, g, j0, j1, num_sms, s, err, nullptr, 0, nullptr, 0, k0, k1);
 }
 
@@ -964,6 +991,7 @@ int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j
                              uint32_t dbg, cudaEvent_t k0, cudaEvent_t k1)
 {
     if (g.B == 8) return launch_t<8>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg);
+    if (g.B == 16) return launch_t<16>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg);
     return launch_t<4>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg);
 }
 

@@ -13,7 +13,7 @@ def psnr(a, b):
 
 
 @pytest.mark.parametrize("W,B,kind", [(512, 8, "structured"), (512, 4, "structured"), (1024, 8, "noise"),
-                                      (1024, 8, "structured")])
+                                      (1024, 8, "structured"), (1024, 16, "structured"), (1024, 16, "noise")])
 def test_engines_agree_full_pool(fic, handle, W, B, kind):
     p = getattr(fic.synth, kind)(W, W, 7)
     img = fic.synth.grey_to_argb(p)

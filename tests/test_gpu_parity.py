@@ -111,7 +111,7 @@ def test_full_pool_direct(fic, handle, oracle, request, name, B, wk):
     assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, W, H, B, wk), 3)
 
 
-@pytest.mark.parametrize("name,B,wk", [f for f in FULL if f[1] in (4, 8)])
+@pytest.mark.parametrize("name,B,wk", FULL)
 def test_full_pool_tcgen05(fic, handle, oracle, request, name, B, wk):
     img = request.getfixturevalue(name)
     H, W = img.shape
@@ -125,7 +125,8 @@ def test_full_pool_tcgen05(fic, handle, oracle, request, name, B, wk):
     assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, W, H, B, wk), 3)
 
 
-@pytest.mark.parametrize("kind,B", [("noise", 8), ("structured", 8), ("structured", 4), ("sparse", 8), ("flat", 8)])
+@pytest.mark.parametrize("kind,B", [("noise", 8), ("structured", 8), ("structured", 4), ("sparse", 8), ("flat", 8),
+                                    ("noise", 16), ("structured", 16), ("sparse", 16)])
 def test_full_pool_tcgen05_synthetic(fic, handle, oracle, kind, B):
     W = H = 128
     if kind == "noise":
@@ -315,7 +316,7 @@ def test_randomised_parity_sweep(fic, handle, oracle):
         oinfo = oracle.encode(img, B, wk, rgb=rgb)
         ostream = oracle.write_data(oinfo, W, H, B, wk, rgb=rgb)
         engines = [fic.FIC_ENGINE_DIRECT]
-        if not rgb and B in (4, 8) and wk == dpw == dph:
+        if not rgb and wk == dpw == dph:
             engines.append(fic.FIC_ENGINE_UMMA)
         for eng in engines:
             handle.set_engine(eng)
@@ -332,3 +333,21 @@ def test_randomised_parity_sweep(fic, handle, oracle):
         assert (dimg == oimg).all() and dit == oit and np.float32(davg) == np.float32(oavg), (W, H, B, wk, rgb, kind)
         cases += 1
     assert cases == 70
+
+
+def test_tcgen05_b16_digit_overflow_falls_back(fic, handle, oracle):
+    """B = 16: a lone 255 in a domain block of mean 0 gives d - dmean = 255 = 127 + 128, one more than two s8
+    digits hold; the library must notice and run the exact direct search instead."""
+    p = np.zeros((128, 128), np.uint8)
+    p[40:42, 40:42] = 255          # one white 2x2 patch -> one decimated pixel of 255 among zeros
+    p[100:110, 90:120] = 37        # some structure elsewhere so that ranges are not all flat
+    img = to_argb_grey(p)
+    wk = 2 * 128 // 16 - 3
+    handle.set_engine(fic.FIC_ENGINE_UMMA)
+    try:
+        info, q = handle.encode(img, 16, wk, rgb=False)
+        assert handle.timings().engine == fic.FIC_ENGINE_DIRECT
+    finally:
+        handle.set_engine(fic.FIC_ENGINE_AUTO)
+    oinfo = oracle.encode(img, 16, wk)
+    assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, 128, 128, 16, wk), 3)
