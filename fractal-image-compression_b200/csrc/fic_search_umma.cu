@@ -34,7 +34,7 @@
 // pixel is more than 127 grey levels from its block mean, so the MMA issuer skips the l
 // K-slices of every domain tile whose `l` digits are all zero -- most tiles).  Then
 //     kov = sum_k r_k * h_k + sum_k r_k * l_k + rmean_i * (-alpha_j),   alpha_j = sum d - n*dmean_j
-// i.e. A row = [ r | r | rmean 0.. ] (u8) and B row = [ h | l | -alpha 0.. ] (s8), K
+// i.e. A row = [ r | r | rmean rmean 0.. ] (u8) and B row = [ h | l | -alpha/2 -alpha/2 0.. ] (s8), K
 // padded to a multiple of 32 (one kind::i8 MMA consumes K = 32).  The duplicated `r`
 // half of A is not stored twice: the MMA issuer points the A descriptor of K-slices 2,3
 // back at slices 0,1 (B = 8).  The accumulator IS kov; no per-output correction exists.
@@ -211,7 +211,9 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
             *(uint4 *)(rowp + c * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             *(uint4 *)(rowp + (PCH + c) * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
-        *(uint4 *)(rowp + (2 * PCH) * 128) = make_uint4((uint32_t)((-alpha) & 0xff), 0, 0, 0);
+        // -alpha in two s8 columns (alpha <= n - 1 = 255 at B = 16); A carries rmean in both
+        const int a1 = alpha >> 1, a2 = alpha - a1;
+        *(uint4 *)(rowp + (2 * PCH) * 128) = make_uint4((uint32_t)((-a1) & 0xff) | ((uint32_t)((-a2) & 0xff) << 8), 0, 0, 0);
         *(uint4 *)(rowp + (2 * PCH + 1) * 128) = make_uint4(0, 0, 0, 0);
         pos_dom[pos] = (int32_t)j;
         pos_var[pos] = varD;
@@ -277,7 +279,7 @@ k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ 
         if (B == 4) *(uint4 *)(rowp + (PCH + c) * 128) = v;  // [r r] shares one 32-byte slice
     }
     constexpr int XCH = (B == 4) ? 2 * PCH : PCH;
-    *(uint4 *)(rowp + XCH * 128) = make_uint4((uint32_t)rmean, 0, 0, 0);
+    *(uint4 *)(rowp + XCH * 128) = make_uint4((uint32_t)rmean | ((uint32_t)rmean << 8), 0, 0, 0);
     *(uint4 *)(rowp + (XCH + 1) * 128) = make_uint4(0, 0, 0, 0);
 }
 
@@ -721,8 +723,8 @@ __device__ __forceinline__ float refine_eval_packed(const uint32_t *rw, int rmea
         kov = dp4a_us(rw[4 * c + 2], l.z, kov);
         kov = dp4a_us(rw[4 * c + 3], l.w, kov);
     }
-    const int neg_alpha = (int)(int8_t)(__ldg((const uint32_t *)(rowp + (2 * PCH) * 128)) & 0xff);
-    kov += rmean * neg_alpha;
+    const uint32_t xw = __ldg((const uint32_t *)(rowp + (2 * PCH) * 128));
+    kov += rmean * ((int)(int8_t)(xw & 0xff) + (int)(int8_t)((xw >> 8) & 0xff));  // rmean * (-alpha)
     return grey_error(kov, vR, __dsqrt_rn((double)varD));
 }
 
