@@ -220,8 +220,8 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
         if (j == 0) *dom0_pos = pos;  // the refine step always evaluates domain 0
         if (varD > 0) {  // flat domains have kov == 0: they never set a chunk's max |kov|
             float r = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn((double)varD)));
-            rsd_hi = r * (1.0f + 2.384185791015625e-07f);  // >= 1/sqrt(varD) * (1 + 2^-23)
-            rsd_lo = r * (1.0f - 2.384185791015625e-07f);  // <= 1/sqrt(varD) * (1 - 2^-23)
+            rsd_hi = r * (1.0f + 4.76837158203125e-07f);  // >= 1/sqrt(varD) * (1 + 2^-22): covers r's and M*rhi's rounding
+            rsd_lo = r * (1.0f - 4.76837158203125e-07f);  // <= 1/sqrt(varD) * (1 - 2^-22)
         }
     }
     for (int o = 16; o > 0; o >>= 1) {

@@ -67,3 +67,41 @@ def test_periodic_image_ties_and_flag_overflow(fic, handle, W, B, period):
     from test_gpu_parity import float_bits_equal
 
     assert (q1 == q2).all() and float_bits_equal(i1, i2)
+
+
+def test_full_size_4096(fic, handle):
+    """BASELINE configs[2] at full size (4096^2, B=8, whole pool = 2.7e11 evaluations), checked through
+    properties that do not need the oracle at this size: (a) random range-row slices searched by the direct
+    CUDA-core kernel (itself oracle-exact on every small case) give the same codes, (b) sharding by range rows
+    does not change a single code, (c) the reference decoder rule converges and reconstructs the image."""
+    W, B = 4096, 8
+    p = fic.synth.structured(W, W, 1)
+    img = fic.synth.grey_to_argb(p)
+    wk = 2 * W // B - 3
+    NR = (W // B) ** 2
+    info, q = handle.encode(img, B, wk, rgb=False)
+    assert handle.timings().engine == fic.FIC_ENGINE_UMMA
+    # (a) spot-check against the direct search
+    rng = np.random.default_rng(7)
+    handle.set_engine(fic.FIC_ENGINE_DIRECT)
+    try:
+        for j0 in rng.integers(0, NR - 64, 6):
+            j0 = int(j0)
+            i2 = np.zeros_like(info)
+            q2 = np.zeros_like(q)
+            handle.encode(img, B, wk, rgb=False, range_begin=j0, range_end=j0 + 64, info=i2, q=q2)
+            assert (q2[j0:j0 + 64] == q[j0:j0 + 64]).all()
+            assert np.array_equal(i2[j0:j0 + 64], info[j0:j0 + 64], equal_nan=True)
+    finally:
+        handle.set_engine(fic.FIC_ENGINE_AUTO)
+    # (b) two range-row shards == the unsharded encode
+    q3 = np.zeros_like(q)
+    i3 = np.zeros_like(info)
+    cut = (W // B) * 200
+    handle.encode(img, B, wk, rgb=False, range_begin=0, range_end=cut, info=i3, q=q3)
+    handle.encode(img, B, wk, rgb=False, range_begin=cut, range_end=NR, info=i3, q=q3)
+    assert (q3 == q).all()
+    # (c) decode
+    dec, avg, it = handle.decode(q, W, W, B, wk, False)
+    rec = ((dec.view(np.uint32) >> 16) & 0xFF).astype(np.uint8)
+    assert it < 50 and avg < 1 and psnr(p, rec) > 25.0
