@@ -27,6 +27,8 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# DRAM bytes (read + write) of one k_umma_search launch from `ncu --set full` (profiles/), by (kind, size, B)
+TRAFFIC = {("i8", 4096, 8): 1428918000}
 sys.path.insert(0, ROOT)
 
 
@@ -40,6 +42,8 @@ def parse():
     ap.add_argument("--block", type=int, default=8)
     ap.add_argument("--pattern", default="structured", choices=["structured", "noise"])
     ap.add_argument("--engine", default="auto", choices=["auto", "direct", "umma"])
+    ap.add_argument("--mma", default="auto", choices=["auto", "i8", "f16"],
+                    help="tensor-core instruction kind of the tcgen05 search (auto: f16 for B=4,8; i8 for B=16)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -206,6 +210,8 @@ def run_ours(args):
 
     handle = fic.Handle(local)
     handle.set_engine({"auto": fic.FIC_ENGINE_AUTO, "direct": fic.FIC_ENGINE_DIRECT, "umma": fic.FIC_ENGINE_UMMA}[args.engine])
+    handle.set_umma_kind({"auto": fic.FIC_UMMA_KIND_AUTO, "i8": fic.FIC_UMMA_KIND_I8, "f16": fic.FIC_UMMA_KIND_F16}[args.mma])
+    mma = "i8" if (B == 16 or args.mma == "i8") else "f16"   # what the library runs (B = 16 has no f16 variant)
     stream = torch.cuda.Stream(dev)   # library work, NCCL ordering and the timing events all use this stream
     torch.cuda.set_stream(stream)
     handle.set_stream(stream.cuda_stream)
@@ -304,28 +310,34 @@ def run_ours(args):
     value = evals / (ms_per_step * 1e-3)
     pk, pk_kind = peaks()
     k_ms = statistics.mean(kernel_ms)
-    int8_peak = 2.0 * pk["bf16_tflops"]  # TOP/s: the i8 pipe issues 2x the bf16 rate
+    # Roofline of the dominant kernel.  MEASURED_PEAKS.json carries the cuBLAS bf16 rate (burst figure: the
+    # kernel is timed alone by its own events); kind::f16 runs at the bf16 rate, kind::i8 at twice that.
+    # A bare tcgen05.mma loop of the same kind and MMA shape is measured live as a second denominator.
+    f16_peak = float(pk["bf16_tflops"])
+    peak = f16_peak if mma == "f16" else 2.0 * f16_peak
     try:
         handle.set_stream(None)
-        int8_measured = handle.measure_int8_peak()  # bare tcgen05.mma.kind::i8 loop on this GPU, this run
+        bare = handle.measure_mma_peak(fic.FIC_UMMA_KIND_F16 if mma == "f16" else fic.FIC_UMMA_KIND_I8, 128)
     except Exception as exc:  # diagnostics only
-        int8_measured = None
-        sys.stderr.write(f"int8 peak measurement failed: {exc}\n")
-    ops = 2.0 * B * B * step_evals       # algorithmic int8 ops of one launch (2*B^2 per eval)
+        bare = None
+        sys.stderr.write(f"tensor peak measurement failed: {exc}\n")
+    ops = 2.0 * B * B * step_evals       # algorithmic ops of one launch (2*B^2 per evaluation)
     achieved = ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    nominal = 2250.0 if mma == "f16" else 4500.0
+    is_umma = engine == fic.FIC_ENGINE_UMMA
     roofline = {
-        "bound": "tensor", "kernel": "k_umma_search" if engine == fic.FIC_ENGINE_UMMA else "k_search_direct_grey",
-        "achieved": achieved, "peak": int8_peak, "unit": "TOP/s", "frac": achieved / int8_peak,
-        "peak_source": f"2 x bf16_tflops ({pk['bf16_tflops']}) of {pk_kind} (MEASURED_PEAKS.json has no int8 entry; "
-                       f"nominal dense int8 is 4500)",
-        "frac_of_nominal_4500": achieved / 4500.0,
-        "int8_peak_measured_tops": int8_measured,
-        "frac_of_measured_int8": (achieved / int8_measured) if int8_measured else None,
+        "bound": "tensor", "kernel": f"k_umma_search (tcgen05.mma.kind::{mma})" if is_umma else "k_search_direct_grey",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s" if mma == "f16" else "TOP/s", "frac": achieved / peak,
+        "peak_source": (f"bf16_tflops ({pk['bf16_tflops']}, burst) of {pk_kind}" if mma == "f16" else
+                        f"2 x bf16_tflops ({pk['bf16_tflops']}, burst) of {pk_kind} (no int8 entry there)"),
+        "frac_of_nominal": achieved / nominal, "nominal": nominal,
+        "bare_mma_loop_measured": bare,
+        "frac_of_bare_mma_loop": (achieved / bare) if bare else None,
         "kernel_ms": k_ms, "search_ms": statistics.mean(search_ms),
         "pool_ms": statistics.mean(pool_ms),
         # dram__bytes_read.sum + dram__bytes_write.sum of one k_umma_search launch from `ncu --set full`
-        # (profiles/r1_k_umma_search_4096x4096_B8_raw.txt); only known for the profiled workload
-        "traffic": 1428918000 if (engine == fic.FIC_ENGINE_UMMA and size == 4096 and B == 8 and world == 1) else None,
+        # (profiles/); only known for the profiled workload
+        "traffic": TRAFFIC.get((mma, size, B)) if (is_umma and world == 1) else None,
     }
     line = {
         "metric": "encode_evals_per_s", "value": value / 1e9, "unit": "Gevals/s",
@@ -334,7 +346,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
         "config": {"workload": f"synthetic {args.pattern} {size}x{size} grey, B={B}, widthKernel={wk} (full pool)",
-                   "ranges": NR, "domains": ND, "engine": "tcgen05" if engine == fic.FIC_ENGINE_UMMA else "direct",
+                   "ranges": NR, "domains": ND, "engine": f"tcgen05 kind::{mma}" if engine == fic.FIC_ENGINE_UMMA else "direct",
                    "parallelism": f"range-rows x{world}", "l2": "flushed between timed iterations (256 MiB write)"},
         "clocks": clocks,
         "e2e": {"value": evals / (e2e_ms / args.steps * 1e-3) / 1e9, "unit": "Gevals/s",

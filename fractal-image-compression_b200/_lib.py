@@ -15,14 +15,16 @@ LIB_PATH = os.path.join(HERE, "lib", "libfic_b200.so")
 FIC_OK = 0
 FIC_E_ARG, FIC_E_CUDA, FIC_E_NOMEM, FIC_E_STREAM, FIC_E_INTERNAL = -1, -2, -3, -4, -5
 FIC_ENGINE_AUTO, FIC_ENGINE_DIRECT, FIC_ENGINE_UMMA = 0, 1, 2
+FIC_UMMA_KIND_AUTO, FIC_UMMA_KIND_I8, FIC_UMMA_KIND_F16 = 0, 1, 2
 FIC_OPT_ENGINE = 1
+FIC_OPT_UMMA_KIND = 2
 
 # every symbol include/fic_b200.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "fic_create", "fic_destroy", "fic_last_error", "fic_version", "fic_set_option", "fic_set_stream",
     "fic_get_timings", "fic_geometry", "fic_encode_grey", "fic_encode_rgb", "fic_encode_planes_dev",
     "fic_sync", "fic_decode", "fic_collage", "fic_build_pool", "fic_stream_size", "fic_stream_write",
-    "fic_stream_read_header", "fic_stream_read_codes", "fic_measure_int8_peak",
+    "fic_stream_read_header", "fic_stream_read_codes", "fic_measure_int8_peak", "fic_measure_mma_peak",
 ]
 
 
@@ -74,6 +76,7 @@ def load() -> C.CDLL:
     L.fic_collage.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.fic_build_pool.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.fic_measure_int8_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.fic_measure_mma_peak.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.fic_stream_size.argtypes = [C.c_int] * 4
     L.fic_stream_size.restype = C.c_size_t
     L.fic_stream_write.argtypes = [C.c_int] * 5 + [vp, vp, C.c_size_t]

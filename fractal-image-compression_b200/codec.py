@@ -97,6 +97,10 @@ class Handle:
     def set_engine(self, engine: int):
         self._check(self._L.fic_set_option(self._h, _lib.FIC_OPT_ENGINE, int(engine)))
 
+    def set_umma_kind(self, kind: int):
+        """Tensor-core instruction kind of the tcgen05 search: FIC_UMMA_KIND_AUTO / _I8 / _F16."""
+        self._check(self._L.fic_set_option(self._h, _lib.FIC_OPT_UMMA_KIND, int(kind)))
+
     def set_stream(self, cuda_stream: int | None):
         """None -> the handle's own stream; an integer cudaStream_t otherwise.  torch reports its default
         stream as 0, which the C ABI reads as "own stream": pass the legacy-default handle instead."""
@@ -166,6 +170,12 @@ class Handle:
         """Dense int8 tensor-pipe rate of this GPU in TOP/s, from a bare tcgen05.mma.kind::i8 loop."""
         v = C.c_double(0.0)
         self._check(self._L.fic_measure_int8_peak(self._h, C.byref(v)))
+        return v.value
+
+    def measure_mma_peak(self, kind: int, n_cols: int = 128) -> float:
+        """Dense tensor-pipe rate in TOP/s of kind::i8 / kind::f16 at the MMA shape M = 128 x N = n_cols."""
+        v = C.c_double(0.0)
+        self._check(self._L.fic_measure_mma_peak(self._h, int(kind), int(n_cols), C.byref(v)))
         return v.value
 
     def build_pool(self, argb: np.ndarray, B: int, rgb: bool):

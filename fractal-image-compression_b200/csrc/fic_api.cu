@@ -50,6 +50,7 @@ struct fic_handle {
     cudaEvent_t ev[8] = {nullptr};
     Work w;
     int engine_opt = FIC_ENGINE_AUTO;
+    int umma_kind = FIC_UMMA_KIND_AUTO;
     fic_timings tm;
     char err[512];
     bool tm_pending_dev = false;
@@ -174,6 +175,10 @@ int fic_set_option(fic_handle *h, int option, int value)
         h->engine_opt = value;
         return FIC_OK;
     }
+    if (option == FIC_OPT_UMMA_KIND && value >= FIC_UMMA_KIND_AUTO && value <= FIC_UMMA_KIND_F16) {
+        h->umma_kind = value;
+        return FIC_OK;
+    }
     return set_err(h, FIC_E_ARG, "unknown option %d / value %d", option, value);
 }
 
@@ -244,8 +249,8 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     ENSURE(w.rsum, S_RSUM, sizeof(int32_t) * g.C * g.NR);
     ENSURE(w.best, S_BEST, sizeof(int32_t) * g.NR);
     if (engine == FIC_ENGINE_UMMA) {
-        ENSURE(w.opA, S_OPA, umma_opA_bytes(g, j0, j1, h->num_sms));
-        ENSURE(w.opB, S_OPB, umma_opB_bytes(g));
+        ENSURE(w.opA, S_OPA, umma_opA_bytes(g, j0, j1, h->num_sms, h->umma_kind));
+        ENSURE(w.opB, S_OPB, umma_opB_bytes(g, h->umma_kind));
     }
     Work call = w;  // per-call view: the source planes may belong to the caller
     call.src = const_cast<uint8_t *>(d_src);
@@ -257,7 +262,7 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     CU(cudaEventRecord(h->ev[2], s));
     if (engine == FIC_ENGINE_UMMA) {
         const char *why = nullptr;
-        int n = launch_search_umma(call, g, j0, j1, h->num_sms, s, &why, h->ev[6], h->ev[7]);
+        int n = launch_search_umma(call, g, j0, j1, h->num_sms, s, &why, h->umma_kind, h->ev[6], h->ev[7]);
         if (n == -2) {  // B = 16 digit overflow (a 255 pixel in a block of mean 0): exact direct search instead
             engine = FIC_ENGINE_DIRECT;
             CU(cudaEventRecord(h->ev[6], s));
@@ -360,16 +365,19 @@ int fic_encode_planes_dev(fic_handle *h, const uint8_t *d_planes, int is_rgb, in
     return rc;
 }
 
-int fic_measure_int8_peak(fic_handle *h, double *tops)
+int fic_measure_mma_peak(fic_handle *h, int kind, int n_cols, double *tops)
 {
-    if (!h || !tops) return FIC_E_ARG;
+    if (!h || !tops || (kind != FIC_UMMA_KIND_I8 && kind != FIC_UMMA_KIND_F16) || (n_cols != 128 && n_cols != 256))
+        return FIC_E_ARG;
     CU(cudaSetDevice(h->device));
     const char *why = nullptr;
-    double v = measure_int8_peak(h->num_sms, h->stream, 3, &why);
-    if (v < 0) return set_err(h, FIC_E_CUDA, "int8 peak measurement failed: %s", why ? why : "?");
+    double v = measure_mma_peak(h->num_sms, h->stream, 3, kind == FIC_UMMA_KIND_F16, n_cols, &why);
+    if (v < 0) return set_err(h, FIC_E_CUDA, "tensor peak measurement failed: %s", why ? why : "?");
     *tops = v;
     return FIC_OK;
 }
+
+int fic_measure_int8_peak(fic_handle *h, double *tops) { return fic_measure_mma_peak(h, FIC_UMMA_KIND_I8, 256, tops); }
 
 int fic_build_pool(fic_handle *h, const int32_t *argb, int is_rgb, int W, int H, int B, uint8_t *decimated,
                    int32_t *dom_sum, int32_t *dom_sumsq)

@@ -59,18 +59,22 @@ int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_
                  cudaStream_t s);
 
 // tcgen05 fused full-pool search (grey, window == whole pool).
-// bare tcgen05 kind::i8 loop: measured dense int8 rate of this GPU in TOP/s (< 0 on error)
-double measure_int8_peak(int num_sms, cudaStream_t s, int reps, const char **err);
+// bare tcgen05.mma loop (M = 128, N = n_cols in {128, 256}): measured dense rate of kind::i8 (f16 = 0) or
+// kind::f16 on this GPU in TOP/s (< 0 on error)
+double measure_mma_peak(int num_sms, cudaStream_t s, int reps, int f16, int n_cols, const char **err);
 bool umma_applicable(const Geom &g);
-size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms);
-size_t umma_opB_bytes(const Geom &g);
+// `kind`: FIC_UMMA_KIND_AUTO / _I8 / _F16 (B = 16 always runs kind::i8); umma_default_kind = what AUTO picks
+int umma_default_kind(const Geom &g);
+size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms, int kind);
+size_t umma_opB_bytes(const Geom &g, int kind);
 // device table: sweep position -> domain index (-1: padding), valid after a launch; probe only
-void umma_debug_positions(const Work &w, const Geom &g, int64_t rows, int num_sms, const int32_t **d_pos_dom,
-                          int64_t *npos);
+void umma_debug_positions(const Work &w, const Geom &g, int64_t rows, int num_sms, int kind,
+                          const int32_t **d_pos_dom, int64_t *npos);
 int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms,
-                       cudaStream_t s, const char **err, cudaEvent_t k0 = nullptr, cudaEvent_t k1 = nullptr);
+                       cudaStream_t s, const char **err, int kind, cudaEvent_t k0 = nullptr,
+                       cudaEvent_t k1 = nullptr);
 int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms,
-                             cudaStream_t s, const char **err, int32_t *dump, int64_t dump_ld,
+                             cudaStream_t s, const char **err, int kind, int32_t *dump, int64_t dump_ld,
                              int *status_dev, int variant, uint32_t dbg = 0, cudaEvent_t k0 = nullptr,
                              cudaEvent_t k1 = nullptr);
 

@@ -61,6 +61,7 @@
 //   warps 4-19  epilogue: warp e owns TMEM lane quarter e % 4 and column half (e / 4) & 1
 //               of accumulators (e / 8) and (e / 8) + 2; one thread = two range rows
 // A work unit is (super-block of 512 rows) x (1/n_chunks of the domain tiles).
+#include <cuda_fp16.h>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "fic_device.cuh"
@@ -80,12 +81,15 @@ constexpr int kBoundBytes = kChunksPerTile * 2 * 4 + 16;  // (rhi, rlo) f32 per 
 constexpr int kFlagCap = 32;                         // flagged chunks kept per (row, unit, column half)
 constexpr float kOneMinusEps = 1.0f - 1.9073486328125e-06f;  // 1 - 2^-19 (applied to the squared score)
 
-template <int B>
+// Operand geometry of one (block size, MMA kind) pair.  F16 = false: kind::i8, two s8 digits per
+// centred domain pixel.  F16 = true: kind::f16, both operands centred and stored as binary16.
+// A "K-slice" is the 32 bytes of K one tcgen05.mma consumes (32 i8 or 16 f16 elements).
+template <int B, bool F16>
 struct Cfg;
 template <>
-struct Cfg<8> {
+struct Cfg<8, false> {
     static constexpr int n = 64;
-    static constexpr int KS_A = 3;   // physical A K-slices (32 B each): r[0:32] r[32:64] [rmean 0..]
+    static constexpr int KS_A = 3;   // physical A K-slices: r[0:32] r[32:64] [rmean rmean 0..]
     static constexpr int KS_B = 5;   // h[0:32] h[32:64] l[0:32] l[32:64] [-alpha 0..]
     static constexpr int NS = 5;     // MMA K-slices
     static constexpr int NSTAGE = 7;
@@ -93,7 +97,7 @@ struct Cfg<8> {
     __host__ __device__ static constexpr bool is_l_slice(int s) { return s == 2 || s == 3; }
 };
 template <>
-struct Cfg<4> {
+struct Cfg<4, false> {
     static constexpr int n = 16;
     static constexpr int KS_A = 2;   // [r r] [rmean 0..]
     static constexpr int KS_B = 2;   // [h l] [-alpha 0..]
@@ -102,9 +106,8 @@ struct Cfg<4> {
     __host__ __device__ static constexpr int amap(int s) { return s; }
     __host__ __device__ static constexpr bool is_l_slice(int) { return false; }  // h and l share slice 0
 };
-
 template <>
-struct Cfg<16> {
+struct Cfg<16, false> {
     static constexpr int n = 256;
     static constexpr int KS_A = 9;   // r[0:256] (8 slices) [rmean 0..]
     static constexpr int KS_B = 17;  // h (8 slices) l (8 slices) [-alpha 0..]
@@ -113,10 +116,30 @@ struct Cfg<16> {
     __host__ __device__ static constexpr int amap(int s) { return s < 16 ? (s & 7) : 8; }
     __host__ __device__ static constexpr bool is_l_slice(int s) { return s >= 8 && s < 16; }
 };
+template <>
+struct Cfg<8, true> {
+    static constexpr int n = 64;
+    static constexpr int KS_A = 4;   // (r - rmean)[0:64] as binary16: 4 slices of 16 elements
+    static constexpr int KS_B = 4;   // (d - dmean)[0:64] as binary16
+    static constexpr int NS = 4;
+    static constexpr int NSTAGE = 8;
+    __host__ __device__ static constexpr int amap(int s) { return s; }
+    __host__ __device__ static constexpr bool is_l_slice(int) { return false; }
+};
+template <>
+struct Cfg<4, true> {
+    static constexpr int n = 16;
+    static constexpr int KS_A = 1;
+    static constexpr int KS_B = 1;
+    static constexpr int NS = 1;
+    static constexpr int NSTAGE = 8;
+    __host__ __device__ static constexpr int amap(int s) { return s; }
+    __host__ __device__ static constexpr bool is_l_slice(int) { return false; }
+};
 
-template <int B>
+template <int B, bool F16>
 struct Lay {
-    using C = Cfg<B>;
+    using C = Cfg<B, F16>;
     static constexpr int SBO_A = C::KS_A * 256;
     static constexpr int SBO_B = C::KS_B * 256;
     static constexpr int A_BLOCK_BYTES = (kBlockM / 8) * SBO_A;
@@ -154,25 +177,34 @@ __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
     return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
 }
 
+// Two integers in [-255, 255] as a packed pair of binary16 (exact: |v| < 2048).
+__device__ __forceinline__ uint32_t pack_h2(int lo, int hi)
+{
+    const __half2 v = __halves2half2(__int2half_rn(lo), __int2half_rn(hi));
+    return *(const uint32_t *)&v;
+}
+
 // One thread per sweep position (a warp = one 32-position chunk): centre the domain by its
-// integer mean, split into two s8 digits, write the tile-blob row, the position tables used
-// by the refine step, and the chunk's scale bounds.
-template <int B>
+// integer mean, write the tile-blob row (kind::i8: two s8 digits + the -alpha columns; kind::f16:
+// binary16), the position tables and the raw pixels used by the refine step, and the chunk's scale
+// bounds.
+template <int B, bool F16>
 __global__ void __launch_bounds__(128)
 k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
                     const int32_t *__restrict__ dsq, const int32_t *__restrict__ perm, uint8_t *__restrict__ opB,
-                    int32_t *__restrict__ pos_dom, int32_t *__restrict__ pos_var, int64_t *__restrict__ dom0_pos,
-                    int *__restrict__ unsupported, Geom g, int64_t ntiles, uint32_t mult)
+                    int32_t *__restrict__ pos_dom, int32_t *__restrict__ pos_var, int32_t *__restrict__ pos_sum,
+                    uint8_t *__restrict__ pos_raw, int64_t *__restrict__ dom0_pos, int *__restrict__ unsupported,
+                    Geom g, int64_t ntiles, uint32_t mult)
 {
-    using L = Lay<B>;
-    constexpr int n = Cfg<B>::n;
+    using L = Lay<B, F16>;
+    constexpr int n = Cfg<B, F16>::n;
     const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t tile = pos / kTileN;
     const int row = (int)(pos % kTileN);
     const int64_t sp = sweep_to_sorted(pos, mult, ntiles * kChunksPerTile);
     uint8_t *blob = opB + tile * L::B_TILE_BYTES;
     uint8_t *rowp = blob + (row >> 3) * L::SBO_B + (row & 7) * 16;
-    constexpr int NCH = Cfg<B>::KS_B * 2;  // 16-byte chunks per row
+    constexpr int NCH = Cfg<B, F16>::KS_B * 2;  // 16-byte chunks per row
     float rsd_hi = 0.0f, rsd_lo = __int_as_float(0x7f800000);
     int any_l = 0;
     if (sp >= g.ND) {
@@ -180,43 +212,66 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
         for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
         pos_dom[pos] = -1;
         pos_var[pos] = 0;
+        pos_sum[pos] = 0;
     } else {
         const int64_t j = perm[sp];
         const int gx = (int)(j % g.dpw), gy = (int)(j / g.dpw);
         const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
         int dmean;
         const int varD = dom_var(dsum[j], dsq[j], n, &dmean);
-        const int alpha = dsum[j] - n * dmean;
-        constexpr int PCH = n / 16;  // pixel chunks per digit
+        constexpr int PCH = n / 16;  // 16-pixel groups
 #pragma unroll
         for (int c = 0; c < PCH; c++) {
-            uint32_t hw[4], lw[4];
+            int dv[16];
+            uint32_t raw[4];
 #pragma unroll
             for (int w = 0; w < 4; w++) {
-                int hv[4], lv[4];
+                raw[w] = 0;
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    int k = c * 16 + w * 4 + e;
-                    int dt = (int)__ldg(p + (int64_t)(k / B) * g.sw + (k % B)) - dmean;
-                    hv[e] = max(-128, min(127, dt));  // the low digit is zero unless |dt| > 127
-                    lv[e] = dt - hv[e];
-                    any_l |= lv[e];
-                    // B = 16 only: d = 255 in a block of mean 0 gives dt = 255 = 127 + 128, one more than two
-                    // s8 digits hold; the caller then falls back to the direct search for this image
-                    if (B == 16 && lv[e] > 127) *unsupported = 1;
+                    const int k = c * 16 + w * 4 + e;
+                    const int d = (int)__ldg(p + (int64_t)(k / B) * g.sw + (k % B));
+                    raw[w] |= (uint32_t)d << (8 * e);
+                    dv[w * 4 + e] = d - dmean;
                 }
-                hw[w] = pack4(hv[0], hv[1], hv[2], hv[3]);
-                lw[w] = pack4(lv[0], lv[1], lv[2], lv[3]);
             }
-            *(uint4 *)(rowp + c * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *(uint4 *)(rowp + (PCH + c) * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            *(uint4 *)(pos_raw + pos * n + c * 16) = make_uint4(raw[0], raw[1], raw[2], raw[3]);
+            if (F16) {
+                *(uint4 *)(rowp + (2 * c) * 128) =
+                    make_uint4(pack_h2(dv[0], dv[1]), pack_h2(dv[2], dv[3]), pack_h2(dv[4], dv[5]), pack_h2(dv[6], dv[7]));
+                *(uint4 *)(rowp + (2 * c + 1) * 128) = make_uint4(pack_h2(dv[8], dv[9]), pack_h2(dv[10], dv[11]),
+                                                                  pack_h2(dv[12], dv[13]), pack_h2(dv[14], dv[15]));
+            } else {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    int hv[4], lv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        hv[e] = max(-128, min(127, dv[w * 4 + e]));  // the low digit is zero unless |dt| > 127
+                        lv[e] = dv[w * 4 + e] - hv[e];
+                        any_l |= lv[e];
+                        // B = 16 only: d = 255 in a block of mean 0 gives dt = 255 = 127 + 128, one more than two
+                        // s8 digits hold; the caller then falls back to the direct search for this image
+                        if (B == 16 && lv[e] > 127) *unsupported = 1;
+                    }
+                    hw[w] = pack4(hv[0], hv[1], hv[2], hv[3]);
+                    lw[w] = pack4(lv[0], lv[1], lv[2], lv[3]);
+                }
+                *(uint4 *)(rowp + c * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *(uint4 *)(rowp + (PCH + c) * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
         }
-        // -alpha in two s8 columns (alpha <= n - 1 = 255 at B = 16); A carries rmean in both
-        const int a1 = alpha >> 1, a2 = alpha - a1;
-        *(uint4 *)(rowp + (2 * PCH) * 128) = make_uint4((uint32_t)((-a1) & 0xff) | ((uint32_t)((-a2) & 0xff) << 8), 0, 0, 0);
-        *(uint4 *)(rowp + (2 * PCH + 1) * 128) = make_uint4(0, 0, 0, 0);
+        if (!F16) {
+            // -alpha in two s8 columns (alpha <= n - 1 = 255 at B = 16); A carries rmean in both
+            const int alpha = dsum[j] - n * dmean;
+            const int a1 = alpha >> 1, a2 = alpha - a1;
+            *(uint4 *)(rowp + (2 * PCH) * 128) = make_uint4((uint32_t)((-a1) & 0xff) | ((uint32_t)((-a2) & 0xff) << 8), 0, 0, 0);
+            *(uint4 *)(rowp + (2 * PCH + 1) * 128) = make_uint4(0, 0, 0, 0);
+        }
         pos_dom[pos] = (int32_t)j;
         pos_var[pos] = varD;
+        pos_sum[pos] = dsum[j];
         if (j == 0) *dom0_pos = pos;  // the refine step always evaluates domain 0
         if (varD > 0) {  // flat domains have kov == 0: they never set a chunk's max |kov|
             float r = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn((double)varD)));
@@ -237,21 +292,22 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
     if (threadIdx.x == 0) *(uint4 *)(blob + L::B_OP_BYTES + kChunksPerTile * 8) = make_uint4((uint32_t)tile_has_l, 0, 0, 0);
 }
 
-// One thread per (padded) range row of the slice [j0, j1): raw pixels + integer mean.
-template <int B>
+// One thread per (padded) range row of the slice [j0, j1).  kind::i8: raw pixels + the integer mean
+// columns; kind::f16: pixels centred by the integer mean, as binary16.
+template <int B, bool F16>
 __global__ void __launch_bounds__(128)
 k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, uint8_t *__restrict__ opA,
                    int32_t *__restrict__ vRout, Geom g, int64_t j0, int64_t j1, int64_t rows_padded)
 {
-    using L = Lay<B>;
-    constexpr int n = Cfg<B>::n;
+    using L = Lay<B, F16>;
+    constexpr int n = Cfg<B, F16>::n;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows_padded) return;
     int64_t sb = i / kRowsPerSB;
     int rr = (int)(i % kRowsPerSB);
     int blk = rr / kBlockM, row = rr % kBlockM;
     uint8_t *rowp = opA + sb * L::A_SB_BYTES + blk * L::A_BLOCK_BYTES + (row >> 3) * L::SBO_A + (row & 7) * 16;
-    constexpr int NCH = Cfg<B>::KS_A * 2;
+    constexpr int NCH = Cfg<B, F16>::KS_A * 2;
     int64_t j = j0 + i;
     if (j >= j1) {
 #pragma unroll
@@ -274,13 +330,26 @@ k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ 
             // 4 consecutive k share a pixel row for B >= 4; 4-byte aligned since xr*B, k%B are multiples of 4
             w4[w] = *(const uint32_t *)(p + (int64_t)(k / B) * g.W + (k % B));
         }
-        uint4 v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-        *(uint4 *)(rowp + c * 128) = v;
-        if (B == 4) *(uint4 *)(rowp + (PCH + c) * 128) = v;  // [r r] shares one 32-byte slice
+        if (F16) {
+            uint32_t hw[8];
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                hw[2 * w] = pack_h2((int)(w4[w] & 0xff) - rmean, (int)((w4[w] >> 8) & 0xff) - rmean);
+                hw[2 * w + 1] = pack_h2((int)((w4[w] >> 16) & 0xff) - rmean, (int)(w4[w] >> 24) - rmean);
+            }
+            *(uint4 *)(rowp + (2 * c) * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *(uint4 *)(rowp + (2 * c + 1) * 128) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        } else {
+            uint4 v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            *(uint4 *)(rowp + c * 128) = v;
+            if (B == 4) *(uint4 *)(rowp + (PCH + c) * 128) = v;  // [r r] shares one 32-byte slice
+        }
     }
-    constexpr int XCH = (B == 4) ? 2 * PCH : PCH;
-    *(uint4 *)(rowp + XCH * 128) = make_uint4((uint32_t)rmean | ((uint32_t)rmean << 8), 0, 0, 0);
-    *(uint4 *)(rowp + (XCH + 1) * 128) = make_uint4(0, 0, 0, 0);
+    if (!F16) {
+        constexpr int XCH = (B == 4) ? 2 * PCH : PCH;
+        *(uint4 *)(rowp + XCH * 128) = make_uint4((uint32_t)rmean | ((uint32_t)rmean << 8), 0, 0, 0);
+        *(uint4 *)(rowp + (XCH + 1) * 128) = make_uint4(0, 0, 0, 0);
+    }
 }
 
 // ---------------------------------------------------------------- PTX wrappers -------
@@ -359,6 +428,14 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(
@@ -379,10 +456,10 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr)
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
     return v;
 }
-__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c)
+__device__ __forceinline__ int dp4a_uu(uint32_t a_u8x4, uint32_t b_u8x4, int c)
 {
     int d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_u8x4), "r"(c));
     return d;
 }
 
@@ -400,20 +477,23 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // at bit 24.
 constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
                             ((uint32_t)(kBlockM >> 4) << 24);
+// kind::f16: D = f32 (c_format 1), A = B = binary16 (format 0), both K-major.
+constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+                               ((uint32_t)(kBlockM >> 4) << 24);
 
 // ---------------------------------------------------------------- the search kernel --
 
 // DBG (probe builds only): 1 = skip the scoring, 3 = skip the TMEM loads too.  DUMP: write every
 // accumulator to `dump` (the probe's exactness check).  The product runs <B, 0, false>.
-template <int B, int DBG, bool DUMP>
+template <int B, bool F16, int DBG, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
               int32_t *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, int n_sb, int n_chunks, int ntiles,
               int64_t rows_padded, int32_t *__restrict__ dump, int64_t dump_ld, volatile int *status,
               uint32_t lbo_bytes_a, uint32_t sbo_bytes_a, uint32_t lbo_bytes_b, uint32_t sbo_bytes_b)
 {
-    using C = Cfg<B>;
-    using L = Lay<B>;
+    using C = Cfg<B, F16>;
+    using L = Lay<B, F16>;
     constexpr int NSTAGE = C::NSTAGE;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [A super-block][NSTAGE domain tiles][barriers]
@@ -509,7 +589,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                             if (C::is_l_slice(s) && !has_l) continue;  // sum r*l == 0 for the whole tile
                             const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + C::amap(s) * 256) >> 4);
                             const uint64_t bd = b_desc + (uint64_t)((s * 256) >> 4);
-                            tc_mma_i8(tmem_base + q * kTileN, ad, bd, kIdesc, s > 0 ? 1u : 0u);
+                            if (F16) tc_mma_f16(tmem_base + q * kTileN, ad, bd, kIdescF16, s > 0 ? 1u : 0u);
+                            else tc_mma_i8(tmem_base + q * kTileN, ad, bd, kIdesc, s > 0 ? 1u : 0u);
                         }
                         tc_commit(BAR_T_FULL(q));
                     }
@@ -592,20 +673,40 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                             if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
                         }
                         if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring
-                        int mx0 = 0, mn0 = 0, mx1 = 0, mn1 = 0;  // two independent chains each: ALU latency
+                        float M;  // max |kov| over the chunk, exact
+                        if (F16) {
+                            // binary32 accumulators holding exact integers: FMNMX3 |a|, |b|, c takes two per op
+                            float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
 #pragma unroll
-                        for (int k = 0; k < 32; k += 4) {
-                            mx0 = max(mx0, max((int)v[k], (int)v[k + 1]));
-                            mn0 = min(mn0, min((int)v[k], (int)v[k + 1]));
-                            mx1 = max(mx1, max((int)v[k + 2], (int)v[k + 3]));
-                            mn1 = min(mn1, min((int)v[k + 2], (int)v[k + 3]));
+                            for (int k = 0; k < 32; k += 8) {
+                                m0 = fmaxf(m0, fmaxf(fabsf(__uint_as_float(v[k])), fabsf(__uint_as_float(v[k + 1]))));
+                                m1 = fmaxf(m1, fmaxf(fabsf(__uint_as_float(v[k + 2])), fabsf(__uint_as_float(v[k + 3]))));
+                                m2 = fmaxf(m2, fmaxf(fabsf(__uint_as_float(v[k + 4])), fabsf(__uint_as_float(v[k + 5]))));
+                                m3 = fmaxf(m3, fmaxf(fabsf(__uint_as_float(v[k + 6])), fabsf(__uint_as_float(v[k + 7]))));
+                            }
+                            M = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                        } else {
+                            int mx0 = 0, mn0 = 0, mx1 = 0, mn1 = 0;  // two independent chains each: ALU latency
+#pragma unroll
+                            for (int k = 0; k < 32; k += 4) {
+                                mx0 = max(mx0, max((int)v[k], (int)v[k + 1]));
+                                mn0 = min(mn0, min((int)v[k], (int)v[k + 1]));
+                                mx1 = max(mx1, max((int)v[k + 2], (int)v[k + 3]));
+                                mn1 = min(mn1, min((int)v[k + 2], (int)v[k + 3]));
+                            }
+                            M = __int2float_rn(max(max(mx0, mx1), -min(mn0, mn1)));
                         }
-                        const float M = __int2float_rn(max(max(mx0, mx1), -min(mn0, mn1)));  // max |kov|, exact
                         const int c = half * 2 + cc;                   // chunk of the tile
                         if (DUMP) {
 #pragma unroll
-                            for (int k = 0; k < 32; k++)
-                                dump[row[sl] * dump_ld + (int64_t)t * kTileN + c * 32 + k] = (int)v[k];
+                            for (int k = 0; k < 32; k++) {
+                                int iv = (int)v[k];
+                                if (F16) {  // a non-integral accumulator must fail the probe's check
+                                    const float f = __uint_as_float(v[k]);
+                                    iv = (f == rintf(f) && fabsf(f) < 2.0e9f) ? (int)f : (int)0x80000000;
+                                }
+                                dump[row[sl] * dump_ld + (int64_t)t * kTileN + c * 32 + k] = iv;
+                            }
                         }
                         if (M * (cc ? bnd.z : bnd.x) > thresh[sl]) {  // may hold the winner or one of its float ties
                             if (cnt[sl] < kFlagCap) my_list[sl][cnt[sl]] = t * kChunksPerTile + c;
@@ -638,24 +739,26 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     }
 }
 
-// ---------------------------------------------------------------- int8 pipe peak -------
+// ---------------------------------------------------------------- tensor pipe peak -----
 
-// Bare tcgen05.mma.kind::i8 loop (M=128, N=256, K=32 per instruction, operands resident in shared
-// memory, two alternating TMEM accumulators, no epilogue): measures what the int8 tensor pipe of
-// this GPU sustains, the denominator of the search kernel's roofline (MEASURED_PEAKS.json only
-// carries a bf16 figure).
-__global__ void __launch_bounds__(128, 1) k_int8_peak(int iters, uint32_t seed)
+// Bare tcgen05.mma loop (M=128, N columns, one 32-byte K-slice per instruction, operands resident
+// in shared memory, alternating TMEM accumulators, no epilogue): measures what the tensor pipe of
+// this GPU sustains for the instruction shape the search uses -- the denominator of the search
+// kernel's roofline (MEASURED_PEAKS.json only carries a cuBLAS bf16 figure).
+template <bool F16, int N>
+__global__ void __launch_bounds__(128, 1) k_mma_peak(int iters, uint32_t seed)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;                 // 128 rows x 32 B, core-matrix order (16 groups x 256 B)
-    uint8_t *sB = smem + 4096;          // 256 rows x 32 B
+    uint8_t *sB = smem + 4096;          // N rows x 32 B
     uint64_t *bar = (uint64_t *)(smem + 4096 + 8192);
     uint32_t *tmem_slot = (uint32_t *)(bar + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < (4096 + 8192) / 4; i += blockDim.x) {
         uint32_t x = (uint32_t)i * 2654435761u + seed + blockIdx.x * 40503u;
         x ^= x >> 15; x *= 0x2c1b3c6du; x ^= x >> 12;
+        if (F16) x &= 0x3fff3fffu;  // finite binary16 values below 2: no NaN / Inf arithmetic
         ((uint32_t *)smem)[i] = x;
     }
     if (threadIdx.x == 0) {
@@ -677,16 +780,20 @@ __global__ void __launch_bounds__(128, 1) k_int8_peak(int iters, uint32_t seed)
         const uint32_t elected = elect_one();
         const uint64_t ad = make_desc(smem_u32(sA), 128, 256);
         const uint64_t bd = make_desc(smem_u32(sB), 128, 256);
-        constexpr uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) |
-                                   ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc = (F16 ? ((1u << 4) | (0u << 7) | (0u << 10)) : ((2u << 4) | (0u << 7) | (1u << 10))) |
+                                   ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr int NACC = 512 / N;
         if (elected) {
-            for (int i = 0; i < iters; i++) tc_mma_i8(tmem_base + (i & 1) * 256, ad, bd, idesc, i > 1 ? 1u : 0u);
+            for (int i = 0; i < iters; i++) {
+                const uint32_t d = tmem_base + (uint32_t)(i & (NACC - 1)) * N;
+                if (F16) tc_mma_f16(d, ad, bd, idesc, i >= NACC ? 1u : 0u);
+                else tc_mma_i8(d, ad, bd, idesc, i >= NACC ? 1u : 0u);
+            }
             tc_commit(smem_u32(bar));
         }
         __syncwarp();
         mbar_wait(smem_u32(bar), 0, nullptr, 9);
     }
-    (void)lane;
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -697,34 +804,27 @@ __global__ void __launch_bounds__(128, 1) k_int8_peak(int iters, uint32_t seed)
 
 // ---------------------------------------------------------------- refine --------------
 
-// Exact score of the candidate at sweep position `pos` for one range row, from the packed
-// operand row (coalesced 16-byte loads): kov = sum r*h + sum r*l + rmean*(-alpha), then the
-// reference's own expression (FC:677-683).  rw[] = the range block as packed u8 words.
+// Exact score of the candidate at sweep position `pos` for one range row, from the raw domain
+// pixels packed per sweep position (64 contiguous bytes at B = 8; a warp reads one 32-candidate
+// chunk as one contiguous block):
+//     kov = sum (r - rmean)(d - dmean) = sum r*d - rmean * dsum - dmean * vR      (exact in s32)
+// then the reference's own expression (FC:677-683).  rw[] = the range block as packed u8 words.
 template <int B>
-__device__ __forceinline__ float refine_eval_packed(const uint32_t *rw, int rmean, int vR, const uint8_t *__restrict__ opB,
-                                                    int64_t pos, int varD)
+__device__ __forceinline__ float refine_eval_raw(const uint32_t *rw, int rmean, int vR, const uint8_t *__restrict__ pos_raw,
+                                                 int64_t pos, int dsum, int varD)
 {
-    using L = Lay<B>;
-    constexpr int PCH = Cfg<B>::n / 16;
-    const int64_t tile = pos / kTileN;
-    const int row = (int)(pos % kTileN);
-    const uint8_t *rowp = opB + tile * L::B_TILE_BYTES + (row >> 3) * L::SBO_B + (row & 7) * 16;
+    constexpr int n = B * B;
+    const uint4 *dp = (const uint4 *)(pos_raw + pos * n);
     int kov = 0;
 #pragma unroll
-    for (int c = 0; c < PCH; c++) {
-        const uint4 h = __ldg((const uint4 *)(rowp + c * 128));
-        const uint4 l = __ldg((const uint4 *)(rowp + (PCH + c) * 128));
-        kov = dp4a_us(rw[4 * c + 0], h.x, kov);
-        kov = dp4a_us(rw[4 * c + 1], h.y, kov);
-        kov = dp4a_us(rw[4 * c + 2], h.z, kov);
-        kov = dp4a_us(rw[4 * c + 3], h.w, kov);
-        kov = dp4a_us(rw[4 * c + 0], l.x, kov);
-        kov = dp4a_us(rw[4 * c + 1], l.y, kov);
-        kov = dp4a_us(rw[4 * c + 2], l.z, kov);
-        kov = dp4a_us(rw[4 * c + 3], l.w, kov);
+    for (int c = 0; c < n / 16; c++) {
+        const uint4 d = __ldg(dp + c);
+        kov = dp4a_uu(rw[4 * c + 0], d.x, kov);
+        kov = dp4a_uu(rw[4 * c + 1], d.y, kov);
+        kov = dp4a_uu(rw[4 * c + 2], d.z, kov);
+        kov = dp4a_uu(rw[4 * c + 3], d.w, kov);
     }
-    const uint32_t xw = __ldg((const uint32_t *)(rowp + (2 * PCH) * 128));
-    kov += rmean * ((int)(int8_t)(xw & 0xff) + (int)(int8_t)((xw >> 8) & 0xff));  // rmean * (-alpha)
+    kov -= rmean * dsum + (dsum / n) * vR;
     return grey_error(kov, vR, __dsqrt_rn((double)varD));
 }
 
@@ -734,8 +834,8 @@ __device__ __forceinline__ float refine_eval_packed(const uint32_t *rw, int rmea
 // the smallest error.  A row whose flag list overflowed is rescanned in full -- slow, exact.
 template <int B>
 __global__ void __launch_bounds__(128)
-k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ opB,
-              const int32_t *__restrict__ pos_dom, const int32_t *__restrict__ pos_var,
+k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ pos_raw,
+              const int32_t *__restrict__ pos_dom, const int32_t *__restrict__ pos_var, const int32_t *__restrict__ pos_sum,
               const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
               int64_t rows_padded, int64_t rows, int64_t npos, const int64_t *__restrict__ dom0_pos,
               int32_t *__restrict__ best, Geom g, int64_t j0)
@@ -764,7 +864,7 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
     auto consider = [&](int64_t pos) {
         const int idx = pos_dom[pos];
         if (idx >= 0) {
-            const float err = refine_eval_packed<B>(rw, rmean, vR, opB, pos, pos_var[pos]);
+            const float err = refine_eval_raw<B>(rw, rmean, vR, pos_raw, pos, pos_sum[pos], pos_var[pos]);
             if (err < be || (err == be && idx < bi)) { be = err; bi = idx; }
         }
     };
@@ -822,16 +922,20 @@ inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
     return p;
 }
 
-// opB workspace: [tile blobs][pos_dom s32][pos_var s32][dom0 pos s64][sort: keys x2, vals x2, cub temp]
-template <int B>
+// opB workspace: [tile blobs][pos_dom s32][pos_var s32][pos_sum s32][pos_raw u8 x n][dom0 pos s64]
+//                [sort: keys x2, vals x2, cub temp]
+template <int B, bool F16>
 struct OpBLayout {
-    size_t off_posdom, off_posvar, off_dom0, off_keys0, off_keys1, off_vals0, off_vals1, off_temp, temp_bytes, total;
+    size_t off_posdom, off_posvar, off_possum, off_posraw, off_dom0, off_keys0, off_keys1, off_vals0, off_vals1, off_temp,
+        temp_bytes, total;
     OpBLayout(const Geom &g, const Plan &p)
     {
-        size_t o = (size_t)p.ntiles * Lay<B>::B_TILE_BYTES;
+        size_t o = (size_t)p.ntiles * Lay<B, F16>::B_TILE_BYTES;
         auto take = [&](size_t bytes) { size_t at = (o + 255) & ~(size_t)255; o = at + bytes; return at; };
         off_posdom = take((size_t)p.npos * 4);
         off_posvar = take((size_t)p.npos * 4);
+        off_possum = take((size_t)p.npos * 4);
+        off_posraw = take((size_t)p.npos * (B * B));
         off_dom0 = take(16);  // s64 sweep position of domain 0, then the s32 `unsupported` flag
         off_keys0 = take((size_t)g.ND * 4);
         off_keys1 = take((size_t)g.ND * 4);
@@ -846,20 +950,21 @@ struct OpBLayout {
     }
 };
 
-template <int B>
+template <int B, bool F16>
 size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p = make_plan(g, rows, num_sms);
     // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap]
-    return (size_t)p.n_sb * Lay<B>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 2 * 4 * (1 + kFlagCap) + 1024;
+    return (size_t)p.n_sb * Lay<B, F16>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 2 * 4 * (1 + kFlagCap) +
+           1024;
 }
 
-template <int B>
+template <int B, bool F16>
 int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s, const char **err,
              int32_t *dump, int64_t dump_ld, int *status_dev, int variant, cudaEvent_t k0 = nullptr,
              cudaEvent_t k1 = nullptr, uint32_t dbg = 0)
 {
-    using L = Lay<B>;
+    using L = Lay<B, F16>;
     int64_t rows = j1 - j0;
     if (rows <= 0) return 0;
     Plan p = make_plan(g, rows, num_sms);
@@ -868,9 +973,11 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     int32_t *vR = (int32_t *)(opA + (size_t)p.n_sb * L::A_SB_BYTES);
     int32_t *flag_cnt = vR + rp;
     int32_t *flag_list = flag_cnt + rp * p.n_chunks * 2;
-    OpBLayout<B> lay(g, p);
+    OpBLayout<B, F16> lay(g, p);
     int32_t *pos_dom = (int32_t *)(w.opB + lay.off_posdom);
     int32_t *pos_var = (int32_t *)(w.opB + lay.off_posvar);
+    int32_t *pos_sum = (int32_t *)(w.opB + lay.off_possum);
+    uint8_t *pos_raw = w.opB + lay.off_posraw;
     int64_t *dom0 = (int64_t *)(w.opB + lay.off_dom0);
     int *unsupported = (int *)(dom0 + 1);
     int launches = 0;
@@ -885,24 +992,24 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     launches += 4;  // key kernel + radix passes (approximate; they are not the timed kernel)
     // 2. operand blobs
     cudaMemsetAsync(unsupported, 0, sizeof(int), s);
-    k_umma_pack_domains<B><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(w.dec, w.dsum, w.dsq, dv.Current(), w.opB, pos_dom,
-                                                                           pos_var, dom0, unsupported, g, p.ntiles, p.mult);
-    if (B == 16) {  // rare digit overflow (see k_umma_pack_domains): decided on the host before the search starts
+    k_umma_pack_domains<B, F16><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(
+        w.dec, w.dsum, w.dsq, dv.Current(), w.opB, pos_dom, pos_var, pos_sum, pos_raw, dom0, unsupported, g, p.ntiles, p.mult);
+    if (B == 16 && !F16) {  // rare digit overflow (see k_umma_pack_domains): decided on the host before the search starts
         int flag = 0;
         ce = cudaMemcpyAsync(&flag, unsupported, sizeof(int), cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
         if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
         if (flag) return -2;
     }
-    k_umma_pack_ranges<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
+    k_umma_pack_ranges<B, F16><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
     launches += 2;
     // 3. the fused search
     using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int32_t *, int32_t *, int, int, int,
                              int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
-    KernelT kern = k_umma_search<B, 0, false>;  // dbg (probe only): 1 / 3 strip the scoring / the TMEM loads too
-    if (dump) kern = k_umma_search<B, 0, true>;
-    else if ((dbg & 3u) == 1) kern = k_umma_search<B, 1, false>;
-    else if ((dbg & 3u) == 3) kern = k_umma_search<B, 3, false>;
+    KernelT kern = k_umma_search<B, F16, 0, false>;  // dbg (probe only): 1 / 3 strip the scoring / the TMEM loads too
+    if (dump) kern = k_umma_search<B, F16, 0, true>;
+    else if ((dbg & 3u) == 1) kern = k_umma_search<B, F16, 1, false>;
+    else if ((dbg & 3u) == 3) kern = k_umma_search<B, F16, 3, false>;
     ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
     int n_units = p.n_sb * p.n_chunks;
@@ -914,46 +1021,66 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
                                                dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
     if (k1) cudaEventRecord(k1, s);
     // 4. exact refine of the flagged chunks
-    k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, w.opB, pos_dom, pos_var, flag_list, flag_cnt,
-                                                                p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
+    k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_dom, pos_var, pos_sum, flag_list,
+                                                                flag_cnt, p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
     launches += 2;
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
     return launches;
 }
 
+// Dispatch on (block size, MMA kind): B = 16 has no kind::f16 variant (see umma_default_kind).
+#define FIC_UMMA_DISPATCH(B_, F_, EXPR_I8_4, EXPR_I8_8, EXPR_I8_16, EXPR_F16_4, EXPR_F16_8) \
+    ((B_) == 16 ? (EXPR_I8_16) : ((F_) ? ((B_) == 8 ? (EXPR_F16_8) : (EXPR_F16_4)) : ((B_) == 8 ? (EXPR_I8_8) : (EXPR_I8_4))))
+
 }  // namespace
 
-void umma_debug_positions(const Work &w, const Geom &g, int64_t rows, int num_sms, const int32_t **d_pos_dom,
+// kind::f16 with binary32 accumulation is exact while every partial sum stays below 2^24:
+// |kov| <= n * 255^2 = 4.2e6 (B = 8), 2.6e5 (B = 4).  B = 16 (1.66e7, and half the tensor rate of kind::i8
+// for a kernel that is tensor-bound there) stays on kind::i8.
+int umma_default_kind(const Geom &g) { return g.B == 16 ? FIC_UMMA_KIND_I8 : FIC_UMMA_KIND_F16; }
+
+static bool use_f16(const Geom &g, int kind)
+{
+    if (g.B == 16) return false;
+    return (kind == FIC_UMMA_KIND_AUTO ? umma_default_kind(g) : kind) == FIC_UMMA_KIND_F16;
+}
+
+void umma_debug_positions(const Work &w, const Geom &g, int64_t rows, int num_sms, int kind, const int32_t **d_pos_dom,
                           int64_t *npos)
 {
     Plan p = make_plan(g, rows, num_sms);
     *npos = p.npos;
-    if (g.B == 8) *d_pos_dom = (const int32_t *)(w.opB + OpBLayout<8>(g, p).off_posdom);
-    else if (g.B == 16) *d_pos_dom = (const int32_t *)(w.opB + OpBLayout<16>(g, p).off_posdom);
-    else *d_pos_dom = (const int32_t *)(w.opB + OpBLayout<4>(g, p).off_posdom);
+    const size_t off = FIC_UMMA_DISPATCH(g.B, use_f16(g, kind), (OpBLayout<4, false>(g, p).off_posdom),
+                                         (OpBLayout<8, false>(g, p).off_posdom), (OpBLayout<16, false>(g, p).off_posdom),
+                                         (OpBLayout<4, true>(g, p).off_posdom), (OpBLayout<8, true>(g, p).off_posdom));
+    *d_pos_dom = (const int32_t *)(w.opB + off);
 }
 
-// Returns the measured dense int8 rate in TOP/s (2 ops per MAC), best of `reps` launches of ~`ms_target` ms.
-double measure_int8_peak(int num_sms, cudaStream_t s, int reps, const char **err)
+// Returns the measured dense rate in TOP/s (2 ops per MAC) of kind::i8 (f16 = 0) or kind::f16 with M = 128 and
+// N = n_cols (128 or 256), best of `reps` launches.
+double measure_mma_peak(int num_sms, cudaStream_t s, int reps, int f16, int n_cols, const char **err)
 {
     const int smem = 200 * 1024;  // far more than needed: guarantees one CTA (one 512-column TMEM allocation) per SM
-    cudaError_t ce = cudaFuncSetAttribute(k_int8_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    void (*kern)(int, uint32_t) = f16 ? (n_cols == 128 ? k_mma_peak<true, 128> : k_mma_peak<true, 256>)
+                                      : (n_cols == 128 ? k_mma_peak<false, 128> : k_mma_peak<false, 256>);
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1.0; }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const int iters = 200000;  // 128 clk each at full rate: ~13 ms at 1.9 GHz
+    const int iters = 200000 * 256 / n_cols;  // ~13 ms at full rate and 1.9 GHz
+    const double k_per_mma = f16 ? 16.0 : 32.0;
     double best = 0.0;
     for (int r = 0; r < reps + 1; r++) {
         cudaEventRecord(e0, s);
-        k_int8_peak<<<num_sms, 128, smem, s>>>(iters, 0x9e3779b9u + r);
+        kern<<<num_sms, 128, smem, s>>>(iters, 0x9e3779b9u + r);
         cudaEventRecord(e1, s);
         ce = cudaStreamSynchronize(s);
         if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); best = -1.0; break; }
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        double tops = 2.0 * 128.0 * 256.0 * 32.0 * (double)iters * num_sms / (ms * 1e-3) / 1e12;
+        double tops = 2.0 * 128.0 * (double)n_cols * k_per_mma * (double)iters * num_sms / (ms * 1e-3) / 1e12;
         if (r > 0 && tops > best) best = tops;  // launch 0 is the warm-up
     }
     cudaEventDestroy(e0);
@@ -966,35 +1093,39 @@ bool umma_applicable(const Geom &g)
     return g.C == 1 && (g.B == 4 || g.B == 8 || g.B == 16) && g.wk == g.dpw && g.wk == g.dph;
 }
 
-size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms)
+size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms, int kind)
 {
-    return g.B == 8 ? opA_bytes_t<8>(g, j1 - j0, num_sms)
-                    : (g.B == 16 ? opA_bytes_t<16>(g, j1 - j0, num_sms) : opA_bytes_t<4>(g, j1 - j0, num_sms));
+    const int64_t rows = j1 - j0;
+    return FIC_UMMA_DISPATCH(g.B, use_f16(g, kind), (opA_bytes_t<4, false>(g, rows, num_sms)),
+                             (opA_bytes_t<8, false>(g, rows, num_sms)), (opA_bytes_t<16, false>(g, rows, num_sms)),
+                             (opA_bytes_t<4, true>(g, rows, num_sms)), (opA_bytes_t<8, true>(g, rows, num_sms)));
 }
 
-size_t umma_opB_bytes(const Geom &g)
+size_t umma_opB_bytes(const Geom &g, int kind)
 {
     Plan p = make_plan(g, kRowsPerSB, 148);  // the opB layout depends on the pool only
-    return g.B == 8 ? OpBLayout<8>(g, p).total : (g.B == 16 ? OpBLayout<16>(g, p).total : OpBLayout<4>(g, p).total);
-}
-
-int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s,
-                       const char **err, cudaEvent_t k0, cudaEvent_t k1)
-{
-    if (g.B == 8) return launch_t<8>(w, g, j0, j1, num_sms, s, err, nullptr, 0, nullptr, 0, k0, k1);
-    if (g.B == 16) return launch_t<16>(w, g, j0, j1, num_sms, s, err, nullptr, 0, nullptr, 0, k0, k1);
-    return launch_t<4>(w, g, j0, j1, num_sms, s, err, nullptr, 0, nullptr, 0, k0, k1);
+    return FIC_UMMA_DISPATCH(g.B, use_f16(g, kind), (OpBLayout<4, false>(g, p).total), (OpBLayout<8, false>(g, p).total),
+                             (OpBLayout<16, false>(g, p).total), (OpBLayout<4, true>(g, p).total),
+                             (OpBLayout<8, true>(g, p).total));
 }
 
 // Debug entry used by tools/umma_probe: also dumps the raw accumulators (kov) of every
 // (row, sweep position) pair, and lets the probe pick the descriptor variant.
 int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s,
-                             const char **err, int32_t *dump, int64_t dump_ld, int *status_dev, int variant,
+                             const char **err, int kind, int32_t *dump, int64_t dump_ld, int *status_dev, int variant,
                              uint32_t dbg, cudaEvent_t k0, cudaEvent_t k1)
 {
-    if (g.B == 8) return launch_t<8>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg);
-    if (g.B == 16) return launch_t<16>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg);
-    return launch_t<4>(w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg);
+#define FIC_UMMA_ARGS w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg
+    return FIC_UMMA_DISPATCH(g.B, use_f16(g, kind), (launch_t<4, false>(FIC_UMMA_ARGS)), (launch_t<8, false>(FIC_UMMA_ARGS)),
+                             (launch_t<16, false>(FIC_UMMA_ARGS)), (launch_t<4, true>(FIC_UMMA_ARGS)),
+                             (launch_t<8, true>(FIC_UMMA_ARGS)));
+#undef FIC_UMMA_ARGS
+}
+
+int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s,
+                       const char **err, int kind, cudaEvent_t k0, cudaEvent_t k1)
+{
+    return launch_search_umma_debug(w, g, j0, j1, num_sms, s, err, kind, nullptr, 0, nullptr, 0, 0, k0, k1);
 }
 
 }  // namespace fic

@@ -55,7 +55,14 @@ extern "C" {
 #define FIC_ENGINE_DIRECT 1 /* direct (CUDA-core) windowed search for every window    */
 #define FIC_ENGINE_UMMA 2   /* force the tcgen05 search; FIC_E_ARG if not applicable  */
 
+/* Tensor-core instruction kind of the tcgen05 search (fic_set_option(FIC_OPT_UMMA_KIND, ...)).
+ * Both produce the exact integer covariances, hence the same codes. */
+#define FIC_UMMA_KIND_AUTO 0 /* kind::f16 for B = 4, 8; kind::i8 for B = 16               */
+#define FIC_UMMA_KIND_I8 1   /* u8 x s8 -> s32, two s8 digits per centred domain pixel    */
+#define FIC_UMMA_KIND_F16 2  /* binary16 x binary16 -> binary32 (B = 16 still runs i8)    */
+
 #define FIC_OPT_ENGINE 1
+#define FIC_OPT_UMMA_KIND 2
 
 typedef struct fic_handle fic_handle;
 
@@ -131,6 +138,10 @@ int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, in
  * loop (no epilogue, operands resident in shared memory): *tops receives TOP/s (2 ops per MAC).
  * bench.py uses it as the measured roofline denominator of the search kernel. */
 int fic_measure_int8_peak(fic_handle *h, double *tops);
+
+/* The same loop for either instruction kind (FIC_UMMA_KIND_I8 / FIC_UMMA_KIND_F16) and MMA shape
+ * M = 128 x N = n_cols (128: the shape the search issues; 256: the widest single-CTA shape). */
+int fic_measure_mma_peak(fic_handle *h, int kind, int n_cols, double *tops);
 
 /* ---- domain pool inspection (tests / debugging; not on the hot path) ---------- */
 

@@ -18,14 +18,19 @@ def test_engines_agree_full_pool(fic, handle, W, B, kind):
     p = getattr(fic.synth, kind)(W, W, 7)
     img = fic.synth.grey_to_argb(p)
     wk = 2 * W // B - 3
+    from test_gpu_parity import float_bits_equal
+
     handle.set_engine(fic.FIC_ENGINE_DIRECT)
     i1, q1 = handle.encode(img, B, wk, rgb=False)
     handle.set_engine(fic.FIC_ENGINE_UMMA)
-    i2, q2 = handle.encode(img, B, wk, rgb=False)
-    handle.set_engine(fic.FIC_ENGINE_AUTO)
-    from test_gpu_parity import float_bits_equal
-
-    assert (q1 == q2).all() and float_bits_equal(i1, i2)
+    try:
+        for mma in (fic.FIC_UMMA_KIND_I8, fic.FIC_UMMA_KIND_F16):   # both tensor-core instruction kinds
+            handle.set_umma_kind(mma)
+            i2, q2 = handle.encode(img, B, wk, rgb=False)
+            assert (q1 == q2).all() and float_bits_equal(i1, i2), mma
+    finally:
+        handle.set_engine(fic.FIC_ENGINE_AUTO)
+        handle.set_umma_kind(fic.FIC_UMMA_KIND_AUTO)
 
 
 def test_roundtrip_2048(fic, handle):
@@ -59,14 +64,19 @@ def test_periodic_image_ties_and_flag_overflow(fic, handle, W, B, period):
     p[::64, ::64] ^= 1  # a few irregularities so that not every range block is the same
     img = fic.synth.grey_to_argb(p)
     wk = 2 * W // B - 3
+    from test_gpu_parity import float_bits_equal
+
     handle.set_engine(fic.FIC_ENGINE_DIRECT)
     i1, q1 = handle.encode(img, B, wk, rgb=False)
     handle.set_engine(fic.FIC_ENGINE_UMMA)
-    i2, q2 = handle.encode(img, B, wk, rgb=False)
-    handle.set_engine(fic.FIC_ENGINE_AUTO)
-    from test_gpu_parity import float_bits_equal
-
-    assert (q1 == q2).all() and float_bits_equal(i1, i2)
+    try:
+        for mma in (fic.FIC_UMMA_KIND_I8, fic.FIC_UMMA_KIND_F16):   # both tensor-core instruction kinds
+            handle.set_umma_kind(mma)
+            i2, q2 = handle.encode(img, B, wk, rgb=False)
+            assert (q1 == q2).all() and float_bits_equal(i1, i2), mma
+    finally:
+        handle.set_engine(fic.FIC_ENGINE_AUTO)
+        handle.set_umma_kind(fic.FIC_UMMA_KIND_AUTO)
 
 
 def test_full_size_4096(fic, handle):

@@ -111,26 +111,41 @@ def test_full_pool_direct(fic, handle, oracle, request, name, B, wk):
     assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, W, H, B, wk), 3)
 
 
+KINDS = ["i8", "f16"]   # tensor-core instruction kind of the fused search; B = 16 always runs kind::i8
+
+
+def _kind(fic, mma):
+    return fic.FIC_UMMA_KIND_I8 if mma == "i8" else fic.FIC_UMMA_KIND_F16
+
+
+@pytest.mark.parametrize("mma", KINDS)
 @pytest.mark.parametrize("name,B,wk", FULL)
-def test_full_pool_tcgen05(fic, handle, oracle, request, name, B, wk):
+def test_full_pool_tcgen05(fic, handle, oracle, request, name, B, wk, mma):
     img = request.getfixturevalue(name)
     H, W = img.shape
     handle.set_engine(fic.FIC_ENGINE_UMMA)
+    handle.set_umma_kind(_kind(fic, mma))
     try:
         info, q = handle.encode(img, B, wk, rgb=False)
         assert handle.timings().engine == fic.FIC_ENGINE_UMMA
     finally:
         handle.set_engine(fic.FIC_ENGINE_AUTO)
+        handle.set_umma_kind(fic.FIC_UMMA_KIND_AUTO)
     oinfo = oracle.encode(img, B, wk, nthreads=8)
     assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, W, H, B, wk), 3)
 
 
+@pytest.mark.parametrize("mma", KINDS)
 @pytest.mark.parametrize("kind,B", [("noise", 8), ("structured", 8), ("structured", 4), ("sparse", 8), ("flat", 8),
-                                    ("noise", 16), ("structured", 16), ("sparse", 16)])
-def test_full_pool_tcgen05_synthetic(fic, handle, oracle, kind, B):
+                                    ("binary", 8), ("binary", 4), ("noise", 16), ("structured", 16), ("sparse", 16)])
+def test_full_pool_tcgen05_synthetic(fic, handle, oracle, kind, B, mma):
+    if B == 16 and mma == "f16":
+        pytest.skip("B = 16 has no kind::f16 variant")
     W = H = 128
     if kind == "noise":
         p = fic.synth.noise(W, H, 3)
+    elif kind == "binary":   # 0 / 255 in 4x4 cells: the largest |kov| the operands can produce
+        p = np.kron((fic.synth.noise(W // 4, H // 4, 5) >> 7).astype(np.uint8) * 255, np.ones((4, 4), np.uint8))
     elif kind == "structured":
         p = fic.synth.structured(W, H, 3)
     elif kind == "flat":
@@ -141,10 +156,12 @@ def test_full_pool_tcgen05_synthetic(fic, handle, oracle, kind, B):
     img = to_argb_grey(p)
     wk = 2 * W // B - 3
     handle.set_engine(fic.FIC_ENGINE_UMMA)
+    handle.set_umma_kind(_kind(fic, mma))
     try:
         info, q = handle.encode(img, B, wk, rgb=False)
     finally:
         handle.set_engine(fic.FIC_ENGINE_AUTO)
+        handle.set_umma_kind(fic.FIC_UMMA_KIND_AUTO)
     oinfo = oracle.encode(img, B, wk, nthreads=8)
     assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, W, H, B, wk), 3)
 
@@ -276,10 +293,12 @@ def test_cpp_host_cli_roundtrip(tmp_path, oracle, lena_grey):
     assert (dec == ((oimg.view(np.uint32) >> 16) & 0xFF)).all()
 
 
-def test_int8_peak_measurement(handle):
+def test_tensor_peak_measurement(fic, handle):
     tops = handle.measure_int8_peak()
     # nominal dense int8 on B200 is 4500 TOP/s; anything far outside means the loop is not measuring the pipe
     assert 1000.0 < tops < 5500.0, tops
+    tf = handle.measure_mma_peak(fic.FIC_UMMA_KIND_F16, 128)   # nominal dense f16: 2250
+    assert 500.0 < tf < 2750.0, tf
 
 
 def _random_plane(rng, W, H, kind):
@@ -315,15 +334,18 @@ def test_randomised_parity_sweep(fic, handle, oracle):
             img = to_argb_grey(_random_plane(rng, W, H, kind))
         oinfo = oracle.encode(img, B, wk, rgb=rgb)
         ostream = oracle.write_data(oinfo, W, H, B, wk, rgb=rgb)
-        engines = [fic.FIC_ENGINE_DIRECT]
+        engines = [(fic.FIC_ENGINE_DIRECT, fic.FIC_UMMA_KIND_AUTO)]
         if not rgb and wk == dpw == dph:
-            engines.append(fic.FIC_ENGINE_UMMA)
-        for eng in engines:
+            engines += [(fic.FIC_ENGINE_UMMA, fic.FIC_UMMA_KIND_I8), (fic.FIC_ENGINE_UMMA, fic.FIC_UMMA_KIND_F16)]
+        for eng, mma in engines:
             handle.set_engine(eng)
+            handle.set_umma_kind(mma)
             try:
                 info, q = handle.encode(img, B, wk, rgb=rgb)
             finally:
                 handle.set_engine(fic.FIC_ENGINE_AUTO)
+                handle.set_umma_kind(fic.FIC_UMMA_KIND_AUTO)
+            eng = (eng, mma)
             assert float_bits_equal(info, oinfo), (W, H, B, wk, rgb, kind, eng)
             assert (q == q_from_stream(ostream, 5 if rgb else 3)).all(), (W, H, B, wk, rgb, kind, eng)
         # decoder on the same stream

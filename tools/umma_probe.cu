@@ -1,12 +1,16 @@
 // umma_probe -- development probe for the tcgen05 fused search (not part of the product).
 //
-//   umma_probe <mode> <B> <W> [variant] [pattern]
+//   umma_probe <mode> <B> <W> [variant] [pattern] [dbg] [kind]
 //     mode   check : dump every accumulator (kov) and compare with a CPU integer dot
 //                    product, then compare winners with the direct CUDA-core search
 //            time  : no dump; time the fused search and the direct search, compare winners
+//            peak  : bare tcgen05.mma loops (B, W ignored): tensor-pipe rate by kind and MMA shape
 //     B      4 | 8       W = H, multiple of B
 //     variant 0 = descriptor strides as designed (LBO 128, SBO KS*256), 1 = swapped
-//     pattern 0 = noise, 1 = structured, 2 = flat + sparse dots (tie-heavy)
+//     pattern 0 = noise, 1 = structured, 2 = flat + sparse dots (tie-heavy), 3 = binary 0/255 noise,
+//             4 = binary 0/255 in 4x4 pixel cells (the largest |kov| the operands can produce)
+//     dbg     1 = no scoring math, 3 = no TMEM loads either (timing floors)
+//     kind    0 = auto, 1 = kind::i8, 2 = kind::f16
 //
 // Runs each experiment in its own process so that a faulting variant cannot poison the
 // next one; every mbarrier wait in the kernel is bounded (trap + status code).
@@ -59,8 +63,13 @@ static void make_image(std::vector<uint8_t> &img, int W, int H, int pattern, uin
             else if (pattern == 1) {
                 v = (tri(x + (int)seed, 97) + tri(3 * y + x, 211) + tri((x * y) / 64, 151)) / 3 + (int)((h >> 28)) - 8;
                 v = v < 0 ? 0 : (v > 255 ? 255 : v);
-            } else {
+            } else if (pattern == 2) {
                 v = 100 + ((h & 0xff) == 0 ? (int)((h >> 8) & 3) + 1 : 0);
+            } else if (pattern == 3) {
+                v = (h >> 31) ? 255 : 0;
+            } else {
+                uint32_t hc = lowbias32((uint32_t)((y / 4) * W + (x / 4)) + seed * 0x9E3779B9u);
+                v = (hc >> 31) ? 255 : 0;
             }
             img[(size_t)y * W + x] = (uint8_t)v;
         }
@@ -72,18 +81,32 @@ int main(int argc, char **argv)
         printf("usage: umma_probe check|time B W [variant] [pattern]\n");
         return 2;
     }
+    if (!strcmp(argv[1], "peak")) {  // bare MMA loops: rate by kind and shape
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, 0));
+        cudaStream_t s;
+        CK(cudaStreamCreate(&s));
+        for (int f16 = 0; f16 < 2; f16++)
+            for (int n = 128; n <= 256; n += 128) {
+                const char *err = "";
+                double t = measure_mma_peak(prop.multiProcessorCount, s, 3, f16, n, &err);
+                printf("peak kind::%s M=128 N=%d: %.1f TOP/s %s\n", f16 ? "f16" : "i8", n, t, t < 0 ? err : "");
+            }
+        return 0;
+    }
     bool check = !strcmp(argv[1], "check");
     int B = atoi(argv[2]), W = atoi(argv[3]);
     int variant = argc > 4 ? atoi(argv[4]) : 0;
     int pattern = argc > 5 ? atoi(argv[5]) : 0;
     uint32_t dbg = argc > 6 ? (uint32_t)atoi(argv[6]) : 0;  // 1: no scoring math, 3: no TMEM loads either, 4: no slow path
+    int kind = argc > 7 ? atoi(argv[7]) : 0;
     int H = W;
     Geom g;
     const char *why = "";
     int wk = 2 * (W / B) - 3;
     if (make_geom(W, H, B, wk, 0, &g, &why)) { printf("bad geometry: %s\n", why); return 2; }
     if (!umma_applicable(g)) { printf("umma not applicable\n"); return 2; }
-    printf("probe mode=%s B=%d W=%d variant=%d pattern=%d NR=%lld ND=%lld\n", argv[1], B, W, variant, pattern,
+    printf("probe mode=%s B=%d W=%d variant=%d pattern=%d kind=%d NR=%lld ND=%lld\n", argv[1], B, W, variant, pattern, kind,
            (long long)g.NR, (long long)g.ND);
 
     cudaDeviceProp prop;
@@ -104,8 +127,8 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&w.dsq, 4 * g.ND));
     CK(cudaMalloc(&w.rsum, 4 * g.NR));
     CK(cudaMalloc(&w.best, 4 * g.NR));
-    CK(cudaMalloc(&w.opA, umma_opA_bytes(g, 0, g.NR, prop.multiProcessorCount)));
-    CK(cudaMalloc(&w.opB, umma_opB_bytes(g)));
+    CK(cudaMalloc(&w.opA, umma_opA_bytes(g, 0, g.NR, prop.multiProcessorCount, kind)));
+    CK(cudaMalloc(&w.opB, umma_opB_bytes(g, kind)));
     CK(cudaMemcpy(w.src, img.data(), (size_t)W * H, cudaMemcpyHostToDevice));
     cudaStream_t s;
     CK(cudaStreamCreate(&s));
@@ -144,7 +167,7 @@ int main(int argc, char **argv)
         cudaEvent_t k0, k1;
         CK(cudaEventCreate(&k0));
         CK(cudaEventCreate(&k1));
-        int n = launch_search_umma_debug(w, g, 0, g.NR, prop.multiProcessorCount, s, &err, dump, dump_ld, status_d, variant, dbg, k0, k1);
+        int n = launch_search_umma_debug(w, g, 0, g.NR, prop.multiProcessorCount, s, &err, kind, dump, dump_ld, status_d, variant, dbg, k0, k1);
         if (n < 0) { printf("launch failed: %s\n", err); return 3; }
         CK(cudaEventRecord(e1, s));
         CK(cudaStreamSynchronize(s));
@@ -155,9 +178,9 @@ int main(int argc, char **argv)
     }
     CK(cudaMemcpy(best_umma.data(), w.best, 4 * g.NR, cudaMemcpyDeviceToHost));
     double evals = (double)g.NR * (double)g.ND;
-    printf("direct search: %.3f ms (%.3e evals/s)   umma: %.3f ms (%.3e evals/s, %.1f%% of 4.5 POPS int8 at 2*B*B ops/eval)\n",
+    printf("direct search: %.3f ms (%.3e evals/s)   umma: %.3f ms (%.3e evals/s, %.1f%% of 4.5 POPS int8 / %.1f%% of 2.25 PFLOPS f16 at 2*B*B ops/eval)\n",
            ms_direct, evals / (ms_direct * 1e-3), ms_umma, evals / (ms_umma * 1e-3),
-           100.0 * evals * 2 * g.n / (ms_umma * 1e-3) / 4.5e15);
+           100.0 * evals * 2 * g.n / (ms_umma * 1e-3) / 4.5e15, 100.0 * evals * 2 * g.n / (ms_umma * 1e-3) / 2.25e15);
 
     int rc = 0;
     if (check) {
@@ -168,7 +191,7 @@ int main(int argc, char **argv)
         long long bad = 0, shown = 0;
         const int32_t *d_pos_dom;
         int64_t npos;
-        umma_debug_positions(w, g, g.NR, prop.multiProcessorCount, &d_pos_dom, &npos);
+        umma_debug_positions(w, g, g.NR, prop.multiProcessorCount, kind, &d_pos_dom, &npos);
         std::vector<int32_t> pos_dom(npos);
         CK(cudaMemcpy(pos_dom.data(), d_pos_dom, npos * 4, cudaMemcpyDeviceToHost));
         std::vector<int64_t> pos_of(g.ND, -1);
