@@ -150,6 +150,15 @@ struct Lay {
                                       kRowsPerSB * 4 /*per-row lower bound shared by the two column halves*/;
 };
 
+// Flag threshold from the best lower bound lb of the row's max x = |kov| / sqrt(varD): candidates with
+// x^2 <= lb^2 * (1 - 2^-19) - vR^2 * 2^-21 cannot reach the minimal float error.  A non-positive right-hand
+// side means even x = 0 (kov == 0, flat domains) may tie with the best -> -1: everything is a candidate.
+__device__ __forceinline__ float flag_threshold(float lb, float tie_abs)
+{
+    const float rad = lb * lb * kOneMinusEps - tie_abs;
+    return rad > 0.0f ? sqrtf(rad) : -1.0f;
+}
+
 // ---------------------------------------------------------------- sweep order --------
 
 // Sweep chunk P (32 positions) holds sorted chunk (P * mult) mod nch (mult coprime to nch).
@@ -175,6 +184,14 @@ __global__ void k_umma_sortkeys(const int32_t *__restrict__ dsum, const int32_t 
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
 {
     return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+}
+
+// Raw domain pixels for the refine step: per 32-position chunk, 16-byte piece c of position p sits at
+// [chunk][c][p % 32], so a warp that evaluates one chunk reads 512 contiguous bytes per load.
+template <int n>
+__host__ __device__ __forceinline__ int64_t raw_offset(int64_t pos, int c)
+{
+    return (pos >> 5) * (32 * n) + c * 512 + (pos & 31) * 16;
 }
 
 // Two integers in [-255, 255] as a packed pair of binary16 (exact: |v| < 2048).
@@ -235,7 +252,7 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
                     dv[w * 4 + e] = d - dmean;
                 }
             }
-            *(uint4 *)(pos_raw + pos * n + c * 16) = make_uint4(raw[0], raw[1], raw[2], raw[3]);
+            *(uint4 *)(pos_raw + raw_offset<n>(pos, c)) = make_uint4(raw[0], raw[1], raw[2], raw[3]);
             if (F16) {
                 *(uint4 *)(rowp + (2 * c) * 128) =
                     make_uint4(pack_h2(dv[0], dv[1]), pack_h2(dv[2], dv[3]), pack_h2(dv[4], dv[5]), pack_h2(dv[6], dv[7]));
@@ -449,6 +466,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_max_shared_u32(uint32_t saddr, uint32_t v)
+{
+    asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr)
 {
@@ -623,13 +654,13 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             float thresh[2], lbmax[2], tie_abs[2];
             int cnt[2];
             int32_t *my_list[2];
-            uint32_t *sh_lb[2];
+            uint32_t sh_lb[2];  // shared-space address of the row's lower bound (shared by the two column halves)
             // the previous unit's bounds are dead once all 16 epilogue warps are here; reset them
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 #pragma unroll
             for (int sl = 0; sl < 2; sl++) {
-                sh_lb[sl] = s_lb + (qa + 2 * sl) * kBlockM + lq * 32 + lane;
-                if (half == 0) *sh_lb[sl] = 0u;
+                sh_lb[sl] = smem_u32(s_lb + (qa + 2 * sl) * kBlockM + lq * 32 + lane);
+                if (half == 0) sts_u32(sh_lb[sl], 0u);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 #pragma unroll
@@ -653,10 +684,10 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
                     tc_fence_after();
                     {   // adopt a better lower bound found by the warp that scans the other column half
-                        const float other = __uint_as_float(*(volatile uint32_t *)sh_lb[sl]);
+                        const float other = __uint_as_float(lds_volatile_u32(sh_lb[sl]));
                         if (other > lbmax[sl]) {
                             lbmax[sl] = other;
-                            thresh[sl] = sqrtf(fmaxf(other * other * kOneMinusEps - tie_abs[sl], 0.0f));
+                            thresh[sl] = flag_threshold(other, tie_abs[sl]);
                         }
                     }
 #pragma unroll
@@ -714,8 +745,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                             const float lb = M * (cc ? bnd.w : bnd.y);
                             if (lb > lbmax[sl]) {
                                 lbmax[sl] = lb;
-                                atomicMax(sh_lb[sl], __float_as_uint(lb));  // positive floats order like their bits
-                                thresh[sl] = sqrtf(fmaxf(lb * lb * kOneMinusEps - tie_abs[sl], 0.0f));
+                                red_max_shared_u32(sh_lb[sl], __float_as_uint(lb));  // positive floats order like their bits
+                                thresh[sl] = flag_threshold(lb, tie_abs[sl]);
                             }
                         }
                     }
@@ -804,34 +835,34 @@ __global__ void __launch_bounds__(128, 1) k_mma_peak(int iters, uint32_t seed)
 
 // ---------------------------------------------------------------- refine --------------
 
-// Exact score of the candidate at sweep position `pos` for one range row, from the raw domain
-// pixels packed per sweep position (64 contiguous bytes at B = 8; a warp reads one 32-candidate
-// chunk as one contiguous block):
+// Exact integer covariance of the candidate at sweep position `pos` with one range row, from the raw
+// domain pixels (see raw_offset):
 //     kov = sum (r - rmean)(d - dmean) = sum r*d - rmean * dsum - dmean * vR      (exact in s32)
-// then the reference's own expression (FC:677-683).  rw[] = the range block as packed u8 words.
+// rw[] = the range block as packed u8 words.
 template <int B>
-__device__ __forceinline__ float refine_eval_raw(const uint32_t *rw, int rmean, int vR, const uint8_t *__restrict__ pos_raw,
-                                                 int64_t pos, int dsum, int varD)
+__device__ __forceinline__ int refine_kov(const uint32_t *rw, int rmean, int vR, const uint8_t *__restrict__ pos_raw,
+                                          int64_t pos, int dsum)
 {
     constexpr int n = B * B;
-    const uint4 *dp = (const uint4 *)(pos_raw + pos * n);
     int kov = 0;
 #pragma unroll
     for (int c = 0; c < n / 16; c++) {
-        const uint4 d = __ldg(dp + c);
+        const uint4 d = __ldg((const uint4 *)(pos_raw + raw_offset<n>(pos, c)));
         kov = dp4a_uu(rw[4 * c + 0], d.x, kov);
         kov = dp4a_uu(rw[4 * c + 1], d.y, kov);
         kov = dp4a_uu(rw[4 * c + 2], d.z, kov);
         kov = dp4a_uu(rw[4 * c + 3], d.w, kov);
     }
-    kov -= rmean * dsum + (dsum / n) * vR;
-    return grey_error(kov, vR, __dsqrt_rn((double)varD));
+    return kov - (rmean * dsum + (dsum / n) * vR);
 }
 
 // One warp per range row, lane = candidate within a flagged chunk.  The winner is the
 // lexicographic (error, index) minimum over every candidate of every flagged chunk plus domain
 // 0 (which wins when the whole row ties, e.g. all scores 0) = the reference's first index with
 // the smallest error.  A row whose flag list overflowed is rescanned in full -- slow, exact.
+// Each lane runs the search kernel's filter once more on its own candidates (x bounded from the exact
+// integer kov and a correctly rounded binary32 1/sqrt(varD)), so the reference's double-precision
+// expression (FC:677-683) is only evaluated for candidates that can still win or tie.
 template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ pos_raw,
@@ -861,11 +892,21 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
     }
     float be = 10000000.0f;  // FC:615
     int bi = 0x7fffffff;
+    const float tie_abs = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
+    float lb = 0.0f, th = -1.0f;  // lane-local lower bound of the row's max x and the flag threshold from it
     auto consider = [&](int64_t pos) {
         const int idx = pos_dom[pos];
         if (idx >= 0) {
-            const float err = refine_eval_raw<B>(rw, rmean, vR, pos_raw, pos, pos_sum[pos], pos_var[pos]);
-            if (err < be || (err == be && idx < bi)) { be = err; bi = idx; }
+            const int varD = pos_var[pos];
+            const int kov = refine_kov<B>(rw, rmean, vR, pos_raw, pos, pos_sum[pos]);
+            // x = |kov| / sqrt(varD) within (1 +- 2^-22): |kov| and varD < 2^24 are exact in binary32
+            const float ax = varD > 0 ? fabsf((float)kov) * __frsqrt_rn((float)varD) : 0.0f;
+            if (ax * (1.0f + 2.384185791015625e-07f) > th) {
+                const float err = grey_error(kov, vR, __dsqrt_rn((double)varD));
+                if (err < be || (err == be && idx < bi)) { be = err; bi = idx; }
+                const float xlo = ax * (1.0f - 2.384185791015625e-07f);
+                if (xlo > lb) { lb = xlo; th = flag_threshold(lb, tie_abs); }
+            }
         }
     };
     if (lane == 0) consider(*dom0_pos);

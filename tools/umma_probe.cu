@@ -75,8 +75,77 @@ static void make_image(std::vector<uint8_t> &img, int W, int H, int pattern, uin
         }
 }
 
+// ---- TMEM read-bandwidth microbenchmark ("ldtm" mode) -----------------------------------------
+// `nw` warps per SM sub-partition issue `iters` tcgen05.ld.32x32b.x32 (4 KB each) back to back, waiting
+// for every `batch`-th load.  Reports clocks per load per sub-partition.
+__global__ void __launch_bounds__(512, 1) k_ldtm_bw(int iters, int batch, long long *clk_out)
+{
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(&slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t acc = 0;
+    __syncthreads();
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+        uint32_t v[32];
+        const uint32_t a = base + (uint32_t)(((i + (warp >> 2)) & 15) * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(a)
+            : "memory");
+        if ((i % batch) == batch - 1) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            acc ^= v[0] ^ v[31];
+        }
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    long long t1 = clock64();
+    if (lane == 0) clk_out[blockIdx.x * 16 + warp] = (t1 - t0) + (acc == 0x12345u ? 1 : 0);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(slot), "r"(512u) : "memory");
+}
+
+static int run_ldtm()
+{
+    long long *d;
+    if (cudaMalloc(&d, 148 * 16 * 8) != cudaSuccess) return 3;
+    const int iters = 20000;
+    for (int nw = 1; nw <= 4; nw *= 2)
+        for (int batch = 1; batch <= 2; batch++) {
+            cudaMemset(d, 0, 148 * 16 * 8);
+            k_ldtm_bw<<<8, nw * 128>>>(iters, batch, d);
+            if (cudaDeviceSynchronize() != cudaSuccess) { printf("ldtm kernel failed\n"); return 3; }
+            long long h[16];
+            cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+            long long mx = 0;
+            for (int w = 0; w < nw * 4; w++) mx = h[w] > mx ? h[w] : mx;
+            const double clk_per_ld = (double)mx / iters / nw;  // per sub-partition: nw warps share it
+            printf("ldtm: %d warp(s)/sub-partition, wait every %d load(s): %.1f clk per 4 KB load per sub-partition -> %.1f B/clk/SMSP\n",
+                   nw, batch, clk_per_ld, 4096.0 / clk_per_ld);
+        }
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
+    if (argc > 1 && !strcmp(argv[1], "ldtm")) return run_ldtm();
     if (argc < 4) {
         printf("usage: umma_probe check|time B W [variant] [pattern]\n");
         return 2;
