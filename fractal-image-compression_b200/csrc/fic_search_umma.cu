@@ -514,7 +514,8 @@ constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(
 
 // ---------------------------------------------------------------- the search kernel --
 
-// DBG (probe builds only): 1 = skip the scoring, 3 = skip the TMEM loads too.  DUMP: write every
+// DBG (probe builds only): 1 = skip the scoring, 3 = skip the TMEM loads too, 4 = issue the MMAs of the first tile
+// of a unit only (the epilogue alone), 8 = count the cycles an epilogue warp spends in each phase (into `dump`).  DUMP: write every
 // accumulator to `dump` (the probe's exactness check).  The product runs <B, 0, false>.
 template <int B, bool F16, int DBG, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -617,6 +618,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     if (elected) {
 #pragma unroll
                         for (int s = 0; s < C::NS; s++) {
+                            if ((DBG & 4) && t != t0) continue;        // probe only: epilogue without the tensor pipe
                             if (C::is_l_slice(s) && !has_l) continue;  // sum r*l == 0 for the whole tile
                             const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + C::amap(s) * 256) >> 4);
                             const uint64_t bd = b_desc + (uint64_t)((s * 256) >> 4);
@@ -645,6 +647,17 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         const int half = kk & 1, qa = kk >> 1;
         const uint32_t t_lane0 = tmem_base + ((uint32_t)(lq * 32) << 16) + half * 64;
         uint32_t stage = 0, phase = 0, tf_phase = 0;
+        // DBG & 8 (probe only): per-warp cycle accounting of the epilogue phases.  tcgen05.wait::ld is a
+        // scoreboard wait, so the TMEM latency shows up at the first use of the loaded registers ("math").
+        uint32_t tk_b = 0, tk_t = 0, tk_l = 0, tk_m = 0, tk_mark = 0;
+        const uint32_t tk_begin = (DBG & 8) ? (uint32_t)clock() : 0u;
+        auto tick = [&](uint32_t &acc) {
+            if (DBG & 8) {
+                const uint32_t now = (uint32_t)clock();
+                acc += now - tk_mark;
+                tk_mark = now;
+            }
+        };
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             int sb = u / n_chunks, ch = u % n_chunks;
             int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
@@ -673,16 +686,25 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 cnt[sl] = 0;
                 my_list[sl] = flag_list + (((int64_t)ch * rows_padded + row[sl]) * 2 + half) * kFlagCap;
             }
+            if (DBG & 8) tk_mark = (uint32_t)clock();
             for (int t = t0; t < t1; t++) {
                 mbar_wait(BAR_B_FULL(stage), phase, status, 6);
                 // (rhi, rlo) of this warp's two chunks of the tile
                 const float4 bnd = lds_f4(smem_u32(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES) + half * 16);
+                tick(tk_b);
 #pragma unroll
                 for (int sl = 0; sl < 2; sl++) {
                     const int q = qa + 2 * sl;
                     const uint32_t ta = t_lane0 + q * kTileN;
                     mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
                     tc_fence_after();
+                    if (sl == 1) {
+                        // Every MMA that reads this tile's shared-memory stage has completed (all 16 warps pass
+                        // here, half of them after the tile's last commit) and its bounds are in registers:
+                        // release the stage now, not at the end of the tile, so the next TMA starts earlier.
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR_B_EMPTY(stage));
+                    }
                     {   // adopt a better lower bound found by the warp that scans the other column half
                         const float other = __uint_as_float(lds_volatile_u32(sh_lb[sl]));
                         if (other > lbmax[sl]) {
@@ -690,6 +712,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                             thresh[sl] = flag_threshold(other, tie_abs[sl]);
                         }
                     }
+                    tick(tk_t);
 #pragma unroll
                     for (int cc = 0; cc < 2; cc++) {
                         uint32_t v[32];
@@ -697,6 +720,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                             tmem_ld32(ta + cc * 32, v);
                             tmem_ld_wait();
                         }
+                        tick(tk_l);
                         if (cc == 1) {
                             // last read of this half of accumulator q for this tile: hand it back
                             tc_fence_before();
@@ -706,16 +730,19 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                         if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring
                         float M;  // max |kov| over the chunk, exact
                         if (F16) {
-                            // binary32 accumulators holding exact integers: FMNMX3 |a|, |b|, c takes two per op
-                            float m0 = 0.0f, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+                            // binary32 accumulators holding exact integers.  FMNMX3 takes |.| on all three
+                            // operands: a 3-input tree over 32 values is 16 instructions (four chains of 3, then 4).
+                            auto av = [&](int k) { return fabsf(__uint_as_float(v[k])); };
+                            float c4[4];
 #pragma unroll
-                            for (int k = 0; k < 32; k += 8) {
-                                m0 = fmaxf(m0, fmaxf(fabsf(__uint_as_float(v[k])), fabsf(__uint_as_float(v[k + 1]))));
-                                m1 = fmaxf(m1, fmaxf(fabsf(__uint_as_float(v[k + 2])), fabsf(__uint_as_float(v[k + 3]))));
-                                m2 = fmaxf(m2, fmaxf(fabsf(__uint_as_float(v[k + 4])), fabsf(__uint_as_float(v[k + 5]))));
-                                m3 = fmaxf(m3, fmaxf(fabsf(__uint_as_float(v[k + 6])), fabsf(__uint_as_float(v[k + 7]))));
+                            for (int i = 0; i < 4; i++) {
+                                c4[i] = fmaxf(fmaxf(av(8 * i), av(8 * i + 1)), av(8 * i + 2));
+                                c4[i] = fmaxf(c4[i], fmaxf(av(8 * i + 3), av(8 * i + 4)));
+                                c4[i] = fmaxf(c4[i], fmaxf(av(8 * i + 5), av(8 * i + 6)));
                             }
-                            M = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                            const float m01 = fmaxf(fmaxf(c4[0], c4[1]), av(7));
+                            const float m23 = fmaxf(fmaxf(c4[2], c4[3]), av(15));
+                            M = fmaxf(fmaxf(fmaxf(m01, m23), av(23)), av(31));
                         } else {
                             int mx0 = 0, mn0 = 0, mx1 = 0, mn1 = 0;  // two independent chains each: ALU latency
 #pragma unroll
@@ -749,16 +776,22 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                                 thresh[sl] = flag_threshold(lb, tie_abs[sl]);
                             }
                         }
+                        tick(tk_m);
                     }
                 }
-                // the tile's bounds are consumed
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR_B_EMPTY(stage));
                 tf_phase ^= 1;
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
 #pragma unroll
             for (int sl = 0; sl < 2; sl++) flag_cnt[((int64_t)ch * rows_padded + row[sl]) * 2 + half] = cnt[sl];
+        }
+        if ((DBG & 8) && lane == 0 && dump) {
+            int32_t *o = dump + ((int64_t)blockIdx.x * kEpiWarps + e) * 8;
+            o[0] = (int32_t)((uint32_t)clock() - tk_begin);
+            o[1] = (int32_t)tk_b;
+            o[2] = (int32_t)tk_t;
+            o[3] = (int32_t)tk_l;
+            o[4] = (int32_t)tk_m;
         }
     }
 
@@ -1048,9 +1081,12 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int32_t *, int32_t *, int, int, int,
                              int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
     KernelT kern = k_umma_search<B, F16, 0, false>;  // dbg (probe only): 1 / 3 strip the scoring / the TMEM loads too
-    if (dump) kern = k_umma_search<B, F16, 0, true>;
+    if (dump && !(dbg & 8u)) kern = k_umma_search<B, F16, 0, true>;
     else if ((dbg & 3u) == 1) kern = k_umma_search<B, F16, 1, false>;
     else if ((dbg & 3u) == 3) kern = k_umma_search<B, F16, 3, false>;
+    else if (dbg == 4) kern = k_umma_search<B, F16, 4, false>;
+    else if (dbg == 8) { kern = k_umma_search<B, F16, 8, false>; dump = w.best; }    // phase cycle counts -> w.best
+    else if (dbg == 12) { kern = k_umma_search<B, F16, 12, false>; dump = w.best; }
     ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
     int n_units = p.n_sb * p.n_chunks;
@@ -1062,7 +1098,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
                                                dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
     if (k1) cudaEventRecord(k1, s);
     // 4. exact refine of the flagged chunks
-    k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_dom, pos_var, pos_sum, flag_list,
+    if (!(dbg & 8u)) k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_dom, pos_var, pos_sum, flag_list,
                                                                 flag_cnt, p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
     launches += 2;
     ce = cudaGetLastError();

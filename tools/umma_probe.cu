@@ -122,6 +122,108 @@ __global__ void __launch_bounds__(512, 1) k_ldtm_bw(int iters, int batch, long l
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(slot), "r"(512u) : "memory");
 }
 
+// ---- ALU-pipe issue-rate microbenchmark ("alu" mode) -------------------------------------------
+// 8 independent chains per thread so that latency never limits; OP selects the instruction.
+// One dependent chain per thread: clocks per instruction = the instruction's dependent-issue latency.
+template <int OP>
+__global__ void __launch_bounds__(32, 1) k_alu_latency(int iters, const float *in, float *out, long long *clk_out)
+{
+    float f = in[threadIdx.x];
+    int v = __float_as_int(f);
+    const float x = in[5], y = in[6];
+    const int xi = __float_as_int(x), yi = __float_as_int(y);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 64; r++) {
+            if (OP == 0) f = fmaxf(f, fmaxf(fabsf(x), fabsf(y)));
+            else if (OP == 1) f = fmaxf(f, fabsf(x));
+            else if (OP == 2) v = max(v, max(xi, yi));
+            else if (OP == 3) f = f + x;
+            else v = max(v, xi);
+            asm volatile("" : "+f"(f), "+r"(v));
+        }
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = f + (float)v;
+    if (threadIdx.x == 0) clk_out[0] = t1 - t0;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(512, 1) k_alu_rate(int iters, const float *in, float *out, long long *clk_out)
+{
+    float f[8];
+    int v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { f[i] = in[threadIdx.x + 32 * i]; v[i] = __float_as_int(f[i]); }
+    const float x = in[5], y = in[6];
+    const int xi = __float_as_int(x), yi = __float_as_int(y);
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (OP == 0) f[i] = fmaxf(f[i], fmaxf(fabsf(x), fabsf(y)));        // FMNMX3 |a|,|b|,c
+                else if (OP == 1) f[i] = fmaxf(f[i], fabsf(x));                        // FMNMX
+                else if (OP == 2) v[i] = max(v[i], max(xi, yi));                       // VIMNMX3
+                else if (OP == 3) f[i] = f[i] + x;                                     // FADD (FMA pipe)
+                else v[i] = max(v[i], xi);                                             // VIMNMX (2-input)
+            }
+            // keep the compiler from collapsing the chains
+            asm volatile("" : "+f"(f[0]), "+f"(f[1]), "+f"(f[2]), "+f"(f[3]), "+f"(f[4]), "+f"(f[5]), "+f"(f[6]), "+f"(f[7]));
+            asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]));
+        }
+    }
+    long long t1 = clock64();
+    float acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc += f[i] + (float)v[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if ((threadIdx.x & 31) == 0) clk_out[blockIdx.x * 16 + (threadIdx.x >> 5)] = t1 - t0;
+}
+
+static int run_alu()
+{
+    float *in, *out;
+    long long *d;
+    cudaMalloc(&in, 4096 * 4);
+    cudaMalloc(&out, 148 * 512 * 4);
+    cudaMalloc(&d, 148 * 16 * 8);
+    std::vector<float> h(4096);
+    for (int i = 0; i < 4096; i++) h[i] = (float)(i % 97) - 40.0f;
+    cudaMemcpy(in, h.data(), 4096 * 4, cudaMemcpyHostToDevice);
+    const int iters = 2000;
+    const char *names[5] = {"FMNMX3 |a|,|b|,c", "FMNMX |a|,b", "VIMNMX3", "FADD", "VIMNMX"};
+    for (int op = 0; op < 5; op++) {
+        if (op == 0) k_alu_latency<0><<<1, 32>>>(iters, in, out, d);
+        else if (op == 1) k_alu_latency<1><<<1, 32>>>(iters, in, out, d);
+        else if (op == 2) k_alu_latency<2><<<1, 32>>>(iters, in, out, d);
+        else if (op == 3) k_alu_latency<3><<<1, 32>>>(iters, in, out, d);
+        else k_alu_latency<4><<<1, 32>>>(iters, in, out, d);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("alu latency kernel failed\n"); return 3; }
+        long long lc = 0;
+        cudaMemcpy(&lc, d, 8, cudaMemcpyDeviceToHost);
+        printf("alu: %-18s dependent chain: %.2f clk per instruction\n", names[op], (double)lc / ((double)iters * 64.0));
+        for (int nw = 1; nw <= 4; nw *= 2) {
+            if (op == 0) k_alu_rate<0><<<8, nw * 128>>>(iters, in, out, d);
+            else if (op == 1) k_alu_rate<1><<<8, nw * 128>>>(iters, in, out, d);
+            else if (op == 2) k_alu_rate<2><<<8, nw * 128>>>(iters, in, out, d);
+            else if (op == 3) k_alu_rate<3><<<8, nw * 128>>>(iters, in, out, d);
+            else k_alu_rate<4><<<8, nw * 128>>>(iters, in, out, d);
+            if (cudaDeviceSynchronize() != cudaSuccess) { printf("alu kernel failed\n"); return 3; }
+            long long hc[16];
+            cudaMemcpy(hc, d, sizeof hc, cudaMemcpyDeviceToHost);
+            long long mx = 0;
+            for (int w = 0; w < nw * 4; w++) mx = hc[w] > mx ? hc[w] : mx;
+            printf("alu: %-18s %d warp(s)/sub-partition: %.2f clk per warp-instruction per sub-partition\n", names[op], nw,
+                   (double)mx / ((double)iters * 64.0 * nw));
+        }
+    }
+    return 0;
+}
+
 static int run_ldtm()
 {
     long long *d;
@@ -146,6 +248,7 @@ static int run_ldtm()
 int main(int argc, char **argv)
 {
     if (argc > 1 && !strcmp(argv[1], "ldtm")) return run_ldtm();
+    if (argc > 1 && !strcmp(argv[1], "alu")) return run_alu();
     if (argc < 4) {
         printf("usage: umma_probe check|time B W [variant] [pattern]\n");
         return 2;
@@ -300,7 +403,15 @@ int main(int argc, char **argv)
         printf("accumulator check: %lld mismatches of %lld\n", bad, (long long)(g.NR * g.ND));
         if (bad) rc = 1;
     }
-    if (dbg & 3u) { printf("dbg run: winners not checked\nPROBE DONE\n"); return 0; }
+    if (dbg & 8u) {  // per-warp cycle accounting written by the kernel into w.best
+        for (int cta = 0; cta < 2; cta++)
+            for (int e = 0; e < 16; e++) {
+                const int32_t *o = &best_umma[(size_t)(cta * 16 + e) * 8];
+                printf("cta %d epilogue warp %2d: total %9d clk  wait B_FULL %5.1f%%  wait T_FULL %5.1f%%  LDTM %5.1f%%  math %5.1f%%\n", cta, e,
+                       o[0], 100.0 * o[1] / o[0], 100.0 * o[2] / o[0], 100.0 * o[3] / o[0], 100.0 * o[4] / o[0]);
+            }
+    }
+    if (dbg & 15u) { printf("dbg run: winners not checked\nPROBE DONE\n"); return 0; }
     long long diff = 0, shown = 0;
     for (int64_t i = 0; i < g.NR; i++)
         if (best_direct[i] != best_umma[i]) {
