@@ -224,6 +224,100 @@ static int run_alu()
     return 0;
 }
 
+// ---- does a tcgen05.ld in flight block the sub-partition's issue port? ("mix" mode) --------------
+// Per sub-partition: `nl` warps loop over tcgen05.ld.x32 (+ wait), `na` warps loop over independent FMNMX3.
+__global__ void __launch_bounds__(1024, 1) k_mix(int iters, int nl, int na, const float *in, float *out, long long *clk_out)
+{
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(&slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int idx = warp >> 2;  // index of the warp within its sub-partition
+    const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16);
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) f[i] = in[threadIdx.x % 64 + 32 * i];
+    const float x = in[5], y = in[6];
+    uint32_t acc = 0;
+    __syncthreads();
+    long long t0 = clock64();
+    if (idx < nl) {
+        for (int i = 0; i < iters; i++) {
+            uint32_t v[32];
+            const uint32_t a = base + (uint32_t)(((i + idx) & 15) * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(a)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            acc ^= v[0] ^ v[31];
+        }
+    } else if (idx < nl + na) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) f[i] = fmaxf(f[i], fmaxf(fabsf(x), fabsf(y)));
+                asm volatile("" : "+f"(f[0]), "+f"(f[1]), "+f"(f[2]), "+f"(f[3]), "+f"(f[4]), "+f"(f[5]), "+f"(f[6]), "+f"(f[7]));
+            }
+        }
+    }
+    long long t1 = clock64();
+    float s = (float)acc;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += f[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (lane == 0) clk_out[blockIdx.x * 32 + warp] = t1 - t0;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(slot), "r"(512u) : "memory");
+}
+
+static int run_mix()
+{
+    float *in, *out;
+    long long *d;
+    cudaMalloc(&in, 4096 * 4);
+    cudaMalloc(&out, 8 * 1024 * 4);
+    cudaMalloc(&d, 8 * 32 * 8);
+    std::vector<float> h(4096);
+    for (int i = 0; i < 4096; i++) h[i] = (float)(i % 97) - 40.0f;
+    cudaMemcpy(in, h.data(), 4096 * 4, cudaMemcpyHostToDevice);
+    const int iters = 20000;
+    const int cfg[6][2] = {{2, 0}, {0, 2}, {2, 2}, {4, 0}, {0, 4}, {4, 4}};
+    for (int c = 0; c < 6; c++) {
+        const int nl = cfg[c][0], na = cfg[c][1];
+        k_mix<<<8, (nl + na) * 128>>>(iters, nl, na, in, out, d);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("mix kernel failed\n"); return 3; }
+        long long hc[32];
+        cudaMemcpy(hc, d, sizeof hc, cudaMemcpyDeviceToHost);
+        long long ml = 0, ma = 0;
+        for (int w = 0; w < (nl + na) * 4; w++) {
+            if ((w >> 2) < nl) ml = hc[w] > ml ? hc[w] : ml;
+            else ma = hc[w] > ma ? hc[w] : ma;
+        }
+        printf("mix: %d load warp(s) + %d FMNMX3 warp(s) per sub-partition:", nl, na);
+        if (nl) printf("  %.1f clk per 4 KB tcgen05.ld per sub-partition", (double)ml / iters / nl);
+        if (na) printf("  %.2f clk per FMNMX3 per sub-partition", (double)ma / ((double)iters * 32.0 * na));
+        printf("\n");
+    }
+    return 0;
+}
+
 static int run_ldtm()
 {
     long long *d;
@@ -249,6 +343,7 @@ int main(int argc, char **argv)
 {
     if (argc > 1 && !strcmp(argv[1], "ldtm")) return run_ldtm();
     if (argc > 1 && !strcmp(argv[1], "alu")) return run_alu();
+    if (argc > 1 && !strcmp(argv[1], "mix")) return run_mix();
     if (argc < 4) {
         printf("usage: umma_probe check|time B W [variant] [pattern]\n");
         return 2;
