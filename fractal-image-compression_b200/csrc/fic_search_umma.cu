@@ -1,7 +1,7 @@
 // fic_search_umma.cu -- K2+K3: the full-pool range x domain search as an exact integer
-// contraction on the 5th-generation tensor cores (tcgen05, kind::i8, accumulators in
-// TMEM), with the scoring / argmin epilogue fused so that no score matrix is ever
-// written to HBM.  sm_100a only.
+// contraction on the 5th-generation tensor cores (tcgen05, accumulators in TMEM), with the
+// scoring / argmin filter fused into the epilogue so that no score matrix is ever written to
+// HBM.  sm_100a only.
 //
 // What is computed.  For range block i and domain block j the reference scores
 //     error = vR^2 * (1 - (kov / (vR * sqrt(varD)))^2)          (FC:677-683)
@@ -13,11 +13,11 @@
 // within a relative 2^-20 (and an absolute 2^-21 in (x/vR)^2, the resolution of 1 - r^2)
 // of the row maximum.  The reference's answer is the lowest index in T.
 //
-//   1. The tensor cores produce kov[i][j] exactly (u8 x s8 -> s32).
+//   1. The tensor cores produce kov[i][j] exactly (two instruction kinds, below).
 //   2. The fused epilogue needs no per-candidate floating point: domains are swept in
 //      order of increasing varD, so every 32-column chunk of an accumulator shares the
-//      scale 1/sqrt(varD) up to a tiny spread [rlo, rhi].  A thread takes the integer
-//      max |kov| of its row over the chunk (VIMNMX3), and with M = max |kov|:
+//      scale 1/sqrt(varD) up to a tiny spread [rlo, rhi].  A thread takes the exact
+//      max |kov| of its row over the chunk, and with M = max |kov|:
 //      M*rhi bounds every x of the chunk from above, M*rlo bounds the row maximum from
 //      below.  A chunk is flagged when M*rhi exceeds the row's threshold
 //      thresh^2 = lb_max^2 * (1 - 2^-19) - vR^2 * 2^-21  (lb_max = running max of M*rlo),
@@ -28,7 +28,13 @@
 // Result: the same winner index as the reference for every row, bit for bit, in any sweep
 // order.
 //
-// How kov becomes one u8 x s8 GEMM.  With dt = d - dmean_j (|dt| <= 254 for B <= 8),
+// kov on the tensor cores, kind::f16 (B = 4, 8).  A row = (r - rmean), B row = (d - dmean), both as
+// binary16: integers of magnitude <= 255 are exact, every product and every partial sum is an integer
+// below n * 127.5^2 = 1.04e6 (Cauchy-Schwarz; n = 64) << 2^24, so the binary32 accumulator holds kov
+// exactly whatever the summation order (the probe dumps and checks every accumulator).  K = n.
+// The epilogue takes max |kov| with FMNMX3 |a|, |b|, |c|: 16 instructions per 32 values.
+//
+// kov on the tensor cores, kind::i8 (B = 16; selectable for B = 4, 8).  With dt = d - dmean_j
 // (B = 16: |dt| <= 255; the single case dt = +255 does not fit and sends the image to the direct
 // search), split dt = h + l, h = clamp(dt, -128, 127), l = dt - h (both fit s8; l is zero unless a
 // pixel is more than 127 grey levels from its block mean, so the MMA issuer skips the l
@@ -36,8 +42,9 @@
 //     kov = sum_k r_k * h_k + sum_k r_k * l_k + rmean_i * (-alpha_j),   alpha_j = sum d - n*dmean_j
 // i.e. A row = [ r | r | rmean rmean 0.. ] (u8) and B row = [ h | l | -alpha/2 -alpha/2 0.. ] (s8), K
 // padded to a multiple of 32 (one kind::i8 MMA consumes K = 32).  The duplicated `r`
-// half of A is not stored twice: the MMA issuer points the A descriptor of K-slices 2,3
-// back at slices 0,1 (B = 8).  The accumulator IS kov; no per-output correction exists.
+// half of A is not stored twice: the MMA issuer points the A descriptor of the `l` K-slices
+// back at the `r` slices.  The s32 accumulator IS kov; max |kov| needs a max and a min chain
+// (32 VIMNMX3 per 32 values), which is why kind::f16 wins where the epilogue is the bottleneck.
 //
 // Data movement.  Operands are packed once per encode by two HBM-bound kernels into
 // "blobs" that are already in the canonical no-swizzle K-major UMMA shared-memory
@@ -55,7 +62,7 @@
 //   warp 0      TMA producer: A super-block (512 range rows, resident for the whole
 //               unit) + a ring of domain tiles (128 domains each)
 //   warp 1      MMA issuer (warp-uniform loop, one elected lane issues): per domain tile
-//               4 accumulators (128 rows x 128 domains s32 = all 512 TMEM columns) x NS
+//               4 accumulators (128 rows x 128 domains = all 512 TMEM columns) x NS
 //               K-slices of tcgen05.mma, tcgen05.commit -> t_full[q]
 //   warp 2      TMEM allocator
 //   warps 4-19  epilogue: warp e owns TMEM lane quarter e % 4 and column half (e / 4) & 1
