@@ -18,10 +18,11 @@ FIC_ENGINE_AUTO, FIC_ENGINE_DIRECT, FIC_ENGINE_UMMA = 0, 1, 2
 FIC_UMMA_KIND_AUTO, FIC_UMMA_KIND_I8, FIC_UMMA_KIND_F16 = 0, 1, 2
 FIC_OPT_ENGINE = 1
 FIC_OPT_UMMA_KIND = 2
+FIC_OPT_F16_EXACT = 3
 
 # every symbol include/fic_b200.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
-    "fic_create", "fic_destroy", "fic_last_error", "fic_version", "fic_set_option", "fic_set_stream",
+    "fic_create", "fic_destroy", "fic_last_error", "fic_version", "fic_set_option", "fic_get_option", "fic_set_stream",
     "fic_get_timings", "fic_geometry", "fic_encode_grey", "fic_encode_rgb", "fic_encode_planes_dev",
     "fic_sync", "fic_decode", "fic_collage", "fic_build_pool", "fic_stream_size", "fic_stream_write",
     "fic_stream_read_header", "fic_stream_read_codes", "fic_measure_int8_peak", "fic_measure_mma_peak",
@@ -64,6 +65,7 @@ def load() -> C.CDLL:
     L.fic_last_error.restype = C.c_char_p
     L.fic_version.restype = C.c_char_p
     L.fic_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.fic_get_option.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
     L.fic_set_stream.argtypes = [vp, vp]
     L.fic_get_timings.argtypes = [vp, C.POINTER(Timings)]
     L.fic_geometry.argtypes = [C.c_int] * 4 + [C.POINTER(i64), C.POINTER(i64)]

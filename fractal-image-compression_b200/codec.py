@@ -101,6 +101,13 @@ class Handle:
         """Tensor-core instruction kind of the tcgen05 search: FIC_UMMA_KIND_AUTO / _I8 / _F16."""
         self._check(self._L.fic_set_option(self._h, _lib.FIC_OPT_UMMA_KIND, int(kind)))
 
+    def f16_exact(self) -> bool:
+        """True if this device's kind::f16 tensor path reproduced the exact integer covariances in the
+        library's self-test (run once per handle); False means the handle runs kind::i8 instead."""
+        v = C.c_int(0)
+        self._check(self._L.fic_get_option(self._h, _lib.FIC_OPT_F16_EXACT, C.byref(v)))
+        return bool(v.value)
+
     def set_stream(self, cuda_stream: int | None):
         """None -> the handle's own stream; an integer cudaStream_t otherwise.  torch reports its default
         stream as 0, which the C ABI reads as "own stream": pass the legacy-default handle instead."""

@@ -51,6 +51,7 @@ struct fic_handle {
     Work w;
     int engine_opt = FIC_ENGINE_AUTO;
     int umma_kind = FIC_UMMA_KIND_AUTO;
+    int f16_state = 0;  // kind::f16 self-test: 0 not run yet, 1 exact, -1 not exact on this device (use kind::i8)
     fic_timings tm;
     char err[512];
     bool tm_pending_dev = false;
@@ -182,6 +183,25 @@ int fic_set_option(fic_handle *h, int option, int value)
     return set_err(h, FIC_E_ARG, "unknown option %d / value %d", option, value);
 }
 
+int fic_get_option(fic_handle *h, int option, int *value)
+{
+    if (!h || !value) return FIC_E_ARG;
+    if (option == FIC_OPT_ENGINE) { *value = h->engine_opt; return FIC_OK; }
+    if (option == FIC_OPT_UMMA_KIND) { *value = h->umma_kind; return FIC_OK; }
+    if (option == FIC_OPT_F16_EXACT) {
+        if (h->f16_state == 0) {
+            CU(cudaSetDevice(h->device));
+            const char *why = nullptr;
+            int ok = umma_f16_selftest(h->num_sms, h->stream, &why);
+            if (ok < 0) return set_err(h, FIC_E_CUDA, "kind::f16 self-test failed to run: %s", why ? why : "?");
+            h->f16_state = ok ? 1 : -1;
+        }
+        *value = h->f16_state > 0;
+        return FIC_OK;
+    }
+    return set_err(h, FIC_E_ARG, "unknown option %d", option);
+}
+
 int fic_set_stream(fic_handle *h, void *cuda_stream)
 {
     if (!h) return FIC_E_ARG;
@@ -248,9 +268,20 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     ENSURE(w.dsq, S_DSQ, sizeof(int32_t) * g.C * g.ND);
     ENSURE(w.rsum, S_RSUM, sizeof(int32_t) * g.C * g.NR);
     ENSURE(w.best, S_BEST, sizeof(int32_t) * g.NR);
+    int kind = h->umma_kind;
     if (engine == FIC_ENGINE_UMMA) {
-        ENSURE(w.opA, S_OPA, umma_opA_bytes(g, j0, j1, h->num_sms, h->umma_kind));
-        ENSURE(w.opB, S_OPB, umma_opB_bytes(g, h->umma_kind));
+        // The first kind::f16 search of a handle verifies, once, that this device's f16 tensor path
+        // accumulates the integer covariances exactly; a device that does not runs kind::i8 instead.
+        const bool wants_f16 = g.B != 16 && (kind == FIC_UMMA_KIND_F16 || (kind == FIC_UMMA_KIND_AUTO && umma_default_kind(g) == FIC_UMMA_KIND_F16));
+        if (wants_f16 && h->f16_state == 0) {
+            const char *why = nullptr;
+            int ok = umma_f16_selftest(h->num_sms, s, &why);
+            if (ok < 0) return set_err(h, FIC_E_CUDA, "kind::f16 self-test failed to run: %s", why ? why : "?");
+            h->f16_state = ok ? 1 : -1;
+        }
+        if (wants_f16 && h->f16_state < 0) kind = FIC_UMMA_KIND_I8;
+        ENSURE(w.opA, S_OPA, umma_opA_bytes(g, j0, j1, h->num_sms, kind));
+        ENSURE(w.opB, S_OPB, umma_opB_bytes(g, kind));
     }
     Work call = w;  // per-call view: the source planes may belong to the caller
     call.src = const_cast<uint8_t *>(d_src);
@@ -262,7 +293,7 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     CU(cudaEventRecord(h->ev[2], s));
     if (engine == FIC_ENGINE_UMMA) {
         const char *why = nullptr;
-        int n = launch_search_umma(call, g, j0, j1, h->num_sms, s, &why, h->umma_kind, h->ev[6], h->ev[7]);
+        int n = launch_search_umma(call, g, j0, j1, h->num_sms, s, &why, kind, h->ev[6], h->ev[7]);
         if (n == -2) {  // B = 16 digit overflow (a 255 pixel in a block of mean 0): exact direct search instead
             engine = FIC_ENGINE_DIRECT;
             CU(cudaEventRecord(h->ev[6], s));

@@ -71,6 +71,8 @@
 #include <cuda_fp16.h>
 #include <cub/device/device_radix_sort.cuh>
 
+#include <vector>
+
 #include "fic_device.cuh"
 
 namespace fic {
@@ -1170,6 +1172,100 @@ double measure_mma_peak(int num_sms, cudaStream_t s, int reps, int f16, int n_co
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return best;
+}
+
+// ---------------------------------------------------------------- kind::f16 self-test -
+
+namespace {
+
+// Integer reference of every accumulator the search kernel dumped: kov[i][pos] = sum (r - rmean)(d - dmean).
+__global__ void k_umma_selftest_check(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec,
+                                      const int32_t *__restrict__ rsum, const int32_t *__restrict__ dsum,
+                                      const int32_t *__restrict__ pos_dom, const int32_t *__restrict__ dump, int64_t dump_ld,
+                                      int64_t npos, Geom g, unsigned int *__restrict__ bad)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.NR * npos) return;
+    const int64_t i = t / npos, pos = t % npos;
+    const int j = pos_dom[pos];
+    if (j < 0) return;
+    const int B = g.B, n = g.n;
+    const int rmean = rsum[i] / n, dmean = dsum[j] / n;
+    const uint8_t *r = src + (int64_t)((i / g.rpw) * B) * g.W + (i % g.rpw) * B;
+    const uint8_t *d = dec + (int64_t)((j / g.dpw) * g.step) * g.sw + (j % g.dpw) * g.step;
+    int kov = 0;
+    for (int k = 0; k < n; k++)
+        kov += ((int)r[(int64_t)(k / B) * g.W + k % B] - rmean) * ((int)d[(int64_t)(k / B) * g.sw + k % B] - dmean);
+    if (dump[i * dump_ld + pos] != kov) atomicAdd(bad, 1u);
+}
+
+}  // namespace
+
+// Runs the kind::f16 search on a 128 x 128 test image that mixes the largest covariances the operands can
+// produce (0 / 255 cells), noise and smooth content, dumps every accumulator and compares it with integer
+// arithmetic.  1: every binary32 accumulator held the exact integer; 0: not (the caller then uses kind::i8);
+// < 0: CUDA error.  The encoder's results never depend on this (the refine step recomputes kov in s32), but a
+// device whose f16 tensor path rounded would flag the wrong chunks.
+int umma_f16_selftest(int num_sms, cudaStream_t s, const char **err)
+{
+    const int W = 128, B = 8;
+    Geom g;
+    if (make_geom(W, W, B, 2 * (W / B) - 3, 0, &g, err)) return -1;
+    std::vector<uint8_t> img((size_t)W * W);
+    for (int y = 0; y < W; y++)
+        for (int x = 0; x < W; x++) {
+            uint32_t hpix = (uint32_t)(y * W + x) * 2654435761u;
+            hpix ^= hpix >> 15; hpix *= 0x2c1b3c6du; hpix ^= hpix >> 12;
+            uint32_t hcell = (uint32_t)((y / 4) * W + x / 4) * 2246822519u;
+            hcell ^= hcell >> 13; hcell *= 0x9e3779b1u; hcell ^= hcell >> 16;
+            int v;
+            if (y < 64 && x < 64) v = (hcell >> 31) ? 255 : 0;          // 0 / 255 in 4x4 cells
+            else if (y < 64) v = (int)(hpix >> 24);                      // noise
+            else if (x < 64) v = (hpix >> 31) ? 255 : 0;                 // 0 / 255 per pixel
+            else v = (3 * x + 2 * y + (int)(hpix >> 29)) & 255;          // ramps
+            img[(size_t)y * W + x] = (uint8_t)v;
+        }
+    Work w;
+    Plan p = make_plan(g, g.NR, num_sms);
+    const int64_t dump_ld = p.npos;
+    int32_t *dump = nullptr;
+    unsigned int *bad = nullptr;
+    cudaError_t ce = cudaSuccess;
+    auto alloc = [&](void **ptr, size_t bytes) { if (ce == cudaSuccess) ce = cudaMalloc(ptr, bytes); };
+    alloc((void **)&w.src, (size_t)W * W);
+    alloc((void **)&w.dec, (size_t)g.sw * g.sh);
+    alloc((void **)&w.dsum, 4 * g.ND);
+    alloc((void **)&w.dsq, 4 * g.ND);
+    alloc((void **)&w.rsum, 4 * g.NR);
+    alloc((void **)&w.best, 4 * g.NR);
+    alloc((void **)&w.opA, opA_bytes_t<8, true>(g, g.NR, num_sms));
+    alloc((void **)&w.opB, OpBLayout<8, true>(g, p).total);
+    alloc((void **)&dump, (size_t)p.rp * dump_ld * 4);
+    alloc((void **)&bad, 4);
+    int result = -1;
+    if (ce == cudaSuccess) {
+        cudaMemcpyAsync(w.src, img.data(), img.size(), cudaMemcpyHostToDevice, s);
+        cudaMemsetAsync(dump, 0x7f, (size_t)p.rp * dump_ld * 4, s);
+        cudaMemsetAsync(bad, 0, 4, s);
+        launch_decimate(w.src, w.dec, g, s);
+        launch_domain_stats(w.dec, w.dsum, w.dsq, g, s);
+        launch_range_stats(w.src, w.rsum, g, s);
+        if (launch_t<8, true>(w, g, 0, g.NR, num_sms, s, err, dump, dump_ld, nullptr, 0) >= 0) {
+            const int64_t total = g.NR * p.npos;
+            k_umma_selftest_check<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+                w.src, w.dec, w.rsum, w.dsum, (const int32_t *)(w.opB + OpBLayout<8, true>(g, p).off_posdom), dump, dump_ld,
+                p.npos, g, bad);
+            unsigned int hbad = 1;
+            ce = cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, s);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+            if (ce == cudaSuccess) result = hbad == 0 ? 1 : 0;
+        }
+    }
+    if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); result = -1; }
+    for (void *ptr : {(void *)w.src, (void *)w.dec, (void *)w.dsum, (void *)w.dsq, (void *)w.rsum, (void *)w.best, (void *)w.opA,
+                      (void *)w.opB, (void *)dump, (void *)bad})
+        if (ptr) cudaFree(ptr);
+    return result;
 }
 
 bool umma_applicable(const Geom &g)

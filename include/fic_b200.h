@@ -63,6 +63,10 @@ extern "C" {
 
 #define FIC_OPT_ENGINE 1
 #define FIC_OPT_UMMA_KIND 2
+/* Read-only (fic_get_option): 1 if this device's kind::f16 tensor path reproduced the exact integer
+ * covariances in the library's self-test (run once per handle, before the first kind::f16 search);
+ * 0 means the handle silently runs kind::i8 instead. */
+#define FIC_OPT_F16_EXACT 3
 
 typedef struct fic_handle fic_handle;
 
@@ -88,6 +92,7 @@ void fic_destroy(fic_handle *h);
 const char *fic_last_error(const fic_handle *h); /* h may be NULL: last create error */
 const char *fic_version(void);
 int fic_set_option(fic_handle *h, int option, int value);
+int fic_get_option(fic_handle *h, int option, int *value);
 /* Run subsequent calls on a caller-provided CUDA stream (cudaStream_t), or NULL for
  * the handle's own stream (pass cudaStreamLegacy, 0x1, to mean the legacy default stream).  Used by the torch.distributed host so that library work
  * orders after the NCCL broadcast without a device-wide sync. */

@@ -293,6 +293,12 @@ def test_cpp_host_cli_roundtrip(tmp_path, oracle, lena_grey):
     assert (dec == ((oimg.view(np.uint32) >> 16) & 0xFF)).all()
 
 
+def test_f16_tensor_path_is_exact_on_this_device(handle):
+    """The library's own self-test (every binary32 accumulator of a kind::f16 search on worst-case content against
+    integer arithmetic) must pass on a B200; a failing device would silently be served by kind::i8."""
+    assert handle.f16_exact()
+
+
 def test_tensor_peak_measurement(fic, handle):
     tops = handle.measure_int8_peak()
     # nominal dense int8 on B200 is 4500 TOP/s; anything far outside means the loop is not measuring the pipe
