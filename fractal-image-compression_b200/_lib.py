@@ -16,6 +16,7 @@ FIC_OK = 0
 FIC_E_ARG, FIC_E_CUDA, FIC_E_NOMEM, FIC_E_STREAM, FIC_E_INTERNAL = -1, -2, -3, -4, -5
 FIC_ENGINE_AUTO, FIC_ENGINE_DIRECT, FIC_ENGINE_UMMA = 0, 1, 2
 FIC_UMMA_KIND_AUTO, FIC_UMMA_KIND_I8, FIC_UMMA_KIND_F16 = 0, 1, 2
+FIC_MODE_GREY, FIC_MODE_RGB, FIC_MODE_GREY_ISO = 0, 1, 2
 FIC_OPT_ENGINE = 1
 FIC_OPT_UMMA_KIND = 2
 FIC_OPT_F16_EXACT = 3
@@ -23,7 +24,7 @@ FIC_OPT_F16_EXACT = 3
 # every symbol include/fic_b200.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "fic_create", "fic_destroy", "fic_last_error", "fic_version", "fic_set_option", "fic_get_option", "fic_set_stream",
-    "fic_get_timings", "fic_geometry", "fic_encode_grey", "fic_encode_rgb", "fic_encode_planes_dev",
+    "fic_get_timings", "fic_geometry", "fic_encode_grey", "fic_encode_rgb", "fic_encode_grey_iso", "fic_encode_planes_dev",
     "fic_sync", "fic_decode", "fic_collage", "fic_build_pool", "fic_stream_size", "fic_stream_write",
     "fic_stream_read_header", "fic_stream_read_codes", "fic_measure_int8_peak", "fic_measure_mma_peak",
 ]
@@ -69,7 +70,7 @@ def load() -> C.CDLL:
     L.fic_set_stream.argtypes = [vp, vp]
     L.fic_get_timings.argtypes = [vp, C.POINTER(Timings)]
     L.fic_geometry.argtypes = [C.c_int] * 4 + [C.POINTER(i64), C.POINTER(i64)]
-    for fn in (L.fic_encode_grey, L.fic_encode_rgb):
+    for fn in (L.fic_encode_grey, L.fic_encode_rgb, L.fic_encode_grey_iso):
         fn.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, i64, i64, vp, vp]
     L.fic_encode_planes_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64, i64, vp, vp]
     L.fic_sync.argtypes = [vp]

@@ -130,12 +130,13 @@ class Handle:
         self._check(self._L.fic_geometry(W, H, B, wk, C.byref(nr), C.byref(nd)))
         return nr.value, nd.value
 
-    def encode(self, argb: np.ndarray, B: int, wk: int, rgb: bool, range_begin: int = 0,
+    def encode(self, argb: np.ndarray, B: int, wk: int, rgb, range_begin: int = 0,
                range_end: int | None = None, info: np.ndarray | None = None, q: np.ndarray | None = None):
-        """Runs fic_encode_grey / fic_encode_rgb; returns (imageInfo float32[NR][S], qcodes int32[NR][S])."""
+        """Runs fic_encode_grey / fic_encode_rgb (rgb = False / True) or the isometry extension fic_encode_grey_iso
+        (rgb = FIC_MODE_GREY_ISO); returns (imageInfo float32[NR][S], qcodes int32[NR][S]), S = 3 / 5 / 4."""
         a = np.ascontiguousarray(argb, dtype=np.int32)
         H, W = a.shape
-        S = 5 if rgb else 3
+        S = (3, 5, 4)[int(rgb)]
         nr = (W // B) * (H // B) if B > 0 else 0
         if range_end is None:
             range_end = nr
@@ -143,7 +144,7 @@ class Handle:
             info = np.zeros((max(nr, 0), S), np.float32)
         if q is None:
             q = np.zeros((max(nr, 0), S), np.int32)
-        fn = self._L.fic_encode_rgb if rgb else self._L.fic_encode_grey
+        fn = (self._L.fic_encode_grey, self._L.fic_encode_rgb, self._L.fic_encode_grey_iso)[int(rgb)]
         self._check(fn(self._h, _ptr(a), W, H, B, wk, range_begin, range_end, _ptr(info), _ptr(q)))
         return info, q
 
@@ -211,7 +212,7 @@ def stream_write(q: np.ndarray, W: int, H: int, B: int, wk: int, rgb: bool) -> b
 
 
 def stream_read(stream: bytes):
-    """Returns (is_rgb, W, H, B, wk, qcodes int32[NR][S])."""
+    """Returns (mode, W, H, B, wk, qcodes int32[NR][S]); mode is False (grey), True (RGB) or FIC_MODE_GREY_ISO (2)."""
     L = _lib.load()
     buf = np.frombuffer(stream, np.uint8)
     v = [C.c_int() for _ in range(5)]
@@ -220,12 +221,12 @@ def stream_read(stream: bytes):
     if rc:
         raise FicError(rc, "malformed .run stream")
     rgb, W, H, B, wk = [x.value for x in v]
-    S = 5 if rgb else 3
+    S = (3, 5, 4)[rgb]
     q = np.empty(((W // B) * (H // B), S), np.int32)
     rc = L.fic_stream_read_codes(_ptr(buf), len(buf), _ptr(q))
     if rc:
         raise FicError(rc, "malformed .run stream")
-    return bool(rgb), W, H, B, wk, q
+    return (rgb if rgb == _lib.FIC_MODE_GREY_ISO else bool(rgb)), W, H, B, wk, q
 
 
 class FractalCompression:

@@ -15,10 +15,11 @@ using namespace fic;
 // ------------------------------------------------------------------------------------
 // geometry / argument checking
 // ------------------------------------------------------------------------------------
-int fic::make_geom(int W, int H, int B, int wk, int is_rgb, Geom *g, const char **why)
+int fic::make_geom(int W, int H, int B, int wk, int mode, Geom *g, const char **why)
 {
     const char *dummy;
     if (!why) why = &dummy;
+    if (mode < FIC_MODE_GREY || mode > FIC_MODE_GREY_ISO) { *why = "mode must be FIC_MODE_GREY, FIC_MODE_RGB or FIC_MODE_GREY_ISO"; return FIC_E_ARG; }
     // FC:1019 `abstand = blockgroesse / 4` is 0 for B < 4 (ArithmeticException); the
     // reference GUI offers 4, 8, 16 (RLEAppView.fxml:55).  Larger blocks leave the range
     // in which the reference's float covariance is an exact integer, so they are refused.
@@ -34,7 +35,8 @@ int fic::make_geom(int W, int H, int B, int wk, int is_rgb, Geom *g, const char 
     if (ND >= (1 << 24) || (int64_t)wk * wk >= (1 << 24)) { *why = "domain pool too large for the reference's float index (>= 2^24)"; return FIC_E_ARG; }
     g->W = W; g->H = H; g->B = B; g->n = B * B; g->wk = wk;
     g->rpw = rpw; g->rph = rph; g->dpw = dpw; g->dph = dph;
-    g->sw = W / 2; g->sh = H / 2; g->step = B / 4; g->C = is_rgb ? 3 : 1;
+    g->sw = W / 2; g->sh = H / 2; g->step = B / 4; g->C = mode == FIC_MODE_RGB ? 3 : 1;
+    g->n_iso = mode == FIC_MODE_GREY_ISO ? 8 : 1;
     g->NR = (int64_t)rpw * rph; g->ND = ND;
     return FIC_OK;
 }
@@ -344,7 +346,7 @@ static int encode_host(fic_handle *h, int is_rgb, const int32_t *argb, int W, in
     memset(&h->tm, 0, sizeof h->tm);
     Work &w = h->w;
     cudaStream_t s = h->stream;
-    int S = is_rgb ? 5 : 3;
+    int S = code_stride(g);
     ENSURE(w.argb, S_ARGB, sizeof(int32_t) * (size_t)W * H);
     ENSURE(w.src, S_SRC, (size_t)g.C * W * H);
     ENSURE(w.info, S_INFO, sizeof(float) * g.NR * S);
@@ -376,6 +378,12 @@ int fic_encode_rgb(fic_handle *h, const int32_t *argb, int W, int H, int B, int 
                    int64_t range_end, float *info, int32_t *qcodes)
 {
     return encode_host(h, 1, argb, W, H, B, wk, range_begin, range_end, info, qcodes);
+}
+
+int fic_encode_grey_iso(fic_handle *h, const int32_t *argb, int W, int H, int B, int wk, int64_t range_begin,
+                        int64_t range_end, float *info, int32_t *qcodes)
+{
+    return encode_host(h, FIC_MODE_GREY_ISO, argb, W, H, B, wk, range_begin, range_end, info, qcodes);
 }
 
 int fic_encode_planes_dev(fic_handle *h, const uint8_t *d_planes, int is_rgb, int W, int H, int B, int wk,
@@ -456,7 +464,7 @@ int fic_decode(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int
     memset(&h->tm, 0, sizeof h->tm);
     Work &w = h->w;
     cudaStream_t s = h->stream;
-    int S = is_rgb ? 5 : 3;
+    int S = code_stride(g);
     size_t plane = (size_t)W * H;
     ENSURE(w.q, S_Q, sizeof(int32_t) * g.NR * S);
     ENSURE(w.dcode, S_DCODE, sizeof(float) * g.NR * (S + 1));
@@ -541,7 +549,7 @@ int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, in
     CU(cudaSetDevice(h->device));
     Work &w = h->w;
     cudaStream_t s = h->stream;
-    int S = is_rgb ? 5 : 3;
+    int S = code_stride(g);
     size_t plane = (size_t)W * H;
     ENSURE(w.argb, S_ARGB, sizeof(int32_t) * plane);
     ENSURE(w.src, S_SRC, g.C * plane);
@@ -585,14 +593,15 @@ static int32_t get_be32(const uint8_t *p)
 size_t fic_stream_size(int is_rgb, int W, int H, int B)
 {
     if (B <= 0 || W <= 0 || H <= 0) return 0;
-    return 20 + (size_t)(is_rgb ? 20 : 12) * (size_t)(W / B) * (size_t)(H / B);
+    const size_t per_range = is_rgb == FIC_MODE_GREY_ISO ? 16 : (is_rgb ? 20 : 12);
+    return 20 + per_range * (size_t)(W / B) * (size_t)(H / B);
 }
 
 int fic_stream_write(int is_rgb, int W, int H, int B, int wk, const int32_t *qcodes, uint8_t *out, size_t out_bytes)
 {
     size_t need = fic_stream_size(is_rgb, W, H, B);
     if (!qcodes || !out || need == 0 || out_bytes < need) return FIC_E_ARG;
-    put_be32(out, is_rgb ? 1 : 0);  // FC:234-238
+    put_be32(out, is_rgb == FIC_MODE_GREY_ISO ? 2 : (is_rgb ? 1 : 0));  // FC:234-238; 2 = isometry extension
     put_be32(out + 4, W);
     put_be32(out + 8, H);
     put_be32(out + 12, B);
@@ -606,7 +615,8 @@ int fic_stream_read_header(const uint8_t *stream, size_t nbytes, int *is_rgb, in
                            size_t *qcodes_off)
 {
     if (!stream || nbytes < 20) return FIC_E_STREAM;
-    int rgb = get_be32(stream) != 0;  // FC:548-552: 0 -> grey, anything else -> RGB
+    // FC:548-552: 0 -> grey, anything else -> RGB; this library's isometry extension writes 2
+    int rgb = get_be32(stream) == 2 ? FIC_MODE_GREY_ISO : (get_be32(stream) != 0);
     int w = get_be32(stream + 4), hh = get_be32(stream + 8), b = get_be32(stream + 12), k = get_be32(stream + 16);
     Geom g;
     if (make_geom(w, hh, b, k, rgb, &g, nullptr)) return FIC_E_STREAM;

@@ -49,6 +49,26 @@ __host__ __device__ inline void range_window(const Geom &g, int64_t j, int *dy, 
     window_origin(i, g.dpw, g.dph, g.wk, dy, dx);
 }
 
+// Isometry extension (not in the reference): T_k maps range pixel (ry, rx) of a B x B block to the domain
+// pixel (sy, sx) it is compared with / reconstructed from.  0 identity, 1-3 rotations, 4 mirror x, 5 mirror y,
+// 6 transpose, 7 anti-transpose.
+__host__ __device__ inline void iso_map(int k, int B, int ry, int rx, int *sy, int *sx)
+{
+    const int m = B - 1;
+    switch (k & 7) {
+    case 0: *sy = ry;     *sx = rx;     break;
+    case 1: *sy = m - rx; *sx = ry;     break;
+    case 2: *sy = m - ry; *sx = m - rx; break;
+    case 3: *sy = rx;     *sx = m - ry; break;
+    case 4: *sy = ry;     *sx = m - rx; break;
+    case 5: *sy = m - ry; *sx = rx;     break;
+    case 6: *sy = rx;     *sx = ry;     break;
+    default: *sy = m - rx; *sx = m - ry; break;
+    }
+}
+// iso_map(iso_inverse(k)) undoes iso_map(k): the rotations by 90 and 270 degrees swap, the rest are involutions.
+__host__ __device__ inline int iso_inverse(int k) { return k == 1 ? 3 : (k == 3 ? 1 : k); }
+
 #ifdef __CUDACC__
 
 // Java (int)float: truncate toward zero, saturate, NaN -> 0 == cvt.rzi.s32.f32.

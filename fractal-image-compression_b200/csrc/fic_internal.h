@@ -17,11 +17,16 @@ struct Geom {
     int sw, sh;           // decimated image size (W/2, H/2)
     int step;             // domain grid stride in decimated pixels (B/4, FC:1019)
     int C;                // channels: 1 grey, 3 RGB
+    int n_iso;            // isometries searched per candidate: 1 (the reference), 8 (extension, grey only)
     int64_t NR, ND;
 };
 
-// Returns FIC_OK or FIC_E_ARG (same rejections as the reference's exceptions).
-int make_geom(int W, int H, int B, int wk, int is_rgb, Geom *g, const char **why);
+// Floats / ints per range in the code tables: {c, a, b} grey, {c, a, bR, bG, bB} RGB, {c, a, b, k} grey + isometry.
+__host__ __device__ inline int code_stride(const Geom &g) { return g.C == 3 ? 5 : (g.n_iso > 1 ? 4 : 3); }
+
+// mode: FIC_MODE_GREY / FIC_MODE_RGB / FIC_MODE_GREY_ISO.  Returns FIC_OK or FIC_E_ARG (same rejections as the
+// reference's exceptions).
+int make_geom(int W, int H, int B, int wk, int mode, Geom *g, const char **why);
 
 // Device workspace owned by a handle (grow-only).
 struct Work {

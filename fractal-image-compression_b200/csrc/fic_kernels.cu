@@ -375,6 +375,62 @@ k_search_direct_rgb(const uint8_t *__restrict__ src, const uint8_t *__restrict__
     if (threadIdx.x == 0) best[j] = best_c;
 }
 
+// Isometry extension of k_search_direct_grey: every candidate is scored under the 8 isometries (inner loop,
+// k ascending); best[j] = c * 8 + k of the lexicographic (error, c, k) minimum -- what an ascending
+// (c, k) double loop with strict < yields.  s_rt[k][p] holds (r - rmean) of the range pixel that isometry k
+// maps onto domain pixel p, so one pass over the domain block feeds all eight dot products.
+__global__ void __launch_bounds__(kDirectThreads)
+k_search_direct_grey_iso(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec,
+                         const int32_t *__restrict__ dsum, const int32_t *__restrict__ dsq,
+                         const int32_t *__restrict__ rsum, int32_t *__restrict__ best, Geom g, int64_t j0)
+{
+    __shared__ short s_rt[8][256];  // B <= 16
+    __shared__ float s_err[kDirectThreads / 32];
+    __shared__ int s_c[kDirectThreads / 32];
+    int64_t j = j0 + blockIdx.x;
+    int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    int rs = rsum[j];
+    int rmean = rs / g.n;
+    int vR = rs - g.n * rmean;
+    for (int t = threadIdx.x; t < 8 * g.n; t += kDirectThreads) {
+        int k = t / g.n, p = t % g.n;
+        int ry, rx;  // the range pixel that T_k sends to domain pixel p
+        iso_map(iso_inverse(k), g.B, p / g.B, p % g.B, &ry, &rx);
+        s_rt[k][p] = (short)((int)src[(int64_t)(yr * g.B + ry) * g.W + xr * g.B + rx] - rmean);
+    }
+    __syncthreads();
+    int dy, dx;
+    range_window(g, j, &dy, &dx);
+    float best_err = 10000000.0f;
+    int best_c = 0;
+    int ncand = g.wk * g.wk;
+    for (int c = threadIdx.x; c < ncand; c += kDirectThreads) {
+        int ky = c / g.wk, kx = c - ky * g.wk;
+        int gx = dx + kx, gy = dy + ky;
+        int64_t idx = gx + (int64_t)gy * g.dpw;
+        const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+        int dot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int sy = 0; sy < g.B; sy++) {
+            const uint8_t *row = p + (int64_t)sy * g.sw;
+            for (int sx = 0; sx < g.B; sx++) {
+                const int d = (int)__ldg(row + sx);
+#pragma unroll
+                for (int k = 0; k < 8; k++) dot[k] += (int)s_rt[k][sy * g.B + sx] * d;
+            }
+        }
+        int dmean;
+        int varD = dom_var(dsum[idx], dsq[idx], g.n, &dmean);
+        const double sqd = __dsqrt_rn((double)varD);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            float err = grey_error(dot[k] - dmean * vR, vR, sqd);
+            if (err < best_err) { best_err = err; best_c = c * 8 + k; }
+        }
+    }
+    block_argmin(best_err, best_c, s_err, s_c);
+    if (threadIdx.x == 0) best[j] = best_c;
+}
+
 int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, cudaStream_t s)
 {
     if (j1 <= j0) return 0;
@@ -382,7 +438,9 @@ int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, c
     int launches = 0;
     while (left > 0) {  // grid.x limit is 2^31-1; chunk anyway to keep launches bounded
         unsigned chunk = (unsigned)(left < (1 << 30) ? left : (1 << 30));
-        if (g.C == 1)
+        if (g.C == 1 && g.n_iso > 1)
+            k_search_direct_grey_iso<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, g, at);
+        else if (g.C == 1)
             k_search_direct_grey<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, g, at);
         else
             k_search_direct_rgb<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.rsum, w.best, g, at);
@@ -405,7 +463,9 @@ __global__ void k_solve_grey(const uint8_t *__restrict__ src, const uint8_t *__r
     int64_t j = j0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= j1) return;
     int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
-    int c = best[j];
+    const bool iso = g.n_iso > 1;  // extension: best = c * 8 + isometry
+    int c = iso ? best[j] >> 3 : best[j];
+    const int kiso = iso ? best[j] & 7 : 0;
     int dy, dx;
     range_window(g, j, &dy, &dx);
     int ky = c / g.wk, kx = c - ky * g.wk;
@@ -417,8 +477,11 @@ __global__ void k_solve_grey(const uint8_t *__restrict__ src, const uint8_t *__r
     const uint8_t *pd = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
     int dot = 0;
     for (int ry = 0; ry < g.B; ry++)
-        for (int rx = 0; rx < g.B; rx++)
-            dot += ((int)pr[(int64_t)ry * g.W + rx] - rmean) * (int)pd[(int64_t)ry * g.sw + rx];
+        for (int rx = 0; rx < g.B; rx++) {
+            int sy = ry, sx = rx;
+            if (iso) iso_map(kiso, g.B, ry, rx, &sy, &sx);
+            dot += ((int)pr[(int64_t)ry * g.W + rx] - rmean) * (int)pd[(int64_t)sy * g.sw + sx];
+        }
     int dmean;
     int varD = dom_var(dsum[idx], dsq[idx], g.n, &dmean);
     int kov = dot - dmean * vR;
@@ -427,15 +490,18 @@ __global__ void k_solve_grey(const uint8_t *__restrict__ src, const uint8_t *__r
     else if (a > 1.0f) a = 1.0f;
     float b = __fsub_rn((float)rmean, __fmul_rn(a, (float)dmean));  // FC:641
     float fc = (float)c;
+    const int S = iso ? 4 : 3;
     if (info) {
-        info[3 * j + 0] = fc;
-        info[3 * j + 1] = a;
-        info[3 * j + 2] = b;
+        info[S * j + 0] = fc;
+        info[S * j + 1] = a;
+        info[S * j + 2] = b;
+        if (iso) info[S * j + 3] = (float)kiso;
     }
     if (q) {
-        q[3 * j + 0] = j_f2i(fc);                     // FC:242
-        q[3 * j + 1] = j_f2i(__fmul_rn(a, 100.0f));   // FC:243
-        q[3 * j + 2] = j_f2i(b);                      // FC:244
+        q[S * j + 0] = j_f2i(fc);                     // FC:242
+        q[S * j + 1] = j_f2i(__fmul_rn(a, 100.0f));   // FC:243
+        q[S * j + 2] = j_f2i(b);                      // FC:244
+        if (iso) q[S * j + 3] = kiso;
     }
 }
 
@@ -522,14 +588,15 @@ __global__ void k_dequant(const int32_t *__restrict__ q, const float *__restrict
 {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= g.NR) return;
-    int S = g.C == 1 ? 3 : 5;
+    int S = code_stride(g);
     float v[5];
     if (unquantised) {
         for (int k = 0; k < S; k++) v[k] = info_in[S * j + k];
     } else if (g.C == 1) {
-        v[0] = (float)q[3 * j];
-        v[1] = __fdiv_rn((float)q[3 * j + 1], 100.0f);
-        v[2] = (float)q[3 * j + 2];
+        v[0] = (float)q[S * j];
+        v[1] = __fdiv_rn((float)q[S * j + 1], 100.0f);
+        v[2] = (float)q[S * j + 2];
+        if (S == 4) v[3] = (float)(q[S * j + 3] & 7);  // isometry index (extension)
     } else {
         v[0] = (float)q[5 * j];
         v[1] = __fdiv_rn((float)q[5 * j + 1], 1000000.0f);
@@ -603,17 +670,28 @@ k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, ui
         int xr = x / g.B, yr = y / g.B;
         int rx = x - xr * g.B, ry = y - yr * g.B;
         int64_t j = (int64_t)yr * g.rpw + xr;
-        constexpr int S = C == 1 ? 3 : 5;
+        const int S = code_stride(g);
         const float *cd = code + S * j;
         float a = cd[1];
         const int off = doff[j];
         int64_t planeI = (int64_t)g.W * g.H, planeD = (int64_t)g.sw * g.sh;
         int e[4] = {0, 0, 0, 0};
+        // domain pixel of each of the quad's four range pixels: the same position, or (isometry extension,
+        // grey only) the position the range's isometry maps it to
+        int o00 = ry * g.sw + rx, o10 = o00 + 1, o01 = o00 + g.sw, o11 = o01 + 1;
+        if (C == 1 && g.n_iso > 1) {
+            const int kiso = j_f2i(cd[3]);
+            int sy, sx;
+            iso_map(kiso, g.B, ry, rx, &sy, &sx);         o00 = sy * g.sw + sx;
+            iso_map(kiso, g.B, ry, rx + 1, &sy, &sx);     o10 = sy * g.sw + sx;
+            iso_map(kiso, g.B, ry + 1, rx, &sy, &sx);     o01 = sy * g.sw + sx;
+            iso_map(kiso, g.B, ry + 1, rx + 1, &sy, &sx); o11 = sy * g.sw + sx;
+        }
 #pragma unroll
         for (int c = 0; c < C; c++) {
             float b = cd[2 + c];
-            const uint8_t *pd = dec_in + c * planeD + off + ry * g.sw + rx;
-            int d00 = pd[0], d10 = pd[1], d01 = pd[g.sw], d11 = pd[g.sw + 1];
+            const uint8_t *pd = dec_in + c * planeD + off;
+            int d00 = pd[o00], d10 = pd[o10], d01 = pd[o01], d11 = pd[o11];
             // FC:396 / FC:482: (int)(a * domain + b), float multiply then float add
             int v00 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d00), b)));
             int v10 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d10), b)));
@@ -727,7 +805,7 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out, const float *d_code,
                         const int32_t *d_off, const Geom &g, unsigned long long *d_acc, int32_t *d_perr, cudaStream_t s)
 {
-    if (g.W % 8 == 0) {
+    if (g.W % 8 == 0 && g.n_iso == 1) {  // the isometry extension uses the quad kernel (per-pixel gather)
         int64_t strips = (int64_t)(g.W / 8) * (g.H / 2);
         unsigned blocks = (unsigned)((strips + 255) / 256);
         if (g.C == 1)

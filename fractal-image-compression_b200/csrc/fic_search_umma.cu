@@ -318,8 +318,11 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
     if (threadIdx.x == 0) *(uint4 *)(blob + L::B_OP_BYTES + kChunksPerTile * 8) = make_uint4((uint32_t)tile_has_l, 0, 0, 0);
 }
 
-// One thread per (padded) range row of the slice [j0, j1).  kind::i8: raw pixels + the integer mean
-// columns; kind::f16: pixels centred by the integer mean, as binary16.
+// One thread per (padded) operand row of the slice [j0, j1).  kind::i8: raw pixels + the integer mean
+// columns; kind::f16: pixels centred by the integer mean, as binary16.  With the isometry extension
+// (g.n_iso = 8) a range block owns 8 adjacent rows: row v = (j - j0) * 8 + k holds the block permuted so that
+// its dot product with an unpermuted domain block is kov(r, T_k d) -- column p carries the range pixel that
+// T_k maps onto domain pixel p.  Means and sums do not depend on k.
 template <int B, bool F16>
 __global__ void __launch_bounds__(128)
 k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, uint8_t *__restrict__ opA,
@@ -334,7 +337,8 @@ k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ 
     int blk = rr / kBlockM, row = rr % kBlockM;
     uint8_t *rowp = opA + sb * L::A_SB_BYTES + blk * L::A_BLOCK_BYTES + (row >> 3) * L::SBO_A + (row & 7) * 16;
     constexpr int NCH = Cfg<B, F16>::KS_A * 2;
-    int64_t j = j0 + i;
+    const int64_t j = j0 + i / g.n_iso;
+    const int kiso = (int)(i % g.n_iso);
     if (j >= j1) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
@@ -353,8 +357,18 @@ k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ 
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             int k = c * 16 + w * 4;
-            // 4 consecutive k share a pixel row for B >= 4; 4-byte aligned since xr*B, k%B are multiples of 4
-            w4[w] = *(const uint32_t *)(p + (int64_t)(k / B) * g.W + (k % B));
+            if (kiso == 0) {
+                // 4 consecutive k share a pixel row for B >= 4; 4-byte aligned since xr*B, k%B are multiples of 4
+                w4[w] = *(const uint32_t *)(p + (int64_t)(k / B) * g.W + (k % B));
+            } else {
+                w4[w] = 0;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    int ry, rx;  // the range pixel that T_kiso sends to domain pixel k + e
+                    iso_map(iso_inverse(kiso), B, (k + e) / B, (k + e) % B, &ry, &rx);
+                    w4[w] |= (uint32_t)p[(int64_t)ry * g.W + rx] << (8 * e);
+                }
+            }
         }
         if (F16) {
             uint32_t hw[8];
@@ -911,18 +925,22 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
               const int32_t *__restrict__ pos_dom, const int32_t *__restrict__ pos_var, const int32_t *__restrict__ pos_sum,
               const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
               int64_t rows_padded, int64_t rows, int64_t npos, const int64_t *__restrict__ dom0_pos,
-              int32_t *__restrict__ best, Geom g, int64_t j0)
+              int32_t *__restrict__ best, int2 *__restrict__ vbest, Geom g, int64_t j0)
 {
     constexpr int n = B * B;
     constexpr int NW = n / 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * 4 + warp;
+    const int64_t i = (int64_t)blockIdx.x * 4 + warp;  // operand row (see k_umma_pack_ranges)
     if (i >= rows) return;
-    const int64_t j = j0 + i;
+    const int64_t j = j0 + i / g.n_iso;
+    const int kiso = (int)(i % g.n_iso);
     const int rs = rsum[j];
     const int rmean = rs / n, vR = rs - n * rmean;
     if (vR == 0) {  // FC:677-678 + FC:627: all errors are 0, the first candidate wins
-        if (lane == 0) best[j] = 0;
+        if (lane == 0) {
+            if (g.n_iso == 1) best[j] = 0;
+            else vbest[i] = make_int2(0, 0);  // (binary32 bits of the error, domain index)
+        }
         return;
     }
     const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
@@ -930,7 +948,17 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
 #pragma unroll
     for (int w = 0; w < NW; w++) {
         const int k = 4 * w;
-        rw[w] = __ldg((const uint32_t *)(src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)));
+        if (kiso == 0) {
+            rw[w] = __ldg((const uint32_t *)(src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)));
+        } else {  // the same permutation as the operand row
+            rw[w] = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int ry, rx;
+                iso_map(iso_inverse(kiso), B, (k + e) / B, (k + e) % B, &ry, &rx);
+                rw[w] |= (uint32_t)__ldg(src + (int64_t)(yr * B + ry) * g.W + xr * B + rx) << (8 * e);
+            }
+        }
     }
     float be = 10000000.0f;  // FC:615
     int bi = 0x7fffffff;
@@ -967,7 +995,29 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
         int i2 = __shfl_down_sync(0xffffffffu, bi, o);
         if (e2 < be || (e2 == be && i2 < bi)) { be = e2; bi = i2; }
     }
-    if (lane == 0) best[j] = bi == 0x7fffffff ? 0 : bi;
+    if (lane == 0) {
+        if (bi == 0x7fffffff) { bi = 0; be = 0.0f; }
+        if (g.n_iso == 1) best[j] = bi;
+        else vbest[i] = make_int2(__float_as_int(be), bi);
+    }
+}
+
+// Isometry extension: the winner of a range block is the lexicographic (error, c, k) minimum over its 8 operand
+// rows (each row already holds its lowest c among equal errors) = what an ascending (c, k) double loop with
+// strict < yields.  best[j] = c * 8 + k.
+__global__ void k_umma_merge_iso(const int2 *__restrict__ vbest, int32_t *__restrict__ best, int64_t ranges, int64_t j0)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ranges) return;
+    float be = 0.0f;
+    int bc = 0x7fffffff;
+    for (int k = 0; k < 8; k++) {
+        const int2 v = vbest[r * 8 + k];
+        const float e = __int_as_float(v.x);
+        const int c = v.y * 8 + k;
+        if (k == 0 || e < be || (e == be && c < bc)) { be = e; bc = c; }
+    }
+    best[j0 + r] = bc;
 }
 
 // ---------------------------------------------------------------- host side ------------
@@ -1037,9 +1087,9 @@ template <int B, bool F16>
 size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p = make_plan(g, rows, num_sms);
-    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap]
+    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap][vbest int2 (isometries)]
     return (size_t)p.n_sb * Lay<B, F16>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 2 * 4 * (1 + kFlagCap) +
-           1024;
+           (size_t)p.rp * 8 + 1024;
 }
 
 template <int B, bool F16>
@@ -1048,14 +1098,15 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
              cudaEvent_t k1 = nullptr, uint32_t dbg = 0)
 {
     using L = Lay<B, F16>;
-    int64_t rows = j1 - j0;
-    if (rows <= 0) return 0;
+    if (j1 <= j0) return 0;
+    const int64_t rows = (j1 - j0) * g.n_iso;  // operand rows: one per (range, isometry)
     Plan p = make_plan(g, rows, num_sms);
     const int64_t rp = p.rp;
     uint8_t *opA = w.opA;
     int32_t *vR = (int32_t *)(opA + (size_t)p.n_sb * L::A_SB_BYTES);
     int32_t *flag_cnt = vR + rp;
     int32_t *flag_list = flag_cnt + rp * p.n_chunks * 2;
+    int2 *vbest = (int2 *)(((uintptr_t)(flag_list + rp * p.n_chunks * 2 * kFlagCap) + 15) & ~(uintptr_t)15);
     OpBLayout<B, F16> lay(g, p);
     int32_t *pos_dom = (int32_t *)(w.opB + lay.off_posdom);
     int32_t *pos_var = (int32_t *)(w.opB + lay.off_posvar);
@@ -1108,7 +1159,11 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     if (k1) cudaEventRecord(k1, s);
     // 4. exact refine of the flagged chunks
     if (!(dbg & 8u)) k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_dom, pos_var, pos_sum, flag_list,
-                                                                flag_cnt, p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
+                                                                flag_cnt, p.n_chunks, rp, rows, p.npos, dom0, w.best, vbest, g, j0);
+    if (g.n_iso > 1 && !(dbg & 8u)) {
+        k_umma_merge_iso<<<(unsigned)((j1 - j0 + 255) / 256), 256, 0, s>>>(vbest, w.best, j1 - j0, j0);
+        launches++;
+    }
     launches += 2;
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
@@ -1275,7 +1330,7 @@ bool umma_applicable(const Geom &g)
 
 size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms, int kind)
 {
-    const int64_t rows = j1 - j0;
+    const int64_t rows = (j1 - j0) * g.n_iso;  // operand rows: one per (range, isometry)
     return FIC_UMMA_DISPATCH(g.B, use_f16(g, kind), (opA_bytes_t<4, false>(g, rows, num_sms)),
                              (opA_bytes_t<8, false>(g, rows, num_sms)), (opA_bytes_t<16, false>(g, rows, num_sms)),
                              (opA_bytes_t<4, true>(g, rows, num_sms)), (opA_bytes_t<8, true>(g, rows, num_sms)));

@@ -50,6 +50,13 @@ extern "C" {
 #define FIC_E_STREAM (-4)  /* malformed .run stream                               */
 #define FIC_E_INTERNAL (-5)
 
+/* Code layout / colour mode (the `is_rgb` argument of the entries below; 0 and 1 are the reference's isRGB
+ * header flag, FC:234-238).  FIC_MODE_GREY_ISO is an EXTENSION the reference does not have: every candidate
+ * domain block is tried under the 8 isometries of the square; codes carry a 4th value, the isometry index. */
+#define FIC_MODE_GREY 0     /* {c, a, b} per range                       */
+#define FIC_MODE_RGB 1      /* {c, a, bR, bG, bB} per range              */
+#define FIC_MODE_GREY_ISO 2 /* {c, a, b, k} per range; k = isometry 0..7 */
+
 /* Search engine selection (fic_set_option(FIC_OPT_ENGINE, ...)). */
 #define FIC_ENGINE_AUTO 0   /* tcgen05 fused search when the window is the whole pool */
 #define FIC_ENGINE_DIRECT 1 /* direct (CUDA-core) windowed search for every window    */
@@ -111,6 +118,15 @@ int fic_encode_grey(fic_handle *h, const int32_t *argb, int W, int H, int B, int
                     int64_t range_begin, int64_t range_end, float *info, int32_t *qcodes);
 int fic_encode_rgb(fic_handle *h, const int32_t *argb, int W, int H, int B, int wk,
                    int64_t range_begin, int64_t range_end, float *info, int32_t *qcodes);
+
+/* EXTENSION (the reference searches the identity only, FC:642): grey encode whose candidate loop has an
+ * inner loop over the 8 isometries of the domain block -- order (c, k) lexicographic, the reference's score
+ * (FC:655-687) and strict-< rule.  info / qcodes are [NR][4] = {c, a, b, k} / {(int)c, (int)(a*100), (int)b, k};
+ * k: 0 identity, 1-3 rotations by 90/180/270 degrees, 4 mirror x, 5 mirror y, 6 transpose, 7 anti-transpose
+ * (the range pixel (ry, rx) takes the domain pixel T_k(ry, rx)).  Every
+ * entry that takes `is_rgb` accepts FIC_MODE_GREY_ISO for these codes; the stream header then carries 2. */
+int fic_encode_grey_iso(fic_handle *h, const int32_t *argb, int W, int H, int B, int wk,
+                        int64_t range_begin, int64_t range_end, float *info, int32_t *qcodes);
 
 /* Same, with the image already resident in device memory as 8-bit planes
  * (grey: red channel, W*H bytes; RGB: R, G, B planes, 3*W*H bytes) and device output

@@ -325,6 +325,69 @@ static void best_domainblock(const codebook_t *cb, int dpw, int wk, int dy, int 
     res[0] = best[0]; res[1] = a; res[2] = b;
 }
 
+/* ------------------------------------------------------------------ isometry extension
+ * NOT IN THE REFERENCE (which searches the identity only, FC:642, FC:733): the classical 8 isometries of
+ * a square block.  T_k maps a range pixel (ry, rx) to the domain pixel (sy, sx) whose value it is compared
+ * with / reconstructed from.  k: 0 identity, 1-3 rotations by 90/180/270 degrees, 4 mirror x, 5 mirror y,
+ * 6 transpose, 7 anti-transpose.  Parity of this mode is defined by this file, not by the reference. */
+void fic_oracle_iso_map(int k, int B, int ry, int rx, int *sy, int *sx)
+{
+    int m = B - 1;
+    switch (k & 7) {
+    case 0: *sy = ry;     *sx = rx;     break;
+    case 1: *sy = m - rx; *sx = ry;     break;
+    case 2: *sy = m - ry; *sx = m - rx; break;
+    case 3: *sy = rx;     *sx = m - ry; break;
+    case 4: *sy = ry;     *sx = m - rx; break;
+    case 5: *sy = m - ry; *sx = rx;     break;
+    case 6: *sy = rx;     *sx = ry;     break;
+    default: *sy = m - rx; *sx = m - ry; break;
+    }
+}
+
+/* getBestDomainblock with the candidate loop extended by an inner loop over the 8 isometries: same score
+ * (err_var_cov on the permuted domain block), same strict-< rule, candidate order (c, k) lexicographic.
+ * res = {c, a, b, k}. */
+static void best_domainblock_iso(const codebook_t *cb, int dpw, int wk, int dy, int dx, int B,
+                                 const int *range, int rangeM, float res[4])
+{
+    float smallest = 10000000;
+    float best[7] = {0, 0, 0, 0, 0, 0, 0};
+    int n = cb->n;
+    int32_t *perm = (int32_t *)malloc(sizeof(int32_t) * n);
+    int c = 0;
+    for (int ky = 0; ky < wk; ky++) {
+        for (int kx = 0; kx < wk; kx++, c++) {
+            long index = dx + kx + (long)(dy + ky) * dpw;
+            const dblock_t *src = &cb->blk[index];
+            for (int k = 0; k < 8; k++) {
+                dblock_t db = *src;  /* mean and variance are invariant under a pixel permutation */
+                for (int ry = 0; ry < B; ry++)
+                    for (int rx = 0; rx < B; rx++) {
+                        int sy, sx;
+                        fic_oracle_iso_map(k, B, ry, rx, &sy, &sx);
+                        perm[rx + ry * B] = src->argb[sx + sy * B];
+                    }
+                db.argb = perm;
+                float ab[5];
+                err_var_cov(range, rangeM, &db, n, ab);
+                if (ab[0] < smallest) {
+                    smallest = ab[0];
+                    best[0] = (float)c;
+                    best[1] = ab[0]; best[2] = ab[1]; best[3] = ab[2]; best[4] = ab[3]; best[5] = ab[4];
+                    best[6] = (float)k;
+                }
+            }
+        }
+    }
+    free(perm);
+    float a = best[2] / best[3];
+    if (a < -1) a = -1;
+    else if (a > 1) a = 1;
+    float b = best[4] - a * best[5];
+    res[0] = best[0]; res[1] = a; res[2] = b; res[3] = best[6];
+}
+
 /* ------------------------------------------------------------------ RGB search */
 
 /* FC:760-808 getErrorVarianceCovarianceRGB ->
@@ -432,9 +495,12 @@ static void *encode_job(void *arg)
         for (int ry = 0; ry < B && y + ry < H; ry++)
             for (int rx = 0; rx < B && x + rx < W; rx++) {
                 int32_t v = jb->argb[(x + rx) + (y + ry) * W];
-                range[k++] = jb->is_rgb ? v : ch_r(v);
+                range[k++] = jb->is_rgb == 1 ? v : ch_r(v);
             }
-        if (!jb->is_rgb) {
+        if (jb->is_rgb == 2) { /* grey + isometries (extension) */
+            int rangeM = mittelwert((const int *)range, n);
+            best_domainblock_iso(jb->cb, dpw, wk, dy, dx, B, (const int *)range, rangeM, jb->info + 4 * j);
+        } else if (!jb->is_rgb) {
             int rangeM = mittelwert((const int *)range, n); /* FC:154 */
             best_domainblock(jb->cb, dpw, wk, dy, dx, (const int *)range, rangeM, jb->info + 3 * j);
         } else {
@@ -454,7 +520,7 @@ static int encode_common(const int32_t *argb, int W, int H, int B, int wk, int i
     long nr = (long)(W / B) * (H / B);
     if (j0 < 0 || j1 > nr || j0 > j1) return -5;
     codebook_t cb;
-    if (codebook_build(&cb, argb, W, H, B, is_rgb)) return -6;
+    if (codebook_build(&cb, argb, W, H, B, is_rgb == 1)) return -6;
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     if ((long)nthreads > j1 - j0) nthreads = (int)(j1 - j0 > 0 ? j1 - j0 : 1);
@@ -489,6 +555,12 @@ int fic_oracle_encode_rgb(const int32_t *argb, int W, int H, int B, int wk,
     return encode_common(argb, W, H, B, wk, 1, range_begin, range_end, nthreads, info);
 }
 
+int fic_oracle_encode_grey_iso(const int32_t *argb, int W, int H, int B, int wk,
+                               long range_begin, long range_end, int nthreads, float *info)
+{
+    return encode_common(argb, W, H, B, wk, 2, range_begin, range_end, nthreads, info);
+}
+
 /* ------------------------------------------------------------------ stream I/O */
 
 static void put_be32(uint8_t **p, int32_t v)
@@ -518,6 +590,15 @@ size_t fic_oracle_write_data(int is_rgb, int W, int H, int B, int wk, const floa
             put_be32(&p, j_f2i(info[3 * r + 2]));
         }
         return 20 + 12 * (size_t)nr;
+    }
+    if (is_rgb == 2) { /* extension: grey codes + isometry index */
+        for (long r = 0; r < nr; r++) {
+            put_be32(&p, j_f2i(info[4 * r + 0]));
+            put_be32(&p, j_f2i(info[4 * r + 1] * 100));
+            put_be32(&p, j_f2i(info[4 * r + 2]));
+            put_be32(&p, j_f2i(info[4 * r + 3]));
+        }
+        return 20 + 16 * (size_t)nr;
     }
     for (long r = 0; r < nr; r++) {
         put_be32(&p, j_f2i(info[5 * r + 0]));
@@ -557,7 +638,7 @@ static int sweep(int32_t *img, int W, int H, int B, int is_rgb, const float *d, 
                  int unquantised_collage, const int32_t *src, float *avg)
 {
     codebook_t cb;
-    if (codebook_build(&cb, src ? src : img, W, H, B, is_rgb)) return -1;
+    if (codebook_build(&cb, src ? src : img, W, H, B, is_rgb == 1)) return -1;
     long i = 0;
     float acc = avg ? *avg : 0;
     (void)unquantised_collage;
@@ -571,7 +652,12 @@ static int sweep(int32_t *img, int W, int H, int B, int is_rgb, const float *d, 
                 for (int rx = 0; rx < B && x + rx < W; rx++) {
                     int32_t old = img[x + rx + (y + ry) * W];
                     int32_t dv = dom[rx + ry * B];
-                    if (!is_rgb) {
+                    if (is_rgb == 2) { /* extension: the domain pixel the isometry c[3] maps (ry, rx) to */
+                        int sy, sx;
+                        fic_oracle_iso_map(j_f2i(c[3]), B, ry, rx, &sy, &sx);
+                        dv = dom[sx + sy * B];
+                    }
+                    if (is_rgb != 1) {
                         int range = ch_r(old);
                         int v = thresh(j_f2i(c[1] * (float)dv + c[2]));
                         img[x + rx + (y + ry) * W] = pack(v, v, v);
@@ -597,17 +683,23 @@ static int sweep(int32_t *img, int W, int H, int B, int is_rgb, const float *d, 
 int fic_oracle_decode(const uint8_t *s, size_t nbytes, int32_t *out, float *avg_error, int *iters)
 {
     if (nbytes < 20) return -1;
-    int is_rgb = get_be32(s) != 0;
+    int is_rgb = get_be32(s) == 2 ? 2 : (get_be32(s) != 0); /* 2: isometry extension stream */
     int W = get_be32(s + 4), H = get_be32(s + 8), B = get_be32(s + 12), wk = get_be32(s + 16);
     int rc = check_args(W, H, B, wk);
     if (rc) return rc;
     long nr = (long)(W / B) * (H / B);
-    int stride = is_rgb ? 5 : 3;
+    int stride = is_rgb == 1 ? 5 : (is_rgb == 2 ? 4 : 3);
     if (nbytes < 20 + (size_t)nr * stride * 4) return -7;
     float *d = (float *)malloc(sizeof(float) * (size_t)nr * stride);
     const uint8_t *p = s + 20;
     for (long r = 0; r < nr; r++) {
-        if (!is_rgb) {
+        if (is_rgb == 2) {
+            d[4 * r + 0] = (float)get_be32(p);
+            d[4 * r + 1] = (float)get_be32(p + 4) / 100.0f;
+            d[4 * r + 2] = (float)get_be32(p + 8);
+            d[4 * r + 3] = (float)get_be32(p + 12);
+            p += 16;
+        } else if (!is_rgb) {
             d[3 * r + 0] = (float)get_be32(p);
             d[3 * r + 1] = (float)get_be32(p + 4) / 100.0f;
             d[3 * r + 2] = (float)get_be32(p + 8);
@@ -646,7 +738,7 @@ int fic_oracle_collage(const int32_t *argb, int W, int H, int B, int wk, int is_
 {
     int rc = check_args(W, H, B, wk);
     if (rc) return rc;
-    int stride = is_rgb ? 5 : 3;
+    int stride = is_rgb == 1 ? 5 : (is_rgb == 2 ? 4 : 3);
     calculate_indices(info, stride, W, H, B, wk);                 /* FC:273 / FC:311 */
     for (long k = 0; k < (long)W * H; k++) out[k] = (int32_t)0xffa0a0a0; /* RI:19, RI:31 */
     return sweep(out, W, H, B, is_rgb, info, stride, 1, argb, NULL);

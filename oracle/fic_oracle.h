@@ -50,6 +50,14 @@ int fic_oracle_encode_grey(const int32_t *argb, int W, int H, int B, int wk,
 int fic_oracle_encode_rgb(const int32_t *argb, int W, int H, int B, int wk,
                           long range_begin, long range_end, int nthreads, float *info);
 
+/* EXTENSION (not in the reference, which has no isometries): grey encode whose candidate loop has an inner
+ * loop over the 8 isometries of the domain block (order (c, k) lexicographic, same score, same strict-<
+ * rule) -> info[NR][4] = {c, a, b, k}.  is_rgb == 2 selects this mode in write_data / collage, and a stream
+ * whose first header int is 2 decodes with it.  fic_oracle_iso_map: range pixel (ry, rx) -> domain pixel. */
+void fic_oracle_iso_map(int k, int B, int ry, int rx, int *sy, int *sx);
+int fic_oracle_encode_grey_iso(const int32_t *argb, int W, int H, int B, int wk,
+                               long range_begin, long range_end, int nthreads, float *info);
+
 /* writeData (FC:230-261): serialises header + quantised codes, big endian.
  * Returns the byte count (20 + 12*NR grey, 20 + 20*NR RGB); out may be NULL. */
 size_t fic_oracle_write_data(int is_rgb, int W, int H, int B, int wk, const float *info,

@@ -41,7 +41,7 @@ def lib() -> C.CDLL:
             fn.restype = None
         L.fic_oracle_create_codebook.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, f32p]
         L.fic_oracle_create_codebook.restype = C.c_long
-        for fn in (L.fic_oracle_encode_grey, L.fic_oracle_encode_rgb):
+        for fn in (L.fic_oracle_encode_grey, L.fic_oracle_encode_rgb, L.fic_oracle_encode_grey_iso):
             fn.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_long, C.c_int, f32p]
             fn.restype = C.c_int
         L.fic_oracle_write_data.argtypes = [C.c_int] * 5 + [f32p, u8p]
@@ -100,27 +100,34 @@ def create_codebook(argb, B: int, rgb: bool = False):
     return pool, mean, var
 
 
+def _mode(rgb: bool, iso: bool) -> int:
+    """Stream / code layout: 0 grey (3 per range), 1 RGB (5), 2 grey + isometry index (4; extension)."""
+    assert not (rgb and iso)
+    return 2 if iso else int(bool(rgb))
+
+
 def encode(argb, B: int, wk: int, rgb: bool = False, range_begin: int = 0, range_end: int | None = None,
-           nthreads: int = 1) -> np.ndarray:
-    """imageInfo[NR][3] (grey) or imageInfoRGB[NR][5]: {window-local idx, a, b...} floats."""
+           nthreads: int = 1, iso: bool = False) -> np.ndarray:
+    """imageInfo[NR][3] (grey) or imageInfoRGB[NR][5]: {window-local idx, a, b...} floats; iso=True (extension,
+    not in the reference): 8 isometries per candidate -> [NR][4] = {idx, a, b, isometry}."""
     a = _argb(argb)
     H, W = a.shape
     nr = (W // B) * (H // B)
     if range_end is None:
         range_end = nr
-    info = np.zeros((nr, 5 if rgb else 3), np.float32)
-    fn = lib().fic_oracle_encode_rgb if rgb else lib().fic_oracle_encode_grey
+    info = np.zeros((nr, (3, 5, 4)[_mode(rgb, iso)]), np.float32)
+    fn = (lib().fic_oracle_encode_grey, lib().fic_oracle_encode_rgb, lib().fic_oracle_encode_grey_iso)[_mode(rgb, iso)]
     rc = fn(_p(a, C.c_int32), W, H, B, wk, range_begin, range_end, nthreads, _p(info, C.c_float))
     if rc:
         raise ValueError(f"oracle encode rejected arguments (rc={rc})")
     return info
 
 
-def write_data(info: np.ndarray, W: int, H: int, B: int, wk: int, rgb: bool = False) -> bytes:
+def write_data(info: np.ndarray, W: int, H: int, B: int, wk: int, rgb: bool = False, iso: bool = False) -> bytes:
     info = np.ascontiguousarray(info, np.float32)
-    n = lib().fic_oracle_write_data(int(rgb), W, H, B, wk, _p(info, C.c_float), None)
+    n = lib().fic_oracle_write_data(_mode(rgb, iso), W, H, B, wk, _p(info, C.c_float), None)
     buf = np.empty(n, np.uint8)
-    lib().fic_oracle_write_data(int(rgb), W, H, B, wk, _p(info, C.c_float), _p(buf, C.c_uint8))
+    lib().fic_oracle_write_data(_mode(rgb, iso), W, H, B, wk, _p(info, C.c_float), _p(buf, C.c_uint8))
     return buf.tobytes()
 
 
@@ -139,12 +146,12 @@ def decode(stream: bytes, avg_error_in: float = 0.0):
     return out, np.float32(avg.value), it.value
 
 
-def collage(argb, info: np.ndarray, B: int, wk: int, rgb: bool = False) -> np.ndarray:
+def collage(argb, info: np.ndarray, B: int, wk: int, rgb: bool = False, iso: bool = False) -> np.ndarray:
     a = _argb(argb)
     H, W = a.shape
     info = np.ascontiguousarray(info, np.float32).copy()
     out = np.empty((H, W), np.int32)
-    rc = lib().fic_oracle_collage(_p(a, C.c_int32), W, H, B, wk, int(rgb), _p(info, C.c_float), _p(out, C.c_int32))
+    rc = lib().fic_oracle_collage(_p(a, C.c_int32), W, H, B, wk, _mode(rgb, iso), _p(info, C.c_float), _p(out, C.c_int32))
     if rc:
         raise ValueError(f"oracle collage failed (rc={rc})")
     return out
