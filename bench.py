@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--block", type=int, default=8)
     ap.add_argument("--pattern", default="structured", choices=["structured", "noise"])
     ap.add_argument("--engine", default="auto", choices=["auto", "direct", "umma"])
+    ap.add_argument("--iso", action="store_true",
+                    help="isometry extension: 8 isometries per candidate domain (8x the evaluations; not a reference mode)")
     ap.add_argument("--mma", default="auto", choices=["auto", "i8", "f16"],
                     help="tensor-core instruction kind of the tcgen05 search (auto: f16 for B=4,8; i8 for B=16)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
@@ -128,7 +130,7 @@ def make_image(args, size):
 # CPU arm: the oracle port of the reference (the Java encoder cannot run: no JVM here)
 # ----------------------------------------------------------------------------------------
 
-def cpu_sample(plane, B, wk, nthreads, target_s):
+def cpu_sample(plane, B, wk, nthreads, target_s, iso=False):
     """Times the oracle's range loop on the first R ranges of the workload.  The codebook
     build is timed separately (a call with zero ranges) and subtracted, so the figure is
     the search rate the reference would sustain over the full image."""
@@ -137,15 +139,15 @@ def cpu_sample(plane, B, wk, nthreads, target_s):
 
     argb = fic.synth.grey_to_argb(plane)
     t0 = time.perf_counter()
-    O.encode(argb, B, wk, range_begin=0, range_end=0, nthreads=1)
+    O.encode(argb, B, wk, range_begin=0, range_end=0, nthreads=1, iso=iso)
     t_pool = time.perf_counter() - t0
     R = nthreads
     t0 = time.perf_counter()
-    O.encode(argb, B, wk, range_begin=0, range_end=R, nthreads=nthreads)
+    O.encode(argb, B, wk, range_begin=0, range_end=R, nthreads=nthreads, iso=iso)
     t_probe = max(time.perf_counter() - t0 - t_pool, 1e-3)
     R = max(nthreads, int(R * target_s / t_probe) // nthreads * nthreads)
     t0 = time.perf_counter()
-    O.encode(argb, B, wk, range_begin=0, range_end=R, nthreads=nthreads)
+    O.encode(argb, B, wk, range_begin=0, range_end=R, nthreads=nthreads, iso=iso)
     t = max(time.perf_counter() - t0 - t_pool, 1e-6)
     return R, t, t_pool
 
@@ -157,16 +159,17 @@ def run_reference(args):
     size, B, wk, NR, ND = workload(args)
     plane = make_image(args, size)
     threads = os.cpu_count() or 1
+    n_iso = 8 if args.iso else 1
     per_step = max(1.0, min(10.0, 100.0 / max(1, args.steps + args.warmup)))
     rates, times = [], []
     R = 0
     for i in range(args.warmup + args.steps):
-        R, t, t_pool = cpu_sample(plane, B, wk, threads, per_step)
+        R, t, t_pool = cpu_sample(plane, B, wk, threads, per_step, args.iso)
         if i >= args.warmup:
-            rates.append(R * ND / t)
+            rates.append(R * ND * n_iso / t)
             times.append(t)
     v = statistics.mean(rates)
-    full_s = NR * ND / v
+    full_s = NR * ND * n_iso / v
     line = {
         "impl": "reference", "metric": "encode_evals_per_s", "value": v / 1e9, "unit": "Gevals/s",
         "mpixel_per_s": size * size / full_s / 1e6,
@@ -206,7 +209,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     size, B, wk, NR, ND = workload(args)
     plane = make_image(args, size)
-    evals = float(NR) * float(ND)
+    n_iso = 8 if args.iso else 1
+    mode = fic.FIC_MODE_GREY_ISO if args.iso else fic.FIC_MODE_GREY
+    S = 4 if args.iso else 3
+    evals = float(NR) * float(ND) * n_iso
 
     handle = fic.Handle(local)
     handle.set_engine({"auto": fic.FIC_ENGINE_AUTO, "direct": fic.FIC_ENGINE_DIRECT, "umma": fic.FIC_ENGINE_UMMA}[args.engine])
@@ -218,31 +224,31 @@ def run_ours(args):
     enc = ShardedEncoder(handle=handle) if world > 1 else None
 
     d_planes = torch.from_numpy(plane).to(dev).reshape(1, size, size).contiguous() if rank == 0 else None
-    d_info = torch.empty((NR, 3), dtype=torch.float32, device=dev)
-    d_q = torch.empty((NR, 3), dtype=torch.int32, device=dev)
+    d_info = torch.empty((NR, S), dtype=torch.float32, device=dev)
+    d_q = torch.empty((NR, S), dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # pinned host buffers for the e2e leg
     h_argb = torch.from_numpy(fic.synth.grey_to_argb(plane)).pin_memory() if rank == 0 else None
     h_plane = torch.from_numpy(plane).pin_memory() if rank == 0 else None
-    h_info = torch.empty((NR, 3), dtype=torch.float32).pin_memory()
-    h_q = torch.empty((NR, 3), dtype=torch.int32).pin_memory()
+    h_info = torch.empty((NR, S), dtype=torch.float32).pin_memory()
+    h_q = torch.empty((NR, S), dtype=torch.int32).pin_memory()
 
     def step_device():
         if world == 1:
-            handle.encode_planes_dev(d_planes.data_ptr(), False, size, size, B, wk, 0, NR, d_info.data_ptr(), d_q.data_ptr())
+            handle.encode_planes_dev(d_planes.data_ptr(), mode, size, size, B, wk, 0, NR, d_info.data_ptr(), d_q.data_ptr())
             return None
-        return enc.encode(d_planes, False, size, size, B, wk, device=dev)
+        return enc.encode(d_planes, mode, size, size, B, wk, device=dev)
 
     def step_e2e():
         if world == 1:
             # the call a user of the library makes: host ARGB in, host codes out
             handle.set_stream(None)
-            handle.encode(h_argb.numpy(), B, wk, rgb=False, info=h_info.numpy(), q=h_q.numpy())
+            handle.encode(h_argb.numpy(), B, wk, rgb=mode, info=h_info.numpy(), q=h_q.numpy())
             handle.set_stream(stream.cuda_stream)
             return
         pl = h_plane.to(dev, non_blocking=True).reshape(1, size, size) if rank == 0 else None
-        out = enc.encode(pl, False, size, size, B, wk, device=dev)
+        out = enc.encode(pl, mode, size, size, B, wk, device=dev)
         if rank == 0:
             h_info.copy_(out[0], non_blocking=True)
             h_q.copy_(out[1], non_blocking=True)
@@ -337,7 +343,7 @@ def run_ours(args):
         "pool_ms": statistics.mean(pool_ms),
         # dram__bytes_read.sum + dram__bytes_write.sum of one k_umma_search launch from `ncu --set full`
         # (profiles/); only known for the profiled workload
-        "traffic": TRAFFIC.get((mma, size, B)) if (is_umma and world == 1) else None,
+        "traffic": TRAFFIC.get((mma, size, B)) if (is_umma and world == 1 and not args.iso) else None,
     }
     line = {
         "metric": "encode_evals_per_s", "value": value / 1e9, "unit": "Gevals/s",
@@ -345,14 +351,15 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": f"synthetic {args.pattern} {size}x{size} grey, B={B}, widthKernel={wk} (full pool)",
-                   "ranges": NR, "domains": ND, "engine": f"tcgen05 kind::{mma}" if engine == fic.FIC_ENGINE_UMMA else "direct",
+        "config": {"workload": f"synthetic {args.pattern} {size}x{size} grey, B={B}, widthKernel={wk} (full pool)"
+                               + (", 8 isometries per domain (extension)" if args.iso else ""),
+                   "ranges": NR, "domains": ND, "isometries": n_iso, "engine": f"tcgen05 kind::{mma}" if engine == fic.FIC_ENGINE_UMMA else "direct",
                    "parallelism": f"range-rows x{world}", "l2": "flushed between timed iterations (256 MiB write)"},
         "clocks": clocks,
         "e2e": {"value": evals / (e2e_ms / args.steps * 1e-3) / 1e9, "unit": "Gevals/s",
                 "mpixel_per_s": size * size / (e2e_ms / args.steps * 1e-3) / 1e6,
                 "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": size * size * (4 if world == 1 else 1), "d2h_bytes_per_step": NR * 24},
+                "h2d_bytes_per_step": size * size * (4 if world == 1 else 1), "d2h_bytes_per_step": NR * 8 * S},
         "gpu_launches": launches,
         "roofline": roofline,
     }
@@ -362,7 +369,7 @@ def run_ours(args):
         q_host = d_q.cpu().numpy()
         handle.set_stream(None)
         t0 = time.perf_counter()
-        dec, avg_err, iters = handle.decode(q_host, size, size, B, wk, False)
+        dec, avg_err, iters = handle.decode(q_host, size, size, B, wk, mode)
         t_dec = time.perf_counter() - t0
         rec = ((dec.view(np.uint32) >> 16) & 0xFF).astype(np.float64)
         mse = float(np.mean((rec - plane.astype(np.float64)) ** 2))
@@ -370,14 +377,14 @@ def run_ours(args):
                           "ms_total_host_clock": t_dec * 1e3, "device_ms": handle.timings().total_ms,
                           "mpixel_per_s_per_sweep": size * size * iters / max(handle.timings().total_ms, 1e-9) / 1e3}
     if world == 1 and not args.no_cpu_baseline:
-        R, tcpu, t_pool = cpu_sample(plane, B, wk, 1, args.cpu_seconds)
-        v = R * ND / tcpu
+        R, tcpu, t_pool = cpu_sample(plane, B, wk, 1, args.cpu_seconds, args.iso)
+        v = R * ND * n_iso / tcpu
         line["cpu_baseline"] = {
             "value": v / 1e9, "unit": "Gevals/s", "cores": 1, "kind": "port",
             "host_cores": os.cpu_count(),
             "sample": f"first {R} of {NR} range blocks against the full pool, single thread like the reference "
                       f"(C restatement; JVM unavailable; codebook build {t_pool:.2f}s excluded)",
-            "full_image_seconds_extrapolated": NR * ND / v,
+            "full_image_seconds_extrapolated": NR * ND * n_iso / v,
         }
     print(json.dumps(line))
     if world > 1:

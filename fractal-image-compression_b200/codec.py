@@ -148,7 +148,7 @@ class Handle:
         self._check(fn(self._h, _ptr(a), W, H, B, wk, range_begin, range_end, _ptr(info), _ptr(q)))
         return info, q
 
-    def encode_planes_dev(self, d_planes: int, rgb: bool, W: int, H: int, B: int, wk: int, range_begin: int,
+    def encode_planes_dev(self, d_planes: int, rgb, W: int, H: int, B: int, wk: int, range_begin: int,
                           range_end: int, d_info: int | None, d_q: int | None):
         """Asynchronous device-pointer entry (fic_encode_planes_dev)."""
         self._check(self._L.fic_encode_planes_dev(self._h, C.c_void_p(d_planes), int(rgb), W, H, B, wk,
@@ -243,6 +243,7 @@ class FractalCompression:
     imageInfoRGB: np.ndarray | None = None   # FC:18
     _handle: Handle | None = None
     device = 0
+    isometries = False   # extension (not in the reference): 8 isometries per candidate domain, grey images only
 
     @classmethod
     def handle(cls) -> Handle:
@@ -268,9 +269,10 @@ class FractalCompression:
 
     @classmethod
     def encodeGrayScale(cls, input: RasterImage, out) -> RasterImage:  # FC:109-162
-        info, q = cls.handle().encode(input.argb, cls.blockgroesse, cls.widthKernel, rgb=False)
+        mode = _lib.FIC_MODE_GREY_ISO if cls.isometries else _lib.FIC_MODE_GREY
+        info, q = cls.handle().encode(input.argb, cls.blockgroesse, cls.widthKernel, rgb=mode)
         cls.imageInfo, cls._q = info, q
-        cls.writeData(out, 0, input.width, input.height)
+        cls.writeData(out, mode, input.width, input.height)
         return cls.getBestGeneratedCollage(input)
 
     @classmethod
@@ -282,12 +284,13 @@ class FractalCompression:
 
     @classmethod
     def writeData(cls, out, isRGB: int, width: int, height: int):  # FC:230-261
-        out.write(stream_write(cls._q, width, height, cls.blockgroesse, cls.widthKernel, bool(isRGB)))
+        out.write(stream_write(cls._q, width, height, cls.blockgroesse, cls.widthKernel, int(isRGB)))
         out.close()  # FC:259
 
     @classmethod
     def getBestGeneratedCollage(cls, originalImage: RasterImage) -> RasterImage:  # FC:269-300
-        out = cls.handle().collage(originalImage.argb, cls.imageInfo, cls.blockgroesse, cls.widthKernel, rgb=False)
+        mode = _lib.FIC_MODE_GREY_ISO if cls.imageInfo.shape[1] == 4 else _lib.FIC_MODE_GREY
+        out = cls.handle().collage(originalImage.argb, cls.imageInfo, cls.blockgroesse, cls.widthKernel, rgb=mode)
         return RasterImage.from_argb(out)
 
     @classmethod

@@ -315,7 +315,7 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     CU(cudaGetLastError());
     h->tm.engine = engine;
     h->tm.launches += launches;
-    h->tm.search_evals = (double)(j1 - j0) * (double)g.wk * (double)g.wk;
+    h->tm.search_evals = (double)(j1 - j0) * (double)g.wk * (double)g.wk * (double)g.n_iso;
     return FIC_OK;
 }
 

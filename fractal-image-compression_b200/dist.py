@@ -52,7 +52,7 @@ class ShardedEncoder:
             from .codec import Handle
 
             self._handle = Handle(planes.device.index or 0)
-        S = 5 if rgb else 3
+        S = (3, 5, 4)[int(rgb)]   # grey, RGB, grey + isometry index (extension)
         NR = (W // B) * (H // B)
         key = (NR, S, planes.device)
         if key not in self._bufs:
@@ -60,15 +60,15 @@ class ShardedEncoder:
                                torch.empty((NR, S), dtype=torch.int32, device=planes.device))
         info, q = self._bufs[key]
         self._handle.set_stream(torch.cuda.current_stream(planes.device).cuda_stream)
-        self._handle.encode_planes_dev(planes.data_ptr(), rgb, W, H, B, wk, j0, j1, info.data_ptr(), q.data_ptr())
+        self._handle.encode_planes_dev(planes.data_ptr(), int(rgb), W, H, B, wk, j0, j1, info.data_ptr(), q.data_ptr())
         return info, q
 
-    def encode(self, planes: torch.Tensor | None, rgb: bool, W: int, H: int, B: int, wk: int,
+    def encode(self, planes: torch.Tensor | None, rgb, W: int, H: int, B: int, wk: int,
                device: torch.device | str = "cpu"):
         """planes: uint8 [C, H, W] on rank 0 (ignored elsewhere).  Returns (info, q) tensors on rank 0
         (on `device`), None on the other ranks."""
-        C = 3 if rgb else 1
-        S = 5 if rgb else 3
+        C = 3 if int(rgb) == 1 else 1
+        S = (3, 5, 4)[int(rgb)]
         rpw, rph = W // B, H // B
         NR = rpw * rph
         if self.rank == 0:

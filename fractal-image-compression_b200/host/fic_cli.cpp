@@ -48,6 +48,11 @@ static void write_pnm(const char *path, const RasterImage &img)
 
 int main(int argc, char **argv)
 {
+    // a trailing "iso" selects the isometry extension for encode / roundtrip
+    if (argc > 2 && !strcmp(argv[argc - 1], "iso")) {
+        FractalCompression::isometries = true;
+        argc--;
+    }
     try {
         if (argc >= 4 && !strcmp(argv[1], "encode")) {
             if (argc > 4) FractalCompression::blockgroesse = atoi(argv[4]);
@@ -72,7 +77,7 @@ int main(int argc, char **argv)
             printf("MSE %.9g (%d iterations)\n", FractalCompression::getAvgError(), FractalCompression::lastIterations);
             return 0;
         }
-        fprintf(stderr, "usage: fic_cli encode in.pnm out.run [B] [wk] | decode in.run out.pnm | roundtrip in.pnm [B] [wk]\n");
+        fprintf(stderr, "usage: fic_cli encode in.pnm out.run [B] [wk] [iso] | decode in.run out.pnm | roundtrip in.pnm [B] [wk] [iso]\n");
         return 2;
     } catch (const std::exception &e) {
         fprintf(stderr, "fic_cli: %s\n", e.what());

@@ -31,6 +31,9 @@ public:
     static inline int widthKernel = 2;    // FC:15
     static inline float avgError = 0.0f;  // FC:20 (never reset between decodes)
     static inline int device = 0;
+    // Extension, not in the reference: try every candidate domain under the 8 isometries of the square
+    // (grey images only; codes gain a 4th int, the stream header carries 2 instead of 0).
+    static inline bool isometries = false;
 
     static float getAvgError() { return avgError; }  // FC:22-24
 
@@ -47,14 +50,14 @@ public:
     // FC:54-59 -> FC:109-162 / FC:171-219.  Writes the .run stream to `out`, returns the collage.
     static RasterImage encode(const RasterImage &in, std::ostream &out)
     {
-        const bool rgb = !isGreyScale(in);
-        const int S = rgb ? 5 : 3;
+        const int rgb = !isGreyScale(in) ? FIC_MODE_RGB : (isometries ? FIC_MODE_GREY_ISO : FIC_MODE_GREY);
+        const int S = rgb == FIC_MODE_RGB ? 5 : (rgb == FIC_MODE_GREY_ISO ? 4 : 3);
         int64_t nr = 0;
         check(fic_geometry(in.width, in.height, blockgroesse, widthKernel, &nr, nullptr), "fic_geometry");
         imageInfo.assign((size_t)nr * S, 0.0f);  // FC:124 / FC:185
         std::vector<int32_t> q((size_t)nr * S);
-        check((rgb ? fic_encode_rgb : fic_encode_grey)(handle(), in.argb.data(), in.width, in.height, blockgroesse,
-                                                       widthKernel, 0, nr, imageInfo.data(), q.data()),
+        auto entry = rgb == FIC_MODE_RGB ? fic_encode_rgb : (rgb == FIC_MODE_GREY_ISO ? fic_encode_grey_iso : fic_encode_grey);
+        check(entry(handle(), in.argb.data(), in.width, in.height, blockgroesse, widthKernel, 0, nr, imageInfo.data(), q.data()),
               "fic_encode");
         // FC:230-261 writeData
         std::vector<uint8_t> bytes(fic_stream_size(rgb, in.width, in.height, blockgroesse));

@@ -124,3 +124,35 @@ def test_iso_row_shards_and_large(fic, handle):
     for a, b in [(0, cut), (cut, NR)]:
         handle.encode(img, B, wk, rgb=fic.FIC_MODE_GREY_ISO, range_begin=a, range_end=b, info=i3, q=q3)
     assert (q3 == q).all() and float_bits_equal(i3, info)
+
+
+def test_iso_facades(tmp_path, fic, oracle, lena64):
+    """The isometry switch of the Python facade and of the C++ CLI produce the restatement's stream."""
+    import io
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    want = oracle.write_data(oracle.encode(lena64, 8, 5, iso=True), 64, 64, 8, 5, iso=True)
+    FC = fic.FractalCompression
+    FC.blockgroesse, FC.widthKernel, FC.isometries = 8, 5, True
+    try:
+        sink = fic.ByteSink()
+        collage = FC.encode(fic.RasterImage.from_argb(lena64), sink)
+        assert sink.getvalue() == want
+        assert (collage.argb == oracle.collage(lena64, oracle.encode(lena64, 8, 5, iso=True), 8, 5, iso=True)).all()
+        FC.avgError = np.float32(0.0)
+        dec = FC.decode(io.BytesIO(want))
+        oimg, oavg, _ = oracle.decode(want)
+        assert (dec.argb == oimg).all() and FC.getAvgError() == oavg
+    finally:
+        FC.blockgroesse, FC.widthKernel, FC.isometries = 8, 2, False
+    cli = os.path.join(ROOT, "fractal-image-compression_b200", "lib", "fic_cli")
+    if os.path.exists(cli):
+        pgm, run = tmp_path / "l.pgm", tmp_path / "l.run"
+        plane = ((lena64.view(np.uint32) >> 16) & 0xFF).astype(np.uint8)
+        with open(pgm, "wb") as f:
+            f.write(b"P5\n64 64\n255\n" + plane.tobytes())
+        subprocess.run([cli, "encode", str(pgm), str(run), "8", "5", "iso"], check=True, capture_output=True, text=True)
+        assert open(run, "rb").read() == want
