@@ -53,23 +53,26 @@ rank = dist.get_rank()
 W = H = 64; B = 8; wk = 13
 plane = fic.synth.structured(W, H, 5)
 argb = fic.synth.grey_to_argb(plane)
-def worker(planes, rgb, W, H, B, wk, j0, j1):      # test double: the CPU oracle computes this rank's rows
+def worker(planes, mode, W, H, B, wk, j0, j1):     # test double: the CPU oracle computes this rank's rows
     img = fic.synth.grey_to_argb(planes[0].numpy())
-    info = O.encode(img, B, wk, rgb=rgb, range_begin=j0, range_end=j1)
-    q = np.frombuffer(O.write_data(info, W, H, B, wk, rgb=rgb)[20:], ">i4").astype(np.int32).reshape(-1, 3)
+    iso = mode == fic.FIC_MODE_GREY_ISO
+    info = O.encode(img, B, wk, range_begin=j0, range_end=j1, iso=iso)
+    q = np.frombuffer(O.write_data(info, W, H, B, wk, iso=iso)[20:], ">i4").astype(np.int32).reshape(-1, 4 if iso else 3)
     return torch.from_numpy(info), torch.from_numpy(q.copy())
 enc = ShardedEncoder(worker=worker)
-planes = torch.from_numpy(argb_to_planes(argb, False)) if rank == 0 else None
-out = enc.encode(planes, False, W, H, B, wk, device="cpu")
-if rank == 0:
-    info, q = out
-    full = O.encode(argb, B, wk)
-    assert info.numpy().tobytes() == full.tobytes(), "sharded codes differ from the single-process encode"
-    want = O.write_data(full, W, H, B, wk)
-    assert fic.stream_write(q.numpy(), W, H, B, wk, rgb=False) == want
-    print("SHARDED_OK")
-else:
-    assert out is None
+for mode in (fic.FIC_MODE_GREY, fic.FIC_MODE_GREY_ISO):     # the reference's grey codes, and the isometry extension
+    iso = mode == fic.FIC_MODE_GREY_ISO
+    planes = torch.from_numpy(argb_to_planes(argb, False)) if rank == 0 else None
+    out = enc.encode(planes, mode, W, H, B, wk, device="cpu")
+    if rank == 0:
+        info, q = out
+        full = O.encode(argb, B, wk, iso=iso)
+        assert info.numpy().tobytes() == full.tobytes(), "sharded codes differ from the single-process encode"
+        want = O.write_data(full, W, H, B, wk, iso=iso)
+        assert fic.stream_write(q.numpy(), W, H, B, wk, rgb=mode) == want
+        print("SHARDED_OK", mode)
+    else:
+        assert out is None
 dist.destroy_process_group()
 '''
 
@@ -82,4 +85,4 @@ def test_world_size_2_gloo(tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", "29731", str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "SHARDED_OK" in r.stdout
+    assert "SHARDED_OK 0" in r.stdout and "SHARDED_OK 2" in r.stdout

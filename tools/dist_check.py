@@ -19,8 +19,8 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 rank, world = dist.get_rank(), dist.get_world_size()
 ok = True
-for W, B, rgb in [(1024, 8, False), (512, 4, False), (256, 8, True)]:
-    if rgb:
+for W, B, rgb in [(1024, 8, False), (512, 4, False), (256, 8, True), (512, 8, fic.FIC_MODE_GREY_ISO)]:
+    if rgb is True:
         planes_np = np.stack([fic.synth.structured(W, W, s) for s in (1, 2, 3)])
         wk = 2
     else:
@@ -33,7 +33,7 @@ for W, B, rgb in [(1024, 8, False), (512, 4, False), (256, 8, True)]:
     if rank == 0:
         info, q = out
         h = fic.Handle(local)
-        if rgb:
+        if rgb is True:
             a = planes_np.astype(np.uint32)
             argb = (0xFF000000 | (a[0] << 16) | (a[1] << 8) | a[2]).view(np.int32)
         else:
