@@ -71,6 +71,7 @@
 #include <cuda_fp16.h>
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cmath>
 #include <vector>
 
 #include "fic_device.cuh"
@@ -1032,7 +1033,11 @@ struct Plan {
     int64_t npos;   // ntiles * 128 sweep positions
 };
 
-// Split the domain sweep so that the unit count fills whole waves of num_sms CTAs.
+// Split the domain sweep of a super-block into n_chunks units.  More units fill the last wave of num_sms CTAs
+// better, but every unit starts its own running maximum, so a row collects about 2 * n_chunks * (ln(chunks per
+// list) + 0.58) flagged chunks for the refine step (records of a random sequence).  n_chunks minimises a small
+// cost model of search + refine time; its constants are B200 measurements (clocks per domain tile of
+// k_umma_search, whole-GPU nanoseconds per flagged chunk of k_umma_refine) -- only their ratio matters.
 inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p;
@@ -1041,12 +1046,16 @@ inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
     p.ntiles = (int)((g.ND + kTileN - 1) / kTileN);
     p.npos = (int64_t)p.ntiles * kTileN;
     p.n_chunks = 1;
-    double best_eff = 0;
+    const double tile_s = (g.B == 16 ? 4650.0 : (g.B == 8 ? 1550.0 : 1400.0)) / 1.9e9;
+    const double flag_s = 0.11e-9 * (g.n / 64.0) * (g.n > 64 ? 0.7 : 1.0);
+    double best_cost = 0;
     for (int c = 1; c <= 8 && c <= p.ntiles; c++) {
-        int64_t units = (int64_t)p.n_sb * c;
-        int64_t waves = (units + num_sms - 1) / num_sms;
-        double eff = (double)units / (double)(waves * num_sms);
-        if (eff > best_eff + 0.02) { best_eff = eff; p.n_chunks = c; }
+        const int64_t units = (int64_t)p.n_sb * c;
+        const int64_t waves = (units + num_sms - 1) / num_sms;
+        const double tiles_per_unit = (double)((p.ntiles + c - 1) / c);
+        const double flags_per_row = 2.0 * c * (log(2.0 * tiles_per_unit) + 0.58);
+        const double cost = (double)waves * tiles_per_unit * tile_s + (double)rows * flags_per_row * flag_s;
+        if (c == 1 || cost < best_cost * 0.98) { best_cost = cost; p.n_chunks = c; }
     }
     const uint64_t nch = (uint64_t)p.ntiles * kChunksPerTile;
     uint64_t m = (uint64_t)((double)nch * 0.6180339887498949) | 1u;  // golden-ratio stride, odd
