@@ -544,8 +544,8 @@ constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(
 template <int B, bool F16, int DBG, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
-              int32_t *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, int n_sb, int n_chunks, int ntiles,
-              int64_t rows_padded, int32_t *__restrict__ dump, int64_t dump_ld, volatile int *status,
+              int32_t *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, uint32_t *__restrict__ row_lb, int n_sb,
+              int n_chunks, int ntiles, int64_t rows_padded, int32_t *__restrict__ dump, int64_t dump_ld, volatile int *status,
               uint32_t lbo_bytes_a, uint32_t sbo_bytes_a, uint32_t lbo_bytes_b, uint32_t sbo_bytes_b)
 {
     using C = Cfg<B, F16>;
@@ -600,7 +600,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, a_phase = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                int sb = u / n_chunks, ch = u % n_chunks;
+                int sb = u % n_sb, ch = u / n_sb;  // chunk-major: see the epilogue (bounds carried between units)
                 int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
                 mbar_wait(BAR_A_EMPTY, a_phase ^ 1, status, 1);
                 mbar_expect_tx(BAR_A_FULL, L::A_SB_BYTES);
@@ -626,7 +626,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         const uint64_t a_desc0 = make_desc(smem_u32(sA), lbo_bytes_a, sbo_bytes_a);
         const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo_bytes_b, sbo_bytes_b);
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            int ch = u % n_chunks;
+            int ch = u / n_sb;
             int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
             mbar_wait(BAR_A_FULL, a_phase, status, 3);
             for (int t = t0; t < t1; t++) {
@@ -683,7 +683,10 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             }
         };
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            int sb = u / n_chunks, ch = u % n_chunks;
+            // Units are ordered chunk-major (u = ch * n_sb + sb): the units of one super-block run in different
+            // waves, so the lower bounds a row reached in an earlier unit (row_lb, global memory) can seed the
+            // later ones -- any earlier bound is a valid bound, a missed one only costs extra flags.
+            int sb = u % n_sb, ch = u / n_sb;
             int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
             // Running filter state of this thread's two rows (see the file header).  vR == 0: every
             // candidate scores error 0 and the first one wins (FC:677-678, FC:627) -> never flag.
@@ -707,6 +710,13 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 thresh[sl] = (vR == 0) ? __int_as_float(0x7f800000) : -1.0f;
                 lbmax[sl] = 0.0f;
                 tie_abs[sl] = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
+                if (ch > 0 && vR != 0) {  // bound reached by the earlier units of this row
+                    const float seed = __uint_as_float(*(volatile const uint32_t *)(row_lb + row[sl]));
+                    if (seed > 0.0f) {
+                        lbmax[sl] = seed;
+                        thresh[sl] = flag_threshold(seed, tie_abs[sl]);
+                    }
+                }
                 cnt[sl] = 0;
                 my_list[sl] = flag_list + (((int64_t)ch * rows_padded + row[sl]) * 2 + half) * kFlagCap;
             }
@@ -807,7 +817,10 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
 #pragma unroll
-            for (int sl = 0; sl < 2; sl++) flag_cnt[((int64_t)ch * rows_padded + row[sl]) * 2 + half] = cnt[sl];
+            for (int sl = 0; sl < 2; sl++) {
+                flag_cnt[((int64_t)ch * rows_padded + row[sl]) * 2 + half] = cnt[sl];
+                if (n_chunks > 1 && lbmax[sl] > 0.0f) atomicMax(row_lb + row[sl], __float_as_uint(lbmax[sl]));
+            }
         }
         if ((DBG & 8) && lane == 0 && dump) {
             int32_t *o = dump + ((int64_t)blockIdx.x * kEpiWarps + e) * 8;
@@ -1034,8 +1047,9 @@ struct Plan {
 };
 
 // Split the domain sweep of a super-block into n_chunks units.  More units fill the last wave of num_sms CTAs
-// better, but every unit starts its own running maximum, so a row collects about 2 * n_chunks * (ln(chunks per
-// list) + 0.58) flagged chunks for the refine step (records of a random sequence).  n_chunks minimises a small
+// better, but every unit adds flagged chunks for the refine step: the first unit of a row about
+// 2 * (ln(chunks per list) + 0.58) (records of a random sequence, two column halves), every later one -- seeded
+// with the bound the earlier ones reached -- about 2 * 1.5.  n_chunks minimises a small
 // cost model of search + refine time; its constants are B200 measurements (clocks per domain tile of
 // k_umma_search, whole-GPU nanoseconds per flagged chunk of k_umma_refine) -- only their ratio matters.
 inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
@@ -1053,7 +1067,7 @@ inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
         const int64_t units = (int64_t)p.n_sb * c;
         const int64_t waves = (units + num_sms - 1) / num_sms;
         const double tiles_per_unit = (double)((p.ntiles + c - 1) / c);
-        const double flags_per_row = 2.0 * c * (log(2.0 * tiles_per_unit) + 0.58);
+        const double flags_per_row = 2.0 * (log(2.0 * tiles_per_unit) + 0.58) + 2.0 * (c - 1) * 1.5;
         const double cost = (double)waves * tiles_per_unit * tile_s + (double)rows * flags_per_row * flag_s;
         if (c == 1 || cost < best_cost * 0.98) { best_cost = cost; p.n_chunks = c; }
     }
@@ -1096,9 +1110,9 @@ template <int B, bool F16>
 size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p = make_plan(g, rows, num_sms);
-    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap][vbest int2 (isometries)]
+    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap][vbest int2 (isometries)][row_lb u32]
     return (size_t)p.n_sb * Lay<B, F16>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 2 * 4 * (1 + kFlagCap) +
-           (size_t)p.rp * 8 + 1024;
+           (size_t)p.rp * 8 + (size_t)p.rp * 4 + 1024;
 }
 
 template <int B, bool F16>
@@ -1116,6 +1130,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     int32_t *flag_cnt = vR + rp;
     int32_t *flag_list = flag_cnt + rp * p.n_chunks * 2;
     int2 *vbest = (int2 *)(((uintptr_t)(flag_list + rp * p.n_chunks * 2 * kFlagCap) + 15) & ~(uintptr_t)15);
+    uint32_t *row_lb = (uint32_t *)(vbest + rp);  // per operand row: best lower bound of max x reached by finished units
     OpBLayout<B, F16> lay(g, p);
     int32_t *pos_dom = (int32_t *)(w.opB + lay.off_posdom);
     int32_t *pos_var = (int32_t *)(w.opB + lay.off_posvar);
@@ -1147,8 +1162,8 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     k_umma_pack_ranges<B, F16><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
     launches += 2;
     // 3. the fused search
-    using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int32_t *, int32_t *, int, int, int,
-                             int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
+    using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int32_t *, int32_t *, uint32_t *, int, int,
+                             int, int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
     KernelT kern = k_umma_search<B, F16, 0, false>;  // dbg (probe only): 1 / 3 strip the scoring / the TMEM loads too
     if (dump && !(dbg & 8u)) kern = k_umma_search<B, F16, 0, true>;
     else if ((dbg & 3u) == 1) kern = k_umma_search<B, F16, 1, false>;
@@ -1163,7 +1178,8 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     uint32_t lbo_a = 128, sbo_a = L::SBO_A, lbo_b = 128, sbo_b = L::SBO_B;
     if (variant == 1) { lbo_a = L::SBO_A; sbo_a = 128; lbo_b = L::SBO_B; sbo_b = 128; }  // probe only
     if (k0) cudaEventRecord(k0, s);
-    kern<<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, flag_list, flag_cnt, p.n_sb, p.n_chunks, p.ntiles, rp,
+    if (p.n_chunks > 1) cudaMemsetAsync(row_lb, 0, (size_t)rp * 4, s);
+    kern<<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, flag_list, flag_cnt, row_lb, p.n_sb, p.n_chunks, p.ntiles, rp,
                                                dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
     if (k1) cudaEventRecord(k1, s);
     // 4. exact refine of the flagged chunks
