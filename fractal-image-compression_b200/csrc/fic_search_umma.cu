@@ -545,7 +545,7 @@ template <int B, bool F16, int DBG, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
               int32_t *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, uint32_t *__restrict__ row_lb, int n_sb,
-              int n_chunks, int ntiles, int64_t rows_padded, int32_t *__restrict__ dump, int64_t dump_ld, volatile int *status,
+              int n_chunks, int ntiles, int iso_shift, int64_t rows_padded, int32_t *__restrict__ dump, int64_t dump_ld, volatile int *status,
               uint32_t lbo_bytes_a, uint32_t sbo_bytes_a, uint32_t lbo_bytes_b, uint32_t sbo_bytes_b)
 {
     using C = Cfg<B, F16>;
@@ -699,7 +699,9 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 #pragma unroll
             for (int sl = 0; sl < 2; sl++) {
-                sh_lb[sl] = smem_u32(s_lb + (qa + 2 * sl) * kBlockM + lq * 32 + lane);
+                // (isometry extension: the 8 operand rows of a range block compete for one winner and have the
+                // same vR, so they share one bound -- a chunk is flagged only if it can beat the best of all 8)
+                sh_lb[sl] = smem_u32(s_lb + (qa + 2 * sl) * kBlockM + (((lq * 32 + lane) >> iso_shift) << iso_shift));
                 if (half == 0) sts_u32(sh_lb[sl], 0u);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
@@ -711,7 +713,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 lbmax[sl] = 0.0f;
                 tie_abs[sl] = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
                 if (ch > 0 && vR != 0) {  // bound reached by the earlier units of this row
-                    const float seed = __uint_as_float(*(volatile const uint32_t *)(row_lb + row[sl]));
+                    const float seed = __uint_as_float(*(volatile const uint32_t *)(row_lb + ((row[sl] >> iso_shift) << iso_shift)));
                     if (seed > 0.0f) {
                         lbmax[sl] = seed;
                         thresh[sl] = flag_threshold(seed, tie_abs[sl]);
@@ -819,7 +821,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
 #pragma unroll
             for (int sl = 0; sl < 2; sl++) {
                 flag_cnt[((int64_t)ch * rows_padded + row[sl]) * 2 + half] = cnt[sl];
-                if (n_chunks > 1 && lbmax[sl] > 0.0f) atomicMax(row_lb + row[sl], __float_as_uint(lbmax[sl]));
+                if (n_chunks > 1 && lbmax[sl] > 0.0f)
+                    atomicMax(row_lb + ((row[sl] >> iso_shift) << iso_shift), __float_as_uint(lbmax[sl]));
             }
         }
         if ((DBG & 8) && lane == 0 && dump) {
@@ -1163,7 +1166,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     launches += 2;
     // 3. the fused search
     using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int32_t *, int32_t *, uint32_t *, int, int,
-                             int, int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
+                             int, int, int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
     KernelT kern = k_umma_search<B, F16, 0, false>;  // dbg (probe only): 1 / 3 strip the scoring / the TMEM loads too
     if (dump && !(dbg & 8u)) kern = k_umma_search<B, F16, 0, true>;
     else if ((dbg & 3u) == 1) kern = k_umma_search<B, F16, 1, false>;
@@ -1179,7 +1182,8 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     if (variant == 1) { lbo_a = L::SBO_A; sbo_a = 128; lbo_b = L::SBO_B; sbo_b = 128; }  // probe only
     if (k0) cudaEventRecord(k0, s);
     if (p.n_chunks > 1) cudaMemsetAsync(row_lb, 0, (size_t)rp * 4, s);
-    kern<<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, flag_list, flag_cnt, row_lb, p.n_sb, p.n_chunks, p.ntiles, rp,
+    kern<<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, flag_list, flag_cnt, row_lb, p.n_sb, p.n_chunks, p.ntiles,
+                                               g.n_iso > 1 ? 3 : 0, rp,
                                                dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
     if (k1) cudaEventRecord(k1, s);
     // 4. exact refine of the flagged chunks
