@@ -431,13 +431,18 @@ __device__ __noinline__ void mbar_timeout(volatile int *status, int code)
     }
     __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int *status, int code)
+// The polling loop lives out of line: the hot loops only carry the first try.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, volatile int *status, int code)
 {
-    if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 2000000000ll) mbar_timeout(status, code);
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int *status, int code)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(bar, parity, status, code);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
