@@ -163,10 +163,26 @@ struct Lay {
 // Flag threshold from the best lower bound lb of the row's max x = |kov| / sqrt(varD): candidates with
 // x^2 <= lb^2 * (1 - 2^-19) - vR^2 * 2^-21 cannot reach the minimal float error.  A non-positive right-hand
 // side means even x = 0 (kov == 0, flat domains) may tie with the best -> -1: everything is a candidate.
-__device__ __forceinline__ float flag_threshold(float lb, float tie_abs)
+__device__ __noinline__ float flag_threshold(float lb, float tie_abs)  // rare path: kept out of the hot loops
 {
     const float rad = lb * lb * kOneMinusEps - tie_abs;
     return rad > 0.0f ? sqrtf(rad) : -1.0f;
+}
+
+// Rare path of the search epilogue, out of line so that the hot loop stays short: record a flagged chunk and,
+// if it raises the row's lower bound, publish the bound (shared-memory slot `sh_lb`) and recompute the threshold.
+struct RowFilter { float thresh, lbmax; int cnt; };
+__device__ __noinline__ RowFilter flag_chunk(RowFilter st, float lb, float tie_abs, int32_t *list, int chunk_id, uint32_t sh_lb)
+{
+    if (st.cnt < kFlagCap) list[st.cnt] = chunk_id;
+    st.cnt++;
+    if (lb > st.lbmax) {
+        st.lbmax = lb;
+        asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(sh_lb), "r"(__float_as_uint(lb)) : "memory");  // positive floats order like their bits
+        const float rad = lb * lb * kOneMinusEps - tie_abs;
+        st.thresh = rad > 0.0f ? sqrtf(rad) : -1.0f;
+    }
+    return st;
 }
 
 // ---------------------------------------------------------------- sweep order --------
@@ -808,14 +824,11 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                             }
                         }
                         if (M * (cc ? bnd.z : bnd.x) > thresh[sl]) {  // may hold the winner or one of its float ties
-                            if (cnt[sl] < kFlagCap) my_list[sl][cnt[sl]] = t * kChunksPerTile + c;
-                            cnt[sl]++;
-                            const float lb = M * (cc ? bnd.w : bnd.y);
-                            if (lb > lbmax[sl]) {
-                                lbmax[sl] = lb;
-                                red_max_shared_u32(sh_lb[sl], __float_as_uint(lb));  // positive floats order like their bits
-                                thresh[sl] = flag_threshold(lb, tie_abs[sl]);
-                            }
+                            RowFilter st = {thresh[sl], lbmax[sl], cnt[sl]};
+                            st = flag_chunk(st, M * (cc ? bnd.w : bnd.y), tie_abs[sl], my_list[sl], t * kChunksPerTile + c, sh_lb[sl]);
+                            thresh[sl] = st.thresh;
+                            lbmax[sl] = st.lbmax;
+                            cnt[sl] = st.cnt;
                         }
                         tick(tk_m);
                     }
