@@ -65,8 +65,8 @@
 //               4 accumulators (128 rows x 128 domains = all 512 TMEM columns) x NS
 //               K-slices of tcgen05.mma, tcgen05.commit -> t_full[q]
 //   warp 2      TMEM allocator
-//   warps 4-19  epilogue: warp e owns TMEM lane quarter e % 4 and column half (e / 4) & 1
-//               of accumulators (e / 8) and (e / 8) + 2; one thread = two range rows
+//   warps 4-19  epilogue: warp e owns TMEM lane quarter e % 4 of accumulator e / 4; one thread = one
+//               range row, all 128 domains of a tile
 // A work unit is (super-block of 512 rows) x (1/n_chunks of the domain tiles).
 #include <cuda_fp16.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -172,13 +172,15 @@ __device__ __noinline__ float flag_threshold(float lb, float tie_abs)  // rare p
 // Rare path of the search epilogue, out of line so that the hot loop stays short: record a flagged chunk and,
 // if it raises the row's lower bound, publish the bound (shared-memory slot `sh_lb`) and recompute the threshold.
 struct RowFilter { float thresh, lbmax; int cnt; };
-__device__ __noinline__ RowFilter flag_chunk(RowFilter st, float lb, float tie_abs, int32_t *list, int chunk_id, uint32_t sh_lb)
+__device__ __noinline__ RowFilter flag_chunk(RowFilter st, float lb, float tie_abs, int32_t *list, int chunk_id, uint32_t sh_lb,
+                                             int publish)
 {
     if (st.cnt < kFlagCap) list[st.cnt] = chunk_id;
     st.cnt++;
     if (lb > st.lbmax) {
         st.lbmax = lb;
-        asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(sh_lb), "r"(__float_as_uint(lb)) : "memory");  // positive floats order like their bits
+        if (publish)  // positive floats order like their bits
+            asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(sh_lb), "r"(__float_as_uint(lb)) : "memory");
         const float rad = lb * lb * kOneMinusEps - tie_abs;
         st.thresh = rad > 0.0f ? sqrtf(rad) : -1.0f;
     }
@@ -597,7 +599,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         }
         for (int q = 0; q < kAccs; q++) {
             mbar_init(BAR_T_FULL(q), 1);
-            mbar_init(BAR_T_EMPTY(q), 2 * kEpiWarps / kAccs);  // 4 lane quarters x 2 column halves
+            mbar_init(BAR_T_EMPTY(q), kEpiWarps / kAccs);  // the 4 lane quarters of the accumulator
         }
         mbar_init(BAR_A_FULL, 1);
         mbar_init(BAR_A_EMPTY, 1);
@@ -683,14 +685,13 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        // Warp e: TMEM lane quarter lq = e % 4 (== warp % 4, the quarter this warp may access), column half
-        // `half` (64 of the 128 domains of a tile) of the two accumulators qa and qa + 2.  Two warps share
-        // each (accumulator, lane quarter), so an accumulator is drained in two chunk-times, and every warp
-        // alternates between two accumulators so that one is ready while the other is being refilled.
+        // Warp e: TMEM lane quarter lq = e % 4 (== warp % 4, the quarter this warp may access) of accumulator
+        // q = e / 4: one thread = one range row, all 128 domains of a tile.  Per tile a warp makes ONE visit (one
+        // t_full wait, four 32-column loads, one hand-back); the four warps of an SM sub-partition own the four
+        // accumulators, which the issuer completes 1/4 tile apart, so their work is naturally staggered.
         const int e = warp - 4;
-        const int lq = e & 3, kk = e >> 2;
-        const int half = kk & 1, qa = kk >> 1;
-        const uint32_t t_lane0 = tmem_base + ((uint32_t)(lq * 32) << 16) + half * 64;
+        const int lq = e & 3, q = e >> 2;
+        const uint32_t ta = tmem_base + ((uint32_t)(lq * 32) << 16) + q * kTileN;
         uint32_t stage = 0, phase = 0, tf_phase = 0;
         // DBG & 8 (probe only): per-warp cycle accounting of the epilogue phases.  tcgen05.wait::ld is a
         // scoreboard wait, so the TMEM latency shows up at the first use of the loaded registers ("math").
@@ -705,143 +706,128 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         };
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             // Units are ordered chunk-major (u = ch * n_sb + sb): the units of one super-block run in different
-            // waves, so the lower bounds a row reached in an earlier unit (row_lb, global memory) can seed the
+            // waves, so the lower bound a row reached in an earlier unit (row_lb, global memory) can seed the
             // later ones -- any earlier bound is a valid bound, a missed one only costs extra flags.
             int sb = u % n_sb, ch = u / n_sb;
             int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
-            // Running filter state of this thread's two rows (see the file header).  vR == 0: every
-            // candidate scores error 0 and the first one wins (FC:677-678, FC:627) -> never flag.
-            int64_t row[2];
-            float thresh[2], lbmax[2], tie_abs[2];
-            int cnt[2];
-            int32_t *my_list[2];
-            uint32_t sh_lb[2];  // shared-space address of the row's lower bound (shared by the two column halves)
-            // the previous unit's bounds are dead once all 16 epilogue warps are here; reset them
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-#pragma unroll
-            for (int sl = 0; sl < 2; sl++) {
-                // (isometry extension: the 8 operand rows of a range block compete for one winner and have the
-                // same vR, so they share one bound -- a chunk is flagged only if it can beat the best of all 8)
-                sh_lb[sl] = smem_u32(s_lb + (qa + 2 * sl) * kBlockM + (((lq * 32 + lane) >> iso_shift) << iso_shift));
-                if (half == 0) sts_u32(sh_lb[sl], 0u);
+            // Running filter state of this thread's row (see the file header).  vR == 0: every candidate
+            // scores error 0 and the first one wins (FC:677-678, FC:627) -> never flag.
+            const int64_t row = (int64_t)sb * kRowsPerSB + q * kBlockM + lq * 32 + lane;
+            const int vR = vRarr[row];
+            RowFilter st;
+            st.thresh = (vR == 0) ? __int_as_float(0x7f800000) : -1.0f;
+            st.lbmax = 0.0f;
+            st.cnt = 0;
+            const float tie_abs = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
+            // Isometry extension: the 8 operand rows of a range block (8 adjacent lanes) compete for one winner and
+            // have the same vR, so they share one bound through shared memory: a chunk is flagged only if it can
+            // beat the best of all 8.
+            const uint32_t sh_lb = smem_u32(s_lb + q * kBlockM + (((lq * 32 + lane) >> iso_shift) << iso_shift));
+            if (iso_shift) {
+                sts_u32(sh_lb, 0u);
+                __syncwarp();
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-#pragma unroll
-            for (int sl = 0; sl < 2; sl++) {
-                row[sl] = (int64_t)sb * kRowsPerSB + (qa + 2 * sl) * kBlockM + lq * 32 + lane;
-                const int vR = vRarr[row[sl]];
-                thresh[sl] = (vR == 0) ? __int_as_float(0x7f800000) : -1.0f;
-                lbmax[sl] = 0.0f;
-                tie_abs[sl] = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
-                if (ch > 0 && vR != 0) {  // bound reached by the earlier units of this row
-                    const float seed = __uint_as_float(*(volatile const uint32_t *)(row_lb + ((row[sl] >> iso_shift) << iso_shift)));
-                    if (seed > 0.0f) {
-                        lbmax[sl] = seed;
-                        thresh[sl] = flag_threshold(seed, tie_abs[sl]);
-                    }
+            if (ch > 0 && vR != 0) {  // bound reached by the earlier units of this row
+                const float seed = __uint_as_float(*(volatile const uint32_t *)(row_lb + ((row >> iso_shift) << iso_shift)));
+                if (seed > 0.0f) {
+                    st.lbmax = seed;
+                    st.thresh = flag_threshold(seed, tie_abs);
                 }
-                cnt[sl] = 0;
-                my_list[sl] = flag_list + (((int64_t)ch * rows_padded + row[sl]) * 2 + half) * kFlagCap;
             }
+            int32_t *const list0 = flag_list + (((int64_t)ch * rows_padded + row) * 2) * kFlagCap;
+            int cnt0 = 0, cnt1 = 0;  // entries of the two lists (column halves) of this (row, unit)
             if (DBG & 8) tk_mark = (uint32_t)clock();
             for (int t = t0; t < t1; t++) {
                 mbar_wait(BAR_B_FULL(stage), phase, status, 6);
-                // (rhi, rlo) of this warp's two chunks of the tile
-                const float4 bnd = lds_f4(smem_u32(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES) + half * 16);
+                // (rhi, rlo) of the tile's four chunks
+                const uint32_t bnd_addr = smem_u32(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES);
+                const float4 bnd01 = lds_f4(bnd_addr), bnd23 = lds_f4(bnd_addr + 16);
                 tick(tk_b);
+                mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
+                tc_fence_after();
+                // Every warp passes here; the warps of accumulator 3 after the tile's last commit: by the time all
+                // 16 have arrived every MMA that reads this tile's shared-memory stage has completed, and the
+                // bounds are in registers.  Release the stage now, not at the end of the tile.
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR_B_EMPTY(stage));
+                if (iso_shift) {  // adopt a better bound found by another isometry of the same range block
+                    const float other = __uint_as_float(lds_volatile_u32(sh_lb));
+                    if (other > st.lbmax) {
+                        st.lbmax = other;
+                        st.thresh = flag_threshold(other, tie_abs);
+                    }
+                }
+                tick(tk_t);
 #pragma unroll
-                for (int sl = 0; sl < 2; sl++) {
-                    const int q = qa + 2 * sl;
-                    const uint32_t ta = t_lane0 + q * kTileN;
-                    mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
-                    tc_fence_after();
-                    if (sl == 1) {
-                        // Every MMA that reads this tile's shared-memory stage has completed (all 16 warps pass
-                        // here, half of them after the tile's last commit) and its bounds are in registers:
-                        // release the stage now, not at the end of the tile, so the next TMA starts earlier.
+                for (int c = 0; c < kChunksPerTile; c++) {
+                    uint32_t v[32];
+                    if (!(DBG & 2)) {
+                        tmem_ld32(ta + c * 32, v);
+                        tmem_ld_wait();
+                    }
+                    tick(tk_l);
+                    if (c == kChunksPerTile - 1) {
+                        // last read of accumulator q for this tile: hand it back
+                        tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(BAR_B_EMPTY(stage));
+                        if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
                     }
-                    {   // adopt a better lower bound found by the warp that scans the other column half
-                        const float other = __uint_as_float(lds_volatile_u32(sh_lb[sl]));
-                        if (other > lbmax[sl]) {
-                            lbmax[sl] = other;
-                            thresh[sl] = flag_threshold(other, tie_abs[sl]);
+                    if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring
+                    float M;  // max |kov| over the chunk, exact
+                    if (F16) {
+                        // binary32 accumulators holding exact integers.  FMNMX3 takes |.| on all three
+                        // operands: a 3-input tree over 32 values is 16 instructions (four chains of 3, then 4).
+                        auto av = [&](int k) { return fabsf(__uint_as_float(v[k])); };
+                        float c4[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            c4[i] = fmaxf(fmaxf(av(8 * i), av(8 * i + 1)), av(8 * i + 2));
+                            c4[i] = fmaxf(c4[i], fmaxf(av(8 * i + 3), av(8 * i + 4)));
+                            c4[i] = fmaxf(c4[i], fmaxf(av(8 * i + 5), av(8 * i + 6)));
+                        }
+                        const float m01 = fmaxf(fmaxf(c4[0], c4[1]), av(7));
+                        const float m23 = fmaxf(fmaxf(c4[2], c4[3]), av(15));
+                        M = fmaxf(fmaxf(fmaxf(m01, m23), av(23)), av(31));
+                    } else {
+                        int mx0 = 0, mn0 = 0, mx1 = 0, mn1 = 0;  // two independent chains each: ALU latency
+#pragma unroll
+                        for (int k = 0; k < 32; k += 4) {
+                            mx0 = max(mx0, max((int)v[k], (int)v[k + 1]));
+                            mn0 = min(mn0, min((int)v[k], (int)v[k + 1]));
+                            mx1 = max(mx1, max((int)v[k + 2], (int)v[k + 3]));
+                            mn1 = min(mn1, min((int)v[k + 2], (int)v[k + 3]));
+                        }
+                        M = __int2float_rn(max(max(mx0, mx1), -min(mn0, mn1)));
+                    }
+                    if (DUMP) {
+#pragma unroll
+                        for (int k = 0; k < 32; k++) {
+                            int iv = (int)v[k];
+                            if (F16) {  // a non-integral accumulator must fail the probe's check
+                                const float f = __uint_as_float(v[k]);
+                                iv = (f == rintf(f) && fabsf(f) < 2.0e9f) ? (int)f : (int)0x80000000;
+                            }
+                            dump[row * dump_ld + (int64_t)t * kTileN + c * 32 + k] = iv;
                         }
                     }
-                    tick(tk_t);
-#pragma unroll
-                    for (int cc = 0; cc < 2; cc++) {
-                        uint32_t v[32];
-                        if (!(DBG & 2)) {
-                            tmem_ld32(ta + cc * 32, v);
-                            tmem_ld_wait();
-                        }
-                        tick(tk_l);
-                        if (cc == 1) {
-                            // last read of this half of accumulator q for this tile: hand it back
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
-                        }
-                        if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring
-                        float M;  // max |kov| over the chunk, exact
-                        if (F16) {
-                            // binary32 accumulators holding exact integers.  FMNMX3 takes |.| on all three
-                            // operands: a 3-input tree over 32 values is 16 instructions (four chains of 3, then 4).
-                            auto av = [&](int k) { return fabsf(__uint_as_float(v[k])); };
-                            float c4[4];
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                c4[i] = fmaxf(fmaxf(av(8 * i), av(8 * i + 1)), av(8 * i + 2));
-                                c4[i] = fmaxf(c4[i], fmaxf(av(8 * i + 3), av(8 * i + 4)));
-                                c4[i] = fmaxf(c4[i], fmaxf(av(8 * i + 5), av(8 * i + 6)));
-                            }
-                            const float m01 = fmaxf(fmaxf(c4[0], c4[1]), av(7));
-                            const float m23 = fmaxf(fmaxf(c4[2], c4[3]), av(15));
-                            M = fmaxf(fmaxf(fmaxf(m01, m23), av(23)), av(31));
-                        } else {
-                            int mx0 = 0, mn0 = 0, mx1 = 0, mn1 = 0;  // two independent chains each: ALU latency
-#pragma unroll
-                            for (int k = 0; k < 32; k += 4) {
-                                mx0 = max(mx0, max((int)v[k], (int)v[k + 1]));
-                                mn0 = min(mn0, min((int)v[k], (int)v[k + 1]));
-                                mx1 = max(mx1, max((int)v[k + 2], (int)v[k + 3]));
-                                mn1 = min(mn1, min((int)v[k + 2], (int)v[k + 3]));
-                            }
-                            M = __int2float_rn(max(max(mx0, mx1), -min(mn0, mn1)));
-                        }
-                        const int c = half * 2 + cc;                   // chunk of the tile
-                        if (DUMP) {
-#pragma unroll
-                            for (int k = 0; k < 32; k++) {
-                                int iv = (int)v[k];
-                                if (F16) {  // a non-integral accumulator must fail the probe's check
-                                    const float f = __uint_as_float(v[k]);
-                                    iv = (f == rintf(f) && fabsf(f) < 2.0e9f) ? (int)f : (int)0x80000000;
-                                }
-                                dump[row[sl] * dump_ld + (int64_t)t * kTileN + c * 32 + k] = iv;
-                            }
-                        }
-                        if (M * (cc ? bnd.z : bnd.x) > thresh[sl]) {  // may hold the winner or one of its float ties
-                            RowFilter st = {thresh[sl], lbmax[sl], cnt[sl]};
-                            st = flag_chunk(st, M * (cc ? bnd.w : bnd.y), tie_abs[sl], my_list[sl], t * kChunksPerTile + c, sh_lb[sl]);
-                            thresh[sl] = st.thresh;
-                            lbmax[sl] = st.lbmax;
-                            cnt[sl] = st.cnt;
-                        }
-                        tick(tk_m);
+                    const float rhi = c == 0 ? bnd01.x : (c == 1 ? bnd01.z : (c == 2 ? bnd23.x : bnd23.z));
+                    const float rlo = c == 0 ? bnd01.y : (c == 1 ? bnd01.w : (c == 2 ? bnd23.y : bnd23.w));
+                    if (M * rhi > st.thresh) {  // may hold the winner or one of its float ties
+                        // the refine step reads two lists per (row, unit), one per column half, as the layout of
+                        // the earlier two-warps-per-accumulator mapping had it
+                        st.cnt = c < 2 ? cnt0 : cnt1;
+                        st = flag_chunk(st, M * rlo, tie_abs, list0 + (c >> 1) * kFlagCap, t * kChunksPerTile + c, sh_lb, iso_shift);
+                        if (c < 2) cnt0 = st.cnt;
+                        else cnt1 = st.cnt;
                     }
+                    tick(tk_m);
                 }
                 tf_phase ^= 1;
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
-#pragma unroll
-            for (int sl = 0; sl < 2; sl++) {
-                flag_cnt[((int64_t)ch * rows_padded + row[sl]) * 2 + half] = cnt[sl];
-                if (n_chunks > 1 && lbmax[sl] > 0.0f)
-                    atomicMax(row_lb + ((row[sl] >> iso_shift) << iso_shift), __float_as_uint(lbmax[sl]));
-            }
+            flag_cnt[((int64_t)ch * rows_padded + row) * 2] = cnt0;
+            flag_cnt[((int64_t)ch * rows_padded + row) * 2 + 1] = cnt1;
+            if (n_chunks > 1 && st.lbmax > 0.0f) atomicMax(row_lb + ((row >> iso_shift) << iso_shift), __float_as_uint(st.lbmax));
         }
         if ((DBG & 8) && lane == 0 && dump) {
             int32_t *o = dump + ((int64_t)blockIdx.x * kEpiWarps + e) * 8;
