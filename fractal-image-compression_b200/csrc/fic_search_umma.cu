@@ -99,6 +99,7 @@ struct Cfg;
 template <>
 struct Cfg<8, false> {
     static constexpr int n = 64;
+    static constexpr bool KSPLIT = false;
     static constexpr int KS_A = 3;   // physical A K-slices: r[0:32] r[32:64] [rmean rmean 0..]
     static constexpr int KS_B = 5;   // h[0:32] h[32:64] l[0:32] l[32:64] [-alpha 0..]
     static constexpr int NS = 5;     // MMA K-slices
@@ -109,6 +110,7 @@ struct Cfg<8, false> {
 template <>
 struct Cfg<4, false> {
     static constexpr int n = 16;
+    static constexpr bool KSPLIT = false;
     static constexpr int KS_A = 2;   // [r r] [rmean 0..]
     static constexpr int KS_B = 2;   // [h l] [-alpha 0..]
     static constexpr int NS = 2;
@@ -119,16 +121,23 @@ struct Cfg<4, false> {
 template <>
 struct Cfg<16, false> {
     static constexpr int n = 256;
+    // The A super-block (144 KB) leaves room for 72 KB of domain operands, not for two whole 68 KB tiles.  A tile
+    // therefore travels as two parts, P0 = [h (8 slices) | -alpha (1 slice)] + the tile's bounds and P1 = [l (8
+    // slices)], through a ring of two 36 KB slots: the copy of one part overlaps the MMAs on the other, and P1 is
+    // neither copied nor multiplied when the tile's low digits are all zero.
+    static constexpr bool KSPLIT = true;
+    static constexpr int KS_P0 = 9, KS_P1 = 8;
     static constexpr int KS_A = 9;   // r[0:256] (8 slices) [rmean 0..]
-    static constexpr int KS_B = 17;  // h (8 slices) l (8 slices) [-alpha 0..]
+    static constexpr int KS_B = 17;  // h (8 slices) l (8 slices) [-alpha 0..] (K-slices per tile, both parts)
     static constexpr int NS = 17;
-    static constexpr int NSTAGE = 1; // A super-block 144 KB + one 68 KB domain tile fill shared memory
+    static constexpr int NSTAGE = 2; // part slots
     __host__ __device__ static constexpr int amap(int s) { return s < 16 ? (s & 7) : 8; }
     __host__ __device__ static constexpr bool is_l_slice(int s) { return s >= 8 && s < 16; }
 };
 template <>
 struct Cfg<8, true> {
     static constexpr int n = 64;
+    static constexpr bool KSPLIT = false;
     static constexpr int KS_A = 4;   // (r - rmean)[0:64] as binary16: 4 slices of 16 elements
     static constexpr int KS_B = 4;   // (d - dmean)[0:64] as binary16
     static constexpr int NS = 4;
@@ -139,6 +148,7 @@ struct Cfg<8, true> {
 template <>
 struct Cfg<4, true> {
     static constexpr int n = 16;
+    static constexpr bool KSPLIT = false;
     static constexpr int KS_A = 1;
     static constexpr int KS_B = 1;
     static constexpr int NS = 1;
@@ -147,16 +157,30 @@ struct Cfg<4, true> {
     __host__ __device__ static constexpr bool is_l_slice(int) { return false; }
 };
 
+template <class C>
+constexpr int ksplit_p0()
+{
+    if constexpr (C::KSPLIT) return C::KS_P0;
+    else return C::KS_B;
+}
+
 template <int B, bool F16>
 struct Lay {
     using C = Cfg<B, F16>;
     static constexpr int SBO_A = C::KS_A * 256;
-    static constexpr int SBO_B = C::KS_B * 256;
     static constexpr int A_BLOCK_BYTES = (kBlockM / 8) * SBO_A;
     static constexpr int A_SB_BYTES = kAccs * A_BLOCK_BYTES;
+    // Domain tile blob in global memory.  Unsplit: [operand, SBO_B between 8-row groups][bounds + flag].
+    // Split (Cfg::KSPLIT): [part P0, SBO_B][bounds + flag][part P1, SBO_P1].  B_OP_BYTES is the offset of the bounds.
+    static constexpr int KS0 = ksplit_p0<C>();
+    static constexpr int SBO_B = KS0 * 256;
+    static constexpr int SBO_P1 = (C::KS_B - KS0) * 256;
     static constexpr int B_OP_BYTES = (kTileN / 8) * SBO_B;
-    static constexpr int B_TILE_BYTES = B_OP_BYTES + kBoundBytes;
-    static constexpr int SMEM_BYTES = A_SB_BYTES + C::NSTAGE * B_TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+    static constexpr int P0_BYTES = B_OP_BYTES + kBoundBytes;
+    static constexpr int P1_BYTES = (kTileN / 8) * SBO_P1;
+    static constexpr int B_TILE_BYTES = P0_BYTES + P1_BYTES;
+    static constexpr int SLOT_BYTES = C::KSPLIT ? ((P0_BYTES + 127) / 128) * 128 : B_TILE_BYTES;  // one ring entry in shared memory
+    static constexpr int SMEM_BYTES = A_SB_BYTES + C::NSTAGE * SLOT_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
                                       kRowsPerSB * 4 /*per-row lower bound shared by the two column halves*/;
 };
 
@@ -247,14 +271,20 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
     const int64_t tile = pos / kTileN;
     const int row = (int)(pos % kTileN);
     const int64_t sp = sweep_to_sorted(pos, mult, ntiles * kChunksPerTile);
+    constexpr bool KSPLIT = Cfg<B, F16>::KSPLIT;
     uint8_t *blob = opB + tile * L::B_TILE_BYTES;
     uint8_t *rowp = blob + (row >> 3) * L::SBO_B + (row & 7) * 16;
-    constexpr int NCH = Cfg<B, F16>::KS_B * 2;  // 16-byte chunks per row
+    // K-split tiles keep the low digits in a second part behind the bounds (see Lay)
+    uint8_t *rowp1 = blob + L::P0_BYTES + (row >> 3) * L::SBO_P1 + (row & 7) * 16;
+    constexpr int NCH = L::KS0 * 2;                              // 16-byte chunks per row (of part P0)
+    constexpr int NCH1 = (Cfg<B, F16>::KS_B - L::KS0) * 2;      // ... of part P1
     float rsd_hi = 0.0f, rsd_lo = __int_as_float(0x7f800000);
     int any_l = 0;
     if (sp >= g.ND) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int c = 0; c < NCH1; c++) *(uint4 *)(rowp1 + c * 128) = make_uint4(0, 0, 0, 0);
         pos_dom[pos] = -1;
         pos_var[pos] = 0;
         pos_sum[pos] = 0;
@@ -304,15 +334,17 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
                     lw[w] = pack4(lv[0], lv[1], lv[2], lv[3]);
                 }
                 *(uint4 *)(rowp + c * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *(uint4 *)(rowp + (PCH + c) * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                if (KSPLIT) *(uint4 *)(rowp1 + c * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                else *(uint4 *)(rowp + (PCH + c) * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
         }
         if (!F16) {
             // -alpha in two s8 columns (alpha <= n - 1 = 255 at B = 16); A carries rmean in both
             const int alpha = dsum[j] - n * dmean;
             const int a1 = alpha >> 1, a2 = alpha - a1;
-            *(uint4 *)(rowp + (2 * PCH) * 128) = make_uint4((uint32_t)((-a1) & 0xff) | ((uint32_t)((-a2) & 0xff) << 8), 0, 0, 0);
-            *(uint4 *)(rowp + (2 * PCH + 1) * 128) = make_uint4(0, 0, 0, 0);
+            constexpr int ACH = KSPLIT ? PCH : 2 * PCH;  // first 16-byte chunk of the alpha K-slice
+            *(uint4 *)(rowp + ACH * 128) = make_uint4((uint32_t)((-a1) & 0xff) | ((uint32_t)((-a2) & 0xff) << 8), 0, 0, 0);
+            *(uint4 *)(rowp + (ACH + 1) * 128) = make_uint4(0, 0, 0, 0);
         }
         pos_dom[pos] = (int32_t)j;
         pos_var[pos] = varD;
@@ -579,7 +611,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     uint8_t *sB = smem + L::A_SB_BYTES;
-    uint64_t *bars = (uint64_t *)(sB + NSTAGE * L::B_TILE_BYTES);
+    uint64_t *bars = (uint64_t *)(sB + NSTAGE * L::SLOT_BYTES);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR_B_FULL = [&](int s) { return bar0 + 8u * s; };
     auto BAR_B_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
@@ -595,7 +627,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NSTAGE; s++) {
             mbar_init(BAR_B_FULL(s), 1);
-            mbar_init(BAR_B_EMPTY(s), kEpiWarps);
+            mbar_init(BAR_B_EMPTY(s), C::KSPLIT ? 1 : kEpiWarps);  // K-split: released by the MMA issuer's commit alone
         }
         for (int q = 0; q < kAccs; q++) {
             mbar_init(BAR_T_FULL(q), 1);
@@ -629,11 +661,26 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 mbar_expect_tx(BAR_A_FULL, L::A_SB_BYTES);
                 bulk_g2s(smem_u32(sA), opA + (int64_t)sb * L::A_SB_BYTES, L::A_SB_BYTES, BAR_A_FULL);
                 for (int t = t0; t < t1; t++) {
-                    mbar_wait(BAR_B_EMPTY(stage), phase ^ 1, status, 2);
-                    mbar_expect_tx(BAR_B_FULL(stage), L::B_TILE_BYTES);
-                    bulk_g2s(smem_u32(sB + stage * L::B_TILE_BYTES), opB + (int64_t)t * L::B_TILE_BYTES,
-                             L::B_TILE_BYTES, BAR_B_FULL(stage));
-                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    const uint8_t *blob = opB + (int64_t)t * L::B_TILE_BYTES;
+                    if (C::KSPLIT) {
+                        // part P0 (high digits, -alpha, bounds), then part P1 (low digits) unless they are all zero
+                        mbar_wait(BAR_B_EMPTY(stage), phase ^ 1, status, 2);
+                        mbar_expect_tx(BAR_B_FULL(stage), L::P0_BYTES);
+                        bulk_g2s(smem_u32(sB + stage * L::SLOT_BYTES), blob, L::P0_BYTES, BAR_B_FULL(stage));
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        const uint32_t has_l = __ldg((const uint32_t *)(blob + L::B_OP_BYTES + kChunksPerTile * 8));
+                        if (has_l) {
+                            mbar_wait(BAR_B_EMPTY(stage), phase ^ 1, status, 2);
+                            mbar_expect_tx(BAR_B_FULL(stage), L::P1_BYTES);
+                            bulk_g2s(smem_u32(sB + stage * L::SLOT_BYTES), blob + L::P0_BYTES, L::P1_BYTES, BAR_B_FULL(stage));
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        }
+                    } else {
+                        mbar_wait(BAR_B_EMPTY(stage), phase ^ 1, status, 2);
+                        mbar_expect_tx(BAR_B_FULL(stage), L::B_TILE_BYTES);
+                        bulk_g2s(smem_u32(sB + stage * L::SLOT_BYTES), blob, L::B_TILE_BYTES, BAR_B_FULL(stage));
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    }
                 }
                 a_phase ^= 1;
             }
@@ -655,9 +702,55 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             for (int t = t0; t < t1; t++) {
                 mbar_wait(BAR_B_FULL(stage), phase, status, 4);
                 tc_fence_after();
-                const uint64_t b_desc = b_desc0 + (uint64_t)((stage * L::B_TILE_BYTES) >> 4);
                 // tile flag written by k_umma_pack_domains: 0 -> every low digit of the tile is zero
-                const uint32_t has_l = *(volatile const uint32_t *)(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES + kChunksPerTile * 8);
+                const uint32_t has_l = *(volatile const uint32_t *)(sB + stage * L::SLOT_BYTES + L::B_OP_BYTES + kChunksPerTile * 8);
+                if (C::KSPLIT) {
+                    // part P0: K-slices 0 .. KS0-1 of every accumulator; the slot is released as soon as these MMAs
+                    // have read it (commit), so that the next copy overlaps the MMAs on part P1 / the next tile
+                    const uint64_t b0 = make_desc(smem_u32(sB + stage * L::SLOT_BYTES), 128, L::SBO_B);
+#pragma unroll
+                    for (int q = 0; q < kAccs; q++) {
+                        mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ 1, status, 5);
+                        tc_fence_after();
+                        if (elected) {
+#pragma unroll
+                            for (int s = 0; s < L::KS0; s++) {
+                                if ((DBG & 4) && t != t0) continue;  // probe only: epilogue without the tensor pipe
+                                const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + s * 256) >> 4);  // r slice s; s = 8: rmean
+                                tc_mma_i8(tmem_base + q * kTileN, ad, b0 + (uint64_t)((s * 256) >> 4), kIdesc, s > 0 ? 1u : 0u);
+                            }
+                            if (!has_l) tc_commit(BAR_T_FULL(q));
+                        }
+                        __syncwarp();
+                        t_phase ^= 1u << q;
+                    }
+                    if (elected) tc_commit(BAR_B_EMPTY(stage));
+                    __syncwarp();
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    if (has_l) {
+                        mbar_wait(BAR_B_FULL(stage), phase, status, 4);
+                        tc_fence_after();
+                        const uint64_t b1 = make_desc(smem_u32(sB + stage * L::SLOT_BYTES), 128, L::SBO_P1);
+#pragma unroll
+                        for (int q = 0; q < kAccs; q++) {
+                            if (elected) {
+#pragma unroll
+                                for (int s = 0; s < C::KS_B - L::KS0; s++) {
+                                    if ((DBG & 4) && t != t0) continue;
+                                    const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + s * 256) >> 4);  // r slice s again
+                                    tc_mma_i8(tmem_base + q * kTileN, ad, b1 + (uint64_t)((s * 256) >> 4), kIdesc, 1u);
+                                }
+                                tc_commit(BAR_T_FULL(q));
+                            }
+                            __syncwarp();
+                        }
+                        if (elected) tc_commit(BAR_B_EMPTY(stage));
+                        __syncwarp();
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+                    continue;
+                }
+                const uint64_t b_desc = b_desc0 + (uint64_t)((stage * L::SLOT_BYTES) >> 4);
 #pragma unroll
                 for (int q = 0; q < kAccs; q++) {
                     mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ 1, status, 5);
@@ -737,11 +830,31 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             int32_t *const list0 = flag_list + (((int64_t)ch * rows_padded + row) * 2) * kFlagCap;
             int cnt0 = 0, cnt1 = 0;  // entries of the two lists (column halves) of this (row, unit)
             if (DBG & 8) tk_mark = (uint32_t)clock();
+            // K-split tiles: the bounds come from the tile blob in global memory (the shared-memory slot belongs to
+            // the MMA issuer alone), fetched one tile ahead
+            float4 nb01 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), nb23 = nb01;
+            if (C::KSPLIT && t0 < t1) {
+                const float4 *gb = (const float4 *)(opB + (int64_t)t0 * L::B_TILE_BYTES + L::B_OP_BYTES);
+                nb01 = __ldg(gb);
+                nb23 = __ldg(gb + 1);
+            }
             for (int t = t0; t < t1; t++) {
-                mbar_wait(BAR_B_FULL(stage), phase, status, 6);
                 // (rhi, rlo) of the tile's four chunks
-                const uint32_t bnd_addr = smem_u32(sB + stage * L::B_TILE_BYTES + L::B_OP_BYTES);
-                const float4 bnd01 = lds_f4(bnd_addr), bnd23 = lds_f4(bnd_addr + 16);
+                float4 bnd01, bnd23;
+                if (C::KSPLIT) {
+                    bnd01 = nb01;
+                    bnd23 = nb23;
+                    if (t + 1 < t1) {
+                        const float4 *gb = (const float4 *)(opB + (int64_t)(t + 1) * L::B_TILE_BYTES + L::B_OP_BYTES);
+                        nb01 = __ldg(gb);
+                        nb23 = __ldg(gb + 1);
+                    }
+                } else {
+                    mbar_wait(BAR_B_FULL(stage), phase, status, 6);
+                    const uint32_t bnd_addr = smem_u32(sB + stage * L::SLOT_BYTES + L::B_OP_BYTES);
+                    bnd01 = lds_f4(bnd_addr);
+                    bnd23 = lds_f4(bnd_addr + 16);
+                }
                 tick(tk_b);
                 mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
                 tc_fence_after();
@@ -749,7 +862,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 // 16 have arrived every MMA that reads this tile's shared-memory stage has completed, and the
                 // bounds are in registers.  Release the stage now, not at the end of the tile.
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR_B_EMPTY(stage));
+                if (!C::KSPLIT && lane == 0) mbar_arrive(BAR_B_EMPTY(stage));
                 if (iso_shift) {  // adopt a better bound found by another isometry of the same range block
                     const float other = __uint_as_float(lds_volatile_u32(sh_lb));
                     if (other > st.lbmax) {
