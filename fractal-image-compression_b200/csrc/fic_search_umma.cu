@@ -261,7 +261,7 @@ template <int B, bool F16>
 __global__ void __launch_bounds__(128)
 k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
                     const int32_t *__restrict__ dsq, const int32_t *__restrict__ perm, uint8_t *__restrict__ opB,
-                    int32_t *__restrict__ pos_dom, int32_t *__restrict__ pos_var, int32_t *__restrict__ pos_sum,
+                    int32_t *__restrict__ pos_dom, int4 *__restrict__ pos_info,
                     uint8_t *__restrict__ pos_raw, int64_t *__restrict__ dom0_pos, int *__restrict__ unsupported,
                     Geom g, int64_t ntiles, uint32_t mult)
 {
@@ -286,8 +286,7 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
 #pragma unroll
         for (int c = 0; c < NCH1; c++) *(uint4 *)(rowp1 + c * 128) = make_uint4(0, 0, 0, 0);
         pos_dom[pos] = -1;
-        pos_var[pos] = 0;
-        pos_sum[pos] = 0;
+        pos_info[pos] = make_int4(-1, 0, 0, 0);
     } else {
         const int64_t j = perm[sp];
         const int gx = (int)(j % g.dpw), gy = (int)(j / g.dpw);
@@ -347,8 +346,7 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
             *(uint4 *)(rowp + (ACH + 1) * 128) = make_uint4(0, 0, 0, 0);
         }
         pos_dom[pos] = (int32_t)j;
-        pos_var[pos] = varD;
-        pos_sum[pos] = dsum[j];
+        pos_info[pos] = make_int4((int32_t)j, varD, dsum[j], 0);  // what the refine step needs, in one 16-byte load
         if (j == 0) *dom0_pos = pos;  // the refine step always evaluates domain 0
         if (varD > 0) {  // flat domains have kov == 0: they never set a chunk's max |kov|
             float r = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn((double)varD)));
@@ -1056,7 +1054,7 @@ __device__ __forceinline__ int refine_kov(const uint32_t *rw, int rmean, int vR,
 template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ pos_raw,
-              const int32_t *__restrict__ pos_dom, const int32_t *__restrict__ pos_var, const int32_t *__restrict__ pos_sum,
+              const int4 *__restrict__ pos_info,
               const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
               int64_t rows_padded, int64_t rows, int64_t npos, const int64_t *__restrict__ dom0_pos,
               int32_t *__restrict__ best, int2 *__restrict__ vbest, Geom g, int64_t j0)
@@ -1099,10 +1097,11 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
     const float tie_abs = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
     float lb = 0.0f, th = -1.0f;  // lane-local lower bound of the row's max x and the flag threshold from it
     auto consider = [&](int64_t pos) {
-        const int idx = pos_dom[pos];
+        const int4 pi = __ldg(pos_info + pos);  // {domain index (-1: padding), varD, sum d, -}
+        const int idx = pi.x;
         if (idx >= 0) {
-            const int varD = pos_var[pos];
-            const int kov = refine_kov<B>(rw, rmean, vR, pos_raw, pos, pos_sum[pos]);
+            const int varD = pi.y;
+            const int kov = refine_kov<B>(rw, rmean, vR, pos_raw, pos, pi.z);
             // x = |kov| / sqrt(varD) within (1 +- 2^-22): |kov| and varD < 2^24 are exact in binary32
             const float ax = varD > 0 ? fabsf((float)kov) * __frsqrt_rn((float)varD) : 0.0f;
             if (ax * (1.0f + 2.384185791015625e-07f) > th) {
@@ -1114,16 +1113,22 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
         }
     };
     if (lane == 0) consider(*dom0_pos);
-    bool overflow = false;
-    for (int lh = 0; lh < 2 * n_chunks && !overflow; lh++) {  // (domain chunk of the unit, column half) lists
-        const int64_t li = ((int64_t)(lh >> 1) * rows_padded + i) * 2 + (lh & 1);
-        const int cnt = flag_cnt[li];
-        if (cnt > kFlagCap) { overflow = true; break; }
-        const int32_t *lst = flag_list + li * kFlagCap;
-        for (int e = 0; e < cnt; e++) consider((int64_t)lst[e] * 32 + lane);
-    }
-    if (overflow)
+    // The row's 2 * n_chunks (<= 16) list lengths are read by as many lanes at once, a list (<= 32 entries) by
+    // one coalesced load: the loop below then has no dependent global loads besides the candidates themselves.
+    const int n_lists = 2 * n_chunks;  // (domain chunk of the unit, column half)
+    const int my_cnt = lane < n_lists ? flag_cnt[((int64_t)(lane >> 1) * rows_padded + i) * 2 + (lane & 1)] : 0;
+    const bool overflow = __any_sync(0xffffffffu, my_cnt > kFlagCap);
+    if (!overflow) {
+        for (int lh = 0; lh < n_lists; lh++) {
+            const int cnt = __shfl_sync(0xffffffffu, my_cnt, lh);
+            if (cnt == 0) continue;
+            const int32_t *lst = flag_list + (((int64_t)(lh >> 1) * rows_padded + i) * 2 + (lh & 1)) * kFlagCap;
+            const int mine = lane < cnt ? lst[lane] : 0;
+            for (int e = 0; e < cnt; e++) consider((int64_t)__shfl_sync(0xffffffffu, mine, e) * 32 + lane);
+        }
+    } else {
         for (int64_t pos = lane; pos < npos; pos += 32) consider(pos);
+    }
     for (int o = 16; o > 0; o >>= 1) {
         float e2 = __shfl_down_sync(0xffffffffu, be, o);
         int i2 = __shfl_down_sync(0xffffffffu, bi, o);
@@ -1198,19 +1203,18 @@ inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
     return p;
 }
 
-// opB workspace: [tile blobs][pos_dom s32][pos_var s32][pos_sum s32][pos_raw u8 x n][dom0 pos s64]
+// opB workspace: [tile blobs][pos_dom s32][pos_info int4][pos_raw u8 x n][dom0 pos s64]
 //                [sort: keys x2, vals x2, cub temp]
 template <int B, bool F16>
 struct OpBLayout {
-    size_t off_posdom, off_posvar, off_possum, off_posraw, off_dom0, off_keys0, off_keys1, off_vals0, off_vals1, off_temp,
+    size_t off_posdom, off_posinfo, off_posraw, off_dom0, off_keys0, off_keys1, off_vals0, off_vals1, off_temp,
         temp_bytes, total;
     OpBLayout(const Geom &g, const Plan &p)
     {
         size_t o = (size_t)p.ntiles * Lay<B, F16>::B_TILE_BYTES;
         auto take = [&](size_t bytes) { size_t at = (o + 255) & ~(size_t)255; o = at + bytes; return at; };
         off_posdom = take((size_t)p.npos * 4);
-        off_posvar = take((size_t)p.npos * 4);
-        off_possum = take((size_t)p.npos * 4);
+        off_posinfo = take((size_t)p.npos * 16);
         off_posraw = take((size_t)p.npos * (B * B));
         off_dom0 = take(16);  // s64 sweep position of domain 0, then the s32 `unsupported` flag
         off_keys0 = take((size_t)g.ND * 4);
@@ -1253,8 +1257,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     uint32_t *row_lb = (uint32_t *)(vbest + rp);  // per operand row: best lower bound of max x reached by finished units
     OpBLayout<B, F16> lay(g, p);
     int32_t *pos_dom = (int32_t *)(w.opB + lay.off_posdom);
-    int32_t *pos_var = (int32_t *)(w.opB + lay.off_posvar);
-    int32_t *pos_sum = (int32_t *)(w.opB + lay.off_possum);
+    int4 *pos_info = (int4 *)(w.opB + lay.off_posinfo);
     uint8_t *pos_raw = w.opB + lay.off_posraw;
     int64_t *dom0 = (int64_t *)(w.opB + lay.off_dom0);
     int *unsupported = (int *)(dom0 + 1);
@@ -1271,7 +1274,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     // 2. operand blobs
     cudaMemsetAsync(unsupported, 0, sizeof(int), s);
     k_umma_pack_domains<B, F16><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(
-        w.dec, w.dsum, w.dsq, dv.Current(), w.opB, pos_dom, pos_var, pos_sum, pos_raw, dom0, unsupported, g, p.ntiles, p.mult);
+        w.dec, w.dsum, w.dsq, dv.Current(), w.opB, pos_dom, pos_info, pos_raw, dom0, unsupported, g, p.ntiles, p.mult);
     if (B == 16 && !F16) {  // rare digit overflow (see k_umma_pack_domains): decided on the host before the search starts
         int flag = 0;
         ce = cudaMemcpyAsync(&flag, unsupported, sizeof(int), cudaMemcpyDeviceToHost, s);
@@ -1304,7 +1307,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
                                                dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
     if (k1) cudaEventRecord(k1, s);
     // 4. exact refine of the flagged chunks
-    if (!(dbg & 8u)) k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_dom, pos_var, pos_sum, flag_list,
+    if (!(dbg & 8u)) k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_info, flag_list,
                                                                 flag_cnt, p.n_chunks, rp, rows, p.npos, dom0, w.best, vbest, g, j0);
     if (g.n_iso > 1 && !(dbg & 8u)) {
         k_umma_merge_iso<<<(unsigned)((j1 - j0 + 255) / 256), 256, 0, s>>>(vbest, w.best, j1 - j0, j0);
