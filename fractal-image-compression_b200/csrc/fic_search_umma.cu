@@ -625,7 +625,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NSTAGE; s++) {
             mbar_init(BAR_B_FULL(s), 1);
-            mbar_init(BAR_B_EMPTY(s), C::KSPLIT ? 1 : kEpiWarps);  // K-split: released by the MMA issuer's commit alone
+            mbar_init(BAR_B_EMPTY(s), 1);  // released by the MMA issuer's commit alone: the epilogue never touches the ring
         }
         for (int q = 0; q < kAccs; q++) {
             mbar_init(BAR_T_FULL(q), 1);
@@ -768,6 +768,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     __syncwarp();
                     t_phase ^= 1u << q;
                 }
+                if (elected) tc_commit(BAR_B_EMPTY(stage));  // the slot is free once these MMAs have read it
+                __syncwarp();
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
             if (elected) tc_commit(BAR_A_EMPTY);  // every MMA that reads this A super-block has completed
@@ -783,7 +785,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         const int e = warp - 4;
         const int lq = e & 3, q = e >> 2;
         const uint32_t ta = tmem_base + ((uint32_t)(lq * 32) << 16) + q * kTileN;
-        uint32_t stage = 0, phase = 0, tf_phase = 0;
+        uint32_t tf_phase = 0;
         // DBG & 8 (probe only): per-warp cycle accounting of the epilogue phases.  tcgen05.wait::ld is a
         // scoreboard wait, so the TMEM latency shows up at the first use of the loaded registers ("math").
         uint32_t tk_b = 0, tk_t = 0, tk_l = 0, tk_m = 0, tk_mark = 0;
@@ -828,39 +830,25 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             int32_t *const list0 = flag_list + (((int64_t)ch * rows_padded + row) * 2) * kFlagCap;
             int cnt0 = 0, cnt1 = 0;  // entries of the two lists (column halves) of this (row, unit)
             if (DBG & 8) tk_mark = (uint32_t)clock();
-            // K-split tiles: the bounds come from the tile blob in global memory (the shared-memory slot belongs to
-            // the MMA issuer alone), fetched one tile ahead
+            // The bounds come from the tile blob in global memory (the shared-memory ring belongs to the producer and
+            // the MMA issuer alone), fetched one tile ahead: a broadcast load, served by L1/L2.
             float4 nb01 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), nb23 = nb01;
-            if (C::KSPLIT && t0 < t1) {
+            if (t0 < t1) {
                 const float4 *gb = (const float4 *)(opB + (int64_t)t0 * L::B_TILE_BYTES + L::B_OP_BYTES);
                 nb01 = __ldg(gb);
                 nb23 = __ldg(gb + 1);
             }
             for (int t = t0; t < t1; t++) {
                 // (rhi, rlo) of the tile's four chunks
-                float4 bnd01, bnd23;
-                if (C::KSPLIT) {
-                    bnd01 = nb01;
-                    bnd23 = nb23;
-                    if (t + 1 < t1) {
-                        const float4 *gb = (const float4 *)(opB + (int64_t)(t + 1) * L::B_TILE_BYTES + L::B_OP_BYTES);
-                        nb01 = __ldg(gb);
-                        nb23 = __ldg(gb + 1);
-                    }
-                } else {
-                    mbar_wait(BAR_B_FULL(stage), phase, status, 6);
-                    const uint32_t bnd_addr = smem_u32(sB + stage * L::SLOT_BYTES + L::B_OP_BYTES);
-                    bnd01 = lds_f4(bnd_addr);
-                    bnd23 = lds_f4(bnd_addr + 16);
+                const float4 bnd01 = nb01, bnd23 = nb23;
+                if (t + 1 < t1) {
+                    const float4 *gb = (const float4 *)(opB + (int64_t)(t + 1) * L::B_TILE_BYTES + L::B_OP_BYTES);
+                    nb01 = __ldg(gb);
+                    nb23 = __ldg(gb + 1);
                 }
                 tick(tk_b);
                 mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
                 tc_fence_after();
-                // Every warp passes here; the warps of accumulator 3 after the tile's last commit: by the time all
-                // 16 have arrived every MMA that reads this tile's shared-memory stage has completed, and the
-                // bounds are in registers.  Release the stage now, not at the end of the tile.
-                __syncwarp();
-                if (!C::KSPLIT && lane == 0) mbar_arrive(BAR_B_EMPTY(stage));
                 if (iso_shift) {  // adopt a better bound found by another isometry of the same range block
                     const float other = __uint_as_float(lds_volatile_u32(sh_lb));
                     if (other > st.lbmax) {
@@ -934,7 +922,6 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     tick(tk_m);
                 }
                 tf_phase ^= 1;
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
             flag_cnt[((int64_t)ch * rows_padded + row) * 2] = cnt0;
             flag_cnt[((int64_t)ch * rows_padded + row) * 2 + 1] = cnt1;
