@@ -51,7 +51,8 @@
 // layout (8x16-byte core matrices, LBO = 128 B between K-adjacent core matrices,
 // SBO = KS*256 B between 8-row groups).  A blob is moved with ONE 1-D TMA bulk copy
 // (cp.async.bulk, SASS UBLKCP) that completes on an mbarrier; a domain tile blob also
-// carries the (rhi, rlo) pair of each of its four 32-column chunks.
+// carries the (rhi, rlo) pair of each of its four 32-column chunks.  (B = 16: a tile is two
+// blobs, high digits + bounds and low digits, see Cfg<16, false>.)
 //
 // Sweep order.  Sorted position sp holds domain perm[sp] (perm = domains by increasing
 // varD, k_umma_sortkeys + cub radix sort).  Sorted chunks (32 positions) are visited in
@@ -63,11 +64,16 @@
 //               unit) + a ring of domain tiles (128 domains each)
 //   warp 1      MMA issuer (warp-uniform loop, one elected lane issues): per domain tile
 //               4 accumulators (128 rows x 128 domains = all 512 TMEM columns) x NS
-//               K-slices of tcgen05.mma, tcgen05.commit -> t_full[q]
+//               K-slices of tcgen05.mma, tcgen05.commit -> t_full[q]; a second commit hands
+//               the ring slot back to the producer (the epilogue never touches the ring)
 //   warp 2      TMEM allocator
 //   warps 4-19  epilogue: warp e owns TMEM lane quarter e % 4 of accumulator e / 4; one thread = one
-//               range row, all 128 domains of a tile
-// A work unit is (super-block of 512 rows) x (1/n_chunks of the domain tiles).
+//               range row, all 128 domains of a tile: per tile one t_full wait, four
+//               tcgen05.ld.32x32b.x32, one hand-back (t_empty[q]); the tile's bounds come from
+//               the blob in global memory, one tile ahead.  Rare paths (flag recording,
+//               mbarrier polling) are out of line.
+// A work unit is (super-block of 512 rows) x (1/n_chunks of the domain tiles); units are
+// ordered chunk-major and a row's lower bound is carried from unit to unit (row_lb).
 #include <cuda_fp16.h>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -553,17 +559,7 @@ __device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t saddr)
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_max_shared_u32(uint32_t saddr, uint32_t v)
-{
-    asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float4 lds_f4(uint32_t saddr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
-    return v;
-}
 __device__ __forceinline__ int dp4a_uu(uint32_t a_u8x4, uint32_t b_u8x4, int c)
 {
     int d;
