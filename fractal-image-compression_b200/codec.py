@@ -155,10 +155,13 @@ class Handle:
                                                   range_begin, range_end, C.c_void_p(d_info or 0),
                                                   C.c_void_p(d_q or 0)))
 
-    def decode(self, q: np.ndarray, W: int, H: int, B: int, wk: int, rgb: bool, avg_error: float = 0.0,
-               max_iters: int = 50):
+    def decode(self, q: np.ndarray, W: int, H: int, B: int, wk: int, rgb, avg_error: float = 0.0,
+               max_iters: int = 50, out: np.ndarray | None = None):
+        """fic_decode.  `out` (int32 [H, W], e.g. a view of pinned memory) receives the ARGB image; allocated if None."""
         qq = np.ascontiguousarray(q, dtype=np.int32)
-        out = np.empty((H, W), np.int32)
+        if out is None:
+            out = np.empty((H, W), np.int32)
+        assert out.dtype == np.int32 and out.shape == (H, W) and out.flags["C_CONTIGUOUS"]
         avg = C.c_float(avg_error)
         it = C.c_int(0)
         self._check(self._L.fic_decode(self._h, int(rgb), W, H, B, wk, _ptr(qq), max_iters, _ptr(out),

@@ -296,12 +296,6 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     if (engine == FIC_ENGINE_UMMA) {
         const char *why = nullptr;
         int n = launch_search_umma(call, g, j0, j1, h->num_sms, s, &why, kind, h->ev[6], h->ev[7]);
-        if (n == -2) {  // B = 16 digit overflow (a 255 pixel in a block of mean 0): exact direct search instead
-            engine = FIC_ENGINE_DIRECT;
-            CU(cudaEventRecord(h->ev[6], s));
-            n = launch_search_direct(call, g, j0, j1, s);
-            CU(cudaEventRecord(h->ev[7], s));
-        }
         if (n < 0) return set_err(h, FIC_E_CUDA, "tcgen05 search launch failed: %s", why ? why : "?");
         launches += n;
     } else {

@@ -35,12 +35,12 @@
 // The epilogue takes max |kov| with FMNMX3 |a|, |b|, |c|: 16 instructions per 32 values.
 //
 // kov on the tensor cores, kind::i8 (B = 16; selectable for B = 4, 8).  With dt = d - dmean_j
-// (B = 16: |dt| <= 255; the single case dt = +255 does not fit and sends the image to the direct
-// search), split dt = h + l, h = clamp(dt, -128, 127), l = dt - h (both fit s8; l is zero unless a
+// (|dt| <= 255; +255 only occurs in a block of mean 0, whose row is stored negated -- only |kov| is used),
+// split dt = h + l, h = clamp(dt, -128, 127), l = dt - h (both fit s8; l is zero unless a
 // pixel is more than 127 grey levels from its block mean, so the MMA issuer skips the l
 // K-slices of every domain tile whose `l` digits are all zero -- most tiles).  Then
 //     kov = sum_k r_k * h_k + sum_k r_k * l_k + rmean_i * (-alpha_j),   alpha_j = sum d - n*dmean_j
-// i.e. A row = [ r | r | rmean rmean 0.. ] (u8) and B row = [ h | l | -alpha/2 -alpha/2 0.. ] (s8), K
+// i.e. A row = [ r | r | rmean x3 0.. ] (u8) and B row = [ h | l | -alpha in three parts 0.. ] (s8), K
 // padded to a multiple of 32 (one kind::i8 MMA consumes K = 32).  The duplicated `r`
 // half of A is not stored twice: the MMA issuer points the A descriptor of the `l` K-slices
 // back at the `r` slices.  The s32 accumulator IS kov; max |kov| needs a max and a min chain
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(128)
 k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
                     const int32_t *__restrict__ dsq, const int32_t *__restrict__ perm, uint8_t *__restrict__ opB,
                     int32_t *__restrict__ pos_dom, int4 *__restrict__ pos_info,
-                    uint8_t *__restrict__ pos_raw, int64_t *__restrict__ dom0_pos, int *__restrict__ unsupported,
+                    uint8_t *__restrict__ pos_raw, int64_t *__restrict__ dom0_pos,
                     Geom g, int64_t ntiles, uint32_t mult)
 {
     using L = Lay<B, F16>;
@@ -300,6 +300,10 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
         int dmean;
         const int varD = dom_var(dsum[j], dsq[j], n, &dmean);
         constexpr int PCH = n / 16;  // 16-pixel groups
+        // kind::i8: dt = d - dmean reaches +255 only in a block of mean 0 (B = 16), one more than the two s8 digits
+        // 127 + 127 hold, while -255 = -128 - 127 fits.  Such a row is stored negated: the accumulator becomes
+        // -kov, and only |kov| is ever used (the refine step recomputes kov from the raw pixels).
+        const int sgn = (!F16 && dmean == 0) ? -1 : 1;
 #pragma unroll
         for (int c = 0; c < PCH; c++) {
             int dv[16];
@@ -312,7 +316,7 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
                     const int k = c * 16 + w * 4 + e;
                     const int d = (int)__ldg(p + (int64_t)(k / B) * g.sw + (k % B));
                     raw[w] |= (uint32_t)d << (8 * e);
-                    dv[w * 4 + e] = d - dmean;
+                    dv[w * 4 + e] = sgn * (d - dmean);
                 }
             }
             *(uint4 *)(pos_raw + raw_offset<n>(pos, c)) = make_uint4(raw[0], raw[1], raw[2], raw[3]);
@@ -331,9 +335,6 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
                         hv[e] = max(-128, min(127, dv[w * 4 + e]));  // the low digit is zero unless |dt| > 127
                         lv[e] = dv[w * 4 + e] - hv[e];
                         any_l |= lv[e];
-                        // B = 16 only: d = 255 in a block of mean 0 gives dt = 255 = 127 + 128, one more than two
-                        // s8 digits hold; the caller then falls back to the direct search for this image
-                        if (B == 16 && lv[e] > 127) *unsupported = 1;
                     }
                     hw[w] = pack4(hv[0], hv[1], hv[2], hv[3]);
                     lw[w] = pack4(lv[0], lv[1], lv[2], lv[3]);
@@ -344,11 +345,13 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
             }
         }
         if (!F16) {
-            // -alpha in two s8 columns (alpha <= n - 1 = 255 at B = 16); A carries rmean in both
-            const int alpha = dsum[j] - n * dmean;
-            const int a1 = alpha >> 1, a2 = alpha - a1;
+            // -alpha (times the row's sign) in three s8 columns (alpha <= n - 1 = 255 at B = 16: thirds fit either
+            // sign); A carries rmean in all three
+            const int alpha = sgn * (dsum[j] - n * dmean);
+            const int a1 = alpha / 3, a2 = (alpha - a1) / 2, a3 = alpha - a1 - a2;
             constexpr int ACH = KSPLIT ? PCH : 2 * PCH;  // first 16-byte chunk of the alpha K-slice
-            *(uint4 *)(rowp + ACH * 128) = make_uint4((uint32_t)((-a1) & 0xff) | ((uint32_t)((-a2) & 0xff) << 8), 0, 0, 0);
+            *(uint4 *)(rowp + ACH * 128) = make_uint4(
+                (uint32_t)((-a1) & 0xff) | ((uint32_t)((-a2) & 0xff) << 8) | ((uint32_t)((-a3) & 0xff) << 16), 0, 0, 0);
             *(uint4 *)(rowp + (ACH + 1) * 128) = make_uint4(0, 0, 0, 0);
         }
         pos_dom[pos] = (int32_t)j;
@@ -442,7 +445,7 @@ k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ 
     }
     if (!F16) {
         constexpr int XCH = (B == 4) ? 2 * PCH : PCH;
-        *(uint4 *)(rowp + XCH * 128) = make_uint4((uint32_t)rmean | ((uint32_t)rmean << 8), 0, 0, 0);
+        *(uint4 *)(rowp + XCH * 128) = make_uint4((uint32_t)rmean | ((uint32_t)rmean << 8) | ((uint32_t)rmean << 16), 0, 0, 0);
         *(uint4 *)(rowp + (XCH + 1) * 128) = make_uint4(0, 0, 0, 0);
     }
 }
@@ -1199,7 +1202,7 @@ struct OpBLayout {
         off_posdom = take((size_t)p.npos * 4);
         off_posinfo = take((size_t)p.npos * 16);
         off_posraw = take((size_t)p.npos * (B * B));
-        off_dom0 = take(16);  // s64 sweep position of domain 0, then the s32 `unsupported` flag
+        off_dom0 = take(16);  // s64 sweep position of domain 0
         off_keys0 = take((size_t)g.ND * 4);
         off_keys1 = take((size_t)g.ND * 4);
         off_vals0 = take((size_t)g.ND * 4);
@@ -1243,7 +1246,6 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     int4 *pos_info = (int4 *)(w.opB + lay.off_posinfo);
     uint8_t *pos_raw = w.opB + lay.off_posraw;
     int64_t *dom0 = (int64_t *)(w.opB + lay.off_dom0);
-    int *unsupported = (int *)(dom0 + 1);
     int launches = 0;
     cudaError_t ce;
     // 1. domains by increasing varD
@@ -1255,16 +1257,8 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
     launches += 4;  // key kernel + radix passes (approximate; they are not the timed kernel)
     // 2. operand blobs
-    cudaMemsetAsync(unsupported, 0, sizeof(int), s);
     k_umma_pack_domains<B, F16><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(
-        w.dec, w.dsum, w.dsq, dv.Current(), w.opB, pos_dom, pos_info, pos_raw, dom0, unsupported, g, p.ntiles, p.mult);
-    if (B == 16 && !F16) {  // rare digit overflow (see k_umma_pack_domains): decided on the host before the search starts
-        int flag = 0;
-        ce = cudaMemcpyAsync(&flag, unsupported, sizeof(int), cudaMemcpyDeviceToHost, s);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-        if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
-        if (flag) return -2;
-    }
+        w.dec, w.dsum, w.dsq, dv.Current(), w.opB, pos_dom, pos_info, pos_raw, dom0, g, p.ntiles, p.mult);
     k_umma_pack_ranges<B, F16><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
     launches += 2;
     // 3. the fused search

@@ -363,9 +363,10 @@ def test_randomised_parity_sweep(fic, handle, oracle):
     assert cases == 70
 
 
-def test_tcgen05_b16_digit_overflow_falls_back(fic, handle, oracle):
-    """B = 16: a lone 255 in a domain block of mean 0 gives d - dmean = 255 = 127 + 128, one more than two s8
-    digits hold; the library must notice and run the exact direct search instead."""
+def test_tcgen05_b16_extreme_digit(fic, handle, oracle):
+    """B = 16: a lone 255 in a domain block of mean 0 gives d - dmean = +255 = 127 + 128, one more than two s8
+    digits hold.  The tensor-core path stores such rows negated (-255 = -128 - 127 fits; only |kov| is used) and must
+    stay on the tensor cores with the oracle's codes."""
     p = np.zeros((128, 128), np.uint8)
     p[40:42, 40:42] = 255          # one white 2x2 patch -> one decimated pixel of 255 among zeros
     p[100:110, 90:120] = 37        # some structure elsewhere so that ranges are not all flat
@@ -374,7 +375,7 @@ def test_tcgen05_b16_digit_overflow_falls_back(fic, handle, oracle):
     handle.set_engine(fic.FIC_ENGINE_UMMA)
     try:
         info, q = handle.encode(img, 16, wk, rgb=False)
-        assert handle.timings().engine == fic.FIC_ENGINE_DIRECT
+        assert handle.timings().engine == fic.FIC_ENGINE_UMMA
     finally:
         handle.set_engine(fic.FIC_ENGINE_AUTO)
     oinfo = oracle.encode(img, 16, wk)
