@@ -1043,22 +1043,18 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
               const int4 *__restrict__ pos_info,
               const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
               int64_t rows_padded, int64_t rows, int64_t npos, const int64_t *__restrict__ dom0_pos,
-              int32_t *__restrict__ best, int2 *__restrict__ vbest, Geom g, int64_t j0)
+              int32_t *__restrict__ best, Geom g, int64_t j0)
 {
     constexpr int n = B * B;
     constexpr int NW = n / 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * 4 + warp;  // operand row (see k_umma_pack_ranges)
+    const int64_t i = (int64_t)blockIdx.x * 4 + warp;  // operand row == range block (the isometry extension has its own kernel)
     if (i >= rows) return;
-    const int64_t j = j0 + i / g.n_iso;
-    const int kiso = (int)(i % g.n_iso);
+    const int64_t j = j0 + i;
     const int rs = rsum[j];
     const int rmean = rs / n, vR = rs - n * rmean;
     if (vR == 0) {  // FC:677-678 + FC:627: all errors are 0, the first candidate wins
-        if (lane == 0) {
-            if (g.n_iso == 1) best[j] = 0;
-            else vbest[i] = make_int2(0, 0);  // (binary32 bits of the error, domain index)
-        }
+        if (lane == 0) best[j] = 0;
         return;
     }
     const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
@@ -1066,17 +1062,7 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
 #pragma unroll
     for (int w = 0; w < NW; w++) {
         const int k = 4 * w;
-        if (kiso == 0) {
-            rw[w] = __ldg((const uint32_t *)(src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)));
-        } else {  // the same permutation as the operand row
-            rw[w] = 0;
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                int ry, rx;
-                iso_map(iso_inverse(kiso), B, (k + e) / B, (k + e) % B, &ry, &rx);
-                rw[w] |= (uint32_t)__ldg(src + (int64_t)(yr * B + ry) * g.W + xr * B + rx) << (8 * e);
-            }
-        }
+        rw[w] = __ldg((const uint32_t *)(src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)));
     }
     float be = 10000000.0f;  // FC:615
     int bi = 0x7fffffff;
@@ -1120,29 +1106,107 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
         int i2 = __shfl_down_sync(0xffffffffu, bi, o);
         if (e2 < be || (e2 == be && i2 < bi)) { be = e2; bi = i2; }
     }
-    if (lane == 0) {
-        if (bi == 0x7fffffff) { bi = 0; be = 0.0f; }
-        if (g.n_iso == 1) best[j] = bi;
-        else vbest[i] = make_int2(__float_as_int(be), bi);
-    }
+    if (lane == 0) best[j] = bi == 0x7fffffff ? 0 : bi;
 }
 
-// Isometry extension: the winner of a range block is the lexicographic (error, c, k) minimum over its 8 operand
-// rows (each row already holds its lowest c among equal errors) = what an ascending (c, k) double loop with
-// strict < yields.  best[j] = c * 8 + k.
-__global__ void k_umma_merge_iso(const int2 *__restrict__ vbest, int32_t *__restrict__ best, int64_t ranges, int64_t j0)
+// Isometry extension: refine of a whole range block by one warp.  The block's 8 operand rows (one per isometry,
+// see k_umma_pack_ranges) share the running bound in the search kernel, so most of them carry no flagged chunk at
+// all: the warp reads the 16 list lengths of a domain chunk (8 rows x 2 column halves, contiguous) with one load,
+// skips the empty rows, and rebuilds the permuted range block (from a shared-memory copy) only for rows that have
+// work.  The winner is the lexicographic (error, c, k) minimum = what an ascending (c, k) double loop with strict <
+// yields; best[j] = c * 8 + k.
+template <int B>
+__global__ void __launch_bounds__(128)
+k_umma_refine_iso(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ pos_raw,
+                  const int4 *__restrict__ pos_info, const int32_t *__restrict__ flag_list,
+                  const int32_t *__restrict__ flag_cnt, int n_chunks, int64_t rows_padded, int64_t ranges, int64_t npos,
+                  const int64_t *__restrict__ dom0_pos, int32_t *__restrict__ best, Geom g, int64_t j0)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int n = B * B;
+    constexpr int NW = n / 4;
+    __shared__ uint8_t s_blk[4][n];  // the range block of each of the block's 4 warps, raster order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 4 + warp;
     if (r >= ranges) return;
-    float be = 0.0f;
-    int bc = 0x7fffffff;
-    for (int k = 0; k < 8; k++) {
-        const int2 v = vbest[r * 8 + k];
-        const float e = __int_as_float(v.x);
-        const int c = v.y * 8 + k;
-        if (k == 0 || e < be || (e == be && c < bc)) { be = e; bc = c; }
+    const int64_t j = j0 + r;
+    const int rs = rsum[j];
+    const int rmean = rs / n, vR = rs - n * rmean;
+    if (vR == 0) {  // FC:677-678 + FC:627: all errors are 0, the first candidate wins
+        if (lane == 0) best[j] = 0;
+        return;
     }
-    best[j0 + r] = bc;
+    const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    for (int w = lane; w < NW; w += 32) {
+        const int k = 4 * w;
+        ((uint32_t *)s_blk[warp])[w] = __ldg((const uint32_t *)(src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)));
+    }
+    __syncwarp();
+    uint32_t rw[NW];  // the block permuted for the isometry at hand (same layout as the operand row)
+    auto build = [&](int kiso) {
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                int ry, rx;  // the range pixel that T_kiso sends to domain pixel 4 * w + e
+                iso_map(iso_inverse(kiso), B, (4 * w + e) / B, (4 * w + e) % B, &ry, &rx);
+                word |= (uint32_t)s_blk[warp][ry * B + rx] << (8 * e);
+            }
+            rw[w] = word;
+        }
+    };
+    float be = 10000000.0f;  // FC:615
+    int bi = 0x7fffffff;     // c * 8 + k
+    const float tie_abs = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
+    float lb = 0.0f, th = -1.0f;  // lane-local bound / threshold, shared by the 8 isometries (they compete for one winner)
+    auto consider = [&](int64_t pos, int kiso) {
+        const int4 pi = __ldg(pos_info + pos);  // {domain index (-1: padding), varD, sum d, -}
+        if (pi.x >= 0) {
+            const int kov = refine_kov<B>(rw, rmean, vR, pos_raw, pos, pi.z);
+            const float ax = pi.y > 0 ? fabsf((float)kov) * __frsqrt_rn((float)pi.y) : 0.0f;
+            if (ax * (1.0f + 2.384185791015625e-07f) > th) {
+                const float err = grey_error(kov, vR, __dsqrt_rn((double)pi.y));
+                const int c = pi.x * 8 + kiso;
+                if (err < be || (err == be && c < bi)) { be = err; bi = c; }
+                const float xlo = ax * (1.0f - 2.384185791015625e-07f);
+                if (xlo > lb) { lb = xlo; th = flag_threshold(lb, tie_abs); }
+            }
+        }
+    };
+    build(0);
+    if (lane == 0) consider(*dom0_pos, 0);  // (domain 0, identity) wins when the whole block ties
+    int built = 0;
+    bool overflow = false;
+    for (int ch = 0; ch < n_chunks && !overflow; ch++) {
+        // 16 contiguous list lengths: operand row 8 r + k, column half h at lane 2 k + h
+        const int64_t base = ((int64_t)ch * rows_padded + r * 8) * 2;
+        const int my_cnt = lane < 16 ? flag_cnt[base + lane] : 0;
+        if (__any_sync(0xffffffffu, my_cnt > kFlagCap)) { overflow = true; break; }
+        for (int kiso = 0; kiso < 8; kiso++) {
+            const int c0 = __shfl_sync(0xffffffffu, my_cnt, 2 * kiso), c1 = __shfl_sync(0xffffffffu, my_cnt, 2 * kiso + 1);
+            if ((c0 | c1) == 0) continue;
+            if (built != kiso) { build(kiso); built = kiso; }
+            for (int h = 0; h < 2; h++) {
+                const int cnt = h ? c1 : c0;
+                if (cnt == 0) continue;
+                const int32_t *lst = flag_list + (base + 2 * kiso + h) * kFlagCap;
+                const int mine = lane < cnt ? lst[lane] : 0;
+                for (int e = 0; e < cnt; e++) consider((int64_t)__shfl_sync(0xffffffffu, mine, e) * 32 + lane, kiso);
+            }
+        }
+    }
+    if (overflow) {  // slow, exact: every candidate under every isometry
+        for (int kiso = 0; kiso < 8; kiso++) {
+            build(kiso);
+            for (int64_t pos = lane; pos < npos; pos += 32) consider(pos, kiso);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        float e2 = __shfl_down_sync(0xffffffffu, be, o);
+        int i2 = __shfl_down_sync(0xffffffffu, bi, o);
+        if (e2 < be || (e2 == be && i2 < bi)) { be = e2; bi = i2; }
+    }
+    if (lane == 0) best[j] = bi == 0x7fffffff ? 0 : bi;
 }
 
 // ---------------------------------------------------------------- host side ------------
@@ -1220,9 +1284,9 @@ template <int B, bool F16>
 size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p = make_plan(g, rows, num_sms);
-    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap][vbest int2 (isometries)][row_lb u32]
+    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap][row_lb u32]
     return (size_t)p.n_sb * Lay<B, F16>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 2 * 4 * (1 + kFlagCap) +
-           (size_t)p.rp * 8 + (size_t)p.rp * 4 + 1024;
+           (size_t)p.rp * 4 + 1024;
 }
 
 template <int B, bool F16>
@@ -1239,8 +1303,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     int32_t *vR = (int32_t *)(opA + (size_t)p.n_sb * L::A_SB_BYTES);
     int32_t *flag_cnt = vR + rp;
     int32_t *flag_list = flag_cnt + rp * p.n_chunks * 2;
-    int2 *vbest = (int2 *)(((uintptr_t)(flag_list + rp * p.n_chunks * 2 * kFlagCap) + 15) & ~(uintptr_t)15);
-    uint32_t *row_lb = (uint32_t *)(vbest + rp);  // per operand row: best lower bound of max x reached by finished units
+    uint32_t *row_lb = (uint32_t *)(flag_list + rp * p.n_chunks * 2 * kFlagCap);  // per operand row: best lower bound of max x reached by finished units
     OpBLayout<B, F16> lay(g, p);
     int32_t *pos_dom = (int32_t *)(w.opB + lay.off_posdom);
     int4 *pos_info = (int4 *)(w.opB + lay.off_posinfo);
@@ -1284,11 +1347,13 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
                                                dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
     if (k1) cudaEventRecord(k1, s);
     // 4. exact refine of the flagged chunks
-    if (!(dbg & 8u)) k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_info, flag_list,
-                                                                flag_cnt, p.n_chunks, rp, rows, p.npos, dom0, w.best, vbest, g, j0);
-    if (g.n_iso > 1 && !(dbg & 8u)) {
-        k_umma_merge_iso<<<(unsigned)((j1 - j0 + 255) / 256), 256, 0, s>>>(vbest, w.best, j1 - j0, j0);
-        launches++;
+    if (!(dbg & 8u)) {
+        if (g.n_iso > 1)
+            k_umma_refine_iso<B><<<(unsigned)((j1 - j0 + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_info, flag_list, flag_cnt,
+                                                                             p.n_chunks, rp, j1 - j0, p.npos, dom0, w.best, g, j0);
+        else
+            k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_info, flag_list, flag_cnt,
+                                                                        p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
     }
     launches += 2;
     ce = cudaGetLastError();
