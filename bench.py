@@ -354,7 +354,9 @@ def run_ours(args):
         "config": {"workload": f"synthetic {args.pattern} {size}x{size} grey, B={B}, widthKernel={wk} (full pool)"
                                + (", 8 isometries per domain (extension)" if args.iso else ""),
                    "ranges": NR, "domains": ND, "isometries": n_iso, "engine": f"tcgen05 kind::{mma}" if engine == fic.FIC_ENGINE_UMMA else "direct",
-                   "parallelism": f"range-rows x{world}", "l2": "flushed between timed iterations (256 MiB write)"},
+                   "parallelism": f"range-rows x{world}", "l2": "flushed between timed iterations (256 MiB write)",
+                   # the library's once-per-handle check that kind::f16 accumulators are the exact integer covariances
+                   "f16_exact_selftest": bool(handle.f16_exact()) if mma == "f16" else None},
         "clocks": clocks,
         "e2e": {"value": evals / (e2e_ms / args.steps * 1e-3) / 1e9, "unit": "Gevals/s",
                 "mpixel_per_s": size * size / (e2e_ms / args.steps * 1e-3) / 1e6,
