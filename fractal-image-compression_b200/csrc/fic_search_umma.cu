@@ -70,7 +70,7 @@
 //   warps 4-19  epilogue: warp e owns TMEM lane quarter e % 4 of accumulator e / 4; one thread = one
 //               range row, all 128 domains of a tile: per tile one t_full wait, four
 //               tcgen05.ld.32x32b.x32, one hand-back (t_empty[q]); the tile's bounds come from
-//               the blob in global memory, one tile ahead.  Rare paths (flag recording,
+//               the blob in global memory at the top of each tile.  Rare paths (flag recording,
 //               mbarrier polling) are out of line.
 // A work unit is (super-block of 512 rows) x (1/n_chunks of the domain tiles); units are
 // ordered chunk-major and a row's lower bound is carried from unit to unit (row_lb).
@@ -829,22 +829,12 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             int32_t *const list0 = flag_list + (((int64_t)ch * rows_padded + row) * 2) * kFlagCap;
             int cnt0 = 0, cnt1 = 0;  // entries of the two lists (column halves) of this (row, unit)
             if (DBG & 8) tk_mark = (uint32_t)clock();
-            // The bounds come from the tile blob in global memory (the shared-memory ring belongs to the producer and
-            // the MMA issuer alone), fetched one tile ahead: a broadcast load, served by L1/L2.
-            float4 nb01 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), nb23 = nb01;
-            if (t0 < t1) {
-                const float4 *gb = (const float4 *)(opB + (int64_t)t0 * L::B_TILE_BYTES + L::B_OP_BYTES);
-                nb01 = __ldg(gb);
-                nb23 = __ldg(gb + 1);
-            }
             for (int t = t0; t < t1; t++) {
-                // (rhi, rlo) of the tile's four chunks
-                const float4 bnd01 = nb01, bnd23 = nb23;
-                if (t + 1 < t1) {
-                    const float4 *gb = (const float4 *)(opB + (int64_t)(t + 1) * L::B_TILE_BYTES + L::B_OP_BYTES);
-                    nb01 = __ldg(gb);
-                    nb23 = __ldg(gb + 1);
-                }
+                // (rhi, rlo) of the tile's four chunks, from the tile blob in global memory (the shared-memory ring
+                // belongs to the producer and the MMA issuer alone): a broadcast load that every warp of the CTA
+                // repeats, so it is an L1 hit for all but the first; its latency hides behind the t_full wait.
+                const float4 *gb = (const float4 *)(opB + (int64_t)t * L::B_TILE_BYTES + L::B_OP_BYTES);
+                const float4 bnd01 = __ldg(gb), bnd23 = __ldg(gb + 1);
                 tick(tk_b);
                 mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
                 tc_fence_after();
