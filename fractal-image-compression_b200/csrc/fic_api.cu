@@ -146,8 +146,13 @@ int fic_create(int device, fic_handle **out)
         return FIC_E_CUDA;
     }
     h->stream = h->own_stream;
-    for (int i = 0; i < 8; i++) cudaEventCreate(&h->ev[i]);
-    cudaHostAlloc((void **)&h->h_acc, 64 * sizeof(unsigned long long), cudaHostAllocDefault);
+    for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h->h_acc, 64 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        set_err(nullptr, FIC_E_CUDA, "creating events / pinned scratch: %s", cudaGetErrorString(e));
+        fic_destroy(h);
+        return FIC_E_CUDA;
+    }
     *out = h;
     return FIC_OK;
 }
