@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--engine", default="auto", choices=["auto", "direct", "umma"])
     ap.add_argument("--iso", action="store_true",
                     help="isometry extension: 8 isometries per candidate domain (8x the evaluations; not a reference mode)")
+    ap.add_argument("--rgb", action="store_true",
+                    help="RGB encode (FC:171-226: one shared domain and contrast for the three channels); tensor cores for B = 4, 8")
     ap.add_argument("--mma", default="auto", choices=["auto", "i8", "f16"],
                     help="tensor-core instruction kind of the tcgen05 search (auto: f16 for B=4,8; i8 for B=16)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
@@ -123,31 +125,44 @@ def make_image(args, size):
     import fractal_image_compression_b200 as fic
 
     gen = fic.synth.structured if args.pattern == "structured" else fic.synth.noise
+    if args.rgb:   # three planes (R, G, B), seeds 1..3
+        return np.stack([gen(size, size, s) for s in (1, 2, 3)], 0)
     return gen(size, size, 1)
+
+
+def to_argb(plane):
+    import fractal_image_compression_b200 as fic
+
+    if plane.ndim == 2:
+        return fic.synth.grey_to_argb(plane)
+    v = plane.astype(np.uint32)
+    return (np.uint32(0xFF000000) | (v[0] << np.uint32(16)) | (v[1] << np.uint32(8)) | v[2]).view(np.int32)
 
 
 # ----------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference (the Java encoder cannot run: no JVM here)
 # ----------------------------------------------------------------------------------------
 
-def cpu_sample(plane, B, wk, nthreads, target_s, iso=False):
+def cpu_sample(plane, B, wk, nthreads, target_s, iso=False, rgb=False):
     """Times the oracle's range loop on the first R ranges of the workload.  The codebook
     build is timed separately (a call with zero ranges) and subtracted, so the figure is
     the search rate the reference would sustain over the full image."""
     from oracle import oracle as O
     import fractal_image_compression_b200 as fic
 
-    argb = fic.synth.grey_to_argb(plane)
+    argb = to_argb(plane)
+    kw = {"rgb": True} if rgb else {"iso": iso}
     t0 = time.perf_counter()
-    O.encode(argb, B, wk, range_begin=0, range_end=0, nthreads=1, iso=iso)
+    O.encode(argb, B, wk, range_begin=0, range_end=0, nthreads=1, **kw)
     t_pool = time.perf_counter() - t0
     R = nthreads
     t0 = time.perf_counter()
-    O.encode(argb, B, wk, range_begin=0, range_end=R, nthreads=nthreads, iso=iso)
+    O.encode(argb, B, wk, range_begin=0, range_end=R, nthreads=nthreads, **kw)
     t_probe = max(time.perf_counter() - t0 - t_pool, 1e-3)
     R = max(nthreads, int(R * target_s / t_probe) // nthreads * nthreads)
+    R = min(R, (argb.shape[0] // B) * (argb.shape[1] // B))   # small images: the whole image is the sample
     t0 = time.perf_counter()
-    O.encode(argb, B, wk, range_begin=0, range_end=R, nthreads=nthreads, iso=iso)
+    O.encode(argb, B, wk, range_begin=0, range_end=R, nthreads=nthreads, **kw)
     t = max(time.perf_counter() - t0 - t_pool, 1e-6)
     return R, t, t_pool
 
@@ -164,7 +179,7 @@ def run_reference(args):
     rates, times = [], []
     R = 0
     for i in range(args.warmup + args.steps):
-        R, t, t_pool = cpu_sample(plane, B, wk, threads, per_step, args.iso)
+        R, t, t_pool = cpu_sample(plane, B, wk, threads, per_step, args.iso, args.rgb)
         if i >= args.warmup:
             rates.append(R * ND * n_iso / t)
             times.append(t)
@@ -176,7 +191,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": statistics.mean(times) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic {args.pattern} {size}x{size} grey, B={B}, widthKernel={wk} (full pool)",
+        "config": {"workload": f"synthetic {args.pattern} {size}x{size} {'RGB' if args.rgb else 'grey'}, B={B}, widthKernel={wk} (full pool)",
                    "ranges": NR, "domains": ND},
         "cpu_baseline": {"value": v / 1e9, "unit": "Gevals/s", "cores": threads, "kind": "port",
                          "sample": f"first {R} of {NR} range blocks against the full pool per step "
@@ -210,26 +225,29 @@ def run_ours(args):
     size, B, wk, NR, ND = workload(args)
     plane = make_image(args, size)
     n_iso = 8 if args.iso else 1
-    mode = fic.FIC_MODE_GREY_ISO if args.iso else fic.FIC_MODE_GREY
-    S = 4 if args.iso else 3
+    if args.iso and args.rgb:
+        raise SystemExit("--iso and --rgb exclude each other (the isometry extension is grey only)")
+    mode = fic.FIC_MODE_GREY_ISO if args.iso else (fic.FIC_MODE_RGB if args.rgb else fic.FIC_MODE_GREY)
+    S = 4 if args.iso else (5 if args.rgb else 3)
+    C = 3 if args.rgb else 1
     evals = float(NR) * float(ND) * n_iso
 
     handle = fic.Handle(local)
     handle.set_engine({"auto": fic.FIC_ENGINE_AUTO, "direct": fic.FIC_ENGINE_DIRECT, "umma": fic.FIC_ENGINE_UMMA}[args.engine])
     handle.set_umma_kind({"auto": fic.FIC_UMMA_KIND_AUTO, "i8": fic.FIC_UMMA_KIND_I8, "f16": fic.FIC_UMMA_KIND_F16}[args.mma])
-    mma = "i8" if (B == 16 or args.mma == "i8") else "f16"   # what the library runs (B = 16 has no f16 variant)
+    mma = "i8" if (B == 16 or (args.mma == "i8" and not args.rgb)) else "f16"   # what the library runs (B = 16 has no f16 variant, RGB no i8 one)
     stream = torch.cuda.Stream(dev)   # library work, NCCL ordering and the timing events all use this stream
     torch.cuda.set_stream(stream)
     handle.set_stream(stream.cuda_stream)
     enc = ShardedEncoder(handle=handle) if world > 1 else None
 
-    d_planes = torch.from_numpy(plane).to(dev).reshape(1, size, size).contiguous() if rank == 0 else None
+    d_planes = torch.from_numpy(plane).to(dev).reshape(C, size, size).contiguous() if rank == 0 else None
     d_info = torch.empty((NR, S), dtype=torch.float32, device=dev)
     d_q = torch.empty((NR, S), dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # pinned host buffers for the e2e leg
-    h_argb = torch.from_numpy(fic.synth.grey_to_argb(plane)).pin_memory() if rank == 0 else None
+    h_argb = torch.from_numpy(to_argb(plane)).pin_memory() if rank == 0 else None
     h_plane = torch.from_numpy(plane).pin_memory() if rank == 0 else None
     h_info = torch.empty((NR, S), dtype=torch.float32).pin_memory()
     h_q = torch.empty((NR, S), dtype=torch.int32).pin_memory()
@@ -247,7 +265,7 @@ def run_ours(args):
             handle.encode(h_argb.numpy(), B, wk, rgb=mode, info=h_info.numpy(), q=h_q.numpy())
             handle.set_stream(stream.cuda_stream)
             return
-        pl = h_plane.to(dev, non_blocking=True).reshape(1, size, size) if rank == 0 else None
+        pl = h_plane.to(dev, non_blocking=True).reshape(C, size, size) if rank == 0 else None
         out = enc.encode(pl, mode, size, size, B, wk, device=dev)
         if rank == 0:
             h_info.copy_(out[0], non_blocking=True)
@@ -332,7 +350,7 @@ def run_ours(args):
     nominal = 2250.0 if mma == "f16" else 4500.0
     is_umma = engine == fic.FIC_ENGINE_UMMA
     roofline = {
-        "bound": "tensor", "kernel": f"k_umma_search (tcgen05.mma.kind::{mma})" if is_umma else "k_search_direct_grey",
+        "bound": "tensor", "kernel": f"k_umma_search (tcgen05.mma.kind::{mma})" if is_umma else ("k_search_direct_rgb" if args.rgb else "k_search_direct_grey"),
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s" if mma == "f16" else "TOP/s", "frac": achieved / peak,
         "peak_source": (f"bf16_tflops ({pk['bf16_tflops']}, burst) of {pk_kind}" if mma == "f16" else
                         f"2 x bf16_tflops ({pk['bf16_tflops']}, burst) of {pk_kind} (no int8 entry there)"),
@@ -343,7 +361,7 @@ def run_ours(args):
         "pool_ms": statistics.mean(pool_ms),
         # dram__bytes_read.sum + dram__bytes_write.sum of one k_umma_search launch from `ncu --set full`
         # (profiles/); only known for the profiled workload
-        "traffic": TRAFFIC.get((mma, size, B)) if (is_umma and world == 1 and not args.iso) else None,
+        "traffic": TRAFFIC.get((mma, size, B)) if (is_umma and world == 1 and not args.iso and not args.rgb) else None,
     }
     line = {
         "metric": "encode_evals_per_s", "value": value / 1e9, "unit": "Gevals/s",
@@ -351,7 +369,7 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": f"synthetic {args.pattern} {size}x{size} grey, B={B}, widthKernel={wk} (full pool)"
+        "config": {"workload": f"synthetic {args.pattern} {size}x{size} {'RGB' if args.rgb else 'grey'}, B={B}, widthKernel={wk} (full pool)"
                                + (", 8 isometries per domain (extension)" if args.iso else ""),
                    "ranges": NR, "domains": ND, "isometries": n_iso, "engine": f"tcgen05 kind::{mma}" if engine == fic.FIC_ENGINE_UMMA else "direct",
                    "parallelism": f"range-rows x{world}", "l2": "flushed between timed iterations (256 MiB write)",
@@ -361,7 +379,7 @@ def run_ours(args):
         "e2e": {"value": evals / (e2e_ms / args.steps * 1e-3) / 1e9, "unit": "Gevals/s",
                 "mpixel_per_s": size * size / (e2e_ms / args.steps * 1e-3) / 1e6,
                 "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": size * size * (4 if world == 1 else 1), "d2h_bytes_per_step": NR * 8 * S},
+                "h2d_bytes_per_step": size * size * (4 if world == 1 else C), "d2h_bytes_per_step": NR * 8 * S},
         "gpu_launches": launches,
         "roofline": roofline,
     }
@@ -376,13 +394,14 @@ def run_ours(args):
         t0 = time.perf_counter()
         dec, avg_err, iters = handle.decode(q_host, size, size, B, wk, mode, out=h_dec.numpy())
         t_dec = time.perf_counter() - t0
-        rec = ((dec.view(np.uint32) >> 16) & 0xFF).astype(np.float64)
+        du = dec.view(np.uint32)
+        rec = (np.stack([(du >> 16) & 0xFF, (du >> 8) & 0xFF, du & 0xFF], 0) if args.rgb else ((du >> 16) & 0xFF)).astype(np.float64)
         mse = float(np.mean((rec - plane.astype(np.float64)) ** 2))
         line["decode"] = {"iterations": int(iters), "avg_error": float(avg_err), "psnr_db": 10 * np.log10(255.0 ** 2 / max(mse, 1e-12)),
                           "ms_total_host_clock": t_dec * 1e3, "device_ms": handle.timings().total_ms,
                           "mpixel_per_s_per_sweep": size * size * iters / max(handle.timings().total_ms, 1e-9) / 1e3}
     if world == 1 and not args.no_cpu_baseline:
-        R, tcpu, t_pool = cpu_sample(plane, B, wk, 1, args.cpu_seconds, args.iso)
+        R, tcpu, t_pool = cpu_sample(plane, B, wk, 1, args.cpu_seconds, args.iso, args.rgb)
         v = R * ND * n_iso / tcpu
         line["cpu_baseline"] = {
             "value": v / 1e9, "unit": "Gevals/s", "cores": 1, "kind": "port",

@@ -265,7 +265,7 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     int engine = FIC_ENGINE_DIRECT;
     if (h->engine_opt == FIC_ENGINE_UMMA) {
         if (!umma_applicable(g))
-            return set_err(h, FIC_E_ARG, "tcgen05 search needs a grey image and widthKernel == domain blocks per width == per height");
+            return set_err(h, FIC_E_ARG, "tcgen05 search needs widthKernel == domain blocks per width == per height (and, for RGB, blockgroesse 4 or 8 without isometries)");
         engine = FIC_ENGINE_UMMA;
     } else if (h->engine_opt == FIC_ENGINE_AUTO && umma_applicable(g) && (j1 - j0) * g.ND >= (int64_t)1 << 22) {
         engine = FIC_ENGINE_UMMA;
@@ -279,14 +279,21 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     if (engine == FIC_ENGINE_UMMA) {
         // The first kind::f16 search of a handle verifies, once, that this device's f16 tensor path
         // accumulates the integer covariances exactly; a device that does not runs kind::i8 instead.
-        const bool wants_f16 = g.B != 16 && (kind == FIC_UMMA_KIND_F16 || (kind == FIC_UMMA_KIND_AUTO && umma_default_kind(g) == FIC_UMMA_KIND_F16));
+        // RGB has a kind::f16 tensor path only; without an exact f16 path it stays on the CUDA-core kernel.
+        const bool rgb = g.C == 3;
+        const bool wants_f16 = rgb || (g.B != 16 && (kind == FIC_UMMA_KIND_F16 || (kind == FIC_UMMA_KIND_AUTO && umma_default_kind(g) == FIC_UMMA_KIND_F16)));
         if (wants_f16 && h->f16_state == 0) {
             const char *why = nullptr;
             int ok = umma_f16_selftest(h->num_sms, s, &why);
             if (ok < 0) return set_err(h, FIC_E_CUDA, "kind::f16 self-test failed to run: %s", why ? why : "?");
             h->f16_state = ok ? 1 : -1;
         }
-        if (wants_f16 && h->f16_state < 0) kind = FIC_UMMA_KIND_I8;
+        if (wants_f16 && h->f16_state < 0) {
+            if (rgb) engine = FIC_ENGINE_DIRECT;
+            else kind = FIC_UMMA_KIND_I8;
+        }
+    }
+    if (engine == FIC_ENGINE_UMMA) {
         ENSURE(w.opA, S_OPA, umma_opA_bytes(g, j0, j1, h->num_sms, kind));
         ENSURE(w.opB, S_OPB, umma_opB_bytes(g, kind));
     }

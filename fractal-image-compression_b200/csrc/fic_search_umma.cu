@@ -450,6 +450,163 @@ k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------- RGB operands --------
+//
+// The reference's RGB score (FC:760-808) uses ONE covariance for the three channels,
+//     kov = sum gR_i * gD_i,   gR_i = sum_c (r_ci - rmean_c),   gD_i = sum_c (d_ci - dmean_c),
+// accumulated sequentially in binary32, and  r = kov / (vR * vD)  with the small integers vR = sum gR_i and
+// vD = sum gD_i (FC:790-791; the domain's `variance` is never set on this path).  error = vR^2 (1 - r^2) is again a
+// non-increasing function of x = |kov| / vD, so the grey machinery applies with sqrt(varD) := vD:
+//   * operands gR, gD are integers in [-765, 765]: exact in binary16, kind::f16 only;
+//   * a domain with vD == 0 has r = 0 whatever its kov (FC:797): its operand row is zeroed so that it scores x = 0;
+//   * a range row is "safe" when sum |gR_i| * 765 < 2^24: every partial sum of every summation order is then an
+//     integer below 2^24, so the reference's float kov, the tensor-core accumulator and the refine step's FMA chain
+//     are all the same exact integer.  Other rows (blocks of extreme contrast; none in natural images) keep the
+//     CUDA-core kernel, which walks the float sum literally (launch_search_direct_rgb_masked).
+constexpr int kRgbSafeSum = ((1 << 24) - 1) / 765;  // 21931
+
+__device__ __forceinline__ int rgb_dom_vd(const int32_t *__restrict__ dsum, int64_t ND, int64_t j, int n, int dm[3])
+{
+    int vd = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int ds = dsum[(int64_t)c * ND + j];
+        dm[c] = ds / n;
+        vd += ds - n * dm[c];
+    }
+    return vd;
+}
+
+// Sort keys of the RGB pool: vD^2 (plays the role of varD), payload: the domain index.
+__global__ void k_umma_sortkeys_rgb(const int32_t *__restrict__ dsum, int n, int64_t ND, uint32_t *__restrict__ keys,
+                                    int32_t *__restrict__ vals)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ND) return;
+    int dm[3];
+    const int vd = rgb_dom_vd(dsum, ND, j, n, dm);
+    keys[j] = (uint32_t)(vd * vd);
+    vals[j] = (int32_t)j;
+}
+
+// RGB twin of k_umma_pack_domains<B, true>: the operand row holds gD as binary16 (zeros when vD == 0), pos_info =
+// {domain, vD, 0, 0}; the refine step re-reads the operand row itself, so no raw copy is kept.
+template <int B>
+__global__ void __launch_bounds__(128)
+k_umma_pack_domains_rgb(const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
+                        const int32_t *__restrict__ perm, uint8_t *__restrict__ opB, int32_t *__restrict__ pos_dom,
+                        int4 *__restrict__ pos_info, int64_t *__restrict__ dom0_pos, Geom g, int64_t ntiles, uint32_t mult)
+{
+    using L = Lay<B, true>;
+    constexpr int n = B * B;
+    const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tile = pos / kTileN;
+    const int row = (int)(pos % kTileN);
+    const int64_t sp = sweep_to_sorted(pos, mult, ntiles * kChunksPerTile);
+    uint8_t *blob = opB + tile * L::B_TILE_BYTES;
+    uint8_t *rowp = blob + (row >> 3) * L::SBO_B + (row & 7) * 16;
+    constexpr int NCH = n / 8;  // 16-byte chunks (8 binary16) per row
+    float rsd_hi = 0.0f, rsd_lo = __int_as_float(0x7f800000);
+    if (sp >= g.ND) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
+        pos_dom[pos] = -1;
+        pos_info[pos] = make_int4(-1, 0, 0, 0);
+    } else {
+        const int64_t j = perm[sp];
+        const int gx = (int)(j % g.dpw), gy = (int)(j / g.dpw);
+        const int64_t plane = (int64_t)g.sw * g.sh;
+        const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+        int dm[3];
+        const int vd = rgb_dom_vd(dsum, g.ND, j, n, dm);
+        const int dmsum = dm[0] + dm[1] + dm[2];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            int dv[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int k = c * 8 + e;
+                const uint8_t *q = p + (int64_t)(k / B) * g.sw + (k % B);
+                const int d3 = (int)__ldg(q) + (int)__ldg(q + plane) + (int)__ldg(q + 2 * plane);
+                dv[e] = vd != 0 ? d3 - dmsum : 0;
+            }
+            *(uint4 *)(rowp + c * 128) =
+                make_uint4(pack_h2(dv[0], dv[1]), pack_h2(dv[2], dv[3]), pack_h2(dv[4], dv[5]), pack_h2(dv[6], dv[7]));
+        }
+        pos_dom[pos] = (int32_t)j;
+        pos_info[pos] = make_int4((int32_t)j, vd, 0, 0);
+        if (j == 0) *dom0_pos = pos;
+        if (vd > 0) {
+            float r = __double2float_rn(__ddiv_rn(1.0, (double)vd));
+            rsd_hi = r * (1.0f + 4.76837158203125e-07f);  // >= (1 / vD) * (1 + 2^-22), see k_umma_pack_domains
+            rsd_lo = r * (1.0f - 4.76837158203125e-07f);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        rsd_hi = fmaxf(rsd_hi, __shfl_xor_sync(0xffffffffu, rsd_hi, o));
+        rsd_lo = fminf(rsd_lo, __shfl_xor_sync(0xffffffffu, rsd_lo, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (rsd_hi == 0.0f) rsd_lo = 0.0f;
+        *(float2 *)(blob + L::B_OP_BYTES + (row >> 5) * 8) = make_float2(rsd_hi, rsd_lo);
+    }
+    if (threadIdx.x == 0) *(uint4 *)(blob + L::B_OP_BYTES + kChunksPerTile * 8) = make_uint4(0, 0, 0, 0);
+}
+
+// RGB twin of k_umma_pack_ranges<B, true>: gR as binary16; vRout = vR for safe rows and 0 (= "flag nothing") for the
+// rows left to the CUDA-core kernel, which are marked in `direct_rows`.
+template <int B>
+__global__ void __launch_bounds__(128)
+k_umma_pack_ranges_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, uint8_t *__restrict__ opA,
+                       int32_t *__restrict__ vRout, uint8_t *__restrict__ direct_rows, Geom g, int64_t j0, int64_t j1,
+                       int64_t rows_padded)
+{
+    using L = Lay<B, true>;
+    constexpr int n = B * B;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows_padded) return;
+    int64_t sb = i / kRowsPerSB;
+    int rr = (int)(i % kRowsPerSB);
+    int blk = rr / kBlockM, row = rr % kBlockM;
+    uint8_t *rowp = opA + sb * L::A_SB_BYTES + blk * L::A_BLOCK_BYTES + (row >> 3) * L::SBO_A + (row & 7) * 16;
+    constexpr int NCH = n / 8;
+    const int64_t j = j0 + i;
+    if (j >= j1) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
+        vRout[i] = 0;
+        direct_rows[i] = 0;
+        return;
+    }
+    const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    const int64_t plane = (int64_t)g.W * g.H;
+    const uint8_t *p = src + (int64_t)(yr * B) * g.W + xr * B;
+    int rmsum = 0, vR = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int rs = rsum[(int64_t)c * g.NR + j];
+        rmsum += rs / n;
+        vR += rs - n * (rs / n);
+    }
+    int sabs = 0;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        int rv[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int k = c * 8 + e;
+            const uint8_t *q = p + (int64_t)(k / B) * g.W + (k % B);
+            rv[e] = (int)q[0] + (int)q[plane] + (int)q[2 * plane] - rmsum;
+            sabs += abs(rv[e]);
+        }
+        *(uint4 *)(rowp + c * 128) =
+            make_uint4(pack_h2(rv[0], rv[1]), pack_h2(rv[2], rv[3]), pack_h2(rv[4], rv[5]), pack_h2(rv[6], rv[7]));
+    }
+    const bool safe = sabs <= kRgbSafeSum;
+    vRout[i] = safe ? vR : 0;
+    direct_rows[i] = safe ? 0 : 1;
+}
+
 // ---------------------------------------------------------------- PTX wrappers -------
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1199,6 +1356,102 @@ k_umma_refine_iso(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
     if (lane == 0) best[j] = bi == 0x7fffffff ? 0 : bi;
 }
 
+// RGB twin of k_umma_refine (safe rows only, see "RGB operands"): kov is rebuilt from the binary16 operand row of the
+// candidate with a binary32 FMA chain -- exact, every partial sum being an integer below 2^24 -- and scored with the
+// reference's all-float expression (FC:797-803).
+template <int B>
+__global__ void __launch_bounds__(128)
+k_umma_refine_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ opB,
+                  const int4 *__restrict__ pos_info, const uint8_t *__restrict__ direct_rows,
+                  const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
+                  int64_t rows_padded, int64_t rows, int64_t npos, const int64_t *__restrict__ dom0_pos,
+                  int32_t *__restrict__ best, Geom g, int64_t j0)
+{
+    using L = Lay<B, true>;
+    constexpr int n = B * B;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 4 + warp;
+    if (i >= rows) return;
+    if (direct_rows[i]) return;  // scored by the CUDA-core kernel
+    const int64_t j = j0 + i;
+    int rmsum = 0, vRi = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int rs = rsum[(int64_t)c * g.NR + j];
+        rmsum += rs / n;
+        vRi += rs - n * (rs / n);
+    }
+    if (vRi == 0) {  // FC:797 + FC:710: all errors are 0, the first candidate wins
+        if (lane == 0) best[j] = 0;
+        return;
+    }
+    const float vR = (float)vRi;
+    const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    const int64_t plane = (int64_t)g.W * g.H;
+    float gR[n];
+#pragma unroll
+    for (int k = 0; k < n; k++) {
+        const uint8_t *q = src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B);
+        gR[k] = (float)((int)__ldg(q) + (int)__ldg(q + plane) + (int)__ldg(q + 2 * plane) - rmsum);
+    }
+    float be = 10000000.0f;  // FC:698
+    int bi = 0x7fffffff;
+    const float tie_abs = (float)(vRi * vRi) * 4.76837158203125e-07f;  // vR^2 * 2^-21
+    float lb = 0.0f, th = -1.0f;
+    auto consider = [&](int64_t pos) {
+        const int4 pi = __ldg(pos_info + pos);  // {domain index (-1: padding), vD, -, -}
+        const int idx = pi.x;
+        if (idx >= 0) {
+            const int row = (int)(pos % kTileN);
+            const uint8_t *rowp = opB + (pos / kTileN) * L::B_TILE_BYTES + (row >> 3) * L::SBO_B + (row & 7) * 16;
+            float kov = 0.0f;
+#pragma unroll
+            for (int c = 0; c < n / 8; c++) {
+                const uint4 d = __ldg((const uint4 *)(rowp + c * 128));
+                const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float2 f = __half22float2(*(const __half2 *)&w[e]);
+                    kov = __fmaf_rn(gR[c * 8 + 2 * e], f.x, kov);
+                    kov = __fmaf_rn(gR[c * 8 + 2 * e + 1], f.y, kov);
+                }
+            }
+            const float vD = (float)pi.y;
+            const float ax = pi.y > 0 ? __fdiv_rn(fabsf(kov), vD) : 0.0f;  // x within (1 +- 2^-24)
+            if (ax * (1.0f + 2.384185791015625e-07f) > th) {
+                float r = 0.0f;
+                if (pi.y != 0) r = __fdiv_rn(kov, __fmul_rn(vR, vD));   // FC:797-800 (vR != 0 here)
+                r = __fmul_rn(r, r);
+                const float err = __fmul_rn(__fmul_rn(vR, vR), __fsub_rn(1.0f, r));  // FC:803
+                if (err < be || (err == be && idx < bi)) { be = err; bi = idx; }
+                const float xlo = ax * (1.0f - 2.384185791015625e-07f);
+                if (xlo > lb) { lb = xlo; th = flag_threshold(lb, tie_abs); }
+            }
+        }
+    };
+    if (lane == 0) consider(*dom0_pos);
+    const int n_lists = 2 * n_chunks;
+    const int my_cnt = lane < n_lists ? flag_cnt[((int64_t)(lane >> 1) * rows_padded + i) * 2 + (lane & 1)] : 0;
+    const bool overflow = __any_sync(0xffffffffu, my_cnt > kFlagCap);
+    if (!overflow) {
+        for (int lh = 0; lh < n_lists; lh++) {
+            const int cnt = __shfl_sync(0xffffffffu, my_cnt, lh);
+            if (cnt == 0) continue;
+            const int32_t *lst = flag_list + (((int64_t)(lh >> 1) * rows_padded + i) * 2 + (lh & 1)) * kFlagCap;
+            const int mine = lane < cnt ? lst[lane] : 0;
+            for (int e = 0; e < cnt; e++) consider((int64_t)__shfl_sync(0xffffffffu, mine, e) * 32 + lane);
+        }
+    } else {
+        for (int64_t pos = lane; pos < npos; pos += 32) consider(pos);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        float e2 = __shfl_down_sync(0xffffffffu, be, o);
+        int i2 = __shfl_down_sync(0xffffffffu, bi, o);
+        if (e2 < be || (e2 == be && i2 < bi)) { be = e2; bi = i2; }
+    }
+    if (lane == 0) best[j] = bi == 0x7fffffff ? 0 : bi;
+}
+
 // ---------------------------------------------------------------- host side ------------
 
 inline int64_t pad_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -1274,9 +1527,9 @@ template <int B, bool F16>
 size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p = make_plan(g, rows, num_sms);
-    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap][row_lb u32]
+    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap][row_lb u32][direct_rows u8]
     return (size_t)p.n_sb * Lay<B, F16>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 2 * 4 * (1 + kFlagCap) +
-           (size_t)p.rp * 4 + 1024;
+           (size_t)p.rp * 4 + (size_t)p.rp + 1024;
 }
 
 template <int B, bool F16>
@@ -1294,6 +1547,9 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     int32_t *flag_cnt = vR + rp;
     int32_t *flag_list = flag_cnt + rp * p.n_chunks * 2;
     uint32_t *row_lb = (uint32_t *)(flag_list + rp * p.n_chunks * 2 * kFlagCap);  // per operand row: best lower bound of max x reached by finished units
+    uint8_t *direct_rows = (uint8_t *)(row_lb + rp);  // RGB only: rows left to the CUDA-core kernel
+    const bool rgb = g.C == 3;                        // kind::f16 only (see "RGB operands")
+    if (rgb && !F16) { *err = "the RGB tensor path is kind::f16 only"; return -1; }
     OpBLayout<B, F16> lay(g, p);
     int32_t *pos_dom = (int32_t *)(w.opB + lay.off_posdom);
     int4 *pos_info = (int4 *)(w.opB + lay.off_posinfo);
@@ -1304,15 +1560,25 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     // 1. domains by increasing varD
     cub::DoubleBuffer<uint32_t> dk((uint32_t *)(w.opB + lay.off_keys0), (uint32_t *)(w.opB + lay.off_keys1));
     cub::DoubleBuffer<int32_t> dv((int32_t *)(w.opB + lay.off_vals0), (int32_t *)(w.opB + lay.off_vals1));
-    k_umma_sortkeys<<<(unsigned)((g.ND + 255) / 256), 256, 0, s>>>(w.dsum, w.dsq, g.n, g.ND, dk.Current(), dv.Current());
+    if (rgb) k_umma_sortkeys_rgb<<<(unsigned)((g.ND + 255) / 256), 256, 0, s>>>(w.dsum, g.n, g.ND, dk.Current(), dv.Current());
+    else k_umma_sortkeys<<<(unsigned)((g.ND + 255) / 256), 256, 0, s>>>(w.dsum, w.dsq, g.n, g.ND, dk.Current(), dv.Current());
     size_t temp_bytes = lay.temp_bytes;
     ce = cub::DeviceRadixSort::SortPairs(w.opB + lay.off_temp, temp_bytes, dk, dv, (int)g.ND, 0, 24, s);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
     launches += 4;  // key kernel + radix passes (approximate; they are not the timed kernel)
     // 2. operand blobs
-    k_umma_pack_domains<B, F16><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(
-        w.dec, w.dsum, w.dsq, dv.Current(), w.opB, pos_dom, pos_info, pos_raw, dom0, g, p.ntiles, p.mult);
-    k_umma_pack_ranges<B, F16><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
+    if constexpr (F16) {
+        if (rgb) {
+            k_umma_pack_domains_rgb<B><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(
+                w.dec, w.dsum, dv.Current(), w.opB, pos_dom, pos_info, dom0, g, p.ntiles, p.mult);
+            k_umma_pack_ranges_rgb<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, direct_rows, g, j0, j1, rp);
+        }
+    }
+    if (!rgb) {
+        k_umma_pack_domains<B, F16><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(
+            w.dec, w.dsum, w.dsq, dv.Current(), w.opB, pos_dom, pos_info, pos_raw, dom0, g, p.ntiles, p.mult);
+        k_umma_pack_ranges<B, F16><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
+    }
     launches += 2;
     // 3. the fused search
     using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int32_t *, int32_t *, uint32_t *, int, int,
@@ -1338,7 +1604,13 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     if (k1) cudaEventRecord(k1, s);
     // 4. exact refine of the flagged chunks
     if (!(dbg & 8u)) {
-        if (g.n_iso > 1)
+        if (rgb) {
+            if constexpr (F16) {
+                k_umma_refine_rgb<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, w.opB, pos_info, direct_rows, flag_list,
+                                                                                flag_cnt, p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
+                launches += launch_search_direct_rgb_masked(w, g, j0, j1, direct_rows, s);
+            }
+        } else if (g.n_iso > 1)
             k_umma_refine_iso<B><<<(unsigned)((j1 - j0 + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_info, flag_list, flag_cnt,
                                                                              p.n_chunks, rp, j1 - j0, p.npos, dom0, w.best, g, j0);
         else
@@ -1365,6 +1637,7 @@ int umma_default_kind(const Geom &g) { return g.B == 16 ? FIC_UMMA_KIND_I8 : FIC
 static bool use_f16(const Geom &g, int kind)
 {
     if (g.B == 16) return false;
+    if (g.C == 3) return true;  // the RGB operands need binary16 (see "RGB operands")
     return (kind == FIC_UMMA_KIND_AUTO ? umma_default_kind(g) : kind) == FIC_UMMA_KIND_F16;
 }
 
@@ -1506,7 +1779,9 @@ int umma_f16_selftest(int num_sms, cudaStream_t s, const char **err)
 
 bool umma_applicable(const Geom &g)
 {
-    return g.C == 1 && (g.B == 4 || g.B == 8 || g.B == 16) && g.wk == g.dpw && g.wk == g.dph;
+    if (g.wk != g.dpw || g.wk != g.dph) return false;
+    if (g.C == 3) return g.n_iso == 1 && (g.B == 4 || g.B == 8);  // kind::f16 only, which B = 16 does not have
+    return g.B == 4 || g.B == 8 || g.B == 16;
 }
 
 size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms, int kind)

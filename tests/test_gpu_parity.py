@@ -343,6 +343,8 @@ def test_randomised_parity_sweep(fic, handle, oracle):
         engines = [(fic.FIC_ENGINE_DIRECT, fic.FIC_UMMA_KIND_AUTO)]
         if not rgb and wk == dpw == dph:
             engines += [(fic.FIC_ENGINE_UMMA, fic.FIC_UMMA_KIND_I8), (fic.FIC_ENGINE_UMMA, fic.FIC_UMMA_KIND_F16)]
+        if rgb and wk == dpw == dph and B != 16:   # RGB tensor path: kind::f16 only
+            engines += [(fic.FIC_ENGINE_UMMA, fic.FIC_UMMA_KIND_AUTO)]
         for eng, mma in engines:
             handle.set_engine(eng)
             handle.set_umma_kind(mma)
