@@ -58,7 +58,7 @@ extern "C" {
 #define FIC_MODE_GREY_ISO 2 /* {c, a, b, k} per range; k = isometry 0..7 */
 
 /* Search engine selection (fic_set_option(FIC_OPT_ENGINE, ...)). */
-#define FIC_ENGINE_AUTO 0   /* tcgen05 fused search when the window is the whole pool */
+#define FIC_ENGINE_AUTO 0   /* tcgen05 fused search when the window is the whole pool (RGB: blockgroesse 4, 8) */
 #define FIC_ENGINE_DIRECT 1 /* direct (CUDA-core) windowed search for every window    */
 #define FIC_ENGINE_UMMA 2   /* force the tcgen05 search; FIC_E_ARG if not applicable  */
 
