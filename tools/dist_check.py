@@ -19,10 +19,10 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 rank, world = dist.get_rank(), dist.get_world_size()
 ok = True
-for W, B, rgb in [(1024, 8, False), (512, 4, False), (256, 8, True), (512, 8, fic.FIC_MODE_GREY_ISO)]:
+for W, B, rgb in [(1024, 8, False), (512, 4, False), (256, 8, True), (1024, 8, True), (512, 8, fic.FIC_MODE_GREY_ISO)]:
     if rgb is True:
         planes_np = np.stack([fic.synth.structured(W, W, s) for s in (1, 2, 3)])
-        wk = 2
+        wk = 2 if W == 256 else 2 * W // B - 3   # the reference's default window / the full pool (tensor cores)
     else:
         planes_np = fic.synth.structured(W, W, 3)[None]
         wk = 2 * W // B - 3

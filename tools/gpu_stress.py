@@ -53,18 +53,27 @@ def main():
         wk = 2 * r - 3
         kind = int(rng.integers(0, 7))
         iso = bool(rng.random() < 0.25)
-        mode = fic.FIC_MODE_GREY_ISO if iso else fic.FIC_MODE_GREY
-        img = fic.synth.grey_to_argb(plane(rng, W, W, kind))
+        rgb = not iso and B != 16 and bool(rng.random() < 0.35)   # RGB tensor path: kind::f16, B = 4 or 8
+        mode = fic.FIC_MODE_GREY_ISO if iso else (fic.FIC_MODE_RGB if rgb else fic.FIC_MODE_GREY)
+        if rgb:
+            # channels equal (largest |gR|: the rows the CUDA-core kernel keeps), independent, or of mixed kinds
+            how = int(rng.integers(0, 3))
+            first = plane(rng, W, W, kind)
+            v = [first if how == 0 else plane(rng, W, W, kind if how == 1 else int(rng.integers(0, 7))) for _ in range(3)]
+            v = [a.astype(np.uint32) for a in v]
+            img = (np.uint32(0xFF000000) | (v[0] << np.uint32(16)) | (v[1] << np.uint32(8)) | v[2]).view(np.int32)
+        else:
+            img = fic.synth.grey_to_argb(plane(rng, W, W, kind))
         h.set_engine(fic.FIC_ENGINE_DIRECT)
         i0, q0 = h.encode(img, B, wk, rgb=mode)
         h.set_engine(fic.FIC_ENGINE_UMMA)
-        for mma in (fic.FIC_UMMA_KIND_I8, fic.FIC_UMMA_KIND_F16):
+        for mma in ((fic.FIC_UMMA_KIND_F16,) if rgb else (fic.FIC_UMMA_KIND_I8, fic.FIC_UMMA_KIND_F16)):
             h.set_umma_kind(mma)
             i1, q1 = h.encode(img, B, wk, rgb=mode)
             same = (q0 == q1).all() and np.array_equal(i0.view(np.uint32)[~np.isnan(i0)], i1.view(np.uint32)[~np.isnan(i1)])
             if not same:
                 bad += 1
-                print(f"MISMATCH case {n}: W={W} B={B} kind={kind} iso={iso} mma={mma} rows={(q0 != q1).any(1).sum()}")
+                print(f"MISMATCH case {n}: W={W} B={B} kind={kind} iso={iso} rgb={rgb} mma={mma} rows={(q0 != q1).any(1).sum()}")
         h.set_umma_kind(fic.FIC_UMMA_KIND_AUTO)
         h.set_engine(fic.FIC_ENGINE_AUTO)
     print(f"STRESS {'PASS' if bad == 0 else 'FAIL'}: {cases} cases, {bad} mismatches")
