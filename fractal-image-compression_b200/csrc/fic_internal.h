@@ -60,7 +60,6 @@ int launch_domain_stats(const uint8_t *d_dec, int32_t *d_dsum, int32_t *d_dsq, c
                         cudaStream_t s);
 int launch_range_stats(const uint8_t *d_src, int32_t *d_rsum, const Geom &g, cudaStream_t s);
 int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, cudaStream_t s);
-int launch_search_direct_rgb_masked(const Work &w, const Geom &g, int64_t j0, int64_t j1, const uint8_t *only, cudaStream_t s);
 int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_info, int32_t *d_q,
                  cudaStream_t s);
 

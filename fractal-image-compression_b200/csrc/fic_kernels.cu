@@ -349,12 +349,11 @@ __device__ __forceinline__ float rgb_range_prep(const uint8_t *src, const int32_
 __global__ void __launch_bounds__(kDirectThreads)
 k_search_direct_rgb(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec,
                     const int32_t *__restrict__ dsum, const int32_t *__restrict__ rsum,
-                    int32_t *__restrict__ best, Geom g, int64_t j0, const uint8_t *__restrict__ only)
+                    int32_t *__restrict__ best, Geom g, int64_t j0)
 {
     __shared__ float s_gR[256];
     __shared__ float s_err[kDirectThreads / 32];
     __shared__ int s_c[kDirectThreads / 32];
-    if (only && !only[blockIdx.x]) return;  // masked launch: the tensor-core path scored this range block
     int64_t j = j0 + blockIdx.x;
     int rm[3];
     float vR = rgb_range_prep(src, rsum, g, j, s_gR, rm);
@@ -444,20 +443,12 @@ int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, c
         else if (g.C == 1)
             k_search_direct_grey<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, g, at);
         else
-            k_search_direct_rgb<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.rsum, w.best, g, at, nullptr);
+            k_search_direct_rgb<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.rsum, w.best, g, at);
         left -= chunk;
         at += chunk;
         launches++;
     }
     return launches;
-}
-
-// The RGB range blocks [j0, j1) whose byte in only[j - j0] is set (see "RGB operands" in fic_search_umma.cu).
-int launch_search_direct_rgb_masked(const Work &w, const Geom &g, int64_t j0, int64_t j1, const uint8_t *only, cudaStream_t s)
-{
-    if (j1 <= j0) return 0;
-    k_search_direct_rgb<<<(unsigned)(j1 - j0), kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.rsum, w.best, g, j0, only);
-    return 1;
 }
 
 // ------------------------------------------------------------------------------------

@@ -459,11 +459,14 @@ k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ 
 // non-increasing function of x = |kov| / vD, so the grey machinery applies with sqrt(varD) := vD:
 //   * operands gR, gD are integers in [-765, 765]: exact in binary16, kind::f16 only;
 //   * a domain with vD == 0 has r = 0 whatever its kov (FC:797): its operand row is zeroed so that it scores x = 0;
-//   * a range row is "safe" when sum |gR_i| * 765 < 2^24: every partial sum of every summation order is then an
-//     integer below 2^24, so the reference's float kov, the tensor-core accumulator and the refine step's FMA chain
-//     are all the same exact integer.  Other rows (blocks of extreme contrast; none in natural images) keep the
-//     CUDA-core kernel, which walks the float sum literally (launch_search_direct_rgb_masked).
-constexpr int kRgbSafeSum = ((1 << 24) - 1) / 765;  // 21931
+//   * exactness for B <= 8.  A channel of a block, centred by its integer mean m = floor(mu), has
+//     sum (v - m)^2 = sum (v - mu)^2 + n (mu - m)^2 <= n (127.5^2 + 1)   (values in [0, 255]: variance <= 127.5^2),
+//     so ||gR||_2, ||gD||_2 <= 3 sqrt(n (127.5^2 + 1)) (triangle inequality over the channels), and by Cauchy-Schwarz
+//     every partial sum of |gR_i gD_i| over any subset of the pixels is <= 9 n (127.5^2 + 1) = 9 364 176 < 2^24 at
+//     n = 64.  Every partial sum of every summation order is therefore an integer below 2^24: the reference's
+//     sequential float kov, the tensor-core accumulator and the refine step's FMA chain are the same exact integer
+//     for every block (the bound 64 * 765^2 of a term-by-term estimate is not attained).  B = 16 (bound 3.7e7) has no
+//     such guarantee -- and no kind::f16 variant: RGB at B = 16 stays on the CUDA-core kernel.
 
 __device__ __forceinline__ int rgb_dom_vd(const int32_t *__restrict__ dsum, int64_t ND, int64_t j, int n, int dm[3])
 {
@@ -553,13 +556,11 @@ k_umma_pack_domains_rgb(const uint8_t *__restrict__ dec, const int32_t *__restri
     if (threadIdx.x == 0) *(uint4 *)(blob + L::B_OP_BYTES + kChunksPerTile * 8) = make_uint4(0, 0, 0, 0);
 }
 
-// RGB twin of k_umma_pack_ranges<B, true>: gR as binary16; vRout = vR for safe rows and 0 (= "flag nothing") for the
-// rows left to the CUDA-core kernel, which are marked in `direct_rows`.
+// RGB twin of k_umma_pack_ranges<B, true>: gR as binary16.
 template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_pack_ranges_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, uint8_t *__restrict__ opA,
-                       int32_t *__restrict__ vRout, uint8_t *__restrict__ direct_rows, Geom g, int64_t j0, int64_t j1,
-                       int64_t rows_padded)
+                       int32_t *__restrict__ vRout, Geom g, int64_t j0, int64_t j1, int64_t rows_padded)
 {
     using L = Lay<B, true>;
     constexpr int n = B * B;
@@ -575,7 +576,6 @@ k_umma_pack_ranges_rgb(const uint8_t *__restrict__ src, const int32_t *__restric
 #pragma unroll
         for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
         vRout[i] = 0;
-        direct_rows[i] = 0;
         return;
     }
     const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
@@ -588,7 +588,6 @@ k_umma_pack_ranges_rgb(const uint8_t *__restrict__ src, const int32_t *__restric
         rmsum += rs / n;
         vR += rs - n * (rs / n);
     }
-    int sabs = 0;
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
         int rv[8];
@@ -597,14 +596,11 @@ k_umma_pack_ranges_rgb(const uint8_t *__restrict__ src, const int32_t *__restric
             const int k = c * 8 + e;
             const uint8_t *q = p + (int64_t)(k / B) * g.W + (k % B);
             rv[e] = (int)q[0] + (int)q[plane] + (int)q[2 * plane] - rmsum;
-            sabs += abs(rv[e]);
         }
         *(uint4 *)(rowp + c * 128) =
             make_uint4(pack_h2(rv[0], rv[1]), pack_h2(rv[2], rv[3]), pack_h2(rv[4], rv[5]), pack_h2(rv[6], rv[7]));
     }
-    const bool safe = sabs <= kRgbSafeSum;
-    vRout[i] = safe ? vR : 0;
-    direct_rows[i] = safe ? 0 : 1;
+    vRout[i] = vR;
 }
 
 // ---------------------------------------------------------------- PTX wrappers -------
@@ -1356,14 +1352,13 @@ k_umma_refine_iso(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
     if (lane == 0) best[j] = bi == 0x7fffffff ? 0 : bi;
 }
 
-// RGB twin of k_umma_refine (safe rows only, see "RGB operands"): kov is rebuilt from the binary16 operand row of the
+// RGB twin of k_umma_refine (see "RGB operands"): kov is rebuilt from the binary16 operand row of the
 // candidate with a binary32 FMA chain -- exact, every partial sum being an integer below 2^24 -- and scored with the
 // reference's all-float expression (FC:797-803).
 template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_refine_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ opB,
-                  const int4 *__restrict__ pos_info, const uint8_t *__restrict__ direct_rows,
-                  const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
+                  const int4 *__restrict__ pos_info, const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
                   int64_t rows_padded, int64_t rows, int64_t npos, const int64_t *__restrict__ dom0_pos,
                   int32_t *__restrict__ best, Geom g, int64_t j0)
 {
@@ -1372,7 +1367,6 @@ k_umma_refine_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * 4 + warp;
     if (i >= rows) return;
-    if (direct_rows[i]) return;  // scored by the CUDA-core kernel
     const int64_t j = j0 + i;
     int rmsum = 0, vRi = 0;
 #pragma unroll
@@ -1527,9 +1521,9 @@ template <int B, bool F16>
 size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p = make_plan(g, rows, num_sms);
-    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap][row_lb u32][direct_rows u8]
+    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap][row_lb u32]
     return (size_t)p.n_sb * Lay<B, F16>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 2 * 4 * (1 + kFlagCap) +
-           (size_t)p.rp * 4 + (size_t)p.rp + 1024;
+           (size_t)p.rp * 4 + 1024;
 }
 
 template <int B, bool F16>
@@ -1547,7 +1541,6 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     int32_t *flag_cnt = vR + rp;
     int32_t *flag_list = flag_cnt + rp * p.n_chunks * 2;
     uint32_t *row_lb = (uint32_t *)(flag_list + rp * p.n_chunks * 2 * kFlagCap);  // per operand row: best lower bound of max x reached by finished units
-    uint8_t *direct_rows = (uint8_t *)(row_lb + rp);  // RGB only: rows left to the CUDA-core kernel
     const bool rgb = g.C == 3;                        // kind::f16 only (see "RGB operands")
     if (rgb && !F16) { *err = "the RGB tensor path is kind::f16 only"; return -1; }
     OpBLayout<B, F16> lay(g, p);
@@ -1571,7 +1564,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
         if (rgb) {
             k_umma_pack_domains_rgb<B><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(
                 w.dec, w.dsum, dv.Current(), w.opB, pos_dom, pos_info, dom0, g, p.ntiles, p.mult);
-            k_umma_pack_ranges_rgb<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, direct_rows, g, j0, j1, rp);
+            k_umma_pack_ranges_rgb<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
         }
     }
     if (!rgb) {
@@ -1605,11 +1598,9 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     // 4. exact refine of the flagged chunks
     if (!(dbg & 8u)) {
         if (rgb) {
-            if constexpr (F16) {
-                k_umma_refine_rgb<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, w.opB, pos_info, direct_rows, flag_list,
-                                                                                flag_cnt, p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
-                launches += launch_search_direct_rgb_masked(w, g, j0, j1, direct_rows, s);
-            }
+            if constexpr (F16)
+                k_umma_refine_rgb<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, w.opB, pos_info, flag_list, flag_cnt,
+                                                                                p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
         } else if (g.n_iso > 1)
             k_umma_refine_iso<B><<<(unsigned)((j1 - j0 + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_info, flag_list, flag_cnt,
                                                                              p.n_chunks, rp, j1 - j0, p.npos, dom0, w.best, g, j0);
@@ -1687,7 +1678,9 @@ double measure_mma_peak(int num_sms, cudaStream_t s, int reps, int f16, int n_co
 
 namespace {
 
-// Integer reference of every accumulator the search kernel dumped: kov[i][pos] = sum (r - rmean)(d - dmean).
+// Integer reference of every accumulator the search kernel dumped.  Grey: kov[i][pos] = sum (r - rmean)(d - dmean);
+// RGB (g.C == 3): sum gR * gD with the channel-summed centred values, 0 for a domain with vD == 0 (its operand row
+// is zeroed, see "RGB operands").
 __global__ void k_umma_selftest_check(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec,
                                       const int32_t *__restrict__ rsum, const int32_t *__restrict__ dsum,
                                       const int32_t *__restrict__ pos_dom, const int32_t *__restrict__ dump, int64_t dump_ld,
@@ -1699,12 +1692,26 @@ __global__ void k_umma_selftest_check(const uint8_t *__restrict__ src, const uin
     const int j = pos_dom[pos];
     if (j < 0) return;
     const int B = g.B, n = g.n;
-    const int rmean = rsum[i] / n, dmean = dsum[j] / n;
+    int rmean = 0, dmean = 0, vd = 0;
+    for (int c = 0; c < g.C; c++) {
+        rmean += rsum[(int64_t)c * g.NR + i] / n;
+        const int ds = dsum[(int64_t)c * g.ND + j];
+        dmean += ds / n;
+        vd += ds - n * (ds / n);
+    }
     const uint8_t *r = src + (int64_t)((i / g.rpw) * B) * g.W + (i % g.rpw) * B;
     const uint8_t *d = dec + (int64_t)((j / g.dpw) * g.step) * g.sw + (j % g.dpw) * g.step;
+    const int64_t rplane = (int64_t)g.W * g.H, dplane = (int64_t)g.sw * g.sh;
     int kov = 0;
-    for (int k = 0; k < n; k++)
-        kov += ((int)r[(int64_t)(k / B) * g.W + k % B] - rmean) * ((int)d[(int64_t)(k / B) * g.sw + k % B] - dmean);
+    for (int k = 0; k < n; k++) {
+        int rv = -rmean, dv = -dmean;
+        for (int c = 0; c < g.C; c++) {
+            rv += (int)r[c * rplane + (int64_t)(k / B) * g.W + k % B];
+            dv += (int)d[c * dplane + (int64_t)(k / B) * g.sw + k % B];
+        }
+        kov += rv * dv;
+    }
+    if (g.C == 3 && vd == 0) kov = 0;
     if (dump[i * dump_ld + pos] != kov) atomicAdd(bad, 1u);
 }
 
@@ -1718,8 +1725,9 @@ __global__ void k_umma_selftest_check(const uint8_t *__restrict__ src, const uin
 int umma_f16_selftest(int num_sms, cudaStream_t s, const char **err)
 {
     const int W = 128, B = 8;
-    Geom g;
-    if (make_geom(W, W, B, 2 * (W / B) - 3, 0, &g, err)) return -1;
+    Geom g, g3;  // the grey pass and the RGB pass (three equal channels: 9 x the grey covariances, up to 9.3e6)
+    if (make_geom(W, W, B, 2 * (W / B) - 3, FIC_MODE_GREY, &g, err) || make_geom(W, W, B, 2 * (W / B) - 3, FIC_MODE_RGB, &g3, err))
+        return -1;
     std::vector<uint8_t> img((size_t)W * W);
     for (int y = 0; y < W; y++)
         for (int x = 0; x < W; x++) {
@@ -1741,11 +1749,11 @@ int umma_f16_selftest(int num_sms, cudaStream_t s, const char **err)
     unsigned int *bad = nullptr;
     cudaError_t ce = cudaSuccess;
     auto alloc = [&](void **ptr, size_t bytes) { if (ce == cudaSuccess) ce = cudaMalloc(ptr, bytes); };
-    alloc((void **)&w.src, (size_t)W * W);
-    alloc((void **)&w.dec, (size_t)g.sw * g.sh);
-    alloc((void **)&w.dsum, 4 * g.ND);
-    alloc((void **)&w.dsq, 4 * g.ND);
-    alloc((void **)&w.rsum, 4 * g.NR);
+    alloc((void **)&w.src, 3 * (size_t)W * W);
+    alloc((void **)&w.dec, 3 * (size_t)g.sw * g.sh);
+    alloc((void **)&w.dsum, 3 * 4 * g.ND);
+    alloc((void **)&w.dsq, 3 * 4 * g.ND);
+    alloc((void **)&w.rsum, 3 * 4 * g.NR);
     alloc((void **)&w.best, 4 * g.NR);
     alloc((void **)&w.opA, opA_bytes_t<8, true>(g, g.NR, num_sms));
     alloc((void **)&w.opB, OpBLayout<8, true>(g, p).total);
@@ -1753,17 +1761,21 @@ int umma_f16_selftest(int num_sms, cudaStream_t s, const char **err)
     alloc((void **)&bad, 4);
     int result = -1;
     if (ce == cudaSuccess) {
-        cudaMemcpyAsync(w.src, img.data(), img.size(), cudaMemcpyHostToDevice, s);
-        cudaMemsetAsync(dump, 0x7f, (size_t)p.rp * dump_ld * 4, s);
+        for (int c = 0; c < 3; c++) cudaMemcpyAsync(w.src + (size_t)c * W * W, img.data(), img.size(), cudaMemcpyHostToDevice, s);
         cudaMemsetAsync(bad, 0, 4, s);
-        launch_decimate(w.src, w.dec, g, s);
-        launch_domain_stats(w.dec, w.dsum, w.dsq, g, s);
-        launch_range_stats(w.src, w.rsum, g, s);
-        if (launch_t<8, true>(w, g, 0, g.NR, num_sms, s, err, dump, dump_ld, nullptr, 0) >= 0) {
-            const int64_t total = g.NR * p.npos;
+        bool launched = true;
+        for (const Geom *gp : {(const Geom *)&g, (const Geom *)&g3}) {
+            cudaMemsetAsync(dump, 0x7f, (size_t)p.rp * dump_ld * 4, s);
+            launch_decimate(w.src, w.dec, *gp, s);
+            launch_domain_stats(w.dec, w.dsum, w.dsq, *gp, s);
+            launch_range_stats(w.src, w.rsum, *gp, s);
+            if (launch_t<8, true>(w, *gp, 0, gp->NR, num_sms, s, err, dump, dump_ld, nullptr, 0) < 0) { launched = false; break; }
+            const int64_t total = gp->NR * p.npos;
             k_umma_selftest_check<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
                 w.src, w.dec, w.rsum, w.dsum, (const int32_t *)(w.opB + OpBLayout<8, true>(g, p).off_posdom), dump, dump_ld,
-                p.npos, g, bad);
+                p.npos, *gp, bad);
+        }
+        if (launched) {
             unsigned int hbad = 1;
             ce = cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, s);
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);

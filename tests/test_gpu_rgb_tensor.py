@@ -1,9 +1,9 @@
 """RGB full-pool search on the tensor cores (tcgen05 kind::f16) against the oracle.
 
 The reference scores RGB candidates with one covariance for the three channels, accumulated sequentially in
-binary32 (FC:760-808).  The tensor path takes the range blocks for which that sum is provably an exact integer
-("safe" rows, see "RGB operands" in csrc/fic_search_umma.cu) and leaves the others to the CUDA-core kernel;
-every case below must equal the oracle bit for bit whichever kernel scored a row.
+binary32 (FC:760-808).  For B <= 8 that sum is provably an exact integer for every pair of blocks ("RGB operands" in
+csrc/fic_search_umma.cu), which is what lets the tensor cores compute it; the extreme-contrast cases below sit at
+the top of the magnitude range (|kov| up to 9.3e6 < 2^24).  Every case must equal the oracle bit for bit.
 """
 import numpy as np
 import pytest
@@ -32,10 +32,10 @@ def _planes(fic, kind, W, H):
     if kind == "grey":      # r = g = b: every gR, gD is three times the grey value
         p = fic.synth.structured(W, H, 7)
         return np.stack([p, p, p], -1)
-    if kind == "binary":    # 0 / 255 in all channels at once: sum |gR| * 765 >= 2^24 -> rows of the CUDA-core kernel
+    if kind == "binary":    # 0 / 255 in all channels at once: the largest |gR|, |gD| and |kov| (9.3e6) the path can meet
         p = np.kron((fic.synth.noise(W // 4, H // 4, 5) >> 7).astype(np.uint8) * 255, np.ones((4, 4), np.uint8))
         return np.stack([p, p, p], -1)
-    if kind == "mixed":     # left half natural, right half extreme contrast: both kernels in one image
+    if kind == "mixed":     # left half natural, right half extreme contrast
         a = np.stack([fic.synth.structured(W, H, s) for s in (8, 9, 10)], -1)
         b = np.kron((fic.synth.noise(W // 2, H // 2, 11) >> 7).astype(np.uint8) * 255, np.ones((2, 2), np.uint8))
         a[:, W // 2:, :] = b[:, W // 2:, None]

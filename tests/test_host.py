@@ -86,3 +86,38 @@ def test_world_size_2_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "SHARDED_OK 0" in r.stdout and "SHARDED_OK 2" in r.stdout
+
+
+def test_rgb_covariance_partial_sums_stay_exact_for_b8():
+    """The bound behind the RGB tensor path: for B <= 8 every partial sum of |gR_i * gD_i| is below
+    2^24, whatever the pixels.  Checked on adversarial blocks (0/255 patterns, aligned and anti-aligned, all channels
+    equal) and random ones, with the integer means the reference uses."""
+    rng = np.random.default_rng(5)
+    n = 64
+    bound = 9 * n * (127.5 ** 2 + 1)
+    assert bound < 2 ** 24
+    worst = 0
+
+    def centred(block):                      # block: (3, n) ints in [0, 255] -> sum over channels of v - floor(mean)
+        return (block - block.sum(1, keepdims=True) // n).sum(0)
+
+    blocks = []
+    for k in range(0, n + 1, 4):             # k pixels at 255, the rest 0, all channels equal
+        b = np.zeros((3, n), np.int64)
+        b[:, :k] = 255
+        blocks.append(b)
+    for _ in range(200):
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            blocks.append(rng.integers(0, 256, (3, n)))
+        elif kind == 1:
+            blocks.append(rng.integers(0, 2, (3, n)) * 255)
+        else:
+            blocks.append(np.repeat(rng.integers(0, 2, (1, n)) * 255, 3, 0))
+    g = np.stack([centred(b) for b in blocks])            # (m, n)
+    assert np.abs(g).max() <= 765
+    l2 = np.sqrt((g.astype(np.float64) ** 2).sum(1))
+    assert l2.max() <= 3 * np.sqrt(n * (127.5 ** 2 + 1)) + 1e-9
+    total = np.abs(g)[:, None, :] * np.abs(g)[None, :, :]  # |gR_i * gD_i| for every pair of blocks
+    worst = int(total.sum(-1).max())
+    assert worst <= bound and worst > 9_000_000            # the bound is nearly attained, and it holds
