@@ -63,7 +63,8 @@ extern "C" {
 #define FIC_ENGINE_UMMA 2   /* force the tcgen05 search; FIC_E_ARG if not applicable  */
 
 /* Tensor-core instruction kind of the tcgen05 search (fic_set_option(FIC_OPT_UMMA_KIND, ...)).
- * Both produce the exact integer covariances, hence the same codes. */
+ * Both produce the exact integer covariances, hence the same codes.  RGB images have a kind::f16 path only
+ * (B = 4, 8): this option does not apply to them. */
 #define FIC_UMMA_KIND_AUTO 0 /* kind::f16 for B = 4, 8; kind::i8 for B = 16               */
 #define FIC_UMMA_KIND_I8 1   /* u8 x s8 -> s32, two s8 digits per centred domain pixel    */
 #define FIC_UMMA_KIND_F16 2  /* binary16 x binary16 -> binary32 (B = 16 still runs i8)    */
@@ -72,7 +73,7 @@ extern "C" {
 #define FIC_OPT_UMMA_KIND 2
 /* Read-only (fic_get_option): 1 if this device's kind::f16 tensor path reproduced the exact integer
  * covariances in the library's self-test (run once per handle, before the first kind::f16 search);
- * 0 means the handle silently runs kind::i8 instead. */
+ * 0 means the handle silently runs kind::i8 (RGB: the CUDA-core search) instead. */
 #define FIC_OPT_F16_EXACT 3
 
 typedef struct fic_handle fic_handle;
