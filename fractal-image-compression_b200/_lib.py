@@ -27,6 +27,7 @@ ABI_SYMBOLS = [
     "fic_get_timings", "fic_geometry", "fic_encode_grey", "fic_encode_rgb", "fic_encode_grey_iso", "fic_encode_planes_dev",
     "fic_sync", "fic_decode", "fic_collage", "fic_build_pool", "fic_stream_size", "fic_stream_write",
     "fic_stream_read_header", "fic_stream_read_codes", "fic_measure_int8_peak", "fic_measure_mma_peak",
+    "fic_pin_host_buffer", "fic_unpin_host_buffer",
 ]
 
 
@@ -80,6 +81,8 @@ def load() -> C.CDLL:
     L.fic_build_pool.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.fic_measure_int8_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.fic_measure_mma_peak.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.fic_pin_host_buffer.argtypes = [vp, vp, C.c_size_t]
+    L.fic_unpin_host_buffer.argtypes = [vp, vp]
     L.fic_stream_size.argtypes = [C.c_int] * 4
     L.fic_stream_size.restype = C.c_size_t
     L.fic_stream_write.argtypes = [C.c_int] * 5 + [vp, vp, C.c_size_t]

@@ -101,6 +101,15 @@ class Handle:
         """Tensor-core instruction kind of the tcgen05 search: FIC_UMMA_KIND_AUTO / _I8 / _F16."""
         self._check(self._L.fic_set_option(self._h, _lib.FIC_OPT_UMMA_KIND, int(kind)))
 
+    def pin(self, array: np.ndarray):
+        """Page-locks a caller-owned contiguous array (fic_pin_host_buffer) so encode/decode copies run at full PCIe
+        rate; pair with unpin() before the array is freed."""
+        assert array.flags["C_CONTIGUOUS"]
+        self._check(self._L.fic_pin_host_buffer(self._h, array.ctypes.data, array.nbytes))
+
+    def unpin(self, array: np.ndarray):
+        self._check(self._L.fic_unpin_host_buffer(self._h, array.ctypes.data))
+
     def f16_exact(self) -> bool:
         """True if this device's kind::f16 tensor path reproduced the exact integer covariances in the
         library's self-test (run once per handle); False means the handle runs kind::i8 instead."""

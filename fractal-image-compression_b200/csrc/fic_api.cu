@@ -410,6 +410,34 @@ int fic_encode_planes_dev(fic_handle *h, const uint8_t *d_planes, int is_rgb, in
     return rc;
 }
 
+int fic_pin_host_buffer(fic_handle *h, void *ptr, size_t bytes)
+{
+    if (!h) return FIC_E_ARG;
+    if (!ptr || bytes == 0) return set_err(h, FIC_E_ARG, "fic_pin_host_buffer: empty buffer");
+    CU(cudaSetDevice(h->device));
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(h, e == cudaErrorMemoryAllocation ? FIC_E_NOMEM : FIC_E_CUDA, "cudaHostRegister(%zu bytes): %s", bytes,
+                       cudaGetErrorString(e));
+    }
+    return FIC_OK;
+}
+
+int fic_unpin_host_buffer(fic_handle *h, void *ptr)
+{
+    if (!h) return FIC_E_ARG;
+    if (!ptr) return set_err(h, FIC_E_ARG, "fic_unpin_host_buffer: NULL");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));  // no copy of this handle may still be reading the buffer
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(h, FIC_E_ARG, "cudaHostUnregister: %s", cudaGetErrorString(e));
+    }
+    return FIC_OK;
+}
+
 int fic_measure_mma_peak(fic_handle *h, int kind, int n_cols, double *tops)
 {
     if (!h || !tops || (kind != FIC_UMMA_KIND_I8 && kind != FIC_UMMA_KIND_F16) || (n_cols != 128 && n_cols != 256))

@@ -139,6 +139,13 @@ int fic_encode_planes_dev(fic_handle *h, const uint8_t *d_planes, int is_rgb, in
                           float *d_info, int32_t *d_qcodes);
 int fic_sync(fic_handle *h);
 
+/* Page-locks (and later releases) a caller-owned host buffer -- the ARGB array, the code arrays -- so that the
+ * copies of fic_encode_* / fic_decode run at full PCIe rate instead of through the driver's staging buffer.
+ * Optional: every entry accepts pageable memory.  A Java host calls it once per off-heap MemorySegment it
+ * reuses; heap arrays handed over by JNI cannot be pinned this way. */
+int fic_pin_host_buffer(fic_handle *h, void *ptr, size_t bytes);
+int fic_unpin_host_buffer(fic_handle *h, void *ptr);
+
 /* ---- decode: replaces FC:378-418 / FC:455-505 (after header + code parsing) --- */
 
 /* `qcodes` are the ints read from the stream after the 5-int header (FC:370-376 /

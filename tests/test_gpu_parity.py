@@ -382,3 +382,25 @@ def test_tcgen05_b16_extreme_digit(fic, handle, oracle):
         handle.set_engine(fic.FIC_ENGINE_AUTO)
     oinfo = oracle.encode(img, 16, wk)
     assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, 128, 128, 16, wk), 3)
+
+
+def test_pinned_caller_buffers(fic, handle, lena_grey):
+    """fic_pin_host_buffer: same results from page-locked caller buffers; double pin / stray unpin are errors."""
+    info0, q0 = handle.encode(lena_grey, 8, 2, rgb=False)
+    img = np.ascontiguousarray(lena_grey).copy()
+    info = np.zeros_like(info0)
+    q = np.zeros_like(q0)
+    for a in (img, info, q):
+        handle.pin(a)
+    try:
+        handle.encode(img, 8, 2, rgb=False, info=info, q=q)
+        assert float_bits_equal(info, info0) and (q == q0).all()
+        with pytest.raises(fic.FicError):
+            handle.pin(img)              # already registered
+    finally:
+        for a in (img, info, q):
+            handle.unpin(a)
+    with pytest.raises(fic.FicError):
+        handle.unpin(img)                # not registered any more
+    info2, q2 = handle.encode(img, 8, 2, rgb=False)   # the handle is still healthy after the rejected calls
+    assert (q2 == q0).all()
