@@ -1173,6 +1173,31 @@ __device__ __forceinline__ int refine_kov(const uint32_t *rw, int rmean, int vR,
     return kov - (rmean * dsum + (dsum / n) * vR);
 }
 
+// Calls consider(sweep position) for this lane's candidate of every flagged chunk of operand row i (a warp walks a
+// row; lane = candidate within the chunk).  The row's 2 * n_chunks (<= 16) list lengths are read by as many lanes at
+// once, a list (<= 32 entries) by one coalesced load: the loop has no dependent global loads besides the candidates
+// themselves.  A row whose flag list overflowed is rescanned in full -- slow, exact.
+template <class F>
+__device__ __forceinline__ void for_each_flagged(int lane, int64_t i, int64_t rows_padded, int n_chunks, int64_t npos,
+                                                 const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt,
+                                                 F &&consider)
+{
+    const int n_lists = 2 * n_chunks;  // (domain chunk of the unit, column half)
+    const int my_cnt = lane < n_lists ? flag_cnt[((int64_t)(lane >> 1) * rows_padded + i) * 2 + (lane & 1)] : 0;
+    const bool overflow = __any_sync(0xffffffffu, my_cnt > kFlagCap);
+    if (!overflow) {
+        for (int lh = 0; lh < n_lists; lh++) {
+            const int cnt = __shfl_sync(0xffffffffu, my_cnt, lh);
+            if (cnt == 0) continue;
+            const int32_t *lst = flag_list + (((int64_t)(lh >> 1) * rows_padded + i) * 2 + (lh & 1)) * kFlagCap;
+            const int mine = lane < cnt ? lst[lane] : 0;
+            for (int e = 0; e < cnt; e++) consider((int64_t)__shfl_sync(0xffffffffu, mine, e) * 32 + lane);
+        }
+    } else {
+        for (int64_t pos = lane; pos < npos; pos += 32) consider(pos);
+    }
+}
+
 // One warp per range row, lane = candidate within a flagged chunk.  The winner is the
 // lexicographic (error, index) minimum over every candidate of every flagged chunk plus domain
 // 0 (which wins when the whole row ties, e.g. all scores 0) = the reference's first index with
@@ -1228,22 +1253,7 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
         }
     };
     if (lane == 0) consider(*dom0_pos);
-    // The row's 2 * n_chunks (<= 16) list lengths are read by as many lanes at once, a list (<= 32 entries) by
-    // one coalesced load: the loop below then has no dependent global loads besides the candidates themselves.
-    const int n_lists = 2 * n_chunks;  // (domain chunk of the unit, column half)
-    const int my_cnt = lane < n_lists ? flag_cnt[((int64_t)(lane >> 1) * rows_padded + i) * 2 + (lane & 1)] : 0;
-    const bool overflow = __any_sync(0xffffffffu, my_cnt > kFlagCap);
-    if (!overflow) {
-        for (int lh = 0; lh < n_lists; lh++) {
-            const int cnt = __shfl_sync(0xffffffffu, my_cnt, lh);
-            if (cnt == 0) continue;
-            const int32_t *lst = flag_list + (((int64_t)(lh >> 1) * rows_padded + i) * 2 + (lh & 1)) * kFlagCap;
-            const int mine = lane < cnt ? lst[lane] : 0;
-            for (int e = 0; e < cnt; e++) consider((int64_t)__shfl_sync(0xffffffffu, mine, e) * 32 + lane);
-        }
-    } else {
-        for (int64_t pos = lane; pos < npos; pos += 32) consider(pos);
-    }
+    for_each_flagged(lane, i, rows_padded, n_chunks, npos, flag_list, flag_cnt, consider);
     for (int o = 16; o > 0; o >>= 1) {
         float e2 = __shfl_down_sync(0xffffffffu, be, o);
         int i2 = __shfl_down_sync(0xffffffffu, bi, o);
@@ -1424,20 +1434,7 @@ k_umma_refine_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
         }
     };
     if (lane == 0) consider(*dom0_pos);
-    const int n_lists = 2 * n_chunks;
-    const int my_cnt = lane < n_lists ? flag_cnt[((int64_t)(lane >> 1) * rows_padded + i) * 2 + (lane & 1)] : 0;
-    const bool overflow = __any_sync(0xffffffffu, my_cnt > kFlagCap);
-    if (!overflow) {
-        for (int lh = 0; lh < n_lists; lh++) {
-            const int cnt = __shfl_sync(0xffffffffu, my_cnt, lh);
-            if (cnt == 0) continue;
-            const int32_t *lst = flag_list + (((int64_t)(lh >> 1) * rows_padded + i) * 2 + (lh & 1)) * kFlagCap;
-            const int mine = lane < cnt ? lst[lane] : 0;
-            for (int e = 0; e < cnt; e++) consider((int64_t)__shfl_sync(0xffffffffu, mine, e) * 32 + lane);
-        }
-    } else {
-        for (int64_t pos = lane; pos < npos; pos += 32) consider(pos);
-    }
+    for_each_flagged(lane, i, rows_padded, n_chunks, npos, flag_list, flag_cnt, consider);
     for (int o = 16; o > 0; o >>= 1) {
         float e2 = __shfl_down_sync(0xffffffffu, be, o);
         int i2 = __shfl_down_sync(0xffffffffu, bi, o);
