@@ -79,7 +79,7 @@ static int set_err(fic_handle *h, int code, const char *fmt, ...)
             return set_err(h, FIC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-enum Slot { S_ARGB, S_SRC, S_DEC, S_DSUM, S_DSQ, S_RSUM, S_BEST, S_INFO, S_Q, S_OPA, S_OPB, S_IMG, S_DEC2, S_DCODE, S_PERR, S_ACC };
+enum Slot { S_ARGB, S_SRC, S_DEC, S_DSUM, S_DSQ, S_RSUM, S_BEST, S_INFO, S_Q, S_OPA, S_OPB, S_IMG, S_DEC2, S_DCODE, S_PERR, S_ACC, S_DEC3 };
 
 template <typename T>
 static int ensure(fic_handle *h, T *&p, int slot, size_t bytes)
@@ -164,7 +164,7 @@ void fic_destroy(fic_handle *h)
     cudaStreamSynchronize(h->stream);
     Work &w = h->w;
     void *ptrs[] = {w.argb, w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, w.info, w.q, w.opA, w.opB,
-                    w.img, w.dec2, w.dcode, w.perr, w.acc, w.avgf};
+                    w.img, w.dec2, w.dcode, w.perr, w.acc, w.avgf, w.dec3};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 8; i++)
@@ -311,6 +311,11 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
         if (n < 0) return set_err(h, FIC_E_CUDA, "tcgen05 search launch failed: %s", why ? why : "?");
         launches += n;
     } else {
+        if (g.C == 3) {  // channel-sum plane of the RGB CUDA-core search (cheap: one pass over W*H/4 pixels)
+            ENSURE(w.dec3, S_DEC3, sizeof(uint16_t) * (size_t)g.sw * g.sh);
+            call.dec3 = w.dec3;
+            launches += launch_sum_planes(w.dec, w.dec3, g, s);
+        }
         CU(cudaEventRecord(h->ev[6], s));
         launches += launch_search_direct(call, g, j0, j1, s);
         CU(cudaEventRecord(h->ev[7], s));

@@ -49,7 +49,8 @@ struct Work {
     float *dcode = nullptr;     // [NR][3|5] dequantised codes with codebook indices, then s32 doff[NR] (domain byte offsets)
     int32_t *perr = nullptr;    // per-pixel squared change in reference loop order (exact avgError path)
     unsigned long long *acc = nullptr;  // [64] integer accumulators / flags
-    size_t cap[16] = {0};
+    uint16_t *dec3 = nullptr;   // RGB: R + G + B of the decimated planes (CUDA-core search)
+    size_t cap[20] = {0};
 };
 
 // ---- kernel launchers (each returns the number of kernels it launched) -----------
@@ -59,6 +60,7 @@ int launch_decimate(const uint8_t *d_src, uint8_t *d_dec, const Geom &g, cudaStr
 int launch_domain_stats(const uint8_t *d_dec, int32_t *d_dsum, int32_t *d_dsq, const Geom &g,
                         cudaStream_t s);
 int launch_range_stats(const uint8_t *d_src, int32_t *d_rsum, const Geom &g, cudaStream_t s);
+int launch_sum_planes(const uint8_t *d_dec, uint16_t *d_dec3, const Geom &g, cudaStream_t s);  // RGB only
 int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, cudaStream_t s);
 int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_info, int32_t *d_q,
                  cudaStream_t s);

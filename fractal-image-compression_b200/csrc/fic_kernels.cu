@@ -299,23 +299,36 @@ struct RgbScore {
     float err, kov;
 };
 
-__device__ __forceinline__ RgbScore rgb_score(const float *s_gR, float vR, const uint8_t *dec, const Geom &g,
-                                              int gx, int gy, int mR, int mG, int mB)
+template <int B>
+__device__ __forceinline__ RgbScore rgb_score(const float *s_gR, float vR, const uint16_t *dec3, const Geom &g,
+                                              int gx, int gy, int dmsum, int vDi)
 {
-    int64_t plane = (int64_t)g.sw * g.sh;
-    const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
-    float dR = (float)mR, dG = (float)mG, dB = (float)mB;
-    float kov = 0.0f, vD = 0.0f;  // FC:775, FC:778 (sqrt(variance) == 0 on the RGB path)
-    for (int ry = 0; ry < g.B; ry++) {
-        const uint8_t *row = p + (int64_t)ry * g.sw;
-        for (int rx = 0; rx < g.B; rx++) {
-            float gD = __fadd_rn(__fadd_rn(__fsub_rn((float)__ldg(row + rx), dR),
-                                           __fsub_rn((float)__ldg(row + plane + rx), dG)),
-                                 __fsub_rn((float)__ldg(row + 2 * plane + rx), dB));  // FC:783-784
-            kov = __fadd_rn(kov, __fmul_rn(s_gR[ry * g.B + rx], gD));                // FC:789
-            vD = __fadd_rn(vD, gD);                                                  // FC:791
+    // dec3 = R + G + B of the decimated planes, dmsum = the sum of the three integer channel means:
+    // gD = (dR - mR) + (dG - mG) + (dB - mB) (FC:783-784, exact small integers in binary32) = dec3 - dmsum.
+    // A block row starts at a multiple of B / 4 pixels: 2-, 4- and 8-byte loads for B = 4, 8, 16.
+    constexpr int LW = B / 4;  // pixels per load
+    const uint16_t *p = dec3 + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+    float kov = 0.0f;  // FC:775
+#pragma unroll 2
+    for (int ry = 0; ry < B; ry++) {
+        const uint16_t *row = p + (int64_t)ry * g.sw;
+#pragma unroll
+        for (int rx = 0; rx < B; rx += LW) {
+            uint32_t w[2];
+            if (LW == 1) w[0] = __ldg(row + rx);
+            else if (LW == 2) w[0] = __ldg((const uint32_t *)(row + rx));
+            else { const uint2 v = __ldg((const uint2 *)(row + rx)); w[0] = v.x; w[1] = v.y; }
+#pragma unroll
+            for (int e = 0; e < LW; e++) {
+                const float gD = (float)((int)((w[e >> 1] >> (16 * (e & 1))) & 0xffffu) - dmsum);
+                // FC:789 kov += gR * gD: the product is an exact integer (< 2^20), so the fused form rounds exactly
+                // like the reference's multiply-then-add, once, in pixel order
+                kov = __fmaf_rn(s_gR[ry * B + rx + e], gD, kov);
+            }
         }
     }
+    // FC:778 + FC:791: vD = sqrt(variance) (0 on the RGB path) + sum gD, an exact small integer = sum_c (dsum_c mod n)
+    const float vD = (float)vDi;
     float r = 0.0f;
     if (!(vR == 0.0f || vD == 0.0f)) r = __fdiv_rn(kov, __fmul_rn(vR, vD));  // FC:797-800
     r = __fmul_rn(r, r);
@@ -346,8 +359,9 @@ __device__ __forceinline__ float rgb_range_prep(const uint8_t *src, const int32_
     return (float)v;
 }
 
+template <int B>
 __global__ void __launch_bounds__(kDirectThreads)
-k_search_direct_rgb(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec,
+k_search_direct_rgb(const uint8_t *__restrict__ src, const uint16_t *__restrict__ dec3,
                     const int32_t *__restrict__ dsum, const int32_t *__restrict__ rsum,
                     int32_t *__restrict__ best, Geom g, int64_t j0)
 {
@@ -367,8 +381,14 @@ k_search_direct_rgb(const uint8_t *__restrict__ src, const uint8_t *__restrict__
         int ky = c / g.wk, kx = c - ky * g.wk;
         int gx = dx + kx, gy = dy + ky;
         int64_t idx = gx + (int64_t)gy * g.dpw;
-        RgbScore sc = rgb_score(s_gR, vR, dec, g, gx, gy, dsum[idx] / g.n, dsum[g.ND + idx] / g.n,
-                                dsum[2 * g.ND + idx] / g.n);
+        int dmsum = 0, vDi = 0;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const int ds = dsum[ch * g.ND + idx];
+            dmsum += ds / g.n;
+            vDi += ds - g.n * (ds / g.n);
+        }
+        RgbScore sc = rgb_score<B>(s_gR, vR, dec3, g, gx, gy, dmsum, vDi);
         if (sc.err < best_err) { best_err = sc.err; best_c = c; }  // FC:710
     }
     block_argmin(best_err, best_c, s_err, s_c);
@@ -431,6 +451,20 @@ k_search_direct_grey_iso(const uint8_t *__restrict__ src, const uint8_t *__restr
     if (threadIdx.x == 0) best[j] = best_c;
 }
 
+// RGB: dec3 = R + G + B of the decimated planes (what k_search_direct_rgb reads instead of three planes).
+__global__ void k_sum_planes(const uint8_t *__restrict__ dec, uint16_t *__restrict__ dec3, int64_t count)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dec3[i] = (uint16_t)((int)dec[i] + (int)dec[count + i] + (int)dec[2 * count + i]);
+}
+
+int launch_sum_planes(const uint8_t *d_dec, uint16_t *d_dec3, const Geom &g, cudaStream_t s)
+{
+    const int64_t count = (int64_t)g.sw * g.sh;
+    k_sum_planes<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_dec, d_dec3, count);
+    return 1;
+}
+
 int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, cudaStream_t s)
 {
     if (j1 <= j0) return 0;
@@ -442,8 +476,12 @@ int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, c
             k_search_direct_grey_iso<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, g, at);
         else if (g.C == 1)
             k_search_direct_grey<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, g, at);
+        else if (g.B == 4)
+            k_search_direct_rgb<4><<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec3, w.dsum, w.rsum, w.best, g, at);
+        else if (g.B == 8)
+            k_search_direct_rgb<8><<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec3, w.dsum, w.rsum, w.best, g, at);
         else
-            k_search_direct_rgb<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.rsum, w.best, g, at);
+            k_search_direct_rgb<16><<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec3, w.dsum, w.rsum, w.best, g, at);
         left -= chunk;
         at += chunk;
         launches++;

@@ -115,3 +115,62 @@ def test_full_size_4096(fic, handle):
     dec, avg, it = handle.decode(q, W, W, B, wk, False)
     rec = ((dec.view(np.uint32) >> 16) & 0xFF).astype(np.uint8)
     assert it < 50 and avg < 1 and psnr(p, rec) > 25.0
+
+
+def _rgb_argb(planes):
+    v = [p.astype(np.uint32) for p in planes]
+    return (np.uint32(0xFF000000) | (v[0] << np.uint32(16)) | (v[1] << np.uint32(8)) | v[2]).view(np.int32)
+
+
+@pytest.mark.parametrize("W,B,kind", [(1024, 8, "structured"), (768, 8, "noise"), (512, 4, "structured"), (512, 8, "periodic"),
+                                      (512, 8, "binary")])
+def test_rgb_engines_agree_full_pool(fic, handle, W, B, kind):
+    """RGB full pool: the tensor-core search (kind::f16) and the CUDA-core kernel, which walks the reference's float
+    sum literally, must agree on every code -- natural, noise, periodic (ties, flag-list overflow) and 0/255 content."""
+    from test_gpu_parity import float_bits_equal
+
+    if kind == "periodic":
+        planes = []
+        for s in (5, 6, 7):
+            p = np.tile(fic.synth.noise(16, 16, s), (W // 16, W // 16)).copy()
+            p[::64, ::64] ^= 1
+            planes.append(p)
+    elif kind == "binary":
+        p = np.kron((fic.synth.noise(W // 2, W // 2, 3) >> 7).astype(np.uint8) * 255, np.ones((2, 2), np.uint8))
+        planes = [p, p, p]
+    else:
+        planes = [getattr(fic.synth, kind)(W, W, s) for s in (1, 2, 3)]
+    img = _rgb_argb(planes)
+    wk = 2 * W // B - 3
+    handle.set_engine(fic.FIC_ENGINE_DIRECT)
+    try:
+        i1, q1 = handle.encode(img, B, wk, rgb=True)
+        handle.set_engine(fic.FIC_ENGINE_UMMA)
+        i2, q2 = handle.encode(img, B, wk, rgb=True)
+        assert handle.timings().engine == fic.FIC_ENGINE_UMMA
+    finally:
+        handle.set_engine(fic.FIC_ENGINE_AUTO)
+    assert (q1 == q2).all() and float_bits_equal(i1, i2)
+
+
+def test_rgb_roundtrip_2048(fic, handle):
+    """2048^2 RGB on the tensor cores: row shards compose to the unsharded result (what the multi-GPU host relies on)
+    and the decoder converges on the codes.  No PSNR bar worth the name: the reference's RGB contrast divides by
+    (varR + varG) + meanB (FC:776, sic), which caps the quality of its own RGB mode (17 dB on this image)."""
+    W = 2048
+    base = fic.synth.structured(W, W, 1)
+    planes = [base, np.clip(base.astype(np.int32) + 20, 0, 255).astype(np.uint8), base]
+    img = _rgb_argb(planes)
+    wk = 2 * W // 8 - 3
+    info, q = handle.encode(img, 8, wk, rgb=True)
+    assert handle.timings().engine == fic.FIC_ENGINE_UMMA     # AUTO picks the tensor cores for RGB too
+    info2 = np.zeros_like(info)
+    q2 = np.zeros_like(q)
+    for j0, j1 in [(0, 256 * 37), (256 * 37, 256 * 38 + 5), (256 * 38 + 5, 256 * 256)]:
+        handle.encode(img, 8, wk, rgb=True, range_begin=j0, range_end=j1, info=info2, q=q2)
+    assert (q2 == q).all() and (info2.view(np.uint32) == info.view(np.uint32)).all()
+    dec, avg, it = handle.decode(q, W, W, 8, wk, True)
+    du = dec.view(np.uint32)
+    rec = np.stack([(du >> 16) & 0xFF, (du >> 8) & 0xFF, du & 0xFF]).astype(np.uint8)
+    assert it <= 50
+    assert psnr(np.stack(planes), rec) > 12.0
