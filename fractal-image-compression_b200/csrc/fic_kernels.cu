@@ -249,22 +249,46 @@ __device__ __forceinline__ void block_argmin(float &err, int &c, float *s_err, i
     }
 }
 
+// sum r * d over one candidate block with packed-byte dot products: kov = sum r d - rmean * sum d - dmean * vR
+// (exact in s32).  s_rw = the range block as packed u8 words (raster order).  A block row of the decimated plane
+// starts at a multiple of B / 4 bytes: 4-, 2- and 1-byte loads for B = 16, 8, 4.
+template <int B>
+__device__ __forceinline__ int grey_dot_raw(const uint32_t *s_rw, const uint8_t *__restrict__ p, int sw)
+{
+    int dot = 0;
+#pragma unroll 4
+    for (int ry = 0; ry < B; ry++) {
+        const uint8_t *row = p + (int64_t)ry * sw;
+#pragma unroll
+        for (int w = 0; w < B / 4; w++) {
+            uint32_t d4;
+            if (B == 16) d4 = __ldg((const uint32_t *)(row + 4 * w));
+            else if (B == 8) d4 = (uint32_t)__ldg((const uint16_t *)(row + 4 * w)) | ((uint32_t)__ldg((const uint16_t *)(row + 4 * w + 2)) << 16);
+            else d4 = (uint32_t)__ldg(row) | ((uint32_t)__ldg(row + 1) << 8) | ((uint32_t)__ldg(row + 2) << 16) | ((uint32_t)__ldg(row + 3) << 24);
+            dot = (int)__dp4a(s_rw[ry * (B / 4) + w], d4, (uint32_t)dot);
+        }
+    }
+    return dot;
+}
+
+template <int B>
 __global__ void __launch_bounds__(kDirectThreads)
 k_search_direct_grey(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dec,
                      const int32_t *__restrict__ dsum, const int32_t *__restrict__ dsq,
                      const int32_t *__restrict__ rsum, int32_t *__restrict__ best, Geom g, int64_t j0)
 {
-    __shared__ int s_rt[256];  // r - rmean, B <= 16
+    constexpr int n = B * B;
+    __shared__ uint32_t s_rw[n / 4];  // the range block, packed bytes
     __shared__ float s_err[kDirectThreads / 32];
     __shared__ int s_c[kDirectThreads / 32];
     int64_t j = j0 + blockIdx.x;
     int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
     int rs = rsum[j];
-    int rmean = rs / g.n;       // FC:72
-    int vR = rs - g.n * rmean;  // sum (r - rmean), FC:671
-    for (int t = threadIdx.x; t < g.n; t += kDirectThreads) {
-        int ry = t / g.B, rx = t % g.B;
-        s_rt[t] = (int)src[(int64_t)(yr * g.B + ry) * g.W + xr * g.B + rx] - rmean;
+    int rmean = rs / n;       // FC:72
+    int vR = rs - n * rmean;  // sum (r - rmean), FC:671
+    for (int t = threadIdx.x; t < n / 4; t += kDirectThreads) {
+        int ry = (4 * t) / B, rx = (4 * t) % B;  // 4-byte aligned: W, xr * B and rx are multiples of 4
+        s_rw[t] = *(const uint32_t *)(src + (int64_t)(yr * B + ry) * g.W + xr * B + rx);
     }
     __syncthreads();
     int dy, dx;
@@ -277,14 +301,10 @@ k_search_direct_grey(const uint8_t *__restrict__ src, const uint8_t *__restrict_
         int gx = dx + kx, gy = dy + ky;
         int64_t idx = gx + (int64_t)gy * g.dpw;  // FC:145
         const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
-        int dot = 0;
-        for (int ry = 0; ry < g.B; ry++) {
-            const uint8_t *row = p + (int64_t)ry * g.sw;
-            for (int rx = 0; rx < g.B; rx++) dot += s_rt[ry * g.B + rx] * (int)__ldg(row + rx);
-        }
+        const int ds = dsum[idx];
         int dmean;
-        int varD = dom_var(dsum[idx], dsq[idx], g.n, &dmean);
-        int kov = dot - dmean * vR;  // sum (r-rmean)(d-dmean)
+        int varD = dom_var(ds, dsq[idx], n, &dmean);
+        int kov = grey_dot_raw<B>(s_rw, p, g.sw) - rmean * ds - dmean * vR;  // sum (r-rmean)(d-dmean)
         float err = grey_error(kov, vR, __dsqrt_rn((double)varD));
         if (err < best_err) { best_err = err; best_c = c; }  // FC:627
     }
@@ -474,8 +494,12 @@ int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, c
         unsigned chunk = (unsigned)(left < (1 << 30) ? left : (1 << 30));
         if (g.C == 1 && g.n_iso > 1)
             k_search_direct_grey_iso<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, g, at);
+        else if (g.C == 1 && g.B == 4)
+            k_search_direct_grey<4><<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, g, at);
+        else if (g.C == 1 && g.B == 8)
+            k_search_direct_grey<8><<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, g, at);
         else if (g.C == 1)
-            k_search_direct_grey<<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, g, at);
+            k_search_direct_grey<16><<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, g, at);
         else if (g.B == 4)
             k_search_direct_rgb<4><<<chunk, kDirectThreads, 0, s>>>(w.src, w.dec3, w.dsum, w.rsum, w.best, g, at);
         else if (g.B == 8)
