@@ -52,23 +52,31 @@ dist.init_process_group("gloo")
 rank = dist.get_rank()
 W = H = 64; B = 8; wk = 13
 plane = fic.synth.structured(W, H, 5)
-argb = fic.synth.grey_to_argb(plane)
+grey = fic.synth.grey_to_argb(plane)
+v = [fic.synth.structured(W, H, s).astype(np.uint32) for s in (5, 6, 7)]
+colour = (np.uint32(0xFF000000) | (v[0] << np.uint32(16)) | (v[1] << np.uint32(8)) | v[2]).view(np.int32)
+def to_argb(planes):
+    p = planes.numpy().astype(np.uint32)
+    if p.shape[0] == 1:
+        return fic.synth.grey_to_argb(planes[0].numpy())
+    return (np.uint32(0xFF000000) | (p[0] << np.uint32(16)) | (p[1] << np.uint32(8)) | p[2]).view(np.int32)
 def worker(planes, mode, W, H, B, wk, j0, j1):     # test double: the CPU oracle computes this rank's rows
-    img = fic.synth.grey_to_argb(planes[0].numpy())
-    iso = mode == fic.FIC_MODE_GREY_ISO
-    info = O.encode(img, B, wk, range_begin=j0, range_end=j1, iso=iso)
-    q = np.frombuffer(O.write_data(info, W, H, B, wk, iso=iso)[20:], ">i4").astype(np.int32).reshape(-1, 4 if iso else 3)
+    iso, rgb = mode == fic.FIC_MODE_GREY_ISO, mode == fic.FIC_MODE_RGB
+    info = O.encode(to_argb(planes), B, wk, rgb=rgb, range_begin=j0, range_end=j1, iso=iso)
+    q = np.frombuffer(O.write_data(info, W, H, B, wk, rgb=rgb, iso=iso)[20:], ">i4").astype(np.int32).reshape(-1, info.shape[1])
     return torch.from_numpy(info), torch.from_numpy(q.copy())
 enc = ShardedEncoder(worker=worker)
-for mode in (fic.FIC_MODE_GREY, fic.FIC_MODE_GREY_ISO):     # the reference's grey codes, and the isometry extension
-    iso = mode == fic.FIC_MODE_GREY_ISO
-    planes = torch.from_numpy(argb_to_planes(argb, False)) if rank == 0 else None
+# the reference's grey and RGB codes, and the isometry extension
+for mode in (fic.FIC_MODE_GREY, fic.FIC_MODE_RGB, fic.FIC_MODE_GREY_ISO):
+    iso, rgb = mode == fic.FIC_MODE_GREY_ISO, mode == fic.FIC_MODE_RGB
+    argb = colour if rgb else grey
+    planes = torch.from_numpy(argb_to_planes(argb, rgb)) if rank == 0 else None
     out = enc.encode(planes, mode, W, H, B, wk, device="cpu")
     if rank == 0:
         info, q = out
-        full = O.encode(argb, B, wk, iso=iso)
+        full = O.encode(argb, B, wk, rgb=rgb, iso=iso)
         assert info.numpy().tobytes() == full.tobytes(), "sharded codes differ from the single-process encode"
-        want = O.write_data(full, W, H, B, wk, iso=iso)
+        want = O.write_data(full, W, H, B, wk, rgb=rgb, iso=iso)
         assert fic.stream_write(q.numpy(), W, H, B, wk, rgb=mode) == want
         print("SHARDED_OK", mode)
     else:
@@ -85,7 +93,7 @@ def test_world_size_2_gloo(tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", "29731", str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "SHARDED_OK 0" in r.stdout and "SHARDED_OK 2" in r.stdout
+    assert all(f"SHARDED_OK {m}" in r.stdout for m in (0, 1, 2))
 
 
 def test_rgb_covariance_partial_sums_stay_exact_for_b8():
