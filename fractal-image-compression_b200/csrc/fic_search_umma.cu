@@ -34,6 +34,10 @@
 // exactly whatever the summation order (the probe dumps and checks every accumulator).  K = n.
 // The epilogue takes max |kov| with FMNMX3 |a|, |b|, |c|: 16 instructions per 32 values.
 //
+// RGB (B = 4, 8; kind::f16 only).  The reference's RGB score has the same shape with the channel-summed centred
+// values gR, gD in [-765, 765] as operands and the integer vD = sum gD in the place of sqrt(varD); its covariance
+// is provably an exact integer below 2^24 for B <= 8.  Same kernel, RGB packers and refine: see "RGB operands".
+//
 // kov on the tensor cores, kind::i8 (B = 16; selectable for B = 4, 8).  With dt = d - dmean_j
 // (|dt| <= 255; +255 only occurs in a block of mean 0, whose row is stored negated -- only |kov| is used),
 // split dt = h + l, h = clamp(dt, -128, 127), l = dt - h (both fit s8; l is zero unless a
