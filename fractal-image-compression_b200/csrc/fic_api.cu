@@ -275,6 +275,7 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     ENSURE(w.dsq, S_DSQ, sizeof(int32_t) * g.C * g.ND);
     ENSURE(w.rsum, S_RSUM, sizeof(int32_t) * g.C * g.NR);
     ENSURE(w.best, S_BEST, sizeof(int32_t) * g.NR);
+    if (g.C == 3) ENSURE(w.dec3, S_DEC3, sizeof(uint16_t) * (size_t)g.sw * g.sh);  // R + G + B of the decimated planes
     int kind = h->umma_kind;
     if (engine == FIC_ENGINE_UMMA) {
         // The first kind::f16 search of a handle verifies, once, that this device's f16 tensor path
@@ -311,11 +312,7 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
         if (n < 0) return set_err(h, FIC_E_CUDA, "tcgen05 search launch failed: %s", why ? why : "?");
         launches += n;
     } else {
-        if (g.C == 3) {  // channel-sum plane of the RGB CUDA-core search (cheap: one pass over W*H/4 pixels)
-            ENSURE(w.dec3, S_DEC3, sizeof(uint16_t) * (size_t)g.sw * g.sh);
-            call.dec3 = w.dec3;
-            launches += launch_sum_planes(w.dec, w.dec3, g, s);
-        }
+        if (g.C == 3) launches += launch_sum_planes(w.dec, w.dec3, g, s);
         CU(cudaEventRecord(h->ev[6], s));
         launches += launch_search_direct(call, g, j0, j1, s);
         CU(cudaEventRecord(h->ev[7], s));

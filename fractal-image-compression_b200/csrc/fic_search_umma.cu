@@ -500,7 +500,7 @@ __global__ void k_umma_sortkeys_rgb(const int32_t *__restrict__ dsum, int n, int
 // {domain, vD, 0, 0}; the refine step re-reads the operand row itself, so no raw copy is kept.
 template <int B>
 __global__ void __launch_bounds__(128)
-k_umma_pack_domains_rgb(const uint8_t *__restrict__ dec, const int32_t *__restrict__ dsum,
+k_umma_pack_domains_rgb(const uint16_t *__restrict__ dec3, const int32_t *__restrict__ dsum,
                         const int32_t *__restrict__ perm, uint8_t *__restrict__ opB, int32_t *__restrict__ pos_dom,
                         int4 *__restrict__ pos_info, int64_t *__restrict__ dom0_pos, Geom g, int64_t ntiles, uint32_t mult)
 {
@@ -522,21 +522,31 @@ k_umma_pack_domains_rgb(const uint8_t *__restrict__ dec, const int32_t *__restri
     } else {
         const int64_t j = perm[sp];
         const int gx = (int)(j % g.dpw), gy = (int)(j / g.dpw);
-        const int64_t plane = (int64_t)g.sw * g.sh;
-        const uint8_t *p = dec + (int64_t)(gy * g.step) * g.sw + gx * g.step;
+        // dec3 = R + G + B of the decimated planes (k_sum_planes); a block row starts at a multiple of B / 4
+        // pixels, so B = 8 reads pixel pairs (4-byte loads)
+        const uint16_t *p = dec3 + (int64_t)(gy * g.step) * g.sw + gx * g.step;
         int dm[3];
         const int vd = rgb_dom_vd(dsum, g.ND, j, n, dm);
         const int dmsum = dm[0] + dm[1] + dm[2];
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             int dv[8];
+            if (B == 8) {
 #pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const int k = c * 8 + e;
-                const uint8_t *q = p + (int64_t)(k / B) * g.sw + (k % B);
-                const int d3 = (int)__ldg(q) + (int)__ldg(q + plane) + (int)__ldg(q + 2 * plane);
-                dv[e] = vd != 0 ? d3 - dmsum : 0;
+                for (int e = 0; e < 8; e += 2) {
+                    const uint32_t w = __ldg((const uint32_t *)(p + (int64_t)c * g.sw + e));  // row c of the block
+                    dv[e] = (int)(w & 0xffffu);
+                    dv[e + 1] = (int)(w >> 16);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int k = c * 8 + e;
+                    dv[e] = (int)__ldg(p + (int64_t)(k / B) * g.sw + (k % B));
+                }
             }
+#pragma unroll
+            for (int e = 0; e < 8; e++) dv[e] = vd != 0 ? dv[e] - dmsum : 0;
             *(uint4 *)(rowp + c * 128) =
                 make_uint4(pack_h2(dv[0], dv[1]), pack_h2(dv[2], dv[3]), pack_h2(dv[4], dv[5]), pack_h2(dv[6], dv[7]));
         }
@@ -1563,8 +1573,9 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     // 2. operand blobs
     if constexpr (F16) {
         if (rgb) {
+            launches += launch_sum_planes(w.dec, w.dec3, g, s);
             k_umma_pack_domains_rgb<B><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(
-                w.dec, w.dsum, dv.Current(), w.opB, pos_dom, pos_info, dom0, g, p.ntiles, p.mult);
+                w.dec3, w.dsum, dv.Current(), w.opB, pos_dom, pos_info, dom0, g, p.ntiles, p.mult);
             k_umma_pack_ranges_rgb<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
         }
     }
@@ -1752,6 +1763,7 @@ int umma_f16_selftest(int num_sms, cudaStream_t s, const char **err)
     auto alloc = [&](void **ptr, size_t bytes) { if (ce == cudaSuccess) ce = cudaMalloc(ptr, bytes); };
     alloc((void **)&w.src, 3 * (size_t)W * W);
     alloc((void **)&w.dec, 3 * (size_t)g.sw * g.sh);
+    alloc((void **)&w.dec3, 2 * (size_t)g.sw * g.sh);
     alloc((void **)&w.dsum, 3 * 4 * g.ND);
     alloc((void **)&w.dsq, 3 * 4 * g.ND);
     alloc((void **)&w.rsum, 3 * 4 * g.NR);
@@ -1784,7 +1796,7 @@ int umma_f16_selftest(int num_sms, cudaStream_t s, const char **err)
         }
     }
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); result = -1; }
-    for (void *ptr : {(void *)w.src, (void *)w.dec, (void *)w.dsum, (void *)w.dsq, (void *)w.rsum, (void *)w.best, (void *)w.opA,
+    for (void *ptr : {(void *)w.src, (void *)w.dec, (void *)w.dec3, (void *)w.dsum, (void *)w.dsq, (void *)w.rsum, (void *)w.best, (void *)w.opA,
                       (void *)w.opB, (void *)dump, (void *)bad})
         if (ptr) cudaFree(ptr);
     return result;
