@@ -2,6 +2,7 @@
 // call sequencing on one CUDA stream, timings, and the .run stream helpers.
 #include <math.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -399,6 +400,7 @@ int fic_encode_planes_dev(fic_handle *h, const uint8_t *d_planes, int is_rgb, in
 {
     if (!h) return FIC_E_ARG;
     if (!d_planes || (!d_info && !d_qcodes)) return set_err(h, FIC_E_ARG, "d_planes and at least one output must be non-NULL");
+    if ((uintptr_t)d_planes & 15) return set_err(h, FIC_E_ARG, "d_planes must be 16-byte aligned (the kernels read it with vector loads)");
     Geom g;
     const char *why = "";
     int rc = make_geom(W, H, B, wk, is_rgb, &g, &why);

@@ -130,7 +130,7 @@ int fic_encode_grey_iso(fic_handle *h, const int32_t *argb, int W, int H, int B,
                         int64_t range_begin, int64_t range_end, float *info, int32_t *qcodes);
 
 /* Same, with the image already resident in device memory as 8-bit planes
- * (grey: red channel, W*H bytes; RGB: R, G, B planes, 3*W*H bytes) and device output
+ * (grey: red channel, W*H bytes; RGB: R, G, B planes, 3*W*H bytes; 16-byte aligned) and device output
  * buffers (float[NR][3|5], int32[NR][3|5]; either may be NULL).  Asynchronous on the
  * handle's stream; fic_sync() waits.  This is the entry the multi-GPU host uses after
  * the NCCL image broadcast. */

@@ -404,3 +404,17 @@ def test_pinned_caller_buffers(fic, handle, lena_grey):
         handle.unpin(img)                # not registered any more
     info2, q2 = handle.encode(img, 8, 2, rgb=False)   # the handle is still healthy after the rejected calls
     assert (q2 == q0).all()
+
+
+def test_planes_dev_rejects_misaligned_input(fic, handle):
+    import torch
+
+    W = H = 64
+    buf = torch.zeros(W * H + 16, dtype=torch.uint8, device="cuda")
+    info = torch.empty((64, 3), dtype=torch.float32, device="cuda")
+    q = torch.empty((64, 3), dtype=torch.int32, device="cuda")
+    with pytest.raises(fic.FicError) as e:
+        handle.encode_planes_dev(buf.data_ptr() + 1, fic.FIC_MODE_GREY, W, H, 8, 2, 0, 64, info.data_ptr(), q.data_ptr())
+    assert e.value.code == fic._lib.FIC_E_ARG
+    handle.encode_planes_dev(buf.data_ptr(), fic.FIC_MODE_GREY, W, H, 8, 2, 0, 64, info.data_ptr(), q.data_ptr())
+    handle.sync()

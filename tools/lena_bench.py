@@ -34,7 +34,9 @@ def main():
              ("LenaGrey 256^2 B=8 full pool (wk=61)", grey("lena_grey_256.u8", 256), 8, 61, False),
              ("LenaGrey 256^2 B=4 full pool (wk=125)", grey("lena_grey_256.u8", 256), 4, 125, False),
              ("Lena64 64^2 B=8 wk=2", grey("lena64.u8", 64), 8, 2, False),
-             ("LenaColored 256^2 B=8 wk=2 (RGB)", rgb("lena_colored_256.rgb", 256), 8, 2, True)]
+             ("LenaColored 256^2 B=8 wk=2 (RGB)", rgb("lena_colored_256.rgb", 256), 8, 2, True),
+             ("LenaColored 256^2 B=8 full pool (RGB)", rgb("lena_colored_256.rgb", 256), 8, 61, True),
+             ("LenaColored 256^2 B=4 full pool (RGB)", rgb("lena_colored_256.rgb", 256), 4, 125, True)]
     print(f"{'case':46s} {'GPU encode':>11s} {'GPU decode':>11s} {'CPU encode':>11s} {'CPU decode':>11s}  evals")
     for name, img, B, wk, is_rgb in cases:
         H, W = img.shape
