@@ -1406,12 +1406,15 @@ k_umma_refine_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
     const float vR = (float)vRi;
     const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
     const int64_t plane = (int64_t)g.W * g.H;
-    float gR[n];
-#pragma unroll
-    for (int k = 0; k < n; k++) {
+    // gR of the warp's range block lives in shared memory (broadcast reads): 64 registers less per thread, and the
+    // occupancy they buy hides the latency of the scattered operand-row reads
+    __shared__ float s_gR[4][n];
+    float *gR = s_gR[warp];
+    for (int k = lane; k < n; k += 32) {
         const uint8_t *q = src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B);
         gR[k] = (float)((int)__ldg(q) + (int)__ldg(q + plane) + (int)__ldg(q + 2 * plane) - rmsum);
     }
+    __syncwarp();
     float be = 10000000.0f;  // FC:698
     int bi = 0x7fffffff;
     const float tie_abs = (float)(vRi * vRi) * 4.76837158203125e-07f;  // vR^2 * 2^-21
