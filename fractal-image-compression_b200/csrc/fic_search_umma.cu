@@ -1179,10 +1179,11 @@ __device__ __forceinline__ int refine_kov(const uint32_t *rw, int rmean, int vR,
 #pragma unroll
     for (int c = 0; c < n / 16; c++) {
         const uint4 d = __ldg((const uint4 *)(pos_raw + raw_offset<n>(pos, c)));
-        kov = dp4a_uu(rw[4 * c + 0], d.x, kov);
-        kov = dp4a_uu(rw[4 * c + 1], d.y, kov);
-        kov = dp4a_uu(rw[4 * c + 2], d.z, kov);
-        kov = dp4a_uu(rw[4 * c + 3], d.w, kov);
+        const uint4 r = *(const uint4 *)(rw + 4 * c);  // registers (B <= 8) or a shared-memory broadcast (B = 16)
+        kov = dp4a_uu(r.x, d.x, kov);
+        kov = dp4a_uu(r.y, d.y, kov);
+        kov = dp4a_uu(r.z, d.z, kov);
+        kov = dp4a_uu(r.w, d.w, kov);
     }
     return kov - (rmean * dsum + (dsum / n) * vR);
 }
@@ -1240,11 +1241,26 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
         return;
     }
     const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
-    uint32_t rw[NW];
+    // The range block as packed u8 words: registers for B <= 8; for B = 16 (64 words) shared memory, read back as
+    // broadcasts -- the registers saved (128 -> see -Xptxas -v) buy the occupancy that hides the raw-pixel reads.
+    constexpr bool RW_SMEM = B == 16;
+    __shared__ __align__(16) uint32_t s_rw[RW_SMEM ? 4 : 1][RW_SMEM ? NW : 4];
+    __align__(16) uint32_t rw_reg[RW_SMEM ? 4 : NW];
+    const uint32_t *rw;
+    if constexpr (RW_SMEM) {
+        for (int w = lane; w < NW; w += 32) {
+            const int k = 4 * w;
+            s_rw[warp][w] = __ldg((const uint32_t *)(src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)));
+        }
+        __syncwarp();
+        rw = s_rw[warp];
+    } else {
 #pragma unroll
-    for (int w = 0; w < NW; w++) {
-        const int k = 4 * w;
-        rw[w] = __ldg((const uint32_t *)(src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)));
+        for (int w = 0; w < NW; w++) {
+            const int k = 4 * w;
+            rw_reg[w] = __ldg((const uint32_t *)(src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)));
+        }
+        rw = rw_reg;
     }
     float be = 10000000.0f;  // FC:615
     int bi = 0x7fffffff;
@@ -1308,20 +1324,23 @@ k_umma_refine_iso(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
         ((uint32_t *)s_blk[warp])[w] = __ldg((const uint32_t *)(src + (int64_t)(yr * B + k / B) * g.W + xr * B + (k % B)));
     }
     __syncwarp();
-    uint32_t rw[NW];  // the block permuted for the isometry at hand (same layout as the operand row)
-    auto build = [&](int kiso) {
+    // The block permuted for each of the 8 isometries (same layout as the operand rows), built once per range block
+    // in shared memory and read back as broadcasts.
+    __shared__ __align__(16) uint32_t s_rw[4][8][NW];
+    for (int t = lane; t < 8 * NW; t += 32) {
+        const int kiso = t / NW, w = t % NW;
+        uint32_t word = 0;
 #pragma unroll
-        for (int w = 0; w < NW; w++) {
-            uint32_t word = 0;
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                int ry, rx;  // the range pixel that T_kiso sends to domain pixel 4 * w + e
-                iso_map(iso_inverse(kiso), B, (4 * w + e) / B, (4 * w + e) % B, &ry, &rx);
-                word |= (uint32_t)s_blk[warp][ry * B + rx] << (8 * e);
-            }
-            rw[w] = word;
+        for (int e = 0; e < 4; e++) {
+            int ry, rx;  // the range pixel that T_kiso sends to domain pixel 4 * w + e
+            iso_map(iso_inverse(kiso), B, (4 * w + e) / B, (4 * w + e) % B, &ry, &rx);
+            word |= (uint32_t)s_blk[warp][ry * B + rx] << (8 * e);
         }
-    };
+        s_rw[warp][kiso][w] = word;
+    }
+    __syncwarp();
+    const uint32_t *rw = s_rw[warp][0];
+    auto build = [&](int kiso) { rw = s_rw[warp][kiso]; };
     float be = 10000000.0f;  // FC:615
     int bi = 0x7fffffff;     // c * 8 + k
     const float tie_abs = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
