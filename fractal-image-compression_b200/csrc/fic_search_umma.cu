@@ -203,13 +203,15 @@ __device__ __noinline__ float flag_threshold(float lb, float tie_abs)  // rare p
     return rad > 0.0f ? sqrtf(rad) : -1.0f;
 }
 
-// Rare path of the search epilogue, out of line so that the hot loop stays short: record a flagged chunk and,
-// if it raises the row's lower bound, publish the bound (shared-memory slot `sh_lb`) and recompute the threshold.
+// Rare path of the search epilogue, out of line so that the hot loop stays short: record a flagged chunk -- its id
+// and the upper bound ub of its scores, which lets the refine step drop the chunk once the row's final bound is
+// known -- and, if it raises the row's lower bound, publish the bound (shared-memory slot `sh_lb`) and recompute the
+// threshold.
 struct RowFilter { float thresh, lbmax; int cnt; };
-__device__ __noinline__ RowFilter flag_chunk(RowFilter st, float lb, float tie_abs, int32_t *list, int chunk_id, uint32_t sh_lb,
-                                             int publish)
+__device__ __noinline__ RowFilter flag_chunk(RowFilter st, float lb, float ub, float tie_abs, int2 *list, int chunk_id,
+                                             uint32_t sh_lb, int publish)
 {
-    if (st.cnt < kFlagCap) list[st.cnt] = chunk_id;
+    if (st.cnt < kFlagCap) list[st.cnt] = make_int2(chunk_id, __float_as_int(ub));
     st.cnt++;
     if (lb > st.lbmax) {
         st.lbmax = lb;
@@ -763,7 +765,7 @@ constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(
 template <int B, bool F16, int DBG, bool DUMP>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
-              int32_t *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, uint32_t *__restrict__ row_lb, int n_sb,
+              int2 *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, uint32_t *__restrict__ row_lb, int n_sb,
               int n_chunks, int ntiles, int iso_shift, int64_t rows_padded, int32_t *__restrict__ dump, int64_t dump_ld, volatile int *status,
               uint32_t lbo_bytes_a, uint32_t sbo_bytes_a, uint32_t lbo_bytes_b, uint32_t sbo_bytes_b)
 {
@@ -993,7 +995,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     st.thresh = flag_threshold(seed, tie_abs);
                 }
             }
-            int32_t *const list0 = flag_list + (((int64_t)ch * rows_padded + row) * 2) * kFlagCap;
+            int2 *const list0 = flag_list + (((int64_t)ch * rows_padded + row) * 2) * kFlagCap;
             int cnt0 = 0, cnt1 = 0;  // entries of the two lists (column halves) of this (row, unit)
             if (DBG & 8) tk_mark = (uint32_t)clock();
             for (int t = t0; t < t1; t++) {
@@ -1067,11 +1069,12 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     }
                     const float rhi = c == 0 ? bnd01.x : (c == 1 ? bnd01.z : (c == 2 ? bnd23.x : bnd23.z));
                     const float rlo = c == 0 ? bnd01.y : (c == 1 ? bnd01.w : (c == 2 ? bnd23.y : bnd23.w));
-                    if (M * rhi > st.thresh) {  // may hold the winner or one of its float ties
+                    const float ub = M * rhi;
+                    if (ub > st.thresh) {  // may hold the winner or one of its float ties
                         // the refine step reads two lists per (row, unit), one per column half, as the layout of
                         // the earlier two-warps-per-accumulator mapping had it
                         st.cnt = c < 2 ? cnt0 : cnt1;
-                        st = flag_chunk(st, M * rlo, tie_abs, list0 + (c >> 1) * kFlagCap, t * kChunksPerTile + c, sh_lb, iso_shift);
+                        st = flag_chunk(st, M * rlo, ub, tie_abs, list0 + (c >> 1) * kFlagCap, t * kChunksPerTile + c, sh_lb, iso_shift);
                         if (c < 2) cnt0 = st.cnt;
                         else cnt1 = st.cnt;
                     }
@@ -1081,7 +1084,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             }
             flag_cnt[((int64_t)ch * rows_padded + row) * 2] = cnt0;
             flag_cnt[((int64_t)ch * rows_padded + row) * 2 + 1] = cnt1;
-            if (n_chunks > 1 && st.lbmax > 0.0f) atomicMax(row_lb + ((row >> iso_shift) << iso_shift), __float_as_uint(st.lbmax));
+            // the row's bound after this unit: seeds its later units and lets the refine step drop stale flags
+            if (st.lbmax > 0.0f) atomicMax(row_lb + ((row >> iso_shift) << iso_shift), __float_as_uint(st.lbmax));
         }
         if ((DBG & 8) && lane == 0 && dump) {
             int32_t *o = dump + ((int64_t)blockIdx.x * kEpiWarps + e) * 8;
@@ -1192,10 +1196,13 @@ __device__ __forceinline__ int refine_kov(const uint32_t *rw, int rmean, int vR,
 // row; lane = candidate within the chunk).  The row's 2 * n_chunks (<= 16) list lengths are read by as many lanes at
 // once, a list (<= 32 entries) by one coalesced load: the loop has no dependent global loads besides the candidates
 // themselves.  A row whose flag list overflowed is rescanned in full -- slow, exact.
+// A chunk whose recorded upper bound does not exceed `th` -- the flag threshold of the row's FINAL lower bound --
+// cannot hold a member of T (the search kernel's own criterion, applied with the bound it reached in the end): it
+// is skipped without touching its candidates.  Most flags are such early records of a still-low bound.
 template <class F>
 __device__ __forceinline__ void for_each_flagged(int lane, int64_t i, int64_t rows_padded, int n_chunks, int64_t npos,
-                                                 const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt,
-                                                 F &&consider)
+                                                 const int2 *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt,
+                                                 float th, F &&consider)
 {
     const int n_lists = 2 * n_chunks;  // (domain chunk of the unit, column half)
     const int my_cnt = lane < n_lists ? flag_cnt[((int64_t)(lane >> 1) * rows_padded + i) * 2 + (lane & 1)] : 0;
@@ -1204,9 +1211,14 @@ __device__ __forceinline__ void for_each_flagged(int lane, int64_t i, int64_t ro
         for (int lh = 0; lh < n_lists; lh++) {
             const int cnt = __shfl_sync(0xffffffffu, my_cnt, lh);
             if (cnt == 0) continue;
-            const int32_t *lst = flag_list + (((int64_t)(lh >> 1) * rows_padded + i) * 2 + (lh & 1)) * kFlagCap;
-            const int mine = lane < cnt ? lst[lane] : 0;
-            for (int e = 0; e < cnt; e++) consider((int64_t)__shfl_sync(0xffffffffu, mine, e) * 32 + lane);
+            const int2 *lst = flag_list + (((int64_t)(lh >> 1) * rows_padded + i) * 2 + (lh & 1)) * kFlagCap;
+            const int2 mine = lane < cnt ? lst[lane] : make_int2(0, 0);
+            unsigned live = __ballot_sync(0xffffffffu, lane < cnt && __int_as_float(mine.y) > th);
+            while (live) {
+                const int e = __ffs(live) - 1;
+                live &= live - 1;
+                consider((int64_t)__shfl_sync(0xffffffffu, mine.x, e) * 32 + lane);
+            }
         }
     } else {
         for (int64_t pos = lane; pos < npos; pos += 32) consider(pos);
@@ -1224,7 +1236,8 @@ template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ pos_raw,
               const int4 *__restrict__ pos_info,
-              const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
+              const int2 *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt,
+              const uint32_t *__restrict__ row_lb, int n_chunks,
               int64_t rows_padded, int64_t rows, int64_t npos, const int64_t *__restrict__ dom0_pos,
               int32_t *__restrict__ best, Geom g, int64_t j0)
 {
@@ -1265,7 +1278,10 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
     float be = 10000000.0f;  // FC:615
     int bi = 0x7fffffff;
     const float tie_abs = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
-    float lb = 0.0f, th = -1.0f;  // lane-local lower bound of the row's max x and the flag threshold from it
+    // lane-local lower bound of the row's max x and the flag threshold from it, seeded with the bound the search
+    // kernel reached for this row
+    float lb = __uint_as_float(row_lb[i]), th = lb > 0.0f ? flag_threshold(lb, tie_abs) : -1.0f;
+    const float th_row = th;
     auto consider = [&](int64_t pos) {
         const int4 pi = __ldg(pos_info + pos);  // {domain index (-1: padding), varD, sum d, -}
         const int idx = pi.x;
@@ -1283,7 +1299,7 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
         }
     };
     if (lane == 0) consider(*dom0_pos);
-    for_each_flagged(lane, i, rows_padded, n_chunks, npos, flag_list, flag_cnt, consider);
+    for_each_flagged(lane, i, rows_padded, n_chunks, npos, flag_list, flag_cnt, th_row, consider);
     for (int o = 16; o > 0; o >>= 1) {
         float e2 = __shfl_down_sync(0xffffffffu, be, o);
         int i2 = __shfl_down_sync(0xffffffffu, bi, o);
@@ -1301,8 +1317,9 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
 template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_refine_iso(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ pos_raw,
-                  const int4 *__restrict__ pos_info, const int32_t *__restrict__ flag_list,
-                  const int32_t *__restrict__ flag_cnt, int n_chunks, int64_t rows_padded, int64_t ranges, int64_t npos,
+                  const int4 *__restrict__ pos_info, const int2 *__restrict__ flag_list,
+                  const int32_t *__restrict__ flag_cnt, const uint32_t *__restrict__ row_lb, int n_chunks,
+                  int64_t rows_padded, int64_t ranges, int64_t npos,
                   const int64_t *__restrict__ dom0_pos, int32_t *__restrict__ best, Geom g, int64_t j0)
 {
     constexpr int n = B * B;
@@ -1344,7 +1361,10 @@ k_umma_refine_iso(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
     float be = 10000000.0f;  // FC:615
     int bi = 0x7fffffff;     // c * 8 + k
     const float tie_abs = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
-    float lb = 0.0f, th = -1.0f;  // lane-local bound / threshold, shared by the 8 isometries (they compete for one winner)
+    // lane-local bound / threshold, shared by the 8 isometries (they compete for one winner), seeded with the bound
+    // the search kernel reached for this range block (its 8 operand rows publish into the first one's slot)
+    float lb = __uint_as_float(row_lb[r * 8]), th = lb > 0.0f ? flag_threshold(lb, tie_abs) : -1.0f;
+    const float th_row = th;
     auto consider = [&](int64_t pos, int kiso) {
         const int4 pi = __ldg(pos_info + pos);  // {domain index (-1: padding), varD, sum d, -}
         if (pi.x >= 0) {
@@ -1375,9 +1395,14 @@ k_umma_refine_iso(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
             for (int h = 0; h < 2; h++) {
                 const int cnt = h ? c1 : c0;
                 if (cnt == 0) continue;
-                const int32_t *lst = flag_list + (base + 2 * kiso + h) * kFlagCap;
-                const int mine = lane < cnt ? lst[lane] : 0;
-                for (int e = 0; e < cnt; e++) consider((int64_t)__shfl_sync(0xffffffffu, mine, e) * 32 + lane, kiso);
+                const int2 *lst = flag_list + (base + 2 * kiso + h) * kFlagCap;
+                const int2 mine = lane < cnt ? lst[lane] : make_int2(0, 0);
+                unsigned live = __ballot_sync(0xffffffffu, lane < cnt && __int_as_float(mine.y) > th_row);  // see for_each_flagged
+                while (live) {
+                    const int e = __ffs(live) - 1;
+                    live &= live - 1;
+                    consider((int64_t)__shfl_sync(0xffffffffu, mine.x, e) * 32 + lane, kiso);
+                }
             }
         }
     }
@@ -1401,7 +1426,8 @@ k_umma_refine_iso(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
 template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_refine_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ opB,
-                  const int4 *__restrict__ pos_info, const int32_t *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt, int n_chunks,
+                  const int4 *__restrict__ pos_info, const int2 *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt,
+                  const uint32_t *__restrict__ row_lb, int n_chunks,
                   int64_t rows_padded, int64_t rows, int64_t npos, const int64_t *__restrict__ dom0_pos,
                   int32_t *__restrict__ best, Geom g, int64_t j0)
 {
@@ -1437,7 +1463,8 @@ k_umma_refine_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
     float be = 10000000.0f;  // FC:698
     int bi = 0x7fffffff;
     const float tie_abs = (float)(vRi * vRi) * 4.76837158203125e-07f;  // vR^2 * 2^-21
-    float lb = 0.0f, th = -1.0f;
+    float lb = __uint_as_float(row_lb[i]), th = lb > 0.0f ? flag_threshold(lb, tie_abs) : -1.0f;  // see k_umma_refine
+    const float th_row = th;
     auto consider = [&](int64_t pos) {
         const int4 pi = __ldg(pos_info + pos);  // {domain index (-1: padding), vD, -, -}
         const int idx = pi.x;
@@ -1470,7 +1497,7 @@ k_umma_refine_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
         }
     };
     if (lane == 0) consider(*dom0_pos);
-    for_each_flagged(lane, i, rows_padded, n_chunks, npos, flag_list, flag_cnt, consider);
+    for_each_flagged(lane, i, rows_padded, n_chunks, npos, flag_list, flag_cnt, th_row, consider);
     for (int o = 16; o > 0; o >>= 1) {
         float e2 = __shfl_down_sync(0xffffffffu, be, o);
         int i2 = __shfl_down_sync(0xffffffffu, bi, o);
@@ -1554,8 +1581,8 @@ template <int B, bool F16>
 size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p = make_plan(g, rows, num_sms);
-    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list s32 x n_chunks x 2 x kFlagCap][row_lb u32]
-    return (size_t)p.n_sb * Lay<B, F16>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 2 * 4 * (1 + kFlagCap) +
+    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list (s32 id, f32 bound) x n_chunks x 2 x kFlagCap][row_lb u32]
+    return (size_t)p.n_sb * Lay<B, F16>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 2 * (4 + 8 * kFlagCap) +
            (size_t)p.rp * 4 + 1024;
 }
 
@@ -1572,7 +1599,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     uint8_t *opA = w.opA;
     int32_t *vR = (int32_t *)(opA + (size_t)p.n_sb * L::A_SB_BYTES);
     int32_t *flag_cnt = vR + rp;
-    int32_t *flag_list = flag_cnt + rp * p.n_chunks * 2;
+    int2 *flag_list = (int2 *)(flag_cnt + rp * p.n_chunks * 2);  // 8-byte aligned: the blobs are, and rp is even
     uint32_t *row_lb = (uint32_t *)(flag_list + rp * p.n_chunks * 2 * kFlagCap);  // per operand row: best lower bound of max x reached by finished units
     const bool rgb = g.C == 3;                        // kind::f16 only (see "RGB operands")
     if (rgb && !F16) { *err = "the RGB tensor path is kind::f16 only"; return -1; }
@@ -1608,7 +1635,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     }
     launches += 2;
     // 3. the fused search
-    using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int32_t *, int32_t *, uint32_t *, int, int,
+    using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int2 *, int32_t *, uint32_t *, int, int,
                              int, int, int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
     KernelT kern = k_umma_search<B, F16, 0, false>;  // dbg (probe only): 1 / 3 strip the scoring / the TMEM loads too
     if (dump && !(dbg & 8u)) kern = k_umma_search<B, F16, 0, true>;
@@ -1624,7 +1651,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     uint32_t lbo_a = 128, sbo_a = L::SBO_A, lbo_b = 128, sbo_b = L::SBO_B;
     if (variant == 1) { lbo_a = L::SBO_A; sbo_a = 128; lbo_b = L::SBO_B; sbo_b = 128; }  // probe only
     if (k0) cudaEventRecord(k0, s);
-    if (p.n_chunks > 1) cudaMemsetAsync(row_lb, 0, (size_t)rp * 4, s);
+    cudaMemsetAsync(row_lb, 0, (size_t)rp * 4, s);
     kern<<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, flag_list, flag_cnt, row_lb, p.n_sb, p.n_chunks, p.ntiles,
                                                g.n_iso > 1 ? 3 : 0, rp,
                                                dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
@@ -1634,13 +1661,13 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
         if (rgb) {
             if constexpr (F16)
                 k_umma_refine_rgb<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, w.opB, pos_info, flag_list, flag_cnt,
-                                                                                p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
+                                                                                row_lb, p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
         } else if (g.n_iso > 1)
             k_umma_refine_iso<B><<<(unsigned)((j1 - j0 + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_info, flag_list, flag_cnt,
-                                                                             p.n_chunks, rp, j1 - j0, p.npos, dom0, w.best, g, j0);
+                                                                             row_lb, p.n_chunks, rp, j1 - j0, p.npos, dom0, w.best, g, j0);
         else
             k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_info, flag_list, flag_cnt,
-                                                                        p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
+                                                                        row_lb, p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
     }
     launches += 2;
     ce = cudaGetLastError();
