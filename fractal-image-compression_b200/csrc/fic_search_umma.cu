@@ -316,14 +316,15 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
             uint32_t raw[4];
 #pragma unroll
             for (int w = 0; w < 4; w++) {
-                raw[w] = 0;
+                // pixels k .. k + 3 of the block share a row; a block row starts at a multiple of B / 4 bytes of the
+                // decimated plane: one 4-byte load for B = 16, two 2-byte loads for B = 8, bytes for B = 4
+                const int k = c * 16 + w * 4;
+                const uint8_t *q = p + (int64_t)(k / B) * g.sw + (k % B);
+                if (B == 16) raw[w] = __ldg((const uint32_t *)q);
+                else if (B == 8) raw[w] = (uint32_t)__ldg((const uint16_t *)q) | ((uint32_t)__ldg((const uint16_t *)(q + 2)) << 16);
+                else raw[w] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) | ((uint32_t)__ldg(q + 3) << 24);
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int k = c * 16 + w * 4 + e;
-                    const int d = (int)__ldg(p + (int64_t)(k / B) * g.sw + (k % B));
-                    raw[w] |= (uint32_t)d << (8 * e);
-                    dv[w * 4 + e] = sgn * (d - dmean);
-                }
+                for (int e = 0; e < 4; e++) dv[w * 4 + e] = sgn * ((int)((raw[w] >> (8 * e)) & 0xffu) - dmean);
             }
             *(uint4 *)(pos_raw + raw_offset<n>(pos, c)) = make_uint4(raw[0], raw[1], raw[2], raw[3]);
             if (F16) {
