@@ -50,6 +50,8 @@ def parse():
                     help="tensor-core instruction kind of the tcgen05 search (auto: f16 for B=4,8; i8 for B=16)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-ranges", type=int, default=128,
+                    help="range blocks of the timed result compared with the CPU oracle after the timed loop (0: skip)")
     return ap.parse_args()
 
 
@@ -167,6 +169,41 @@ def cpu_sample(plane, B, wk, nthreads, target_s, iso=False, rgb=False):
     return R, t, t_pool
 
 
+def parity_spot(plane, B, wk, info, q, K, iso=False, rgb=False, seed=2026):
+    """Untimed check of the result the timed loop produced: K random range blocks plus the first and the last one,
+    recomputed by the CPU oracle (oracle/, the C restatement of FC:613-644 / FC:655-687 / FC:697-808) on all host
+    threads and compared bit for bit -- the unquantised floats of imageInfo[RGB] and the ints writeData emits."""
+    from oracle import oracle as O
+
+    argb = to_argb(plane)
+    NR = info.shape[0]
+    rng = np.random.default_rng(seed)
+    ranges = np.unique(np.concatenate([[0, NR - 1], rng.integers(0, NR, K)])).astype(np.int64)
+    t0 = time.perf_counter()
+    ref = O.encode_list(argb, B, wk, ranges, rgb=rgb, iso=iso, nthreads=os.cpu_count() or 1)
+    t_cpu = time.perf_counter() - t0
+    got = np.ascontiguousarray(info[ranges])
+    # floats must agree bit for bit; a NaN contrast (0/0 on a flat winner, FC:634) must be NaN on both sides
+    same_f = (got.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(got) & np.isnan(ref))
+    scale = {3: (1, 100, 1), 5: (1, 1000000, 100000, 100000, 1), 4: (1, 100, 1, 1)}[info.shape[1]]
+    with np.errstate(invalid="ignore", over="ignore"):
+        refq = np.stack([java_f2i(ref[:, c] * np.float32(scale[c])) for c in range(info.shape[1])], 1)
+    same_q = q[ranges] == refq
+    bad = int((~(same_f.all(1) & same_q.all(1))).sum())
+    return {"ranges": int(len(ranges)), "mismatches": bad, "checker": "oracle", "oracle_seconds": round(t_cpu, 2),
+            "compared": "imageInfo floats (bitwise) and writeData ints"}
+
+
+def java_f2i(x):
+    """Java (int)float: truncate toward zero, saturate, NaN -> 0 (FC:242-244, FC:250-254)."""
+    x = np.asarray(x, np.float32)
+    out = np.zeros(x.shape, np.int32)
+    ok = ~np.isnan(x)
+    xc = np.clip(np.trunc(np.where(ok, x, 0).astype(np.float64)), -2147483648.0, 2147483647.0)
+    out[ok] = xc[ok].astype(np.int64).astype(np.int32)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -252,11 +289,16 @@ def run_ours(args):
     h_info = torch.empty((NR, S), dtype=torch.float32).pin_memory()
     h_q = torch.empty((NR, S), dtype=torch.int32).pin_memory()
 
+    last_out = [None, None]
+
     def step_device():
         if world == 1:
             handle.encode_planes_dev(d_planes.data_ptr(), mode, size, size, B, wk, 0, NR, d_info.data_ptr(), d_q.data_ptr())
             return None
-        return enc.encode(d_planes, mode, size, size, B, wk, device=dev)
+        out = enc.encode(d_planes, mode, size, size, B, wk, device=dev)
+        if out is not None:
+            last_out[0], last_out[1] = out
+        return out
 
     def step_e2e():
         if world == 1:
@@ -400,6 +442,16 @@ def run_ours(args):
         line["decode"] = {"iterations": int(iters), "avg_error": float(avg_err), "psnr_db": 10 * np.log10(255.0 ** 2 / max(mse, 1e-12)),
                           "ms_total_host_clock": t_dec * 1e3, "device_ms": handle.timings().total_ms,
                           "mpixel_per_s_per_sweep": size * size * iters / max(handle.timings().total_ms, 1e-9) / 1e3}
+    rc = 0
+    if args.parity_ranges > 0:
+        # the codes the timed loop left behind (the sharded, gathered result at N > 1) against the oracle
+        if world == 1:
+            res_info, res_q = d_info.cpu().numpy(), d_q.cpu().numpy()
+        else:
+            res_info, res_q = last_out[0].cpu().numpy(), last_out[1].cpu().numpy()
+        line["parity_spot"] = parity_spot(plane, B, wk, res_info, res_q, args.parity_ranges, args.iso, args.rgb)
+        if line["parity_spot"]["mismatches"]:
+            rc = 3
     if world == 1 and not args.no_cpu_baseline:
         R, tcpu, t_pool = cpu_sample(plane, B, wk, 1, args.cpu_seconds, args.iso, args.rgb)
         v = R * ND * n_iso / tcpu
@@ -413,6 +465,9 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if rc:
+        sys.stderr.write("parity_spot: the timed result differs from the oracle\n")
+        sys.exit(rc)
 
 
 def main():

@@ -98,7 +98,12 @@ constexpr int kEpiWarps = 16;
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kChunksPerTile = kTileN / 32;
 constexpr int kBoundBytes = kChunksPerTile * 2 * 4 + 16;  // (rhi, rlo) f32 per 32-column chunk + tile flags (u32 + pad)
-constexpr int kFlagCap = 32;                         // flagged chunks kept per (row, unit, column half)
+// Flag lists of a (row, unit): kListsOf(EPI) lists of kCapOf(EPI) entries each, one list per epilogue warp that scans
+// the row -- two (column halves, a historical split) for the accumulator-per-warp mapping, four (one per 32-column
+// chunk of a tile) for the chunk-per-warp mapping.  Same footprint either way.
+constexpr int kFlagBytes = 4 * (4 + 8 * 16);         // per (row, unit): list lengths + entries, both mappings fit
+__host__ __device__ constexpr int kListsOf(int epi) { return epi ? 4 : 2; }
+__host__ __device__ constexpr int kCapOf(int epi) { return epi ? 16 : 32; }
 constexpr float kOneMinusEps = 1.0f - 1.9073486328125e-06f;  // 1 - 2^-19 (applied to the squared score)
 
 // Operand geometry of one (block size, MMA kind) pair.  F16 = false: kind::i8, two s8 digits per
@@ -207,15 +212,27 @@ __device__ __noinline__ float flag_threshold(float lb, float tie_abs)  // rare p
 // and the upper bound ub of its scores, which lets the refine step drop the chunk once the row's final bound is
 // known -- and, if it raises the row's lower bound, publish the bound (shared-memory slot `sh_lb`) and recompute the
 // threshold.
+// share bit 0: publish a raised bound to `sh_lb`; bit 1: the row is scanned by several warps (chunk-per-warp mapping,
+// isometry rows) -- first adopt the bound the others reached and re-test, so that a stale private threshold costs a
+// visit here, not a flag.
 struct RowFilter { float thresh, lbmax; int cnt; };
-__device__ __noinline__ RowFilter flag_chunk(RowFilter st, float lb, float ub, float tie_abs, int2 *list, int chunk_id,
-                                             uint32_t sh_lb, int publish)
+__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t saddr);
+__device__ __noinline__ RowFilter flag_chunk(RowFilter st, float lb, float ub, float tie_abs, int2 *list, int cap,
+                                             int chunk_id, uint32_t sh_lb, int share)
 {
-    if (st.cnt < kFlagCap) list[st.cnt] = make_int2(chunk_id, __float_as_int(ub));
+    if (share & 2) {
+        const float other = __uint_as_float(lds_volatile_u32(sh_lb));
+        if (other > st.lbmax) {
+            st.lbmax = other;
+            st.thresh = flag_threshold(other, tie_abs);
+            if (!(ub > st.thresh)) return st;
+        }
+    }
+    if (st.cnt < cap) list[st.cnt] = make_int2(chunk_id, __float_as_int(ub));
     st.cnt++;
     if (lb > st.lbmax) {
         st.lbmax = lb;
-        if (publish)  // positive floats order like their bits
+        if (share & 1)  // positive floats order like their bits
             asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(sh_lb), "r"(__float_as_uint(lb)) : "memory");
         const float rad = lb * lb * kOneMinusEps - tie_abs;
         st.thresh = rad > 0.0f ? sqrtf(rad) : -1.0f;
@@ -732,6 +749,17 @@ __device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t saddr)
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
     return v;
 }
+// Zero-instruction scheduling fence on 32 registers: code that consumes v[] stays behind everything issued before.
+__device__ __forceinline__ void pin_order(uint32_t (&v)[32])
+{
+    asm volatile(""
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ int dp4a_uu(uint32_t a_u8x4, uint32_t b_u8x4, int c)
 {
@@ -763,7 +791,12 @@ constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(
 // DBG (probe builds only): 1 = skip the scoring, 3 = skip the TMEM loads too, 4 = issue the MMAs of the first tile
 // of a unit only (the epilogue alone), 8 = count the cycles an epilogue warp spends in each phase (into `dump`).  DUMP: write every
 // accumulator to `dump` (the probe's exactness check).  The product runs <B, 0, false>.
-template <int B, bool F16, int DBG, bool DUMP>
+// EPI selects the epilogue mapping.  0: warp e owns accumulator e / 4 (one visit of four chunk loads per tile).
+// 1: warp e owns 32-column chunk e / 4 of EVERY accumulator: the four warps of an SM sub-partition drain the oldest
+// accumulator together, one tcgen05.ld each, so it goes back to the MMA issuer after one load time instead of four
+// loads and three chunk evaluations; a thread then follows four range rows (one per accumulator), and the four warps
+// that scan a row share its lower bound through shared memory.
+template <int B, bool F16, int DBG, bool DUMP, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
               int2 *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, uint32_t *__restrict__ row_lb, int n_sb,
@@ -779,7 +812,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     uint8_t *sA = smem;
     uint8_t *sB = smem + L::A_SB_BYTES;
     uint64_t *bars = (uint64_t *)(sB + NSTAGE * L::SLOT_BYTES);
-    const uint32_t bar0 = smem_u32(bars);
+    uint32_t bar0 = smem_u32(bars);
+    asm volatile("" : "+r"(bar0));  // opaque: keep the barrier base in a register instead of rematerialising it at every use
     auto BAR_B_FULL = [&](int s) { return bar0 + 8u * s; };
     auto BAR_B_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
     auto BAR_T_FULL = [&](int q) { return bar0 + 8u * (2 * NSTAGE + q); };
@@ -798,7 +832,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         }
         for (int q = 0; q < kAccs; q++) {
             mbar_init(BAR_T_FULL(q), 1);
-            mbar_init(BAR_T_EMPTY(q), kEpiWarps / kAccs);  // the 4 lane quarters of the accumulator
+            mbar_init(BAR_T_EMPTY(q), EPI ? kEpiWarps : kEpiWarps / kAccs);  // every warp that reads the accumulator
         }
         mbar_init(BAR_A_FULL, 1);
         mbar_init(BAR_A_EMPTY, 1);
@@ -945,8 +979,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             __syncwarp();
             a_phase ^= 1;
         }
-    } else if (warp >= 4) {
-        // ===================== epilogue =====================
+    } else if (warp >= 4 && EPI == 0) {
+        // ===================== epilogue, accumulator per warp =====================
         // Warp e: TMEM lane quarter lq = e % 4 (== warp % 4, the quarter this warp may access) of accumulator
         // q = e / 4: one thread = one range row, all 128 domains of a tile.  Per tile a warp makes ONE visit (one
         // t_full wait, four 32-column loads, one hand-back); the four warps of an SM sub-partition own the four
@@ -996,7 +1030,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     st.thresh = flag_threshold(seed, tie_abs);
                 }
             }
-            int2 *const list0 = flag_list + (((int64_t)ch * rows_padded + row) * 2) * kFlagCap;
+            int2 *const list0 = flag_list + (((int64_t)ch * rows_padded + row) * 2) * kCapOf(0);
             int cnt0 = 0, cnt1 = 0;  // entries of the two lists (column halves) of this (row, unit)
             if (DBG & 8) tk_mark = (uint32_t)clock();
             for (int t = t0; t < t1; t++) {
@@ -1075,7 +1109,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                         // the refine step reads two lists per (row, unit), one per column half, as the layout of
                         // the earlier two-warps-per-accumulator mapping had it
                         st.cnt = c < 2 ? cnt0 : cnt1;
-                        st = flag_chunk(st, M * rlo, ub, tie_abs, list0 + (c >> 1) * kFlagCap, t * kChunksPerTile + c, sh_lb, iso_shift);
+                        st = flag_chunk(st, M * rlo, ub, tie_abs, list0 + (c >> 1) * kCapOf(0), kCapOf(0), t * kChunksPerTile + c, sh_lb, iso_shift ? 1 : 0);
                         if (c < 2) cnt0 = st.cnt;
                         else cnt1 = st.cnt;
                     }
@@ -1087,6 +1121,141 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             flag_cnt[((int64_t)ch * rows_padded + row) * 2 + 1] = cnt1;
             // the row's bound after this unit: seeds its later units and lets the refine step drop stale flags
             if (st.lbmax > 0.0f) atomicMax(row_lb + ((row >> iso_shift) << iso_shift), __float_as_uint(st.lbmax));
+        }
+        if ((DBG & 8) && lane == 0 && dump) {
+            int32_t *o = dump + ((int64_t)blockIdx.x * kEpiWarps + e) * 8;
+            o[0] = (int32_t)((uint32_t)clock() - tk_begin);
+            o[1] = (int32_t)tk_b;
+            o[2] = (int32_t)tk_t;
+            o[3] = (int32_t)tk_l;
+            o[4] = (int32_t)tk_m;
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue, chunk per warp =====================
+        // Warp e: TMEM lane quarter lq = e % 4 (== warp % 4, the quarter this warp may access) and 32-column chunk
+        // kc = e / 4 of every accumulator.  Per tile a warp visits the four accumulators in the order the issuer
+        // completes them: t_full wait, ONE tcgen05.ld, hand-back, 16 FMNMX3.  The four warps of a sub-partition
+        // issue their loads of an accumulator together, so the accumulator is free again one load time after it
+        // completed.  A thread follows four rows (row q of accumulator q); the four warps that scan a row keep
+        // private thresholds and meet in shared memory only on the rare flag path (flag_chunk, share = 3).
+        const int e = warp - 4;
+        const int lq = e & 3, kc = e >> 2;
+        const uint32_t ta = tmem_base + ((uint32_t)(lq * 32) << 16) + kc * 32;
+        uint32_t tf_phase = 0;
+        uint32_t tk_b = 0, tk_t = 0, tk_l = 0, tk_m = 0, tk_mark = 0;
+        const uint32_t tk_begin = (DBG & 8) ? (uint32_t)clock() : 0u;
+        auto tick = [&](uint32_t &acc) {
+            if (DBG & 8) {
+                const uint32_t now = (uint32_t)clock();
+                acc += now - tk_mark;
+                tk_mark = now;
+            }
+        };
+        const int rq = lq * 32 + lane;  // row within a 128-row block
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            int sb = u % n_sb, ch = u / n_sb;  // chunk-major: see the accumulator-per-warp branch
+            int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
+            const int64_t row0 = (int64_t)sb * kRowsPerSB + rq;  // this thread's rows: row0 + q * kBlockM
+            // The shared bounds of the previous unit are dead once all 16 epilogue warps are here; the chunk-0 warps
+            // seed them with the bound the row reached in earlier units (row_lb; isometry rows share a slot).
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            if (kc == 0) {
+#pragma unroll
+                for (int q = 0; q < kAccs; q++) {
+                    const int64_t grow = ((row0 + q * kBlockM) >> iso_shift) << iso_shift;
+                    s_lb[q * kBlockM + rq] = ch > 0 ? *(volatile const uint32_t *)(row_lb + grow) : 0u;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            float thresh[kAccs], lbmax[kAccs], tie_abs[kAccs];
+            int cnt[kAccs];
+#pragma unroll
+            for (int q = 0; q < kAccs; q++) {
+                const int vR = vRarr[row0 + q * kBlockM];
+                tie_abs[q] = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
+                const float seed = __uint_as_float(s_lb[q * kBlockM + ((rq >> iso_shift) << iso_shift)]);
+                lbmax[q] = seed;
+                // vR == 0: every candidate scores error 0 and the first one wins (FC:677-678, FC:627) -> never flag
+                thresh[q] = (vR == 0) ? __int_as_float(0x7f800000) : (seed > 0.0f ? flag_threshold(seed, tie_abs[q]) : -1.0f);
+                cnt[q] = 0;
+            }
+            if (DBG & 8) tk_mark = (uint32_t)clock();
+            for (int t = t0; t < t1; t++) {
+                // (rhi, rlo) of this warp's chunk of the tile, from the tile blob in global memory
+                const float2 bnd = __ldg((const float2 *)(opB + (int64_t)t * L::B_TILE_BYTES + L::B_OP_BYTES) + kc);
+                tick(tk_b);
+#pragma unroll
+                for (int q = 0; q < kAccs; q++) {
+                    mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
+                    tc_fence_after();
+                    tick(tk_t);
+                    uint32_t v[32];
+                    if (!(DBG & 2)) {
+                        tmem_ld32(ta + q * kTileN, v);
+                        tmem_ld_wait();
+                    }
+                    tick(tk_l);
+                    tc_fence_before();  // this warp's only read of accumulator q for this tile: hand it back
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
+                    pin_order(v);  // the evaluation below must not be scheduled ahead of the hand-back
+                    if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring
+                    float M;  // max |kov| over the chunk, exact (see the other branch)
+                    if (F16) {
+                        auto av = [&](int k) { return fabsf(__uint_as_float(v[k])); };
+                        float c4[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            c4[i] = fmaxf(fmaxf(av(8 * i), av(8 * i + 1)), av(8 * i + 2));
+                            c4[i] = fmaxf(c4[i], fmaxf(av(8 * i + 3), av(8 * i + 4)));
+                            c4[i] = fmaxf(c4[i], fmaxf(av(8 * i + 5), av(8 * i + 6)));
+                        }
+                        const float m01 = fmaxf(fmaxf(c4[0], c4[1]), av(7));
+                        const float m23 = fmaxf(fmaxf(c4[2], c4[3]), av(15));
+                        M = fmaxf(fmaxf(fmaxf(m01, m23), av(23)), av(31));
+                    } else {
+                        int mx0 = 0, mn0 = 0, mx1 = 0, mn1 = 0;
+#pragma unroll
+                        for (int k = 0; k < 32; k += 4) {
+                            mx0 = max(mx0, max((int)v[k], (int)v[k + 1]));
+                            mn0 = min(mn0, min((int)v[k], (int)v[k + 1]));
+                            mx1 = max(mx1, max((int)v[k + 2], (int)v[k + 3]));
+                            mn1 = min(mn1, min((int)v[k + 2], (int)v[k + 3]));
+                        }
+                        M = __int2float_rn(max(max(mx0, mx1), -min(mn0, mn1)));
+                    }
+                    if (DUMP) {
+#pragma unroll
+                        for (int k = 0; k < 32; k++) {
+                            int iv = (int)v[k];
+                            if (F16) {  // a non-integral accumulator must fail the probe's check
+                                const float f = __uint_as_float(v[k]);
+                                iv = (f == rintf(f) && fabsf(f) < 2.0e9f) ? (int)f : (int)0x80000000;
+                            }
+                            dump[(row0 + q * kBlockM) * dump_ld + (int64_t)t * kTileN + kc * 32 + k] = iv;
+                        }
+                    }
+                    const float ub = M * bnd.x;
+                    if (ub > thresh[q]) {  // may hold the winner or one of its float ties
+                        RowFilter st = {thresh[q], lbmax[q], cnt[q]};
+                        int2 *const list = flag_list + ((((int64_t)ch * rows_padded + row0 + q * kBlockM) * kListsOf(1)) + kc) * kCapOf(1);
+                        st = flag_chunk(st, M * bnd.y, ub, tie_abs[q], list, kCapOf(1), t * kChunksPerTile + kc,
+                                        smem_u32(s_lb + q * kBlockM + ((rq >> iso_shift) << iso_shift)), 3);
+                        thresh[q] = st.thresh;
+                        lbmax[q] = st.lbmax;
+                        cnt[q] = st.cnt;
+                    }
+                    tick(tk_m);
+                }
+                tf_phase ^= 1;
+            }
+#pragma unroll
+            for (int q = 0; q < kAccs; q++) {
+                const int64_t row = row0 + q * kBlockM;
+                flag_cnt[((int64_t)ch * rows_padded + row) * kListsOf(1) + kc] = cnt[q];
+                // the row's bound after this unit: seeds its later units and lets the refine step drop stale flags
+                if (lbmax[q] > 0.0f) atomicMax(row_lb + ((row >> iso_shift) << iso_shift), __float_as_uint(lbmax[q]));
+            }
         }
         if ((DBG & 8) && lane == 0 && dump) {
             int32_t *o = dump + ((int64_t)blockIdx.x * kEpiWarps + e) * 8;
@@ -1203,16 +1372,16 @@ __device__ __forceinline__ int refine_kov(const uint32_t *rw, int rmean, int vR,
 template <class F>
 __device__ __forceinline__ void for_each_flagged(int lane, int64_t i, int64_t rows_padded, int n_chunks, int64_t npos,
                                                  const int2 *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt,
-                                                 float th, F &&consider)
+                                                 float th, int lpu, int cap, F &&consider)
 {
-    const int n_lists = 2 * n_chunks;  // (domain chunk of the unit, column half)
-    const int my_cnt = lane < n_lists ? flag_cnt[((int64_t)(lane >> 1) * rows_padded + i) * 2 + (lane & 1)] : 0;
-    const bool overflow = __any_sync(0xffffffffu, my_cnt > kFlagCap);
+    const int n_lists = lpu * n_chunks;  // (unit of the row, list of the unit): lpu = kListsOf(EPI) <= 4, n_chunks <= 8
+    const int my_cnt = lane < n_lists ? flag_cnt[((int64_t)(lane / lpu) * rows_padded + i) * lpu + (lane % lpu)] : 0;
+    const bool overflow = __any_sync(0xffffffffu, my_cnt > cap);
     if (!overflow) {
         for (int lh = 0; lh < n_lists; lh++) {
             const int cnt = __shfl_sync(0xffffffffu, my_cnt, lh);
             if (cnt == 0) continue;
-            const int2 *lst = flag_list + (((int64_t)(lh >> 1) * rows_padded + i) * 2 + (lh & 1)) * kFlagCap;
+            const int2 *lst = flag_list + (((int64_t)(lh / lpu) * rows_padded + i) * lpu + (lh % lpu)) * cap;
             const int2 mine = lane < cnt ? lst[lane] : make_int2(0, 0);
             unsigned live = __ballot_sync(0xffffffffu, lane < cnt && __int_as_float(mine.y) > th);
             while (live) {
@@ -1238,7 +1407,7 @@ __global__ void __launch_bounds__(128)
 k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ pos_raw,
               const int4 *__restrict__ pos_info,
               const int2 *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt,
-              const uint32_t *__restrict__ row_lb, int n_chunks,
+              const uint32_t *__restrict__ row_lb, int n_chunks, int lpu, int cap,
               int64_t rows_padded, int64_t rows, int64_t npos, const int64_t *__restrict__ dom0_pos,
               int32_t *__restrict__ best, Geom g, int64_t j0)
 {
@@ -1300,7 +1469,7 @@ k_umma_refine(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum,
         }
     };
     if (lane == 0) consider(*dom0_pos);
-    for_each_flagged(lane, i, rows_padded, n_chunks, npos, flag_list, flag_cnt, th_row, consider);
+    for_each_flagged(lane, i, rows_padded, n_chunks, npos, flag_list, flag_cnt, th_row, lpu, cap, consider);
     for (int o = 16; o > 0; o >>= 1) {
         float e2 = __shfl_down_sync(0xffffffffu, be, o);
         int i2 = __shfl_down_sync(0xffffffffu, bi, o);
@@ -1319,7 +1488,7 @@ template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_refine_iso(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ pos_raw,
                   const int4 *__restrict__ pos_info, const int2 *__restrict__ flag_list,
-                  const int32_t *__restrict__ flag_cnt, const uint32_t *__restrict__ row_lb, int n_chunks,
+                  const int32_t *__restrict__ flag_cnt, const uint32_t *__restrict__ row_lb, int n_chunks, int lpu, int cap,
                   int64_t rows_padded, int64_t ranges, int64_t npos,
                   const int64_t *__restrict__ dom0_pos, int32_t *__restrict__ best, Geom g, int64_t j0)
 {
@@ -1385,18 +1554,19 @@ k_umma_refine_iso(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
     int built = 0;
     bool overflow = false;
     for (int ch = 0; ch < n_chunks && !overflow; ch++) {
-        // 16 contiguous list lengths: operand row 8 r + k, column half h at lane 2 k + h
-        const int64_t base = ((int64_t)ch * rows_padded + r * 8) * 2;
-        const int my_cnt = lane < 16 ? flag_cnt[base + lane] : 0;
-        if (__any_sync(0xffffffffu, my_cnt > kFlagCap)) { overflow = true; break; }
+        // 8 * lpu (<= 32) contiguous list lengths: operand row 8 r + k, list h of the unit at lane lpu * k + h
+        const int64_t base = ((int64_t)ch * rows_padded + r * 8) * lpu;
+        const int my_cnt = lane < 8 * lpu ? flag_cnt[base + lane] : 0;
+        if (__any_sync(0xffffffffu, my_cnt > cap)) { overflow = true; break; }
         for (int kiso = 0; kiso < 8; kiso++) {
-            const int c0 = __shfl_sync(0xffffffffu, my_cnt, 2 * kiso), c1 = __shfl_sync(0xffffffffu, my_cnt, 2 * kiso + 1);
-            if ((c0 | c1) == 0) continue;
+            int any = 0;
+            for (int h = 0; h < lpu; h++) any |= __shfl_sync(0xffffffffu, my_cnt, lpu * kiso + h);
+            if (any == 0) continue;
             if (built != kiso) { build(kiso); built = kiso; }
-            for (int h = 0; h < 2; h++) {
-                const int cnt = h ? c1 : c0;
+            for (int h = 0; h < lpu; h++) {
+                const int cnt = __shfl_sync(0xffffffffu, my_cnt, lpu * kiso + h);
                 if (cnt == 0) continue;
-                const int2 *lst = flag_list + (base + 2 * kiso + h) * kFlagCap;
+                const int2 *lst = flag_list + (base + lpu * kiso + h) * cap;
                 const int2 mine = lane < cnt ? lst[lane] : make_int2(0, 0);
                 unsigned live = __ballot_sync(0xffffffffu, lane < cnt && __int_as_float(mine.y) > th_row);  // see for_each_flagged
                 while (live) {
@@ -1428,7 +1598,7 @@ template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_refine_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, const uint8_t *__restrict__ opB,
                   const int4 *__restrict__ pos_info, const int2 *__restrict__ flag_list, const int32_t *__restrict__ flag_cnt,
-                  const uint32_t *__restrict__ row_lb, int n_chunks,
+                  const uint32_t *__restrict__ row_lb, int n_chunks, int lpu, int cap,
                   int64_t rows_padded, int64_t rows, int64_t npos, const int64_t *__restrict__ dom0_pos,
                   int32_t *__restrict__ best, Geom g, int64_t j0)
 {
@@ -1498,7 +1668,7 @@ k_umma_refine_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
         }
     };
     if (lane == 0) consider(*dom0_pos);
-    for_each_flagged(lane, i, rows_padded, n_chunks, npos, flag_list, flag_cnt, th_row, consider);
+    for_each_flagged(lane, i, rows_padded, n_chunks, npos, flag_list, flag_cnt, th_row, lpu, cap, consider);
     for (int o = 16; o > 0; o >>= 1) {
         float e2 = __shfl_down_sync(0xffffffffu, be, o);
         int i2 = __shfl_down_sync(0xffffffffu, bi, o);
@@ -1582,10 +1752,30 @@ template <int B, bool F16>
 size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p = make_plan(g, rows, num_sms);
-    // [A blobs][vR s32][flag_cnt s32 x n_chunks x 2][flag_list (s32 id, f32 bound) x n_chunks x 2 x kFlagCap][row_lb u32]
-    return (size_t)p.n_sb * Lay<B, F16>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * 2 * (4 + 8 * kFlagCap) +
+    // [A blobs][vR s32][flag_cnt s32 x n_chunks x lists][flag_list (s32 id, f32 bound) x n_chunks x lists x cap][row_lb u32]
+    return (size_t)p.n_sb * Lay<B, F16>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * kFlagBytes +
            (size_t)p.rp * 4 + 1024;
 }
+
+using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int2 *, int32_t *, uint32_t *, int, int,
+                         int, int, int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
+
+// dbg (probe only): 1 / 3 strip the scoring / the TMEM loads too, 4: epilogue alone, 8 / 12: phase cycle counts
+template <int B, bool F16, int EPI>
+KernelT pick_kernel(bool dump, uint32_t dbg)
+{
+    if (dump) return k_umma_search<B, F16, 0, true, EPI>;
+    if ((dbg & 3u) == 1) return k_umma_search<B, F16, 1, false, EPI>;
+    if ((dbg & 3u) == 3) return k_umma_search<B, F16, 3, false, EPI>;
+    if (dbg == 4) return k_umma_search<B, F16, 4, false, EPI>;
+    if (dbg == 8) return k_umma_search<B, F16, 8, false, EPI>;
+    if (dbg == 12) return k_umma_search<B, F16, 12, false, EPI>;
+    return k_umma_search<B, F16, 0, false, EPI>;
+}
+
+// Epilogue mapping each configuration runs by default (measured, profiles/README.md).
+template <int B, bool F16>
+constexpr int default_epi() { return 1; }
 
 template <int B, bool F16>
 int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s, const char **err,
@@ -1600,8 +1790,8 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     uint8_t *opA = w.opA;
     int32_t *vR = (int32_t *)(opA + (size_t)p.n_sb * L::A_SB_BYTES);
     int32_t *flag_cnt = vR + rp;
-    int2 *flag_list = (int2 *)(flag_cnt + rp * p.n_chunks * 2);  // 8-byte aligned: the blobs are, and rp is even
-    uint32_t *row_lb = (uint32_t *)(flag_list + rp * p.n_chunks * 2 * kFlagCap);  // per operand row: best lower bound of max x reached by finished units
+    int2 *flag_list = (int2 *)(flag_cnt + rp * p.n_chunks * 4);  // 8-byte aligned: the blobs are, and rp is even
+    uint32_t *row_lb = (uint32_t *)(flag_list + rp * p.n_chunks * 64);  // per operand row: best lower bound of max x reached by finished units
     const bool rgb = g.C == 3;                        // kind::f16 only (see "RGB operands")
     if (rgb && !F16) { *err = "the RGB tensor path is kind::f16 only"; return -1; }
     OpBLayout<B, F16> lay(g, p);
@@ -1636,21 +1826,18 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     }
     launches += 2;
     // 3. the fused search
-    using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int2 *, int32_t *, uint32_t *, int, int,
-                             int, int, int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
-    KernelT kern = k_umma_search<B, F16, 0, false>;  // dbg (probe only): 1 / 3 strip the scoring / the TMEM loads too
-    if (dump && !(dbg & 8u)) kern = k_umma_search<B, F16, 0, true>;
-    else if ((dbg & 3u) == 1) kern = k_umma_search<B, F16, 1, false>;
-    else if ((dbg & 3u) == 3) kern = k_umma_search<B, F16, 3, false>;
-    else if (dbg == 4) kern = k_umma_search<B, F16, 4, false>;
-    else if (dbg == 8) { kern = k_umma_search<B, F16, 8, false>; dump = w.best; }    // phase cycle counts -> w.best
-    else if (dbg == 12) { kern = k_umma_search<B, F16, 12, false>; dump = w.best; }
+    // Epilogue mapping (see k_umma_search): the default of this (block size, kind) pair, or the probe's choice
+    // (variant bit 1: accumulator per warp, bit 2: chunk per warp).
+    const int epi = (variant & 2) ? 0 : ((variant & 4) ? 1 : default_epi<B, F16>());
+    KernelT kern = pick_kernel<B, F16, 0>(dump && !(dbg & 8u), dbg);
+    if (epi) kern = pick_kernel<B, F16, 1>(dump && !(dbg & 8u), dbg);
+    if (dbg == 8 || dbg == 12) dump = w.best;  // phase cycle counts -> w.best
     ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
     int n_units = p.n_sb * p.n_chunks;
     int grid = n_units < num_sms ? n_units : num_sms;
     uint32_t lbo_a = 128, sbo_a = L::SBO_A, lbo_b = 128, sbo_b = L::SBO_B;
-    if (variant == 1) { lbo_a = L::SBO_A; sbo_a = 128; lbo_b = L::SBO_B; sbo_b = 128; }  // probe only
+    if (variant & 1) { lbo_a = L::SBO_A; sbo_a = 128; lbo_b = L::SBO_B; sbo_b = 128; }  // probe only
     if (k0) cudaEventRecord(k0, s);
     cudaMemsetAsync(row_lb, 0, (size_t)rp * 4, s);
     kern<<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, flag_list, flag_cnt, row_lb, p.n_sb, p.n_chunks, p.ntiles,
@@ -1662,13 +1849,13 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
         if (rgb) {
             if constexpr (F16)
                 k_umma_refine_rgb<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, w.opB, pos_info, flag_list, flag_cnt,
-                                                                                row_lb, p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
+                                                                                row_lb, p.n_chunks, kListsOf(epi), kCapOf(epi), rp, rows, p.npos, dom0, w.best, g, j0);
         } else if (g.n_iso > 1)
             k_umma_refine_iso<B><<<(unsigned)((j1 - j0 + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_info, flag_list, flag_cnt,
-                                                                             row_lb, p.n_chunks, rp, j1 - j0, p.npos, dom0, w.best, g, j0);
+                                                                             row_lb, p.n_chunks, kListsOf(epi), kCapOf(epi), rp, j1 - j0, p.npos, dom0, w.best, g, j0);
         else
             k_umma_refine<B><<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w.src, w.rsum, pos_raw, pos_info, flag_list, flag_cnt,
-                                                                        row_lb, p.n_chunks, rp, rows, p.npos, dom0, w.best, g, j0);
+                                                                        row_lb, p.n_chunks, kListsOf(epi), kCapOf(epi), rp, rows, p.npos, dom0, w.best, g, j0);
     }
     launches += 2;
     ce = cudaGetLastError();

@@ -475,6 +475,7 @@ typedef struct {
     const codebook_t *cb;
     long j0, j1;
     float *info;
+    const long *list; /* NULL: ranges j0..j1-1; else ranges list[j0..j1-1] (any order, test spot checks) */
 } job_t;
 
 /* Body of the range loops FC:125-159 (grey) / FC:186-215 (RGB) for j in [j0, j1). */
@@ -485,7 +486,8 @@ static void *encode_job(void *arg)
     int rpw = W / B, rph = H / B, dpw = rpw * 2 - 3, dph = rph * 2 - 3;
     int32_t *range = (int32_t *)malloc(sizeof(int32_t) * n);
     int *tmp = (int *)malloc(sizeof(int) * n);
-    for (long j = jb->j0; j < jb->j1; j++) {
+    for (long jj = jb->j0; jj < jb->j1; jj++) {
+        const long j = jb->list ? jb->list[jj] : jj;
         int x = (int)(j % rpw) * B, y = (int)(j / rpw) * B;
         int i = fic_oracle_domain_block_index(x, y, rpw, rph, dpw, B);
         int dy, dx;
@@ -513,12 +515,16 @@ static void *encode_job(void *arg)
 }
 
 static int encode_common(const int32_t *argb, int W, int H, int B, int wk, int is_rgb,
-                         long j0, long j1, int nthreads, float *info)
+                         long j0, long j1, int nthreads, float *info, const long *list)
 {
     int rc = check_args(W, H, B, wk);
     if (rc) return rc;
     long nr = (long)(W / B) * (H / B);
-    if (j0 < 0 || j1 > nr || j0 > j1) return -5;
+    if (j0 < 0 || j0 > j1) return -5;
+    if (!list && j1 > nr) return -5;
+    if (list)
+        for (long k = j0; k < j1; k++)
+            if (list[k] < 0 || list[k] >= nr) return -5;
     codebook_t cb;
     if (codebook_build(&cb, argb, W, H, B, is_rgb == 1)) return -6;
     if (nthreads < 1) nthreads = 1;
@@ -531,7 +537,7 @@ static int encode_common(const int32_t *argb, int W, int H, int B, int wk, int i
         long a = j0 + t * per, b = a + per;
         if (a > j1) a = j1;
         if (b > j1) b = j1;
-        jobs[t] = (job_t){argb, W, H, B, wk, is_rgb, &cb, a, b, info};
+        jobs[t] = (job_t){argb, W, H, B, wk, is_rgb, &cb, a, b, info, list};
     }
     if (nthreads == 1) {
         encode_job(&jobs[0]);
@@ -546,19 +552,29 @@ static int encode_common(const int32_t *argb, int W, int H, int B, int wk, int i
 int fic_oracle_encode_grey(const int32_t *argb, int W, int H, int B, int wk,
                            long range_begin, long range_end, int nthreads, float *info)
 {
-    return encode_common(argb, W, H, B, wk, 0, range_begin, range_end, nthreads, info);
+    return encode_common(argb, W, H, B, wk, 0, range_begin, range_end, nthreads, info, NULL);
 }
 
 int fic_oracle_encode_rgb(const int32_t *argb, int W, int H, int B, int wk,
                           long range_begin, long range_end, int nthreads, float *info)
 {
-    return encode_common(argb, W, H, B, wk, 1, range_begin, range_end, nthreads, info);
+    return encode_common(argb, W, H, B, wk, 1, range_begin, range_end, nthreads, info, NULL);
 }
 
 int fic_oracle_encode_grey_iso(const int32_t *argb, int W, int H, int B, int wk,
                                long range_begin, long range_end, int nthreads, float *info)
 {
-    return encode_common(argb, W, H, B, wk, 2, range_begin, range_end, nthreads, info);
+    return encode_common(argb, W, H, B, wk, 2, range_begin, range_end, nthreads, info, NULL);
+}
+
+/* The same range-loop body for an arbitrary list of range blocks (spot checks of images whose full encode the
+ * CPU cannot finish): the codebook is built once, info[j] is written for every listed j.  mode: 0 grey, 1 RGB,
+ * 2 grey + isometries (extension). */
+int fic_oracle_encode_list(const int32_t *argb, int W, int H, int B, int wk, int mode,
+                           const long *ranges, long count, int nthreads, float *info)
+{
+    if (mode < 0 || mode > 2 || count < 0 || (count && !ranges)) return -5;
+    return encode_common(argb, W, H, B, wk, mode, 0, count, nthreads, info, ranges);
 }
 
 /* ------------------------------------------------------------------ stream I/O */

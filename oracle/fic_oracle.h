@@ -50,6 +50,12 @@ int fic_oracle_encode_grey(const int32_t *argb, int W, int H, int B, int wk,
 int fic_oracle_encode_rgb(const int32_t *argb, int W, int H, int B, int wk,
                           long range_begin, long range_end, int nthreads, float *info);
 
+/* The same loop body for a list of range blocks (count entries of `ranges`, any order): info[j] is written for
+ * every listed j only.  mode: 0 grey, 1 RGB, 2 grey + isometries.  Used by the spot checks of the 4096^2 / 8192^2
+ * configurations, whose full encode takes the CPU hours. */
+int fic_oracle_encode_list(const int32_t *argb, int W, int H, int B, int wk, int mode,
+                           const long *ranges, long count, int nthreads, float *info);
+
 /* EXTENSION (not in the reference, which has no isometries): grey encode whose candidate loop has an inner
  * loop over the 8 isometries of the domain block (order (c, k) lexicographic, same score, same strict-<
  * rule) -> info[NR][4] = {c, a, b, k}.  is_rgb == 2 selects this mode in write_data / collage, and a stream

@@ -44,6 +44,9 @@ def lib() -> C.CDLL:
         for fn in (L.fic_oracle_encode_grey, L.fic_oracle_encode_rgb, L.fic_oracle_encode_grey_iso):
             fn.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_long, C.c_int, f32p]
             fn.restype = C.c_int
+        L.fic_oracle_encode_list.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long), C.c_long,
+                                             C.c_int, f32p]
+        L.fic_oracle_encode_list.restype = C.c_int
         L.fic_oracle_write_data.argtypes = [C.c_int] * 5 + [f32p, u8p]
         L.fic_oracle_write_data.restype = C.c_size_t
         L.fic_oracle_decode.argtypes = [u8p, C.c_size_t, i32p, f32p, C.POINTER(C.c_int)]
@@ -121,6 +124,23 @@ def encode(argb, B: int, wk: int, rgb: bool = False, range_begin: int = 0, range
     if rc:
         raise ValueError(f"oracle encode rejected arguments (rc={rc})")
     return info
+
+
+def encode_list(argb, B: int, wk: int, ranges, rgb: bool = False, iso: bool = False, nthreads: int = 1) -> np.ndarray:
+    """Codes of the listed range blocks only (the codebook is built once): returns info[len(ranges)][3|5|4] in the
+    order of `ranges`.  For spot checks of images whose full encode the CPU cannot finish."""
+    a = _argb(argb)
+    H, W = a.shape
+    nr = (W // B) * (H // B)
+    mode = _mode(rgb, iso)
+    S = (3, 5, 4)[mode]
+    r = np.ascontiguousarray(ranges, dtype=np.int64)
+    info = np.zeros((nr, S), np.float32)
+    rc = lib().fic_oracle_encode_list(_p(a, C.c_int32), W, H, B, wk, mode, r.ctypes.data_as(C.POINTER(C.c_long)), len(r),
+                                      nthreads, _p(info, C.c_float))
+    if rc:
+        raise ValueError(f"oracle encode_list rejected arguments (rc={rc})")
+    return info[r]
 
 
 def write_data(info: np.ndarray, W: int, H: int, B: int, wk: int, rgb: bool = False, iso: bool = False) -> bytes:

@@ -1,6 +1,10 @@
-"""Full-size checks through size-independent properties (the oracle cannot finish these
-sizes): both search engines must agree on every code, and encode -> decode must
-reconstruct the image to the PSNR fractal coding reaches on this content."""
+"""Full-size checks.  The oracle cannot finish a whole 4096^2 / 8192^2 full-pool encode, but it can finish any
+few hundred range blocks of one (oracle.encode_list builds the codebook once): the headline configurations are
+compared with it on random range blocks plus the first and last range row, bit for bit.  Around that,
+size-independent properties: both search engines agree on every code, row shards compose, and
+encode -> decode reconstructs the image to the PSNR fractal coding reaches on this content."""
+import os
+
 import numpy as np
 import pytest
 
@@ -174,3 +178,108 @@ def test_rgb_roundtrip_2048(fic, handle):
     rec = np.stack([(du >> 16) & 0xFF, (du >> 8) & 0xFF, du & 0xFF]).astype(np.uint8)
     assert it <= 50
     assert psnr(np.stack(planes), rec) > 12.0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs[2] / [3] against the CPU oracle (FC:613-644, FC:655-687, FC:697-808), bit for bit
+# ---------------------------------------------------------------------------------------------------------
+
+def _spot_ranges(NR, rpw, n_random, rows, seed):
+    """n_random random range blocks + the given whole range rows (first / last: the clamped window geometry of
+    FC:522-529 lives there)."""
+    rng = np.random.default_rng(seed)
+    parts = [rng.integers(0, NR, n_random)] + [np.arange(r * rpw, (r + 1) * rpw) for r in rows]
+    return np.unique(np.concatenate(parts)).astype(np.int64)
+
+
+def _quantise(fic_mod, info, S):
+    """writeData's ints from imageInfo floats, Java (int) semantics (FC:242-244, FC:250-254; 4: isometry extension)."""
+    scale = {3: (1, 100, 1), 5: (1, 1000000, 100000, 100000, 1), 4: (1, 100, 1, 1)}[S]
+    out = np.zeros(info.shape, np.int32)
+    with np.errstate(invalid="ignore", over="ignore"):
+        for c in range(S):
+            x = info[:, c] * np.float32(scale[c])
+            ok = ~np.isnan(x)
+            v = np.clip(np.trunc(np.where(ok, x, 0).astype(np.float64)), -2147483648.0, 2147483647.0)
+            out[:, c] = np.where(ok, v, 0).astype(np.int64).astype(np.int32)
+    return out
+
+
+def _assert_equals_oracle(oracle, img, B, wk, info, q, ranges, rgb=False):
+    ref = oracle.encode_list(img, B, wk, ranges, rgb=rgb, nthreads=os.cpu_count() or 1)
+    got = info[ranges]
+    same = (got.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(got) & np.isnan(ref))
+    bad = np.nonzero(~same.all(1))[0]
+    assert bad.size == 0, f"{bad.size} of {len(ranges)} ranges differ from the oracle, first: range {ranges[bad[0]]} gpu {got[bad[0]]} oracle {ref[bad[0]]}"
+    assert (q[ranges] == _quantise(None, ref, info.shape[1])).all()
+
+
+@pytest.mark.parametrize("B,mma", [(8, "f16"), (8, "i8"), (16, "i8"), (4, "f16")])
+def test_headline_4096_equals_oracle(fic, handle, oracle, B, mma):
+    """configs[2]: 4096^2 synthetic grey, full pool, on the tensor cores: >= 256 random range blocks and the first
+    and last range row equal the oracle's codes (imageInfo floats bitwise, writeData ints).  B = 4 (4.4e12
+    evaluations on the GPU, 1 M domains x 16 pixels per oracle range) uses fewer oracle ranges to stay in budget."""
+    W = 4096
+    p = fic.synth.structured(W, W, 1)
+    img = fic.synth.grey_to_argb(p)
+    rpw = W // B
+    wk = 2 * rpw - 3
+    NR = rpw * rpw
+    handle.set_umma_kind(fic.FIC_UMMA_KIND_F16 if mma == "f16" else fic.FIC_UMMA_KIND_I8)
+    try:
+        info, q = handle.encode(img, B, wk, rgb=False)
+    finally:
+        handle.set_umma_kind(fic.FIC_UMMA_KIND_AUTO)
+    assert handle.timings().engine == fic.FIC_ENGINE_UMMA
+    if B == 4:
+        ranges = _spot_ranges(NR, rpw, 96, [], 11)
+        ranges = np.unique(np.concatenate([ranges, np.arange(0, 16), np.arange(NR - 16, NR)]))
+    else:
+        ranges = _spot_ranges(NR, rpw, 256, [0, rpw - 1], 11)
+    _assert_equals_oracle(oracle, img, B, wk, info, q, ranges)
+
+
+def test_headline_4096_noise_equals_oracle(fic, handle, oracle):
+    """The same on uniform noise: every row sees ~1e6 near-equal correlations, the tie-heaviest natural content."""
+    W, B = 4096, 8
+    img = fic.synth.grey_to_argb(fic.synth.noise(W, W, 1))
+    rpw = W // B
+    wk = 2 * rpw - 3
+    info, q = handle.encode(img, B, wk, rgb=False)
+    assert handle.timings().engine == fic.FIC_ENGINE_UMMA
+    _assert_equals_oracle(oracle, img, B, wk, info, q, _spot_ranges(rpw * rpw, rpw, 192, [], 5))
+
+
+def test_headline_4096_rgb_equals_oracle(fic, handle, oracle):
+    """4096^2 RGB, B = 8, full pool on the tensor cores (FC:697-808) against the oracle."""
+    W, B = 4096, 8
+    planes = [fic.synth.structured(W, W, s) for s in (1, 2, 3)]
+    img = _rgb_argb(planes)
+    rpw = W // B
+    wk = 2 * rpw - 3
+    info, q = handle.encode(img, B, wk, rgb=True)
+    assert handle.timings().engine == fic.FIC_ENGINE_UMMA
+    _assert_equals_oracle(oracle, img, B, wk, info, q, _spot_ranges(rpw * rpw, rpw, 256, [0, rpw - 1], 3), rgb=True)
+
+
+def test_headline_8192_sharded_equals_oracle(fic, handle, oracle):
+    """configs[3]: 8192^2 synthetic grey, B = 8, full pool (4.39e12 evaluations), encoded as the 8 range-row shards
+    of the 8-GPU run (fic_encode range_begin / range_end, the call every rank makes) and compared with the oracle on
+    random range blocks of every shard plus the first and last range row."""
+    W, B, G = 8192, 8, 8
+    p = fic.synth.structured(W, W, 1)
+    img = fic.synth.grey_to_argb(p)
+    rpw = W // B
+    wk = 2 * rpw - 3
+    NR = rpw * rpw
+    info = np.zeros((NR, 3), np.float32)
+    q = np.zeros((NR, 3), np.int32)
+    from fractal_image_compression_b200.dist import partition_range_rows
+
+    for j0, j1 in partition_range_rows(rpw, rpw, G):
+        handle.encode(img, B, wk, rgb=False, range_begin=j0, range_end=j1, info=info, q=q)
+        assert handle.timings().engine == fic.FIC_ENGINE_UMMA
+    rng = np.random.default_rng(17)
+    per_shard = [rng.integers(j0, j1, 16) for j0, j1 in partition_range_rows(rpw, rpw, G)]
+    ranges = np.unique(np.concatenate(per_shard + [np.arange(0, 64), np.arange(NR - 64, NR)])).astype(np.int64)
+    _assert_equals_oracle(oracle, img, B, wk, info, q, ranges)
