@@ -4,13 +4,13 @@ lib/libfic_b200.so (include/fic_b200.h); this package is its host-side mirror of
 reference's codec interface plus the torch.distributed plumbing for multi-GPU encodes.
 """
 from . import _lib, synth
-from ._lib import (FIC_ENGINE_AUTO, FIC_ENGINE_DIRECT, FIC_ENGINE_UMMA, FIC_UMMA_KIND_AUTO, FIC_UMMA_KIND_F16,
+from ._lib import (FIC_ENGINE_AUTO, FIC_ENGINE_DIRECT, FIC_ENGINE_FUSED, FIC_ENGINE_UMMA, FIC_UMMA_KIND_AUTO, FIC_UMMA_KIND_F16,
                    FIC_UMMA_KIND_I8, FIC_MODE_GREY, FIC_MODE_RGB, FIC_MODE_GREY_ISO, ABI_SYMBOLS, LIB_PATH, FicError, Timings)
-from .codec import ByteSink, FractalCompression, Handle, RasterImage, stream_read, stream_write
+from .codec import ByteSink, FractalCompression, Handle, MultiHandle, RasterImage, stream_read, stream_write
 
 __all__ = [
-    "ABI_SYMBOLS", "ByteSink", "FIC_ENGINE_AUTO", "FIC_ENGINE_DIRECT", "FIC_ENGINE_UMMA", "FIC_MODE_GREY", "FIC_MODE_GREY_ISO",
+    "ABI_SYMBOLS", "ByteSink", "FIC_ENGINE_AUTO", "FIC_ENGINE_DIRECT", "FIC_ENGINE_FUSED", "FIC_ENGINE_UMMA", "FIC_MODE_GREY", "FIC_MODE_GREY_ISO",
     "FIC_MODE_RGB", "FIC_UMMA_KIND_AUTO",
     "FIC_UMMA_KIND_F16", "FIC_UMMA_KIND_I8", "FicError",
-    "FractalCompression", "Handle", "LIB_PATH", "RasterImage", "Timings", "stream_read", "stream_write", "synth",
+    "FractalCompression", "Handle", "LIB_PATH", "MultiHandle", "RasterImage", "Timings", "stream_read", "stream_write", "synth",
 ]

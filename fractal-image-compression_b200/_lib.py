@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfic_b200.so")
 
 FIC_OK = 0
 FIC_E_ARG, FIC_E_CUDA, FIC_E_NOMEM, FIC_E_STREAM, FIC_E_INTERNAL = -1, -2, -3, -4, -5
-FIC_ENGINE_AUTO, FIC_ENGINE_DIRECT, FIC_ENGINE_UMMA = 0, 1, 2
+FIC_ENGINE_AUTO, FIC_ENGINE_DIRECT, FIC_ENGINE_UMMA, FIC_ENGINE_FUSED = 0, 1, 2, 3
 FIC_UMMA_KIND_AUTO, FIC_UMMA_KIND_I8, FIC_UMMA_KIND_F16 = 0, 1, 2
 FIC_MODE_GREY, FIC_MODE_RGB, FIC_MODE_GREY_ISO = 0, 1, 2
 FIC_OPT_ENGINE = 1
@@ -28,6 +28,10 @@ ABI_SYMBOLS = [
     "fic_sync", "fic_decode", "fic_collage", "fic_build_pool", "fic_stream_size", "fic_stream_write",
     "fic_stream_read_header", "fic_stream_read_codes", "fic_measure_int8_peak", "fic_measure_mma_peak",
     "fic_pin_host_buffer", "fic_unpin_host_buffer",
+    "fic_encode_grey_u8", "fic_encode_rgb_planes", "fic_decode_u8", "fic_decode_planes_dev",
+    "fic_create_multi", "fic_destroy_multi", "fic_multi_last_error", "fic_multi_device_count", "fic_multi_handle",
+    "fic_multi_set_option", "fic_multi_get_timings", "fic_multi_range_slice", "fic_multi_encode_grey",
+    "fic_multi_encode_rgb", "fic_multi_encode_grey_iso", "fic_multi_encode_grey_u8", "fic_multi_encode_rgb_planes",
 ]
 
 
@@ -73,6 +77,24 @@ def load() -> C.CDLL:
     L.fic_geometry.argtypes = [C.c_int] * 4 + [C.POINTER(i64), C.POINTER(i64)]
     for fn in (L.fic_encode_grey, L.fic_encode_rgb, L.fic_encode_grey_iso):
         fn.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, i64, i64, vp, vp]
+    for fn in (L.fic_encode_grey_u8, L.fic_encode_rgb_planes):
+        fn.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, i64, i64, vp, vp]
+    for fn in (L.fic_decode_u8, L.fic_decode_planes_dev):
+        fn.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, f32p, C.POINTER(C.c_int)]
+    L.fic_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.fic_destroy_multi.argtypes = [vp]
+    L.fic_destroy_multi.restype = None
+    L.fic_multi_last_error.argtypes = [vp]
+    L.fic_multi_last_error.restype = C.c_char_p
+    L.fic_multi_device_count.argtypes = [vp]
+    L.fic_multi_handle.argtypes = [vp, C.c_int]
+    L.fic_multi_handle.restype = vp
+    L.fic_multi_set_option.argtypes = [vp, C.c_int, C.c_int]
+    L.fic_multi_get_timings.argtypes = [vp, C.c_int, C.POINTER(Timings)]
+    L.fic_multi_range_slice.argtypes = [vp, C.c_int, C.POINTER(i64), C.POINTER(i64)]
+    for fn in (L.fic_multi_encode_grey, L.fic_multi_encode_rgb, L.fic_multi_encode_grey_iso, L.fic_multi_encode_grey_u8,
+               L.fic_multi_encode_rgb_planes):
+        fn.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     L.fic_encode_planes_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64, i64, vp, vp]
     L.fic_sync.argtypes = [vp]
     L.fic_decode.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, f32p,
@@ -90,7 +112,8 @@ def load() -> C.CDLL:
     L.fic_stream_read_codes.argtypes = [vp, C.c_size_t, vp]
     for name in ABI_SYMBOLS:
         fn = getattr(L, name)
-        if fn.restype is C.c_int and name not in ("fic_version", "fic_last_error", "fic_stream_size"):
+        if fn.restype is C.c_int and name not in ("fic_version", "fic_last_error", "fic_stream_size", "fic_multi_last_error",
+                                                   "fic_multi_handle"):
             fn.restype = C.c_int
     _lib = L
     return L

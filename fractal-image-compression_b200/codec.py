@@ -157,6 +157,25 @@ class Handle:
         self._check(fn(self._h, _ptr(a), W, H, B, wk, range_begin, range_end, _ptr(info), _ptr(q)))
         return info, q
 
+    def encode_u8(self, planes: np.ndarray, B: int, wk: int, range_begin: int = 0, range_end: int | None = None,
+                  info: np.ndarray | None = None, q: np.ndarray | None = None):
+        """fic_encode_grey_u8 (planes: uint8 [H, W]) / fic_encode_rgb_planes (uint8 [3, H, W]): the 8-bit host entries."""
+        a = np.ascontiguousarray(planes, dtype=np.uint8)
+        rgb = a.ndim == 3
+        assert not rgb or a.shape[0] == 3
+        H, W = a.shape[-2:]
+        S = 5 if rgb else 3
+        nr = (W // B) * (H // B) if B > 0 else 0
+        if range_end is None:
+            range_end = nr
+        if info is None:
+            info = np.zeros((max(nr, 0), S), np.float32)
+        if q is None:
+            q = np.zeros((max(nr, 0), S), np.int32)
+        fn = self._L.fic_encode_rgb_planes if rgb else self._L.fic_encode_grey_u8
+        self._check(fn(self._h, _ptr(a), W, H, B, wk, range_begin, range_end, _ptr(info), _ptr(q)))
+        return info, q
+
     def encode_planes_dev(self, d_planes: int, rgb, W: int, H: int, B: int, wk: int, range_begin: int,
                           range_end: int, d_info: int | None, d_q: int | None):
         """Asynchronous device-pointer entry (fic_encode_planes_dev)."""
@@ -176,6 +195,29 @@ class Handle:
         self._check(self._L.fic_decode(self._h, int(rgb), W, H, B, wk, _ptr(qq), max_iters, _ptr(out),
                                        C.byref(avg), C.byref(it)))
         return out, np.float32(avg.value), it.value
+
+    def decode_u8(self, q: np.ndarray, W: int, H: int, B: int, wk: int, rgb, avg_error: float = 0.0,
+                  max_iters: int = 50, out: np.ndarray | None = None):
+        """fic_decode_u8: the image as 8-bit planes, uint8 [H, W] (grey) or [3, H, W] (RGB)."""
+        qq = np.ascontiguousarray(q, dtype=np.int32)
+        shape = (3, H, W) if int(rgb) == 1 else (H, W)
+        if out is None:
+            out = np.empty(shape, np.uint8)
+        assert out.dtype == np.uint8 and out.shape == shape and out.flags["C_CONTIGUOUS"]
+        avg = C.c_float(avg_error)
+        it = C.c_int(0)
+        self._check(self._L.fic_decode_u8(self._h, int(rgb), W, H, B, wk, _ptr(qq), max_iters, _ptr(out),
+                                          C.byref(avg), C.byref(it)))
+        return out, np.float32(avg.value), it.value
+
+    def decode_planes_dev(self, d_q: int, W: int, H: int, B: int, wk: int, rgb, d_planes_out: int,
+                          avg_error: float = 0.0, max_iters: int = 50):
+        """fic_decode_planes_dev: device codes in, device 8-bit planes out; returns (avgError, iterations)."""
+        avg = C.c_float(avg_error)
+        it = C.c_int(0)
+        self._check(self._L.fic_decode_planes_dev(self._h, int(rgb), W, H, B, wk, C.c_void_p(d_q), max_iters,
+                                                  C.c_void_p(d_planes_out), C.byref(avg), C.byref(it)))
+        return np.float32(avg.value), it.value
 
     def collage(self, argb: np.ndarray, info: np.ndarray, B: int, wk: int, rgb: bool):
         """fic_collage; `info` is rewritten in place (window-local -> codebook index, FC:273)."""
@@ -208,6 +250,88 @@ class Handle:
         s2 = np.empty((Cn, nd), np.int32)
         self._check(self._L.fic_build_pool(self._h, _ptr(a), int(rgb), W, H, B, _ptr(dec), _ptr(s1), _ptr(s2)))
         return dec, s1, s2
+
+
+class _BorrowedHandle(Handle):
+    """A per-device context owned by a MultiHandle (fic_multi_handle): never destroyed from here."""
+
+    def __init__(self, L, h, device):
+        self._L, self._h, self.device = L, h, int(device)
+
+    def close(self):
+        self._h = None
+
+    __del__ = close
+
+
+class MultiHandle:
+    """One libfic_b200 context over several GPUs of this process (fic_create_multi): the image is uploaded once,
+    broadcast with NCCL over NVLink, every device searches a slice of range rows and writes its codes straight into
+    the caller's arrays.  Results equal Handle.encode byte for byte."""
+
+    def __init__(self, devices):
+        self._L = _lib.load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        m = C.c_void_p()
+        rc = self._L.fic_create_multi(devs, len(devices), C.byref(m))
+        if rc:
+            raise FicError(rc, self._L.fic_multi_last_error(None).decode())
+        self._m = m
+        self.devices = [int(d) for d in devices]
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._L.fic_destroy_multi(self._m)
+            self._m = None
+
+    __del__ = close
+
+    def _check(self, rc: int):
+        if rc:
+            raise FicError(rc, self._L.fic_multi_last_error(self._m).decode())
+
+    def handle(self, rank: int = 0) -> Handle:
+        h = self._L.fic_multi_handle(self._m, int(rank))
+        if not h:
+            raise IndexError(rank)
+        return _BorrowedHandle(self._L, C.c_void_p(h), self.devices[rank])
+
+    def set_engine(self, engine: int):
+        self._check(self._L.fic_multi_set_option(self._m, _lib.FIC_OPT_ENGINE, int(engine)))
+
+    def set_umma_kind(self, kind: int):
+        self._check(self._L.fic_multi_set_option(self._m, _lib.FIC_OPT_UMMA_KIND, int(kind)))
+
+    def timings(self, rank: int = -1) -> Timings:
+        t = Timings()
+        self._check(self._L.fic_multi_get_timings(self._m, int(rank), C.byref(t)))
+        return t
+
+    def range_slice(self, rank: int):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._L.fic_multi_range_slice(self._m, int(rank), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def encode(self, pixels: np.ndarray, B: int, wk: int, rgb=False, info: np.ndarray | None = None,
+               q: np.ndarray | None = None):
+        """int32 ARGB [H, W] -> fic_multi_encode_grey / _rgb / _grey_iso (rgb = False / True / FIC_MODE_GREY_ISO);
+        uint8 [H, W] / [3, H, W] -> fic_multi_encode_grey_u8 / _rgb_planes."""
+        a = np.ascontiguousarray(pixels)
+        if a.dtype == np.uint8:
+            rgb = a.ndim == 3
+            fn = self._L.fic_multi_encode_rgb_planes if rgb else self._L.fic_multi_encode_grey_u8
+        else:
+            a = np.ascontiguousarray(a, dtype=np.int32)
+            fn = (self._L.fic_multi_encode_grey, self._L.fic_multi_encode_rgb, self._L.fic_multi_encode_grey_iso)[int(rgb)]
+        H, W = a.shape[-2:]
+        S = (3, 5, 4)[int(rgb)]
+        nr = (W // B) * (H // B) if B > 0 else 0
+        if info is None:
+            info = np.zeros((max(nr, 0), S), np.float32)
+        if q is None:
+            q = np.zeros((max(nr, 0), S), np.int32)
+        self._check(fn(self._m, _ptr(a), W, H, B, wk, _ptr(info), _ptr(q)))
+        return info, q
 
 
 # ---- .run stream helpers (native) ---------------------------------------------------

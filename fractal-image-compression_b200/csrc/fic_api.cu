@@ -80,6 +80,15 @@ static int set_err(fic_handle *h, int code, const char *fmt, ...)
             return set_err(h, FIC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Host entries copy from / to caller-owned buffers asynchronously and synchronise before they return.  This guard
+// makes that hold on EVERY return path: an early `return rc` after the first enqueue would otherwise leave a copy in
+// flight on a buffer the caller is free to reuse (pinned buffers are read by the copy engine directly).
+struct DrainOnExit {
+    cudaStream_t s;
+    explicit DrainOnExit(cudaStream_t st) : s(st) {}
+    ~DrainOnExit() { cudaStreamSynchronize(s); }
+};
+
 enum Slot { S_ARGB, S_SRC, S_DEC, S_DSUM, S_DSQ, S_RSUM, S_BEST, S_INFO, S_Q, S_OPA, S_OPB, S_IMG, S_DEC2, S_DCODE, S_PERR, S_ACC, S_DEC3 };
 
 template <typename T>
@@ -180,7 +189,7 @@ const char *fic_last_error(const fic_handle *h) { return h ? h->err : g_create_e
 int fic_set_option(fic_handle *h, int option, int value)
 {
     if (!h) return FIC_E_ARG;
-    if (option == FIC_OPT_ENGINE && value >= FIC_ENGINE_AUTO && value <= FIC_ENGINE_UMMA) {
+    if (option == FIC_OPT_ENGINE && value >= FIC_ENGINE_AUTO && value <= FIC_ENGINE_FUSED) {
         h->engine_opt = value;
         return FIC_OK;
     }
@@ -257,20 +266,52 @@ int fic_sync(fic_handle *h)
 // encode
 // ------------------------------------------------------------------------------------
 
-// Pool build + search + solve on device-resident planes.  Records events 1..4.
-static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, int64_t j0, int64_t j1,
-                            float *d_info, int32_t *d_q)
+// Which search engine a call runs (FIC_OPT_ENGINE): the tcgen05 search for whole-pool windows with enough work to
+// fill the GPU, else the fused one-launch encode for the reference's GUI windows (widthKernel <= 16), else the
+// multi-kernel direct path.
+static int pick_engine(fic_handle *h, const Geom &g, int64_t j0, int64_t j1, int *engine)
 {
-    Work &w = h->w;
-    cudaStream_t s = h->stream;
-    int engine = FIC_ENGINE_DIRECT;
+    *engine = FIC_ENGINE_DIRECT;
     if (h->engine_opt == FIC_ENGINE_UMMA) {
         if (!umma_applicable(g))
             return set_err(h, FIC_E_ARG, "tcgen05 search needs widthKernel == domain blocks per width == per height (and, for RGB, blockgroesse 4 or 8 without isometries)");
-        engine = FIC_ENGINE_UMMA;
-    } else if (h->engine_opt == FIC_ENGINE_AUTO && umma_applicable(g) && (j1 - j0) * g.ND >= (int64_t)1 << 22) {
-        engine = FIC_ENGINE_UMMA;
+        *engine = FIC_ENGINE_UMMA;
+    } else if (h->engine_opt == FIC_ENGINE_FUSED) {
+        if (!fused_encode_applicable(g)) return set_err(h, FIC_E_ARG, "the fused encode needs widthKernel <= 16 and no isometries");
+        *engine = FIC_ENGINE_FUSED;
+    } else if (h->engine_opt == FIC_ENGINE_AUTO) {
+        if (umma_applicable(g) && (j1 - j0) * g.ND >= (int64_t)1 << 22) *engine = FIC_ENGINE_UMMA;
+        else if (fused_encode_applicable(g)) *engine = FIC_ENGINE_FUSED;
     }
+    return FIC_OK;
+}
+
+// Fused windowed encode straight from the caller's pixels (ARGB ints or planes).  Records events 1..4.
+static int encode_fused_on_device(fic_handle *h, const Geom &g, const void *d_pixels, int is_argb, int64_t j0, int64_t j1,
+                                  float *d_info, int32_t *d_q)
+{
+    cudaStream_t s = h->stream;
+    CU(cudaEventRecord(h->ev[1], s));
+    CU(cudaEventRecord(h->ev[2], s));
+    CU(cudaEventRecord(h->ev[6], s));
+    const int launches = launch_encode_fused(d_pixels, is_argb, g, j0, j1, d_info, d_q, s);
+    CU(cudaEventRecord(h->ev[7], s));
+    CU(cudaEventRecord(h->ev[3], s));
+    CU(cudaEventRecord(h->ev[4], s));
+    CU(cudaGetLastError());
+    h->tm.engine = FIC_ENGINE_FUSED;
+    h->tm.launches += launches;
+    h->tm.search_evals = (double)(j1 - j0) * (double)g.wk * (double)g.wk;
+    return FIC_OK;
+}
+
+// Pool build + search + solve on device-resident planes.  Records events 1..4.
+static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, int64_t j0, int64_t j1,
+                            float *d_info, int32_t *d_q, int engine)
+{
+    Work &w = h->w;
+    cudaStream_t s = h->stream;
+    if (engine == FIC_ENGINE_FUSED) return encode_fused_on_device(h, g, d_src, 0, j0, j1, d_info, d_q);
     ENSURE(w.dec, S_DEC, (size_t)g.C * g.sw * g.sh);
     ENSURE(w.dsum, S_DSUM, sizeof(int32_t) * g.C * g.ND);
     ENSURE(w.dsq, S_DSQ, sizeof(int32_t) * g.C * g.ND);
@@ -282,6 +323,8 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
         // The first kind::f16 search of a handle verifies, once, that this device's f16 tensor path
         // accumulates the integer covariances exactly; a device that does not runs kind::i8 instead.
         // RGB has a kind::f16 tensor path only; without an exact f16 path it stays on the CUDA-core kernel.
+        // (The self-test allocates and synchronises on this stream: one-time cost of the first such call;
+        // fic_get_option(FIC_OPT_F16_EXACT) runs it ahead of time.)
         const bool rgb = g.C == 3;
         const bool wants_f16 = rgb || (g.B != 16 && (kind == FIC_UMMA_KIND_F16 || (kind == FIC_UMMA_KIND_AUTO && umma_default_kind(g) == FIC_UMMA_KIND_F16)));
         if (wants_f16 && h->f16_state == 0) {
@@ -307,6 +350,8 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     launches += launch_domain_stats(w.dec, w.dsum, w.dsq, g, s);
     launches += launch_range_stats(d_src, w.rsum, g, s);
     CU(cudaEventRecord(h->ev[2], s));
+    CU(cudaEventRecord(h->ev[6], s));  // (the tcgen05 launcher re-records 6 / 7 around its search kernel)
+    CU(cudaEventRecord(h->ev[7], s));
     if (engine == FIC_ENGINE_UMMA) {
         const char *why = nullptr;
         int n = launch_search_umma(call, g, j0, j1, h->num_sms, s, &why, kind, h->ev[6], h->ev[7]);
@@ -341,11 +386,13 @@ static void collect_timings(fic_handle *h, bool with_copies)
         h->tm.total_ms = ms;
 }
 
-static int encode_host(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, int B, int wk, int64_t j0,
+// `pixels` is the reference's int32 ARGB array (src_u8 == 0: FC:109 / FC:171 hand over RasterImage.argb) or 8-bit
+// planes (src_u8 == 1: grey W*H bytes = the red channel, RGB 3*W*H bytes R, G, B) -- a quarter of the upload.
+static int encode_host(fic_handle *h, int is_rgb, const void *pixels, int src_u8, int W, int H, int B, int wk, int64_t j0,
                        int64_t j1, float *info, int32_t *qcodes)
 {
     if (!h) return FIC_E_ARG;
-    if (!argb || (!info && !qcodes)) return set_err(h, FIC_E_ARG, "argb and at least one of info/qcodes must be non-NULL");
+    if (!pixels || (!info && !qcodes)) return set_err(h, FIC_E_ARG, "the image and at least one of info/qcodes must be non-NULL");
     Geom g;
     const char *why = "";
     int rc = make_geom(W, H, B, wk, is_rgb, &g, &why);
@@ -356,14 +403,23 @@ static int encode_host(fic_handle *h, int is_rgb, const int32_t *argb, int W, in
     Work &w = h->w;
     cudaStream_t s = h->stream;
     int S = code_stride(g);
-    ENSURE(w.argb, S_ARGB, sizeof(int32_t) * (size_t)W * H);
-    ENSURE(w.src, S_SRC, (size_t)g.C * W * H);
+    int engine;
+    if ((rc = pick_engine(h, g, j0, j1, &engine))) return rc;
+    const bool fused_argb = engine == FIC_ENGINE_FUSED && !src_u8;  // the fused kernel reads the ARGB ints itself
+    if (!src_u8) ENSURE(w.argb, S_ARGB, sizeof(int32_t) * (size_t)W * H);
+    if (!fused_argb) ENSURE(w.src, S_SRC, (size_t)g.C * W * H);
     ENSURE(w.info, S_INFO, sizeof(float) * g.NR * S);
     ENSURE(w.q, S_Q, sizeof(int32_t) * g.NR * S);
+    DrainOnExit drain(s);
     CU(cudaEventRecord(h->ev[0], s));
-    CU(cudaMemcpyAsync(w.argb, argb, sizeof(int32_t) * (size_t)W * H, cudaMemcpyHostToDevice, s));
-    h->tm.launches += launch_unpack(w.argb, w.src, W, H, g.C, s);
-    rc = encode_on_device(h, g, w.src, j0, j1, w.info, w.q);
+    if (src_u8) {
+        CU(cudaMemcpyAsync(w.src, pixels, (size_t)g.C * W * H, cudaMemcpyHostToDevice, s));
+    } else {
+        CU(cudaMemcpyAsync(w.argb, pixels, sizeof(int32_t) * (size_t)W * H, cudaMemcpyHostToDevice, s));
+        if (!fused_argb) h->tm.launches += launch_unpack(w.argb, w.src, W, H, g.C, s);
+    }
+    rc = fused_argb ? encode_fused_on_device(h, g, w.argb, 1, j0, j1, w.info, w.q)
+                    : encode_on_device(h, g, w.src, j0, j1, w.info, w.q, engine);
     if (rc) return rc;
     if (j1 > j0) {
         if (info) CU(cudaMemcpyAsync(info + j0 * S, w.info + j0 * S, sizeof(float) * (j1 - j0) * S, cudaMemcpyDeviceToHost, s));
@@ -380,19 +436,31 @@ extern "C" {
 int fic_encode_grey(fic_handle *h, const int32_t *argb, int W, int H, int B, int wk, int64_t range_begin,
                     int64_t range_end, float *info, int32_t *qcodes)
 {
-    return encode_host(h, 0, argb, W, H, B, wk, range_begin, range_end, info, qcodes);
+    return encode_host(h, 0, argb, 0, W, H, B, wk, range_begin, range_end, info, qcodes);
+}
+
+int fic_encode_grey_u8(fic_handle *h, const uint8_t *plane, int W, int H, int B, int wk, int64_t range_begin,
+                       int64_t range_end, float *info, int32_t *qcodes)
+{
+    return encode_host(h, FIC_MODE_GREY, plane, 1, W, H, B, wk, range_begin, range_end, info, qcodes);
+}
+
+int fic_encode_rgb_planes(fic_handle *h, const uint8_t *planes, int W, int H, int B, int wk, int64_t range_begin,
+                          int64_t range_end, float *info, int32_t *qcodes)
+{
+    return encode_host(h, FIC_MODE_RGB, planes, 1, W, H, B, wk, range_begin, range_end, info, qcodes);
 }
 
 int fic_encode_rgb(fic_handle *h, const int32_t *argb, int W, int H, int B, int wk, int64_t range_begin,
                    int64_t range_end, float *info, int32_t *qcodes)
 {
-    return encode_host(h, 1, argb, W, H, B, wk, range_begin, range_end, info, qcodes);
+    return encode_host(h, 1, argb, 0, W, H, B, wk, range_begin, range_end, info, qcodes);
 }
 
 int fic_encode_grey_iso(fic_handle *h, const int32_t *argb, int W, int H, int B, int wk, int64_t range_begin,
                         int64_t range_end, float *info, int32_t *qcodes)
 {
-    return encode_host(h, FIC_MODE_GREY_ISO, argb, W, H, B, wk, range_begin, range_end, info, qcodes);
+    return encode_host(h, FIC_MODE_GREY_ISO, argb, 0, W, H, B, wk, range_begin, range_end, info, qcodes);
 }
 
 int fic_encode_planes_dev(fic_handle *h, const uint8_t *d_planes, int is_rgb, int W, int H, int B, int wk,
@@ -409,7 +477,9 @@ int fic_encode_planes_dev(fic_handle *h, const uint8_t *d_planes, int is_rgb, in
     CU(cudaSetDevice(h->device));
     // Timings of the previous asynchronous call are final once its events completed.
     memset(&h->tm, 0, sizeof h->tm);
-    rc = encode_on_device(h, g, d_planes, range_begin, range_end, d_info, d_qcodes);
+    int engine;
+    if ((rc = pick_engine(h, g, range_begin, range_end, &engine))) return rc;
+    rc = encode_on_device(h, g, d_planes, range_begin, range_end, d_info, d_qcodes, engine);
     h->tm_pending_dev = rc == FIC_OK;
     return rc;
 }
@@ -472,6 +542,7 @@ int fic_build_pool(fic_handle *h, const int32_t *argb, int is_rgb, int W, int H,
     ENSURE(w.dec, S_DEC, (size_t)g.C * g.sw * g.sh);
     ENSURE(w.dsum, S_DSUM, sizeof(int32_t) * g.C * g.ND);
     ENSURE(w.dsq, S_DSQ, sizeof(int32_t) * g.C * g.ND);
+    DrainOnExit drain(s);
     CU(cudaMemcpyAsync(w.argb, argb, sizeof(int32_t) * (size_t)W * H, cudaMemcpyHostToDevice, s));
     launch_unpack(w.argb, w.src, W, H, g.C, s);
     launch_decimate(w.src, w.dec, g, s);
@@ -488,11 +559,24 @@ int fic_build_pool(fic_handle *h, const int32_t *argb, int is_rgb, int W, int H,
 // decode / collage
 // ------------------------------------------------------------------------------------
 
-int fic_decode(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int32_t *qcodes, int max_iters,
-               int32_t *argb_out, float *avg_error, int *iterations)
+// Decoder core.  Codes come from the host (`qcodes`) or from device memory (`d_qcodes`); the image goes to host ARGB
+// ints (the reference's RasterImage.argb), host 8-bit planes or device 8-bit planes -- exactly one of the three.
+//
+// avgError bookkeeping (FC:407-417).  The reference adds every squared pixel change to a binary32 running sum,
+// divides by W*H after the sweep and stops below 1.  The sum is an exact integer while it stays below 2^24, so with
+// W*H <= 2^24 the integer total S decides: S < 2^24 -> the float sum equals S; otherwise the float sum is
+// >= 2^24 >= W*H and the sweep did not converge (its value is then discarded, FC:416-417).  Such sweeps are folded
+// into the device-side state by the sweep kernel's last CTA.  Sweeps whose float sum may be both inexact and kept
+// (carry-in on the first sweep, the last allowed sweep, images above 2^24 pixels) also write the per-pixel squared
+// changes in loop order and are folded by k_sweep_finish, which replays the float accumulation where it must.
+// Sweeps are enqueued eight at a time without looking at the result: once the done flag is set the remaining ones
+// return immediately, and the host reads the state once per batch instead of once per sweep.
+static int decode_core(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int32_t *qcodes, const int32_t *d_qcodes,
+                       int max_iters, int32_t *argb_out, uint8_t *planes_out, uint8_t *d_planes_out, float *avg_error,
+                       int *iterations)
 {
     if (!h) return FIC_E_ARG;
-    if (!qcodes || !argb_out) return set_err(h, FIC_E_ARG, "qcodes and argb_out must be non-NULL");
+    if ((!qcodes && !d_qcodes) || (!argb_out && !planes_out && !d_planes_out)) return set_err(h, FIC_E_ARG, "codes and an output image must be non-NULL");
     if (max_iters < 1) return set_err(h, FIC_E_ARG, "max_iters must be >= 1");
     Geom g;
     const char *why = "";
@@ -504,75 +588,81 @@ int fic_decode(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int
     cudaStream_t s = h->stream;
     int S = code_stride(g);
     size_t plane = (size_t)W * H;
-    ENSURE(w.q, S_Q, sizeof(int32_t) * g.NR * S);
+    if (!d_qcodes) ENSURE(w.q, S_Q, sizeof(int32_t) * g.NR * S);
     ENSURE(w.dcode, S_DCODE, sizeof(float) * g.NR * (S + 1));
-    ENSURE(w.img, S_IMG, g.C * plane);
+    if (!d_planes_out) ENSURE(w.img, S_IMG, g.C * plane);
     ENSURE(w.dec, S_DEC, (size_t)g.C * g.sw * g.sh);
     ENSURE(w.dec2, S_DEC2, (size_t)g.C * g.sw * g.sh);
     ENSURE(w.acc, S_ACC, 64 * sizeof(unsigned long long));
-    ENSURE(w.argb, S_ARGB, sizeof(int32_t) * plane);
-    if (!w.avgf) CU(cudaMalloc((void **)&w.avgf, 256));
+    if (argb_out) ENSURE(w.argb, S_ARGB, sizeof(int32_t) * plane);
+    const bool big = (int64_t)W * H > ((int64_t)1 << 24);
+    const float carry = avg_error ? *avg_error : 0.0f;
+    const float fwh = (float)(W * H);  // FC:413 (float)(width*height)
+    ENSURE(w.perr, S_PERR, sizeof(int32_t) * plane);  // per-pixel squared changes of the sweeps that may need a replay
+    uint8_t *img = d_planes_out ? d_planes_out : w.img;
+    DrainOnExit drain(s);
     CU(cudaEventRecord(h->ev[0], s));
-    CU(cudaMemcpyAsync(w.q, qcodes, sizeof(int32_t) * g.NR * S, cudaMemcpyHostToDevice, s));
+    if (!d_qcodes) CU(cudaMemcpyAsync(w.q, qcodes, sizeof(int32_t) * g.NR * S, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(w.acc, 0, 64 * sizeof(unsigned long long), s));
     int launches = 0;
     int32_t *doff = (int32_t *)(w.dcode + g.NR * S);
-    launches += launch_dequant(w.q, w.dcode, doff, g, 0, nullptr, w.acc, s);
-    launches += launch_fill(w.img, g.C * plane, 128, s);  // FC:360, FC:1142-1148
-    launches += launch_decimate(w.img, w.dec, g, s);
-    CU(cudaMemcpyAsync(h->h_acc, w.acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (h->h_acc[1]) return set_err(h, FIC_E_STREAM, "a code indexes outside the domain pool (the reference would throw ArrayIndexOutOfBounds)");
-
-    // avgError bookkeeping (FC:407-417).  The reference adds every squared pixel change
-    // to a binary32 running sum, divides by W*H after the sweep and stops below 1.  The
-    // sum is an exact integer while it stays below 2^24, so with W*H <= 2^24 the integer
-    // total S decides: S < 2^24 -> the float sum equals S; otherwise the float sum is
-    // >= 2^24 >= W*H and the sweep did not converge (its value is then discarded,
-    // FC:416-417).  Sweeps whose float sum may be both inexact and kept (carry-in on the
-    // first sweep, the last allowed sweep, images above 2^24 pixels) replay the float
-    // accumulation in order on the device (k_serial_avg).
-    const bool big = (int64_t)W * H > ((int64_t)1 << 24);
-    float avg = avg_error ? *avg_error : 0.0f;
-    const float fwh = (float)(W * H);  // FC:413 (float)(width*height)
+    launches += launch_dequant(d_qcodes ? d_qcodes : w.q, w.dcode, doff, g, 0, nullptr, w.acc, s);
+    launches += launch_fill(img, g.C * plane, 128, s);  // FC:360, FC:1142-1148
+    launches += launch_decimate(img, w.dec, g, s);
     uint8_t *dcur = w.dec, *dnext = w.dec2;
-    int done = 0;
-    for (int it = 0; it < max_iters; it++) {
-        bool last = it == max_iters - 1;
-        bool serial = big || last || (it == 0 && avg != 0.0f);
-        if (serial) ENSURE(w.perr, S_PERR, sizeof(int32_t) * plane);
-        CU(cudaMemsetAsync(w.acc, 0, sizeof(unsigned long long), s));
-        launches += launch_decode_sweep(dcur, w.img, dnext, w.dcode, doff, g, w.acc, serial ? w.perr : nullptr, s);
-        float sum;
-        if (serial) {
-            CU(cudaMemcpyAsync(w.avgf, &avg, sizeof(float), cudaMemcpyHostToDevice, s));
-            launches += launch_serial_avg(w.perr, (int64_t)plane, w.avgf, s);
-            CU(cudaMemcpyAsync(h->h_acc + 8, w.avgf, sizeof(float), cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-            memcpy(&sum, h->h_acc + 8, sizeof(float));
-        } else {
-            CU(cudaMemcpyAsync(h->h_acc, w.acc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-            unsigned long long Ssum = h->h_acc[0];
-            sum = Ssum < (1ull << 24) ? (float)Ssum : 2.0f * fwh;
+    const uint32_t *hst = (const uint32_t *)h->h_acc;  // host copy of the state block as 32-bit words: [5..7] = done, iters, avg
+    int it = 0;
+    while (it < max_iters) {
+        const int batch_end = it + 8 < max_iters ? it + 8 : max_iters;
+        for (; it < batch_end; it++) {
+            const bool last = it == max_iters - 1;
+            const bool replay = big || last || (it == 0 && carry != 0.0f);
+            SweepCtl ctl = {w.acc, it, replay ? 0 : 1, fwh};
+            launches += launch_decode_sweep(dcur, img, dnext, w.dcode, doff, g, ctl, replay ? w.perr : nullptr, s);
+            if (replay) launches += launch_sweep_finish(w.perr, (int64_t)plane, w.acc, it, last, it == 0 ? carry : 0.0f, fwh, s);
+            uint8_t *t = dcur; dcur = dnext; dnext = t;
         }
-        done = it + 1;
-        avg = sum / fwh;       // FC:413
-        if (avg < 1) break;    // FC:414
-        if (!last) avg = 0;    // FC:416-417
-        uint8_t *t = dcur; dcur = dnext; dnext = t;
+        CU(cudaMemcpyAsync(h->h_acc, w.acc, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (h->h_acc[1]) return set_err(h, FIC_E_STREAM, "a code indexes outside the domain pool (the reference would throw ArrayIndexOutOfBounds)");
+        if (hst[5]) break;  // converged (FC:414)
     }
-    launches += launch_pack_argb(w.img, w.argb, W, H, g.C, s);
+    if (argb_out) {
+        launches += launch_pack_argb(img, w.argb, W, H, g.C, s);
+        CU(cudaMemcpyAsync(argb_out, w.argb, sizeof(int32_t) * plane, cudaMemcpyDeviceToHost, s));
+    } else if (planes_out) {
+        CU(cudaMemcpyAsync(planes_out, img, g.C * plane, cudaMemcpyDeviceToHost, s));
+    }
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(argb_out, w.argb, sizeof(int32_t) * plane, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(h->ev[5], s));
     CU(cudaStreamSynchronize(s));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]) == cudaSuccess) h->tm.total_ms = ms;
     h->tm.launches = launches;
+    float avg;
+    memcpy(&avg, &hst[7], sizeof avg);
     if (avg_error) *avg_error = avg;
-    if (iterations) *iterations = done;
+    if (iterations) *iterations = (int)hst[6];
     return FIC_OK;
+}
+
+int fic_decode(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int32_t *qcodes, int max_iters,
+               int32_t *argb_out, float *avg_error, int *iterations)
+{
+    return decode_core(h, is_rgb, W, H, B, wk, qcodes, nullptr, max_iters, argb_out, nullptr, nullptr, avg_error, iterations);
+}
+
+int fic_decode_u8(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int32_t *qcodes, int max_iters,
+                  uint8_t *planes_out, float *avg_error, int *iterations)
+{
+    return decode_core(h, is_rgb, W, H, B, wk, qcodes, nullptr, max_iters, nullptr, planes_out, nullptr, avg_error, iterations);
+}
+
+int fic_decode_planes_dev(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int32_t *d_qcodes, int max_iters,
+                          uint8_t *d_planes_out, float *avg_error, int *iterations)
+{
+    if (h && ((uintptr_t)d_planes_out & 15)) return set_err(h, FIC_E_ARG, "d_planes_out must be 16-byte aligned");
+    return decode_core(h, is_rgb, W, H, B, wk, nullptr, d_qcodes, max_iters, nullptr, nullptr, d_planes_out, avg_error, iterations);
 }
 
 int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, int B, int wk, float *info,
@@ -596,6 +686,7 @@ int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, in
     ENSURE(w.dcode, S_DCODE, sizeof(float) * g.NR * (S + 1));
     ENSURE(w.img, S_IMG, g.C * plane);
     ENSURE(w.acc, S_ACC, 64 * sizeof(unsigned long long));
+    DrainOnExit drain(s);
     CU(cudaMemcpyAsync(w.argb, argb, sizeof(int32_t) * plane, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(w.info, info, sizeof(float) * g.NR * S, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(w.acc, 0, 64 * sizeof(unsigned long long), s));
@@ -604,7 +695,7 @@ int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, in
     int32_t *doff = (int32_t *)(w.dcode + g.NR * S);
     launch_dequant(nullptr, w.dcode, doff, g, 1, w.info, w.acc, s);  // FC:273 calculateIndices
     launch_fill(w.img, g.C * plane, 0xa0, s);                  // RasterImage.java:19,31
-    launch_decode_sweep(w.dec, w.img, nullptr, w.dcode, doff, g, nullptr, nullptr, s);
+    launch_decode_sweep(w.dec, w.img, nullptr, w.dcode, doff, g, SweepCtl{nullptr, 0, 0, 0.0f}, nullptr, s);
     launch_pack_argb(w.img, w.argb, W, H, g.C, s);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h->h_acc, w.acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -614,6 +705,312 @@ int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, in
     if (h->h_acc[1]) return set_err(h, FIC_E_STREAM, "a code indexes outside the domain pool");
     return FIC_OK;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// multi-GPU handle: one process, n devices, one NCCL communicator
+// ------------------------------------------------------------------------------------
+//
+// Range blocks are independent (FC:125-159 carries no state but the output index): device r encodes a contiguous
+// slice of range rows.  Every device needs the whole image -- the domain pool spans it -- so the 8-bit plane(s) are
+// uploaded ONCE (to the first device) and broadcast over NVLink with ncclBroadcast; each device then builds the full
+// pool and searches its rows, and copies its code rows straight into the caller's arrays.  No other exchange exists
+// on this path (there is no compute step followed by a collective to fuse).
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2) so that the single-GPU library has no NCCL dependency; a multi
+// handle over more than one device fails with FIC_E_CUDA when it cannot be loaded.
+#include <dlfcn.h>
+
+namespace {
+
+typedef struct ncclComm *nccl_comm_t;
+struct NcclApi {
+    void *so = nullptr;
+    int (*CommInitAll)(nccl_comm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int /*ncclDataType_t*/, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load(char *err, size_t errlen)
+    {
+        if (so) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names)
+            if ((so = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (!so) {
+            snprintf(err, errlen, "cannot load NCCL (libnccl.so.2): %s", dlerror());
+            return false;
+        }
+        CommInitAll = (decltype(CommInitAll))dlsym(so, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(so, "ncclCommDestroy");
+        Broadcast = (decltype(Broadcast))dlsym(so, "ncclBroadcast");
+        GroupStart = (decltype(GroupStart))dlsym(so, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(so, "ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))dlsym(so, "ncclGetErrorString");
+        if (!CommInitAll || !CommDestroy || !Broadcast || !GroupStart || !GroupEnd || !GetErrorString) {
+            snprintf(err, errlen, "libnccl.so.2 lacks an expected symbol");
+            dlclose(so);
+            so = nullptr;
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclUint8 = 1;  // ncclUint8 (nccl.h ncclDataType_t)
+constexpr int kMaxDevices = 64;
+
+}  // namespace
+
+struct fic_multi {
+    int n = 0;
+    int devices[kMaxDevices];
+    fic_handle *h[kMaxDevices] = {nullptr};
+    nccl_comm_t comm[kMaxDevices] = {nullptr};
+    bool has_comm = false;
+    int64_t j0[kMaxDevices], j1[kMaxDevices];  // row slices of the last encode
+    fic_timings tm;
+    char err[512];
+};
+
+static char g_multi_err[512] = "";
+
+static int merr(fic_multi *m, int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(m ? m->err : g_multi_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// Contiguous split of the rph range rows over n devices, in range-block units (the first rph % n devices get one
+// row more) -- the same split as dist.py's partition_range_rows.
+static void split_rows(int rph, int rpw, int n, int64_t *j0, int64_t *j1)
+{
+    const int base = rph / n, extra = rph % n;
+    int row = 0;
+    for (int r = 0; r < n; r++) {
+        const int rows = base + (r < extra ? 1 : 0);
+        j0[r] = (int64_t)row * rpw;
+        j1[r] = (int64_t)(row + rows) * rpw;
+        row += rows;
+    }
+}
+
+// `pixels`: the reference's ARGB ints (src_u8 == 0) or 8-bit planes (src_u8 == 1), host memory.
+static int multi_encode(fic_multi *m, int mode, const void *pixels, int src_u8, int W, int H, int B, int wk, float *info,
+                        int32_t *qcodes)
+{
+    if (!m) return FIC_E_ARG;
+    if (!pixels || (!info && !qcodes)) return merr(m, FIC_E_ARG, "the image and at least one of info/qcodes must be non-NULL");
+    Geom g;
+    const char *why = "";
+    int rc = make_geom(W, H, B, wk, mode, &g, &why);
+    if (rc) return merr(m, rc, "%s", why);
+    const int S = code_stride(g);
+    const size_t plane_bytes = (size_t)g.C * W * H;
+    split_rows(g.rph, g.rpw, m->n, m->j0, m->j1);
+    cudaError_t ce;
+#define MCU(call)                                                                                     \
+    do {                                                                                              \
+        if ((ce = (call)) != cudaSuccess) {                                                           \
+            for (int r_ = 0; r_ < m->n; r_++) { cudaSetDevice(m->devices[r_]); cudaStreamSynchronize(m->h[r_]->stream); } \
+            return merr(m, FIC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(ce), __FILE__, __LINE__); \
+        }                                                                                             \
+    } while (0)
+    // workspaces
+    for (int r = 0; r < m->n; r++) {
+        fic_handle *h = m->h[r];
+        MCU(cudaSetDevice(m->devices[r]));
+        memset(&h->tm, 0, sizeof h->tm);
+        if (r == 0 && !src_u8 && (rc = ensure(h, h->w.argb, S_ARGB, sizeof(int32_t) * (size_t)W * H))) return merr(m, rc, "%s", h->err);
+        if ((rc = ensure(h, h->w.src, S_SRC, plane_bytes)) || (rc = ensure(h, h->w.info, S_INFO, sizeof(float) * g.NR * S)) ||
+            (rc = ensure(h, h->w.q, S_Q, sizeof(int32_t) * g.NR * S)))
+            return merr(m, rc, "%s", h->err);
+    }
+    // one upload, to the first device
+    fic_handle *h0 = m->h[0];
+    MCU(cudaSetDevice(m->devices[0]));
+    MCU(cudaEventRecord(h0->ev[0], h0->stream));
+    if (src_u8) {
+        MCU(cudaMemcpyAsync(h0->w.src, pixels, plane_bytes, cudaMemcpyHostToDevice, h0->stream));
+    } else {
+        MCU(cudaMemcpyAsync(h0->w.argb, pixels, sizeof(int32_t) * (size_t)W * H, cudaMemcpyHostToDevice, h0->stream));
+        h0->tm.launches += launch_unpack(h0->w.argb, h0->w.src, W, H, g.C, h0->stream);
+    }
+    // one broadcast of the planes over NVLink (every device's stream orders its own part)
+    if (m->n > 1) {
+        int nrc = g_nccl.GroupStart();
+        for (int r = 0; r < m->n && nrc == 0; r++) {
+            MCU(cudaSetDevice(m->devices[r]));
+            nrc = g_nccl.Broadcast(h0->w.src, m->h[r]->w.src, plane_bytes, kNcclUint8, 0, m->comm[r], m->h[r]->stream);
+        }
+        const int nrc2 = g_nccl.GroupEnd();
+        if (nrc == 0) nrc = nrc2;
+        if (nrc) {
+            for (int r = 0; r < m->n; r++) { cudaSetDevice(m->devices[r]); cudaStreamSynchronize(m->h[r]->stream); }
+            return merr(m, FIC_E_CUDA, "ncclBroadcast failed: %s", g_nccl.GetErrorString(nrc));
+        }
+    }
+    // every device: full pool, its own range rows, codes straight into the caller's arrays
+    for (int r = 0; r < m->n; r++) {
+        fic_handle *h = m->h[r];
+        MCU(cudaSetDevice(m->devices[r]));
+        int engine;
+        rc = pick_engine(h, g, m->j0[r], m->j1[r], &engine);
+        if (!rc) rc = encode_on_device(h, g, h->w.src, m->j0[r], m->j1[r], h->w.info, h->w.q, engine);
+        if (rc) {
+            for (int q = 0; q < m->n; q++) { cudaSetDevice(m->devices[q]); cudaStreamSynchronize(m->h[q]->stream); }
+            return merr(m, rc, "device %d: %s", m->devices[r], h->err);
+        }
+        const int64_t a = m->j0[r], b = m->j1[r];
+        if (b > a) {
+            if (info) MCU(cudaMemcpyAsync(info + a * S, h->w.info + a * S, sizeof(float) * (b - a) * S, cudaMemcpyDeviceToHost, h->stream));
+            if (qcodes) MCU(cudaMemcpyAsync(qcodes + a * S, h->w.q + a * S, sizeof(int32_t) * (b - a) * S, cudaMemcpyDeviceToHost, h->stream));
+        }
+        MCU(cudaEventRecord(h->ev[5], h->stream));
+    }
+    memset(&m->tm, 0, sizeof m->tm);
+    for (int r = 0; r < m->n; r++) {
+        fic_handle *h = m->h[r];
+        MCU(cudaSetDevice(m->devices[r]));
+        MCU(cudaStreamSynchronize(h->stream));
+        collect_timings(h, r == 0);
+        if (r != 0) {  // ev[0] is recorded on the first device only: this device's time runs from its pool build
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[5]) == cudaSuccess) h->tm.total_ms = ms;
+            if (cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]) == cudaSuccess) h->tm.d2h_ms = ms;
+        }
+        // the handle's view of the call: the slowest device per stage
+        const fic_timings &t = h->tm;
+        m->tm.h2d_ms = fmaxf(m->tm.h2d_ms, t.h2d_ms);
+        m->tm.pool_ms = fmaxf(m->tm.pool_ms, t.pool_ms);
+        m->tm.search_ms = fmaxf(m->tm.search_ms, t.search_ms);
+        m->tm.kernel_ms = fmaxf(m->tm.kernel_ms, t.kernel_ms);
+        m->tm.solve_ms = fmaxf(m->tm.solve_ms, t.solve_ms);
+        m->tm.d2h_ms = fmaxf(m->tm.d2h_ms, t.d2h_ms);
+        m->tm.total_ms = fmaxf(m->tm.total_ms, t.total_ms);
+        m->tm.engine = t.engine;
+        m->tm.launches += t.launches;
+        m->tm.search_evals += t.search_evals;
+    }
+#undef MCU
+    return FIC_OK;
+}
+
+extern "C" {
+
+int fic_create_multi(const int *devices, int n_devices, fic_multi **out)
+{
+    if (!out) return merr(nullptr, FIC_E_ARG, "fic_create_multi: out is NULL");
+    *out = nullptr;
+    if (!devices || n_devices < 1 || n_devices > kMaxDevices) return merr(nullptr, FIC_E_ARG, "fic_create_multi: need 1..%d devices", kMaxDevices);
+    for (int a = 0; a < n_devices; a++)
+        for (int b = a + 1; b < n_devices; b++)
+            if (devices[a] == devices[b]) return merr(nullptr, FIC_E_ARG, "fic_create_multi: device %d listed twice", devices[a]);
+    fic_multi *m = new (std::nothrow) fic_multi();
+    if (!m) return merr(nullptr, FIC_E_NOMEM, "out of host memory");
+    m->err[0] = 0;
+    memset(&m->tm, 0, sizeof m->tm);
+    m->n = n_devices;
+    for (int r = 0; r < n_devices; r++) {
+        m->devices[r] = devices[r];
+        int rc = fic_create(devices[r], &m->h[r]);
+        if (rc) {
+            merr(nullptr, rc, "device %d: %s", devices[r], fic_last_error(nullptr));
+            fic_destroy_multi(m);
+            return rc;
+        }
+    }
+    if (n_devices > 1) {
+        if (!g_nccl.load(g_multi_err, sizeof g_multi_err)) {
+            fic_destroy_multi(m);
+            return FIC_E_CUDA;
+        }
+        int nrc = g_nccl.CommInitAll(m->comm, n_devices, m->devices);
+        if (nrc) {
+            merr(nullptr, FIC_E_CUDA, "ncclCommInitAll over %d devices failed: %s", n_devices, g_nccl.GetErrorString(nrc));
+            fic_destroy_multi(m);
+            return FIC_E_CUDA;
+        }
+        m->has_comm = true;
+    }
+    *out = m;
+    return FIC_OK;
+}
+
+void fic_destroy_multi(fic_multi *m)
+{
+    if (!m) return;
+    for (int r = 0; r < m->n; r++) {
+        if (m->h[r]) {
+            cudaSetDevice(m->devices[r]);
+            cudaStreamSynchronize(m->h[r]->stream);
+        }
+    }
+    if (m->has_comm)
+        for (int r = 0; r < m->n; r++)
+            if (m->comm[r]) g_nccl.CommDestroy(m->comm[r]);
+    for (int r = 0; r < m->n; r++) fic_destroy(m->h[r]);
+    delete m;
+}
+
+const char *fic_multi_last_error(const fic_multi *m) { return m ? m->err : g_multi_err; }
+int fic_multi_device_count(const fic_multi *m) { return m ? m->n : 0; }
+fic_handle *fic_multi_handle(fic_multi *m, int rank) { return (m && rank >= 0 && rank < m->n) ? m->h[rank] : nullptr; }
+
+int fic_multi_set_option(fic_multi *m, int option, int value)
+{
+    if (!m) return FIC_E_ARG;
+    for (int r = 0; r < m->n; r++) {
+        int rc = fic_set_option(m->h[r], option, value);
+        if (rc) return merr(m, rc, "%s", m->h[r]->err);
+    }
+    return FIC_OK;
+}
+
+int fic_multi_get_timings(const fic_multi *m, int rank, fic_timings *out)
+{
+    if (!m || !out || rank >= m->n) return FIC_E_ARG;
+    *out = rank < 0 ? m->tm : m->h[rank]->tm;
+    return FIC_OK;
+}
+
+int fic_multi_range_slice(const fic_multi *m, int rank, int64_t *range_begin, int64_t *range_end)
+{
+    if (!m || rank < 0 || rank >= m->n) return FIC_E_ARG;
+    if (range_begin) *range_begin = m->j0[rank];
+    if (range_end) *range_end = m->j1[rank];
+    return FIC_OK;
+}
+
+int fic_multi_encode_grey(fic_multi *m, const int32_t *argb, int W, int H, int B, int wk, float *info, int32_t *qcodes)
+{
+    return multi_encode(m, FIC_MODE_GREY, argb, 0, W, H, B, wk, info, qcodes);
+}
+int fic_multi_encode_rgb(fic_multi *m, const int32_t *argb, int W, int H, int B, int wk, float *info, int32_t *qcodes)
+{
+    return multi_encode(m, FIC_MODE_RGB, argb, 0, W, H, B, wk, info, qcodes);
+}
+int fic_multi_encode_grey_iso(fic_multi *m, const int32_t *argb, int W, int H, int B, int wk, float *info, int32_t *qcodes)
+{
+    return multi_encode(m, FIC_MODE_GREY_ISO, argb, 0, W, H, B, wk, info, qcodes);
+}
+int fic_multi_encode_grey_u8(fic_multi *m, const uint8_t *plane, int W, int H, int B, int wk, float *info, int32_t *qcodes)
+{
+    return multi_encode(m, FIC_MODE_GREY, plane, 1, W, H, B, wk, info, qcodes);
+}
+int fic_multi_encode_rgb_planes(fic_multi *m, const uint8_t *planes, int W, int H, int B, int wk, float *info, int32_t *qcodes)
+{
+    return multi_encode(m, FIC_MODE_RGB, planes, 1, W, H, B, wk, info, qcodes);
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ------------------------------------------------------------------------------------
 // .run stream helpers (host only; DataOutputStream.writeInt is big endian)

@@ -62,6 +62,11 @@ int launch_domain_stats(const uint8_t *d_dec, int32_t *d_dsum, int32_t *d_dsq, c
 int launch_range_stats(const uint8_t *d_src, int32_t *d_rsum, const Geom &g, cudaStream_t s);
 int launch_sum_planes(const uint8_t *d_dec, uint16_t *d_dec3, const Geom &g, cudaStream_t s);  // RGB only
 int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, cudaStream_t s);
+// Fused windowed encode (widthKernel <= 16, no isometries): decimation, stats, search, solve and quantisation in one
+// launch, straight from the caller's pixels (ARGB ints or 8-bit planes); no intermediate arrays.
+bool fused_encode_applicable(const Geom &g);
+int launch_encode_fused(const void *d_src, int src_is_argb, const Geom &g, int64_t j0, int64_t j1, float *d_info,
+                        int32_t *d_q, cudaStream_t s);
 int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_info, int32_t *d_q,
                  cudaStream_t s);
 
@@ -91,9 +96,21 @@ int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j
 int launch_dequant(const int32_t *d_q, float *d_code, int32_t *d_off, const Geom &g, int unquantised,
                    const float *d_info, unsigned long long *d_acc, cudaStream_t s);
 int launch_fill(uint8_t *d_planes, size_t bytes, int value, cudaStream_t s);
+// Control block of one decoder sweep.  st == nullptr: a plain sweep (the one-shot collage).  Otherwise st points at
+// the decoder state (fic_kernels.cu, "Decoder state block"): the sweep returns at once when the done flag is set,
+// adds its squared pixel changes to st[0] and, with finish != 0, its last CTA folds the sweep into the state
+// (avgError, iteration count, done flag; FC:413-417) so that the host need not look at every sweep.
+struct SweepCtl {
+    unsigned long long *st;
+    int it;      // sweep index (FC:381 counter)
+    int finish;  // 1: fold inside the sweep kernel -- only when the float sum needs no replay (see k_sweep_finish)
+    float fwh;   // (float)(W*H), FC:413
+};
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out,
                         const float *d_code, const int32_t *d_off, const Geom &g,
-                        unsigned long long *d_acc, int32_t *d_perr, cudaStream_t s);
-int launch_serial_avg(const int32_t *d_perr, int64_t count, float *d_avg_inout, cudaStream_t s);
+                        const SweepCtl &ctl, int32_t *d_perr, cudaStream_t s);
+// folds a sweep whose float running sum may have to be replayed in loop order (see k_sweep_finish)
+int launch_sweep_finish(const int32_t *d_perr, int64_t count, unsigned long long *d_state, int it, int last,
+                        float carry, float fwh, cudaStream_t s);
 
 }  // namespace fic

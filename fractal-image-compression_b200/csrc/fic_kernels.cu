@@ -513,6 +513,232 @@ int launch_search_direct(const Work &w, const Geom &g, int64_t j0, int64_t j1, c
     return launches;
 }
 
+
+// ------------------------------------------------------------------------------------
+// K2f: fused windowed encode -- the reference's default configuration in ONE launch.
+//
+// For the windows the reference's GUI offers (widthKernel <= 16, RLEAppView.fxml:104) the whole chain
+// scaleImage -> createCodebuch -> Domainblock stats -> window search -> solve -> quantise (FC:119-159 /
+// FC:181-215) fits one CTA per range block: the CTA decimates the (wk-1)*B/4 + B pixel square of the source that
+// its window covers into shared memory (a few KB; neighbouring ranges redo the overlap, which is cheaper than four
+// more launches and three intermediate arrays), takes the range block's mean, scores the wk*wk candidates straight
+// from shared memory with the same integer sums and the same float/double expression as the other paths, reduces
+// to the lexicographic (error, index) minimum and lets thread 0 solve and quantise the winner.  Pixels come from the
+// caller's ARGB ints (no unpack pass) or from 8-bit planes.  256^2, B = 8, wk = 2: 1024 CTAs, a few microseconds.
+// ------------------------------------------------------------------------------------
+template <int C, bool ARGB>
+__device__ __forceinline__ void fused_px(const void *__restrict__ src, int64_t plane, int64_t o, int v[C])
+{
+    if (ARGB) {
+        const uint32_t p = (uint32_t)__ldg((const int32_t *)src + o);
+        v[0] = (p >> 16) & 0xff;  // grey: the red channel (FC:596, FC:977)
+        if (C == 3) { v[1] = (p >> 8) & 0xff; v[C - 1] = p & 0xff; }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; c++) v[c] = __ldg((const uint8_t *)src + c * plane + o);
+    }
+}
+
+template <int B, int C, bool ARGB>
+__global__ void __launch_bounds__(kDirectThreads)
+k_encode_fused(const void *__restrict__ src, float *__restrict__ info, int32_t *__restrict__ q, Geom g, int64_t j0)
+{
+    constexpr int n = B * B, step = B / 4;
+    extern __shared__ __align__(16) uint8_t s_tile[];  // C planes of TW x TW decimated pixels
+    __shared__ int s_r[C][n];                          // the range block, per channel
+    __shared__ float s_gR[C == 3 ? n : 1];             // RGB: sum over the channels of (r - rmean_c), FC:785-786
+    __shared__ int s_sum[C][kDirectThreads / 32];
+    __shared__ float s_err[kDirectThreads / 32];
+    __shared__ int s_c[kDirectThreads / 32];
+    const int64_t j = j0 + blockIdx.x;
+    const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
+    const int64_t plane = (int64_t)g.W * g.H;
+    int dy, dx;
+    range_window(g, j, &dy, &dx);
+    const int TW = (g.wk - 1) * step + B;
+    // ---- the window's decimated pixels (FC:970-1007 / FC:901-962, tap quirks as k_decimate)
+    for (int t = threadIdx.x; t < TW * TW; t += kDirectThreads) {
+        const int ty = t / TW, tx = t - ty * TW;
+        const int x = 2 * (dx * step + tx), y = 2 * (dy * step + ty);
+        int p00[C], p10[C], p01[C], p11[C];
+        const int64_t o = (int64_t)y * g.W + x;
+        fused_px<C, ARGB>(src, plane, o, p00);
+        fused_px<C, ARGB>(src, plane, o + 1, p10);
+        fused_px<C, ARGB>(src, plane, o + g.W, p01);
+        fused_px<C, ARGB>(src, plane, o + g.W + 1, p11);
+#pragma unroll
+        for (int c = 0; c < C; c++) s_tile[c * TW * TW + t] = (uint8_t)dec_tap4(p00[c], p10[c], p01[c], p11[c], x, g.H, C == 3);
+    }
+    // ---- the range block and its integer means (FC:588-602, FC:67-73)
+    int part[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) part[c] = 0;
+    for (int t = threadIdx.x; t < n; t += kDirectThreads) {
+        int v[C];
+        fused_px<C, ARGB>(src, plane, (int64_t)(yr * B + t / B) * g.W + xr * B + t % B, v);
+#pragma unroll
+        for (int c = 0; c < C; c++) { s_r[c][t] = v[c]; part[c] += v[c]; }
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        for (int o = 16; o > 0; o >>= 1) part[c] += __shfl_xor_sync(0xffffffffu, part[c], o);
+        if ((threadIdx.x & 31) == 0) s_sum[c][threadIdx.x >> 5] = part[c];
+    }
+    __syncthreads();
+    int rm[C], vR = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        int rs = 0;
+        for (int w = 0; w < kDirectThreads / 32; w++) rs += s_sum[c][w];
+        rm[c] = rs / n;          // FC:72
+        vR += rs - n * rm[c];    // sum (r - rmean), FC:671 / FC:790
+    }
+    if (C == 3) {
+        for (int t = threadIdx.x; t < n; t += kDirectThreads)
+            s_gR[t] = (float)((s_r[0][t] - rm[0]) + (s_r[C == 3 ? 1 : 0][t] - rm[C == 3 ? 1 : 0]) + (s_r[C - 1][t] - rm[C - 1]));
+        __syncthreads();
+    }
+    // ---- candidates in ascending order per thread, strict < (FC:619-632 / FC:702-713)
+    float best_err = 10000000.0f;  // FC:615 / FC:698
+    int best_c = 0;
+    const int ncand = g.wk * g.wk;
+    for (int c = threadIdx.x; c < ncand; c += kDirectThreads) {
+        const int ky = c / g.wk, kx = c - ky * g.wk;
+        const uint8_t *p = s_tile + (ky * step) * TW + kx * step;
+        float err;
+        if (C == 1) {
+            int ds = 0, dsq = 0, dot = 0;
+            for (int ry = 0; ry < B; ry++)
+#pragma unroll
+                for (int rx = 0; rx < B; rx++) {
+                    const int d = p[ry * TW + rx];
+                    ds += d;
+                    dsq += d * d;
+                    dot += s_r[0][ry * B + rx] * d;
+                }
+            int dmean;
+            const int varD = dom_var(ds, dsq, n, &dmean);
+            const int kov = dot - rm[0] * ds - dmean * vR;  // sum (r - rmean)(d - dmean)
+            err = grey_error(kov, vR, __dsqrt_rn((double)varD));
+        } else {
+            int dmsum = 0, vDi = 0;
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) {
+                int ds = 0;
+                for (int ry = 0; ry < B; ry++)
+#pragma unroll
+                    for (int rx = 0; rx < B; rx++) ds += p[ch * TW * TW + ry * TW + rx];
+                dmsum += ds / n;
+                vDi += ds - n * (ds / n);
+            }
+            float kov = 0.0f;  // FC:775: sequential binary32 accumulation in pixel order (see rgb_score)
+            for (int ry = 0; ry < B; ry++)
+#pragma unroll
+                for (int rx = 0; rx < B; rx++) {
+                    const int o = ry * TW + rx;
+                    const float gD = (float)((int)p[o] + (int)p[(C == 3 ? 1 : 0) * TW * TW + o] + (int)p[(C - 1) * TW * TW + o] - dmsum);
+                    kov = __fmaf_rn(s_gR[ry * B + rx], gD, kov);
+                }
+            const float fvR = (float)vR, vD = (float)vDi;
+            float r = 0.0f;
+            if (!(fvR == 0.0f || vD == 0.0f)) r = __fdiv_rn(kov, __fmul_rn(fvR, vD));  // FC:797-800
+            r = __fmul_rn(r, r);
+            err = __fmul_rn(__fmul_rn(fvR, fvR), __fsub_rn(1.0f, r));  // FC:803
+        }
+        if (err < best_err) { best_err = err; best_c = c; }  // FC:627 / FC:710
+    }
+    block_argmin(best_err, best_c, s_err, s_c);
+    if (threadIdx.x != 0) return;
+    // ---- solve + quantise the winner (FC:634-643 / FC:718-733; FC:242-244 / FC:250-254)
+    const int c = best_c;
+    const int ky = c / g.wk, kx = c - ky * g.wk;
+    const uint8_t *p = s_tile + (ky * step) * TW + kx * step;
+    const float fc = (float)c;
+    if (C == 1) {
+        int ds = 0, dsq = 0, dot = 0;
+        for (int ry = 0; ry < B; ry++)
+            for (int rx = 0; rx < B; rx++) {
+                const int d = p[ry * TW + rx];
+                ds += d;
+                dsq += d * d;
+                dot += (s_r[0][ry * B + rx] - rm[0]) * d;
+            }
+        int dmean;
+        const int varD = dom_var(ds, dsq, n, &dmean);
+        const int kov = dot - dmean * vR;
+        float a = __fdiv_rn((float)kov, (float)varD);  // FC:634 (0/0 -> NaN on flat winners)
+        if (a < -1.0f) a = -1.0f;                      // FC:636-639 (NaN passes through)
+        else if (a > 1.0f) a = 1.0f;
+        const float b = __fsub_rn((float)rm[0], __fmul_rn(a, (float)dmean));  // FC:641
+        if (info) { info[3 * j] = fc; info[3 * j + 1] = a; info[3 * j + 2] = b; }
+        if (q) { q[3 * j] = j_f2i(fc); q[3 * j + 1] = j_f2i(__fmul_rn(a, 100.0f)); q[3 * j + 2] = j_f2i(b); }
+    } else {
+        int dm[C], dv[C], dmsum = 0;
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) {
+            int ds = 0, dsq = 0;
+            for (int ry = 0; ry < B; ry++)
+                for (int rx = 0; rx < B; rx++) {
+                    const int d = p[ch * TW * TW + ry * TW + rx];
+                    ds += d;
+                    dsq += d * d;
+                }
+            dv[ch] = dom_var(ds, dsq, n, &dm[ch]);
+            dmsum += dm[ch];
+        }
+        float kov = 0.0f;
+        for (int ry = 0; ry < B; ry++)
+            for (int rx = 0; rx < B; rx++) {
+                const int o = ry * TW + rx;
+                const float gD = (float)((int)p[o] + (int)p[(C == 3 ? 1 : 0) * TW * TW + o] + (int)p[(C - 1) * TW * TW + o] - dmsum);
+                kov = __fmaf_rn(s_gR[ry * B + rx], gD, kov);
+            }
+        // FC:776: varianzSquare = varianceR + varianceG + mittelWertB (sic)
+        const float varSq = __fadd_rn(__fadd_rn((float)dv[0], (float)dv[C == 3 ? 1 : 0]), (float)dm[C - 1]);
+        float a = __fdiv_rn(kov, varSq);  // FC:718
+        if (a > 1.0f) a = 1.0f;           // FC:721-724
+        if (a < -1.0f) a = -1.0f;
+        const float bR = __fsub_rn((float)rm[0], __fmul_rn(a, (float)dm[0]));  // FC:727-731
+        const float bG = __fsub_rn((float)rm[C == 3 ? 1 : 0], __fmul_rn(a, (float)dm[C == 3 ? 1 : 0]));
+        const float bB = __fsub_rn((float)rm[C - 1], __fmul_rn(a, (float)dm[C - 1]));
+        if (info) { info[5 * j] = fc; info[5 * j + 1] = a; info[5 * j + 2] = bR; info[5 * j + 3] = bG; info[5 * j + 4] = bB; }
+        if (q) {
+            q[5 * j] = j_f2i(fc);
+            q[5 * j + 1] = j_f2i(__fmul_rn(a, 1000000.0f));
+            q[5 * j + 2] = j_f2i(__fmul_rn(bR, 100000.0f));
+            q[5 * j + 3] = j_f2i(__fmul_rn(bG, 100000.0f));
+            q[5 * j + 4] = j_f2i(bB);
+        }
+    }
+}
+
+bool fused_encode_applicable(const Geom &g) { return g.wk <= 16 && g.n_iso == 1; }
+
+template <int C, bool ARGB>
+static int launch_fused_t(const void *d_src, const Geom &g, int64_t j0, int64_t j1, float *d_info, int32_t *d_q, cudaStream_t s)
+{
+    const int step = g.B / 4, TW = (g.wk - 1) * step + g.B;
+    const size_t smem = (size_t)C * TW * TW;  // <= 3 * 76 * 76 = 17 KB
+    int launches = 0;
+    for (int64_t at = j0; at < j1;) {
+        const unsigned chunk = (unsigned)(j1 - at < (1 << 30) ? j1 - at : (1 << 30));
+        if (g.B == 4) k_encode_fused<4, C, ARGB><<<chunk, kDirectThreads, smem, s>>>(d_src, d_info, d_q, g, at);
+        else if (g.B == 8) k_encode_fused<8, C, ARGB><<<chunk, kDirectThreads, smem, s>>>(d_src, d_info, d_q, g, at);
+        else k_encode_fused<16, C, ARGB><<<chunk, kDirectThreads, smem, s>>>(d_src, d_info, d_q, g, at);
+        at += chunk;
+        launches++;
+    }
+    return launches;
+}
+
+int launch_encode_fused(const void *d_src, int src_is_argb, const Geom &g, int64_t j0, int64_t j1, float *d_info, int32_t *d_q,
+                        cudaStream_t s)
+{
+    if (j1 <= j0) return 0;
+    if (g.C == 1) return src_is_argb ? launch_fused_t<1, true>(d_src, g, j0, j1, d_info, d_q, s) : launch_fused_t<1, false>(d_src, g, j0, j1, d_info, d_q, s);
+    return src_is_argb ? launch_fused_t<3, true>(d_src, g, j0, j1, d_info, d_q, s) : launch_fused_t<3, false>(d_src, g, j0, j1, d_info, d_q, s);
+}
+
 // ------------------------------------------------------------------------------------
 // K3s: code solve + quantisation for the winning candidate (FC:634-643 grey,
 // FC:718-733 RGB; quantisation FC:242-244 / FC:250-254).  One thread per range block.
@@ -707,6 +933,56 @@ int launch_fill(uint8_t *d_planes, size_t bytes, int value, cudaStream_t s)
     return 1;
 }
 
+// Decoder state block (device memory, 8 x u64; fic_api.cu owns it): [0] sum of squared pixel changes of the running
+// sweep, [1] "a code indexes outside the pool", then as 32-bit words from [2]: ticket counter of the running sweep,
+// done flag, sweeps executed, avgError bits.
+enum { ST_TICKET = 4, ST_DONE = 5, ST_ITERS = 6, ST_AVG = 7 };  // indices into (uint32_t *)st
+
+// Sweeps are enqueued ahead of the host's knowledge of convergence (FC:414): once the done flag is set every later
+// sweep returns at once, so the image stays the converged one.
+__device__ __forceinline__ bool sweep_done(const SweepCtl &ctl)
+{
+    return ctl.st && ((volatile const uint32_t *)ctl.st)[ST_DONE] != 0;
+}
+
+// Folds a finished sweep whose float running sum needs no replay into the state: avgError = S / (W*H) with the exact
+// integer S when S < 2^24 (every float partial sum is then exact); S >= 2^24 >= W*H means "not converged" and the
+// value is discarded (FC:416-417).  fic_api.cu only asks for this (ctl.finish) on sweeps where that argument holds.
+__device__ __forceinline__ void sweep_fold(unsigned long long *st, unsigned long long S, int it, float fwh)
+{
+    uint32_t *w = (uint32_t *)st;
+    const float sum = S < (1ull << 24) ? (float)S : 2.0f * fwh;
+    const float avg = __fdiv_rn(sum, fwh);  // FC:413
+    w[ST_ITERS] = (uint32_t)(it + 1);
+    if (avg < 1.0f) {  // FC:414
+        w[ST_AVG] = __float_as_uint(avg);
+        w[ST_DONE] = 1u;
+    } else {
+        w[ST_AVG] = 0u;  // FC:416-417 (never the last sweep here)
+    }
+}
+
+// Common tail of the sweep kernels: add the CTA's squared changes to st[0]; with ctl.finish the last CTA to get
+// here folds the sweep (no separate kernel, no host round trip per sweep).
+__device__ __forceinline__ void sweep_tail(const SweepCtl &ctl, unsigned long long local)
+{
+    if (!ctl.st) return;
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(ctl.st, local);
+    if (!ctl.finish) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        uint32_t *w = (uint32_t *)ctl.st;
+        if (atomicAdd(w + ST_TICKET, 1u) == gridDim.x - 1) {
+            __threadfence();
+            const unsigned long long S = atomicExch(ctl.st, 0ull);
+            w[ST_TICKET] = 0u;
+            sweep_fold(ctl.st, S, ctl.it, ctl.fwh);
+        }
+    }
+}
+
 // One Jacobi sweep of FC:386-412 / FC:463-499.  The reference snapshots the codebook
 // of the current image (FC:382), then rewrites every pixel from it; here the snapshot
 // is the 2x-decimated plane `dec_in` of the current image, and the sweep emits the
@@ -719,9 +995,11 @@ int launch_fill(uint8_t *d_planes, size_t bytes, int value, cudaStream_t s)
 template <int C>
 __global__ void __launch_bounds__(256)
 k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, uint8_t *__restrict__ dec_out,
-               const float *__restrict__ code, const int32_t *__restrict__ doff, Geom g, unsigned long long *acc,
+               const float *__restrict__ code, const int32_t *__restrict__ doff, Geom g, SweepCtl ctl,
                int32_t *__restrict__ perr)
 {
+    if (sweep_done(ctl)) return;
+    unsigned long long *const acc = ctl.st;
     int qw = g.W / 2;
     int64_t quads = (int64_t)qw * (g.H / 2);
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -778,10 +1056,7 @@ k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, ui
             pe[g.B + 1] = e[3];
         }
     }
-    if (acc) {
-        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-        if ((threadIdx.x & 31) == 0 && local) atomicAdd(acc, local);
-    }
+    sweep_tail(ctl, local);
 }
 
 // Vector path (W % 8 == 0): one thread owns an 8 x 2 pixel strip (four quads): 8-byte loads of the old
@@ -790,9 +1065,10 @@ k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, ui
 template <int C>
 __global__ void __launch_bounds__(256)
 k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, uint8_t *__restrict__ dec_out,
-                  const float *__restrict__ code, const int32_t *__restrict__ doff, Geom g, unsigned long long *acc,
+                  const float *__restrict__ code, const int32_t *__restrict__ doff, Geom g, SweepCtl ctl,
                   int32_t *__restrict__ perr)
 {
+    if (sweep_done(ctl)) return;
     const int sw8 = g.W / 8;
     const int64_t strips = (int64_t)sw8 * (g.H / 2);
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -809,21 +1085,51 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
         for (int qd = 0; qd < 4; qd++)
 #pragma unroll
             for (int k = 0; k < 4; k++) e[qd][k] = 0;
+        // B >= 8: the strip lies inside ONE range block -- one code, one domain offset, and the 2 x 8 domain bytes
+        // are two runs of 8 contiguous bytes (2-byte aligned: the domain grid stride B/4 is even), read as 16-bit
+        // words.  B = 4: a strip spans two range blocks; every quad fetches its own code and bytes.
+        const bool one_range = g.B >= 8;
+        const int64_t jr0 = (int64_t)yr * g.rpw + (x0 >> lb);
+        float a0 = 0.0f;
+        int off0 = 0;
+        if (one_range) {
+            a0 = __ldg(code + S * jr0 + 1);
+            off0 = __ldg(doff + jr0) + ry * g.sw + (x0 & bm);
+        }
 #pragma unroll
         for (int c = 0; c < C; c++) {
             uint8_t *pi = img + c * planeI + (int64_t)y * g.W + x0;
             const uint2 o0 = *(const uint2 *)pi, o1 = *(const uint2 *)(pi + g.W);
             const uint32_t old0[2] = {o0.x, o0.y}, old1[2] = {o1.x, o1.y};
             uint32_t n0[2] = {0, 0}, n1[2] = {0, 0}, nd = 0;
+            uint32_t dr0[4], dr1[4];  // domain bytes of the four quads: row ry (low 16 bits hold 2 pixels) and ry + 1
+            float bq = 0.0f;
+            if (one_range) {
+                bq = __ldg(code + S * jr0 + 2 + c);
+                const uint16_t *pd = (const uint16_t *)(dec_in + c * planeD + off0);
+                const uint16_t *pd1 = (const uint16_t *)(dec_in + c * planeD + off0 + g.sw);
+#pragma unroll
+                for (int qd = 0; qd < 4; qd++) {
+                    dr0[qd] = __ldg(pd + qd);
+                    dr1[qd] = __ldg(pd1 + qd);
+                }
+            }
 #pragma unroll
             for (int qd = 0; qd < 4; qd++) {
                 const int x = x0 + 2 * qd;
-                const int xr = x >> lb, rx = x & bm;
-                const int64_t jr = (int64_t)yr * g.rpw + xr;
-                const float *cd = code + S * jr;
-                const float a = cd[1], b = cd[2 + c];
-                const uint8_t *pd = dec_in + c * planeD + doff[jr] + ry * g.sw + rx;
-                const int d00 = pd[0], d10 = pd[1], d01 = pd[g.sw], d11 = pd[g.sw + 1];
+                float a = a0, b = bq;
+                int d00, d10, d01, d11;
+                if (one_range) {
+                    d00 = dr0[qd] & 0xff; d10 = dr0[qd] >> 8; d01 = dr1[qd] & 0xff; d11 = dr1[qd] >> 8;
+                } else {
+                    const int xr = x >> lb, rx = x & bm;
+                    const int64_t jr = (int64_t)yr * g.rpw + xr;
+                    const float *cd = code + S * jr;
+                    a = cd[1];
+                    b = cd[2 + c];
+                    const uint8_t *pd = dec_in + c * planeD + doff[jr] + ry * g.sw + rx;
+                    d00 = pd[0]; d10 = pd[1]; d01 = pd[g.sw]; d11 = pd[g.sw + 1];
+                }
                 // FC:396 / FC:482: (int)(a * domain + b), float multiply then float add
                 const int v00 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d00), b)));
                 const int v10 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d10), b)));
@@ -858,56 +1164,96 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
             }
         }
     }
-    if (acc) {
-        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-        if ((threadIdx.x & 31) == 0 && local) atomicAdd(acc, local);
-    }
+    sweep_tail(ctl, local);
 }
 
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out, const float *d_code,
-                        const int32_t *d_off, const Geom &g, unsigned long long *d_acc, int32_t *d_perr, cudaStream_t s)
+                        const int32_t *d_off, const Geom &g, const SweepCtl &ctl, int32_t *d_perr, cudaStream_t s)
 {
     if (g.W % 8 == 0 && g.n_iso == 1) {  // the isometry extension uses the quad kernel (per-pixel gather)
         int64_t strips = (int64_t)(g.W / 8) * (g.H / 2);
         unsigned blocks = (unsigned)((strips + 255) / 256);
         if (g.C == 1)
-            k_decode_sweep_v8<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, d_acc, d_perr);
+            k_decode_sweep_v8<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
         else
-            k_decode_sweep_v8<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, d_acc, d_perr);
+            k_decode_sweep_v8<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
         return 1;
     }
     int64_t quads = (int64_t)(g.W / 2) * (g.H / 2);
     unsigned blocks = (unsigned)((quads + 255) / 256);
     if (g.C == 1)
-        k_decode_sweep<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, d_acc, d_perr);
+        k_decode_sweep<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
     else
-        k_decode_sweep<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, d_acc, d_perr);
+        k_decode_sweep<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
     return 1;
 }
 
-// Exact replay of the reference's float accumulation `avgError += e` (FC:407) over the
-// per-pixel squared changes in loop order.  Single thread: the binary32 running sum is
-// order dependent once it passes 2^24.  Only launched when the integer sum cannot
-// decide (see fic_api.cu); never on the common path.
-__global__ void k_serial_avg(const int32_t *__restrict__ perr, int64_t count, float *avg)
+// Folds a sweep that may need the reference's float accumulation replayed (FC:407 / FC:493): the first sweep when
+// the never-reset static avgError (FC:20) carries a value in, the last allowed sweep (its value is kept whatever it is,
+// FC:416), and every sweep of an image above 2^24 pixels (where the sum may pass 2^24 and still converge).
+// One warp.  The running binary32 sum is order dependent once it passes 2^24, so it is replayed in loop order over
+// the per-pixel squared changes -- with three shortcuts, none of which changes a bit of the result:
+//   * while the sum is an integer below 2^24 every add is exact, so a whole 128-element group is added at once; if the
+//     sweep's exact total S is below 2^24 (and nothing is carried in) the sum is S and nothing is replayed;
+//   * a group of zeros is skipped, and inside a group only lanes that hold a non-zero term are visited (x + 0 == x);
+//   * the sum never decreases (the terms are >= 0): on a sweep whose value is discarded unless it converged
+//     (FC:413-417) the replay stops once the sum reaches W*H.
+__global__ void k_sweep_finish(const int32_t *__restrict__ perr, int64_t count, unsigned long long *st, int it, int last,
+                               float carry, float fwh)
 {
-    if (blockIdx.x || threadIdx.x) return;
-    float a = *avg;
-    int64_t i = 0;
-    for (; i + 4 <= count; i += 4) {
-        int4 v = *(const int4 *)(perr + i);
-        a = __fadd_rn(a, (float)v.x);
-        a = __fadd_rn(a, (float)v.y);
-        a = __fadd_rn(a, (float)v.z);
-        a = __fadd_rn(a, (float)v.w);
+    if (blockIdx.x || threadIdx.x >= 32) return;
+    uint32_t *w = (uint32_t *)st;
+    if (((volatile uint32_t *)w)[ST_DONE]) return;
+    const int lane = threadIdx.x;
+    const unsigned long long S = *(volatile unsigned long long *)st;
+    float a = carry;  // FC:20: the first sweep starts from whatever the previous decode left; later ones from 0
+    if (!(a == 0.0f && S < (1ull << 24))) {
+        const float limit = last ? __int_as_float(0x7f800000) : fwh;
+        for (int64_t base = 0; base < count && a < limit; base += 128) {
+            const int64_t i = base + 4 * lane;
+            int4 v = make_int4(0, 0, 0, 0);
+            if (i + 4 <= count) v = *(const int4 *)(perr + i);
+            else
+                for (int k = 0; k < 4; k++)
+                    if (i + k < count) (&v.x)[k] = perr[i + k];
+            const int s = v.x + v.y + v.z + v.w;  // <= 4 * 3 * 255^2
+            int tot = s;
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            if (tot == 0) continue;
+            if (a == floorf(a) && __fadd_rn(a, (float)tot) <= 16777216.0f) {  // every partial sum is an exact integer
+                a = __fadd_rn(a, (float)tot);
+                continue;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, s != 0);
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                a = __fadd_rn(a, (float)__shfl_sync(0xffffffffu, v.x, l));
+                a = __fadd_rn(a, (float)__shfl_sync(0xffffffffu, v.y, l));
+                a = __fadd_rn(a, (float)__shfl_sync(0xffffffffu, v.z, l));
+                a = __fadd_rn(a, (float)__shfl_sync(0xffffffffu, v.w, l));
+            }
+        }
+    } else {
+        a = (float)S;
     }
-    for (; i < count; i++) a = __fadd_rn(a, (float)perr[i]);
-    *avg = a;
+    if (lane == 0) {
+        const float avg = __fdiv_rn(a, fwh);  // FC:413
+        *st = 0ull;
+        w[ST_ITERS] = (uint32_t)(it + 1);
+        if (avg < 1.0f) {  // FC:414
+            w[ST_AVG] = __float_as_uint(avg);
+            w[ST_DONE] = 1u;
+        } else {
+            w[ST_AVG] = last ? __float_as_uint(avg) : 0u;  // FC:416-417
+        }
+    }
 }
 
-int launch_serial_avg(const int32_t *d_perr, int64_t count, float *d_avg_inout, cudaStream_t s)
+int launch_sweep_finish(const int32_t *d_perr, int64_t count, unsigned long long *d_state, int it, int last, float carry,
+                        float fwh, cudaStream_t s)
 {
-    k_serial_avg<<<1, 32, 0, s>>>(d_perr, count, d_avg_inout);
+    k_sweep_finish<<<1, 32, 0, s>>>(d_perr, count, d_state, it, last, carry, fwh);
     return 1;
 }
 

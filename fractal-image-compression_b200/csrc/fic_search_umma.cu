@@ -1773,9 +1773,10 @@ KernelT pick_kernel(bool dump, uint32_t dbg)
     return k_umma_search<B, F16, 0, false, EPI>;
 }
 
-// Epilogue mapping each configuration runs by default (measured, profiles/README.md).
+// Epilogue mapping each configuration runs by default (measured, profiles/README.md: the chunk-per-warp mapping hands
+// accumulators back sooner but pays four waits per tile; it lost on every configuration).
 template <int B, bool F16>
-constexpr int default_epi() { return 1; }
+constexpr int default_epi() { return 0; }
 
 template <int B, bool F16>
 int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s, const char **err,

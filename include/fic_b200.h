@@ -58,9 +58,12 @@ extern "C" {
 #define FIC_MODE_GREY_ISO 2 /* {c, a, b, k} per range; k = isometry 0..7 */
 
 /* Search engine selection (fic_set_option(FIC_OPT_ENGINE, ...)). */
-#define FIC_ENGINE_AUTO 0   /* tcgen05 fused search when the window is the whole pool (RGB: blockgroesse 4, 8) */
-#define FIC_ENGINE_DIRECT 1 /* direct (CUDA-core) windowed search for every window    */
+#define FIC_ENGINE_AUTO 0   /* tcgen05 search when the window is the whole pool (RGB: blockgroesse 4, 8); the fused
+                             * one-launch encode for the reference's GUI windows (widthKernel <= 16); else direct */
+#define FIC_ENGINE_DIRECT 1 /* multi-kernel direct (CUDA-core) windowed search for every window */
 #define FIC_ENGINE_UMMA 2   /* force the tcgen05 search; FIC_E_ARG if not applicable  */
+#define FIC_ENGINE_FUSED 3  /* force the fused windowed encode (decimate + stats + search + solve in one launch);
+                             * FIC_E_ARG unless widthKernel <= 16 and no isometries  */
 
 /* Tensor-core instruction kind of the tcgen05 search (fic_set_option(FIC_OPT_UMMA_KIND, ...)).
  * Both produce the exact integer covariances, hence the same codes.  RGB images have a kind::f16 path only
@@ -77,6 +80,7 @@ extern "C" {
 #define FIC_OPT_F16_EXACT 3
 
 typedef struct fic_handle fic_handle;
+typedef struct fic_multi fic_multi; /* one context over several GPUs of the node, see "multi-GPU" below */
 
 /* Per-call device timings in milliseconds (CUDA events on the handle's stream). */
 typedef struct fic_timings {
@@ -87,7 +91,7 @@ typedef struct fic_timings {
     float solve_ms;   /* winner -> (a, b) solve + quantisation                   */
     float d2h_ms;     /* device -> host copies                                   */
     float total_ms;
-    int engine;       /* FIC_ENGINE_DIRECT or FIC_ENGINE_UMMA actually used      */
+    int engine;       /* FIC_ENGINE_DIRECT, _UMMA or _FUSED actually used        */
     int launches;     /* kernels launched by this call                           */
     double search_evals; /* range x candidate evaluations done by the search     */
 } fic_timings;
@@ -119,6 +123,14 @@ int fic_encode_grey(fic_handle *h, const int32_t *argb, int W, int H, int B, int
                     int64_t range_begin, int64_t range_end, float *info, int32_t *qcodes);
 int fic_encode_rgb(fic_handle *h, const int32_t *argb, int W, int H, int B, int wk,
                    int64_t range_begin, int64_t range_end, float *info, int32_t *qcodes);
+
+/* The same calls for hosts that already hold 8-bit pixels (SURVEY 8b allows `const uint8_t*`): `plane` is the red
+ * channel of a grey image (W*H bytes -- what FC:596 / FC:977 read from the ARGB ints), `planes` the R, G, B planes of
+ * an RGB image (3*W*H bytes).  A quarter of the upload of the ARGB entries; results are identical. */
+int fic_encode_grey_u8(fic_handle *h, const uint8_t *plane, int W, int H, int B, int wk,
+                       int64_t range_begin, int64_t range_end, float *info, int32_t *qcodes);
+int fic_encode_rgb_planes(fic_handle *h, const uint8_t *planes, int W, int H, int B, int wk,
+                          int64_t range_begin, int64_t range_end, float *info, int32_t *qcodes);
 
 /* EXTENSION (the reference searches the identity only, FC:642): grey encode whose candidate loop has an
  * inner loop over the 8 isometries of the domain block -- order (c, k) lexicographic, the reference's score
@@ -155,11 +167,48 @@ int fic_unpin_host_buffer(fic_handle *h, void *ptr);
 int fic_decode(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int32_t *qcodes,
                int max_iters, int32_t *argb_out, float *avg_error, int *iterations);
 
+/* The same decoder with the image returned as 8-bit planes (grey: W*H bytes; RGB: R, G, B planes) instead of ARGB
+ * ints: to host memory, or (fic_decode_planes_dev) from device-resident codes -- as fic_encode_planes_dev leaves
+ * them -- to a 16-byte-aligned device buffer.  Both synchronise before they return (avg_error / iterations are host
+ * scalars). */
+int fic_decode_u8(fic_handle *h, int is_rgb, int W, int H, int B, int wk, const int32_t *qcodes,
+                  int max_iters, uint8_t *planes_out, float *avg_error, int *iterations);
+int fic_decode_planes_dev(fic_handle *h, int is_rgb, int W, int H, int B, int wk,
+                          const int32_t *d_qcodes, int max_iters, uint8_t *d_planes_out,
+                          float *avg_error, int *iterations);
+
 /* getBestGeneratedCollage[RGB] (FC:269-347): one decode step from the source image
  * with the unquantised codes.  Like the reference it rewrites info[.][0] in place from
  * window-local to codebook index (FC:273). */
 int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, int B, int wk,
                 float *info, int32_t *argb_out);
+
+/* ---- multi-GPU: the same encode over several GPUs of one node --- */
+
+/* Replaces the same reference loops (FC:119 + FC:125-159, FC:181 + FC:186-215) with the range-block rows sharded
+ * over `n_devices` GPUs of this process: the image is uploaded once, broadcast to the other devices with
+ * ncclBroadcast over NVLink (NCCL is loaded at run time; n_devices == 1 needs none), every device builds the whole
+ * domain pool and searches a contiguous slice of range rows, and each device copies its code rows straight into the
+ * caller's arrays.  Results are byte-identical to the single-device entries for every device count.
+ * `devices` are CUDA ordinals (distinct).  One in-flight call per multi handle. */
+int fic_create_multi(const int *devices, int n_devices, fic_multi **out);
+void fic_destroy_multi(fic_multi *m);
+const char *fic_multi_last_error(const fic_multi *m); /* m may be NULL: last create error */
+int fic_multi_device_count(const fic_multi *m);
+/* The per-device context of `rank` (0 .. n-1), owned by the multi handle: for fic_decode / fic_collage (replicas
+ * only: the decoder does not shard), fic_pin_host_buffer, per-device timings.  Do not fic_destroy it. */
+fic_handle *fic_multi_handle(fic_multi *m, int rank);
+int fic_multi_set_option(fic_multi *m, int option, int value); /* fic_set_option on every device */
+/* rank < 0: the slowest device per stage (total_ms: the longest device timeline); else that device's timings */
+int fic_multi_get_timings(const fic_multi *m, int rank, fic_timings *out);
+/* the range-block interval [begin, end) device `rank` encoded in the last call */
+int fic_multi_range_slice(const fic_multi *m, int rank, int64_t *range_begin, int64_t *range_end);
+
+int fic_multi_encode_grey(fic_multi *m, const int32_t *argb, int W, int H, int B, int wk, float *info, int32_t *qcodes);
+int fic_multi_encode_rgb(fic_multi *m, const int32_t *argb, int W, int H, int B, int wk, float *info, int32_t *qcodes);
+int fic_multi_encode_grey_iso(fic_multi *m, const int32_t *argb, int W, int H, int B, int wk, float *info, int32_t *qcodes);
+int fic_multi_encode_grey_u8(fic_multi *m, const uint8_t *plane, int W, int H, int B, int wk, float *info, int32_t *qcodes);
+int fic_multi_encode_rgb_planes(fic_multi *m, const uint8_t *planes, int W, int H, int B, int wk, float *info, int32_t *qcodes);
 
 /* ---- diagnostics -------------------------------------------------------------- */
 

@@ -80,3 +80,9 @@ def test_no_cpu_fallback(fic):
     with pytest.raises(fic.FicError) as e:
         fic.Handle(0)
     assert e.value.code == fic._lib.FIC_E_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(fic.FicError) as e:   # the multi-GPU handle is built from the same per-device contexts
+        fic.MultiHandle([0])
+    assert e.value.code == fic._lib.FIC_E_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(fic.FicError) as e:
+        fic.MultiHandle([0, 0])
+    assert e.value.code == fic._lib.FIC_E_ARG

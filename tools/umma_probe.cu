@@ -318,6 +318,155 @@ static int run_mix()
     return 0;
 }
 
+
+// ---- accumulator hand-over round trip ("chain" mode) ----------------------------------------------
+// One MMA-issuer warp and four "epilogue" warps (one per TMEM lane quarter) play the search kernel's accumulator
+// protocol with nothing else in the way: issuer waits empty[q], issues ks tcgen05.mma (M = N = 128, K = 16,
+// kind::f16), commits -> full[q]; each epilogue warp waits full[q], does nload tcgen05.ld.x32 (+ wait), arrives on
+// empty[q].  nacc accumulators are used round-robin.  Reports clocks per round: with nacc = 1 that is
+// ks * 64 (the MMAs) + the synchronisation latency of the whole hand-over.
+namespace chain {
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint32_t b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(c)); }
+__device__ __forceinline__ void mb_arrive(uint32_t b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory"); }
+__device__ __forceinline__ uint32_t mb_try(uint32_t b, uint32_t par)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(b), "r"(par) : "memory");
+    return ok;
+}
+__device__ __forceinline__ uint32_t mb_test(uint32_t b, uint32_t par)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(b), "r"(par) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mb_wait(uint32_t b, uint32_t par, int spin)
+{
+    if (spin) { while (!mb_test(b, par)) {} }
+    else { while (!mb_try(b, par)) {} }
+}
+__device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
+}
+}  // namespace chain
+
+__global__ void __launch_bounds__(192, 1) k_chain(int iters, int ks, int nload, int nacc, int flags, long long *clk_out)
+{
+    using namespace chain;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem, *sB = smem + 16384;              // 4 K-slices each: 128 rows x 64 binary16
+    uint64_t *bars = (uint64_t *)(smem + 32768);
+    uint32_t *slot = (uint32_t *)(bars + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 32768 / 4; i += blockDim.x) {
+        uint32_t x = (uint32_t)i * 2654435761u + 12345u;
+        x ^= x >> 15; x *= 0x2c1b3c6du; x ^= x >> 12;
+        ((uint32_t *)smem)[i] = x & 0x3fff3fffu;
+    }
+    const uint32_t bar0 = s32(bars);
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 4; q++) { mb_init(bar0 + 8 * q, 1); mb_init(bar0 + 32 + 8 * q, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *slot;
+    const int spin_epi = flags & 1, spin_iss = flags & 2;
+    if (warp == 1) {
+        const uint64_t ad = desc(s32(sA), 128, 1024), bd = desc(s32(sB), 128, 1024);
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        long long t0 = clock64();
+        for (int i = 0; i < iters; i++) {
+            const int q = i % nacc;
+            mb_wait(bar0 + 32 + 8 * q, ((i / nacc) & 1) ^ 1, spin_iss);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                for (int s = 0; s < ks; s++) {
+                    const uint32_t acc = s > 0;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + q * 128),
+                                 "l"(ad + (uint64_t)((s & 3) * 16)), "l"(bd + (uint64_t)((s & 3) * 16)), "r"(idesc), "r"(acc)
+                                 : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * q) : "memory");
+            }
+            __syncwarp();
+        }
+        // drain: wait until the last round of every accumulator came back
+        for (int q = 0; q < nacc; q++) {
+            const int rounds = (iters - q + nacc - 1) / nacc;  // rounds accumulator q went through
+            mb_wait(bar0 + 32 + 8 * q, (rounds & 1) ^ 1, 0);
+        }
+        long long t1 = clock64();
+        if (lane == 0) clk_out[blockIdx.x] = t1 - t0;
+    } else if (warp >= 2) {
+        const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t sink = 0;
+        for (int i = 0; i < iters; i++) {
+            const int q = i % nacc;
+            mb_wait(bar0 + 8 * q, (i / nacc) & 1, spin_epi);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c = 0; c < nload; c++) {
+                uint32_t v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(ta + q * 128 + c * 32)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                sink ^= v[0] ^ v[31];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mb_arrive(bar0 + 32 + 8 * q);
+        }
+        if (sink == 0x12345u) clk_out[1000] = 1;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+static int run_chain()
+{
+    long long *d;
+    if (cudaMalloc(&d, 2048 * 8) != cudaSuccess) return 3;
+    const int smem = 40 * 1024;
+    cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int iters = 20000;
+    struct Cfg { int ks, nload, nacc, flags; };
+    const Cfg cfgs[] = {{1, 0, 1, 0}, {4, 0, 1, 0}, {1, 0, 1, 1}, {1, 0, 1, 2}, {1, 0, 1, 3}, {1, 1, 1, 0}, {1, 4, 1, 0}, {4, 4, 1, 0},
+                        {4, 0, 4, 0}, {4, 1, 4, 0}, {4, 2, 4, 0}, {4, 3, 4, 0}, {4, 4, 4, 0}, {4, 4, 4, 1}, {4, 4, 4, 3}, {4, 0, 2, 0}, {4, 2, 2, 0},
+                        {2, 0, 4, 0}, {2, 2, 4, 0}, {2, 4, 4, 0}, {1, 0, 4, 0}, {1, 4, 4, 0}};
+    for (const Cfg &c : cfgs) {
+        for (int grid : {1, 148}) {
+            cudaMemset(d, 0, 2048 * 8);
+            k_chain<<<grid, 192, smem>>>(iters, c.ks, c.nload, c.nacc, c.flags, d);
+            if (cudaDeviceSynchronize() != cudaSuccess) { printf("chain kernel failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 3; }
+            long long h[148];
+            cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+            long long mx = 0;
+            for (int b = 0; b < grid; b++) mx = h[b] > mx ? h[b] : mx;
+            printf("chain: ks=%d nload=%d nacc=%d spin(epi=%d,iss=%d) grid=%3d: %.1f clk per round (MMA alone %d)\n", c.ks, c.nload, c.nacc,
+                   c.flags & 1, (c.flags >> 1) & 1, grid, (double)mx / iters, c.ks * 64);
+        }
+    }
+    return 0;
+}
+
 static int run_ldtm()
 {
     long long *d;
@@ -344,6 +493,7 @@ int main(int argc, char **argv)
     if (argc > 1 && !strcmp(argv[1], "ldtm")) return run_ldtm();
     if (argc > 1 && !strcmp(argv[1], "alu")) return run_alu();
     if (argc > 1 && !strcmp(argv[1], "mix")) return run_mix();
+    if (argc > 1 && !strcmp(argv[1], "chain")) return run_chain();
     if (argc < 4) {
         printf("usage: umma_probe check|time B W [variant] [pattern]\n");
         return 2;
