@@ -60,9 +60,13 @@ struct fic_handle {
     bool tm_pending_dev = false;
     // pinned scratch for small device->host reads
     unsigned long long *h_acc = nullptr;
+    // pinned staging for small code tables: one device->host copy instead of two (info and qcodes are adjacent on the
+    // device), then a host memcpy into the caller's arrays -- the reference's default image (1024 ranges) is all latency
+    uint8_t *h_stage = nullptr;
 };
 
 static char g_create_err[512] = "";
+constexpr size_t kStageBytes = 128 << 10;
 
 static int set_err(fic_handle *h, int code, const char *fmt, ...)
 {
@@ -158,6 +162,7 @@ int fic_create(int device, fic_handle **out)
     h->stream = h->own_stream;
     for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&h->h_acc, 64 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&h->h_stage, kStageBytes, cudaHostAllocDefault);
     if (e != cudaSuccess) {
         set_err(nullptr, FIC_E_CUDA, "creating events / pinned scratch: %s", cudaGetErrorString(e));
         fic_destroy(h);
@@ -180,6 +185,7 @@ void fic_destroy(fic_handle *h)
     for (int i = 0; i < 8; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->h_acc) cudaFreeHost(h->h_acc);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -291,12 +297,9 @@ static int encode_fused_on_device(fic_handle *h, const Geom &g, const void *d_pi
                                   float *d_info, int32_t *d_q)
 {
     cudaStream_t s = h->stream;
+    // one kernel: events 1 and 4 bracket it (collect_timings reads the stages of this engine from those two alone)
     CU(cudaEventRecord(h->ev[1], s));
-    CU(cudaEventRecord(h->ev[2], s));
-    CU(cudaEventRecord(h->ev[6], s));
     const int launches = launch_encode_fused(d_pixels, is_argb, g, j0, j1, d_info, d_q, s);
-    CU(cudaEventRecord(h->ev[7], s));
-    CU(cudaEventRecord(h->ev[3], s));
     CU(cudaEventRecord(h->ev[4], s));
     CU(cudaGetLastError());
     h->tm.engine = FIC_ENGINE_FUSED;
@@ -376,6 +379,13 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
 static void collect_timings(fic_handle *h, bool with_copies)
 {
     float ms = 0;
+    if (h->tm.engine == FIC_ENGINE_FUSED) {  // a single kernel between events 1 and 4
+        if (with_copies && cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->tm.h2d_ms = ms;
+        if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[4]) == cudaSuccess) h->tm.search_ms = h->tm.kernel_ms = ms;
+        if (with_copies && cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]) == cudaSuccess) h->tm.d2h_ms = ms;
+        if (cudaEventElapsedTime(&ms, h->ev[with_copies ? 0 : 1], h->ev[with_copies ? 5 : 4]) == cudaSuccess) h->tm.total_ms = ms;
+        return;
+    }
     if (with_copies && cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]) == cudaSuccess) h->tm.h2d_ms = ms;
     if (cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]) == cudaSuccess) h->tm.pool_ms = ms;
     if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) == cudaSuccess) h->tm.search_ms = ms;
@@ -408,8 +418,16 @@ static int encode_host(fic_handle *h, int is_rgb, const void *pixels, int src_u8
     const bool fused_argb = engine == FIC_ENGINE_FUSED && !src_u8;  // the fused kernel reads the ARGB ints itself
     if (!src_u8) ENSURE(w.argb, S_ARGB, sizeof(int32_t) * (size_t)W * H);
     if (!fused_argb) ENSURE(w.src, S_SRC, (size_t)g.C * W * H);
-    ENSURE(w.info, S_INFO, sizeof(float) * g.NR * S);
-    ENSURE(w.q, S_Q, sizeof(int32_t) * g.NR * S);
+    const size_t table = sizeof(float) * (size_t)g.NR * S;  // bytes of one code table (float and int32 entries alike)
+    const bool staged = info && qcodes && 2 * table <= kStageBytes;  // small tables: one copy through pinned staging
+    if (staged) {
+        ENSURE(w.info, S_INFO, 2 * table);  // [imageInfo floats][writeData ints], adjacent
+    } else {
+        ENSURE(w.info, S_INFO, table);
+        ENSURE(w.q, S_Q, table);
+    }
+    float *const d_info = w.info;
+    int32_t *const d_q = staged ? (int32_t *)((uint8_t *)w.info + table) : w.q;
     DrainOnExit drain(s);
     CU(cudaEventRecord(h->ev[0], s));
     if (src_u8) {
@@ -418,15 +436,23 @@ static int encode_host(fic_handle *h, int is_rgb, const void *pixels, int src_u8
         CU(cudaMemcpyAsync(w.argb, pixels, sizeof(int32_t) * (size_t)W * H, cudaMemcpyHostToDevice, s));
         if (!fused_argb) h->tm.launches += launch_unpack(w.argb, w.src, W, H, g.C, s);
     }
-    rc = fused_argb ? encode_fused_on_device(h, g, w.argb, 1, j0, j1, w.info, w.q)
-                    : encode_on_device(h, g, w.src, j0, j1, w.info, w.q, engine);
+    rc = fused_argb ? encode_fused_on_device(h, g, w.argb, 1, j0, j1, d_info, d_q)
+                    : encode_on_device(h, g, w.src, j0, j1, d_info, d_q, engine);
     if (rc) return rc;
     if (j1 > j0) {
-        if (info) CU(cudaMemcpyAsync(info + j0 * S, w.info + j0 * S, sizeof(float) * (j1 - j0) * S, cudaMemcpyDeviceToHost, s));
-        if (qcodes) CU(cudaMemcpyAsync(qcodes + j0 * S, w.q + j0 * S, sizeof(int32_t) * (j1 - j0) * S, cudaMemcpyDeviceToHost, s));
+        if (staged) {
+            CU(cudaMemcpyAsync(h->h_stage, d_info, 2 * table, cudaMemcpyDeviceToHost, s));
+        } else {
+            if (info) CU(cudaMemcpyAsync(info + j0 * S, d_info + j0 * S, sizeof(float) * (j1 - j0) * S, cudaMemcpyDeviceToHost, s));
+            if (qcodes) CU(cudaMemcpyAsync(qcodes + j0 * S, d_q + j0 * S, sizeof(int32_t) * (j1 - j0) * S, cudaMemcpyDeviceToHost, s));
+        }
     }
     CU(cudaEventRecord(h->ev[5], s));
     CU(cudaStreamSynchronize(s));
+    if (staged && j1 > j0) {
+        memcpy(info + j0 * S, h->h_stage + sizeof(float) * j0 * S, sizeof(float) * (j1 - j0) * S);
+        memcpy(qcodes + j0 * S, h->h_stage + table + sizeof(int32_t) * j0 * S, sizeof(int32_t) * (j1 - j0) * S);
+    }
     collect_timings(h, true);
     return FIC_OK;
 }
@@ -608,12 +634,26 @@ static int decode_core(fic_handle *h, int is_rgb, int W, int H, int B, int wk, c
     int32_t *doff = (int32_t *)(w.dcode + g.NR * S);
     launches += launch_dequant(d_qcodes ? d_qcodes : w.q, w.dcode, doff, g, 0, nullptr, w.acc, s);
     launches += launch_fill(img, g.C * plane, 128, s);  // FC:360, FC:1142-1148
-    launches += launch_decimate(img, w.dec, g, s);
+    // the 2x-decimated plane of a constant-128 image is constant 128 for every tap rule (FC:970-1007, FC:901-962)
+    CU(cudaMemsetAsync(w.dec, 128, (size_t)g.C * g.sw * g.sh, s));
     uint8_t *dcur = w.dec, *dnext = w.dec2;
     const uint32_t *hst = (const uint32_t *)h->h_acc;  // host copy of the state block as 32-bit words: [5..7] = done, iters, avg
+    // Small images: the output copy is enqueued behind every batch, so that a decode that converges within the batch
+    // (the usual case) costs one host synchronisation in all; a later batch simply copies again.
+    const bool speculative_out = !d_planes_out && plane * (argb_out ? 4 : g.C) <= ((size_t)4 << 20);
+    auto enqueue_output = [&]() -> int {
+        if (argb_out) {
+            launches += launch_pack_argb(img, w.argb, W, H, g.C, s);
+            CU(cudaMemcpyAsync(argb_out, w.argb, sizeof(int32_t) * plane, cudaMemcpyDeviceToHost, s));
+        } else if (planes_out) {
+            CU(cudaMemcpyAsync(planes_out, img, g.C * plane, cudaMemcpyDeviceToHost, s));
+        }
+        return FIC_OK;
+    };
     int it = 0;
+    bool out_done = false;
     while (it < max_iters) {
-        const int batch_end = it + 8 < max_iters ? it + 8 : max_iters;
+        const int batch_end = it + 8 < max_iters ? it + 8 : max_iters;  // a skipped sweep still costs a launch (~1 us)
         for (; it < batch_end; it++) {
             const bool last = it == max_iters - 1;
             const bool replay = big || last || (it == 0 && carry != 0.0f);
@@ -623,19 +663,21 @@ static int decode_core(fic_handle *h, int is_rgb, int W, int H, int B, int wk, c
             uint8_t *t = dcur; dcur = dnext; dnext = t;
         }
         CU(cudaMemcpyAsync(h->h_acc, w.acc, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        if (speculative_out) {
+            if ((rc = enqueue_output())) return rc;
+            CU(cudaEventRecord(h->ev[5], s));
+        }
         CU(cudaStreamSynchronize(s));
         if (h->h_acc[1]) return set_err(h, FIC_E_STREAM, "a code indexes outside the domain pool (the reference would throw ArrayIndexOutOfBounds)");
+        out_done = speculative_out;
         if (hst[5]) break;  // converged (FC:414)
     }
-    if (argb_out) {
-        launches += launch_pack_argb(img, w.argb, W, H, g.C, s);
-        CU(cudaMemcpyAsync(argb_out, w.argb, sizeof(int32_t) * plane, cudaMemcpyDeviceToHost, s));
-    } else if (planes_out) {
-        CU(cudaMemcpyAsync(planes_out, img, g.C * plane, cudaMemcpyDeviceToHost, s));
+    if (!out_done) {
+        if ((rc = enqueue_output())) return rc;
+        CU(cudaEventRecord(h->ev[5], s));
+        CU(cudaStreamSynchronize(s));
     }
     CU(cudaGetLastError());
-    CU(cudaEventRecord(h->ev[5], s));
-    CU(cudaStreamSynchronize(s));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]) == cudaSuccess) h->tm.total_ms = ms;
     h->tm.launches = launches;

@@ -102,8 +102,8 @@ constexpr int kBoundBytes = kChunksPerTile * 2 * 4 + 16;  // (rhi, rlo) f32 per 
 // the row -- two (column halves, a historical split) for the accumulator-per-warp mapping, four (one per 32-column
 // chunk of a tile) for the chunk-per-warp mapping.  Same footprint either way.
 constexpr int kFlagBytes = 4 * (4 + 8 * 16);         // per (row, unit): list lengths + entries, both mappings fit
-__host__ __device__ constexpr int kListsOf(int epi) { return epi ? 4 : 2; }
-__host__ __device__ constexpr int kCapOf(int epi) { return epi ? 16 : 32; }
+__host__ __device__ constexpr int kListsOf(int epi) { return epi == 1 ? 4 : 2; }
+__host__ __device__ constexpr int kCapOf(int epi) { return epi == 1 ? 16 : 32; }
 constexpr float kOneMinusEps = 1.0f - 1.9073486328125e-06f;  // 1 - 2^-19 (applied to the squared score)
 
 // Operand geometry of one (block size, MMA kind) pair.  F16 = false: kind::i8, two s8 digits per
@@ -832,7 +832,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         }
         for (int q = 0; q < kAccs; q++) {
             mbar_init(BAR_T_FULL(q), 1);
-            mbar_init(BAR_T_EMPTY(q), EPI ? kEpiWarps : kEpiWarps / kAccs);  // every warp that reads the accumulator
+            mbar_init(BAR_T_EMPTY(q), EPI == 1 ? kEpiWarps : kEpiWarps / kAccs);  // every warp that reads the accumulator
         }
         mbar_init(BAR_A_FULL, 1);
         mbar_init(BAR_A_EMPTY, 1);
@@ -893,6 +893,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         // uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.
         uint32_t stage = 0, phase = 0, a_phase = 0, t_phase = 0;  // t_phase: bit q
         const uint32_t elected = elect_one();
+        const long long clk0 = clock64();  // probe only (status != nullptr): elapsed SM clocks of CTA 0's issuer
         // descriptors differ only in the 14-bit start-address field (16-byte units)
         const uint64_t a_desc0 = make_desc(smem_u32(sA), lbo_bytes_a, sbo_bytes_a);
         const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo_bytes_b, sbo_bytes_b);
@@ -979,7 +980,12 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             __syncwarp();
             a_phase ^= 1;
         }
-    } else if (warp >= 4 && EPI == 0) {
+        if (status && blockIdx.x == 0 && elected) {
+            const long long dt = clock64() - clk0;
+            status[2] = (int)(dt & 0x7fffffff);
+            status[3] = (int)(dt >> 31);
+        }
+    } else if (warp >= 4 && EPI != 1) {
         // ===================== epilogue, accumulator per warp =====================
         // Warp e: TMEM lane quarter lq = e % 4 (== warp % 4, the quarter this warp may access) of accumulator
         // q = e / 4: one thread = one range row, all 128 domains of a tile.  Per tile a warp makes ONE visit (one
@@ -1050,6 +1056,66 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     }
                 }
                 tick(tk_t);
+                if constexpr ((EPI == 2 || EPI == 3) && F16 && !DUMP && !(DBG & 3)) {
+                    // Software-pipelined visit (kind::f16).  The first level of the |.| max tree reads all 32 registers
+                    // of a chunk in 11 instructions; the load of the NEXT chunk is issued behind them (into the same
+                    // registers) so that its TMEM latency hides behind the rest of the tree.  EPI == 3 also defers the
+                    // four flag tests (multiply, compare, branch) until the accumulator has been handed back: between
+                    // two loads only the 16 FMNMX3 remain.  The empty asm statements pin the order where it matters.
+                    uint32_t v[32];
+                    float Mc[kChunksPerTile];
+                    tmem_ld32(ta, v);
+                    tmem_ld_wait();
+                    pin_order(v);
+                    auto test = [&](int c) {
+                        const float rhi = c == 0 ? bnd01.x : (c == 1 ? bnd01.z : (c == 2 ? bnd23.x : bnd23.z));
+                        const float rlo = c == 0 ? bnd01.y : (c == 1 ? bnd01.w : (c == 2 ? bnd23.y : bnd23.w));
+                        const float ub = Mc[c] * rhi;
+                        if (ub > st.thresh) {  // may hold the winner or one of its float ties
+                            st.cnt = c < 2 ? cnt0 : cnt1;
+                            st = flag_chunk(st, Mc[c] * rlo, ub, tie_abs, list0 + (c >> 1) * kCapOf(0), kCapOf(0), t * kChunksPerTile + c, sh_lb, iso_shift ? 1 : 0);
+                            if (c < 2) cnt0 = st.cnt;
+                            else cnt1 = st.cnt;
+                        }
+                    };
+#pragma unroll
+                    for (int c = 0; c < kChunksPerTile; c++) {
+                        auto av = [&](int k) { return fabsf(__uint_as_float(v[k])); };
+                        float l[11];
+#pragma unroll
+                        for (int i = 0; i < 10; i++) l[i] = fmaxf(fmaxf(av(3 * i), av(3 * i + 1)), av(3 * i + 2));
+                        l[10] = fmaxf(av(30), av(31));
+                        if (c + 1 < kChunksPerTile) {
+                            uint32_t next = ta + (c + 1) * 32;
+                            asm volatile("" : "+r"(next) : "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]), "f"(l[4]), "f"(l[5]), "f"(l[6]),
+                                         "f"(l[7]), "f"(l[8]), "f"(l[9]), "f"(l[10]));
+                            tmem_ld32(next, v);
+                        }
+                        asm volatile("" : "+f"(l[0]), "+f"(l[1]), "+f"(l[2]), "+f"(l[3]), "+f"(l[4]), "+f"(l[5]), "+f"(l[6]), "+f"(l[7]),
+                                     "+f"(l[8]), "+f"(l[9]), "+f"(l[10]));
+                        const float m0 = fmaxf(fmaxf(l[0], l[1]), l[2]), m1 = fmaxf(fmaxf(l[3], l[4]), l[5]);
+                        const float m2 = fmaxf(fmaxf(l[6], l[7]), l[8]), m3 = fmaxf(fmaxf(l[9], l[10]), m0);
+                        Mc[c] = fmaxf(fmaxf(m1, m2), m3);  // max |kov| over the chunk, exact
+                        if (EPI == 2) test(c);
+                        if (c + 1 < kChunksPerTile) {
+                            tmem_ld_wait();
+                            pin_order(v);
+                            if (c + 1 == kChunksPerTile - 1) {
+                                // the accumulator's last chunk is in registers: hand it back
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
+                                if (EPI == 3) {  // the deferred tests of the first three chunks, in sweep order
+                                    asm volatile("" : "+f"(Mc[0]), "+f"(Mc[1]), "+f"(Mc[2]) : : "memory");
+                                    test(0);
+                                    test(1);
+                                    test(2);
+                                }
+                            }
+                        }
+                    }
+                    if (EPI == 3) test(kChunksPerTile - 1);
+                } else {
 #pragma unroll
                 for (int c = 0; c < kChunksPerTile; c++) {
                     uint32_t v[32];
@@ -1114,6 +1180,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                         else cnt1 = st.cnt;
                     }
                     tick(tk_m);
+                }
                 }
                 tf_phase ^= 1;
             }
@@ -1776,7 +1843,7 @@ KernelT pick_kernel(bool dump, uint32_t dbg)
 // Epilogue mapping each configuration runs by default (measured, profiles/README.md: the chunk-per-warp mapping hands
 // accumulators back sooner but pays four waits per tile; it lost on every configuration).
 template <int B, bool F16>
-constexpr int default_epi() { return 0; }
+constexpr int default_epi() { return !F16 ? 0 : (B == 4 ? 3 : 2); }
 
 template <int B, bool F16>
 int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s, const char **err,
@@ -1828,10 +1895,12 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     launches += 2;
     // 3. the fused search
     // Epilogue mapping (see k_umma_search): the default of this (block size, kind) pair, or the probe's choice
-    // (variant bit 1: accumulator per warp, bit 2: chunk per warp).
-    const int epi = (variant & 2) ? 0 : ((variant & 4) ? 1 : default_epi<B, F16>());
+    // (variant bit 1: accumulator per warp, bit 2: chunk per warp, bit 3: accumulator per warp, software-pipelined).
+    const int epi = (variant & 2) ? 0 : ((variant & 4) ? 1 : ((variant & 8) ? 2 : ((variant & 16) ? 3 : default_epi<B, F16>())));
     KernelT kern = pick_kernel<B, F16, 0>(dump && !(dbg & 8u), dbg);
-    if (epi) kern = pick_kernel<B, F16, 1>(dump && !(dbg & 8u), dbg);
+    if (epi == 1) kern = pick_kernel<B, F16, 1>(dump && !(dbg & 8u), dbg);
+    if (epi == 2) kern = pick_kernel<B, F16, 2>(dump && !(dbg & 8u), dbg);
+    if (epi == 3) kern = pick_kernel<B, F16, 3>(dump && !(dbg & 8u), dbg);
     if (dbg == 8 || dbg == 12) dump = w.best;  // phase cycle counts -> w.best
     ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }

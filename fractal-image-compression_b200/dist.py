@@ -55,7 +55,7 @@ class ShardedEncoder:
         S = (3, 5, 4)[int(rgb)]   # grey, RGB, grey + isometry index (extension)
         NR = (W // B) * (H // B)
         key = (NR, S, planes.device)
-        if key not in self._bufs:
+        if key not in self._bufs:   # scratch, reused by every encode of this shape; only rows [j0, j1) are meaningful
             self._bufs[key] = (torch.empty((NR, S), dtype=torch.float32, device=planes.device),
                                torch.empty((NR, S), dtype=torch.int32, device=planes.device))
         info, q = self._bufs[key]
@@ -81,7 +81,8 @@ class ShardedEncoder:
         j0, j1 = parts[self.rank]
         info, q = self.worker(buf, rgb, W, H, B, wk, j0, j1)
         if self.world == 1:
-            return info, q
+            # the default worker's buffers are scratch that the next encode overwrites: hand out copies
+            return info.clone(), q.clone()
         # gather equal-sized (padded) row slices to rank 0
         maxrows = max(b - a for a, b in parts)
         send = torch.zeros((maxrows, 2 * S), dtype=torch.int32, device=buf.device)

@@ -38,6 +38,32 @@ final class FicNative {
     private static final MethodHandle STREAM_WRITE = h("fic_stream_write", FunctionDescriptor.of(JAVA_INT, JAVA_INT, JAVA_INT,
             JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG));
 
+    // Multi-GPU: one context over several GPUs of the node (one upload, NCCL broadcast over NVLink, range rows sharded).
+    // `-Dfic.devices=0,1,2,3` selects them; without the property the shim stays on the single-device entries above.
+    private static final MethodHandle CREATE_MULTI = h("fic_create_multi", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    private static final MethodHandle MULTI_LAST_ERROR = h("fic_multi_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
+    private static final MethodHandle MULTI_ENCODE_GREY = h("fic_multi_encode_grey", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS,
+            JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle MULTI_ENCODE_RGB = h("fic_multi_encode_rgb", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS,
+            JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
+    private static MemorySegment multi;
+
+    private static synchronized MemorySegment multi() throws Throwable {
+        String prop = System.getProperty("fic.devices");
+        if (prop == null) return null;
+        if (multi == null) {
+            int[] devs = java.util.Arrays.stream(prop.split(",")).mapToInt(x -> Integer.parseInt(x.trim())).toArray();
+            MemorySegment out = Arena.global().allocate(ADDRESS);
+            int rc = (int) CREATE_MULTI.invokeExact(Arena.global().allocateFrom(JAVA_INT, devs), devs.length, out);
+            if (rc != 0) {
+                MemorySegment msg = (MemorySegment) MULTI_LAST_ERROR.invokeExact(MemorySegment.NULL);
+                throw new Exception("libfic_b200 error " + rc + ": " + msg.reinterpret(512).getString(0));
+            }
+            multi = out.get(ADDRESS, 0);
+        }
+        return multi;
+    }
+
     private static MemorySegment handle;  // one context, like the reference's static state (FractalCompression.java:14-20)
 
     private static synchronized MemorySegment handle() throws Throwable {
@@ -63,8 +89,17 @@ final class FicNative {
             MemorySegment in = a.allocateFrom(JAVA_INT, argb);
             MemorySegment outInfo = a.allocate(JAVA_FLOAT, (long) nr * stride);
             MemorySegment outQ = a.allocate(JAVA_INT, (long) nr * stride);
-            MethodHandle f = rgb ? ENCODE_RGB : ENCODE_GREY;
-            check((int) f.invokeExact(handle(), in, w, h, block, wk, 0L, (long) nr, outInfo, outQ), handle());
+            MemorySegment m = multi();
+            if (m != null) {  // the same outputs, range rows sharded over the GPUs of -Dfic.devices
+                int rc = (int) (rgb ? MULTI_ENCODE_RGB : MULTI_ENCODE_GREY).invokeExact(m, in, w, h, block, wk, outInfo, outQ);
+                if (rc != 0) {
+                    MemorySegment msg = (MemorySegment) MULTI_LAST_ERROR.invokeExact(m);
+                    throw new Exception("libfic_b200 error " + rc + ": " + msg.reinterpret(512).getString(0));
+                }
+            } else {
+                MethodHandle f = rgb ? ENCODE_RGB : ENCODE_GREY;
+                check((int) f.invokeExact(handle(), in, w, h, block, wk, 0L, (long) nr, outInfo, outQ), handle());
+            }
             for (int j = 0; j < nr; j++)
                 for (int k = 0; k < stride; k++) info[j][k] = outInfo.getAtIndex(JAVA_FLOAT, (long) j * stride + k);
             MemorySegment.copy(outQ, JAVA_INT, 0, q, 0, nr * stride);
@@ -77,7 +112,10 @@ final class FicNative {
         try (Arena a = Arena.ofConfined()) {
             MemorySegment codes = a.allocateFrom(JAVA_INT, q);
             MemorySegment out = a.allocate(n);
-            check((int) STREAM_WRITE.invokeExact(rgb ? 1 : 0, w, h, block, wk, codes, out, n), handle());
+            // host-only helper: it never touches a handle (and sets no handle error string), so a failure is reported
+            // with a fixed message instead of fic_last_error -- no GPU context is created just to report it
+            int rc = (int) STREAM_WRITE.invokeExact(rgb ? 1 : 0, w, h, block, wk, codes, out, n);
+            if (rc != 0) throw new Exception("libfic_b200 error " + rc + ": fic_stream_write rejected its arguments");
             return out.toArray(JAVA_BYTE);
         }
     }

@@ -381,13 +381,15 @@ __global__ void __launch_bounds__(192, 1) k_chain(int iters, int ks, int nload, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *slot;
     const int spin_epi = flags & 1, spin_iss = flags & 2;
+    const int freerun = flags & 4;   // issuer never waits for the hand-back: pure MMA + commit throughput
+    const int selfwait = flags & 8;  // issuer waits for its own commit (full[q]) each round: commit -> visible latency
     if (warp == 1) {
         const uint64_t ad = desc(s32(sA), 128, 1024), bd = desc(s32(sB), 128, 1024);
         constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         long long t0 = clock64();
         for (int i = 0; i < iters; i++) {
             const int q = i % nacc;
-            mb_wait(bar0 + 32 + 8 * q, ((i / nacc) & 1) ^ 1, spin_iss);
+            if (!freerun && !selfwait) mb_wait(bar0 + 32 + 8 * q, ((i / nacc) & 1) ^ 1, spin_iss);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 for (int s = 0; s < ks; s++) {
@@ -399,15 +401,21 @@ __global__ void __launch_bounds__(192, 1) k_chain(int iters, int ks, int nload, 
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * q) : "memory");
             }
             __syncwarp();
+            if (selfwait) mb_wait(bar0 + 8 * q, (i / nacc) & 1, spin_iss);
         }
-        // drain: wait until the last round of every accumulator came back
-        for (int q = 0; q < nacc; q++) {
-            const int rounds = (iters - q + nacc - 1) / nacc;  // rounds accumulator q went through
-            mb_wait(bar0 + 32 + 8 * q, (rounds & 1) ^ 1, 0);
+        // drain: wait until the last round of every accumulator came back (free-running: until the last commit fired)
+        if (freerun || selfwait) {
+            const int q = (iters - 1) % nacc;
+            mb_wait(bar0 + 8 * q, ((iters - 1) / nacc) & 1, 0);
+        } else {
+            for (int q = 0; q < nacc; q++) {
+                const int rounds = (iters - q + nacc - 1) / nacc;  // rounds accumulator q went through
+                mb_wait(bar0 + 32 + 8 * q, (rounds & 1) ^ 1, 0);
+            }
         }
         long long t1 = clock64();
         if (lane == 0) clk_out[blockIdx.x] = t1 - t0;
-    } else if (warp >= 2) {
+    } else if (warp >= 2 && !freerun && !selfwait) {
         const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t sink = 0;
         for (int i = 0; i < iters; i++) {
@@ -450,7 +458,8 @@ static int run_chain()
     struct Cfg { int ks, nload, nacc, flags; };
     const Cfg cfgs[] = {{1, 0, 1, 0}, {4, 0, 1, 0}, {1, 0, 1, 1}, {1, 0, 1, 2}, {1, 0, 1, 3}, {1, 1, 1, 0}, {1, 4, 1, 0}, {4, 4, 1, 0},
                         {4, 0, 4, 0}, {4, 1, 4, 0}, {4, 2, 4, 0}, {4, 3, 4, 0}, {4, 4, 4, 0}, {4, 4, 4, 1}, {4, 4, 4, 3}, {4, 0, 2, 0}, {4, 2, 2, 0},
-                        {2, 0, 4, 0}, {2, 2, 4, 0}, {2, 4, 4, 0}, {1, 0, 4, 0}, {1, 4, 4, 0}};
+                        {2, 0, 4, 0}, {2, 2, 4, 0}, {2, 4, 4, 0}, {1, 0, 4, 0}, {1, 4, 4, 0},
+                        {1, 0, 4, 4}, {4, 0, 4, 4}, {1, 0, 1, 8}, {4, 0, 1, 8}, {1, 0, 1, 10}, {4, 0, 4, 8}};
     for (const Cfg &c : cfgs) {
         for (int grid : {1, 148}) {
             cudaMemset(d, 0, 2048 * 8);
@@ -460,8 +469,9 @@ static int run_chain()
             cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
             long long mx = 0;
             for (int b = 0; b < grid; b++) mx = h[b] > mx ? h[b] : mx;
-            printf("chain: ks=%d nload=%d nacc=%d spin(epi=%d,iss=%d) grid=%3d: %.1f clk per round (MMA alone %d)\n", c.ks, c.nload, c.nacc,
-                   c.flags & 1, (c.flags >> 1) & 1, grid, (double)mx / iters, c.ks * 64);
+            printf("chain: ks=%d nload=%d nacc=%d spin(epi=%d,iss=%d)%s%s grid=%3d: %.1f clk per round (MMA alone %d)\n", c.ks, c.nload, c.nacc,
+                   c.flags & 1, (c.flags >> 1) & 1, (c.flags & 4) ? " free-running" : "", (c.flags & 8) ? " issuer waits its own commit" : "",
+                   grid, (double)mx / iters, c.ks * 64);
         }
     }
     return 0;
@@ -591,7 +601,9 @@ int main(int argc, char **argv)
         CK(cudaEventElapsedTime(&ms_umma, e0, e1));
         float ms_k = 0;
         CK(cudaEventElapsedTime(&ms_k, k0, k1));
-        printf("umma search run %d: pack+search+merge %.3f ms, k_umma_search alone %.3f ms   dbg=%u status=%d\n", r, ms_umma, ms_k, dbg, *status_h);
+        const long long clk = (long long)status_h[2] | ((long long)status_h[3] << 31);
+        printf("umma search run %d: pack+search+merge %.3f ms, k_umma_search alone %.3f ms   dbg=%u status=%d   CTA 0 issuer: %lld clk (%.3f GHz)\n", r,
+               ms_umma, ms_k, dbg, *status_h, clk, ms_k > 0 ? clk / (ms_k * 1e6) : 0.0);
     }
     CK(cudaMemcpy(best_umma.data(), w.best, 4 * g.NR, cudaMemcpyDeviceToHost));
     double evals = (double)g.NR * (double)g.ND;
