@@ -346,7 +346,8 @@ def run_ours(args):
     handle = fic.Handle(local)
     handle.set_engine({"auto": fic.FIC_ENGINE_AUTO, "direct": fic.FIC_ENGINE_DIRECT, "umma": fic.FIC_ENGINE_UMMA}[args.engine])
     handle.set_umma_kind({"auto": fic.FIC_UMMA_KIND_AUTO, "i8": fic.FIC_UMMA_KIND_I8, "f16": fic.FIC_UMMA_KIND_F16}[args.mma])
-    mma = "i8" if (B == 16 or (args.mma == "i8" and not args.rgb)) else "f16"   # what the library runs (B = 16 has no f16 variant, RGB no i8 one)
+    # what the library runs: RGB has a kind::f16 path only; grey B = 16 a kind::i8 path only
+    mma = "f16" if args.rgb else ("i8" if (B == 16 or args.mma == "i8") else "f16")
     stream = torch.cuda.Stream(dev)   # library work, NCCL ordering and the timing events all use this stream
     torch.cuda.set_stream(stream)
     handle.set_stream(stream.cuda_stream)
@@ -439,10 +440,18 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     e2e_ms, _, _, _, e2e_launches = timed(step_e2e, args.steps, False)
-    e2e_u8_ms = None
+
+    def lib_stages():
+        """The library's own device-side event stamps of the last host-buffer call (copies included)."""
+        tt = handle.timings()
+        return {"h2d": tt.h2d_ms, "pool": tt.pool_ms, "search": tt.search_ms, "solve": tt.solve_ms, "d2h": tt.d2h_ms, "total": tt.total_ms}
+
+    e2e_stages = lib_stages() if world == 1 else None
+    e2e_u8_ms = e2e_u8_stages = None
     if world == 1 and not args.iso:
         step_e2e_u8()
         e2e_u8_ms, _, _, _, _ = timed(step_e2e_u8, args.steps, False)
+        e2e_u8_stages = lib_stages()
 
     if world > 1:
         agg = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -522,10 +531,13 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": roofline,
     }
+    if e2e_stages is not None:
+        line["e2e"]["device_stage_ms"] = e2e_stages   # ms_per_step above is the host clock around the call
     if e2e_u8_ms is not None:
         line["e2e_u8"] = {"value": evals / (e2e_u8_ms / args.steps * 1e-3) / 1e9, "unit": "Gevals/s", "ms_per_step": e2e_u8_ms / args.steps,
                           "h2d_bytes_per_step": size * size * C, "d2h_bytes_per_step": NR * 8 * S,
-                          "entry": "fic_encode_grey_u8 / fic_encode_rgb_planes: 8-bit planes in, the same outputs"}
+                          "entry": "fic_encode_grey_u8 / fic_encode_rgb_planes: 8-bit planes in, the same outputs",
+                          "device_stage_ms": e2e_u8_stages}
     if world == 1:
         # verification leg (untimed part of the contract): the GPU decoder reconstructs the image from the
         # quantised codes just produced; PSNR against the source is what fractal coding reaches on this content
@@ -537,12 +549,34 @@ def run_ours(args):
         t0 = time.perf_counter()
         dec, avg_err, iters = handle.decode(q_host, size, size, B, wk, mode, out=h_dec.numpy())
         t_dec = time.perf_counter() - t0
+        dev_ms = handle.timings().total_ms
         du = dec.view(np.uint32)
         rec = (np.stack([(du >> 16) & 0xFF, (du >> 8) & 0xFF, du & 0xFF], 0) if args.rgb else ((du >> 16) & 0xFF)).astype(np.float64)
         mse = float(np.mean((rec - plane.astype(np.float64)) ** 2))
         line["decode"] = {"iterations": int(iters), "avg_error": float(avg_err), "psnr_db": 10 * np.log10(255.0 ** 2 / max(mse, 1e-12)),
-                          "ms_total_host_clock": t_dec * 1e3, "device_ms": handle.timings().total_ms,
-                          "mpixel_per_s_per_sweep": size * size * iters / max(handle.timings().total_ms, 1e-9) / 1e3}
+                          "ms_total_host_clock": t_dec * 1e3, "device_ms": dev_ms, "entry": "fic_decode: codes from the host, int32 ARGB image to the host",
+                          "mpixel_per_s_per_sweep": size * size * iters / max(dev_ms, 1e-9) / 1e3}
+        if not args.iso:
+            # the same decode with 8-bit planes out (a quarter of the download) and with device-resident codes and image
+            h_pl = torch.empty((C, size, size), dtype=torch.uint8).pin_memory()
+            pl_out = h_pl.numpy() if args.rgb else h_pl.numpy().reshape(size, size)
+            handle.decode_u8(q_host, size, size, B, wk, mode, out=pl_out)
+            out8, avg8, it8 = handle.decode_u8(q_host, size, size, B, wk, mode, out=pl_out)
+            u8_ms = handle.timings().total_ms
+            d_out = torch.empty((C, size, size), dtype=torch.uint8, device=dev)
+            handle.decode_planes_dev(d_q.data_ptr(), size, size, B, wk, mode, d_out.data_ptr())
+            avgd, itd = handle.decode_planes_dev(d_q.data_ptr(), size, size, B, wk, mode, d_out.data_ptr())
+            dev_only_ms = handle.timings().total_ms
+            same = bool((out8.reshape(C, size, size) == rec.astype(np.uint8).reshape(C, size, size)).all()
+                        and (d_out.cpu().numpy() == out8.reshape(C, size, size)).all() and it8 == iters and itd == iters
+                        and float(avg8) == float(avg_err) and float(avgd) == float(avg_err))
+            sweep_bytes = 3.25 * size * size * C + 12.0 * NR   # algorithmic bytes of one decoder sweep
+            line["decode"].update({
+                "device_ms_u8_planes_to_host": u8_ms, "device_ms_device_resident": dev_only_ms, "all_entries_agree": same,
+                "sweep_us_device_resident": dev_only_ms * 1e3 / max(int(iters), 1),
+                "sweep_hbm_roofline_frac": (sweep_bytes / (float(pk["hbm_gbs"]) * 1e9)) / (dev_only_ms * 1e-3 / max(int(iters), 1)),
+                "sweep_roofline_note": "3.25*W*H*C + 12*NR bytes per sweep / measured copy bandwidth, against the whole device-resident call "
+                                       "(code dequantisation, image fill and the skipped sweeps of the batch included) / iterations"})
     rc = 0
     if world == 1 and not args.no_lena:
         handle.set_stream(None)

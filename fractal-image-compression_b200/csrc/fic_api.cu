@@ -280,7 +280,7 @@ static int pick_engine(fic_handle *h, const Geom &g, int64_t j0, int64_t j1, int
     *engine = FIC_ENGINE_DIRECT;
     if (h->engine_opt == FIC_ENGINE_UMMA) {
         if (!umma_applicable(g))
-            return set_err(h, FIC_E_ARG, "tcgen05 search needs widthKernel == domain blocks per width == per height (and, for RGB, blockgroesse 4 or 8 without isometries)");
+            return set_err(h, FIC_E_ARG, "tcgen05 search needs widthKernel == domain blocks per width == per height (and no isometries for RGB)");
         *engine = FIC_ENGINE_UMMA;
     } else if (h->engine_opt == FIC_ENGINE_FUSED) {
         if (!fused_encode_applicable(g)) return set_err(h, FIC_E_ARG, "the fused encode needs widthKernel <= 16 and no isometries");

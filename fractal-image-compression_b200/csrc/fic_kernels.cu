@@ -967,11 +967,15 @@ __device__ __forceinline__ void sweep_fold(unsigned long long *st, unsigned long
 __device__ __forceinline__ void sweep_tail(const SweepCtl &ctl, unsigned long long local)
 {
     if (!ctl.st) return;
+    __shared__ unsigned long long s_part[8];  // blockDim.x == 256
     for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(ctl.st, local);
-    if (!ctl.finish) return;
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
     __syncthreads();
     if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
+        for (int wv = 0; wv < 8; wv++) tot += s_part[wv];
+        if (tot) atomicAdd(ctl.st, tot);
+        if (!ctl.finish) return;
         __threadfence();
         uint32_t *w = (uint32_t *)ctl.st;
         if (atomicAdd(w + ST_TICKET, 1u) == gridDim.x - 1) {
@@ -1002,9 +1006,9 @@ k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, ui
     unsigned long long *const acc = ctl.st;
     int qw = g.W / 2;
     int64_t quads = (int64_t)qw * (g.H / 2);
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long local = 0;
-    if (t < quads) {
+    // grid-stride: a bounded number of CTAs, so that the sweep's sum costs one atomic per CTA, not per warp
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < quads; t += (int64_t)gridDim.x * blockDim.x) {
         int qy = (int)(t / qw), qx = (int)(t - (int64_t)qy * qw);
         int x = 2 * qx, y = 2 * qy;
         int xr = x / g.B, yr = y / g.B;
@@ -1047,7 +1051,7 @@ k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, ui
             *(uchar2 *)(pi + g.W) = make_uchar2(v01, v11);
             if (dec_out) dec_out[c * planeD + (int64_t)qy * g.sw + qx] = (uint8_t)dec_tap4(v00, v10, v01, v11, x, g.H, C == 3);
         }
-        local = (unsigned long long)(e[0] + e[1] + e[2] + e[3]);
+        local += (unsigned long long)(e[0] + e[1] + e[2] + e[3]);
         if (perr) {
             int32_t *pe = perr + j * g.n + ry * g.B + rx;
             pe[0] = e[0];
@@ -1071,9 +1075,8 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
     if (sweep_done(ctl)) return;
     const int sw8 = g.W / 8;
     const int64_t strips = (int64_t)sw8 * (g.H / 2);
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long local = 0;
-    if (t < strips) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < strips; t += (int64_t)gridDim.x * blockDim.x) {
         const int qy = (int)(t / sw8), s8 = (int)(t - (int64_t)qy * sw8);
         const int y = 2 * qy, x0 = 8 * s8;
         constexpr int S = C == 1 ? 3 : 5;
@@ -1167,12 +1170,14 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
     sweep_tail(ctl, local);
 }
 
+constexpr int64_t kSweepCtas = 148 * 8;  // one wave of 256-thread CTAs at full occupancy: grid-stride beyond that
+
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out, const float *d_code,
                         const int32_t *d_off, const Geom &g, const SweepCtl &ctl, int32_t *d_perr, cudaStream_t s)
 {
     if (g.W % 8 == 0 && g.n_iso == 1) {  // the isometry extension uses the quad kernel (per-pixel gather)
         int64_t strips = (int64_t)(g.W / 8) * (g.H / 2);
-        unsigned blocks = (unsigned)((strips + 255) / 256);
+        unsigned blocks = (unsigned)((strips + 255) / 256 < kSweepCtas ? (strips + 255) / 256 : kSweepCtas);
         if (g.C == 1)
             k_decode_sweep_v8<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
         else
@@ -1180,7 +1185,7 @@ int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_
         return 1;
     }
     int64_t quads = (int64_t)(g.W / 2) * (g.H / 2);
-    unsigned blocks = (unsigned)((quads + 255) / 256);
+    unsigned blocks = (unsigned)((quads + 255) / 256 < kSweepCtas ? (quads + 255) / 256 : kSweepCtas);
     if (g.C == 1)
         k_decode_sweep<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
     else

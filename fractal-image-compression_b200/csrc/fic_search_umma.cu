@@ -97,13 +97,14 @@ constexpr int kRowsPerSB = kBlockM * kAccs;
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kChunksPerTile = kTileN / 32;
-constexpr int kBoundBytes = kChunksPerTile * 2 * 4 + 16;  // (rhi, rlo) f32 per 32-column chunk + tile flags (u32 + pad)
-// Flag lists of a (row, unit): kListsOf(EPI) lists of kCapOf(EPI) entries each, one list per epilogue warp that scans
-// the row -- two (column halves, a historical split) for the accumulator-per-warp mapping, four (one per 32-column
-// chunk of a tile) for the chunk-per-warp mapping.  Same footprint either way.
-constexpr int kFlagBytes = 4 * (4 + 8 * 16);         // per (row, unit): list lengths + entries, both mappings fit
-__host__ __device__ constexpr int kListsOf(int epi) { return epi == 1 ? 4 : 2; }
-__host__ __device__ constexpr int kCapOf(int epi) { return epi == 1 ? 16 : 32; }
+// per tile, behind the operand: (rhi, rlo) f32 per 32-column chunk, tile flags (u32 + pad), and per chunk an upper bound of
+// the operand rows' Euclidean norms (RGB at blockgroesse 16 only: bounds the rounding of the float covariances)
+constexpr int kBoundBytes = kChunksPerTile * 2 * 4 + 16 + kChunksPerTile * 4;
+constexpr int kNormOff = kChunksPerTile * 2 * 4 + 16;     // offset of the norms inside the bounds area
+// Flag lists of a (row, unit): two lists (column halves of the tiles, a historical split) of 32 entries each.
+constexpr int kFlagBytes = 4 * (4 + 8 * 16);         // per (row, unit): list lengths + entries (with slack)
+__host__ __device__ constexpr int kListsOf(int) { return 2; }
+__host__ __device__ constexpr int kCapOf(int) { return 32; }
 constexpr float kOneMinusEps = 1.0f - 1.9073486328125e-06f;  // 1 - 2^-19 (applied to the squared score)
 
 // Operand geometry of one (block size, MMA kind) pair.  F16 = false: kind::i8, two s8 digits per
@@ -114,6 +115,7 @@ struct Cfg;
 template <>
 struct Cfg<8, false> {
     static constexpr int n = 64;
+    static constexpr int NB = 4;     // 128-row accumulator blocks per super-block (A operand resident in shared memory)
     static constexpr bool KSPLIT = false;
     static constexpr int KS_A = 3;   // physical A K-slices: r[0:32] r[32:64] [rmean rmean 0..]
     static constexpr int KS_B = 5;   // h[0:32] h[32:64] l[0:32] l[32:64] [-alpha 0..]
@@ -125,6 +127,7 @@ struct Cfg<8, false> {
 template <>
 struct Cfg<4, false> {
     static constexpr int n = 16;
+    static constexpr int NB = 4;     // 128-row accumulator blocks per super-block (A operand resident in shared memory)
     static constexpr bool KSPLIT = false;
     static constexpr int KS_A = 2;   // [r r] [rmean 0..]
     static constexpr int KS_B = 2;   // [h l] [-alpha 0..]
@@ -136,6 +139,7 @@ struct Cfg<4, false> {
 template <>
 struct Cfg<16, false> {
     static constexpr int n = 256;
+    static constexpr int NB = 4;     // 128-row accumulator blocks per super-block (A operand resident in shared memory)
     // The A super-block (144 KB) leaves room for 72 KB of domain operands, not for two whole 68 KB tiles.  A tile
     // therefore travels as two parts, P0 = [h (8 slices) | -alpha (1 slice)] + the tile's bounds and P1 = [l (8
     // slices)], through a ring of two 36 KB slots: the copy of one part overlaps the MMAs on the other, and P1 is
@@ -152,6 +156,7 @@ struct Cfg<16, false> {
 template <>
 struct Cfg<8, true> {
     static constexpr int n = 64;
+    static constexpr int NB = 4;     // 128-row accumulator blocks per super-block (A operand resident in shared memory)
     static constexpr bool KSPLIT = false;
     static constexpr int KS_A = 4;   // (r - rmean)[0:64] as binary16: 4 slices of 16 elements
     static constexpr int KS_B = 4;   // (d - dmean)[0:64] as binary16
@@ -163,11 +168,30 @@ struct Cfg<8, true> {
 template <>
 struct Cfg<4, true> {
     static constexpr int n = 16;
+    static constexpr int NB = 4;     // 128-row accumulator blocks per super-block (A operand resident in shared memory)
     static constexpr bool KSPLIT = false;
     static constexpr int KS_A = 1;
     static constexpr int KS_B = 1;
     static constexpr int NS = 1;
     static constexpr int NSTAGE = 8;
+    __host__ __device__ static constexpr int amap(int s) { return s; }
+    __host__ __device__ static constexpr bool is_l_slice(int) { return false; }
+};
+
+template <>
+struct Cfg<16, true> {
+    // RGB at blockgroesse 16 (see "RGB operands"): K = 256 binary16 = 16 K-slices.  The A operand of 128 rows is 64 KB,
+    // so a super-block holds TWO accumulator blocks (256 rows, 128 KB) and only two of the four TMEM accumulators are
+    // used -- with 16 K-slices per accumulator (1024 clocks) a ring of two hides the hand-over.  The domain tile
+    // (64 KB) travels as two parts of 8 K-slices through two 32 KB slots, like Cfg<16, false>; both parts always exist.
+    static constexpr int n = 256;
+    static constexpr int NB = 2;
+    static constexpr bool KSPLIT = true;
+    static constexpr int KS_P0 = 8, KS_P1 = 8;
+    static constexpr int KS_A = 16;
+    static constexpr int KS_B = 16;
+    static constexpr int NS = 16;
+    static constexpr int NSTAGE = 2;
     __host__ __device__ static constexpr int amap(int s) { return s; }
     __host__ __device__ static constexpr bool is_l_slice(int) { return false; }
 };
@@ -184,7 +208,8 @@ struct Lay {
     using C = Cfg<B, F16>;
     static constexpr int SBO_A = C::KS_A * 256;
     static constexpr int A_BLOCK_BYTES = (kBlockM / 8) * SBO_A;
-    static constexpr int A_SB_BYTES = kAccs * A_BLOCK_BYTES;
+    static constexpr int ROWS_SB = C::NB * kBlockM;            // range rows of one super-block
+    static constexpr int A_SB_BYTES = C::NB * A_BLOCK_BYTES;
     // Domain tile blob in global memory.  Unsplit: [operand, SBO_B between 8-row groups][bounds + flag].
     // Split (Cfg::KSPLIT): [part P0, SBO_B][bounds + flag][part P1, SBO_P1].  B_OP_BYTES is the offset of the bounds.
     static constexpr int KS0 = ksplit_p0<C>();
@@ -414,8 +439,8 @@ k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ 
     constexpr int n = Cfg<B, F16>::n;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows_padded) return;
-    int64_t sb = i / kRowsPerSB;
-    int rr = (int)(i % kRowsPerSB);
+    int64_t sb = i / L::ROWS_SB;
+    int rr = (int)(i % L::ROWS_SB);
     int blk = rr / kBlockM, row = rr % kBlockM;
     uint8_t *rowp = opA + sb * L::A_SB_BYTES + blk * L::A_BLOCK_BYTES + (row >> 3) * L::SBO_A + (row & 7) * 16;
     constexpr int NCH = Cfg<B, F16>::KS_A * 2;
@@ -517,7 +542,18 @@ __global__ void k_umma_sortkeys_rgb(const int32_t *__restrict__ dsum, int n, int
 }
 
 // RGB twin of k_umma_pack_domains<B, true>: the operand row holds gD as binary16 (zeros when vD == 0), pos_info =
-// {domain, vD, 0, 0}; the refine step re-reads the operand row itself, so no raw copy is kept.
+// {domain, vD, 0, 0}; the refine step re-reads the operand row itself, so no raw copy is kept.  B = 16: the row's 32
+// 16-byte pieces are split over the tile's two parts (Cfg<16, true>), and every chunk also records an upper bound of
+// its rows' Euclidean norms ||gD||, from which the search kernel bounds the rounding of the float covariances.
+template <int B>
+__device__ __forceinline__ uint8_t *rgb_dom_piece(uint8_t *blob, int row, int c)
+{
+    using L = Lay<B, true>;
+    constexpr int NCH0 = L::KS0 * 2;  // 16-byte pieces of a row in part P0 (all of them unless the tile is K-split)
+    if (!Cfg<B, true>::KSPLIT || c < NCH0) return blob + (row >> 3) * L::SBO_B + (row & 7) * 16 + c * 128;
+    return blob + L::P0_BYTES + (row >> 3) * L::SBO_P1 + (row & 7) * 16 + (c - NCH0) * 128;
+}
+
 template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_pack_domains_rgb(const uint16_t *__restrict__ dec3, const int32_t *__restrict__ dsum,
@@ -531,43 +567,55 @@ k_umma_pack_domains_rgb(const uint16_t *__restrict__ dec3, const int32_t *__rest
     const int row = (int)(pos % kTileN);
     const int64_t sp = sweep_to_sorted(pos, mult, ntiles * kChunksPerTile);
     uint8_t *blob = opB + tile * L::B_TILE_BYTES;
-    uint8_t *rowp = blob + (row >> 3) * L::SBO_B + (row & 7) * 16;
-    constexpr int NCH = n / 8;  // 16-byte chunks (8 binary16) per row
-    float rsd_hi = 0.0f, rsd_lo = __int_as_float(0x7f800000);
+    constexpr int NCH = n / 8;  // 16-byte pieces (8 binary16) per row
+    float rsd_hi = 0.0f, rsd_lo = __int_as_float(0x7f800000), norm = 0.0f;
     if (sp >= g.ND) {
 #pragma unroll
-        for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
+        for (int c = 0; c < NCH; c++) *(uint4 *)rgb_dom_piece<B>(blob, row, c) = make_uint4(0, 0, 0, 0);
         pos_dom[pos] = -1;
         pos_info[pos] = make_int4(-1, 0, 0, 0);
     } else {
         const int64_t j = perm[sp];
         const int gx = (int)(j % g.dpw), gy = (int)(j / g.dpw);
         // dec3 = R + G + B of the decimated planes (k_sum_planes); a block row starts at a multiple of B / 4
-        // pixels, so B = 8 reads pixel pairs (4-byte loads)
+        // pixels: B = 8 reads pixel pairs (4-byte loads), B = 16 groups of four (8-byte loads)
         const uint16_t *p = dec3 + (int64_t)(gy * g.step) * g.sw + gx * g.step;
         int dm[3];
         const int vd = rgb_dom_vd(dsum, g.ND, j, n, dm);
         const int dmsum = dm[0] + dm[1] + dm[2];
+        uint32_t sumsq = 0;  // sum gD^2 <= 256 * 765^2 = 1.5e8: exact in u32
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             int dv[8];
-            if (B == 8) {
+            const int k0 = c * 8;  // first pixel of the piece: row k0 / B of the block, column k0 % B
+            const uint16_t *q = p + (int64_t)(k0 / B) * g.sw + (k0 % B);
+            if (B == 16) {
+#pragma unroll
+                for (int e = 0; e < 8; e += 4) {
+                    const uint2 w = __ldg((const uint2 *)(q + e));
+                    dv[e] = (int)(w.x & 0xffffu); dv[e + 1] = (int)(w.x >> 16);
+                    dv[e + 2] = (int)(w.y & 0xffffu); dv[e + 3] = (int)(w.y >> 16);
+                }
+            } else if (B == 8) {
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
-                    const uint32_t w = __ldg((const uint32_t *)(p + (int64_t)c * g.sw + e));  // row c of the block
+                    const uint32_t w = __ldg((const uint32_t *)(q + e));
                     dv[e] = (int)(w & 0xffffu);
                     dv[e + 1] = (int)(w >> 16);
                 }
             } else {
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
-                    const int k = c * 8 + e;
+                    const int k = k0 + e;
                     dv[e] = (int)__ldg(p + (int64_t)(k / B) * g.sw + (k % B));
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 8; e++) dv[e] = vd != 0 ? dv[e] - dmsum : 0;
-            *(uint4 *)(rowp + c * 128) =
+            for (int e = 0; e < 8; e++) {
+                dv[e] = vd != 0 ? dv[e] - dmsum : 0;
+                sumsq += (uint32_t)(dv[e] * dv[e]);
+            }
+            *(uint4 *)rgb_dom_piece<B>(blob, row, c) =
                 make_uint4(pack_h2(dv[0], dv[1]), pack_h2(dv[2], dv[3]), pack_h2(dv[4], dv[5]), pack_h2(dv[6], dv[7]));
         }
         pos_dom[pos] = (int32_t)j;
@@ -578,30 +626,34 @@ k_umma_pack_domains_rgb(const uint16_t *__restrict__ dec3, const int32_t *__rest
             rsd_hi = r * (1.0f + 4.76837158203125e-07f);  // >= (1 / vD) * (1 + 2^-22), see k_umma_pack_domains
             rsd_lo = r * (1.0f - 4.76837158203125e-07f);
         }
+        norm = __fsqrt_ru((float)sumsq) * (1.0f + 2.384185791015625e-07f);  // >= ||gD||_2
     }
     for (int o = 16; o > 0; o >>= 1) {
         rsd_hi = fmaxf(rsd_hi, __shfl_xor_sync(0xffffffffu, rsd_hi, o));
         rsd_lo = fminf(rsd_lo, __shfl_xor_sync(0xffffffffu, rsd_lo, o));
+        norm = fmaxf(norm, __shfl_xor_sync(0xffffffffu, norm, o));
     }
     if ((threadIdx.x & 31) == 0) {
         if (rsd_hi == 0.0f) rsd_lo = 0.0f;
         *(float2 *)(blob + L::B_OP_BYTES + (row >> 5) * 8) = make_float2(rsd_hi, rsd_lo);
+        *(float *)(blob + L::B_OP_BYTES + kNormOff + (row >> 5) * 4) = norm;
     }
-    if (threadIdx.x == 0) *(uint4 *)(blob + L::B_OP_BYTES + kChunksPerTile * 8) = make_uint4(0, 0, 0, 0);
+    // tile flag: a K-split tile always has its second part (there is no "all low digits zero" case for binary16)
+    if (threadIdx.x == 0) *(uint4 *)(blob + L::B_OP_BYTES + kChunksPerTile * 8) = make_uint4(Cfg<B, true>::KSPLIT ? 1u : 0u, 0, 0, 0);
 }
 
-// RGB twin of k_umma_pack_ranges<B, true>: gR as binary16.
+// RGB twin of k_umma_pack_ranges<B, true>: gR as binary16; nRout (optional) receives an upper bound of ||gR||_2.
 template <int B>
 __global__ void __launch_bounds__(128)
 k_umma_pack_ranges_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ rsum, uint8_t *__restrict__ opA,
-                       int32_t *__restrict__ vRout, Geom g, int64_t j0, int64_t j1, int64_t rows_padded)
+                       int32_t *__restrict__ vRout, float *__restrict__ nRout, Geom g, int64_t j0, int64_t j1, int64_t rows_padded)
 {
     using L = Lay<B, true>;
     constexpr int n = B * B;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows_padded) return;
-    int64_t sb = i / kRowsPerSB;
-    int rr = (int)(i % kRowsPerSB);
+    int64_t sb = i / L::ROWS_SB;
+    int rr = (int)(i % L::ROWS_SB);
     int blk = rr / kBlockM, row = rr % kBlockM;
     uint8_t *rowp = opA + sb * L::A_SB_BYTES + blk * L::A_BLOCK_BYTES + (row >> 3) * L::SBO_A + (row & 7) * 16;
     constexpr int NCH = n / 8;
@@ -610,6 +662,7 @@ k_umma_pack_ranges_rgb(const uint8_t *__restrict__ src, const int32_t *__restric
 #pragma unroll
         for (int c = 0; c < NCH; c++) *(uint4 *)(rowp + c * 128) = make_uint4(0, 0, 0, 0);
         vRout[i] = 0;
+        if (nRout) nRout[i] = 0.0f;
         return;
     }
     const int xr = (int)(j % g.rpw), yr = (int)(j / g.rpw);
@@ -622,6 +675,7 @@ k_umma_pack_ranges_rgb(const uint8_t *__restrict__ src, const int32_t *__restric
         rmsum += rs / n;
         vR += rs - n * (rs / n);
     }
+    uint32_t sumsq = 0;
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
         int rv[8];
@@ -630,11 +684,13 @@ k_umma_pack_ranges_rgb(const uint8_t *__restrict__ src, const int32_t *__restric
             const int k = c * 8 + e;
             const uint8_t *q = p + (int64_t)(k / B) * g.W + (k % B);
             rv[e] = (int)q[0] + (int)q[plane] + (int)q[2 * plane] - rmsum;
+            sumsq += (uint32_t)(rv[e] * rv[e]);
         }
         *(uint4 *)(rowp + c * 128) =
             make_uint4(pack_h2(rv[0], rv[1]), pack_h2(rv[2], rv[3]), pack_h2(rv[4], rv[5]), pack_h2(rv[6], rv[7]));
     }
     vRout[i] = vR;
+    if (nRout) nRout[i] = __fsqrt_ru((float)sumsq) * (1.0f + 2.384185791015625e-07f);
 }
 
 // ---------------------------------------------------------------- PTX wrappers -------
@@ -791,15 +847,16 @@ constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(
 // DBG (probe builds only): 1 = skip the scoring, 3 = skip the TMEM loads too, 4 = issue the MMAs of the first tile
 // of a unit only (the epilogue alone), 8 = count the cycles an epilogue warp spends in each phase (into `dump`).  DUMP: write every
 // accumulator to `dump` (the probe's exactness check).  The product runs <B, 0, false>.
-// EPI selects the epilogue mapping.  0: warp e owns accumulator e / 4 (one visit of four chunk loads per tile).
-// 1: warp e owns 32-column chunk e / 4 of EVERY accumulator: the four warps of an SM sub-partition drain the oldest
-// accumulator together, one tcgen05.ld each, so it goes back to the MMA issuer after one load time instead of four
-// loads and three chunk evaluations; a thread then follows four range rows (one per accumulator), and the four warps
-// that scan a row share its lower bound through shared memory.
+// EPI selects how an epilogue warp walks its accumulator (warp e owns lane quarter e % 4 of accumulator e / 4 in every
+// variant).  0: load a 32-column chunk, evaluate it, load the next.  2 (kind::f16): software-pipelined -- the load of
+// the next chunk is issued behind the first level of the current chunk's max tree.  3 (kind::f16): as 2, and the four
+// flag tests wait until the accumulator has been handed back.  (A fourth mapping -- every warp takes one chunk of
+// EVERY accumulator, so that the oldest accumulator is drained by four warps at once -- handed accumulators back
+// soonest and still lost on every configuration to its four waits per tile; profiles/README.md.)
 template <int B, bool F16, int DBG, bool DUMP, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
-              int2 *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, uint32_t *__restrict__ row_lb, int n_sb,
+              const float *__restrict__ nRarr, int2 *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, uint32_t *__restrict__ row_lb, int n_sb,
               int n_chunks, int ntiles, int iso_shift, int64_t rows_padded, int32_t *__restrict__ dump, int64_t dump_ld, volatile int *status,
               uint32_t lbo_bytes_a, uint32_t sbo_bytes_a, uint32_t lbo_bytes_b, uint32_t sbo_bytes_b)
 {
@@ -832,7 +889,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         }
         for (int q = 0; q < kAccs; q++) {
             mbar_init(BAR_T_FULL(q), 1);
-            mbar_init(BAR_T_EMPTY(q), EPI == 1 ? kEpiWarps : kEpiWarps / kAccs);  // every warp that reads the accumulator
+            mbar_init(BAR_T_EMPTY(q), kEpiWarps / kAccs);  // the 4 lane quarters of the accumulator
         }
         mbar_init(BAR_A_FULL, 1);
         mbar_init(BAR_A_EMPTY, 1);
@@ -911,15 +968,16 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     // have read it (commit), so that the next copy overlaps the MMAs on part P1 / the next tile
                     const uint64_t b0 = make_desc(smem_u32(sB + stage * L::SLOT_BYTES), 128, L::SBO_B);
 #pragma unroll
-                    for (int q = 0; q < kAccs; q++) {
+                    for (int q = 0; q < C::NB; q++) {
                         mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ 1, status, 5);
                         tc_fence_after();
                         if (elected) {
 #pragma unroll
                             for (int s = 0; s < L::KS0; s++) {
                                 if ((DBG & 4) && t != t0) continue;  // probe only: epilogue without the tensor pipe
-                                const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + s * 256) >> 4);  // r slice s; s = 8: rmean
-                                tc_mma_i8(tmem_base + q * kTileN, ad, b0 + (uint64_t)((s * 256) >> 4), kIdesc, s > 0 ? 1u : 0u);
+                                const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + s * 256) >> 4);  // A slice s (kind::i8: s = 8 is rmean)
+                                if (F16) tc_mma_f16(tmem_base + q * kTileN, ad, b0 + (uint64_t)((s * 256) >> 4), kIdescF16, s > 0 ? 1u : 0u);
+                                else tc_mma_i8(tmem_base + q * kTileN, ad, b0 + (uint64_t)((s * 256) >> 4), kIdesc, s > 0 ? 1u : 0u);
                             }
                             if (!has_l) tc_commit(BAR_T_FULL(q));
                         }
@@ -934,13 +992,16 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                         tc_fence_after();
                         const uint64_t b1 = make_desc(smem_u32(sB + stage * L::SLOT_BYTES), 128, L::SBO_P1);
 #pragma unroll
-                        for (int q = 0; q < kAccs; q++) {
+                        for (int q = 0; q < C::NB; q++) {
                             if (elected) {
 #pragma unroll
                                 for (int s = 0; s < C::KS_B - L::KS0; s++) {
                                     if ((DBG & 4) && t != t0) continue;
-                                    const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + s * 256) >> 4);  // r slice s again
-                                    tc_mma_i8(tmem_base + q * kTileN, ad, b1 + (uint64_t)((s * 256) >> 4), kIdesc, 1u);
+                                    // kind::i8: the low digits meet the r slices again; kind::f16: the second half of K
+                                    const int sa = F16 ? L::KS0 + s : s;
+                                    const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + sa * 256) >> 4);
+                                    if (F16) tc_mma_f16(tmem_base + q * kTileN, ad, b1 + (uint64_t)((s * 256) >> 4), kIdescF16, 1u);
+                                    else tc_mma_i8(tmem_base + q * kTileN, ad, b1 + (uint64_t)((s * 256) >> 4), kIdesc, 1u);
                                 }
                                 tc_commit(BAR_T_FULL(q));
                             }
@@ -954,7 +1015,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 }
                 const uint64_t b_desc = b_desc0 + (uint64_t)((stage * L::SLOT_BYTES) >> 4);
 #pragma unroll
-                for (int q = 0; q < kAccs; q++) {
+                for (int q = 0; q < C::NB; q++) {
                     mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ 1, status, 5);
                     tc_fence_after();
                     if (elected) {
@@ -985,8 +1046,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             status[2] = (int)(dt & 0x7fffffff);
             status[3] = (int)(dt >> 31);
         }
-    } else if (warp >= 4 && EPI != 1) {
-        // ===================== epilogue, accumulator per warp =====================
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
         // Warp e: TMEM lane quarter lq = e % 4 (== warp % 4, the quarter this warp may access) of accumulator
         // q = e / 4: one thread = one range row, all 128 domains of a tile.  Per tile a warp makes ONE visit (one
         // t_full wait, four 32-column loads, one hand-back); the four warps of an SM sub-partition own the four
@@ -995,6 +1056,10 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         const int lq = e & 3, q = e >> 2;
         const uint32_t ta = tmem_base + ((uint32_t)(lq * 32) << 16) + q * kTileN;
         uint32_t tf_phase = 0;
+        // RGB at blockgroesse 16: the float covariances (the reference's sequential sum and the tensor core's) may
+        // round once partial sums pass 2^24; see the chunk test below.  Warps of unused accumulators idle.
+        constexpr bool SLACK = B == 16 && F16;
+        const int n_units_mine = q < C::NB ? n_units : 0;
         // DBG & 8 (probe only): per-warp cycle accounting of the epilogue phases.  tcgen05.wait::ld is a
         // scoreboard wait, so the TMEM latency shows up at the first use of the loaded registers ("math").
         uint32_t tk_b = 0, tk_t = 0, tk_l = 0, tk_m = 0, tk_mark = 0;
@@ -1006,7 +1071,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 tk_mark = now;
             }
         };
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        for (int u = blockIdx.x; u < n_units_mine; u += gridDim.x) {
             // Units are ordered chunk-major (u = ch * n_sb + sb): the units of one super-block run in different
             // waves, so the lower bound a row reached in an earlier unit (row_lb, global memory) can seed the
             // later ones -- any earlier bound is a valid bound, a missed one only costs extra flags.
@@ -1014,8 +1079,9 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
             // Running filter state of this thread's row (see the file header).  vR == 0: every candidate
             // scores error 0 and the first one wins (FC:677-678, FC:627) -> never flag.
-            const int64_t row = (int64_t)sb * kRowsPerSB + q * kBlockM + lq * 32 + lane;
+            const int64_t row = (int64_t)sb * L::ROWS_SB + q * kBlockM + lq * 32 + lane;
             const int vR = vRarr[row];
+            const float nR = SLACK ? nRarr[row] : 0.0f;  // >= ||gR||_2 of this row
             RowFilter st;
             st.thresh = (vR == 0) ? __int_as_float(0x7f800000) : -1.0f;
             st.lbmax = 0.0f;
@@ -1045,6 +1111,8 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 // repeats, so it is an L1 hit for all but the first; its latency hides behind the t_full wait.
                 const float4 *gb = (const float4 *)(opB + (int64_t)t * L::B_TILE_BYTES + L::B_OP_BYTES);
                 const float4 bnd01 = __ldg(gb), bnd23 = __ldg(gb + 1);
+                float4 bndn = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // >= ||gD||_2 of the rows of each chunk
+                if (SLACK) bndn = __ldg(gb + 3);
                 tick(tk_b);
                 mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
                 tc_fence_after();
@@ -1170,12 +1238,27 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     }
                     const float rhi = c == 0 ? bnd01.x : (c == 1 ? bnd01.z : (c == 2 ? bnd23.x : bnd23.z));
                     const float rlo = c == 0 ? bnd01.y : (c == 1 ? bnd01.w : (c == 2 ? bnd23.y : bnd23.w));
-                    const float ub = M * rhi;
+                    float Mu = M, Ml = M;
+                    if (SLACK) {
+                        // Every partial sum of sum gR*gD, in any order, is at most ||gR|| ||gD|| (Cauchy-Schwarz).
+                        // Below 2^24 all of them are exact integers: the accumulator IS the reference's kov.  Above,
+                        // a binary32 sum of 256 exact products is within 255 * 2^-24 * ||gR|| ||gD|| of the true value
+                        // when every add rounds to nearest (the reference's sequential sum) and within twice that
+                        // if the tensor core truncates: |accumulator - kov_reference| < 4.6e-5 * ||gR|| ||gD||.  The
+                        // chunk bounds are widened by that much (6e-5: margin for the norms' own rounding).
+                        const float pn = nR * (c == 0 ? bndn.x : (c == 1 ? bndn.y : (c == 2 ? bndn.z : bndn.w)));
+                        if (pn >= 16777216.0f) {
+                            const float sl = pn * 6.0e-5f;
+                            Mu = M + sl;
+                            Ml = fmaxf(M - sl, 0.0f);
+                        }
+                    }
+                    const float ub = Mu * rhi;
                     if (ub > st.thresh) {  // may hold the winner or one of its float ties
                         // the refine step reads two lists per (row, unit), one per column half, as the layout of
                         // the earlier two-warps-per-accumulator mapping had it
                         st.cnt = c < 2 ? cnt0 : cnt1;
-                        st = flag_chunk(st, M * rlo, ub, tie_abs, list0 + (c >> 1) * kCapOf(0), kCapOf(0), t * kChunksPerTile + c, sh_lb, iso_shift ? 1 : 0);
+                        st = flag_chunk(st, Ml * rlo, ub, tie_abs, list0 + (c >> 1) * kCapOf(0), kCapOf(0), t * kChunksPerTile + c, sh_lb, iso_shift ? 1 : 0);
                         if (c < 2) cnt0 = st.cnt;
                         else cnt1 = st.cnt;
                     }
@@ -1188,141 +1271,6 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             flag_cnt[((int64_t)ch * rows_padded + row) * 2 + 1] = cnt1;
             // the row's bound after this unit: seeds its later units and lets the refine step drop stale flags
             if (st.lbmax > 0.0f) atomicMax(row_lb + ((row >> iso_shift) << iso_shift), __float_as_uint(st.lbmax));
-        }
-        if ((DBG & 8) && lane == 0 && dump) {
-            int32_t *o = dump + ((int64_t)blockIdx.x * kEpiWarps + e) * 8;
-            o[0] = (int32_t)((uint32_t)clock() - tk_begin);
-            o[1] = (int32_t)tk_b;
-            o[2] = (int32_t)tk_t;
-            o[3] = (int32_t)tk_l;
-            o[4] = (int32_t)tk_m;
-        }
-    } else if (warp >= 4) {
-        // ===================== epilogue, chunk per warp =====================
-        // Warp e: TMEM lane quarter lq = e % 4 (== warp % 4, the quarter this warp may access) and 32-column chunk
-        // kc = e / 4 of every accumulator.  Per tile a warp visits the four accumulators in the order the issuer
-        // completes them: t_full wait, ONE tcgen05.ld, hand-back, 16 FMNMX3.  The four warps of a sub-partition
-        // issue their loads of an accumulator together, so the accumulator is free again one load time after it
-        // completed.  A thread follows four rows (row q of accumulator q); the four warps that scan a row keep
-        // private thresholds and meet in shared memory only on the rare flag path (flag_chunk, share = 3).
-        const int e = warp - 4;
-        const int lq = e & 3, kc = e >> 2;
-        const uint32_t ta = tmem_base + ((uint32_t)(lq * 32) << 16) + kc * 32;
-        uint32_t tf_phase = 0;
-        uint32_t tk_b = 0, tk_t = 0, tk_l = 0, tk_m = 0, tk_mark = 0;
-        const uint32_t tk_begin = (DBG & 8) ? (uint32_t)clock() : 0u;
-        auto tick = [&](uint32_t &acc) {
-            if (DBG & 8) {
-                const uint32_t now = (uint32_t)clock();
-                acc += now - tk_mark;
-                tk_mark = now;
-            }
-        };
-        const int rq = lq * 32 + lane;  // row within a 128-row block
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            int sb = u % n_sb, ch = u / n_sb;  // chunk-major: see the accumulator-per-warp branch
-            int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
-            const int64_t row0 = (int64_t)sb * kRowsPerSB + rq;  // this thread's rows: row0 + q * kBlockM
-            // The shared bounds of the previous unit are dead once all 16 epilogue warps are here; the chunk-0 warps
-            // seed them with the bound the row reached in earlier units (row_lb; isometry rows share a slot).
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-            if (kc == 0) {
-#pragma unroll
-                for (int q = 0; q < kAccs; q++) {
-                    const int64_t grow = ((row0 + q * kBlockM) >> iso_shift) << iso_shift;
-                    s_lb[q * kBlockM + rq] = ch > 0 ? *(volatile const uint32_t *)(row_lb + grow) : 0u;
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-            float thresh[kAccs], lbmax[kAccs], tie_abs[kAccs];
-            int cnt[kAccs];
-#pragma unroll
-            for (int q = 0; q < kAccs; q++) {
-                const int vR = vRarr[row0 + q * kBlockM];
-                tie_abs[q] = (float)(vR * vR) * 4.76837158203125e-07f;  // vR^2 * 2^-21
-                const float seed = __uint_as_float(s_lb[q * kBlockM + ((rq >> iso_shift) << iso_shift)]);
-                lbmax[q] = seed;
-                // vR == 0: every candidate scores error 0 and the first one wins (FC:677-678, FC:627) -> never flag
-                thresh[q] = (vR == 0) ? __int_as_float(0x7f800000) : (seed > 0.0f ? flag_threshold(seed, tie_abs[q]) : -1.0f);
-                cnt[q] = 0;
-            }
-            if (DBG & 8) tk_mark = (uint32_t)clock();
-            for (int t = t0; t < t1; t++) {
-                // (rhi, rlo) of this warp's chunk of the tile, from the tile blob in global memory
-                const float2 bnd = __ldg((const float2 *)(opB + (int64_t)t * L::B_TILE_BYTES + L::B_OP_BYTES) + kc);
-                tick(tk_b);
-#pragma unroll
-                for (int q = 0; q < kAccs; q++) {
-                    mbar_wait(BAR_T_FULL(q), tf_phase, status, 7);
-                    tc_fence_after();
-                    tick(tk_t);
-                    uint32_t v[32];
-                    if (!(DBG & 2)) {
-                        tmem_ld32(ta + q * kTileN, v);
-                        tmem_ld_wait();
-                    }
-                    tick(tk_l);
-                    tc_fence_before();  // this warp's only read of accumulator q for this tile: hand it back
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
-                    pin_order(v);  // the evaluation below must not be scheduled ahead of the hand-back
-                    if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring
-                    float M;  // max |kov| over the chunk, exact (see the other branch)
-                    if (F16) {
-                        auto av = [&](int k) { return fabsf(__uint_as_float(v[k])); };
-                        float c4[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            c4[i] = fmaxf(fmaxf(av(8 * i), av(8 * i + 1)), av(8 * i + 2));
-                            c4[i] = fmaxf(c4[i], fmaxf(av(8 * i + 3), av(8 * i + 4)));
-                            c4[i] = fmaxf(c4[i], fmaxf(av(8 * i + 5), av(8 * i + 6)));
-                        }
-                        const float m01 = fmaxf(fmaxf(c4[0], c4[1]), av(7));
-                        const float m23 = fmaxf(fmaxf(c4[2], c4[3]), av(15));
-                        M = fmaxf(fmaxf(fmaxf(m01, m23), av(23)), av(31));
-                    } else {
-                        int mx0 = 0, mn0 = 0, mx1 = 0, mn1 = 0;
-#pragma unroll
-                        for (int k = 0; k < 32; k += 4) {
-                            mx0 = max(mx0, max((int)v[k], (int)v[k + 1]));
-                            mn0 = min(mn0, min((int)v[k], (int)v[k + 1]));
-                            mx1 = max(mx1, max((int)v[k + 2], (int)v[k + 3]));
-                            mn1 = min(mn1, min((int)v[k + 2], (int)v[k + 3]));
-                        }
-                        M = __int2float_rn(max(max(mx0, mx1), -min(mn0, mn1)));
-                    }
-                    if (DUMP) {
-#pragma unroll
-                        for (int k = 0; k < 32; k++) {
-                            int iv = (int)v[k];
-                            if (F16) {  // a non-integral accumulator must fail the probe's check
-                                const float f = __uint_as_float(v[k]);
-                                iv = (f == rintf(f) && fabsf(f) < 2.0e9f) ? (int)f : (int)0x80000000;
-                            }
-                            dump[(row0 + q * kBlockM) * dump_ld + (int64_t)t * kTileN + kc * 32 + k] = iv;
-                        }
-                    }
-                    const float ub = M * bnd.x;
-                    if (ub > thresh[q]) {  // may hold the winner or one of its float ties
-                        RowFilter st = {thresh[q], lbmax[q], cnt[q]};
-                        int2 *const list = flag_list + ((((int64_t)ch * rows_padded + row0 + q * kBlockM) * kListsOf(1)) + kc) * kCapOf(1);
-                        st = flag_chunk(st, M * bnd.y, ub, tie_abs[q], list, kCapOf(1), t * kChunksPerTile + kc,
-                                        smem_u32(s_lb + q * kBlockM + ((rq >> iso_shift) << iso_shift)), 3);
-                        thresh[q] = st.thresh;
-                        lbmax[q] = st.lbmax;
-                        cnt[q] = st.cnt;
-                    }
-                    tick(tk_m);
-                }
-                tf_phase ^= 1;
-            }
-#pragma unroll
-            for (int q = 0; q < kAccs; q++) {
-                const int64_t row = row0 + q * kBlockM;
-                flag_cnt[((int64_t)ch * rows_padded + row) * kListsOf(1) + kc] = cnt[q];
-                // the row's bound after this unit: seeds its later units and lets the refine step drop stale flags
-                if (lbmax[q] > 0.0f) atomicMax(row_lb + ((row >> iso_shift) << iso_shift), __float_as_uint(lbmax[q]));
-            }
         }
         if ((DBG & 8) && lane == 0 && dump) {
             int32_t *o = dump + ((int64_t)blockIdx.x * kEpiWarps + e) * 8;
@@ -1708,11 +1656,14 @@ k_umma_refine_rgb(const uint8_t *__restrict__ src, const int32_t *__restrict__ r
         const int idx = pi.x;
         if (idx >= 0) {
             const int row = (int)(pos % kTileN);
-            const uint8_t *rowp = opB + (pos / kTileN) * L::B_TILE_BYTES + (row >> 3) * L::SBO_B + (row & 7) * 16;
+            uint8_t *const blob = const_cast<uint8_t *>(opB) + (pos / kTileN) * L::B_TILE_BYTES;
+            // the reference's kov: sequential binary32 accumulation in pixel order (FC:781-792); every product is an
+            // exact integer, so the fused multiply-add rounds exactly like the reference's multiply-then-add -- also
+            // where partial sums pass 2^24 (B = 16) and the sum is no longer an exact integer
             float kov = 0.0f;
-#pragma unroll
+#pragma unroll 8
             for (int c = 0; c < n / 8; c++) {
-                const uint4 d = __ldg((const uint4 *)(rowp + c * 128));
+                const uint4 d = __ldg((const uint4 *)rgb_dom_piece<B>(blob, row, c));
                 const uint32_t w[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
@@ -1762,15 +1713,18 @@ struct Plan {
 // with the bound the earlier ones reached -- about 2 * 1.5.  n_chunks minimises a small
 // cost model of search + refine time; its constants are B200 measurements (clocks per domain tile of
 // k_umma_search, whole-GPU nanoseconds per flagged chunk of k_umma_refine) -- only their ratio matters.
+inline int rows_per_sb(const Geom &g) { return (g.C == 3 && g.B == 16 ? 2 : kAccs) * kBlockM; }  // Cfg<...>::NB * 128
+
 inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p;
-    p.rp = pad_up(rows, kRowsPerSB);
-    p.n_sb = (int)(p.rp / kRowsPerSB);
+    const int rows_sb = rows_per_sb(g);
+    p.rp = pad_up(rows, rows_sb);
+    p.n_sb = (int)(p.rp / rows_sb);
     p.ntiles = (int)((g.ND + kTileN - 1) / kTileN);
     p.npos = (int64_t)p.ntiles * kTileN;
     p.n_chunks = 1;
-    const double tile_s = (g.B == 16 ? 4650.0 : (g.B == 8 ? 1550.0 : 1400.0)) / 1.9e9;
+    const double tile_s = (g.B == 16 ? (g.C == 3 ? 2300.0 : 4650.0) : (g.B == 8 ? 1550.0 : 1400.0)) / 1.9e9;
     const double flag_s = 0.11e-9 * (g.n / 64.0) * (g.n > 64 ? 0.7 : 1.0);
     double best_cost = 0;
     for (int c = 1; c <= 8 && c <= p.ntiles; c++) {
@@ -1821,10 +1775,10 @@ size_t opA_bytes_t(const Geom &g, int64_t rows, int num_sms)
     Plan p = make_plan(g, rows, num_sms);
     // [A blobs][vR s32][flag_cnt s32 x n_chunks x lists][flag_list (s32 id, f32 bound) x n_chunks x lists x cap][row_lb u32]
     return (size_t)p.n_sb * Lay<B, F16>::A_SB_BYTES + (size_t)p.rp * 4 + (size_t)p.rp * p.n_chunks * kFlagBytes +
-           (size_t)p.rp * 4 + 1024;
+           (size_t)p.rp * 4 /*row_lb*/ + (size_t)p.rp * 4 /*row norms (RGB, blockgroesse 16)*/ + 1024;
 }
 
-using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, int2 *, int32_t *, uint32_t *, int, int,
+using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, const float *, int2 *, int32_t *, uint32_t *, int, int,
                          int, int, int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
 
 // dbg (probe only): 1 / 3 strip the scoring / the TMEM loads too, 4: epilogue alone, 8 / 12: phase cycle counts
@@ -1840,10 +1794,10 @@ KernelT pick_kernel(bool dump, uint32_t dbg)
     return k_umma_search<B, F16, 0, false, EPI>;
 }
 
-// Epilogue mapping each configuration runs by default (measured, profiles/README.md: the chunk-per-warp mapping hands
-// accumulators back sooner but pays four waits per tile; it lost on every configuration).
+// Epilogue variant each configuration runs by default (measured, profiles/README.md): kind::f16 B = 8 gains 1.5-5 %
+// from the pipelined loads, B = 4 (epilogue bound) 10 % from deferring the flag tests as well.
 template <int B, bool F16>
-constexpr int default_epi() { return !F16 ? 0 : (B == 4 ? 3 : 2); }
+constexpr int default_epi() { return (!F16 || B == 16) ? 0 : (B == 4 ? 3 : 2); }
 
 template <int B, bool F16>
 int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s, const char **err,
@@ -1860,6 +1814,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     int32_t *flag_cnt = vR + rp;
     int2 *flag_list = (int2 *)(flag_cnt + rp * p.n_chunks * 4);  // 8-byte aligned: the blobs are, and rp is even
     uint32_t *row_lb = (uint32_t *)(flag_list + rp * p.n_chunks * 64);  // per operand row: best lower bound of max x reached by finished units
+    float *row_norm = (float *)(row_lb + rp);                            // per operand row: >= ||gR||_2 (RGB at blockgroesse 16)
     const bool rgb = g.C == 3;                        // kind::f16 only (see "RGB operands")
     if (rgb && !F16) { *err = "the RGB tensor path is kind::f16 only"; return -1; }
     OpBLayout<B, F16> lay(g, p);
@@ -1884,7 +1839,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
             launches += launch_sum_planes(w.dec, w.dec3, g, s);
             k_umma_pack_domains_rgb<B><<<(unsigned)((p.npos + 127) / 128), 128, 0, s>>>(
                 w.dec3, w.dsum, dv.Current(), w.opB, pos_dom, pos_info, dom0, g, p.ntiles, p.mult);
-            k_umma_pack_ranges_rgb<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, g, j0, j1, rp);
+            k_umma_pack_ranges_rgb<B><<<(unsigned)((rp + 127) / 128), 128, 0, s>>>(w.src, w.rsum, opA, vR, B == 16 ? row_norm : nullptr, g, j0, j1, rp);
         }
     }
     if (!rgb) {
@@ -1895,10 +1850,9 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     launches += 2;
     // 3. the fused search
     // Epilogue mapping (see k_umma_search): the default of this (block size, kind) pair, or the probe's choice
-    // (variant bit 1: accumulator per warp, bit 2: chunk per warp, bit 3: accumulator per warp, software-pipelined).
-    const int epi = (variant & 2) ? 0 : ((variant & 4) ? 1 : ((variant & 8) ? 2 : ((variant & 16) ? 3 : default_epi<B, F16>())));
+    // (variant bit 1: plain, bit 3: software-pipelined, bit 4: pipelined with deferred flag tests).
+    const int epi = (variant & 2) ? 0 : ((variant & 8) ? 2 : ((variant & 16) ? 3 : default_epi<B, F16>()));
     KernelT kern = pick_kernel<B, F16, 0>(dump && !(dbg & 8u), dbg);
-    if (epi == 1) kern = pick_kernel<B, F16, 1>(dump && !(dbg & 8u), dbg);
     if (epi == 2) kern = pick_kernel<B, F16, 2>(dump && !(dbg & 8u), dbg);
     if (epi == 3) kern = pick_kernel<B, F16, 3>(dump && !(dbg & 8u), dbg);
     if (dbg == 8 || dbg == 12) dump = w.best;  // phase cycle counts -> w.best
@@ -1910,7 +1864,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     if (variant & 1) { lbo_a = L::SBO_A; sbo_a = 128; lbo_b = L::SBO_B; sbo_b = 128; }  // probe only
     if (k0) cudaEventRecord(k0, s);
     cudaMemsetAsync(row_lb, 0, (size_t)rp * 4, s);
-    kern<<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, flag_list, flag_cnt, row_lb, p.n_sb, p.n_chunks, p.ntiles,
+    kern<<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, row_norm, flag_list, flag_cnt, row_lb, p.n_sb, p.n_chunks, p.ntiles,
                                                g.n_iso > 1 ? 3 : 0, rp,
                                                dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
     if (k1) cudaEventRecord(k1, s);
@@ -1934,8 +1888,8 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
 }
 
 // Dispatch on (block size, MMA kind): B = 16 has no kind::f16 variant (see umma_default_kind).
-#define FIC_UMMA_DISPATCH(B_, F_, EXPR_I8_4, EXPR_I8_8, EXPR_I8_16, EXPR_F16_4, EXPR_F16_8) \
-    ((B_) == 16 ? (EXPR_I8_16) : ((F_) ? ((B_) == 8 ? (EXPR_F16_8) : (EXPR_F16_4)) : ((B_) == 8 ? (EXPR_I8_8) : (EXPR_I8_4))))
+#define FIC_UMMA_DISPATCH(B_, F_, EXPR_I8_4, EXPR_I8_8, EXPR_I8_16, EXPR_F16_4, EXPR_F16_8, EXPR_F16_16) \
+    ((B_) == 16 ? ((F_) ? (EXPR_F16_16) : (EXPR_I8_16)) : ((F_) ? ((B_) == 8 ? (EXPR_F16_8) : (EXPR_F16_4)) : ((B_) == 8 ? (EXPR_I8_8) : (EXPR_I8_4))))
 
 }  // namespace
 
@@ -1946,8 +1900,8 @@ int umma_default_kind(const Geom &g) { return g.B == 16 ? FIC_UMMA_KIND_I8 : FIC
 
 static bool use_f16(const Geom &g, int kind)
 {
+    if (g.C == 3) return true;  // the RGB operands need binary16 (see "RGB operands"), at every block size
     if (g.B == 16) return false;
-    if (g.C == 3) return true;  // the RGB operands need binary16 (see "RGB operands")
     return (kind == FIC_UMMA_KIND_AUTO ? umma_default_kind(g) : kind) == FIC_UMMA_KIND_F16;
 }
 
@@ -1958,7 +1912,8 @@ void umma_debug_positions(const Work &w, const Geom &g, int64_t rows, int num_sm
     *npos = p.npos;
     const size_t off = FIC_UMMA_DISPATCH(g.B, use_f16(g, kind), (OpBLayout<4, false>(g, p).off_posdom),
                                          (OpBLayout<8, false>(g, p).off_posdom), (OpBLayout<16, false>(g, p).off_posdom),
-                                         (OpBLayout<4, true>(g, p).off_posdom), (OpBLayout<8, true>(g, p).off_posdom));
+                                         (OpBLayout<4, true>(g, p).off_posdom), (OpBLayout<8, true>(g, p).off_posdom),
+                                         (OpBLayout<16, true>(g, p).off_posdom));
     *d_pos_dom = (const int32_t *)(w.opB + off);
 }
 
@@ -2112,7 +2067,7 @@ int umma_f16_selftest(int num_sms, cudaStream_t s, const char **err)
 bool umma_applicable(const Geom &g)
 {
     if (g.wk != g.dpw || g.wk != g.dph) return false;
-    if (g.C == 3) return g.n_iso == 1 && (g.B == 4 || g.B == 8);  // kind::f16 only, which B = 16 does not have
+    if (g.C == 3) return g.n_iso == 1 && (g.B == 4 || g.B == 8 || g.B == 16);  // kind::f16 only
     return g.B == 4 || g.B == 8 || g.B == 16;
 }
 
@@ -2121,15 +2076,16 @@ size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms, int ki
     const int64_t rows = (j1 - j0) * g.n_iso;  // operand rows: one per (range, isometry)
     return FIC_UMMA_DISPATCH(g.B, use_f16(g, kind), (opA_bytes_t<4, false>(g, rows, num_sms)),
                              (opA_bytes_t<8, false>(g, rows, num_sms)), (opA_bytes_t<16, false>(g, rows, num_sms)),
-                             (opA_bytes_t<4, true>(g, rows, num_sms)), (opA_bytes_t<8, true>(g, rows, num_sms)));
+                             (opA_bytes_t<4, true>(g, rows, num_sms)), (opA_bytes_t<8, true>(g, rows, num_sms)),
+                             (opA_bytes_t<16, true>(g, rows, num_sms)));
 }
 
 size_t umma_opB_bytes(const Geom &g, int kind)
 {
-    Plan p = make_plan(g, kRowsPerSB, 148);  // the opB layout depends on the pool only
+    Plan p = make_plan(g, rows_per_sb(g), 148);  // the opB layout depends on the pool only
     return FIC_UMMA_DISPATCH(g.B, use_f16(g, kind), (OpBLayout<4, false>(g, p).total), (OpBLayout<8, false>(g, p).total),
                              (OpBLayout<16, false>(g, p).total), (OpBLayout<4, true>(g, p).total),
-                             (OpBLayout<8, true>(g, p).total));
+                             (OpBLayout<8, true>(g, p).total), (OpBLayout<16, true>(g, p).total));
 }
 
 // Debug entry used by tools/umma_probe: also dumps the raw accumulators (kov) of every
@@ -2141,7 +2097,7 @@ int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j
 #define FIC_UMMA_ARGS w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg
     return FIC_UMMA_DISPATCH(g.B, use_f16(g, kind), (launch_t<4, false>(FIC_UMMA_ARGS)), (launch_t<8, false>(FIC_UMMA_ARGS)),
                              (launch_t<16, false>(FIC_UMMA_ARGS)), (launch_t<4, true>(FIC_UMMA_ARGS)),
-                             (launch_t<8, true>(FIC_UMMA_ARGS)));
+                             (launch_t<8, true>(FIC_UMMA_ARGS)), (launch_t<16, true>(FIC_UMMA_ARGS)));
 #undef FIC_UMMA_ARGS
 }
 
