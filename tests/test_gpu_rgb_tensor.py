@@ -121,11 +121,11 @@ def test_rgb_b16_full_pool_tcgen05_synthetic(fic, handle, oracle, kind):
 
 
 def test_rgb_b16_auto_engine_and_lena(fic, handle, oracle, lena_colored):
-    """AUTO picks the tensor cores for RGB at B = 16 once the pool is large enough; Lena and a 384^2 natural image."""
+    """AUTO picks the tensor cores for RGB at B = 16 once the pool is large enough; Lena and a 640^2 natural image."""
     info, q = _encode_umma(fic, handle, lena_colored, 16, 29)
     oinfo = oracle.encode(lena_colored, 16, 29, rgb=True, nthreads=8)
     assert_codes_equal(info, q, oinfo, oracle.write_data(oinfo, 256, 256, 16, 29, rgb=True), 5)
-    W = 384
+    W = 640   # 1600 ranges x 5929 domains: above the tensor path's work threshold (2^22 evaluations)
     img = to_argb_rgb(np.stack([fic.synth.structured(W, W, s) for s in (1, 2, 3)], -1))
     wk = 2 * W // 16 - 3
     info, q = handle.encode(img, 16, wk, rgb=True)
