@@ -121,7 +121,7 @@ static int ensure(fic_handle *h, T *&p, int slot, size_t bytes)
 
 extern "C" {
 
-const char *fic_version(void) { return "fic_b200 0.1 (sm_100a)"; }
+const char *fic_version(void) { return "fic_b200 0.2 (sm_100a)"; }
 
 int fic_create(int device, fic_handle **out)
 {
@@ -286,8 +286,10 @@ static int pick_engine(fic_handle *h, const Geom &g, int64_t j0, int64_t j1, int
         if (!fused_encode_applicable(g)) return set_err(h, FIC_E_ARG, "the fused encode needs widthKernel <= 16 and no isometries");
         *engine = FIC_ENGINE_FUSED;
     } else if (h->engine_opt == FIC_ENGINE_AUTO) {
+        // the fused kernel spends one CTA per range block and wins where launches dominate (<= 16 K range blocks,
+        // 1.8 ms against 0.45 ms for the multi-kernel path at 4096^2, widthKernel 2: measured, profiles/README.md)
         if (umma_applicable(g) && (j1 - j0) * g.ND >= (int64_t)1 << 22) *engine = FIC_ENGINE_UMMA;
-        else if (fused_encode_applicable(g)) *engine = FIC_ENGINE_FUSED;
+        else if (fused_encode_applicable(g) && g.NR <= 16384) *engine = FIC_ENGINE_FUSED;
     }
     return FIC_OK;
 }

@@ -77,6 +77,8 @@ double measure_mma_peak(int num_sms, cudaStream_t s, int reps, int f16, int n_co
 // 1: kind::f16 accumulators are the exact integer covariances on this device; 0: not; < 0: CUDA error
 int umma_f16_selftest(int num_sms, cudaStream_t s, const char **err);
 bool umma_applicable(const Geom &g);
+// in-tree stable radix sort on 24-bit keys (probe / tests): result in the *_out arrays; 0 or a CUDA error code
+int umma_debug_sort(uint32_t *d_keys, int32_t *d_vals, uint32_t *d_keys_out, int32_t *d_vals_out, int64_t n, cudaStream_t s);
 // `kind`: FIC_UMMA_KIND_AUTO / _I8 / _F16 (B = 16 always runs kind::i8); umma_default_kind = what AUTO picks
 int umma_default_kind(const Geom &g);
 size_t umma_opA_bytes(const Geom &g, int64_t j0, int64_t j1, int num_sms, int kind);

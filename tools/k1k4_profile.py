@@ -13,6 +13,7 @@ import fractal_image_compression_b200 as fic  # noqa: E402
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 img = fic.synth.grey_to_argb(fic.synth.structured(W, W, 1))
 h = fic.Handle(0)
+h.set_engine(fic.FIC_ENGINE_FUSED)
 info, q = h.encode(img, 8, 2, rgb=False)         # reference default window: the fused one-launch encode
 t = h.timings()
 print(f"encode wk=2 (engine {t.engine}): total {t.total_ms:.3f} ms (h2d {t.h2d_ms:.3f}, kernel {t.kernel_ms:.3f}, d2h {t.d2h_ms:.3f})")

@@ -477,6 +477,54 @@ static int run_chain()
     return 0;
 }
 
+// ---- in-tree radix sort against std::stable_sort ("sort" mode) ----------------------------------
+#include <algorithm>
+static int run_sort()
+{
+    cudaStream_t s;
+    cudaStreamCreate(&s);
+    int rc = 0;
+    const long long sizes[] = {1, 31, 2048, 2049, 100000, 1042441, 4182025, 16752649};
+    for (long long n : sizes)
+        for (int mode = 0; mode < 3; mode++) {
+            std::vector<uint32_t> k(n);
+            std::vector<int32_t> v(n);
+            uint32_t x = 12345u + (uint32_t)n + mode;
+            for (long long i = 0; i < n; i++) {
+                x = lowbias32(x + (uint32_t)i);
+                k[i] = mode == 0 ? (x & 0xffffffu) : (mode == 1 ? (x & 0xffu) * 65793u % 16777216u : (uint32_t)(i % 7 == 0 ? 0 : 5));  // wide / few values / ties
+                v[i] = (int32_t)i;
+            }
+            uint32_t *dk, *dko;
+            int32_t *dv, *dvo;
+            cudaMalloc(&dk, n * 4 + 16); cudaMalloc(&dko, n * 4 + 16); cudaMalloc(&dv, n * 4 + 16); cudaMalloc(&dvo, n * 4 + 16);
+            cudaMemcpy(dk, k.data(), n * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(dv, v.data(), n * 4, cudaMemcpyHostToDevice);
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            cudaEventRecord(e0, s);
+            int e = umma_debug_sort(dk, dv, dko, dvo, n, s);
+            cudaEventRecord(e1, s);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            std::vector<uint32_t> ko(n);
+            std::vector<int32_t> vo(n);
+            cudaMemcpy(ko.data(), dko, n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(vo.data(), dvo, n * 4, cudaMemcpyDeviceToHost);
+            std::vector<int32_t> ref(n);
+            for (long long i = 0; i < n; i++) ref[i] = (int32_t)i;
+            std::stable_sort(ref.begin(), ref.end(), [&](int32_t a, int32_t b) { return k[a] < k[b]; });
+            long long bad = 0;
+            for (long long i = 0; i < n; i++) bad += (vo[i] != ref[i]) || (ko[i] != k[ref[i]]);
+            printf("sort: n=%lld mode=%d rc=%d %.3f ms (incl. scratch allocation): %lld mismatches vs std::stable_sort\n", n, mode, e, ms, bad);
+            if (bad || e) rc = 1;
+            cudaFree(dk); cudaFree(dko); cudaFree(dv); cudaFree(dvo);
+        }
+    printf(rc ? "SORT FAIL\n" : "SORT PASS\n");
+    return rc;
+}
+
 static int run_ldtm()
 {
     long long *d;
@@ -504,6 +552,7 @@ int main(int argc, char **argv)
     if (argc > 1 && !strcmp(argv[1], "alu")) return run_alu();
     if (argc > 1 && !strcmp(argv[1], "mix")) return run_mix();
     if (argc > 1 && !strcmp(argv[1], "chain")) return run_chain();
+    if (argc > 1 && !strcmp(argv[1], "sort")) return run_sort();
     if (argc < 4) {
         printf("usage: umma_probe check|time B W [variant] [pattern]\n");
         return 2;
