@@ -42,10 +42,13 @@ def main():
             for h, u in zip(hdr, units):
                 if any(h == k or h.startswith(k + ".") or h == k.strip() for k in KEYS) or h in KEYS:
                     f.write(f"{h} [{u}] = {d[h]}\n")
+    if len(raw) > 3:   # several kernels in one report: the per-kernel metrics above are the summary
+        print("wrote", out + "_raw.txt")
+        return
     src = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv"]))))
     hdr = src[1]
-    data = src[2:]
     ix = {h: i for i, h in enumerate(hdr)}
+    data = [r for r in src[2:] if len(r) == len(hdr) and r[ix["# Samples"]].isdigit()]
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot = sum(int(r[ix["# Samples"]]) for r in data) or 1
     with open(out + "_source_top.txt", "w") as f:
@@ -61,4 +64,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception as exc:  # a summary that fails must not keep the (large) report from being deleted by the caller
+        print("summarize_ncu failed:", exc)
+        sys.exit(0)
