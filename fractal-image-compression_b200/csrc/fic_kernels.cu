@@ -1066,6 +1066,15 @@ k_decode_sweep(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, ui
 // Vector path (W % 8 == 0): one thread owns an 8 x 2 pixel strip (four quads): 8-byte loads of the old
 // pixels, 8-byte stores of the new ones, one 4-byte store of the new decimated pixels; the 16 domain
 // bytes are gathered from the (L2-resident) decimated plane.
+// (int)(float) followed by the reference's clamp to [0, 255] (FC:396-402, FC:743-749) in one instruction: the
+// conversion truncates toward zero and saturates to the destination range, NaN -> 0, like Java's cast + applyThreshold.
+__device__ __forceinline__ uint32_t f2u8_rz_sat(float f)
+{
+    uint32_t r;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(f));
+    return r;
+}
+
 template <int C>
 __global__ void __launch_bounds__(256)
 k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, uint8_t *__restrict__ dec_out,
@@ -1076,22 +1085,17 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
     const int sw8 = g.W / 8;
     const int64_t strips = (int64_t)sw8 * (g.H / 2);
     unsigned long long local = 0;
+    constexpr int S = C == 1 ? 3 : 5;
+    const int64_t planeI = (int64_t)g.W * g.H, planeD = (int64_t)g.sw * g.sh;
+    const int lb = __ffs(g.B) - 1, bm = g.B - 1;  // B is a power of two
+    // B >= 8: the strip lies inside ONE range block -- one code, one domain offset, and the 2 x 8 domain bytes
+    // are two runs of 8 contiguous bytes (2-byte aligned: the domain grid stride B/4 is even), read as 16-bit
+    // words.  B = 4: a strip spans two range blocks; every quad fetches its own code and bytes.
+    const bool one_range = g.B >= 8;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < strips; t += (int64_t)gridDim.x * blockDim.x) {
         const int qy = (int)(t / sw8), s8 = (int)(t - (int64_t)qy * sw8);
         const int y = 2 * qy, x0 = 8 * s8;
-        constexpr int S = C == 1 ? 3 : 5;
-        const int64_t planeI = (int64_t)g.W * g.H, planeD = (int64_t)g.sw * g.sh;
-        const int lb = __ffs(g.B) - 1, bm = g.B - 1;  // B is a power of two
         const int yr = y >> lb, ry = y & bm;
-        int e[4][4];
-#pragma unroll
-        for (int qd = 0; qd < 4; qd++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) e[qd][k] = 0;
-        // B >= 8: the strip lies inside ONE range block -- one code, one domain offset, and the 2 x 8 domain bytes
-        // are two runs of 8 contiguous bytes (2-byte aligned: the domain grid stride B/4 is even), read as 16-bit
-        // words.  B = 4: a strip spans two range blocks; every quad fetches its own code and bytes.
-        const bool one_range = g.B >= 8;
         const int64_t jr0 = (int64_t)yr * g.rpw + (x0 >> lb);
         float a0 = 0.0f;
         int off0 = 0;
@@ -1099,6 +1103,7 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
             a0 = __ldg(code + S * jr0 + 1);
             off0 = __ldg(doff + jr0) + ry * g.sw + (x0 & bm);
         }
+        uint32_t esq[4][C];  // per quad: packed |old - new| of its four pixels (only unpacked when perr is asked for)
 #pragma unroll
         for (int c = 0; c < C; c++) {
             uint8_t *pi = img + c * planeI + (int64_t)y * g.W + x0;
@@ -1121,49 +1126,53 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
             for (int qd = 0; qd < 4; qd++) {
                 const int x = x0 + 2 * qd;
                 float a = a0, b = bq;
-                int d00, d10, d01, d11;
-                if (one_range) {
-                    d00 = dr0[qd] & 0xff; d10 = dr0[qd] >> 8; d01 = dr1[qd] & 0xff; d11 = dr1[qd] >> 8;
-                } else {
+                if (!one_range) {
                     const int xr = x >> lb, rx = x & bm;
                     const int64_t jr = (int64_t)yr * g.rpw + xr;
                     const float *cd = code + S * jr;
                     a = cd[1];
                     b = cd[2 + c];
                     const uint8_t *pd = dec_in + c * planeD + doff[jr] + ry * g.sw + rx;
-                    d00 = pd[0]; d10 = pd[1]; d01 = pd[g.sw]; d11 = pd[g.sw + 1];
+                    dr0[qd] = (uint32_t)pd[0] | ((uint32_t)pd[1] << 8);
+                    dr1[qd] = (uint32_t)pd[g.sw] | ((uint32_t)pd[g.sw + 1] << 8);
                 }
-                // FC:396 / FC:482: (int)(a * domain + b), float multiply then float add
-                const int v00 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d00), b)));
-                const int v10 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d10), b)));
-                const int v01 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d01), b)));
-                const int v11 = clamp255(j_f2i(__fadd_rn(__fmul_rn(a, (float)d11), b)));
+                // FC:396 / FC:482: (int)(a * domain + b), float multiply then float add, then the clamp
+                const uint32_t v00 = f2u8_rz_sat(__fadd_rn(__fmul_rn(a, (float)(dr0[qd] & 0xffu)), b));
+                const uint32_t v10 = f2u8_rz_sat(__fadd_rn(__fmul_rn(a, (float)(dr0[qd] >> 8)), b));
+                const uint32_t v01 = f2u8_rz_sat(__fadd_rn(__fmul_rn(a, (float)(dr1[qd] & 0xffu)), b));
+                const uint32_t v11 = f2u8_rz_sat(__fadd_rn(__fmul_rn(a, (float)(dr1[qd] >> 8)), b));
                 const int sh = 16 * (qd & 1);
-                const int p00 = (old0[qd >> 1] >> sh) & 0xff, p10 = (old0[qd >> 1] >> (sh + 8)) & 0xff;
-                const int p01 = (old1[qd >> 1] >> sh) & 0xff, p11 = (old1[qd >> 1] >> (sh + 8)) & 0xff;
-                e[qd][0] += (p00 - v00) * (p00 - v00);  // FC:407 / FC:493
-                e[qd][1] += (p10 - v10) * (p10 - v10);
-                e[qd][2] += (p01 - v01) * (p01 - v01);
-                e[qd][3] += (p11 - v11) * (p11 - v11);
-                n0[qd >> 1] |= ((uint32_t)v00 | ((uint32_t)v10 << 8)) << sh;
-                n1[qd >> 1] |= ((uint32_t)v01 | ((uint32_t)v11 << 8)) << sh;
-                nd |= (uint32_t)dec_tap4(v00, v10, v01, v11, x, g.H, C == 3) << (8 * qd);
+                const uint32_t newq = v00 | (v10 << 8) | (v01 << 16) | (v11 << 24);
+                const uint32_t oldq = ((old0[qd >> 1] >> sh) & 0xffffu) | (((old1[qd >> 1] >> sh) & 0xffffu) << 16);
+                const uint32_t ad = __vabsdiffu4(oldq, newq);
+                esq[qd][c] = ad;
+                local += (unsigned long long)__dp4a(ad, ad, 0u);  // FC:407 / FC:493: sum of the squared pixel changes
+                n0[qd >> 1] |= (newq & 0xffffu) << sh;
+                n1[qd >> 1] |= (newq >> 16) << sh;
+                nd |= (uint32_t)dec_tap4((int)v00, (int)v10, (int)v01, (int)v11, x, g.H, C == 3) << (8 * qd);
             }
             *(uint2 *)pi = make_uint2(n0[0], n0[1]);
             *(uint2 *)(pi + g.W) = make_uint2(n1[0], n1[1]);
             if (dec_out) *(uint32_t *)(dec_out + c * planeD + (int64_t)qy * g.sw + 4 * s8) = nd;
         }
+        if (perr) {  // per-pixel squared change, summed over the channels, in the reference's loop order
 #pragma unroll
-        for (int qd = 0; qd < 4; qd++) {
-            local += (unsigned long long)(e[qd][0] + e[qd][1] + e[qd][2] + e[qd][3]);
-            if (perr) {
+            for (int qd = 0; qd < 4; qd++) {
                 const int x = x0 + 2 * qd;
                 const int xr = x >> lb, rx = x & bm;
+                int e[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int c = 0; c < C; c++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int d = (int)((esq[qd][c] >> (8 * k)) & 0xffu);
+                        e[k] += d * d;
+                    }
                 int32_t *pe = perr + ((int64_t)yr * g.rpw + xr) * g.n + ry * g.B + rx;
-                pe[0] = e[qd][0];
-                pe[1] = e[qd][1];
-                pe[g.B] = e[qd][2];
-                pe[g.B + 1] = e[qd][3];
+                pe[0] = e[0];
+                pe[1] = e[1];
+                pe[g.B] = e[2];
+                pe[g.B + 1] = e[3];
             }
         }
     }
