@@ -1179,26 +1179,36 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
     sweep_tail(ctl, local);
 }
 
-constexpr int64_t kSweepCtas = 148 * 8;  // one wave of 256-thread CTAs at full occupancy: grid-stride beyond that
+// The sweeps are grid-stride over exactly one wave of resident CTAs (SMs x occupancy of the kernel): a second, partly
+// filled wave cost a third of the sweep at 4096^2 (1184 CTAs on 740 slots, profiles/README.md).
+template <class K>
+static int64_t sweep_wave_ctas(K kernel)
+{
+    int dev = 0, sms = 148, per_sm = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    return (int64_t)sms * per_sm;
+}
 
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out, const float *d_code,
                         const int32_t *d_off, const Geom &g, const SweepCtl &ctl, int32_t *d_perr, cudaStream_t s)
 {
+    static const int64_t wave_v8_1 = sweep_wave_ctas(k_decode_sweep_v8<1>), wave_v8_3 = sweep_wave_ctas(k_decode_sweep_v8<3>);
+    static const int64_t wave_q_1 = sweep_wave_ctas(k_decode_sweep<1>), wave_q_3 = sweep_wave_ctas(k_decode_sweep<3>);
     if (g.W % 8 == 0 && g.n_iso == 1) {  // the isometry extension uses the quad kernel (per-pixel gather)
-        int64_t strips = (int64_t)(g.W / 8) * (g.H / 2);
-        unsigned blocks = (unsigned)((strips + 255) / 256 < kSweepCtas ? (strips + 255) / 256 : kSweepCtas);
+        const int64_t strips = (int64_t)(g.W / 8) * (g.H / 2), need = (strips + 255) / 256;
         if (g.C == 1)
-            k_decode_sweep_v8<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
+            k_decode_sweep_v8<1><<<(unsigned)(need < wave_v8_1 ? need : wave_v8_1), 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
         else
-            k_decode_sweep_v8<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
+            k_decode_sweep_v8<3><<<(unsigned)(need < wave_v8_3 ? need : wave_v8_3), 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
         return 1;
     }
-    int64_t quads = (int64_t)(g.W / 2) * (g.H / 2);
-    unsigned blocks = (unsigned)((quads + 255) / 256 < kSweepCtas ? (quads + 255) / 256 : kSweepCtas);
+    const int64_t quads = (int64_t)(g.W / 2) * (g.H / 2), need = (quads + 255) / 256;
     if (g.C == 1)
-        k_decode_sweep<1><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
+        k_decode_sweep<1><<<(unsigned)(need < wave_q_1 ? need : wave_q_1), 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
     else
-        k_decode_sweep<3><<<blocks, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
+        k_decode_sweep<3><<<(unsigned)(need < wave_q_3 ? need : wave_q_3), 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
     return 1;
 }
 
