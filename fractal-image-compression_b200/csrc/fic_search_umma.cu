@@ -34,9 +34,10 @@
 // exactly whatever the summation order (the probe dumps and checks every accumulator).  K = n.
 // The epilogue takes max |kov| with FMNMX3 |a|, |b|, |c|: 16 instructions per 32 values.
 //
-// RGB (B = 4, 8; kind::f16 only).  The reference's RGB score has the same shape with the channel-summed centred
+// RGB (kind::f16 only).  The reference's RGB score has the same shape with the channel-summed centred
 // values gR, gD in [-765, 765] as operands and the integer vD = sum gD in the place of sqrt(varD); its covariance
-// is provably an exact integer below 2^24 for B <= 8.  Same kernel, RGB packers and refine: see "RGB operands".
+// is provably an exact integer below 2^24 for B <= 8, and at B = 16 the chunk bounds are widened by the worst-case
+// rounding of the float sums.  Same kernel, RGB packers and refine: see "RGB operands".
 //
 // kov on the tensor cores, kind::i8 (B = 16; selectable for B = 4, 8).  With dt = d - dmean_j
 // (|dt| <= 255; +255 only occurs in a block of mean 0, whose row is stored negated -- only |kov| is used),
@@ -75,9 +76,11 @@
 //               range row, all 128 domains of a tile: per tile one t_full wait, four
 //               tcgen05.ld.32x32b.x32, one hand-back (t_empty[q]); the tile's bounds come from
 //               the blob in global memory at the top of each tile.  Rare paths (flag recording,
-//               mbarrier polling) are out of line.
+//               mbarrier polling) are out of line.  kind::f16, B <= 8: the four loads are software-pipelined
+//               (template parameter EPI).
 // A work unit is (super-block of 512 rows) x (1/n_chunks of the domain tiles); units are
-// ordered chunk-major and a row's lower bound is carried from unit to unit (row_lb).
+// ordered chunk-major and a row's lower bound is carried from unit to unit (row_lb).  (RGB at B = 16:
+// 256-row super-blocks, two of the four accumulators, Cfg<16, true>.)
 #include <cuda_fp16.h>
 
 #include <cmath>
@@ -236,27 +239,16 @@ __device__ __noinline__ float flag_threshold(float lb, float tie_abs)  // rare p
 // and the upper bound ub of its scores, which lets the refine step drop the chunk once the row's final bound is
 // known -- and, if it raises the row's lower bound, publish the bound (shared-memory slot `sh_lb`) and recompute the
 // threshold.
-// share bit 0: publish a raised bound to `sh_lb`; bit 1: the row is scanned by several warps (chunk-per-warp mapping,
-// isometry rows) -- first adopt the bound the others reached and re-test, so that a stale private threshold costs a
-// visit here, not a flag.
+// share != 0: publish a raised bound to `sh_lb` (isometry rows share one bound).
 struct RowFilter { float thresh, lbmax; int cnt; };
-__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t saddr);
 __device__ __noinline__ RowFilter flag_chunk(RowFilter st, float lb, float ub, float tie_abs, int2 *list, int cap,
                                              int chunk_id, uint32_t sh_lb, int share)
 {
-    if (share & 2) {
-        const float other = __uint_as_float(lds_volatile_u32(sh_lb));
-        if (other > st.lbmax) {
-            st.lbmax = other;
-            st.thresh = flag_threshold(other, tie_abs);
-            if (!(ub > st.thresh)) return st;
-        }
-    }
     if (st.cnt < cap) list[st.cnt] = make_int2(chunk_id, __float_as_int(ub));
     st.cnt++;
     if (lb > st.lbmax) {
         st.lbmax = lb;
-        if (share & 1)  // positive floats order like their bits
+        if (share)  // positive floats order like their bits
             asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(sh_lb), "r"(__float_as_uint(lb)) : "memory");
         const float rad = lb * lb * kOneMinusEps - tie_abs;
         st.thresh = rad > 0.0f ? sqrtf(rad) : -1.0f;
@@ -639,8 +631,12 @@ k_umma_pack_ranges(const uint8_t *__restrict__ src, const int32_t *__restrict__ 
 //     every partial sum of |gR_i gD_i| over any subset of the pixels is <= 9 n (127.5^2 + 1) = 9 364 176 < 2^24 at
 //     n = 64.  Every partial sum of every summation order is therefore an integer below 2^24: the reference's
 //     sequential float kov, the tensor-core accumulator and the refine step's FMA chain are the same exact integer
-//     for every block (the bound 64 * 765^2 of a term-by-term estimate is not attained).  B = 16 (bound 3.7e7) has no
-//     such guarantee -- and no kind::f16 variant: RGB at B = 16 stays on the CUDA-core kernel.
+//     for every block (the bound 64 * 765^2 of a term-by-term estimate is not attained);
+//   * B = 16: the same bound is 3.7e7 > 2^24.  On extreme-contrast content the reference's sequential float sum ROUNDS,
+//     and what it ranks by is the rounded value kov_ref.  The tensor cores then act as a filter with honest bounds
+//     (Cfg<16, true>, SLACK in the search epilogue): |accumulator - kov_ref| < 4.6e-5 ||gR|| ||gD|| wherever
+//     ||gR|| ||gD|| >= 2^24 and 0 below; the packers store upper bounds of ||gR|| per range row and of max ||gD|| per
+//     32-domain chunk.  k_umma_refine_rgb replays the float sum in pixel order, i.e. ranks by kov_ref itself.
 
 __device__ __forceinline__ int rgb_dom_vd(const int32_t *__restrict__ dsum, int64_t ND, int64_t j, int n, int dm[3])
 {
@@ -2007,7 +2003,7 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     return launches;
 }
 
-// Dispatch on (block size, MMA kind): B = 16 has no kind::f16 variant (see umma_default_kind).
+// Dispatch on (block size, MMA kind): grey B = 16 runs kind::i8 only, kind::f16 at B = 16 is the RGB configuration.
 #define FIC_UMMA_DISPATCH(B_, F_, EXPR_I8_4, EXPR_I8_8, EXPR_I8_16, EXPR_F16_4, EXPR_F16_8, EXPR_F16_16) \
     ((B_) == 16 ? ((F_) ? (EXPR_F16_16) : (EXPR_I8_16)) : ((F_) ? ((B_) == 8 ? (EXPR_F16_8) : (EXPR_F16_4)) : ((B_) == 8 ? (EXPR_I8_8) : (EXPR_I8_4))))
 

@@ -58,8 +58,8 @@ extern "C" {
 #define FIC_MODE_GREY_ISO 2 /* {c, a, b, k} per range; k = isometry 0..7 */
 
 /* Search engine selection (fic_set_option(FIC_OPT_ENGINE, ...)). */
-#define FIC_ENGINE_AUTO 0   /* tcgen05 search when the window is the whole pool (RGB: blockgroesse 4, 8); the fused
-                             * one-launch encode for the reference's GUI windows (widthKernel <= 16); else direct */
+#define FIC_ENGINE_AUTO 0   /* tcgen05 search when the window is the whole pool; the fused one-launch encode for the
+                             * reference's GUI windows (widthKernel <= 16) on images of up to 16 K range blocks; else direct */
 #define FIC_ENGINE_DIRECT 1 /* multi-kernel direct (CUDA-core) windowed search for every window */
 #define FIC_ENGINE_UMMA 2   /* force the tcgen05 search; FIC_E_ARG if not applicable  */
 #define FIC_ENGINE_FUSED 3  /* force the fused windowed encode (decimate + stats + search + solve in one launch);
@@ -67,7 +67,7 @@ extern "C" {
 
 /* Tensor-core instruction kind of the tcgen05 search (fic_set_option(FIC_OPT_UMMA_KIND, ...)).
  * Both produce the exact integer covariances, hence the same codes.  RGB images have a kind::f16 path only
- * (B = 4, 8): this option does not apply to them. */
+ * (blockgroesse 4, 8 and 16): this option does not apply to them. */
 #define FIC_UMMA_KIND_AUTO 0 /* kind::f16 for B = 4, 8; kind::i8 for B = 16               */
 #define FIC_UMMA_KIND_I8 1   /* u8 x s8 -> s32, two s8 digits per centred domain pixel    */
 #define FIC_UMMA_KIND_F16 2  /* binary16 x binary16 -> binary32 (B = 16 still runs i8)    */
