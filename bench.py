@@ -48,6 +48,8 @@ def parse():
                     help="RGB encode (FC:171-226: one shared domain and contrast for the three channels); tensor cores for B = 4, 8")
     ap.add_argument("--mma", default="auto", choices=["auto", "i8", "f16"],
                     help="tensor-core instruction kind of the tcgen05 search (auto: f16 for B=4,8; i8 for B=16)")
+    ap.add_argument("--pair", default="auto", choices=["auto", "on", "off"],
+                    help="CTA pairs (tcgen05 cta_group::2) of the tcgen05 search; auto = pairs at B = 8")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lena", action="store_true", help="skip the bundled-image object (BASELINE configs[0], [1], [4])")
@@ -346,6 +348,7 @@ def run_ours(args):
     handle = fic.Handle(local)
     handle.set_engine({"auto": fic.FIC_ENGINE_AUTO, "direct": fic.FIC_ENGINE_DIRECT, "umma": fic.FIC_ENGINE_UMMA}[args.engine])
     handle.set_umma_kind({"auto": fic.FIC_UMMA_KIND_AUTO, "i8": fic.FIC_UMMA_KIND_I8, "f16": fic.FIC_UMMA_KIND_F16}[args.mma])
+    handle.set_umma_pair({"auto": fic.FIC_UMMA_PAIR_AUTO, "on": fic.FIC_UMMA_PAIR_ON, "off": fic.FIC_UMMA_PAIR_OFF}[args.pair])
     # what the library runs: RGB has a kind::f16 path only; grey B = 16 a kind::i8 path only
     mma = "f16" if args.rgb else ("i8" if (B == 16 or args.mma == "i8") else "f16")
     stream = torch.cuda.Stream(dev)   # library work, NCCL ordering and the timing events all use this stream
@@ -436,6 +439,7 @@ def run_ours(args):
     t = handle.timings()
     engine = t.engine
     step_evals = t.search_evals  # this rank's evaluations per step
+    pair_used = handle.umma_pair_used()
 
     for _ in range(2):
         step_e2e()
@@ -476,7 +480,8 @@ def run_ours(args):
     peak = f16_peak if mma == "f16" else 2.0 * f16_peak
     try:
         handle.set_stream(None)
-        bare = handle.measure_mma_peak(fic.FIC_UMMA_KIND_F16 if mma == "f16" else fic.FIC_UMMA_KIND_I8, 128)
+        kk = fic.FIC_UMMA_KIND_F16 if mma == "f16" else fic.FIC_UMMA_KIND_I8
+        bare = handle.measure_mma_peak_pair(kk) if pair_used else handle.measure_mma_peak(kk, 128)
     except Exception as exc:  # diagnostics only
         bare = None
         sys.stderr.write(f"tensor peak measurement failed: {exc}\n")
@@ -489,14 +494,25 @@ def run_ours(args):
     achieved = ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
     nominal = 2250.0 if mma == "f16" else 4500.0
     is_umma = engine == fic.FIC_ENGINE_UMMA
+    # The tensor pipe's own ceiling at the clock the GPU actually held during the timed steps (nvidia-smi samples):
+    # 8192 (kind::f16) / 16384 (kind::i8) dense operations per clock and SM.  Both measured peaks above are taken under
+    # the board's power cap with random operands; the search's operands are small integers and toggle less, so the
+    # kernel can exceed them -- the per-clock ceiling is the one it cannot.
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_mhz = clocks.get("sm_mhz") if isinstance(clocks, dict) else None
+    pipe_at_clock = (8192.0 if mma == "f16" else 16384.0) * n_sm * float(sm_mhz) * 1e6 / 1e12 if sm_mhz else None
     roofline = {
-        "bound": "tensor", "kernel": f"k_umma_search (tcgen05.mma.kind::{mma})" if is_umma else ("k_search_direct_rgb" if args.rgb else "k_search_direct_grey"),
+        "bound": "tensor", "kernel": (f"k_umma_search (tcgen05.mma{'.cta_group::2' if pair_used else ''}.kind::{mma})" if is_umma
+                                      else ("k_search_direct_rgb" if args.rgb else "k_search_direct_grey")),
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s" if mma == "f16" else "TOP/s", "frac": achieved / peak,
         "peak_source": (f"bf16_tflops ({pk['bf16_tflops']}, burst) of {pk_kind}" if mma == "f16" else
                         f"2 x bf16_tflops ({pk['bf16_tflops']}, burst) of {pk_kind} (no int8 entry there)"),
         "frac_of_nominal": achieved / nominal, "nominal": nominal,
         "bare_mma_loop_measured": bare,
+        "bare_mma_loop_shape": "cta_group::2 M=256 N=128" if pair_used else "cta_group::1 M=128 N=128",
         "frac_of_bare_mma_loop": (achieved / bare) if bare else None,
+        "pipe_peak_at_sampled_clock": pipe_at_clock, "sampled_sm_mhz": sm_mhz,
+        "frac_of_pipe_at_sampled_clock": (achieved / pipe_at_clock) if pipe_at_clock else None,
         # north_star quotes the int8 tensor pipe: the same algorithmic rate against its nominal dense peak and against
         # a bare kind::i8 tcgen05.mma loop measured in this run (whatever instruction kind the kernel itself issues)
         "frac_of_int8_nominal": achieved / 4500.0,
@@ -506,7 +522,7 @@ def run_ours(args):
         "pool_ms": statistics.mean(pool_ms),
         # dram__bytes_read.sum + dram__bytes_write.sum of one k_umma_search launch from `ncu --set full`
         # (profiles/); only known for the profiled workload
-        "traffic": TRAFFIC.get((mma, size, B)) if (is_umma and world == 1 and not args.iso and not args.rgb) else None,
+        "traffic": TRAFFIC.get((mma + ("_pair" if pair_used else ""), size, B)) if (is_umma and world == 1 and not args.iso and not args.rgb) else None,
         "traffic_source": "constant from the ncu --set full capture of this kernel on this workload (profiles/), not measured in this run",
     }
     line = {
@@ -518,6 +534,7 @@ def run_ours(args):
         "config": {"workload": f"synthetic {args.pattern} {size}x{size} {'RGB' if args.rgb else 'grey'}, B={B}, widthKernel={wk} (full pool)"
                                + (", 8 isometries per domain (extension)" if args.iso else ""),
                    "ranges": NR, "domains": ND, "isometries": n_iso, "engine": f"tcgen05 kind::{mma}" if engine == fic.FIC_ENGINE_UMMA else "direct",
+                   "cta_pairs": bool(pair_used),
                    "parallelism": f"range-rows x{world}", "l2": "flushed between timed iterations (256 MiB write)",
                    # the library's once-per-handle check that kind::f16 accumulators are the exact integer covariances
                    "f16_exact_selftest": bool(handle.f16_exact()) if mma == "f16" else None},

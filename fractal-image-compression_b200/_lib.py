@@ -20,13 +20,16 @@ FIC_MODE_GREY, FIC_MODE_RGB, FIC_MODE_GREY_ISO = 0, 1, 2
 FIC_OPT_ENGINE = 1
 FIC_OPT_UMMA_KIND = 2
 FIC_OPT_F16_EXACT = 3
+FIC_OPT_UMMA_PAIR = 4
+FIC_OPT_UMMA_PAIR_USED = 5
+FIC_UMMA_PAIR_AUTO, FIC_UMMA_PAIR_OFF, FIC_UMMA_PAIR_ON = 0, 1, 2
 
 # every symbol include/fic_b200.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "fic_create", "fic_destroy", "fic_last_error", "fic_version", "fic_set_option", "fic_get_option", "fic_set_stream",
     "fic_get_timings", "fic_geometry", "fic_encode_grey", "fic_encode_rgb", "fic_encode_grey_iso", "fic_encode_planes_dev",
     "fic_sync", "fic_decode", "fic_collage", "fic_build_pool", "fic_stream_size", "fic_stream_write",
-    "fic_stream_read_header", "fic_stream_read_codes", "fic_measure_int8_peak", "fic_measure_mma_peak",
+    "fic_stream_read_header", "fic_stream_read_codes", "fic_measure_int8_peak", "fic_measure_mma_peak", "fic_measure_mma_peak_pair",
     "fic_pin_host_buffer", "fic_unpin_host_buffer",
     "fic_encode_grey_u8", "fic_encode_rgb_planes", "fic_decode_u8", "fic_decode_planes_dev",
     "fic_create_multi", "fic_destroy_multi", "fic_multi_last_error", "fic_multi_device_count", "fic_multi_handle",
@@ -103,6 +106,7 @@ def load() -> C.CDLL:
     L.fic_build_pool.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.fic_measure_int8_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.fic_measure_mma_peak.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.fic_measure_mma_peak_pair.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.fic_pin_host_buffer.argtypes = [vp, vp, C.c_size_t]
     L.fic_unpin_host_buffer.argtypes = [vp, vp]
     L.fic_stream_size.argtypes = [C.c_int] * 4

@@ -101,6 +101,16 @@ class Handle:
         """Tensor-core instruction kind of the tcgen05 search: FIC_UMMA_KIND_AUTO / _I8 / _F16."""
         self._check(self._L.fic_set_option(self._h, _lib.FIC_OPT_UMMA_KIND, int(kind)))
 
+    def set_umma_pair(self, pair: int):
+        """CTA pairs (tcgen05 cta_group::2) of the tcgen05 search: FIC_UMMA_PAIR_AUTO / _OFF / _ON."""
+        self._check(self._L.fic_set_option(self._h, _lib.FIC_OPT_UMMA_PAIR, int(pair)))
+
+    def umma_pair_used(self) -> bool:
+        """True if the last tcgen05 search of this handle ran the CTA-pair kernel."""
+        v = C.c_int(0)
+        self._check(self._L.fic_get_option(self._h, _lib.FIC_OPT_UMMA_PAIR_USED, C.byref(v)))
+        return bool(v.value)
+
     def pin(self, array: np.ndarray):
         """Page-locks a caller-owned contiguous array (fic_pin_host_buffer) so encode/decode copies run at full PCIe
         rate; pair with unpin() before the array is freed."""
@@ -240,6 +250,12 @@ class Handle:
         self._check(self._L.fic_measure_mma_peak(self._h, int(kind), int(n_cols), C.byref(v)))
         return v.value
 
+    def measure_mma_peak_pair(self, kind: int) -> float:
+        """The same for the CTA-pair shape (cta_group::2, M = 256 x N = 128)."""
+        v = C.c_double(0.0)
+        self._check(self._L.fic_measure_mma_peak_pair(self._h, int(kind), C.byref(v)))
+        return v.value
+
     def build_pool(self, argb: np.ndarray, B: int, rgb: bool):
         a = np.ascontiguousarray(argb, dtype=np.int32)
         H, W = a.shape
@@ -301,6 +317,9 @@ class MultiHandle:
 
     def set_umma_kind(self, kind: int):
         self._check(self._L.fic_multi_set_option(self._m, _lib.FIC_OPT_UMMA_KIND, int(kind)))
+
+    def set_umma_pair(self, pair: int):
+        self._check(self._L.fic_multi_set_option(self._m, _lib.FIC_OPT_UMMA_PAIR, int(pair)))
 
     def timings(self, rank: int = -1) -> Timings:
         t = Timings()

@@ -54,6 +54,8 @@ struct fic_handle {
     Work w;
     int engine_opt = FIC_ENGINE_AUTO;
     int umma_kind = FIC_UMMA_KIND_AUTO;
+    int umma_pair = FIC_UMMA_PAIR_AUTO;  // FIC_OPT_UMMA_PAIR
+    int pair_used = 0;                   // did the last tcgen05 search run the CTA-pair kernel
     int f16_state = 0;  // kind::f16 self-test: 0 not run yet, 1 exact, -1 not exact on this device (use kind::i8)
     fic_timings tm;
     char err[512];
@@ -203,6 +205,10 @@ int fic_set_option(fic_handle *h, int option, int value)
         h->umma_kind = value;
         return FIC_OK;
     }
+    if (option == FIC_OPT_UMMA_PAIR && value >= FIC_UMMA_PAIR_AUTO && value <= FIC_UMMA_PAIR_ON) {
+        h->umma_pair = value;
+        return FIC_OK;
+    }
     return set_err(h, FIC_E_ARG, "unknown option %d / value %d", option, value);
 }
 
@@ -211,6 +217,8 @@ int fic_get_option(fic_handle *h, int option, int *value)
     if (!h || !value) return FIC_E_ARG;
     if (option == FIC_OPT_ENGINE) { *value = h->engine_opt; return FIC_OK; }
     if (option == FIC_OPT_UMMA_KIND) { *value = h->umma_kind; return FIC_OK; }
+    if (option == FIC_OPT_UMMA_PAIR) { *value = h->umma_pair; return FIC_OK; }
+    if (option == FIC_OPT_UMMA_PAIR_USED) { *value = h->pair_used; return FIC_OK; }
     if (option == FIC_OPT_F16_EXACT) {
         if (h->f16_state == 0) {
             CU(cudaSetDevice(h->device));
@@ -324,6 +332,7 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     ENSURE(w.best, S_BEST, sizeof(int32_t) * g.NR);
     if (g.C == 3) ENSURE(w.dec3, S_DEC3, sizeof(uint16_t) * (size_t)g.sw * g.sh);  // R + G + B of the decimated planes
     int kind = h->umma_kind;
+    h->pair_used = 0;
     if (engine == FIC_ENGINE_UMMA) {
         // The first kind::f16 search of a handle verifies, once, that this device's f16 tensor path
         // accumulates the integer covariances exactly; a device that does not runs kind::i8 instead.
@@ -359,7 +368,7 @@ static int encode_on_device(fic_handle *h, const Geom &g, const uint8_t *d_src, 
     CU(cudaEventRecord(h->ev[7], s));
     if (engine == FIC_ENGINE_UMMA) {
         const char *why = nullptr;
-        int n = launch_search_umma(call, g, j0, j1, h->num_sms, s, &why, kind, h->ev[6], h->ev[7]);
+        int n = launch_search_umma(call, g, j0, j1, h->num_sms, s, &why, kind, h->ev[6], h->ev[7], h->umma_pair, &h->pair_used);
         if (n < 0) return set_err(h, FIC_E_CUDA, "tcgen05 search launch failed: %s", why ? why : "?");
         launches += n;
     } else {
@@ -553,6 +562,17 @@ int fic_measure_mma_peak(fic_handle *h, int kind, int n_cols, double *tops)
 }
 
 int fic_measure_int8_peak(fic_handle *h, double *tops) { return fic_measure_mma_peak(h, FIC_UMMA_KIND_I8, 256, tops); }
+
+int fic_measure_mma_peak_pair(fic_handle *h, int kind, double *tops)
+{
+    if (!h || !tops || (kind != FIC_UMMA_KIND_I8 && kind != FIC_UMMA_KIND_F16)) return FIC_E_ARG;
+    CU(cudaSetDevice(h->device));
+    const char *why = nullptr;
+    double v = measure_mma_peak_pair(h->num_sms, h->stream, 3, kind == FIC_UMMA_KIND_F16, nullptr, &why);
+    if (v < 0) return set_err(h, FIC_E_CUDA, "tensor peak measurement (CTA pairs) failed: %s", why ? why : "?");
+    *tops = v;
+    return FIC_OK;
+}
 
 int fic_build_pool(fic_handle *h, const int32_t *argb, int is_rgb, int W, int H, int B, uint8_t *decimated,
                    int32_t *dom_sum, int32_t *dom_sumsq)

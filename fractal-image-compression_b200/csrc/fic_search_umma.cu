@@ -84,6 +84,8 @@
 #include <cuda_fp16.h>
 
 #include <cmath>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "fic_device.cuh"
@@ -222,8 +224,14 @@ struct Lay {
     static constexpr int P1_BYTES = (kTileN / 8) * SBO_P1;
     static constexpr int B_TILE_BYTES = P0_BYTES + P1_BYTES;
     static constexpr int SLOT_BYTES = C::KSPLIT ? ((P0_BYTES + 127) / 128) * 128 : B_TILE_BYTES;  // one ring entry in shared memory
-    static constexpr int SMEM_BYTES = A_SB_BYTES + C::NSTAGE * SLOT_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ +
-                                      kRowsPerSB * 4 /*per-row lower bound shared by the two column halves*/;
+    // CTA pairs (tcgen05 cta_group::2, see k_umma_search<..., PAIR>): each CTA of the pair holds HALF of every domain
+    // tile (64 operand rows = the first / second 8 row groups of the blob), so the ring has twice the depth in the
+    // same shared memory (capped: the barrier area holds 2 * 12 + 10 mbarriers).
+    static constexpr int PAIR_SLOT_BYTES = B_OP_BYTES / 2;
+    static constexpr int PAIR_STAGES = (C::NSTAGE * SLOT_BYTES) / PAIR_SLOT_BYTES < 12 ? (C::NSTAGE * SLOT_BYTES) / PAIR_SLOT_BYTES : 12;
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int SMEM_BYTES = A_SB_BYTES + C::NSTAGE * SLOT_BYTES + 1024 /*alignment slack*/ + BAR_BYTES /*barriers*/ +
+                                      kRowsPerSB * 4 /*per-row lower bound shared by the rows of a range block (isometry extension)*/;
 };
 
 // Flag threshold from the best lower bound lb of the row's max x = |kov| / sqrt(varD): candidates with
@@ -903,6 +911,54 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// ---- CTA pairs (cta_group::2): the two CTAs of a cluster of 2 share one tcgen05.mma of M = 256 ----
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// Remote arrive.  Default semantics (release at CTA scope), as for the local arrives: these barriers order tcgen05 /
+// TMA (async proxy) work through tcgen05.fence and complete_tx, no generic-proxy data crosses the pair -- a
+// .release.cluster here costs a MEMBAR.GPU per hand-back and the matching .acquire.cluster wait an L1 invalidation.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit2(uint32_t bar, uint32_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma2_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile(
@@ -962,6 +1018,11 @@ constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(kTi
 // kind::f16: D = f32 (c_format 1), A = B = binary16 (format 0), both K-major.
 constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
                                ((uint32_t)(kBlockM >> 4) << 24);
+// cta_group::2: M = 256 (128 rows in each CTA of the pair), N = 128 (64 operand rows from each CTA)
+constexpr uint32_t kIdescPair = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+                                ((uint32_t)((2 * kBlockM) >> 4) << 24);
+constexpr uint32_t kIdescF16Pair = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+                                   ((uint32_t)((2 * kBlockM) >> 4) << 24);
 
 // ---------------------------------------------------------------- the search kernel --
 
@@ -974,7 +1035,15 @@ constexpr uint32_t kIdescF16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(
 // flag tests wait until the accumulator has been handed back.  (A fourth mapping -- every warp takes one chunk of
 // EVERY accumulator, so that the oldest accumulator is drained by four warps at once -- handed accumulators back
 // soonest and still lost on every configuration to its four waits per tile; profiles/README.md.)
-template <int B, bool F16, int DBG, bool DUMP, int EPI>
+//
+// PAIR: the kernel runs as clusters of two CTAs (one TPC) sharing every tcgen05.mma (cta_group::2, M = 256, N = 128):
+// each CTA keeps its own super-block (its 4 x 128 accumulator rows in its own TMEM) and supplies HALF of every domain
+// tile (64 operand rows), so a unit is (two adjacent super-blocks) x (1/n_chunks of the tiles), the ring's TMA traffic
+// and the tensor pipe's shared-memory reads of the domain operand halve.  CTA 0 of the pair issues; its commits are
+// multicast to both CTAs' barriers; CTA 1's warp 1 relays "my half has landed" to CTA 0's full barriers and CTA 1's
+// epilogue warps hand accumulators back on CTA 0's t_empty barriers (remote mbarrier arrives).  The epilogue is
+// the same code in both CTAs.  n_sb must be even.
+template <int B, bool F16, int DBG, bool DUMP, int EPI, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, const int32_t *__restrict__ vRarr,
               const float *__restrict__ nRarr, int2 *__restrict__ flag_list, int32_t *__restrict__ flag_cnt, uint32_t *__restrict__ row_lb, int n_sb,
@@ -983,13 +1052,15 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
 {
     using C = Cfg<B, F16>;
     using L = Lay<B, F16>;
-    constexpr int NSTAGE = C::NSTAGE;
+    static_assert(!PAIR || (F16 && !C::KSPLIT), "CTA pairs: kind::f16, whole-tile slots");
+    constexpr int NSTAGE = PAIR ? L::PAIR_STAGES : C::NSTAGE;
+    constexpr int SLOT = PAIR ? L::PAIR_SLOT_BYTES : L::SLOT_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [A super-block][NSTAGE domain tiles][barriers]
+    // carve: [A super-block][NSTAGE domain tiles (PAIR: half tiles)][barriers]
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     uint8_t *sB = smem + L::A_SB_BYTES;
-    uint64_t *bars = (uint64_t *)(sB + NSTAGE * L::SLOT_BYTES);
+    uint64_t *bars = (uint64_t *)(sB + C::NSTAGE * L::SLOT_BYTES);
     uint32_t bar0 = smem_u32(bars);
     asm volatile("" : "+r"(bar0));  // opaque: keep the barrier base in a register instead of rematerialising it at every use
     auto BAR_B_FULL = [&](int s) { return bar0 + 8u * s; };
@@ -999,42 +1070,52 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     const uint32_t BAR_A_FULL = bar0 + 8u * (2 * NSTAGE + 2 * kAccs);
     const uint32_t BAR_A_EMPTY = BAR_A_FULL + 8u;
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * NSTAGE + 2 * kAccs + 2);
-    uint32_t *s_lb = (uint32_t *)((uint8_t *)bars + 256);  // [kRowsPerSB] binary32 bits of the row's lower bound
+    uint32_t *s_lb = (uint32_t *)((uint8_t *)bars + L::BAR_BYTES);  // [kRowsPerSB] binary32 bits of the row's lower bound
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // PAIR: rank of this CTA in its pair; units are walked per pair (cluster), super-block 2 * (pair index) + rank
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int u_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, u_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_sbu = PAIR ? (n_sb >> 1) : n_sb;  // super-blocks (PAIR: pairs of them) per domain chunk
 
     if (warp == 1 && lane == 0) {
+        // PAIR, CTA 0: the full barriers also collect CTA 1's relayed arrival, t_empty the hand-backs of both CTAs
+        const uint32_t both = (PAIR && rank == 0) ? 2u : 1u;
         for (int s = 0; s < NSTAGE; s++) {
-            mbar_init(BAR_B_FULL(s), 1);
-            mbar_init(BAR_B_EMPTY(s), 1);  // released by the MMA issuer's commit alone: the epilogue never touches the ring
+            mbar_init(BAR_B_FULL(s), both);
+            mbar_init(BAR_B_EMPTY(s), PAIR ? 2 : 1);  // released by the MMA issuers' commits alone (PAIR: two issuers): the epilogue never touches the ring
         }
         for (int q = 0; q < kAccs; q++) {
             mbar_init(BAR_T_FULL(q), 1);
-            mbar_init(BAR_T_EMPTY(q), kEpiWarps / kAccs);  // the 4 lane quarters of the accumulator
+            mbar_init(BAR_T_EMPTY(q), both * (kEpiWarps / kAccs));  // the 4 lane quarters of the accumulator (PAIR: of both CTAs)
         }
-        mbar_init(BAR_A_FULL, 1);
-        mbar_init(BAR_A_EMPTY, 1);
+        mbar_init(BAR_A_FULL, both);
+        mbar_init(BAR_A_EMPTY, PAIR ? 2 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {  // one warp of EACH CTA of the pair
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's barriers are initialised and its TMEM allocated before anything remote
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_units = n_sb * n_chunks;
+    const int n_units = n_sbu * n_chunks;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, a_phase = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                int sb = u % n_sb, ch = u / n_sb;  // chunk-major: see the epilogue (bounds carried between units)
+            for (int u = u_first; u < n_units; u += u_step) {
+                int sb = PAIR ? 2 * (u % n_sbu) + (int)rank : u % n_sbu, ch = u / n_sbu;  // chunk-major: see the epilogue (bounds carried between units)
                 int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
                 mbar_wait(BAR_A_EMPTY, a_phase ^ 1, status, 1);
                 mbar_expect_tx(BAR_A_FULL, L::A_SB_BYTES);
@@ -1054,6 +1135,12 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                             bulk_g2s(smem_u32(sB + stage * L::SLOT_BYTES), blob + L::P0_BYTES, L::P1_BYTES, BAR_B_FULL(stage));
                             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                         }
+                    } else if (PAIR) {
+                        // this CTA's half of the tile: operand rows 64 * rank .. 64 * rank + 63 (8 row groups, contiguous)
+                        mbar_wait(BAR_B_EMPTY(stage), phase ^ 1, status, 2);
+                        mbar_expect_tx(BAR_B_FULL(stage), SLOT);
+                        bulk_g2s(smem_u32(sB + stage * SLOT), blob + rank * SLOT, SLOT, BAR_B_FULL(stage));
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     } else {
                         mbar_wait(BAR_B_EMPTY(stage), phase ^ 1, status, 2);
                         mbar_expect_tx(BAR_B_FULL(stage), L::B_TILE_BYTES);
@@ -1065,6 +1152,106 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             }
         }
         __syncwarp();
+    } else if (PAIR && (warp == 1 || warp == 3)) {
+        // ===================== MMA issuers of a pair (CTA 0) =====================
+        // What bounds the pair kernel once the operands stream at full rate is the issuing thread itself: per
+        // accumulator one barrier wait, the descriptor moves into uniform registers, four tcgen05.mma and a commit
+        // -- a serial chain of 250-300 clocks on a sub-partition it shares with four busy epilogue warps, against
+        // 256 clocks of tensor work.  Two warps on different sub-partitions therefore issue side by side: warp 1
+        // owns accumulators 0 and 2, warp 3 accumulators 1 and 3.  MMAs of different accumulators need no mutual
+        // order; a ring slot (and the A super-block) is free once BOTH issuers' commits have arrived.
+        if constexpr (PAIR) {
+            if (rank == 0) {
+                const int qi = warp >> 1;  // 0 or 1
+                uint32_t stage = 0, phase = 0, a_phase = 0, t_phase = 0;
+                const uint32_t elected = elect_one();
+                const long long clk0 = clock64();
+                unsigned long long ns0 = 0;
+                if (status) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+                const uint64_t a_desc0 = make_desc(smem_u32(sA), lbo_bytes_a, sbo_bytes_a);
+                const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo_bytes_b, sbo_bytes_b);
+                uint32_t iw_t = 0, iw_b = 0;
+                uint32_t ts_e[2] = {0, 0}, ts_i[2] = {0, 0};
+                for (int u = u_first; u < n_units; u += u_step) {
+                    int ch = u / n_sbu;
+                    int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
+                    mbar_wait(BAR_A_FULL, a_phase, status, 3);
+                    for (int t = t0; t < t1; t++) {
+                        const uint32_t wb0 = (DBG & 8) ? (uint32_t)clock() : 0u;
+                        mbar_wait(BAR_B_FULL(stage), phase, status, 4);  // both halves: this CTA's copy + the peer's relayed arrival
+                        if (DBG & 8) iw_b += (uint32_t)clock() - wb0;
+                        tc_fence_after();
+                        const uint64_t b_desc = b_desc0 + (uint64_t)((stage * SLOT) >> 4);
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const int q = qi + 2 * k;
+                            const uint32_t w0 = (DBG & 8) ? (uint32_t)clock() : 0u;
+                            mbar_wait(BAR_T_EMPTY(q), ((t_phase >> k) & 1) ^ 1, status, 5);  // the epilogue warps of both CTAs
+                            if (DBG & 8) {
+                                const uint32_t now = (uint32_t)clock();
+                                iw_t += now - w0;
+                                ts_e[k] += now;
+                            }
+                            tc_fence_after();
+                            if (elected) {
+#pragma unroll
+                                for (int s = 0; s < C::NS; s++) {
+                                    if ((DBG & 4) && t != t0) continue;  // probe only: epilogue without the tensor pipe
+                                    const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + C::amap(s) * 256) >> 4);
+                                    tc_mma2_f16(tmem_base + q * kTileN, ad, b_desc + (uint64_t)((s * 256) >> 4), kIdescF16Pair, s > 0 ? 1u : 0u);
+                                }
+                                tc_commit2(BAR_T_FULL(q), 3u);
+                                if (k == 1) tc_commit2(BAR_B_EMPTY(stage), 3u);  // this issuer's MMAs have read both CTAs' slots
+                            }
+                            __syncwarp();
+                            if (DBG & 8) ts_i[k] += (uint32_t)clock();
+                            t_phase ^= 1u << k;
+                        }
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+                    if (elected) tc_commit2(BAR_A_EMPTY, 3u);  // this issuer's MMAs on the A super-block have completed
+                    __syncwarp();
+                    a_phase ^= 1;
+                }
+                if (status && blockIdx.x == 0 && elected && qi == 0) {
+                    const long long dt = clock64() - clk0;
+                    unsigned long long ns1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+                    status[2] = (int)(dt & 0x7fffffff);
+                    status[3] = (int)(dt >> 31);
+                    status[4] = (int)(ns1 - ns0);  // the same interval in nanoseconds: the SM's real clock under load
+                    status[5] = (int)iw_t;
+                    status[6] = (int)iw_b;
+                }
+                if ((DBG & 8) && dump && blockIdx.x == 0 && elected) {
+                    for (int k = 0; k < 2; k++) {
+                        dump[32768 + qi + 2 * k] = (int32_t)ts_e[k];
+                        dump[32768 + kAccs + qi + 2 * k] = (int32_t)ts_i[k];
+                    }
+                }
+            } else if (warp == 1) {
+                // ===================== relay (CTA 1 of a pair) =====================
+                // CTA 0 issues the pair's MMAs and must know that CTA 1's operands have landed: one thread follows this
+                // CTA's own full barriers and forwards every completion to the barrier at the same offset in CTA 0.
+                if (lane == 0) {
+                    uint32_t stage = 0, phase = 0, a_phase = 0;
+                    const uint32_t ra_full = mapa_u32(BAR_A_FULL, 0);
+                    for (int u = u_first; u < n_units; u += u_step) {
+                        int ch = u / n_sbu;
+                        int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
+                        mbar_wait(BAR_A_FULL, a_phase, status, 3);
+                        mbar_arrive_cluster(ra_full);
+                        for (int t = t0; t < t1; t++) {
+                            mbar_wait(BAR_B_FULL(stage), phase, status, 4);
+                            mbar_arrive_cluster(mapa_u32(BAR_B_FULL(stage), 0));
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        }
+                        a_phase ^= 1;
+                    }
+                }
+                __syncwarp();
+            }
+        }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // The whole warp walks the (warp-uniform) loop so that addresses and descriptors live in
@@ -1072,15 +1259,21 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         uint32_t stage = 0, phase = 0, a_phase = 0, t_phase = 0;  // t_phase: bit q
         const uint32_t elected = elect_one();
         const long long clk0 = clock64();  // probe only (status != nullptr): elapsed SM clocks of CTA 0's issuer
+        unsigned long long ns0 = 0;
+        if (status) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
         // descriptors differ only in the 14-bit start-address field (16-byte units)
         const uint64_t a_desc0 = make_desc(smem_u32(sA), lbo_bytes_a, sbo_bytes_a);
         const uint64_t b_desc0 = make_desc(smem_u32(sB), lbo_bytes_b, sbo_bytes_b);
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            int ch = u / n_sb;
+        uint32_t iw_t = 0, iw_b = 0;  // DBG & 8: clocks the issuer spent waiting for accumulators / for domain tiles
+        uint32_t ts_e[kAccs] = {0, 0, 0, 0}, ts_i[kAccs] = {0, 0, 0, 0};  // DBG & 8: sums (mod 2^32) of the clock at "accumulator free seen" / "MMAs issued"
+        for (int u = u_first; u < n_units; u += u_step) {
+            int ch = u / n_sbu;
             int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
             mbar_wait(BAR_A_FULL, a_phase, status, 3);
             for (int t = t0; t < t1; t++) {
+                const uint32_t wb0 = (DBG & 8) ? (uint32_t)clock() : 0u;
                 mbar_wait(BAR_B_FULL(stage), phase, status, 4);
+                if (DBG & 8) iw_b += (uint32_t)clock() - wb0;
                 tc_fence_after();
                 // tile flag written by k_umma_pack_domains: 0 -> every low digit of the tile is zero
                 const uint32_t has_l = *(volatile const uint32_t *)(sB + stage * L::SLOT_BYTES + L::B_OP_BYTES + kChunksPerTile * 8);
@@ -1164,8 +1357,19 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         }
         if (status && blockIdx.x == 0 && elected) {
             const long long dt = clock64() - clk0;
+            unsigned long long ns1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
             status[2] = (int)(dt & 0x7fffffff);
             status[3] = (int)(dt >> 31);
+            status[4] = (int)(ns1 - ns0);  // the same interval in nanoseconds: the SM's real clock under load
+            status[5] = (int)iw_t;
+            status[6] = (int)iw_b;
+            if ((DBG & 8) && dump) {
+                for (int q = 0; q < kAccs; q++) {
+                    dump[32768 + q] = (int32_t)ts_e[q];
+                    dump[32768 + kAccs + q] = (int32_t)ts_i[q];
+                }
+            }
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
@@ -1177,6 +1381,12 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         const int lq = e & 3, q = e >> 2;
         const uint32_t ta = tmem_base + ((uint32_t)(lq * 32) << 16) + q * kTileN;
         uint32_t tf_phase = 0;
+        // hand-back target: this CTA's t_empty[q]; PAIR: the issuing CTA's (a shared::cluster address)
+        const uint32_t bar_hand_back = PAIR ? mapa_u32(BAR_T_EMPTY(q), 0) : BAR_T_EMPTY(q);
+        auto hand_back = [&]() {
+            if (PAIR) mbar_arrive_cluster(bar_hand_back);
+            else mbar_arrive(bar_hand_back);
+        };
         // RGB at blockgroesse 16: the float covariances (the reference's sequential sum and the tensor core's) may
         // round once partial sums pass 2^24; see the chunk test below.  Warps of unused accumulators idle.
         constexpr bool SLACK = B == 16 && F16;
@@ -1184,6 +1394,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         // DBG & 8 (probe only): per-warp cycle accounting of the epilogue phases.  tcgen05.wait::ld is a
         // scoreboard wait, so the TMEM latency shows up at the first use of the loaded registers ("math").
         uint32_t tk_b = 0, tk_t = 0, tk_l = 0, tk_m = 0, tk_mark = 0;
+        uint32_t ts_f = 0, ts_h = 0;  // DBG & 8: sums (mod 2^32) of the clock at "t_full seen" / "handed back"
         const uint32_t tk_begin = (DBG & 8) ? (uint32_t)clock() : 0u;
         auto tick = [&](uint32_t &acc) {
             if (DBG & 8) {
@@ -1192,11 +1403,11 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 tk_mark = now;
             }
         };
-        for (int u = blockIdx.x; u < n_units_mine; u += gridDim.x) {
+        for (int u = u_first; u < n_units_mine; u += u_step) {
             // Units are ordered chunk-major (u = ch * n_sb + sb): the units of one super-block run in different
             // waves, so the lower bound a row reached in an earlier unit (row_lb, global memory) can seed the
             // later ones -- any earlier bound is a valid bound, a missed one only costs extra flags.
-            int sb = u % n_sb, ch = u / n_sb;
+            int sb = PAIR ? 2 * (u % n_sbu) + (int)rank : u % n_sbu, ch = u / n_sbu;
             int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
             // Running filter state of this thread's row (see the file header).  vR == 0: every candidate
             // scores error 0 and the first one wins (FC:677-678, FC:627) -> never flag.
@@ -1245,6 +1456,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                     }
                 }
                 tick(tk_t);
+                if (DBG & 8) ts_f += tk_mark;
                 if constexpr ((EPI == 2 || EPI == 3) && F16 && !DUMP && !(DBG & 3)) {
                     // Software-pipelined visit (kind::f16).  The first level of the |.| max tree reads all 32 registers
                     // of a chunk in 11 instructions; the load of the NEXT chunk is issued behind them (into the same
@@ -1293,7 +1505,9 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                                 // the accumulator's last chunk is in registers: hand it back
                                 tc_fence_before();
                                 __syncwarp();
-                                if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
+                                if (lane == 0) hand_back();
+                                tick(tk_l);  // t_full seen -> accumulator handed back
+                                if (DBG & 8) ts_h += tk_mark;
                                 if (EPI == 3) {  // the deferred tests of the first three chunks, in sweep order
                                     asm volatile("" : "+f"(Mc[0]), "+f"(Mc[1]), "+f"(Mc[2]) : : "memory");
                                     test(0);
@@ -1304,6 +1518,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                         }
                     }
                     if (EPI == 3) test(kChunksPerTile - 1);
+                    tick(tk_m);  // hand-back -> end of the visit
                 } else {
 #pragma unroll
                 for (int c = 0; c < kChunksPerTile; c++) {
@@ -1317,7 +1532,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                         // last read of accumulator q for this tile: hand it back
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(BAR_T_EMPTY(q));
+                        if (lane == 0) hand_back();
                     }
                     if (DBG & 1) continue;  // probe only: measure the pipeline without the scoring
                     float M;  // max |kov| over the chunk, exact
@@ -1400,14 +1615,18 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             o[2] = (int32_t)tk_t;
             o[3] = (int32_t)tk_l;
             o[4] = (int32_t)tk_m;
+            o[5] = (int32_t)ts_f;
+            o[6] = (int32_t)ts_h;
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();  // neither CTA leaves (shared memory, barriers, TMEM) while the other may still touch it
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -1471,6 +1690,67 @@ __global__ void __launch_bounds__(128, 1) k_mma_peak(int iters, uint32_t seed)
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// The same loop issued by CTA pairs: tcgen05.mma.cta_group::2, M = 256 (128 rows per CTA), N = 128 (64 operand rows
+// per CTA): per MMA an SM reads 4 KB of A and 2 KB of B from its shared memory instead of 4 + 4.  out[blockIdx.x]
+// receives the CTA's TMEM base address (both CTAs of a pair must report the same one).
+template <bool F16>
+__global__ void __launch_bounds__(128, 1) k_mma_peak_pair(int iters, uint32_t seed, uint32_t *out)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                 // 128 rows x 32 B, core-matrix order (16 groups x 256 B)
+    uint8_t *sB = smem + 4096;          // this CTA's 64 of the 128 B rows x 32 B
+    uint64_t *bar = (uint64_t *)(smem + 4096 + 8192);
+    uint32_t *tmem_slot = (uint32_t *)(bar + 1);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = cluster_ctarank();
+    for (int i = threadIdx.x; i < (4096 + 8192) / 4; i += blockDim.x) {
+        uint32_t x = (uint32_t)i * 2654435761u + seed + blockIdx.x * 40503u;
+        x ^= x >> 15; x *= 0x2c1b3c6du; x ^= x >> 12;
+        if (F16) x &= 0x3fff3fffu;
+        ((uint32_t *)smem)[i] = x;
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0 && out) out[blockIdx.x] = tmem_base;
+    if (warp == 1) {
+        if (rank == 0) {
+            const uint32_t elected = elect_one();
+            const uint64_t ad = make_desc(smem_u32(sA), 128, 256);
+            const uint64_t bd = make_desc(smem_u32(sB), 128, 256);
+            constexpr uint32_t idesc = (F16 ? ((1u << 4) | (0u << 7) | (0u << 10)) : ((2u << 4) | (0u << 7) | (1u << 10))) |
+                                       ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            if (elected) {
+                for (int i = 0; i < iters; i++) {
+                    const uint32_t d = tmem_base + (uint32_t)(i & 1) * 128;
+                    if (F16) tc_mma2_f16(d, ad, bd, idesc, i >= 2 ? 1u : 0u);
+                    else tc_mma2_i8(d, ad, bd, idesc, i >= 2 ? 1u : 0u);
+                }
+                tc_commit2(smem_u32(bar), 3u);
+            }
+            __syncwarp();
+        }
+        mbar_wait(smem_u32(bar), 0, nullptr, 9);  // both CTAs: the pair's MMAs have completed
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }
 }
 
@@ -1840,7 +2120,9 @@ inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
 {
     Plan p;
     const int rows_sb = rows_per_sb(g);
-    p.rp = pad_up(rows, rows_sb);
+    // an even number of 512-row super-blocks: CTA pairs (k_umma_search<..., PAIR>) take two at a time; padding rows
+    // are zero operands with vR = 0 (never flagged)
+    p.rp = pad_up(rows, rows_sb == kRowsPerSB ? 2 * rows_sb : rows_sb);
     p.n_sb = (int)(p.rp / rows_sb);
     p.ntiles = (int)((g.ND + kTileN - 1) / kTileN);
     p.npos = (int64_t)p.ntiles * kTileN;
@@ -1900,16 +2182,63 @@ using KernelT = void (*)(const uint8_t *, const uint8_t *, const int32_t *, cons
                          int, int, int64_t, int32_t *, int64_t, volatile int *, uint32_t, uint32_t, uint32_t, uint32_t);
 
 // dbg (probe only): 1 / 3 strip the scoring / the TMEM loads too, 4: epilogue alone, 8 / 12: phase cycle counts
-template <int B, bool F16, int EPI>
+template <int B, bool F16, int EPI, bool PAIR = false>
 KernelT pick_kernel(bool dump, uint32_t dbg)
 {
-    if (dump) return k_umma_search<B, F16, 0, true, EPI>;
-    if ((dbg & 3u) == 1) return k_umma_search<B, F16, 1, false, EPI>;
-    if ((dbg & 3u) == 3) return k_umma_search<B, F16, 3, false, EPI>;
-    if (dbg == 4) return k_umma_search<B, F16, 4, false, EPI>;
-    if (dbg == 8) return k_umma_search<B, F16, 8, false, EPI>;
-    if (dbg == 12) return k_umma_search<B, F16, 12, false, EPI>;
-    return k_umma_search<B, F16, 0, false, EPI>;
+    if (dump) return k_umma_search<B, F16, 0, true, EPI, PAIR>;
+    if ((dbg & 3u) == 1) return k_umma_search<B, F16, 1, false, EPI, PAIR>;
+    if ((dbg & 3u) == 3) return k_umma_search<B, F16, 3, false, EPI, PAIR>;
+    if (dbg == 4) return k_umma_search<B, F16, 4, false, EPI, PAIR>;
+    if (dbg == 8) return k_umma_search<B, F16, 8, false, EPI, PAIR>;
+    if constexpr (!PAIR) {
+        if (dbg == 12) return k_umma_search<B, F16, 12, false, EPI>;
+    }
+    return k_umma_search<B, F16, 0, false, EPI, PAIR>;
+}
+
+// CTA pairs exist for the kind::f16 kernels with whole-tile ring slots (B = 4, 8; grey, RGB and the isometry extension).
+// Default where measured faster: B = 8 (17.6 against 20.8 ms at 4096^2); B = 4 is bound by its epilogue (K = 16 keeps the
+// tensor pipe a quarter busy) and loses 4 % to the pair's extra barrier traffic.
+template <int B, bool F16>
+constexpr bool pair_capable() { return F16 && !Cfg<B, F16>::KSPLIT; }
+template <int B, bool F16>
+constexpr bool pair_default() { return pair_capable<B, F16>() && B == 8; }
+
+// Can a cluster of two CTAs of this kernel be co-scheduled on this device (it cannot under some MIG / MPS partitions)?
+inline bool pair_launchable(KernelT kern, int smem_bytes)
+{
+    // asked once per (kernel, device): the occupancy query is a host-side driver call
+    static std::mutex mu;
+    static std::vector<std::tuple<KernelT, int, bool>> known;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (const auto &k : known)
+            if (std::get<0>(k) == kern && std::get<1>(k) == dev) return std::get<2>(k);
+    }
+    const bool ok = [&]() {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, (const void *)kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return n >= 1;
+    }();
+    std::lock_guard<std::mutex> lock(mu);
+    known.emplace_back(kern, dev, ok);
+    return ok;
 }
 
 // Epilogue variant each configuration runs by default (measured, profiles/README.md): kind::f16 B = 8 gains 1.5-5 %
@@ -1920,7 +2249,7 @@ constexpr int default_epi() { return (!F16 || B == 16) ? 0 : (B == 4 ? 3 : 2); }
 template <int B, bool F16>
 int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s, const char **err,
              int32_t *dump, int64_t dump_ld, int *status_dev, int variant, cudaEvent_t k0 = nullptr,
-             cudaEvent_t k1 = nullptr, uint32_t dbg = 0)
+             cudaEvent_t k1 = nullptr, uint32_t dbg = 0, int *pair_used = nullptr)
 {
     using L = Lay<B, F16>;
     if (j1 <= j0) return 0;
@@ -1967,22 +2296,58 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     // 3. the fused search
     // Epilogue mapping (see k_umma_search): the default of this (block size, kind) pair, or the probe's choice
     // (variant bit 1: plain, bit 3: software-pipelined, bit 4: pipelined with deferred flag tests).
+    // CTA pairs: variant bit 5 = on, bit 6 = off, neither = where measured faster (pair_default).  The pair kernel runs
+    // the deferred-test epilogue (EPI 3) unless the probe asks for EPI 2: with the tensor pipe at its full rate the
+    // earlier hand-back is worth 10 %.
     const int epi = (variant & 2) ? 0 : ((variant & 8) ? 2 : ((variant & 16) ? 3 : default_epi<B, F16>()));
+    bool pair = false;
+    if constexpr (pair_capable<B, F16>())
+        pair = ((variant & 32) ? true : ((variant & 64) ? false : pair_default<B, F16>())) && dbg != 12 && num_sms >= 2;
     KernelT kern = pick_kernel<B, F16, 0>(dump && !(dbg & 8u), dbg);
     if (epi == 2) kern = pick_kernel<B, F16, 2>(dump && !(dbg & 8u), dbg);
     if (epi == 3) kern = pick_kernel<B, F16, 3>(dump && !(dbg & 8u), dbg);
+    if constexpr (pair_capable<B, F16>()) {
+        if (pair) {
+            KernelT pk = (variant & 8) ? pick_kernel<B, F16, 2, true>(dump, dbg) : pick_kernel<B, F16, 3, true>(dump, dbg);
+            ce = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
+            if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
+            if (pair_launchable(pk, L::SMEM_BYTES)) kern = pk;
+            else pair = false;  // no co-scheduled CTA pairs on this device / partition: the single-CTA kernel
+        }
+    }
+    if (pair_used) *pair_used = pair ? 1 : 0;
     if (dbg == 8 || dbg == 12) dump = w.best;  // phase cycle counts -> w.best
     ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
-    int n_units = p.n_sb * p.n_chunks;
-    int grid = n_units < num_sms ? n_units : num_sms;
+    int n_units = pair ? (p.n_sb / 2) * p.n_chunks : p.n_sb * p.n_chunks;
+    const int slots = pair ? num_sms / 2 : num_sms;  // CTAs, or CTA pairs (one TPC each)
+    int grid = (n_units < slots ? n_units : slots) * (pair ? 2 : 1);
     uint32_t lbo_a = 128, sbo_a = L::SBO_A, lbo_b = 128, sbo_b = L::SBO_B;
     if (variant & 1) { lbo_a = L::SBO_A; sbo_a = 128; lbo_b = L::SBO_B; sbo_b = 128; }  // probe only
     if (k0) cudaEventRecord(k0, s);
     cudaMemsetAsync(row_lb, 0, (size_t)rp * 4, s);
-    kern<<<grid, kThreads, L::SMEM_BYTES, s>>>(opA, w.opB, vR, row_norm, flag_list, flag_cnt, row_lb, p.n_sb, p.n_chunks, p.ntiles,
-                                               g.n_iso > 1 ? 3 : 0, rp,
-                                               dump, dump_ld, status_dev, lbo_a, sbo_a, lbo_b, sbo_b);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = L::SMEM_BYTES;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = pair ? 1 : 0;
+        const uint8_t *opA_c = opA, *opB_c = w.opB;
+        const int32_t *vR_c = vR;
+        const float *norm_c = row_norm;
+        const int iso_shift = g.n_iso > 1 ? 3 : 0;
+        volatile int *status_v = status_dev;
+        ce = cudaLaunchKernelEx(&cfg, kern, opA_c, opB_c, vR_c, norm_c, flag_list, flag_cnt, row_lb, p.n_sb, p.n_chunks, p.ntiles, iso_shift,
+                                rp, dump, dump_ld, status_v, lbo_a, sbo_a, lbo_b, sbo_b);
+        if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
+    }
     if (k1) cudaEventRecord(k1, s);
     // 4. exact refine of the flagged chunks
     if (!(dbg & 8u)) {
@@ -2193,6 +2558,53 @@ int umma_debug_sort(uint32_t *d_keys, int32_t *d_vals, uint32_t *d_keys_out, int
     return (int)ce;
 }
 
+// Bare loop of the CTA-pair instruction shape (cta_group::2, M = 256, N = 128): TOP/s, best of `reps`; tmem_bases (if
+// not null) receives the TMEM base address each of the first 4 CTAs was given.
+double measure_mma_peak_pair(int num_sms, cudaStream_t s, int reps, int f16, uint32_t *tmem_bases, const char **err)
+{
+    const int smem = 200 * 1024;
+    void (*kern)(int, uint32_t, uint32_t *) = f16 ? k_mma_peak_pair<true> : k_mma_peak_pair<false>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1.0; }
+    uint32_t *d_out = nullptr;
+    if (cudaMalloc((void **)&d_out, 4 * (size_t)num_sms) != cudaSuccess) { *err = "cudaMalloc"; return -1.0; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 200000 * 2;
+    const double k_per_mma = f16 ? 16.0 : 32.0;
+    const int grid = num_sms / 2 * 2;
+    double best = 0.0;
+    for (int r = 0; r < reps + 1; r++) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaEventRecord(e0, s);
+        ce = cudaLaunchKernelEx(&cfg, kern, iters, (uint32_t)(0x9e3779b9u + r), d_out);
+        cudaEventRecord(e1, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); best = -1.0; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tops = 2.0 * 256.0 * 128.0 * k_per_mma * (double)iters * (grid / 2) / (ms * 1e-3) / 1e12;
+        if (r > 0 && tops > best) best = tops;
+    }
+    if (tmem_bases && best >= 0.0) cudaMemcpy(tmem_bases, d_out, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return best;
+}
+
 bool umma_applicable(const Geom &g)
 {
     if (g.wk != g.dpw || g.wk != g.dph) return false;
@@ -2221,9 +2633,9 @@ size_t umma_opB_bytes(const Geom &g, int kind)
 // (row, sweep position) pair, and lets the probe pick the descriptor variant.
 int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s,
                              const char **err, int kind, int32_t *dump, int64_t dump_ld, int *status_dev, int variant,
-                             uint32_t dbg, cudaEvent_t k0, cudaEvent_t k1)
+                             uint32_t dbg, cudaEvent_t k0, cudaEvent_t k1, int *pair_used)
 {
-#define FIC_UMMA_ARGS w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg
+#define FIC_UMMA_ARGS w, g, j0, j1, num_sms, s, err, dump, dump_ld, status_dev, variant, k0, k1, dbg, pair_used
     return FIC_UMMA_DISPATCH(g.B, use_f16(g, kind), (launch_t<4, false>(FIC_UMMA_ARGS)), (launch_t<8, false>(FIC_UMMA_ARGS)),
                              (launch_t<16, false>(FIC_UMMA_ARGS)), (launch_t<4, true>(FIC_UMMA_ARGS)),
                              (launch_t<8, true>(FIC_UMMA_ARGS)), (launch_t<16, true>(FIC_UMMA_ARGS)));
@@ -2231,9 +2643,10 @@ int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j
 }
 
 int launch_search_umma(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, cudaStream_t s,
-                       const char **err, int kind, cudaEvent_t k0, cudaEvent_t k1)
+                       const char **err, int kind, cudaEvent_t k0, cudaEvent_t k1, int pair, int *pair_used)
 {
-    return launch_search_umma_debug(w, g, j0, j1, num_sms, s, err, kind, nullptr, 0, nullptr, 0, 0, k0, k1);
+    const int variant = pair == FIC_UMMA_PAIR_ON ? 32 : (pair == FIC_UMMA_PAIR_OFF ? 64 : 0);
+    return launch_search_umma_debug(w, g, j0, j1, num_sms, s, err, kind, nullptr, 0, nullptr, variant, 0, k0, k1, pair_used);
 }
 
 }  // namespace fic

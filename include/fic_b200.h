@@ -72,12 +72,23 @@ extern "C" {
 #define FIC_UMMA_KIND_I8 1   /* u8 x s8 -> s32, two s8 digits per centred domain pixel    */
 #define FIC_UMMA_KIND_F16 2  /* binary16 x binary16 -> binary32 (B = 16 still runs i8)    */
 
+/* CTA pairs of the tcgen05 search (fic_set_option(FIC_OPT_UMMA_PAIR, ...)): two CTAs of one TPC share every
+ * tcgen05.mma (cta_group::2, M = 256), each supplying half of every domain tile.  Same codes either way.  The
+ * pair kernel exists for kind::f16 at blockgroesse 4 and 8 (grey, RGB, isometry extension); elsewhere, and on a
+ * device partition that cannot co-schedule a 2-CTA cluster, the option is ignored. */
+#define FIC_UMMA_PAIR_AUTO 0 /* pairs where measured faster: blockgroesse 8 */
+#define FIC_UMMA_PAIR_OFF 1
+#define FIC_UMMA_PAIR_ON 2
+
 #define FIC_OPT_ENGINE 1
 #define FIC_OPT_UMMA_KIND 2
 /* Read-only (fic_get_option): 1 if this device's kind::f16 tensor path reproduced the exact integer
  * covariances in the library's self-test (run once per handle, before the first kind::f16 search);
  * 0 means the handle silently runs kind::i8 (RGB: the CUDA-core search) instead. */
 #define FIC_OPT_F16_EXACT 3
+#define FIC_OPT_UMMA_PAIR 4
+/* Read-only: 1 if the handle's last tcgen05 search ran the CTA-pair kernel. */
+#define FIC_OPT_UMMA_PAIR_USED 5
 
 typedef struct fic_handle fic_handle;
 typedef struct fic_multi fic_multi; /* one context over several GPUs of the node, see "multi-GPU" below */
@@ -220,6 +231,10 @@ int fic_measure_int8_peak(fic_handle *h, double *tops);
 /* The same loop for either instruction kind (FIC_UMMA_KIND_I8 / FIC_UMMA_KIND_F16) and MMA shape
  * M = 128 x N = n_cols (128: the shape the search issues; 256: the widest single-CTA shape). */
 int fic_measure_mma_peak(fic_handle *h, int kind, int n_cols, double *tops);
+
+/* The loop issued by CTA pairs (tcgen05.mma.cta_group::2, M = 256, N = 128: the shape the pair form of the
+ * search kernel issues, FIC_OPT_UMMA_PAIR). */
+int fic_measure_mma_peak_pair(fic_handle *h, int kind, double *tops);
 
 /* ---- domain pool inspection (tests / debugging; not on the hot path) ---------- */
 

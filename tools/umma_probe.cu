@@ -568,6 +568,13 @@ int main(int argc, char **argv)
                 double t = measure_mma_peak(prop.multiProcessorCount, s, 3, f16, n, &err);
                 printf("peak kind::%s M=128 N=%d: %.1f TOP/s %s\n", f16 ? "f16" : "i8", n, t, t < 0 ? err : "");
             }
+        for (int f16 = 0; f16 < 2; f16++) {  // CTA pairs: cta_group::2, M = 256, N = 128
+            const char *err = "";
+            uint32_t bases[4] = {0xdeadu, 0xdeadu, 0xdeadu, 0xdeadu};
+            double t = measure_mma_peak_pair(prop.multiProcessorCount, s, 3, f16, bases, &err);
+            printf("peak kind::%s cta_group::2 M=256 N=128: %.1f TOP/s %s  (TMEM bases of CTAs 0-3: %x %x %x %x)\n", f16 ? "f16" : "i8", t,
+                   t < 0 ? err : "", bases[0], bases[1], bases[2], bases[3]);
+        }
         return 0;
     }
     bool check = !strcmp(argv[1], "check");
@@ -630,7 +637,7 @@ int main(int argc, char **argv)
 
     int ntiles = (int)((g.ND + 127) / 128);
     int64_t dump_ld = (int64_t)ntiles * 128;
-    int64_t rp = (g.NR + 511) / 512 * 512;
+    int64_t rp = (g.NR + 1023) / 1024 * 1024;  // make_plan pads the rows to an even number of super-blocks
     int32_t *dump = nullptr;
     if (check) {
         CK(cudaMalloc(&dump, (size_t)rp * dump_ld * 4));
@@ -651,8 +658,9 @@ int main(int argc, char **argv)
         float ms_k = 0;
         CK(cudaEventElapsedTime(&ms_k, k0, k1));
         const long long clk = (long long)status_h[2] | ((long long)status_h[3] << 31);
-        printf("umma search run %d: pack+search+merge %.3f ms, k_umma_search alone %.3f ms   dbg=%u status=%d   CTA 0 issuer: %lld clk (%.3f GHz)\n", r,
-               ms_umma, ms_k, dbg, *status_h, clk, ms_k > 0 ? clk / (ms_k * 1e6) : 0.0);
+        printf("umma search run %d: pack+search+merge %.3f ms, k_umma_search alone %.3f ms   dbg=%u status=%d   CTA 0 issuer: %lld clk in %.3f ms (%.3f GHz)\n", r,
+               ms_umma, ms_k, dbg, *status_h, clk, status_h[4] * 1e-6, status_h[4] > 0 ? clk / (double)status_h[4] : 0.0);
+        if (dbg & 8u) printf("  issuer waits: accumulators %u clk, domain tiles %u clk\n", (unsigned)status_h[5], (unsigned)status_h[6]);
     }
     CK(cudaMemcpy(best_umma.data(), w.best, 4 * g.NR, cudaMemcpyDeviceToHost));
     double evals = (double)g.NR * (double)g.ND;
@@ -714,9 +722,22 @@ int main(int argc, char **argv)
         for (int cta = 0; cta < 2; cta++)
             for (int e = 0; e < 16; e++) {
                 const int32_t *o = &best_umma[(size_t)(cta * 16 + e) * 8];
-                printf("cta %d epilogue warp %2d: total %9d clk  wait B_FULL %5.1f%%  wait T_FULL %5.1f%%  LDTM %5.1f%%  math %5.1f%%\n", cta, e,
+                printf("cta %d epilogue warp %2d: total %9d clk  bounds+rest %5.1f%%  wait T_FULL %5.1f%%  to hand-back %5.1f%%  after %5.1f%%\n", cta, e,
                        o[0], 100.0 * o[1] / o[0], 100.0 * o[2] / o[0], 100.0 * o[3] / o[0], 100.0 * o[4] / o[0]);
             }
+    }
+    if (dbg & 8u) {  // hand-over chain of CTA 0 (pair kernel): average clocks between the four events of an accumulator's cycle
+        const long long tiles = (long long)(((g.ND + 127) / 128));
+        const int32_t *is = &best_umma[32768];
+        printf("CTA 0 hand-over chain (sums mod 2^32; divide by the tiles CTA 0 walked):\n");
+        for (int q = 0; q < 4; q++)
+            for (int lq = 0; lq < 4; lq++) {
+                const int32_t *o = &best_umma[(size_t)(q * 4 + lq) * 8];
+                printf("  acc %d quarter %d: sum(full seen - issued) %u  sum(handed back - full seen) %u  sum(free seen - handed back) %d  sum(issued - free seen) %u\n", q, lq,
+                       (unsigned)((uint32_t)o[5] - (uint32_t)is[4 + q]), (unsigned)((uint32_t)o[6] - (uint32_t)o[5]),
+                       (int)((uint32_t)is[q] - (uint32_t)o[6]), (unsigned)((uint32_t)is[4 + q] - (uint32_t)is[q]));
+            }
+        (void)tiles;
     }
     if (dbg & 15u) { printf("dbg run: winners not checked\nPROBE DONE\n"); return 0; }
     long long diff = 0, shown = 0;
