@@ -28,7 +28,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 # DRAM bytes (read + write) of one k_umma_search launch from `ncu --set full` (profiles/), by (kind, size, B)
-TRAFFIC = {("i8", 4096, 8): 1428918000, ("f16", 4096, 8): 651115008}
+TRAFFIC = {("i8", 4096, 8): 1428918000, ("f16", 4096, 8): 651115008, ("f16_pair", 4096, 8): 659304704}
 sys.path.insert(0, ROOT)
 
 

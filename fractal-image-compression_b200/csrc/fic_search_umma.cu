@@ -81,6 +81,18 @@
 // A work unit is (super-block of 512 rows) x (1/n_chunks of the domain tiles); units are
 // ordered chunk-major and a row's lower bound is carried from unit to unit (row_lb).  (RGB at B = 16:
 // 256-row super-blocks, two of the four accumulators, Cfg<16, true>.)
+//
+// CTA pairs (kind::f16 at B = 8 by default; FIC_OPT_UMMA_PAIR): the kernel runs as clusters of two CTAs -- the two SMs
+// of a TPC -- that share every tcgen05.mma (cta_group::2, M = 256, N = 128).  Each CTA keeps its own super-block
+// (its 4 accumulators of 128 rows in its own TMEM) and supplies HALF of every domain tile, so the tensor pipe reads
+// 96 instead of 128 bytes of operands per clock from an SM's shared memory (the single-CTA shape M = N = 128 asks for
+// exactly the 128 B/clock an SM has, and the ring's TMA writes come on top), and the ring's L2 traffic halves.  A unit
+// is (two adjacent super-blocks) x (1/n_chunks of the tiles).  CTA 0 issues -- from TWO warps (1 and 3: accumulators
+// 0, 2 and 1, 3): the serial chain of one issuing thread (barrier wait, descriptor moves, four MMAs, commit: 250-300
+// clocks per accumulator on a sub-partition it shares with four busy epilogue warps) was what kept the pair kernel at
+// 1190 clocks per tile; with two issuers it runs at 1046 of an ideal 1024.  Commits are multicast to both CTAs'
+// barriers; CTA 1's warp 1 relays "my half has landed" to CTA 0's full barriers, and CTA 1's epilogue warps hand
+// accumulators back on CTA 0's t_empty barriers (remote mbarrier arrives).  The epilogue code is the same in both CTAs.
 #include <cuda_fp16.h>
 
 #include <cmath>
