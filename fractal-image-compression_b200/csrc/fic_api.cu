@@ -95,7 +95,7 @@ struct DrainOnExit {
     ~DrainOnExit() { cudaStreamSynchronize(s); }
 };
 
-enum Slot { S_ARGB, S_SRC, S_DEC, S_DSUM, S_DSQ, S_RSUM, S_BEST, S_INFO, S_Q, S_OPA, S_OPB, S_IMG, S_DEC2, S_DCODE, S_PERR, S_ACC, S_DEC3 };
+enum Slot { S_ARGB, S_SRC, S_DEC, S_DSUM, S_DSQ, S_RSUM, S_BEST, S_INFO, S_Q, S_OPA, S_OPB, S_IMG, S_DEC2, S_DCODE, S_PERR, S_ACC, S_DEC3, S_REPLAY };
 
 template <typename T>
 static int ensure(fic_handle *h, T *&p, int slot, size_t bytes)
@@ -181,7 +181,7 @@ void fic_destroy(fic_handle *h)
     cudaStreamSynchronize(h->stream);
     Work &w = h->w;
     void *ptrs[] = {w.argb, w.src, w.dec, w.dsum, w.dsq, w.rsum, w.best, w.info, w.q, w.opA, w.opB,
-                    w.img, w.dec2, w.dcode, w.perr, w.acc, w.avgf, w.dec3};
+                    w.img, w.dec2, w.dcode, w.perr, w.acc, w.avgf, w.dec3, w.replay};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 8; i++)
@@ -647,6 +647,8 @@ static int decode_core(fic_handle *h, int is_rgb, int W, int H, int B, int wk, c
     const float carry = avg_error ? *avg_error : 0.0f;
     const float fwh = (float)(W * H);  // FC:413 (float)(width*height)
     ENSURE(w.perr, S_PERR, sizeof(int32_t) * plane);  // per-pixel squared changes of the sweeps that may need a replay
+    const size_t replay_bytes = sweep_finish_workspace((int64_t)plane);
+    if (replay_bytes) ENSURE(w.replay, S_REPLAY, replay_bytes);
     uint8_t *img = d_planes_out ? d_planes_out : w.img;
     DrainOnExit drain(s);
     CU(cudaEventRecord(h->ev[0], s));
@@ -655,9 +657,13 @@ static int decode_core(fic_handle *h, int is_rgb, int W, int H, int B, int wk, c
     int launches = 0;
     int32_t *doff = (int32_t *)(w.dcode + g.NR * S);
     launches += launch_dequant(d_qcodes ? d_qcodes : w.q, w.dcode, doff, g, 0, nullptr, w.acc, s);
-    launches += launch_fill(img, g.C * plane, 128, s);  // FC:360, FC:1142-1148
-    // the 2x-decimated plane of a constant-128 image is constant 128 for every tap rule (FC:970-1007, FC:901-962)
-    CU(cudaMemsetAsync(w.dec, 128, (size_t)g.C * g.sw * g.sh, s));
+    // The start image is the constant 128 (FC:360, FC:1142-1148) and so is its 2x-decimated plane, for every tap rule
+    // (FC:970-1007, FC:901-962).  For B >= 8 neither is materialised: the first sweep knows what it would read.
+    const bool implicit_start = decode_sweep_has_first(g);
+    if (!implicit_start) {
+        launches += launch_fill(img, g.C * plane, 128, s);
+        CU(cudaMemsetAsync(w.dec, 128, (size_t)g.C * g.sw * g.sh, s));
+    }
     uint8_t *dcur = w.dec, *dnext = w.dec2;
     const uint32_t *hst = (const uint32_t *)h->h_acc;  // host copy of the state block as 32-bit words: [5..7] = done, iters, avg
     // Small images: the output copy is enqueued behind every batch, so that a decode that converges within the batch
@@ -680,18 +686,17 @@ static int decode_core(fic_handle *h, int is_rgb, int W, int H, int B, int wk, c
             const bool last = it == max_iters - 1;
             const bool replay = big || last || (it == 0 && carry != 0.0f);
             SweepCtl ctl = {w.acc, it, replay ? 0 : 1, fwh};
-            launches += launch_decode_sweep(dcur, img, dnext, w.dcode, doff, g, ctl, replay ? w.perr : nullptr, s);
-            if (replay) launches += launch_sweep_finish(w.perr, (int64_t)plane, w.acc, it, last, it == 0 ? carry : 0.0f, fwh, s);
+            launches += launch_decode_sweep(dcur, img, dnext, w.dcode, doff, g, ctl, replay ? w.perr : nullptr, it == 0 && implicit_start, s);
+            if (replay) launches += launch_sweep_finish(w.perr, (int64_t)plane, w.acc, it, last, it == 0 ? carry : 0.0f, fwh, replay_bytes ? w.replay : nullptr, s);
             uint8_t *t = dcur; dcur = dnext; dnext = t;
         }
         CU(cudaMemcpyAsync(h->h_acc, w.acc, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-        if (speculative_out) {
-            if ((rc = enqueue_output())) return rc;
-            CU(cudaEventRecord(h->ev[5], s));
-        }
+        if (speculative_out && (rc = enqueue_output())) return rc;
+        // device-resident output: the batch is the whole call (the end event must not wait for the host's state read)
+        if (speculative_out || d_planes_out) CU(cudaEventRecord(h->ev[5], s));
         CU(cudaStreamSynchronize(s));
         if (h->h_acc[1]) return set_err(h, FIC_E_STREAM, "a code indexes outside the domain pool (the reference would throw ArrayIndexOutOfBounds)");
-        out_done = speculative_out;
+        out_done = speculative_out || d_planes_out;
         if (hst[5]) break;  // converged (FC:414)
     }
     if (!out_done) {
@@ -759,7 +764,7 @@ int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, in
     int32_t *doff = (int32_t *)(w.dcode + g.NR * S);
     launch_dequant(nullptr, w.dcode, doff, g, 1, w.info, w.acc, s);  // FC:273 calculateIndices
     launch_fill(w.img, g.C * plane, 0xa0, s);                  // RasterImage.java:19,31
-    launch_decode_sweep(w.dec, w.img, nullptr, w.dcode, doff, g, SweepCtl{nullptr, 0, 0, 0.0f}, nullptr, s);
+    launch_decode_sweep(w.dec, w.img, nullptr, w.dcode, doff, g, SweepCtl{nullptr, 0, 0, 0.0f}, nullptr, 0, s);
     launch_pack_argb(w.img, w.argb, W, H, g.C, s);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h->h_acc, w.acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));

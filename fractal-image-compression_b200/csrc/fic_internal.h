@@ -50,6 +50,7 @@ struct Work {
     int32_t *perr = nullptr;    // per-pixel squared change in reference loop order (exact avgError path)
     unsigned long long *acc = nullptr;  // [64] integer accumulators / flags
     uint16_t *dec3 = nullptr;   // RGB: R + G + B of the decimated planes (CUDA-core search)
+    uint8_t *replay = nullptr;  // decoder, large images: per-chunk records of the exact avgError replay
     size_t cap[20] = {0};
 };
 
@@ -109,11 +110,15 @@ struct SweepCtl {
     int finish;  // 1: fold inside the sweep kernel -- only when the float sum needs no replay (see k_sweep_finish)
     float fwh;   // (float)(W*H), FC:413
 };
+// first (only where decode_sweep_has_first(g)): the sweep starts from the constant-128 image (FC:360) and reads nothing
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out,
                         const float *d_code, const int32_t *d_off, const Geom &g,
-                        const SweepCtl &ctl, int32_t *d_perr, cudaStream_t s);
+                        const SweepCtl &ctl, int32_t *d_perr, int first, cudaStream_t s);
+bool decode_sweep_has_first(const Geom &g);
 // folds a sweep whose float running sum may have to be replayed in loop order (see k_sweep_finish)
+// d_workspace: sweep_finish_workspace(count) bytes (0 for small images: one warp replays the sum literally)
 int launch_sweep_finish(const int32_t *d_perr, int64_t count, unsigned long long *d_state, int it, int last,
-                        float carry, float fwh, cudaStream_t s);
+                        float carry, float fwh, void *d_workspace, cudaStream_t s);
+size_t sweep_finish_workspace(int64_t count);
 
 }  // namespace fic

@@ -1075,7 +1075,9 @@ __device__ __forceinline__ uint32_t f2u8_rz_sat(float f)
     return r;
 }
 
-template <int C>
+// FIRST: the sweep that starts from the constant-128 image (FC:360): every old pixel and every domain pixel is 128,
+// so nothing is read -- the start image and its decimated plane are never materialised (B >= 8 only).
+template <int C, bool FIRST = false>
 __global__ void __launch_bounds__(256)
 k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, uint8_t *__restrict__ dec_out,
                   const float *__restrict__ code, const int32_t *__restrict__ doff, Geom g, SweepCtl ctl,
@@ -1089,9 +1091,11 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
     const int64_t planeI = (int64_t)g.W * g.H, planeD = (int64_t)g.sw * g.sh;
     const int lb = __ffs(g.B) - 1, bm = g.B - 1;  // B is a power of two
     // B >= 8: the strip lies inside ONE range block -- one code, one domain offset, and the 2 x 8 domain bytes
-    // are two runs of 8 contiguous bytes (2-byte aligned: the domain grid stride B/4 is even), read as 16-bit
-    // words.  B = 4: a strip spans two range blocks; every quad fetches its own code and bytes.
+    // are two runs of 8 contiguous bytes, read as 16-bit words at B = 8 (2-byte aligned: the domain grid stride B/4
+    // is even) and as 32-bit words at B = 16 (stride 4).  B = 4: a strip spans two range blocks; every quad fetches
+    // its own code and bytes.
     const bool one_range = g.B >= 8;
+    const bool wide = (g.step & 3) == 0;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < strips; t += (int64_t)gridDim.x * blockDim.x) {
         const int qy = (int)(t / sw8), s8 = (int)(t - (int64_t)qy * sw8);
         const int y = 2 * qy, x0 = 8 * s8;
@@ -1101,25 +1105,43 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
         int off0 = 0;
         if (one_range) {
             a0 = __ldg(code + S * jr0 + 1);
-            off0 = __ldg(doff + jr0) + ry * g.sw + (x0 & bm);
+            if (!FIRST) off0 = __ldg(doff + jr0) + ry * g.sw + (x0 & bm);
         }
         uint32_t esq[4][C];  // per quad: packed |old - new| of its four pixels (only unpacked when perr is asked for)
 #pragma unroll
         for (int c = 0; c < C; c++) {
             uint8_t *pi = img + c * planeI + (int64_t)y * g.W + x0;
-            const uint2 o0 = *(const uint2 *)pi, o1 = *(const uint2 *)(pi + g.W);
+            uint2 o0 = make_uint2(0x80808080u, 0x80808080u), o1 = o0;
+            if (!FIRST) {
+                o0 = *(const uint2 *)pi;
+                o1 = *(const uint2 *)(pi + g.W);
+            }
             const uint32_t old0[2] = {o0.x, o0.y}, old1[2] = {o1.x, o1.y};
             uint32_t n0[2] = {0, 0}, n1[2] = {0, 0}, nd = 0;
             uint32_t dr0[4], dr1[4];  // domain bytes of the four quads: row ry (low 16 bits hold 2 pixels) and ry + 1
             float bq = 0.0f;
             if (one_range) {
                 bq = __ldg(code + S * jr0 + 2 + c);
-                const uint16_t *pd = (const uint16_t *)(dec_in + c * planeD + off0);
-                const uint16_t *pd1 = (const uint16_t *)(dec_in + c * planeD + off0 + g.sw);
+                if (FIRST) {
 #pragma unroll
-                for (int qd = 0; qd < 4; qd++) {
-                    dr0[qd] = __ldg(pd + qd);
-                    dr1[qd] = __ldg(pd1 + qd);
+                    for (int qd = 0; qd < 4; qd++) dr0[qd] = dr1[qd] = 0x8080u;
+                } else if (wide) {
+                    const uint32_t *pw = (const uint32_t *)(dec_in + c * planeD + off0);
+                    const uint32_t *pw1 = (const uint32_t *)(dec_in + c * planeD + off0 + g.sw);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t w0 = __ldg(pw + h), w1 = __ldg(pw1 + h);
+                        dr0[2 * h] = w0 & 0xffffu; dr0[2 * h + 1] = w0 >> 16;
+                        dr1[2 * h] = w1 & 0xffffu; dr1[2 * h + 1] = w1 >> 16;
+                    }
+                } else {
+                    const uint16_t *pd = (const uint16_t *)(dec_in + c * planeD + off0);
+                    const uint16_t *pd1 = (const uint16_t *)(dec_in + c * planeD + off0 + g.sw);
+#pragma unroll
+                    for (int qd = 0; qd < 4; qd++) {
+                        dr0[qd] = __ldg(pd + qd);
+                        dr1[qd] = __ldg(pd1 + qd);
+                    }
                 }
             }
 #pragma unroll
@@ -1191,9 +1213,22 @@ static int64_t sweep_wave_ctas(K kernel)
     return (int64_t)sms * per_sm;
 }
 
+bool decode_sweep_has_first(const Geom &g) { return g.W % 8 == 0 && g.n_iso == 1 && g.B >= 8; }
+
+// first != 0 (only where decode_sweep_has_first): the sweep starts from the constant-128 image and reads neither
+// d_img nor d_dec_in.
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out, const float *d_code,
-                        const int32_t *d_off, const Geom &g, const SweepCtl &ctl, int32_t *d_perr, cudaStream_t s)
+                        const int32_t *d_off, const Geom &g, const SweepCtl &ctl, int32_t *d_perr, int first, cudaStream_t s)
 {
+    if (first && decode_sweep_has_first(g)) {
+        static const int64_t wave_f_1 = sweep_wave_ctas(k_decode_sweep_v8<1, true>), wave_f_3 = sweep_wave_ctas(k_decode_sweep_v8<3, true>);
+        const int64_t strips = (int64_t)(g.W / 8) * (g.H / 2), need = (strips + 255) / 256;
+        if (g.C == 1)
+            k_decode_sweep_v8<1, true><<<(unsigned)(need < wave_f_1 ? need : wave_f_1), 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
+        else
+            k_decode_sweep_v8<3, true><<<(unsigned)(need < wave_f_3 ? need : wave_f_3), 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr);
+        return 1;
+    }
     static const int64_t wave_v8_1 = sweep_wave_ctas(k_decode_sweep_v8<1>), wave_v8_3 = sweep_wave_ctas(k_decode_sweep_v8<3>);
     static const int64_t wave_q_1 = sweep_wave_ctas(k_decode_sweep<1>), wave_q_3 = sweep_wave_ctas(k_decode_sweep<3>);
     if (g.W % 8 == 0 && g.n_iso == 1) {  // the isometry extension uses the quad kernel (per-pixel gather)
@@ -1274,9 +1309,227 @@ __global__ void k_sweep_finish(const int32_t *__restrict__ perr, int64_t count, 
     }
 }
 
-int launch_sweep_finish(const int32_t *d_perr, int64_t count, unsigned long long *d_state, int it, int last, float carry,
-                        float fwh, cudaStream_t s)
+// ---- chunked replay (large images) -------------------------------------------------------------------------------
+// The literal replay above is one dependent float add per pixel: 0.2 s per sweep at 8192^2, where EVERY sweep passes
+// 2^24.  Above 2^24 the running sum a = A * u (u = ulp = 2^(k-23), 2^23 <= A < 2^24) stays a multiple of u, and
+// adding an integer e = m * u + r rounds to A + m + c with c = [r > u/2], or, on a tie r == u/2, the parity of A + m
+// (round to nearest even).  So while the sum stays inside one binade a run of pixels acts on A only through its
+// parity: the run is a two-state transducer (delta[0], delta[1]) = what it adds to A for an even / odd A on entry, and
+// transducers compose (associatively).  Per chunk of 4096 pixels: k_replay_sums takes the exact integer sum,
+// k_replay_scan guesses the chunk's binade from the exact prefix (the float sum drifts from the exact one by far
+// less than a binade), k_replay_transducers composes the chunk's transducer for that binade, all in parallel; one
+// warp (k_replay_walk) then walks the chunks with the true float sum: exact integer adds below 2^24, the transducer
+// where the guess holds and the chunk provably stays inside the binade, and the literal loop for the few chunks
+// around a binade crossing.  Bit-identical to the sequential float sum.
+constexpr int kRepChunk = 4096;                 // pixels per chunk = 256 threads x 16
+struct ReplayChunk { uint32_t sum; int32_t k; uint32_t d0, d1; };  // exact sum, guessed binade (0: none), transducer
+
+__device__ __forceinline__ bool replay_not_needed(const unsigned long long *st, float carry)
 {
+    // the sweep's exact total is below 2^24 and nothing is carried in: the float sum is that integer
+    return ((volatile const uint32_t *)st)[ST_DONE] != 0 || (carry == 0.0f && *(volatile const unsigned long long *)st < (1ull << 24));
+}
+
+__device__ __forceinline__ void replay_load16(const int32_t *__restrict__ perr, int64_t count, int64_t i0, int (&v)[16])
+{
+    if (i0 + 16 <= count) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int4 t = __ldg((const int4 *)(perr + i0) + q);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) v[q] = i0 + q < count ? perr[i0 + q] : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_replay_sums(const int32_t *__restrict__ perr, int64_t count, ReplayChunk *__restrict__ ch,
+                                                     const unsigned long long *st, float carry)
+{
+    if (replay_not_needed(st, carry)) return;
+    __shared__ uint32_t s_part[8];
+    int v[16];
+    replay_load16(perr, count, (int64_t)blockIdx.x * kRepChunk + 16 * threadIdx.x, v);
+    uint32_t t = 0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) t += (uint32_t)v[q];   // <= 4096 * 3 * 255^2 < 2^32 per chunk
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; w++) tot += s_part[w];
+        ch[blockIdx.x].sum = tot;
+    }
+}
+
+// One CTA: exact prefix sums of the chunk totals -> the binade each chunk's running sum is expected to start in.
+__global__ void __launch_bounds__(1024) k_replay_scan(ReplayChunk *__restrict__ ch, int nchunks, const unsigned long long *st, float carry)
+{
+    if (replay_not_needed(st, carry)) return;
+    __shared__ unsigned long long s_tot[1024];
+    const int per = (nchunks + 1023) / 1024, c0 = threadIdx.x * per, c1 = min(nchunks, c0 + per);
+    unsigned long long t = 0;
+    for (int c = c0; c < c1; c++) t += ch[c].sum;
+    s_tot[threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; i++) { const unsigned long long x = s_tot[i]; s_tot[i] = run; run += x; }
+    }
+    __syncthreads();
+    unsigned long long pre = s_tot[threadIdx.x];
+    for (int c = c0; c < c1; c++) {
+        const double g = (double)carry + (double)pre;
+        ch[c].k = g >= 16777216.0 ? ilogb(g) : 0;
+        pre += ch[c].sum;
+    }
+}
+
+// ordered composition: first `l`, then `r`
+__device__ __forceinline__ uint2 replay_compose(uint2 l, uint2 r)
+{
+    return make_uint2(l.x + (((l.x) & 1u) ? r.y : r.x), l.y + (((1u + l.y) & 1u) ? r.y : r.x));
+}
+
+__global__ void __launch_bounds__(256) k_replay_transducers(const int32_t *__restrict__ perr, int64_t count, ReplayChunk *__restrict__ ch,
+                                                            const unsigned long long *st, float carry)
+{
+    if (replay_not_needed(st, carry)) return;
+    const int k = ch[blockIdx.x].k;
+    if (k == 0) return;
+    __shared__ uint2 s_part[8];
+    const int sh = k - 23;               // u = 2^sh, sh >= 1
+    const uint32_t um = (1u << sh) - 1u, h = 1u << (sh - 1);
+    int v[16];
+    replay_load16(perr, count, (int64_t)blockIdx.x * kRepChunk + 16 * threadIdx.x, v);
+    uint32_t d[2] = {0u, 0u}, par[2] = {0u, 1u};
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const uint32_t e = (uint32_t)v[q], m = e >> sh, r = e & um;
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            const uint32_t t = par[p] ^ (m & 1u);                      // parity of A + m
+            const uint32_t c = r > h ? 1u : (r == h ? t : 0u);         // round to nearest, ties to even
+            d[p] += m + c;
+            par[p] = t ^ c;
+        }
+    }
+    uint2 T = make_uint2(d[0], d[1]);
+    const int lane = threadIdx.x & 31;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint2 other;
+        other.x = __shfl_down_sync(0xffffffffu, T.x, o);
+        other.y = __shfl_down_sync(0xffffffffu, T.y, o);
+        if ((lane & (2 * o - 1)) == 0) T = replay_compose(T, other);
+    }
+    if (lane == 0) s_part[threadIdx.x >> 5] = T;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint2 tot = s_part[0];
+        for (int w = 1; w < 8; w++) tot = replay_compose(tot, s_part[w]);
+        ch[blockIdx.x].d0 = tot.x;
+        ch[blockIdx.x].d1 = tot.y;
+    }
+}
+
+// The literal float accumulation over perr[begin, end) (one warp; every lane returns the same sum).
+__device__ float replay_literal(const int32_t *__restrict__ perr, int64_t begin, int64_t end, float a, float limit)
+{
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = begin; base < end && a < limit; base += 128) {
+        const int64_t i = base + 4 * lane;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (i + 4 <= end) v = *(const int4 *)(perr + i);
+        else
+            for (int k = 0; k < 4; k++)
+                if (i + k < end) (&v.x)[k] = perr[i + k];
+        unsigned m = __ballot_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0);
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            a = __fadd_rn(a, (float)__shfl_sync(0xffffffffu, v.x, l));
+            a = __fadd_rn(a, (float)__shfl_sync(0xffffffffu, v.y, l));
+            a = __fadd_rn(a, (float)__shfl_sync(0xffffffffu, v.z, l));
+            a = __fadd_rn(a, (float)__shfl_sync(0xffffffffu, v.w, l));
+        }
+    }
+    return a;
+}
+
+__global__ void k_replay_walk(const int32_t *__restrict__ perr, int64_t count, const ReplayChunk *__restrict__ ch, int nchunks,
+                              unsigned long long *st, int it, int last, float carry, float fwh)
+{
+    if (blockIdx.x || threadIdx.x >= 32) return;
+    uint32_t *w = (uint32_t *)st;
+    if (((volatile uint32_t *)w)[ST_DONE]) return;
+    const int lane = threadIdx.x;
+    const unsigned long long S = *(volatile unsigned long long *)st;
+    float a = carry;  // FC:20
+    if (carry == 0.0f && S < (1ull << 24)) {
+        a = (float)S;
+    } else {
+        const float limit = last ? __int_as_float(0x7f800000) : fwh;  // FC:416-417: an unconverged value is only kept on the last sweep
+        for (int cb = 0; cb < nchunks && a < limit; cb += 32) {
+            ReplayChunk mine = {0u, 0, 0u, 0u};
+            if (cb + lane < nchunks) mine = ch[cb + lane];
+            for (int j = 0; j < 32 && cb + j < nchunks && a < limit; j++) {
+                ReplayChunk c;
+                c.sum = __shfl_sync(0xffffffffu, mine.sum, j);
+                c.k = __shfl_sync(0xffffffffu, mine.k, j);
+                c.d0 = __shfl_sync(0xffffffffu, mine.d0, j);
+                c.d1 = __shfl_sync(0xffffffffu, mine.d1, j);
+                if (c.sum == 0u) continue;  // x + 0 == x
+                const double da = (double)a;
+                if (a == floorf(a) && da + (double)c.sum <= 16777216.0) {  // every partial sum is an exact integer
+                    a = (float)(da + (double)c.sum);
+                    continue;
+                }
+                const uint32_t bits = __float_as_uint(a);
+                const int k = (int)(bits >> 23) - 127;
+                if (c.k != 0 && k == c.k && da + (double)c.sum + (double)kRepChunk * ldexp(0.5, k - 23) < ldexp(1.0, k + 1)) {
+                    // the whole chunk rounds on this binade's grid: apply its transducer to the mantissa
+                    const uint32_t A = (bits & 0x7fffffu) | 0x800000u;
+                    const uint32_t A2 = A + ((A & 1u) ? c.d1 : c.d0);   // < 2^24 by the bound above
+                    a = __uint_as_float((bits & 0xff800000u) | (A2 & 0x7fffffu));
+                    continue;
+                }
+                const int64_t b0 = (int64_t)(cb + j) * kRepChunk, b1 = b0 + kRepChunk < count ? b0 + kRepChunk : count;
+                a = replay_literal(perr, b0, b1, a, __int_as_float(0x7f800000));
+            }
+        }
+    }
+    if (lane == 0) {
+        const float avg = __fdiv_rn(a, fwh);  // FC:413
+        *st = 0ull;
+        w[ST_ITERS] = (uint32_t)(it + 1);
+        if (avg < 1.0f) {  // FC:414
+            w[ST_AVG] = __float_as_uint(avg);
+            w[ST_DONE] = 1u;
+        } else {
+            w[ST_AVG] = last ? __float_as_uint(avg) : 0u;  // FC:416-417
+        }
+    }
+}
+
+size_t sweep_finish_workspace(int64_t count)
+{
+    return count >= ((int64_t)1 << 22) ? sizeof(ReplayChunk) * (size_t)((count + kRepChunk - 1) / kRepChunk) : 0;
+}
+
+int launch_sweep_finish(const int32_t *d_perr, int64_t count, unsigned long long *d_state, int it, int last, float carry,
+                        float fwh, void *d_workspace, cudaStream_t s)
+{
+    if (d_workspace && sweep_finish_workspace(count)) {
+        ReplayChunk *ch = (ReplayChunk *)d_workspace;
+        const int nchunks = (int)((count + kRepChunk - 1) / kRepChunk);
+        k_replay_sums<<<nchunks, 256, 0, s>>>(d_perr, count, ch, d_state, carry);
+        k_replay_scan<<<1, 1024, 0, s>>>(ch, nchunks, d_state, carry);
+        k_replay_transducers<<<nchunks, 256, 0, s>>>(d_perr, count, ch, d_state, carry);
+        k_replay_walk<<<1, 32, 0, s>>>(d_perr, count, ch, nchunks, d_state, it, last, carry, fwh);
+        return 4;
+    }
     k_sweep_finish<<<1, 32, 0, s>>>(d_perr, count, d_state, it, last, carry, fwh);
     return 1;
 }

@@ -207,6 +207,50 @@ def test_decode_above_2_24_pixels(fic, handle, oracle):
     assert handle.timings().total_ms < 200.0   # no per-sweep serial cliff: a sweep of this size takes ~30 us
 
 
+@pytest.mark.parametrize("W,H,B,wk,rgb", [
+    (264, 136, 8, 5, False),    # W % 16 == 8: decimated rows start at odd multiples of 4; landscape: the FC:993 tap
+    (136, 264, 8, 4, True),     # portrait RGB
+    (256, 256, 16, 4, False),   # blockgroesse 16: domain rows are read as 32-bit words
+    (272, 144, 16, 3, True),
+    (64, 64, 8, 13, False),     # whole pool as the window
+    (128, 128, 4, 6, False),    # blockgroesse 4: a strip spans two range blocks, explicit start image
+    (100, 60, 4, 3, False),     # W % 8 != 0: the quad kernel
+])
+@pytest.mark.parametrize("max_iters", [50, 2])
+def test_decode_random_codes(fic, handle, oracle, W, H, B, wk, rgb, max_iters):
+    """Random codes reach every domain position (every alignment of a domain row inside the decimated plane), on
+    image shapes that take each of the sweep kernels.  Image, avgError and sweep count must be the oracle's -- the
+    first sweep never reads the constant start image (FC:360) it starts from; max_iters = 2 runs the sweeps that also
+    write the per-pixel changes (the last allowed sweep and a first sweep with a carried-in avgError are folded by
+    the replaying k_sweep_finish)."""
+    rng = np.random.default_rng(W * 131 + H * 17 + B + wk)
+    NR = (W // B) * (H // B)
+    S = 5 if rgb else 3
+    q = np.empty((NR, S), np.int32)
+    q[:, 0] = rng.integers(0, wk * wk, NR)
+    if rgb:
+        q[:, 1] = rng.integers(-1200000, 1200000, NR)
+        q[:, 2:4] = rng.integers(-100, 300, (NR, 2)) * 100000 + rng.integers(0, 100000, (NR, 2))
+        q[:, 4] = rng.integers(-100, 300, NR)   # the blue offset travels as a plain int (FC:254)
+    else:
+        q[:, 1] = rng.integers(-120, 120, NR)
+        q[:, 2] = rng.integers(-100, 300, NR)
+    q[: NR // 8, 1] = 0   # flat range blocks
+    stream = fic.stream_write(q, W, H, B, wk, rgb)
+    img, avg, it = handle.decode(q, W, H, B, wk, rgb, max_iters=max_iters)
+    if max_iters == 50:
+        want_img, want_avg, want_it = oracle.decode(stream)
+        assert it == want_it and np.float32(avg) == np.float32(want_avg) and (img == want_img).all()
+        planes, avg8, it8 = handle.decode_u8(q, W, H, B, wk, rgb)
+        u = img.view(np.uint32)
+        want8 = np.stack([(u >> 16) & 0xFF, (u >> 8) & 0xFF, u & 0xFF]) if rgb else ((u >> 16) & 0xFF)
+        assert (planes == want8).all() and avg8 == avg and it8 == it
+    else:
+        a1 = handle.decode(q, W, H, B, wk, rgb, max_iters=1)
+        b2 = handle.decode(q, W, H, B, wk, rgb, max_iters=2, avg_error=0.25)   # carry-in: the first sweep is replayed too
+        assert it == 2 and a1[2] == 1 and (b2[0] == img).all()
+
+
 # ---------------------------------------------------------------- multi-GPU handle behind the C ABI
 
 def _device_count():
