@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "fic_get_timings", "fic_geometry", "fic_encode_grey", "fic_encode_rgb", "fic_encode_grey_iso", "fic_encode_planes_dev",
     "fic_sync", "fic_decode", "fic_collage", "fic_build_pool", "fic_stream_size", "fic_stream_write",
     "fic_stream_read_header", "fic_stream_read_codes", "fic_measure_int8_peak", "fic_measure_mma_peak", "fic_measure_mma_peak_pair",
-    "fic_pin_host_buffer", "fic_unpin_host_buffer",
+    "fic_pin_host_buffer", "fic_unpin_host_buffer", "fic_debug_float_sum",
     "fic_encode_grey_u8", "fic_encode_rgb_planes", "fic_decode_u8", "fic_decode_planes_dev",
     "fic_create_multi", "fic_destroy_multi", "fic_multi_last_error", "fic_multi_device_count", "fic_multi_handle",
     "fic_multi_set_option", "fic_multi_get_timings", "fic_multi_range_slice", "fic_multi_encode_grey",
@@ -109,6 +109,7 @@ def load() -> C.CDLL:
     L.fic_measure_mma_peak_pair.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.fic_pin_host_buffer.argtypes = [vp, vp, C.c_size_t]
     L.fic_unpin_host_buffer.argtypes = [vp, vp]
+    L.fic_debug_float_sum.argtypes = [vp, vp, i64, C.c_float, f32p]
     L.fic_stream_size.argtypes = [C.c_int] * 4
     L.fic_stream_size.restype = C.c_size_t
     L.fic_stream_write.argtypes = [C.c_int] * 5 + [vp, vp, C.c_size_t]

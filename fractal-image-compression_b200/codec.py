@@ -206,6 +206,14 @@ class Handle:
                                        C.byref(avg), C.byref(it)))
         return out, np.float32(avg.value), it.value
 
+    def float_sum(self, terms: np.ndarray, carry: float = 0.0) -> np.float32:
+        """fic_debug_float_sum: the reference's sequential binary32 running sum (FC:407) over integer terms, computed
+        the way the decoder folds a sweep."""
+        t = np.ascontiguousarray(terms, dtype=np.int32)
+        out = C.c_float(0)
+        self._check(self._L.fic_debug_float_sum(self._h, _ptr(t), t.size, C.c_float(carry), C.byref(out)))
+        return np.float32(out.value)
+
     def decode_u8(self, q: np.ndarray, W: int, H: int, B: int, wk: int, rgb, avg_error: float = 0.0,
                   max_iters: int = 50, out: np.ndarray | None = None):
         """fic_decode_u8: the image as 8-bit planes, uint8 [H, W] (grey) or [3, H, W] (RGB)."""

@@ -574,6 +574,33 @@ int fic_measure_mma_peak_pair(fic_handle *h, int kind, double *tops)
     return FIC_OK;
 }
 
+int fic_debug_float_sum(fic_handle *h, const int32_t *terms, int64_t count, float carry, float *sum)
+{
+    if (!h || !terms || !sum || count < 1) return FIC_E_ARG;
+    CU(cudaSetDevice(h->device));
+    Work &w = h->w;
+    cudaStream_t s = h->stream;
+    ENSURE(w.perr, S_PERR, sizeof(int32_t) * (size_t)count);
+    ENSURE(w.acc, S_ACC, 64 * sizeof(unsigned long long));
+    const size_t replay_bytes = sweep_finish_workspace(count);
+    if (replay_bytes) ENSURE(w.replay, S_REPLAY, replay_bytes);
+    unsigned long long state[8] = {0};
+    for (int64_t i = 0; i < count; i++) {
+        if (terms[i] < 0 || terms[i] > 3 * 255 * 255) return set_err(h, FIC_E_ARG, "terms must lie in [0, 3 * 255^2]");
+        state[0] += (unsigned long long)terms[i];  // what a sweep leaves in the state block: the exact total
+    }
+    DrainOnExit drain(s);
+    CU(cudaMemcpyAsync(w.perr, terms, sizeof(int32_t) * (size_t)count, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(w.acc, state, sizeof state, cudaMemcpyHostToDevice, s));
+    // "last sweep" keeps the value whatever it is; divided by 1 it is the sum itself
+    launch_sweep_finish(w.perr, count, w.acc, 0, 1, carry, 1.0f, replay_bytes ? w.replay : nullptr, s);
+    CU(cudaMemcpyAsync(h->h_acc, w.acc, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaGetLastError());
+    memcpy(sum, &((const uint32_t *)h->h_acc)[7], sizeof *sum);
+    return FIC_OK;
+}
+
 int fic_build_pool(fic_handle *h, const int32_t *argb, int is_rgb, int W, int H, int B, uint8_t *decimated,
                    int32_t *dom_sum, int32_t *dom_sumsq)
 {

@@ -1316,18 +1316,24 @@ __global__ void k_sweep_finish(const int32_t *__restrict__ perr, int64_t count, 
 // (round to nearest even).  So while the sum stays inside one binade a run of pixels acts on A only through its
 // parity: the run is a two-state transducer (delta[0], delta[1]) = what it adds to A for an even / odd A on entry, and
 // transducers compose (associatively).  Per chunk of 4096 pixels: k_replay_sums takes the exact integer sum,
-// k_replay_scan guesses the chunk's binade from the exact prefix (the float sum drifts from the exact one by far
-// less than a binade), k_replay_transducers composes the chunk's transducer for that binade, all in parallel; one
+// k_replay_scan guesses the chunk's binade from the exact prefix, k_replay_transducers composes the chunk's
+// transducers for that binade and the one below (the float sum falls behind the exact one -- on a grid of 2 an added 1
+// is a tie that an even mantissa drops -- but rarely by more than a binade), all in parallel; one
 // warp (k_replay_walk) then walks the chunks with the true float sum: exact integer adds below 2^24, the transducer
 // where the guess holds and the chunk provably stays inside the binade, and the literal loop for the few chunks
-// around a binade crossing.  Bit-identical to the sequential float sum.
+// around a binade crossing; 32 chunks at a time through their composed transducer (k_replay_groups) where that holds
+// for all of them.  Bit-identical to the sequential float sum.
 constexpr int kRepChunk = 4096;                 // pixels per chunk = 256 threads x 16
-struct ReplayChunk { uint32_t sum; int32_t k; uint32_t d0, d1; };  // exact sum, guessed binade (0: none), transducer
+struct ReplayChunk { uint32_t sum; int32_t k; uint32_t d0, d1, e0, e1; };  // exact sum, guessed binade (0: none), transducers for binades k and k - 1
 
-__device__ __forceinline__ bool replay_not_needed(const unsigned long long *st, float carry)
+// skip_from: exact totals from which a sweep certainly did not converge (only its value < W*H would be kept, FC:413-417).
+// Every float add loses at most half an ulp, and below W*H an ulp is at most ulp(W*H): with S >= W*H + count * ulp / 2
+// the float sum cannot end below W*H.  (~0 on the last allowed sweep, whose value is kept whatever it is.)
+__device__ __forceinline__ bool replay_not_needed(const unsigned long long *st, float carry, unsigned long long skip_from)
 {
-    // the sweep's exact total is below 2^24 and nothing is carried in: the float sum is that integer
-    return ((volatile const uint32_t *)st)[ST_DONE] != 0 || (carry == 0.0f && *(volatile const unsigned long long *)st < (1ull << 24));
+    // done already; or the sweep's exact total is below 2^24 and nothing is carried in: the float sum is that integer
+    const unsigned long long S = *(volatile const unsigned long long *)st;
+    return ((volatile const uint32_t *)st)[ST_DONE] != 0 || (carry == 0.0f && S < (1ull << 24)) || S >= skip_from;
 }
 
 __device__ __forceinline__ void replay_load16(const int32_t *__restrict__ perr, int64_t count, int64_t i0, int (&v)[16])
@@ -1345,9 +1351,9 @@ __device__ __forceinline__ void replay_load16(const int32_t *__restrict__ perr, 
 }
 
 __global__ void __launch_bounds__(256) k_replay_sums(const int32_t *__restrict__ perr, int64_t count, ReplayChunk *__restrict__ ch,
-                                                     const unsigned long long *st, float carry)
+                                                     const unsigned long long *st, float carry, unsigned long long skip_from)
 {
-    if (replay_not_needed(st, carry)) return;
+    if (replay_not_needed(st, carry, skip_from)) return;
     __shared__ uint32_t s_part[8];
     int v[16];
     replay_load16(perr, count, (int64_t)blockIdx.x * kRepChunk + 16 * threadIdx.x, v);
@@ -1365,9 +1371,10 @@ __global__ void __launch_bounds__(256) k_replay_sums(const int32_t *__restrict__
 }
 
 // One CTA: exact prefix sums of the chunk totals -> the binade each chunk's running sum is expected to start in.
-__global__ void __launch_bounds__(1024) k_replay_scan(ReplayChunk *__restrict__ ch, int nchunks, const unsigned long long *st, float carry)
+__global__ void __launch_bounds__(1024) k_replay_scan(ReplayChunk *__restrict__ ch, int nchunks, const unsigned long long *st, float carry,
+                                                      unsigned long long skip_from)
 {
-    if (replay_not_needed(st, carry)) return;
+    if (replay_not_needed(st, carry, skip_from)) return;
     __shared__ unsigned long long s_tot[1024];
     const int per = (nchunks + 1023) / 1024, c0 = threadIdx.x * per, c1 = min(nchunks, c0 + per);
     unsigned long long t = 0;
@@ -1394,43 +1401,57 @@ __device__ __forceinline__ uint2 replay_compose(uint2 l, uint2 r)
 }
 
 __global__ void __launch_bounds__(256) k_replay_transducers(const int32_t *__restrict__ perr, int64_t count, ReplayChunk *__restrict__ ch,
-                                                            const unsigned long long *st, float carry)
+                                                            const unsigned long long *st, float carry, unsigned long long skip_from)
 {
-    if (replay_not_needed(st, carry)) return;
+    if (replay_not_needed(st, carry, skip_from)) return;
     const int k = ch[blockIdx.x].k;
     if (k == 0) return;
-    __shared__ uint2 s_part[8];
-    const int sh = k - 23;               // u = 2^sh, sh >= 1
-    const uint32_t um = (1u << sh) - 1u, h = 1u << (sh - 1);
+    __shared__ uint4 s_part[8];
     int v[16];
     replay_load16(perr, count, (int64_t)blockIdx.x * kRepChunk + 16 * threadIdx.x, v);
-    uint32_t d[2] = {0u, 0u}, par[2] = {0u, 1u};
+    // binade k: u = 2^sh; binade k - 1 (only if it is still >= 24): u = 2^(sh - 1)
+    const int sh = k - 23, shl = sh > 1 ? sh - 1 : 1;
+    uint32_t d[4] = {0u, 0u, 0u, 0u}, par[4] = {0u, 1u, 0u, 1u};
 #pragma unroll
     for (int q = 0; q < 16; q++) {
-        const uint32_t e = (uint32_t)v[q], m = e >> sh, r = e & um;
+        const uint32_t e = (uint32_t)v[q];
 #pragma unroll
-        for (int p = 0; p < 2; p++) {
-            const uint32_t t = par[p] ^ (m & 1u);                      // parity of A + m
-            const uint32_t c = r > h ? 1u : (r == h ? t : 0u);         // round to nearest, ties to even
-            d[p] += m + c;
-            par[p] = t ^ c;
+        for (int b = 0; b < 2; b++) {
+            const int s2 = b ? shl : sh;
+            const uint32_t m = e >> s2, r = e & ((1u << s2) - 1u), h = 1u << (s2 - 1);
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const uint32_t t = par[2 * b + p] ^ (m & 1u);              // parity of A + m
+                const uint32_t c = r > h ? 1u : (r == h ? t : 0u);         // round to nearest, ties to even
+                d[2 * b + p] += m + c;
+                par[2 * b + p] = t ^ c;
+            }
         }
     }
-    uint2 T = make_uint2(d[0], d[1]);
+    uint4 T = make_uint4(d[0], d[1], d[2], d[3]);
+    auto compose4 = [](uint4 l, uint4 r) {
+        const uint2 hi = replay_compose(make_uint2(l.x, l.y), make_uint2(r.x, r.y));
+        const uint2 lo = replay_compose(make_uint2(l.z, l.w), make_uint2(r.z, r.w));
+        return make_uint4(hi.x, hi.y, lo.x, lo.y);
+    };
     const int lane = threadIdx.x & 31;
     for (int o = 1; o < 32; o <<= 1) {
-        uint2 other;
+        uint4 other;
         other.x = __shfl_down_sync(0xffffffffu, T.x, o);
         other.y = __shfl_down_sync(0xffffffffu, T.y, o);
-        if ((lane & (2 * o - 1)) == 0) T = replay_compose(T, other);
+        other.z = __shfl_down_sync(0xffffffffu, T.z, o);
+        other.w = __shfl_down_sync(0xffffffffu, T.w, o);
+        if ((lane & (2 * o - 1)) == 0) T = compose4(T, other);
     }
     if (lane == 0) s_part[threadIdx.x >> 5] = T;
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint2 tot = s_part[0];
-        for (int w = 1; w < 8; w++) tot = replay_compose(tot, s_part[w]);
+        uint4 tot = s_part[0];
+        for (int w = 1; w < 8; w++) tot = compose4(tot, s_part[w]);
         ch[blockIdx.x].d0 = tot.x;
         ch[blockIdx.x].d1 = tot.y;
+        ch[blockIdx.x].e0 = tot.z;
+        ch[blockIdx.x].e1 = tot.w;
     }
 }
 
@@ -1458,8 +1479,42 @@ __device__ float replay_literal(const int32_t *__restrict__ perr, int64_t begin,
     return a;
 }
 
+// A group of 32 chunks composed into one record (valid when its non-empty chunks share one binade guess), so that the
+// walker steps over 131 072 pixels at a time wherever the sum is far from a binade crossing.
+struct ReplayGroup { unsigned long long sum; int32_t k; uint32_t d0, d1, e0, e1; };
+constexpr int kRepGroup = 32;
+
+__global__ void k_replay_groups(const ReplayChunk *__restrict__ ch, int nchunks, ReplayGroup *__restrict__ gr, int ngroups,
+                                const unsigned long long *st, float carry, unsigned long long skip_from)
+{
+    if (replay_not_needed(st, carry, skip_from)) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    unsigned long long sum = 0, d[2] = {0, 0}, e[2] = {0, 0};
+    int k = -1;  // -1: no non-empty chunk yet; 0: no common transducer
+    for (int c = g * kRepGroup; c < min(nchunks, (g + 1) * kRepGroup); c++) {
+        const ReplayChunk x = ch[c];
+        if (x.sum == 0u) continue;  // identity
+        sum += x.sum;
+        if (k == -1) k = x.k;
+        if (x.k == 0 || x.k != k) k = 0;
+        if (k == 0) continue;
+        // ordered composition (replay_compose) in 64 bits: a total of 2^24 or more can never be applied
+        const unsigned long long d0 = d[0] + ((d[0] & 1ull) ? x.d1 : x.d0), d1 = d[1] + (((1ull + d[1]) & 1ull) ? x.d1 : x.d0);
+        const unsigned long long e0 = e[0] + ((e[0] & 1ull) ? x.e1 : x.e0), e1 = e[1] + (((1ull + e[1]) & 1ull) ? x.e1 : x.e0);
+        d[0] = d0; d[1] = d1; e[0] = e0; e[1] = e1;
+    }
+    ReplayGroup out;
+    out.sum = sum;
+    const bool fits = (d[0] | d[1] | e[0] | e[1]) < (1ull << 24);
+    out.k = (k > 0 && fits) ? k : 0;
+    out.d0 = (uint32_t)d[0]; out.d1 = (uint32_t)d[1]; out.e0 = (uint32_t)e[0]; out.e1 = (uint32_t)e[1];
+    gr[g] = out;
+}
+
 __global__ void k_replay_walk(const int32_t *__restrict__ perr, int64_t count, const ReplayChunk *__restrict__ ch, int nchunks,
-                              unsigned long long *st, int it, int last, float carry, float fwh)
+                              const ReplayGroup *__restrict__ gr, int ngroups, unsigned long long *st, int it, int last, float carry,
+                              float fwh, unsigned long long skip_from)
 {
     if (blockIdx.x || threadIdx.x >= 32) return;
     uint32_t *w = (uint32_t *)st;
@@ -1467,36 +1522,58 @@ __global__ void k_replay_walk(const int32_t *__restrict__ perr, int64_t count, c
     const int lane = threadIdx.x;
     const unsigned long long S = *(volatile unsigned long long *)st;
     float a = carry;  // FC:20
+    // One step over `px` pixels with exact total `sum` (> 0), binade guess kk and transducers d (binade kk) / e (kk - 1),
+    // identical in all lanes.  True if the step could be taken without looking at the pixels.
+    auto step = [&](unsigned long long sum, int kk, uint32_t d0, uint32_t d1, uint32_t e0, uint32_t e1, unsigned long long px) -> bool {
+        const uint32_t bits = __float_as_uint(a);
+        const int k = (int)(bits >> 23) - 127;
+        if (k < 24) {
+            // below 2^24: while the sum is an integer and stays <= 2^24 every add is exact
+            if (a == floorf(a) && a >= 0.0f && (unsigned long long)a + sum <= (1ull << 24)) {
+                a = (float)((uint32_t)a + (uint32_t)sum);
+                return true;
+            }
+            return false;
+        }
+        const int below = kk - k;
+        if (k >= 62 || kk == 0 || (below != 0 && below != 1)) return false;
+        // a = A * 2^(k-23).  If even the largest sum the span can reach (its exact total plus half an ulp per add)
+        // stays inside the binade, every add rounds on this grid: apply the span's transducer to A.
+        const uint32_t A = (bits & 0x7fffffu) | 0x800000u;
+        const unsigned long long ai = (unsigned long long)A << (k - 23);
+        if (ai + sum + (px << (k - 24)) >= (2ull << k)) return false;
+        const uint32_t d = (A & 1u) ? (below ? e1 : d1) : (below ? e0 : d0);
+        a = __uint_as_float((bits & 0xff800000u) | ((A + d) & 0x7fffffu));   // A + d < 2^24
+        return true;
+    };
     if (carry == 0.0f && S < (1ull << 24)) {
         a = (float)S;
+    } else if (S >= skip_from) {
+        a = __fmul_rn(fwh, 2.0f);  // certainly not converged (see replay_not_needed); the value is discarded
     } else {
         const float limit = last ? __int_as_float(0x7f800000) : fwh;  // FC:416-417: an unconverged value is only kept on the last sweep
-        for (int cb = 0; cb < nchunks && a < limit; cb += 32) {
-            ReplayChunk mine = {0u, 0, 0u, 0u};
-            if (cb + lane < nchunks) mine = ch[cb + lane];
-            for (int j = 0; j < 32 && cb + j < nchunks && a < limit; j++) {
-                ReplayChunk c;
-                c.sum = __shfl_sync(0xffffffffu, mine.sum, j);
-                c.k = __shfl_sync(0xffffffffu, mine.k, j);
-                c.d0 = __shfl_sync(0xffffffffu, mine.d0, j);
-                c.d1 = __shfl_sync(0xffffffffu, mine.d1, j);
-                if (c.sum == 0u) continue;  // x + 0 == x
-                const double da = (double)a;
-                if (a == floorf(a) && da + (double)c.sum <= 16777216.0) {  // every partial sum is an exact integer
-                    a = (float)(da + (double)c.sum);
+        for (int gb = 0; gb < ngroups && a < limit; gb += 32) {
+            ReplayGroup mine = {0ull, 0, 0u, 0u, 0u, 0u};
+            if (gb + lane < ngroups) mine = gr[gb + lane];
+            for (int j = 0; j < 32 && gb + j < ngroups && a < limit; j++) {
+                const unsigned long long gsum = __shfl_sync(0xffffffffu, mine.sum, j);
+                if (gsum == 0ull) continue;  // x + 0 == x
+                if (step(gsum, __shfl_sync(0xffffffffu, mine.k, j), __shfl_sync(0xffffffffu, mine.d0, j), __shfl_sync(0xffffffffu, mine.d1, j),
+                         __shfl_sync(0xffffffffu, mine.e0, j), __shfl_sync(0xffffffffu, mine.e1, j), (unsigned long long)kRepGroup * kRepChunk))
                     continue;
+                // chunk by chunk; a chunk that cannot be stepped over either is replayed literally
+                const int c0 = (gb + j) * kRepGroup;
+                ReplayChunk cm = {0u, 0, 0u, 0u, 0u, 0u};
+                if (c0 + lane < nchunks) cm = ch[c0 + lane];
+                for (int i = 0; i < kRepGroup && c0 + i < nchunks && a < limit; i++) {
+                    const uint32_t csum = __shfl_sync(0xffffffffu, cm.sum, i);
+                    if (csum == 0u) continue;
+                    if (step(csum, __shfl_sync(0xffffffffu, cm.k, i), __shfl_sync(0xffffffffu, cm.d0, i), __shfl_sync(0xffffffffu, cm.d1, i),
+                             __shfl_sync(0xffffffffu, cm.e0, i), __shfl_sync(0xffffffffu, cm.e1, i), (unsigned long long)kRepChunk))
+                        continue;
+                    const int64_t b0 = (int64_t)(c0 + i) * kRepChunk, b1 = b0 + kRepChunk < count ? b0 + kRepChunk : count;
+                    a = replay_literal(perr, b0, b1, a, __int_as_float(0x7f800000));
                 }
-                const uint32_t bits = __float_as_uint(a);
-                const int k = (int)(bits >> 23) - 127;
-                if (c.k != 0 && k == c.k && da + (double)c.sum + (double)kRepChunk * ldexp(0.5, k - 23) < ldexp(1.0, k + 1)) {
-                    // the whole chunk rounds on this binade's grid: apply its transducer to the mantissa
-                    const uint32_t A = (bits & 0x7fffffu) | 0x800000u;
-                    const uint32_t A2 = A + ((A & 1u) ? c.d1 : c.d0);   // < 2^24 by the bound above
-                    a = __uint_as_float((bits & 0xff800000u) | (A2 & 0x7fffffu));
-                    continue;
-                }
-                const int64_t b0 = (int64_t)(cb + j) * kRepChunk, b1 = b0 + kRepChunk < count ? b0 + kRepChunk : count;
-                a = replay_literal(perr, b0, b1, a, __int_as_float(0x7f800000));
             }
         }
     }
@@ -1513,22 +1590,35 @@ __global__ void k_replay_walk(const int32_t *__restrict__ perr, int64_t count, c
     }
 }
 
+static int64_t replay_chunks(int64_t count) { return (count + kRepChunk - 1) / kRepChunk; }
+static int64_t replay_groups(int64_t count) { return (replay_chunks(count) + kRepGroup - 1) / kRepGroup; }
+
 size_t sweep_finish_workspace(int64_t count)
 {
-    return count >= ((int64_t)1 << 22) ? sizeof(ReplayChunk) * (size_t)((count + kRepChunk - 1) / kRepChunk) : 0;
+    if (count < ((int64_t)1 << 22)) return 0;
+    return sizeof(ReplayGroup) * (size_t)replay_groups(count) + sizeof(ReplayChunk) * (size_t)replay_chunks(count);
 }
 
 int launch_sweep_finish(const int32_t *d_perr, int64_t count, unsigned long long *d_state, int it, int last, float carry,
                         float fwh, void *d_workspace, cudaStream_t s)
 {
     if (d_workspace && sweep_finish_workspace(count)) {
-        ReplayChunk *ch = (ReplayChunk *)d_workspace;
-        const int nchunks = (int)((count + kRepChunk - 1) / kRepChunk);
-        k_replay_sums<<<nchunks, 256, 0, s>>>(d_perr, count, ch, d_state, carry);
-        k_replay_scan<<<1, 1024, 0, s>>>(ch, nchunks, d_state, carry);
-        k_replay_transducers<<<nchunks, 256, 0, s>>>(d_perr, count, ch, d_state, carry);
-        k_replay_walk<<<1, 32, 0, s>>>(d_perr, count, ch, nchunks, d_state, it, last, carry, fwh);
-        return 4;
+        const int nchunks = (int)replay_chunks(count), ngroups = (int)replay_groups(count);
+        ReplayGroup *gr = (ReplayGroup *)d_workspace;
+        ReplayChunk *ch = (ReplayChunk *)(gr + ngroups);
+        unsigned long long skip_from = ~0ull;
+        if (!last && fwh >= 1.0f && carry >= 0.0f) {
+            int ex = 0;
+            frexpf(fwh, &ex);                                   // fwh = m * 2^ex, 0.5 <= m < 1: ulp(fwh) = 2^(ex - 24)
+            const double half_ulp = ldexp(1.0, ex - 25);
+            skip_from = (unsigned long long)((double)fwh + (double)count * half_ulp) + 2ull;
+        }
+        k_replay_sums<<<nchunks, 256, 0, s>>>(d_perr, count, ch, d_state, carry, skip_from);
+        k_replay_scan<<<1, 1024, 0, s>>>(ch, nchunks, d_state, carry, skip_from);
+        k_replay_transducers<<<nchunks, 256, 0, s>>>(d_perr, count, ch, d_state, carry, skip_from);
+        k_replay_groups<<<(ngroups + 127) / 128, 128, 0, s>>>(ch, nchunks, gr, ngroups, d_state, carry, skip_from);
+        k_replay_walk<<<1, 32, 0, s>>>(d_perr, count, ch, nchunks, gr, ngroups, d_state, it, last, carry, fwh, skip_from);
+        return 5;
     }
     k_sweep_finish<<<1, 32, 0, s>>>(d_perr, count, d_state, it, last, carry, fwh);
     return 1;

@@ -236,6 +236,13 @@ int fic_measure_mma_peak(fic_handle *h, int kind, int n_cols, double *tops);
  * search kernel issues, FIC_OPT_UMMA_PAIR). */
 int fic_measure_mma_peak_pair(fic_handle *h, int kind, double *tops);
 
+/* The decoder's avgError arithmetic on its own (test hook): the reference adds every squared pixel change to a
+ * binary32 running sum in loop order (FractalCompression.java:407), so the value depends on the order once it passes
+ * 2^24.  *sum receives carry + terms[0] + terms[1] + ... accumulated exactly that way, computed as fic_decode folds a
+ * sweep: a one-warp replay for count < 2^22, the chunked transducer replay above.  terms: `count` integers in
+ * [0, 3 * 255^2] (host memory). */
+int fic_debug_float_sum(fic_handle *h, const int32_t *terms, int64_t count, float carry, float *sum);
+
 /* ---- domain pool inspection (tests / debugging; not on the hot path) ---------- */
 
 /* Runs the pool builder only and returns the 2x-decimated plane(s) (W/2*H/2 bytes per

@@ -251,6 +251,67 @@ def test_decode_random_codes(fic, handle, oracle, W, H, B, wk, rgb, max_iters):
         assert it == 2 and a1[2] == 1 and (b2[0] == img).all()
 
 
+def _seq_float_sum(terms, carry):
+    """Sequential binary32 accumulation (np.add.accumulate is strictly left to right)."""
+    x = np.concatenate([[np.float32(carry)], terms.astype(np.float32)])
+    return np.add.accumulate(x, dtype=np.float32)[-1]
+
+
+@pytest.mark.parametrize("kind", ["ones", "small", "uniform", "odd", "sparse", "large", "ramp", "ties4", "mixed"])
+@pytest.mark.parametrize("count", [1 << 20, (1 << 22) + 4097, 1 << 24])
+def test_avg_error_replay(fic, handle, kind, count):
+    """The float running sum behind avgError (FC:407) through both replay forms: one warp below 2^22 terms, per-chunk
+    transducers above.  The distributions put the sum into binades 2^24 .. 2^36 with every tie pattern (odd terms on a
+    grid of 2, multiples of 2 on a grid of 4, ...), cross binades inside chunks, and carry fractions in."""
+    rng = np.random.default_rng(count % 1000 + len(kind))
+    hi = 3 * 255 * 255
+    if kind == "ones":       # on a grid of 2 an added 1 is a tie that an even mantissa drops: the float sum stalls at 2^24
+        t = np.ones(count, np.int64)
+    elif kind == "small":
+        t = rng.integers(0, 4, count)
+    elif kind == "uniform":
+        t = rng.integers(0, 256, count)
+    elif kind == "odd":
+        t = rng.integers(0, 8, count) * 2 + 1
+    elif kind == "sparse":
+        t = np.where(rng.random(count) < 0.01, rng.integers(0, hi + 1, count), 0)
+    elif kind == "large":
+        t = rng.integers(hi - 1000, hi + 1, count)
+    elif kind == "ramp":
+        t = (np.arange(count) * 37 % 1024) * (np.arange(count) // (count // 16) % 2 + 1)
+    elif kind == "ties4":
+        t = rng.integers(0, 64, count) * 4 + 2
+    else:
+        t = np.where(np.arange(count) < count // 3, rng.integers(0, 3, count), rng.integers(0, 70000, count))
+    t = t.astype(np.int32)
+    for carry in (0.0, 0.5863342, 3.5e7):
+        got = handle.float_sum(t, carry)
+        want = _seq_float_sum(t, carry)
+        assert got == want, (kind, count, carry, float(got), float(want))
+
+
+def test_decode_8192_square(fic, handle, oracle):
+    """8192^2 = 2^26 pixels (BASELINE configs[3]'s image size): every sweep's float sum passes 2^24, the converging ones
+    end between 2^24 and 2^26 where binary32 addition rounds.  Random codes (no encode needed); image, avgError and sweep
+    count equal the oracle's, and no sweep falls back to a 2^26-step serial replay."""
+    W = H = 8192
+    B, wk = 8, 2
+    rng = np.random.default_rng(8192)
+    NR = (W // B) * (H // B)
+    q = np.empty((NR, 3), np.int32)
+    q[:, 0] = rng.integers(0, wk * wk, NR)
+    q[:, 1] = rng.integers(-130, 130, NR)   # converges to avgError ~ 0.6: a float sum of ~ 4e7, two binades above 2^24
+    q[:, 2] = rng.integers(-60, 280, NR)
+    stream = fic.stream_write(q, W, H, B, wk, False)
+    want_img, want_avg, want_it = oracle.decode(stream)
+    assert 0.3 < want_avg < 1.0
+    handle.decode_u8(q, W, H, B, wk, False)
+    out, avg, it = handle.decode_u8(q, W, H, B, wk, False)
+    assert it == want_it and avg == want_avg
+    assert (out == ((want_img.view(np.uint32) >> 16) & 0xFF)).all()
+    assert handle.timings().total_ms < 60.0   # 67 MB to the host + a dozen sweeps; the serial replay took 0.2 s per sweep
+
+
 # ---------------------------------------------------------------- multi-GPU handle behind the C ABI
 
 def _device_count():
