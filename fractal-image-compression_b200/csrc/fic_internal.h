@@ -75,7 +75,7 @@ int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_
 // bare tcgen05.mma loop (M = 128, N = n_cols in {128, 256}): measured dense rate of kind::i8 (f16 = 0) or
 // kind::f16 on this GPU in TOP/s (< 0 on error)
 double measure_mma_peak(int num_sms, cudaStream_t s, int reps, int f16, int n_cols, const char **err);
-double measure_mma_peak_pair(int num_sms, cudaStream_t s, int reps, int f16, uint32_t *tmem_bases, const char **err);
+double measure_mma_peak_pair(int num_sms, cudaStream_t s, int reps, int f16, uint32_t *tmem_bases, const char **err, int a_in_tmem = 0);
 // 1: kind::f16 accumulators are the exact integer covariances on this device; 0: not; < 0: CUDA error
 int umma_f16_selftest(int num_sms, cudaStream_t s, const char **err);
 bool umma_applicable(const Geom &g);

@@ -239,7 +239,9 @@ struct Lay {
     // CTA pairs (tcgen05 cta_group::2, see k_umma_search<..., PAIR>): each CTA of the pair holds HALF of every domain
     // tile (64 operand rows = the first / second 8 row groups of the blob), so the ring has twice the depth in the
     // same shared memory (capped: the barrier area holds 2 * 12 + 10 mbarriers).
-    static constexpr int PAIR_SLOT_BYTES = B_OP_BYTES / 2;
+    // K-split configurations: a slot takes half of either part (P0: 8 row groups x SBO_B, P1: 8 x SBO_P1).
+    static constexpr int PAIR_P0_BYTES = B_OP_BYTES / 2, PAIR_P1_BYTES = P1_BYTES / 2;
+    static constexpr int PAIR_SLOT_BYTES = PAIR_P0_BYTES > PAIR_P1_BYTES ? PAIR_P0_BYTES : PAIR_P1_BYTES;
     static constexpr int PAIR_STAGES = (C::NSTAGE * SLOT_BYTES) / PAIR_SLOT_BYTES < 12 ? (C::NSTAGE * SLOT_BYTES) / PAIR_SLOT_BYTES : 12;
     static constexpr int BAR_BYTES = 512;
     static constexpr int SMEM_BYTES = A_SB_BYTES + C::NSTAGE * SLOT_BYTES + 1024 /*alignment slack*/ + BAR_BYTES /*barriers*/ +
@@ -1064,7 +1066,10 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
 {
     using C = Cfg<B, F16>;
     using L = Lay<B, F16>;
-    static_assert(!PAIR || (F16 && !C::KSPLIT), "CTA pairs: kind::f16, whole-tile slots");
+    static_assert(!PAIR || F16 || C::KSPLIT, "CTA pairs: kind::f16, or the K-split configurations (B = 16)");
+    // issuing warps of a pair: two for the whole-tile kernels (see below); one where a tile is 9-17 K-slices per
+    // accumulator (K-split: the issuing thread is not the bottleneck there)
+    constexpr int NISS = (PAIR && !C::KSPLIT) ? 2 : 1;
     constexpr int NSTAGE = PAIR ? L::PAIR_STAGES : C::NSTAGE;
     constexpr int SLOT = PAIR ? L::PAIR_SLOT_BYTES : L::SLOT_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1082,6 +1087,9 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
     const uint32_t BAR_A_FULL = bar0 + 8u * (2 * NSTAGE + 2 * kAccs);
     const uint32_t BAR_A_EMPTY = BAR_A_FULL + 8u;
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * NSTAGE + 2 * kAccs + 2);
+    // K-split pairs: "this tile has a second part" per ring stage, written by the producer ahead of the stage's
+    // expect_tx arrive and read by the issuer / the relay behind their wait on the stage's full barrier
+    const uint32_t s_has_l = bar0 + 400u;
     uint32_t *s_lb = (uint32_t *)((uint8_t *)bars + L::BAR_BYTES);  // [kRowsPerSB] binary32 bits of the row's lower bound
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1095,14 +1103,14 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         const uint32_t both = (PAIR && rank == 0) ? 2u : 1u;
         for (int s = 0; s < NSTAGE; s++) {
             mbar_init(BAR_B_FULL(s), both);
-            mbar_init(BAR_B_EMPTY(s), PAIR ? 2 : 1);  // released by the MMA issuers' commits alone (PAIR: two issuers): the epilogue never touches the ring
+            mbar_init(BAR_B_EMPTY(s), NISS);  // released by the MMA issuers' commits alone: the epilogue never touches the ring
         }
         for (int q = 0; q < kAccs; q++) {
             mbar_init(BAR_T_FULL(q), 1);
             mbar_init(BAR_T_EMPTY(q), both * (kEpiWarps / kAccs));  // the 4 lane quarters of the accumulator (PAIR: of both CTAs)
         }
         mbar_init(BAR_A_FULL, both);
-        mbar_init(BAR_A_EMPTY, PAIR ? 2 : 1);
+        mbar_init(BAR_A_EMPTY, NISS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -1134,7 +1142,21 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
                 bulk_g2s(smem_u32(sA), opA + (int64_t)sb * L::A_SB_BYTES, L::A_SB_BYTES, BAR_A_FULL);
                 for (int t = t0; t < t1; t++) {
                     const uint8_t *blob = opB + (int64_t)t * L::B_TILE_BYTES;
-                    if (C::KSPLIT) {
+                    if (C::KSPLIT && PAIR) {
+                        // this CTA's half (operand rows 64 * rank ..) of part P0, then of part P1 unless its digits are all zero
+                        const uint32_t has_l = __ldg((const uint32_t *)(blob + L::B_OP_BYTES + kChunksPerTile * 8));
+                        mbar_wait(BAR_B_EMPTY(stage), phase ^ 1, status, 2);
+                        sts_u32(s_has_l + 4u * stage, has_l);
+                        mbar_expect_tx(BAR_B_FULL(stage), L::PAIR_P0_BYTES);
+                        bulk_g2s(smem_u32(sB + stage * SLOT), blob + rank * L::PAIR_P0_BYTES, L::PAIR_P0_BYTES, BAR_B_FULL(stage));
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        if (has_l) {
+                            mbar_wait(BAR_B_EMPTY(stage), phase ^ 1, status, 2);
+                            mbar_expect_tx(BAR_B_FULL(stage), L::PAIR_P1_BYTES);
+                            bulk_g2s(smem_u32(sB + stage * SLOT), blob + L::P0_BYTES + rank * L::PAIR_P1_BYTES, L::PAIR_P1_BYTES, BAR_B_FULL(stage));
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        }
+                    } else if (C::KSPLIT) {
                         // part P0 (high digits, -alpha, bounds), then part P1 (low digits) unless they are all zero
                         mbar_wait(BAR_B_EMPTY(stage), phase ^ 1, status, 2);
                         mbar_expect_tx(BAR_B_FULL(stage), L::P0_BYTES);
@@ -1164,7 +1186,7 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
             }
         }
         __syncwarp();
-    } else if (PAIR && (warp == 1 || warp == 3)) {
+    } else if (PAIR && (warp == 1 || (warp == 3 && !C::KSPLIT))) {
         // ===================== MMA issuers of a pair (CTA 0) =====================
         // What bounds the pair kernel once the operands stream at full rate is the issuing thread itself: per
         // accumulator one barrier wait, the descriptor moves into uniform registers, four tcgen05.mma and a commit
@@ -1172,7 +1194,109 @@ k_umma_search(const uint8_t *__restrict__ opA, const uint8_t *__restrict__ opB, 
         // 256 clocks of tensor work.  Two warps on different sub-partitions therefore issue side by side: warp 1
         // owns accumulators 0 and 2, warp 3 accumulators 1 and 3.  MMAs of different accumulators need no mutual
         // order; a ring slot (and the A super-block) is free once BOTH issuers' commits have arrived.
-        if constexpr (PAIR) {
+        if constexpr (PAIR && C::KSPLIT) {
+            if (rank == 0) {
+                // ===================== MMA issuer of a K-split pair (CTA 0, one warp) =====================
+                uint32_t stage = 0, phase = 0, a_phase = 0, t_phase = 0;
+                const uint32_t elected = elect_one();
+                const long long clk0 = clock64();
+                unsigned long long ns0 = 0;
+                if (status) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+                const uint64_t a_desc0 = make_desc(smem_u32(sA), lbo_bytes_a, sbo_bytes_a);
+                for (int u = u_first; u < n_units; u += u_step) {
+                    int ch = u / n_sbu;
+                    int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
+                    mbar_wait(BAR_A_FULL, a_phase, status, 3);
+                    for (int t = t0; t < t1; t++) {
+                        mbar_wait(BAR_B_FULL(stage), phase, status, 4);  // both halves of part P0
+                        tc_fence_after();
+                        const uint32_t has_l = lds_volatile_u32(s_has_l + 4u * stage);
+                        const uint64_t b0 = make_desc(smem_u32(sB + stage * SLOT), 128, L::SBO_B);
+#pragma unroll
+                        for (int q = 0; q < C::NB; q++) {
+                            mbar_wait(BAR_T_EMPTY(q), ((t_phase >> q) & 1) ^ 1, status, 5);  // the epilogue warps of both CTAs
+                            tc_fence_after();
+                            if (elected) {
+#pragma unroll
+                                for (int s = 0; s < L::KS0; s++) {
+                                    if ((DBG & 4) && t != t0) continue;  // probe only: epilogue without the tensor pipe
+                                    const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + s * 256) >> 4);
+                                    if (F16) tc_mma2_f16(tmem_base + q * kTileN, ad, b0 + (uint64_t)((s * 256) >> 4), kIdescF16Pair, s > 0 ? 1u : 0u);
+                                    else tc_mma2_i8(tmem_base + q * kTileN, ad, b0 + (uint64_t)((s * 256) >> 4), kIdescPair, s > 0 ? 1u : 0u);
+                                }
+                                if (!has_l) tc_commit2(BAR_T_FULL(q), 3u);
+                            }
+                            __syncwarp();
+                            t_phase ^= 1u << q;
+                        }
+                        if (elected) tc_commit2(BAR_B_EMPTY(stage), 3u);  // both CTAs' slots are free once these MMAs have read them
+                        __syncwarp();
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        if (has_l) {
+                            mbar_wait(BAR_B_FULL(stage), phase, status, 4);
+                            tc_fence_after();
+                            const uint64_t b1 = make_desc(smem_u32(sB + stage * SLOT), 128, L::SBO_P1);
+#pragma unroll
+                            for (int q = 0; q < C::NB; q++) {
+                                if (elected) {
+#pragma unroll
+                                    for (int s = 0; s < C::KS_B - L::KS0; s++) {
+                                        if ((DBG & 4) && t != t0) continue;
+                                        const int sa = F16 ? L::KS0 + s : s;  // kind::i8: the low digits meet the r slices again
+                                        const uint64_t ad = a_desc0 + (uint64_t)((q * L::A_BLOCK_BYTES + sa * 256) >> 4);
+                                        if (F16) tc_mma2_f16(tmem_base + q * kTileN, ad, b1 + (uint64_t)((s * 256) >> 4), kIdescF16Pair, 1u);
+                                        else tc_mma2_i8(tmem_base + q * kTileN, ad, b1 + (uint64_t)((s * 256) >> 4), kIdescPair, 1u);
+                                    }
+                                    tc_commit2(BAR_T_FULL(q), 3u);
+                                }
+                                __syncwarp();
+                            }
+                            if (elected) tc_commit2(BAR_B_EMPTY(stage), 3u);
+                            __syncwarp();
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    if (elected) tc_commit2(BAR_A_EMPTY, 3u);
+                    __syncwarp();
+                    a_phase ^= 1;
+                }
+                if (status && blockIdx.x == 0 && elected) {
+                    const long long dt = clock64() - clk0;
+                    unsigned long long ns1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+                    status[2] = (int)(dt & 0x7fffffff);
+                    status[3] = (int)(dt >> 31);
+                    status[4] = (int)(ns1 - ns0);
+                    status[5] = 0;
+                    status[6] = 0;
+                }
+            } else {
+                // ===================== relay (CTA 1 of a K-split pair) =====================
+                if (lane == 0) {
+                    uint32_t stage = 0, phase = 0, a_phase = 0;
+                    const uint32_t ra_full = mapa_u32(BAR_A_FULL, 0);
+                    for (int u = u_first; u < n_units; u += u_step) {
+                        int ch = u / n_sbu;
+                        int t0 = (int)((int64_t)ch * ntiles / n_chunks), t1 = (int)((int64_t)(ch + 1) * ntiles / n_chunks);
+                        mbar_wait(BAR_A_FULL, a_phase, status, 3);
+                        mbar_arrive_cluster(ra_full);
+                        for (int t = t0; t < t1; t++) {
+                            mbar_wait(BAR_B_FULL(stage), phase, status, 4);
+                            const uint32_t has_l = lds_volatile_u32(s_has_l + 4u * stage);
+                            mbar_arrive_cluster(mapa_u32(BAR_B_FULL(stage), 0));
+                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                            if (has_l) {
+                                mbar_wait(BAR_B_FULL(stage), phase, status, 4);
+                                mbar_arrive_cluster(mapa_u32(BAR_B_FULL(stage), 0));
+                                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                        a_phase ^= 1;
+                    }
+                }
+                __syncwarp();
+            }
+        } else if constexpr (PAIR) {
             if (rank == 0) {
                 const int qi = warp >> 1;  // 0 or 1
                 uint32_t stage = 0, phase = 0, a_phase = 0, t_phase = 0;
@@ -1708,7 +1832,10 @@ __global__ void __launch_bounds__(128, 1) k_mma_peak(int iters, uint32_t seed)
 // The same loop issued by CTA pairs: tcgen05.mma.cta_group::2, M = 256 (128 rows per CTA), N = 128 (64 operand rows
 // per CTA): per MMA an SM reads 4 KB of A and 2 KB of B from its shared memory instead of 4 + 4.  out[blockIdx.x]
 // receives the CTA's TMEM base address (both CTAs of a pair must report the same one).
-template <bool F16>
+// TS: the A operand comes from tensor memory (tcgen05.mma [d], [a_tmem], b_desc: 8 columns behind the accumulators)
+// instead of shared memory -- a probe of what the tensor pipe sustains under the board's power cap when an SM reads
+// only the B half-tile (2 KB per MMA) from shared memory.
+template <bool F16, bool TS = false>
 __global__ void __launch_bounds__(128, 1) k_mma_peak_pair(int iters, uint32_t seed, uint32_t *out)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1731,7 +1858,7 @@ __global__ void __launch_bounds__(128, 1) k_mma_peak_pair(int iters, uint32_t se
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TS ? 512u : 256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -1739,6 +1866,21 @@ __global__ void __launch_bounds__(128, 1) k_mma_peak_pair(int iters, uint32_t se
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0 && out) out[blockIdx.x] = tmem_base;
+    if (TS) {
+        // this warp's lane quarter of the A operand: 32 rows x 8 columns (one 32-byte K-slice per row)
+        uint32_t x = (uint32_t)threadIdx.x * 2654435761u + seed;
+        x ^= x >> 15; x *= 0x2c1b3c6du; x ^= x >> 12;
+        if (F16) x &= 0x3fff3fffu;
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + 256u;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(ta), "r"(x), "r"(x ^ 0x01010101u),
+                     "r"(x ^ 0x02020202u), "r"(x ^ 0x03030303u), "r"(x ^ 0x04040404u), "r"(x ^ 0x05050505u), "r"(x ^ 0x06060606u),
+                     "r"(x ^ 0x07070707u)
+                     : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        cluster_sync_all();
+        tc_fence_after();
+    }
     if (warp == 1) {
         if (rank == 0) {
             const uint32_t elected = elect_one();
@@ -1749,6 +1891,20 @@ __global__ void __launch_bounds__(128, 1) k_mma_peak_pair(int iters, uint32_t se
             if (elected) {
                 for (int i = 0; i < iters; i++) {
                     const uint32_t d = tmem_base + (uint32_t)(i & 1) * 128;
+                    if (TS) {
+                        const uint32_t acc = i >= 2 ? 1u : 0u;
+                        if (F16)
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                         "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(tmem_base + 256u), "l"(bd),
+                                         "r"(idesc), "r"(acc)
+                                         : "memory");
+                        else
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                         "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(tmem_base + 256u), "l"(bd),
+                                         "r"(idesc), "r"(acc)
+                                         : "memory");
+                        continue;
+                    }
                     if (F16) tc_mma2_f16(d, ad, bd, idesc, i >= 2 ? 1u : 0u);
                     else tc_mma2_i8(d, ad, bd, idesc, i >= 2 ? 1u : 0u);
                 }
@@ -1762,7 +1918,7 @@ __global__ void __launch_bounds__(128, 1) k_mma_peak_pair(int iters, uint32_t se
     cluster_sync_all();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TS ? 512u : 256u) : "memory");
     }
 }
 
@@ -2134,7 +2290,7 @@ inline Plan make_plan(const Geom &g, int64_t rows, int num_sms)
     const int rows_sb = rows_per_sb(g);
     // an even number of 512-row super-blocks: CTA pairs (k_umma_search<..., PAIR>) take two at a time; padding rows
     // are zero operands with vR = 0 (never flagged)
-    p.rp = pad_up(rows, rows_sb == kRowsPerSB ? 2 * rows_sb : rows_sb);
+    p.rp = pad_up(rows, 2 * rows_sb);
     p.n_sb = (int)(p.rp / rows_sb);
     p.ntiles = (int)((g.ND + kTileN - 1) / kTileN);
     p.npos = (int64_t)p.ntiles * kTileN;
@@ -2208,13 +2364,15 @@ KernelT pick_kernel(bool dump, uint32_t dbg)
     return k_umma_search<B, F16, 0, false, EPI, PAIR>;
 }
 
-// CTA pairs exist for the kind::f16 kernels with whole-tile ring slots (B = 4, 8; grey, RGB and the isometry extension).
-// Default where measured faster: B = 8 (17.6 against 20.8 ms at 4096^2); B = 4 is bound by its epilogue (K = 16 keeps the
-// tensor pipe a quarter busy) and loses 4 % to the pair's extra barrier traffic.
+// CTA pairs exist for the kind::f16 kernels (B = 4, 8: grey, RGB and the isometry extension; two issuing warps) and for
+// the K-split B = 16 configurations (kind::i8 grey, kind::f16 RGB; one issuing warp, each CTA loads half of either part
+// of a tile).  Default where measured faster: B = 8 (17.6 against 20.8 ms at 4096^2) and B = 16 (2.47 against 2.77 ms);
+// B = 4 is bound by its epilogue (K = 16 keeps the tensor pipe a quarter busy) and loses 4 % to the pair's extra
+// barrier traffic.
 template <int B, bool F16>
-constexpr bool pair_capable() { return F16 && !Cfg<B, F16>::KSPLIT; }
+constexpr bool pair_capable() { return F16 || B == 16; }
 template <int B, bool F16>
-constexpr bool pair_default() { return pair_capable<B, F16>() && B == 8; }
+constexpr bool pair_default() { return pair_capable<B, F16>() && B >= 8; }
 
 // Can a cluster of two CTAs of this kernel be co-scheduled on this device (it cannot under some MIG / MPS partitions)?
 inline bool pair_launchable(KernelT kern, int smem_bytes)
@@ -2320,7 +2478,9 @@ int launch_t(const Work &w, const Geom &g, int64_t j0, int64_t j1, int num_sms, 
     if (epi == 3) kern = pick_kernel<B, F16, 3>(dump && !(dbg & 8u), dbg);
     if constexpr (pair_capable<B, F16>()) {
         if (pair) {
-            KernelT pk = (variant & 8) ? pick_kernel<B, F16, 2, true>(dump, dbg) : pick_kernel<B, F16, 3, true>(dump, dbg);
+            KernelT pk;
+            if constexpr (F16 && B != 16) pk = (variant & 8) ? pick_kernel<B, F16, 2, true>(dump, dbg) : pick_kernel<B, F16, 3, true>(dump, dbg);
+            else pk = pick_kernel<B, F16, 0, true>(dump, dbg);  // B = 16 (kind::i8, RGB kind::f16): the plain epilogue loop
             ce = cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES);
             if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1; }
             if (pair_launchable(pk, L::SMEM_BYTES)) kern = pk;
@@ -2572,10 +2732,11 @@ int umma_debug_sort(uint32_t *d_keys, int32_t *d_vals, uint32_t *d_keys_out, int
 
 // Bare loop of the CTA-pair instruction shape (cta_group::2, M = 256, N = 128): TOP/s, best of `reps`; tmem_bases (if
 // not null) receives the TMEM base address each of the first 4 CTAs was given.
-double measure_mma_peak_pair(int num_sms, cudaStream_t s, int reps, int f16, uint32_t *tmem_bases, const char **err)
+double measure_mma_peak_pair(int num_sms, cudaStream_t s, int reps, int f16, uint32_t *tmem_bases, const char **err, int a_in_tmem)
 {
     const int smem = 200 * 1024;
-    void (*kern)(int, uint32_t, uint32_t *) = f16 ? k_mma_peak_pair<true> : k_mma_peak_pair<false>;
+    void (*kern)(int, uint32_t, uint32_t *) = a_in_tmem ? (f16 ? k_mma_peak_pair<true, true> : k_mma_peak_pair<false, true>)
+                                                        : (f16 ? k_mma_peak_pair<true> : k_mma_peak_pair<false>);
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (ce != cudaSuccess) { *err = cudaGetErrorString(ce); return -1.0; }
     uint32_t *d_out = nullptr;

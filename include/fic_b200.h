@@ -74,9 +74,10 @@ extern "C" {
 
 /* CTA pairs of the tcgen05 search (fic_set_option(FIC_OPT_UMMA_PAIR, ...)): two CTAs of one TPC share every
  * tcgen05.mma (cta_group::2, M = 256), each supplying half of every domain tile.  Same codes either way.  The
- * pair kernel exists for kind::f16 at blockgroesse 4 and 8 (grey, RGB, isometry extension); elsewhere, and on a
- * device partition that cannot co-schedule a 2-CTA cluster, the option is ignored. */
-#define FIC_UMMA_PAIR_AUTO 0 /* pairs where measured faster: blockgroesse 8 */
+ * pair kernel exists for kind::f16 (grey, RGB, isometry extension) and for kind::i8 at blockgroesse 16; elsewhere
+ * (kind::i8 at blockgroesse 4, 8), and on a device partition that cannot co-schedule a 2-CTA cluster, the option is
+ * ignored. */
+#define FIC_UMMA_PAIR_AUTO 0 /* pairs where measured faster: blockgroesse 8 and 16 */
 #define FIC_UMMA_PAIR_OFF 1
 #define FIC_UMMA_PAIR_ON 2
 

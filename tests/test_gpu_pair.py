@@ -1,6 +1,6 @@
 """CTA pairs of the tcgen05 search (tcgen05 cta_group::2, FIC_OPT_UMMA_PAIR): the pair kernel and the single-CTA
 kernel must both reproduce the oracle's codes bit for bit (FC:613-644, FC:655-687; RGB FC:697-808), on every
-configuration either of them serves, whatever the option says.  AUTO runs pairs at blockgroesse 8."""
+configuration either of them serves, whatever the option says.  AUTO runs pairs at blockgroesse 8 and 16."""
 import os
 
 import numpy as np
@@ -43,10 +43,12 @@ def _encode(fic, handle, img, B, wk, pair, rgb=False, **kw):
 
 @pytest.mark.parametrize("pair", ["on", "off"])
 @pytest.mark.parametrize("kind,W,B", [("noise", 256, 8), ("structured", 256, 8), ("binary", 256, 8), ("flat", 128, 8), ("periodic", 256, 8),
-                                      ("structured", 384, 8), ("structured", 128, 4), ("binary", 128, 4), ("noise", 192, 4)])
+                                      ("structured", 384, 8), ("structured", 128, 4), ("binary", 128, 4), ("noise", 192, 4),
+                                      ("structured", 512, 16), ("binary", 256, 16), ("noise", 384, 16), ("periodic", 256, 16)])
 def test_pair_and_single_equal_oracle_grey(fic, handle, oracle, kind, W, B, pair):
     """Full-pool grey encodes through either kernel against the oracle (384^2: an odd number of 512-row super-blocks,
-    the pair's padded partner; 128^2: a single, mostly padded pair)."""
+    the pair's padded partner; 128^2: a single, mostly padded pair; blockgroesse 16: the K-split kind::i8 kernel, whose
+    pair form loads half of either part of a tile per CTA -- binary content has low digits, i.e. second parts)."""
     img = to_argb_grey(_content(kind, W, 5))
     wk = 2 * (W // B) - 3
     (info, q), used = _encode(fic, handle, img, B, wk, fic.FIC_UMMA_PAIR_ON if pair == "on" else fic.FIC_UMMA_PAIR_OFF)
@@ -56,9 +58,9 @@ def test_pair_and_single_equal_oracle_grey(fic, handle, oracle, kind, W, B, pair
 
 
 @pytest.mark.parametrize("pair", ["on", "off"])
-@pytest.mark.parametrize("kind,B", [("structured", 8), ("binary", 8), ("noise", 4)])
+@pytest.mark.parametrize("kind,B", [("structured", 8), ("binary", 8), ("noise", 4), ("structured", 16), ("binary", 16)])
 def test_pair_and_single_equal_oracle_rgb(fic, handle, oracle, kind, B, pair):
-    W = 128 if B == 4 else 256
+    W = 128 if B == 4 else (384 if B == 16 else 256)
     rgb = np.stack([_content(kind, W, s) for s in (1, 2, 3)], axis=-1)
     img = to_argb_rgb(rgb)
     wk = 2 * (W // B) - 3
@@ -69,8 +71,8 @@ def test_pair_and_single_equal_oracle_rgb(fic, handle, oracle, kind, B, pair):
 
 
 def test_pair_auto_policy(fic, handle, lena_grey):
-    """AUTO: pairs at blockgroesse 8, the single-CTA kernel at 4 (epilogue bound) and for kind::i8 (16); an explicit
-    ON is ignored where no pair kernel exists."""
+    """AUTO: pairs at blockgroesse 8 and 16 (the K-split kind::i8 kernel), the single-CTA kernel at 4 (epilogue
+    bound); an explicit ON is ignored where no pair kernel exists (kind::i8 at blockgroesse 8)."""
     handle.set_engine(fic.FIC_ENGINE_UMMA)
     try:
         handle.encode(lena_grey, 8, 61, rgb=False)
@@ -78,10 +80,11 @@ def test_pair_auto_policy(fic, handle, lena_grey):
         handle.encode(lena_grey, 4, 125, rgb=False)
         assert not handle.umma_pair_used()
         handle.encode(lena_grey, 16, 29, rgb=False)
-        assert not handle.umma_pair_used()
-        handle.set_umma_pair(fic.FIC_UMMA_PAIR_ON)
+        assert handle.umma_pair_used()
+        handle.set_umma_pair(fic.FIC_UMMA_PAIR_OFF)
         handle.encode(lena_grey, 16, 29, rgb=False)
         assert not handle.umma_pair_used()
+        handle.set_umma_pair(fic.FIC_UMMA_PAIR_ON)
         handle.set_umma_kind(fic.FIC_UMMA_KIND_I8)
         handle.encode(lena_grey, 8, 61, rgb=False)
         assert not handle.umma_pair_used()

@@ -575,6 +575,20 @@ int main(int argc, char **argv)
             printf("peak kind::%s cta_group::2 M=256 N=128: %.1f TOP/s %s  (TMEM bases of CTAs 0-3: %x %x %x %x)\n", f16 ? "f16" : "i8", t,
                    t < 0 ? err : "", bases[0], bases[1], bases[2], bases[3]);
         }
+        // sustained (power-capped) rates, kind::f16 pairs: A from shared memory against A from tensor memory, 40 back-to-back
+        // launches each (~0.5 s), alternating twice
+        for (int round = 0; round < 2; round++)
+            for (int ts = 0; ts < 2; ts++) {
+                const char *err = "";
+                double best = 0, sum = 0;
+                for (int r = 0; r < 10; r++) {
+                    double t = measure_mma_peak_pair(prop.multiProcessorCount, s, 3, 1, nullptr, &err, ts);
+                    if (t < 0) { printf("sustained: %s\n", err); return 1; }
+                    sum += t;
+                    if (t > best) best = t;
+                }
+                printf("sustained kind::f16 cta_group::2, A from %s: mean-of-best %.1f, best %.1f TFLOP/s\n", ts ? "TMEM" : "smem", sum / 10, best);
+            }
         return 0;
     }
     bool check = !strcmp(argv[1], "check");
