@@ -1096,11 +1096,14 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
     // its own code and bytes.
     const bool one_range = g.B >= 8;
     const bool wide = (g.step & 3) == 0;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < strips; t += (int64_t)gridDim.x * blockDim.x) {
-        const int qy = (int)(t / sw8), s8 = (int)(t - (int64_t)qy * sw8);
+    // 32-bit strip arithmetic (strips = W * H / 16 < 2^31): a 64-bit division per strip was a quarter of the kernel's instructions
+    const uint32_t nstrips = (uint32_t)strips, usw8 = (uint32_t)sw8;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nstrips; t += gridDim.x * blockDim.x) {
+        const uint32_t uqy = t / usw8;
+        const int qy = (int)uqy, s8 = (int)(t - uqy * usw8);
         const int y = 2 * qy, x0 = 8 * s8;
         const int yr = y >> lb, ry = y & bm;
-        const int64_t jr0 = (int64_t)yr * g.rpw + (x0 >> lb);
+        const int jr0 = yr * g.rpw + (x0 >> lb);
         float a0 = 0.0f;
         int off0 = 0;
         if (one_range) {
