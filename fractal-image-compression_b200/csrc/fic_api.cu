@@ -683,7 +683,10 @@ static int decode_core(fic_handle *h, int is_rgb, int W, int H, int B, int wk, c
     CU(cudaMemsetAsync(w.acc, 0, 64 * sizeof(unsigned long long), s));
     int launches = 0;
     int32_t *doff = (int32_t *)(w.dcode + g.NR * S);
-    launches += launch_dequant(d_qcodes ? d_qcodes : w.q, w.dcode, doff, g, 0, nullptr, w.acc, s);
+    // B >= 8, W % 16 == 0: the sweeps keep the decimated plane row-pair interleaved (k_decode_sweep_il) and take the
+    // domain positions packed
+    const int il = decode_sweep_interleaved(g) ? 1 : 0;
+    launches += launch_dequant(d_qcodes ? d_qcodes : w.q, w.dcode, doff, g, 0, nullptr, w.acc, il, s);
     // The start image is the constant 128 (FC:360, FC:1142-1148) and so is its 2x-decimated plane, for every tap rule
     // (FC:970-1007, FC:901-962).  For B >= 8 neither is materialised: the first sweep knows what it would read.
     const bool implicit_start = decode_sweep_has_first(g);
@@ -713,7 +716,7 @@ static int decode_core(fic_handle *h, int is_rgb, int W, int H, int B, int wk, c
             const bool last = it == max_iters - 1;
             const bool replay = big || last || (it == 0 && carry != 0.0f);
             SweepCtl ctl = {w.acc, it, replay ? 0 : 1, fwh};
-            launches += launch_decode_sweep(dcur, img, dnext, w.dcode, doff, g, ctl, replay ? w.perr : nullptr, it == 0 && implicit_start, s);
+            launches += launch_decode_sweep(dcur, img, dnext, w.dcode, doff, g, ctl, replay ? w.perr : nullptr, it == 0 && implicit_start, il, s);
             if (replay) launches += launch_sweep_finish(w.perr, (int64_t)plane, w.acc, it, last, it == 0 ? carry : 0.0f, fwh, replay_bytes ? w.replay : nullptr, s);
             uint8_t *t = dcur; dcur = dnext; dnext = t;
         }
@@ -789,9 +792,9 @@ int fic_collage(fic_handle *h, int is_rgb, const int32_t *argb, int W, int H, in
     launch_unpack(w.argb, w.src, W, H, g.C, s);
     launch_decimate(w.src, w.dec, g, s);                       // FC:275 codebook of the source
     int32_t *doff = (int32_t *)(w.dcode + g.NR * S);
-    launch_dequant(nullptr, w.dcode, doff, g, 1, w.info, w.acc, s);  // FC:273 calculateIndices
+    launch_dequant(nullptr, w.dcode, doff, g, 1, w.info, w.acc, 0, s);  // FC:273 calculateIndices
     launch_fill(w.img, g.C * plane, 0xa0, s);                  // RasterImage.java:19,31
-    launch_decode_sweep(w.dec, w.img, nullptr, w.dcode, doff, g, SweepCtl{nullptr, 0, 0, 0.0f}, nullptr, 0, s);
+    launch_decode_sweep(w.dec, w.img, nullptr, w.dcode, doff, g, SweepCtl{nullptr, 0, 0, 0.0f}, nullptr, 0, 0, s);
     launch_pack_argb(w.img, w.argb, W, H, g.C, s);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h->h_acc, w.acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));

@@ -98,7 +98,7 @@ int launch_search_umma_debug(const Work &w, const Geom &g, int64_t j0, int64_t j
 
 // decoder
 int launch_dequant(const int32_t *d_q, float *d_code, int32_t *d_off, const Geom &g, int unquantised,
-                   const float *d_info, unsigned long long *d_acc, cudaStream_t s);
+                   const float *d_info, unsigned long long *d_acc, int packed, cudaStream_t s);
 int launch_fill(uint8_t *d_planes, size_t bytes, int value, cudaStream_t s);
 // Control block of one decoder sweep.  st == nullptr: a plain sweep (the one-shot collage).  Otherwise st points at
 // the decoder state (fic_kernels.cu, "Decoder state block"): the sweep returns at once when the done flag is set,
@@ -111,10 +111,13 @@ struct SweepCtl {
     float fwh;   // (float)(W*H), FC:413
 };
 // first (only where decode_sweep_has_first(g)): the sweep starts from the constant-128 image (FC:360) and reads nothing
+// interleaved (only where decode_sweep_interleaved(g)): decoder loop over the row-pair interleaved decimated plane
+// (k_decode_sweep_il); d_off then holds packed positions (launch_dequant with packed = 1)
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out,
                         const float *d_code, const int32_t *d_off, const Geom &g,
-                        const SweepCtl &ctl, int32_t *d_perr, int first, cudaStream_t s);
+                        const SweepCtl &ctl, int32_t *d_perr, int first, int interleaved, cudaStream_t s);
 bool decode_sweep_has_first(const Geom &g);
+bool decode_sweep_interleaved(const Geom &g);
 // folds a sweep whose float running sum may have to be replayed in loop order (see k_sweep_finish)
 // d_workspace: sweep_finish_workspace(count) bytes (0 for small images: one warp replays the sum literally)
 int launch_sweep_finish(const int32_t *d_perr, int64_t count, unsigned long long *d_state, int it, int last,

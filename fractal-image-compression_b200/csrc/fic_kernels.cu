@@ -870,9 +870,11 @@ int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_
 // index (FC:853-893 calculateIndices, float division / float remainder as in Java).
 // With `unquantised` the float codes of an encode are used instead (collage, FC:271).
 // acc[1] is set when an index falls outside the pool (the reference would throw).
+// packed != 0 (decoder loop over the row-pair interleaved plane, k_decode_sweep_il): doff[j] is the domain block's
+// position in the decimated plane as (row << 16) | column instead of its byte offset.
 __global__ void k_dequant(const int32_t *__restrict__ q, const float *__restrict__ info_in,
                           float *__restrict__ code, int32_t *__restrict__ doff, Geom g, int unquantised,
-                          unsigned long long *acc)
+                          unsigned long long *acc, int packed)
 {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= g.NR) return;
@@ -906,13 +908,14 @@ __global__ void k_dequant(const int32_t *__restrict__ q, const float *__restrict
     for (int k = 0; k < S; k++) code[S * j + k] = v[k];
     // byte offset of the domain block (FC:394 codebuch[(int) imgData[i][0]]) inside a decimated plane
     const int idx = j_f2i(v[0]);
-    doff[j] = ((idx / g.dpw) * g.step) * g.sw + (idx % g.dpw) * g.step;
+    const int drow = (idx / g.dpw) * g.step, dcol = (idx % g.dpw) * g.step;
+    doff[j] = packed ? (int32_t)(((uint32_t)drow << 16) | (uint32_t)dcol) : drow * g.sw + dcol;
 }
 
 int launch_dequant(const int32_t *d_q, float *d_code, int32_t *d_off, const Geom &g, int unquantised,
-                   const float *d_info, unsigned long long *d_acc, cudaStream_t s)
+                   const float *d_info, unsigned long long *d_acc, int packed, cudaStream_t s)
 {
-    k_dequant<<<(unsigned)((g.NR + 127) / 128), 128, 0, s>>>(d_q, d_info, d_code, d_off, g, unquantised, d_acc);
+    k_dequant<<<(unsigned)((g.NR + 127) / 128), 128, 0, s>>>(d_q, d_info, d_code, d_off, g, unquantised, d_acc, packed);
     return 1;
 }
 
@@ -1204,6 +1207,142 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
     sweep_tail(ctl, local);
 }
 
+// Decoder-loop sweep for B >= 8 and W % 16 == 0 over a ROW-PAIR INTERLEAVED decimated plane.  What a sweep pays for is
+// L2 sectors: on a plain plane the two 8-byte domain row pieces of a strip lie in two different 32-byte
+// sectors (2.4 sectors per strip with the pieces that straddle one), three quarters of which is over-fetch.  A strip
+// always needs the decimated rows 2k and 2k + 1 of one pair (domain rows start at multiples of B/4 >= 2, strips at even
+// rows), and the decoder owns both sides of the plane -- every sweep writes the plane the next one reads.  It
+// therefore keeps the two rows of a pair interleaved at 8-byte granularity,
+//     byte (y, x)  ->  (y >> 1) * 2 sw + (x >> 3) * 16 + (y & 1) * 8 + (x & 7),
+// so that both pieces of a strip sit in one aligned 16-byte group, or in two adjacent groups when the domain column is
+// not a multiple of 8: one or two 16-byte loads (1.4 sectors per strip) instead of eight 2-byte loads, and the writer
+// still stores its four decimated bytes as one aligned word.  Arithmetic, error sums and the perr order are those
+// of k_decode_sweep_v8; dpos[j] = (row << 16) | column of range j's domain block (k_dequant, packed).
+// Used while the image and the two decimated planes stay L2-resident from sweep to sweep (grey up to ~6000^2): there the
+// sweep is bound by L2 sectors and the interleaved plane saves a quarter of them (4096^2: 18.9 -> 15.7 us).  Measured
+// slower than the plain plane on RGB at 4096^2 (75 MB of planes: 72-95 against 40 us per sweep), so RGB and larger grey
+// images keep k_decode_sweep_v8.
+__host__ __device__ inline bool sweep_interleaved(const Geom &g)
+{
+    return g.B >= 8 && g.W % 16 == 0 && g.n_iso == 1 && g.C == 1 && (int64_t)g.W * g.H + 2 * (int64_t)g.sw * g.sh <= ((int64_t)48 << 20);
+}
+
+__device__ __forceinline__ uint32_t decode_row4(float a, float b, uint32_t dom4)
+{
+    // FC:396 / FC:482: (int)(a * domain + b), float multiply then float add, then the clamp
+    const uint32_t v0 = f2u8_rz_sat(__fadd_rn(__fmul_rn(a, (float)(dom4 & 0xffu)), b));
+    const uint32_t v1 = f2u8_rz_sat(__fadd_rn(__fmul_rn(a, (float)((dom4 >> 8) & 0xffu)), b));
+    const uint32_t v2 = f2u8_rz_sat(__fadd_rn(__fmul_rn(a, (float)((dom4 >> 16) & 0xffu)), b));
+    const uint32_t v3 = f2u8_rz_sat(__fadd_rn(__fmul_rn(a, (float)(dom4 >> 24)), b));
+    return v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+}
+
+template <int C, int B, bool PERR, bool FIRST>
+__global__ void __launch_bounds__(256)
+k_decode_sweep_il(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, uint8_t *__restrict__ dec_out,
+                  const float *__restrict__ code, const int32_t *__restrict__ dpos, Geom g, SweepCtl ctl,
+                  int32_t *__restrict__ perr)
+{
+    if (sweep_done(ctl)) return;
+    constexpr int LB = B == 8 ? 3 : 4, BM = B - 1, S = C == 1 ? 3 : 5;
+    const uint32_t W = (uint32_t)g.W, sw = (uint32_t)g.sw, rpw = (uint32_t)g.rpw;
+    const uint32_t sw8 = W >> 3;
+    const size_t planeI = (size_t)g.W * g.H, planeD = (size_t)g.sw * g.sh;
+    const uint32_t tap_x = (uint32_t)g.H - 1u;  // dec_tap4: columns x >= H - 1 take the constant 128 as their fourth tap
+    unsigned long long local = 0;
+    // A warp owns a tile of 16 x 2 strips: lanes 0-15 the strips of decimated row 2 tr, lanes 16-31 the same columns of
+    // row 2 tr + 1 -- the two rows of one interleaved pair, so that the warp's one store of decimated pixels writes whole
+    // 32-byte sectors (half-written sectors cost a read-modify-write once the planes no longer fit in L2).
+    const uint32_t tiles_x = (sw8 + 15u) >> 4, tiles = tiles_x * ((uint32_t)g.H >> 2);
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t wt = blockIdx.x * 8u + (threadIdx.x >> 5); wt < tiles; wt += gridDim.x * 8u) {
+        const uint32_t tr = wt / tiles_x, tx = wt - tr * tiles_x;
+        const uint32_t qy = 2u * tr + (lane >> 4), s8 = 16u * tx + (lane & 15u);
+        if (s8 >= sw8) continue;
+        const uint32_t y = 2u * qy, x0 = 8u * s8;
+        const uint32_t jr = (y >> LB) * rpw + (x0 >> LB);
+        const float a = __ldg(code + S * jr + 1);
+        uint32_t gbase = 0, o = 0;
+        if (!FIRST) {
+            const uint32_t pos = (uint32_t)__ldg(dpos + jr);
+            const uint32_t yd = (pos >> 16) + (y & BM), xd = (pos & 0xffffu) + (x0 & BM);  // yd is even
+            gbase = (yd >> 1) * (2u * sw) + (xd >> 3) * 16u;
+            o = xd & 7u;  // even
+        }
+        uint8_t *pi = img + (size_t)y * W + x0;
+        uint32_t sq = 0;
+        uint32_t e[PERR ? 16 : 1];
+        if (PERR)
+#pragma unroll
+            for (int k = 0; k < 16; k++) e[k] = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const float b = __ldg(code + S * jr + 2 + c);
+            uint2 d0 = make_uint2(0x80808080u, 0x80808080u), d1 = d0, o0 = d0, o1 = d0;
+            if (!FIRST) {
+                const uint8_t *pg = dec_in + c * planeD + gbase;
+                const uint4 ga = __ldg((const uint4 *)pg);
+                uint4 gb = ga;  // not used when the column is a multiple of 8
+                if (o) gb = __ldg((const uint4 *)(pg + 16));
+                // row ry: bytes o .. o + 7 of the words {ga.x, ga.y, gb.x, gb.y}; row ry + 1: of {ga.z, ga.w, gb.z, gb.w}
+                const uint32_t sh = (o & 3u) * 8u;
+                const bool up = o >= 4u;
+                d0.x = __funnelshift_r(up ? ga.y : ga.x, up ? gb.x : ga.y, sh);
+                d0.y = __funnelshift_r(up ? gb.x : ga.y, up ? gb.y : gb.x, sh);
+                d1.x = __funnelshift_r(up ? ga.w : ga.z, up ? gb.z : ga.w, sh);
+                d1.y = __funnelshift_r(up ? gb.z : ga.w, up ? gb.w : gb.z, sh);
+                o0 = *(const uint2 *)(pi + c * planeI);
+                o1 = *(const uint2 *)(pi + c * planeI + W);
+            }
+            uint2 n0, n1;
+            n0.x = decode_row4(a, b, d0.x);
+            if (FIRST) {  // one domain value: every pixel of the strip is the same
+                n0.y = n0.x; n1 = n0;
+            } else {
+                n0.y = decode_row4(a, b, d0.y);
+                n1.x = decode_row4(a, b, d1.x);
+                n1.y = decode_row4(a, b, d1.y);
+            }
+            *(uint2 *)(pi + c * planeI) = n0;
+            *(uint2 *)(pi + c * planeI + W) = n1;
+            const uint32_t ad[4] = {__vabsdiffu4(o0.x, n0.x), __vabsdiffu4(o0.y, n0.y), __vabsdiffu4(o1.x, n1.x), __vabsdiffu4(o1.y, n1.y)};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                sq = __dp4a(ad[k], ad[k], sq);  // FC:407 / FC:493: sum of the squared pixel changes
+                if (PERR)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t d = (ad[k] >> (8 * i)) & 0xffu;
+                        e[4 * k + i] += d * d;
+                    }
+            }
+            if (dec_out) {
+                // 2x decimation of the new pixels (dec_tap4): quads (x0 + 2 qd, y), bytes {p00, p10, p01, p11}
+                const uint32_t quad[4] = {__byte_perm(n0.x, n1.x, 0x5410), __byte_perm(n0.x, n1.x, 0x7632),
+                                          __byte_perm(n0.y, n1.y, 0x5410), __byte_perm(n0.y, n1.y, 0x7632)};
+                uint32_t nd = 0;
+#pragma unroll
+                for (int qd = 0; qd < 4; qd++) {
+                    const bool edge = x0 + 2u * qd >= tap_x;
+                    const uint32_t wts = edge ? 0x00010101u : (C == 3 ? 0x00020101u : 0x01010101u);
+                    nd |= ((__dp4a(quad[qd], wts, edge ? 128u : 0u) >> 2) & 0xffu) << (8 * qd);
+                }
+                // decimated row qy, columns 4 s8 .. 4 s8 + 3, in the interleaved plane
+                *(uint32_t *)(dec_out + c * planeD + (size_t)(qy >> 1) * (2u * sw) + (s8 >> 1) * 16u + (qy & 1u) * 8u + (s8 & 1u) * 4u) = nd;
+            }
+        }
+        local += sq;
+        if (PERR) {  // per-pixel squared change, summed over the channels, in the reference's loop order
+            int4 *pe = (int4 *)(perr + (size_t)jr * (B * B) + (y & BM) * B + (x0 & BM));
+            pe[0] = make_int4((int)e[0], (int)e[1], (int)e[2], (int)e[3]);
+            pe[1] = make_int4((int)e[4], (int)e[5], (int)e[6], (int)e[7]);
+            pe[B / 4] = make_int4((int)e[8], (int)e[9], (int)e[10], (int)e[11]);
+            pe[B / 4 + 1] = make_int4((int)e[12], (int)e[13], (int)e[14], (int)e[15]);
+        }
+    }
+    sweep_tail(ctl, local);
+}
+
 // The sweeps are grid-stride over exactly one wave of resident CTAs (SMs x occupancy of the kernel): a second, partly
 // filled wave cost a third of the sweep at 4096^2 (1184 CTAs on 740 slots, profiles/README.md).
 template <class K>
@@ -1217,12 +1356,38 @@ static int64_t sweep_wave_ctas(K kernel)
 }
 
 bool decode_sweep_has_first(const Geom &g) { return g.W % 8 == 0 && g.n_iso == 1 && g.B >= 8; }
+bool decode_sweep_interleaved(const Geom &g) { return sweep_interleaved(g); }
+
+template <int C, int B>
+static void launch_sweep_il(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out, const float *d_code, const int32_t *d_pos,
+                            const Geom &g, const SweepCtl &ctl, int32_t *d_perr, int first, cudaStream_t s)
+{
+    static const int64_t wave[4] = {sweep_wave_ctas(k_decode_sweep_il<C, B, false, false>), sweep_wave_ctas(k_decode_sweep_il<C, B, false, true>),
+                                    sweep_wave_ctas(k_decode_sweep_il<C, B, true, false>), sweep_wave_ctas(k_decode_sweep_il<C, B, true, true>)};
+    const int64_t tiles = (int64_t)((g.W / 8 + 15) / 16) * (g.H / 4), need = (tiles + 7) / 8;  // one warp per 16 x 2 strips
+    const int v = (d_perr ? 2 : 0) + (first ? 1 : 0);
+    const unsigned grid = (unsigned)(need < wave[v] ? need : wave[v]);
+    switch (v) {
+    case 0: k_decode_sweep_il<C, B, false, false><<<grid, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_pos, g, ctl, d_perr); break;
+    case 1: k_decode_sweep_il<C, B, false, true><<<grid, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_pos, g, ctl, d_perr); break;
+    case 2: k_decode_sweep_il<C, B, true, false><<<grid, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_pos, g, ctl, d_perr); break;
+    default: k_decode_sweep_il<C, B, true, true><<<grid, 256, 0, s>>>(d_dec_in, d_img, d_dec_out, d_code, d_pos, g, ctl, d_perr); break;
+    }
+}
 
 // first != 0 (only where decode_sweep_has_first): the sweep starts from the constant-128 image and reads neither
 // d_img nor d_dec_in.
+// interleaved != 0 (only where decode_sweep_interleaved): the decimated planes are row-pair interleaved and d_off holds
+// packed positions (launch_dequant with packed = 1).
 int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_out, const float *d_code,
-                        const int32_t *d_off, const Geom &g, const SweepCtl &ctl, int32_t *d_perr, int first, cudaStream_t s)
+                        const int32_t *d_off, const Geom &g, const SweepCtl &ctl, int32_t *d_perr, int first, int interleaved,
+                        cudaStream_t s)
 {
+    if (interleaved && sweep_interleaved(g)) {
+        if (g.B == 8) launch_sweep_il<1, 8>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr, first, s);  // grey only
+        else launch_sweep_il<1, 16>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr, first, s);
+        return 1;
+    }
     if (first && decode_sweep_has_first(g)) {
         static const int64_t wave_f_1 = sweep_wave_ctas(k_decode_sweep_v8<1, true>), wave_f_3 = sweep_wave_ctas(k_decode_sweep_v8<3, true>);
         const int64_t strips = (int64_t)(g.W / 8) * (g.H / 2), need = (strips + 255) / 256;
