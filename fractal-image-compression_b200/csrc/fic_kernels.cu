@@ -1218,13 +1218,13 @@ k_decode_sweep_v8(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
 // not a multiple of 8: one or two 16-byte loads (1.4 sectors per strip) instead of eight 2-byte loads, and the writer
 // still stores its four decimated bytes as one aligned word.  Arithmetic, error sums and the perr order are those
 // of k_decode_sweep_v8; dpos[j] = (row << 16) | column of range j's domain block (k_dequant, packed).
-// Used while the image and the two decimated planes stay L2-resident from sweep to sweep (grey up to ~6000^2): there the
-// sweep is bound by L2 sectors and the interleaved plane saves a quarter of them (4096^2: 18.9 -> 15.7 us).  Measured
-// slower than the plain plane on RGB at 4096^2 (75 MB of planes: 72-95 against 40 us per sweep), so RGB and larger grey
-// images keep k_decode_sweep_v8.
+// Used while the image and the two decimated planes stay L2-resident from sweep to sweep (48 MB: grey up to ~5800^2,
+// RGB up to ~3300^2): there the sweep is bound by L2 sectors and the interleaved plane saves a quarter of them (grey
+// 4096^2: 18.9 -> 15.7 us per sweep; RGB 3072^2: 26.1 -> 22.5).  Beyond L2 it measured slower than the plain plane
+// (RGB at 4096^2, 75 MB of planes: 72-95 against 40 us per sweep), so larger images keep k_decode_sweep_v8.
 __host__ __device__ inline bool sweep_interleaved(const Geom &g)
 {
-    return g.B >= 8 && g.W % 16 == 0 && g.n_iso == 1 && g.C == 1 && (int64_t)g.W * g.H + 2 * (int64_t)g.sw * g.sh <= ((int64_t)48 << 20);
+    return g.B >= 8 && g.W % 16 == 0 && g.n_iso == 1 && g.C * ((int64_t)g.W * g.H + 2 * (int64_t)g.sw * g.sh) <= ((int64_t)48 << 20);
 }
 
 __device__ __forceinline__ uint32_t decode_row4(float a, float b, uint32_t dom4)
@@ -1384,8 +1384,13 @@ int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_
                         cudaStream_t s)
 {
     if (interleaved && sweep_interleaved(g)) {
-        if (g.B == 8) launch_sweep_il<1, 8>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr, first, s);  // grey only
-        else launch_sweep_il<1, 16>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr, first, s);
+        if (g.B == 8) {
+            if (g.C == 1) launch_sweep_il<1, 8>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr, first, s);
+            else launch_sweep_il<3, 8>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr, first, s);
+        } else {
+            if (g.C == 1) launch_sweep_il<1, 16>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr, first, s);
+            else launch_sweep_il<3, 16>(d_dec_in, d_img, d_dec_out, d_code, d_off, g, ctl, d_perr, first, s);
+        }
         return 1;
     }
     if (first && decode_sweep_has_first(g)) {
