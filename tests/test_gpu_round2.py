@@ -210,7 +210,8 @@ def test_decode_above_2_24_pixels(fic, handle, oracle):
 @pytest.mark.parametrize("W,H,B,wk,rgb", [
     (264, 136, 8, 5, False),    # W % 16 == 8: decimated rows start at odd multiples of 4; landscape: the FC:993 tap
     (272, 144, 8, 5, False),    # W % 16 == 0, grey: the decoder loop over the row-pair interleaved plane; landscape
-    (136, 264, 8, 4, True),     # portrait RGB
+    (136, 264, 8, 4, True),     # portrait RGB, plain plane
+    (144, 272, 8, 4, True),     # portrait RGB, W % 16 == 0: interleaved plane
     (256, 256, 16, 4, False),   # blockgroesse 16 (interleaved plane: domain columns are multiples of 4)
     (272, 144, 16, 3, True),
     (64, 64, 8, 13, False),     # whole pool as the window
