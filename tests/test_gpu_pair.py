@@ -96,10 +96,11 @@ def test_pair_auto_policy(fic, handle, lena_grey):
     assert not handle.umma_pair_used()
 
 
-def test_pair_range_slices_compose(fic, handle):
+@pytest.mark.parametrize("W,B", [(1024, 8), (2048, 16)])
+def test_pair_range_slices_compose(fic, handle, W, B):
     """Row shards (what every rank of a multi-GPU encode runs) through the pair kernel: slices whose row counts are
-    not multiples of the pair's 1024 rows compose to the whole-image result of the single-CTA kernel."""
-    W, B = 1024, 8
+    not multiples of the pair's 1024 rows compose to the whole-image result of the single-CTA kernel (B = 16: the
+    K-split pair kernel)."""
     img = to_argb_grey(_content("structured", W, 9))
     rpw = W // B
     wk = 2 * rpw - 3
@@ -114,9 +115,10 @@ def test_pair_range_slices_compose(fic, handle):
     assert (q == q0).all() and float_bits_equal(info, info0)
 
 
-def test_pair_equals_single_at_2048(fic, handle):
-    """The two kernels on a 2048^2 image (65 536 rows, 1.1e9 evaluations per super-block pair): identical codes."""
-    W, B = 2048, 8
+@pytest.mark.parametrize("B", [8, 16])
+def test_pair_equals_single_at_2048(fic, handle, B):
+    """The two kernels on a 2048^2 image (65 536 rows, 1.1e9 evaluations per super-block pair at B = 8): identical codes."""
+    W = 2048
     img = fic.synth.grey_to_argb(fic.synth.structured(W, W, 4))
     wk = 2 * (W // B) - 3
     (info_p, q_p), used_p = _encode(fic, handle, img, B, wk, fic.FIC_UMMA_PAIR_ON)
