@@ -686,6 +686,33 @@ static int decode_core(fic_handle *h, int is_rgb, int W, int H, int B, int wk, c
     // B >= 8, W % 16 == 0: the sweeps keep the decimated plane row-pair interleaved (k_decode_sweep_il) and take the
     // domain positions packed
     const int il = decode_sweep_interleaved(g) ? 1 : 0;
+    const uint32_t *hst = (const uint32_t *)h->h_acc;  // host copy of the state block as 32-bit words: [5..7] = done, iters, avg; [9] = bail
+    // Small images (the reference's own sizes): the whole decode in ONE cooperative launch (k_decode_small) -- unless its
+    // avgError would need the float sum replayed (word 9 of the state: bail), in which case the decode is repeated below.
+    if (il && plane <= ((size_t)1 << 20) &&
+        launch_decode_small(d_qcodes ? d_qcodes : w.q, w.dcode, doff, img, w.dec, w.dec2, argb_out ? w.argb : nullptr, g, w.acc, max_iters,
+                            carry, fwh, s)) {
+        launches++;
+        CU(cudaMemcpyAsync(h->h_acc, w.acc, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        // the output is copied without waiting for the verdict (<= 4 MB); a bailed decode overwrites it below
+        if (argb_out) CU(cudaMemcpyAsync(argb_out, w.argb, sizeof(int32_t) * plane, cudaMemcpyDeviceToHost, s));
+        else if (planes_out) CU(cudaMemcpyAsync(planes_out, img, g.C * plane, cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(h->ev[5], s));
+        CU(cudaStreamSynchronize(s));
+        if (h->h_acc[1]) return set_err(h, FIC_E_STREAM, "a code indexes outside the domain pool (the reference would throw ArrayIndexOutOfBounds)");
+        if (!hst[9]) {
+            CU(cudaGetLastError());
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]) == cudaSuccess) h->tm.total_ms = ms;
+            h->tm.launches = launches;
+            float avg;
+            memcpy(&avg, &hst[7], sizeof avg);
+            if (avg_error) *avg_error = avg;
+            if (iterations) *iterations = (int)hst[6];
+            return FIC_OK;
+        }
+        CU(cudaMemsetAsync(w.acc, 0, 64 * sizeof(unsigned long long), s));
+    }
     launches += launch_dequant(d_qcodes ? d_qcodes : w.q, w.dcode, doff, g, 0, nullptr, w.acc, il, s);
     // The start image is the constant 128 (FC:360, FC:1142-1148) and so is its 2x-decimated plane, for every tap rule
     // (FC:970-1007, FC:901-962).  For B >= 8 neither is materialised: the first sweep knows what it would read.
@@ -695,7 +722,6 @@ static int decode_core(fic_handle *h, int is_rgb, int W, int H, int B, int wk, c
         CU(cudaMemsetAsync(w.dec, 128, (size_t)g.C * g.sw * g.sh, s));
     }
     uint8_t *dcur = w.dec, *dnext = w.dec2;
-    const uint32_t *hst = (const uint32_t *)h->h_acc;  // host copy of the state block as 32-bit words: [5..7] = done, iters, avg
     // Small images: the output copy is enqueued behind every batch, so that a decode that converges within the batch
     // (the usual case) costs one host synchronisation in all; a later batch simply copies again.
     const bool speculative_out = !d_planes_out && plane * (argb_out ? 4 : g.C) <= ((size_t)4 << 20);
@@ -711,7 +737,10 @@ static int decode_core(fic_handle *h, int is_rgb, int W, int H, int B, int wk, c
     int it = 0;
     bool out_done = false;
     while (it < max_iters) {
-        const int batch_end = it + 8 < max_iters ? it + 8 : max_iters;  // a skipped sweep still costs a launch (~1 us)
+        // a skipped sweep still costs a launch (~1.5 us), a second batch a host round trip (~40 us): grey decodes converge
+        // in 5-9 sweeps, the reference's RGB quantisation (FC:250-254) needs 13-22
+        const int batch = (g.C == 3 && speculative_out) ? 16 : 8;
+        const int batch_end = it + batch < max_iters ? it + batch : max_iters;
         for (; it < batch_end; it++) {
             const bool last = it == max_iters - 1;
             const bool replay = big || last || (it == 0 && carry != 0.0f);

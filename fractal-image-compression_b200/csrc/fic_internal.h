@@ -117,6 +117,13 @@ int launch_decode_sweep(const uint8_t *d_dec_in, uint8_t *d_img, uint8_t *d_dec_
                         const float *d_code, const int32_t *d_off, const Geom &g,
                         const SweepCtl &ctl, int32_t *d_perr, int first, int interleaved, cudaStream_t s);
 bool decode_sweep_has_first(const Geom &g);
+// Small images (<= 2^20 pixels, interleaved-plane geometry): dequantisation, every sweep, the convergence rule and the
+// ARGB conversion (d_argb may be null) in ONE cooperative launch.  Returns 1 if launched: the state block (zero on
+// entry) then holds done / sweeps / avgError as after the per-sweep kernels, or word 9 != 0 = "bailed: repeat through the
+// per-sweep kernels" (a float avgError sum that would need a replay).  0: not taken (geometry, device).
+int launch_decode_small(const int32_t *d_q, float *d_code, int32_t *d_pos, uint8_t *d_img, uint8_t *d_dec_a, uint8_t *d_dec_b,
+                        int32_t *d_argb, const Geom &g, unsigned long long *d_state, int max_iters, float carry, float fwh,
+                        cudaStream_t s);
 bool decode_sweep_interleaved(const Geom &g);
 // folds a sweep whose float running sum may have to be replayed in loop order (see k_sweep_finish)
 // d_workspace: sweep_finish_workspace(count) bytes (0 for small images: one warp replays the sum literally)

@@ -872,12 +872,10 @@ int launch_solve(const Work &w, const Geom &g, int64_t j0, int64_t j1, float *d_
 // acc[1] is set when an index falls outside the pool (the reference would throw).
 // packed != 0 (decoder loop over the row-pair interleaved plane, k_decode_sweep_il): doff[j] is the domain block's
 // position in the decimated plane as (row << 16) | column instead of its byte offset.
-__global__ void k_dequant(const int32_t *__restrict__ q, const float *__restrict__ info_in,
-                          float *__restrict__ code, int32_t *__restrict__ doff, Geom g, int unquantised,
-                          unsigned long long *acc, int packed)
+__device__ __forceinline__ void dequant_one(int64_t j, const int32_t *__restrict__ q, const float *__restrict__ info_in,
+                                            float *__restrict__ code, int32_t *__restrict__ doff, const Geom &g, int unquantised,
+                                            unsigned long long *acc, int packed)
 {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= g.NR) return;
     int S = code_stride(g);
     float v[5];
     if (unquantised) {
@@ -906,10 +904,20 @@ __global__ void k_dequant(const int32_t *__restrict__ q, const float *__restrict
     }
     v[0] = (float)(int)result;  // FC:888 stores the index back into the float table
     for (int k = 0; k < S; k++) code[S * j + k] = v[k];
-    // byte offset of the domain block (FC:394 codebuch[(int) imgData[i][0]]) inside a decimated plane
+    // position of the domain block (FC:394 codebuch[(int) imgData[i][0]]) inside a decimated plane: its byte offset, or
+    // (packed) row and column
     const int idx = j_f2i(v[0]);
     const int drow = (idx / g.dpw) * g.step, dcol = (idx % g.dpw) * g.step;
     doff[j] = packed ? (int32_t)(((uint32_t)drow << 16) | (uint32_t)dcol) : drow * g.sw + dcol;
+}
+
+__global__ void k_dequant(const int32_t *__restrict__ q, const float *__restrict__ info_in,
+                          float *__restrict__ code, int32_t *__restrict__ doff, Geom g, int unquantised,
+                          unsigned long long *acc, int packed)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.NR) return;
+    dequant_one(j, q, info_in, code, doff, g, unquantised, acc, packed);
 }
 
 int launch_dequant(const int32_t *d_q, float *d_code, int32_t *d_off, const Geom &g, int unquantised,
@@ -1237,13 +1245,21 @@ __device__ __forceinline__ uint32_t decode_row4(float a, float b, uint32_t dom4)
     return v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
 }
 
-template <int C, int B, bool PERR, bool FIRST>
-__global__ void __launch_bounds__(256)
-k_decode_sweep_il(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, uint8_t *__restrict__ dec_out,
-                  const float *__restrict__ code, const int32_t *__restrict__ dpos, Geom g, SweepCtl ctl,
-                  int32_t *__restrict__ perr)
+// The sweep itself (all strips this CTA owns); returns the thread's sum of squared pixel changes.  NC: the codes and
+// the plane read are constant for the lifetime of the kernel (one launch per sweep) and go through the read-only path;
+// the one-launch decoder (k_decode_small) rewrites them between its barriers and reads them with ordinary loads.
+template <bool NC, class T>
+__device__ __forceinline__ T sweep_ld(const T *p)
 {
-    if (sweep_done(ctl)) return;
+    if (NC) return __ldg(p);
+    return *p;
+}
+
+template <int C, int B, bool PERR, bool FIRST, bool NC = true>
+__device__ __forceinline__ unsigned long long sweep_il_body(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
+                                                            uint8_t *__restrict__ dec_out, const float *__restrict__ code,
+                                                            const int32_t *__restrict__ dpos, const Geom &g, int32_t *__restrict__ perr)
+{
     constexpr int LB = B == 8 ? 3 : 4, BM = B - 1, S = C == 1 ? 3 : 5;
     const uint32_t W = (uint32_t)g.W, sw = (uint32_t)g.sw, rpw = (uint32_t)g.rpw;
     const uint32_t sw8 = W >> 3;
@@ -1261,10 +1277,10 @@ k_decode_sweep_il(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
         if (s8 >= sw8) continue;
         const uint32_t y = 2u * qy, x0 = 8u * s8;
         const uint32_t jr = (y >> LB) * rpw + (x0 >> LB);
-        const float a = __ldg(code + S * jr + 1);
+        const float a = sweep_ld<NC>(code + S * jr + 1);
         uint32_t gbase = 0, o = 0;
         if (!FIRST) {
-            const uint32_t pos = (uint32_t)__ldg(dpos + jr);
+            const uint32_t pos = (uint32_t)sweep_ld<NC>(dpos + jr);
             const uint32_t yd = (pos >> 16) + (y & BM), xd = (pos & 0xffffu) + (x0 & BM);  // yd is even
             gbase = (yd >> 1) * (2u * sw) + (xd >> 3) * 16u;
             o = xd & 7u;  // even
@@ -1277,13 +1293,13 @@ k_decode_sweep_il(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
             for (int k = 0; k < 16; k++) e[k] = 0;
 #pragma unroll
         for (int c = 0; c < C; c++) {
-            const float b = __ldg(code + S * jr + 2 + c);
+            const float b = sweep_ld<NC>(code + S * jr + 2 + c);
             uint2 d0 = make_uint2(0x80808080u, 0x80808080u), d1 = d0, o0 = d0, o1 = d0;
             if (!FIRST) {
                 const uint8_t *pg = dec_in + c * planeD + gbase;
-                const uint4 ga = __ldg((const uint4 *)pg);
+                const uint4 ga = sweep_ld<NC>((const uint4 *)pg);
                 uint4 gb = ga;  // not used when the column is a multiple of 8
-                if (o) gb = __ldg((const uint4 *)(pg + 16));
+                if (o) gb = sweep_ld<NC>((const uint4 *)(pg + 16));
                 // row ry: bytes o .. o + 7 of the words {ga.x, ga.y, gb.x, gb.y}; row ry + 1: of {ga.z, ga.w, gb.z, gb.w}
                 const uint32_t sh = (o & 3u) * 8u;
                 const bool up = o >= 4u;
@@ -1340,7 +1356,114 @@ k_decode_sweep_il(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img,
             pe[B / 4 + 1] = make_int4((int)e[12], (int)e[13], (int)e[14], (int)e[15]);
         }
     }
-    sweep_tail(ctl, local);
+    return local;
+}
+
+template <int C, int B, bool PERR, bool FIRST>
+__global__ void __launch_bounds__(256)
+k_decode_sweep_il(const uint8_t *__restrict__ dec_in, uint8_t *__restrict__ img, uint8_t *__restrict__ dec_out,
+                  const float *__restrict__ code, const int32_t *__restrict__ dpos, Geom g, SweepCtl ctl,
+                  int32_t *__restrict__ perr)
+{
+    if (sweep_done(ctl)) return;
+    sweep_tail(ctl, sweep_il_body<C, B, PERR, FIRST>(dec_in, img, dec_out, code, dpos, g, perr));
+}
+
+// ---- small images: the whole decode in ONE cooperative launch ------------------------------------------------------
+// The reference's default setting (256^2, B = 8) is launch bound on the GPU: code dequantisation, five to nine sweeps of
+// ~2 us each, the output conversion -- a dozen launches of ~2.5 us each.  k_decode_small runs all of it in one
+// cooperative kernel (every CTA resident; a grid barrier on a counter in the state block between the phases): dequantise,
+// then sweep / barrier / fold (one thread decides FC:413-417) / barrier until the sweep converges, then write the ARGB
+// ints.  It takes the cases whose avgError needs no replay of the float sum: the exact total is below 2^24 and nothing
+// is carried in (the float sum IS that integer), or the total is so large that the sweep certainly did not converge
+// (skip_from, see k_replay_*) and is not the last allowed one.  Anything else -- a last sweep that has not converged, a
+// carried-in avgError on a sweep that might converge -- sets the bail word and the host repeats the decode through the
+// per-sweep kernels.
+enum { ST_BARRIER = 8, ST_BAIL = 9 };  // further 32-bit words of the state block
+
+__device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t &epoch)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*(volatile uint32_t *)counter < epoch) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int C, int B>
+__global__ void __launch_bounds__(256)
+k_decode_small(const int32_t *__restrict__ q, float *__restrict__ code, int32_t *__restrict__ dpos, uint8_t *__restrict__ img,
+               uint8_t *__restrict__ dec_a, uint8_t *__restrict__ dec_b, int32_t *__restrict__ argb_out, Geom g,
+               unsigned long long *st, int max_iters, float carry, float fwh, unsigned long long skip_from)
+{
+    __shared__ unsigned long long s_part[8];
+    uint32_t *w = (uint32_t *)st;
+    uint32_t epoch = 0;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < g.NR; j += (int64_t)gridDim.x * 256)
+        dequant_one(j, q, nullptr, code, dpos, g, 0, st, 1);
+    grid_barrier(w + ST_BARRIER, epoch);
+    uint8_t *din = dec_a, *dout = dec_b;
+    bool ok = false;
+    for (int it = 0; it < max_iters; it++) {
+        unsigned long long local = it == 0 ? sweep_il_body<C, B, false, true, false>(din, img, dout, code, dpos, g, nullptr)
+                                           : sweep_il_body<C, B, false, false, false>(din, img, dout, code, dpos, g, nullptr);
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long tot = 0;
+            for (int wv = 0; wv < 8; wv++) tot += s_part[wv];
+            if (tot) atomicAdd(st, tot);
+        }
+        grid_barrier(w + ST_BARRIER, epoch);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const unsigned long long S = atomicExch(st, 0ull);
+            const bool last = it == max_iters - 1;
+            const float c0 = it == 0 ? carry : 0.0f;
+            if (c0 == 0.0f && S < (1ull << 24)) {  // the float sum is the exact integer
+                const float avg = __fdiv_rn((float)S, fwh);  // FC:413
+                w[ST_ITERS] = (uint32_t)(it + 1);
+                if (avg < 1.0f) {  // FC:414
+                    w[ST_AVG] = __float_as_uint(avg);
+                    w[ST_DONE] = 1u;
+                } else {
+                    w[ST_AVG] = last ? __float_as_uint(avg) : 0u;  // FC:416-417
+                }
+            } else if (!last && c0 >= 0.0f && S >= skip_from) {  // certainly not converged; the value is discarded
+                w[ST_ITERS] = (uint32_t)(it + 1);
+                w[ST_AVG] = 0u;
+            } else {
+                w[ST_BAIL] = 1u;
+            }
+            __threadfence();
+        }
+        grid_barrier(w + ST_BARRIER, epoch);
+        const uint32_t done = ((volatile uint32_t *)w)[ST_DONE], bail = ((volatile uint32_t *)w)[ST_BAIL];
+        if (bail) return;
+        if (done || it == max_iters - 1) { ok = true; break; }
+        uint8_t *t = din; din = dout; dout = t;
+    }
+    if (ok && argb_out) {
+        const int64_t quads = (int64_t)g.W * g.H / 4;
+        const uchar4 *planes = (const uchar4 *)img;
+        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < quads; i += (int64_t)gridDim.x * 256) {
+            uchar4 r = planes[i], gg = r, b = r;
+            if (C == 3) {
+                gg = planes[quads + i];
+                b = planes[2 * quads + i];
+            }
+            int4 o;
+            o.x = (int)(0xff000000u | (r.x << 16) | (gg.x << 8) | b.x);
+            o.y = (int)(0xff000000u | (r.y << 16) | (gg.y << 8) | b.y);
+            o.z = (int)(0xff000000u | (r.z << 16) | (gg.z << 8) | b.z);
+            o.w = (int)(0xff000000u | (r.w << 16) | (gg.w << 8) | b.w);
+            ((int4 *)argb_out)[i] = o;
+        }
+    }
 }
 
 // The sweeps are grid-stride over exactly one wave of resident CTAs (SMs x occupancy of the kernel): a second, partly
@@ -1353,6 +1476,55 @@ static int64_t sweep_wave_ctas(K kernel)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     return (int64_t)sms * per_sm;
+}
+
+// Small images: the whole decode in one cooperative launch (k_decode_small).  Returns 1 if the kernel was launched (the
+// state block then tells whether it finished or bailed), 0 if this geometry / device does not take the fused path.
+// The state block must be zero.  skip_from as in launch_sweep_finish.
+template <int C, int B>
+static int launch_small_t(const int32_t *d_q, float *d_code, int32_t *d_pos, uint8_t *d_img, uint8_t *d_dec_a, uint8_t *d_dec_b,
+                          int32_t *d_argb, const Geom &g, unsigned long long *d_state, int max_iters, float carry, float fwh,
+                          unsigned long long skip_from, cudaStream_t s)
+{
+    static int coop = -1, per_sm = 0, sms = 0;
+    if (coop < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_small<C, B>, 256, 0) != cudaSuccess) per_sm = 0;
+        cudaGetLastError();
+    }
+    if (coop <= 0 || per_sm < 1) return 0;
+    const int64_t tiles = (int64_t)((g.W / 8 + 15) / 16) * (g.H / 4);
+    int64_t grid = (tiles + 7) / 8;
+    if (grid > (int64_t)sms * per_sm) grid = (int64_t)sms * per_sm;
+    Geom gg = g;
+    void *args[] = {(void *)&d_q, (void *)&d_code, (void *)&d_pos, (void *)&d_img, (void *)&d_dec_a, (void *)&d_dec_b, (void *)&d_argb,
+                    (void *)&gg, (void *)&d_state, (void *)&max_iters, (void *)&carry, (void *)&fwh, (void *)&skip_from};
+    if (cudaLaunchCooperativeKernel((const void *)k_decode_small<C, B>, dim3((unsigned)grid), dim3(256), args, 0, s) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return 1;
+}
+
+int launch_decode_small(const int32_t *d_q, float *d_code, int32_t *d_pos, uint8_t *d_img, uint8_t *d_dec_a, uint8_t *d_dec_b,
+                        int32_t *d_argb, const Geom &g, unsigned long long *d_state, int max_iters, float carry, float fwh,
+                        cudaStream_t s)
+{
+    if (!sweep_interleaved(g) || (int64_t)g.W * g.H > ((int64_t)1 << 20)) return 0;
+    unsigned long long skip_from = ~0ull;
+    if (fwh >= 1.0f) {
+        int ex = 0;
+        frexpf(fwh, &ex);
+        skip_from = (unsigned long long)((double)fwh + (double)g.W * g.H * ldexp(1.0, ex - 25)) + 2ull;
+    }
+    if (g.B == 8)
+        return g.C == 1 ? launch_small_t<1, 8>(d_q, d_code, d_pos, d_img, d_dec_a, d_dec_b, d_argb, g, d_state, max_iters, carry, fwh, skip_from, s)
+                        : launch_small_t<3, 8>(d_q, d_code, d_pos, d_img, d_dec_a, d_dec_b, d_argb, g, d_state, max_iters, carry, fwh, skip_from, s);
+    return g.C == 1 ? launch_small_t<1, 16>(d_q, d_code, d_pos, d_img, d_dec_a, d_dec_b, d_argb, g, d_state, max_iters, carry, fwh, skip_from, s)
+                    : launch_small_t<3, 16>(d_q, d_code, d_pos, d_img, d_dec_a, d_dec_b, d_argb, g, d_state, max_iters, carry, fwh, skip_from, s);
 }
 
 bool decode_sweep_has_first(const Geom &g) { return g.W % 8 == 0 && g.n_iso == 1 && g.B >= 8; }
