@@ -491,10 +491,28 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
         // 127 + 127 hold, while -255 = -128 - 127 fits.  Such a row is stored negated: the accumulator becomes
         // -kov, and only |kov| is ever used (the refine step recomputes kov from the raw pixels).
         const int sgn = (!F16 && dmean == 0) ? -1 : 1;
+        // B = 8, decimated rows of a multiple of 8 bytes: a block row is 8 bytes at an even column -- the aligned 8-byte
+        // word that holds its start and, unless the column is a multiple of 8, the next one (inside the row: see below),
+        // instead of four 2-byte loads.  The gather is what this kernel pays for: every lane reads another domain.
+        const bool wide8 = B == 8 && (g.sw & 7) == 0;
+        const int col8 = (gx * g.step) & 7;  // the next aligned word ends at most at the row's end when col8 != 0
 #pragma unroll
         for (int c = 0; c < PCH; c++) {
             int dv[16];
             uint32_t raw[4];
+            if (wide8) {
+#pragma unroll
+                for (int r2 = 0; r2 < 2; r2++) {  // 16 pixels = two block rows
+                    const uint8_t *q = p + (int64_t)(c * 2 + r2) * g.sw - col8;
+                    const uint2 lo = __ldg((const uint2 *)q);
+                    uint2 hi = lo;
+                    if (col8) hi = __ldg((const uint2 *)(q + 8));
+                    const uint32_t sh = (uint32_t)(col8 & 3) * 8u;
+                    const bool up = col8 >= 4;
+                    raw[2 * r2] = __funnelshift_r(up ? lo.y : lo.x, up ? hi.x : lo.y, sh);
+                    raw[2 * r2 + 1] = __funnelshift_r(up ? hi.x : lo.y, up ? hi.y : hi.x, sh);
+                }
+            }
 #pragma unroll
             for (int w = 0; w < 4; w++) {
                 // pixels k .. k + 3 of the block share a row; a block row starts at a multiple of B / 4 bytes of the
@@ -502,8 +520,9 @@ k_umma_pack_domains(const uint8_t *__restrict__ dec, const int32_t *__restrict__
                 const int k = c * 16 + w * 4;
                 const uint8_t *q = p + (int64_t)(k / B) * g.sw + (k % B);
                 if (B == 16) raw[w] = __ldg((const uint32_t *)q);
-                else if (B == 8) raw[w] = (uint32_t)__ldg((const uint16_t *)q) | ((uint32_t)__ldg((const uint16_t *)(q + 2)) << 16);
-                else raw[w] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) | ((uint32_t)__ldg(q + 3) << 24);
+                else if (B == 8) {
+                    if (!wide8) raw[w] = (uint32_t)__ldg((const uint16_t *)q) | ((uint32_t)__ldg((const uint16_t *)(q + 2)) << 16);
+                } else raw[w] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) | ((uint32_t)__ldg(q + 3) << 24);
 #pragma unroll
                 for (int e = 0; e < 4; e++) dv[w * 4 + e] = sgn * ((int)((raw[w] >> (8 * e)) & 0xffu) - dmean);
             }
